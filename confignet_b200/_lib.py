@@ -1,0 +1,104 @@
+"""ctypes binding of libconfignet_b200.so (the C ABI declared in include/confignet_b200.h).
+
+The product path has no fallback: if the shared library is missing, importing this module raises;
+if a call fails, ``CnError`` carries the library's message.  Build with ``__graft_entry__.build()``
+(nvcc -gencode arch=compute_100a,code=sm_100a).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libconfignet_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+
+class CnError(RuntimeError):
+    pass
+
+
+class ConvDesc(ctypes.Structure):
+    """cn_conv_desc (include/confignet_b200.h)."""
+    _fields_ = [("nd", ctypes.c_int), ("batch", ctypes.c_int), ("in_dims", ctypes.c_int * 3),
+                ("cin", ctypes.c_int), ("cout", ctypes.c_int), ("ksize", ctypes.c_int * 3),
+                ("stride", ctypes.c_int), ("upsample", ctypes.c_int)]
+
+    def key(self):
+        return (self.nd, self.batch, tuple(self.in_dims), self.cin, self.cout, tuple(self.ksize),
+                self.stride, self.upsample)
+
+
+def make_conv_desc(nd, batch, in_dims, cin, cout, ksize, stride=1, upsample=1):
+    in_dims = list(in_dims) + [1] * (3 - len(in_dims))
+    ksize = list(ksize) + [1] * (3 - len(ksize))
+    return ConvDesc(nd, batch, (ctypes.c_int * 3)(*in_dims), cin, cout, (ctypes.c_int * 3)(*ksize),
+                    stride, upsample)
+
+
+ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+IMPL_AUTO, IMPL_FFMA, IMPL_TC = 0, 1, 2
+
+_F = ctypes.POINTER(ctypes.c_float)
+_V = ctypes.c_void_p
+_I = ctypes.c_int
+_L = ctypes.c_int64
+_f = ctypes.c_float
+_D = ctypes.POINTER(ConvDesc)
+
+# name -> argtypes; every function returns int (0 = ok).  Must list every symbol of the header.
+SIGNATURES = {
+    "cn_conv_out_dims": [_D, ctypes.POINTER(ctypes.c_int)],
+    "cn_conv_fwd": [_D, _V, _V, _V, _I, _f, _V, _I, _V],
+    "cn_conv_dgrad": [_D, _V, _V, _V, _I, _V],
+    "cn_conv_wgrad": [_D, _V, _V, _V, _V, _I, _V],
+    "cn_chan_sums": [_V, _V, _V, _I, _I, _I, _V, _V],
+    "cn_chan_affine": [_V, _V, _V, _V, _I, _I, _I, _I, _f, _V, _V],
+    "cn_lrelu_fwd": [_V, _f, _V, _L, _V],
+    "cn_lrelu_bwd": [_V, _V, _f, _V, _L, _V],
+    "cn_act_bwd": [_V, _V, _I, _f, _V, _L, _V],
+    "cn_axpby": [_V, _V, _f, _f, _V, _L, _V],
+    "cn_maxpool2_fwd": [_V, _I, _I, _I, _I, _V, _V],
+    "cn_maxpool2_bwd": [_V, _V, _V, _I, _I, _I, _I, _V, _V],
+    "cn_rotate3d_fwd": [_V, _V, _I, _I, _I, _V, _V],
+    "cn_rotate3d_bwd_grid": [_V, _V, _I, _I, _I, _V, _V],
+    "cn_rotate3d_bwd_rot": [_V, _V, _V, _I, _I, _I, _V, _V],
+    "cn_reduce": [_V, _V, _L, _I, _f, _f, _V, _V, _V],
+    "cn_reduce_bwd": [_V, _V, _L, _I, _f, _f, _V, _V, _V],
+    "cn_to_uint8": [_V, _V, _L, _V],
+    "cn_from_uint8": [_V, _V, _L, _V],
+    "cn_vgg_preprocess": [_V, _V, _L, _I, _V],
+    "cn_adam_ema_step": [_V, _V, _V, _V, _V, _L, _f, _f, _f, _f, _f, _f, _V],
+}
+NO_STATUS = {"cn_last_error": ctypes.c_char_p, "cn_version": ctypes.c_int, "cn_reduce_ws_floats": ctypes.c_int}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once) and declares the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CnError("libconfignet_b200.so not built (%s); run __graft_entry__.build()" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        if not hasattr(lib, name) and os.environ.get("CN_ALLOW_PARTIAL") == "1":
+            continue        # bring-up only: lets a partially built library be probed
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    for name, restype in NO_STATUS.items():
+        if not hasattr(lib, name) and os.environ.get("CN_ALLOW_PARTIAL") == "1":
+            continue
+        getattr(lib, name).restype = restype
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise CnError("libconfignet_b200 error %d: %s" % (rc, load().cn_last_error().decode()))
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))

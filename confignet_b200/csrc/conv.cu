@@ -1,0 +1,958 @@
+// Convolution / Dense family as implicit GEMMs over channels-last tensors (sm_100a).
+//
+// One geometry description (GemmPlan) drives every variant:
+//   pixel mode : D[m][n] = sum_{tap,c} Src[pix(m,tap)][c] * W(tap,c,n)      forward and dgrad
+//   wgrad mode : D[(tap,c)][n] = sum_m Src[pix(m,tap)][c] * G[m][n]
+// pix(m,tap): u_d = e_d*mstride + off_d(tap), valid iff 0 <= u_d < U_d, source coord = u_d >> ushift.
+// That covers TF-SAME asymmetric padding, stride 2, the fused nearest x2 upsample (ushift=1 in
+// forward; extra (delta,tap) generalized taps in dgrad) and the parity phases of the stride-2 dgrad.
+//
+// Two kernels per mode:
+//   igemm_ffma_kernel : fp32 CUDA-core tiles, scalar gathers, any channel count (skinny layers, tiny M)
+//   igemm_tc_*_kernel : tcgen05.mma kind::tf32 (operands rounded RNA to tf32 by the loader warps),
+//                       fp32 accumulators in TMEM, 128B-swizzled smem stages filled by gather warps,
+//                       mbarrier full/empty pipeline, tcgen05.ld epilogue with fused bias+activation.
+//
+// Reference call sites: keras Conv2D/Conv3D/Dense in confignet/dnn_models/*.py (see include/confignet_b200.h).
+#include "common.cuh"
+#include <map>
+#include <string>
+#include <vector>
+#include <mutex>
+#include <string.h>
+
+// ------------------------------------------------------------------------------------------------
+// Plans (host)
+// ------------------------------------------------------------------------------------------------
+enum { KIND_FWD = 0, KIND_DGRAD = 1 };
+
+struct HostPlan {
+  GemmPlan g;
+  bool valid;
+};
+
+static std::mutex g_plan_mutex;
+static std::map<std::string, HostPlan> g_plans;
+
+static inline int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return r; }
+
+static void same_geometry(const cn_conv_desc* d, int U[3], int O[3], int pb[3]) {
+  for (int i = 0; i < 3; ++i) {
+    if (i < d->nd) {
+      U[i] = d->in_dims[i] * d->upsample;
+      O[i] = (U[i] + d->stride - 1) / d->stride;
+      int tot = (O[i] - 1) * d->stride + d->ksize[i] - U[i];
+      if (tot < 0) tot = 0;
+      pb[i] = tot / 2;                 // TF SAME: the smaller half goes in front
+    } else {
+      U[i] = 1; O[i] = 1; pb[i] = 0;
+    }
+  }
+}
+
+static int validate_desc(const cn_conv_desc* d) {
+  CN_REQUIRE(d != nullptr, CN_ERR_BAD_SHAPE, "null conv descriptor");
+  CN_REQUIRE(d->nd == 0 || d->nd == 2 || d->nd == 3, CN_ERR_BAD_SHAPE, "nd must be 0, 2 or 3 (got %d)", d->nd);
+  CN_REQUIRE(d->batch > 0 && d->cin > 0 && d->cout > 0, CN_ERR_BAD_SHAPE, "batch/cin/cout must be positive");
+  CN_REQUIRE(d->stride == 1 || d->stride == 2, CN_ERR_UNSUPPORTED, "stride must be 1 or 2");
+  CN_REQUIRE(d->upsample == 1 || d->upsample == 2, CN_ERR_UNSUPPORTED, "upsample must be 1 or 2");
+  CN_REQUIRE(!(d->stride == 2 && d->upsample == 2), CN_ERR_UNSUPPORTED, "stride 2 with fused upsample is unsupported");
+  for (int i = 0; i < 3; ++i) {
+    CN_REQUIRE(d->in_dims[i] >= 1 && d->ksize[i] >= 1 && d->ksize[i] <= 7, CN_ERR_BAD_SHAPE, "bad dims/ksize");
+    if (i >= d->nd) CN_REQUIRE(d->in_dims[i] == 1 && d->ksize[i] == 1, CN_ERR_BAD_SHAPE, "unused dims must be 1");
+    CN_REQUIRE(d->in_dims[i] * d->upsample <= 1000, CN_ERR_UNSUPPORTED, "spatial extent too large for packed coordinates");
+  }
+  return CN_OK;
+}
+
+static int pack_off(const int off[3]) {
+  return (off[0] + 8) | ((off[1] + 8) << 10) | ((off[2] + 8) << 20);
+}
+
+// Host-side construction of the plan for (desc, kind, phase); phase is only used by the stride-2 dgrad.
+static int build_plan(const cn_conv_desc* d, int kind, int phase, GemmPlan* out, std::vector<int2>& taps) {
+  int U[3], O[3], pb[3];
+  same_geometry(d, U, O, pb);
+  GemmPlan g;
+  memset(&g, 0, sizeof(g));
+  g.n_img = d->batch;
+  taps.clear();
+  const int kvol = d->ksize[0] * d->ksize[1] * d->ksize[2];
+  const int cc = d->cin * d->cout;
+  if (kind == KIND_FWD) {
+    for (int i = 0; i < 3; ++i) {
+      g.E[i] = O[i]; g.U[i] = U[i]; g.S[i] = d->in_dims[i]; g.Q[i] = O[i]; g.ooff[i] = 0;
+    }
+    g.mstride = d->stride; g.ushift = ilog2(d->upsample); g.ostride = 1;
+    g.Csrc = d->cin; g.Cn = d->cout; g.wsc = d->cout; g.wsn = 1;
+    for (int t = 0; t < kvol; ++t) {
+      int t2 = t % d->ksize[2], t1 = (t / d->ksize[2]) % d->ksize[1], t0 = t / (d->ksize[2] * d->ksize[1]);
+      int off[3] = {t0 - pb[0], t1 - pb[1], t2 - pb[2]};
+      taps.push_back(make_int2(pack_off(off), t * cc));
+    }
+  } else {
+    g.Csrc = d->cout; g.Cn = d->cin; g.wsc = 1; g.wsn = d->cout;
+    int ph[3] = {0, 0, 0};
+    if (d->stride == 2) {
+      // phase bits: bit i = parity of output coordinate along spatial dim i
+      for (int i = 0; i < d->nd; ++i) ph[i] = (phase >> i) & 1;
+    }
+    for (int i = 0; i < 3; ++i) {
+      g.S[i] = O[i]; g.Q[i] = d->in_dims[i];
+      if (d->stride == 2 && i < d->nd) {
+        g.E[i] = (d->in_dims[i] - ph[i] + 1) / 2; g.U[i] = 2 * O[i]; g.ooff[i] = ph[i];
+      } else {
+        g.E[i] = d->in_dims[i]; g.U[i] = O[i]; g.ooff[i] = 0;
+      }
+    }
+    if (d->stride == 2) { g.mstride = 2; g.ushift = 1; g.ostride = 2; }
+    else if (d->upsample == 2) { g.mstride = 2; g.ushift = 0; g.ostride = 1; }
+    else { g.mstride = 1; g.ushift = 0; g.ostride = 1; }
+    const int ndelta = (d->upsample == 2) ? (1 << d->nd) : 1;
+    for (int dl = 0; dl < ndelta; ++dl) {
+      int dd[3] = {0, 0, 0};
+      for (int i = 0; i < d->nd; ++i) dd[i] = (dl >> i) & 1;
+      for (int t = 0; t < kvol; ++t) {
+        int tt[3] = {t / (d->ksize[2] * d->ksize[1]), (t / d->ksize[2]) % d->ksize[1], t % d->ksize[2]};
+        int off[3]; bool ok = true;
+        for (int i = 0; i < 3; ++i) {
+          off[i] = dd[i] + ph[i] + pb[i] - tt[i];
+          if (d->stride == 2 && i < d->nd && (off[i] & 1)) ok = false;
+        }
+        if (!ok) continue;
+        taps.push_back(make_int2(pack_off(off), t * cc));
+      }
+    }
+  }
+  for (size_t i = 0; i < taps.size(); ++i) {
+    int px = taps[i].x;
+    int o0 = (px & 1023), o1 = (px >> 10) & 1023, o2 = (px >> 20) & 1023;
+    CN_REQUIRE(o0 >= 0 && o0 < 24 && o1 < 24 && o2 < 24, CN_ERR_UNSUPPORTED, "tap offset out of packed range");
+  }
+  CN_REQUIRE(taps.size() <= 256, CN_ERR_UNSUPPORTED, "too many generalized taps (%d)", (int)taps.size());
+  g.ntaps = (int)taps.size();
+  g.Ktot = g.ntaps * g.Csrc;
+  long long M = (long long)g.n_img * g.E[0] * g.E[1] * g.E[2];
+  CN_REQUIRE(M < (1ll << 31), CN_ERR_UNSUPPORTED, "too many output rows");
+  g.M = (int)M;
+  long long srcpix = (long long)g.n_img * g.S[0] * g.S[1] * g.S[2];
+  CN_REQUIRE(srcpix * g.Csrc < (1ll << 32) && (long long)g.n_img * g.Q[0] * g.Q[1] * g.Q[2] * g.Cn < (1ll << 32),
+             CN_ERR_UNSUPPORTED, "tensor too large for 32-bit element offsets");
+  g.taps = nullptr;
+  *out = g;
+  return CN_OK;
+}
+
+// Cached device plan (tap table uploaded once; call before CUDA-graph capture).
+static int get_plan(const cn_conv_desc* d, int kind, int phase, GemmPlan* out) {
+  std::string key((const char*)d, sizeof(*d));
+  key.push_back((char)kind);
+  key.push_back((char)phase);
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  auto it = g_plans.find(key);
+  if (it != g_plans.end()) { *out = it->second.g; return CN_OK; }
+  GemmPlan g;
+  std::vector<int2> taps;
+  int rc = build_plan(d, kind, phase, &g, taps);
+  if (rc) return rc;
+  int2* dtaps = nullptr;
+  if (!taps.empty()) {
+    CN_CHECK_CUDA(cudaMalloc(&dtaps, taps.size() * sizeof(int2)));
+    CN_CHECK_CUDA(cudaMemcpy(dtaps, taps.data(), taps.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  }
+  g.taps = dtaps;
+  HostPlan hp; hp.g = g; hp.valid = true;
+  g_plans[key] = hp;
+  *out = g;
+  return CN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device helpers shared by both kernel families
+// ------------------------------------------------------------------------------------------------
+struct RowInfo {
+  uint32_t base;   // n_img * S0*S1*S2 (source pixel index of the sample), 0xffffffff = row out of range
+  uint32_t pk;     // packed e_d*mstride
+};
+
+__host__ __device__ __forceinline__ RowInfo decode_row(const GemmPlan& p, int m) {
+  RowInfo r;
+  if (m >= p.M) { r.base = 0xffffffffu; r.pk = 0; return r; }
+  int e2 = m % p.E[2]; m /= p.E[2];
+  int e1 = m % p.E[1]; m /= p.E[1];
+  int e0 = m % p.E[0]; m /= p.E[0];
+  r.base = (uint32_t)m * (uint32_t)(p.S[0] * p.S[1] * p.S[2]);
+  r.pk = (uint32_t)(e0 * p.mstride) | ((uint32_t)(e1 * p.mstride) << 10) | ((uint32_t)(e2 * p.mstride) << 20);
+  return r;
+}
+
+// destination pixel index of row m
+__host__ __device__ __forceinline__ uint32_t dest_pixel(const GemmPlan& p, int m) {
+  int e2 = m % p.E[2]; m /= p.E[2];
+  int e1 = m % p.E[1]; m /= p.E[1];
+  int e0 = m % p.E[0]; m /= p.E[0];
+  uint32_t q0 = e0 * p.ostride + p.ooff[0], q1 = e1 * p.ostride + p.ooff[1], q2 = e2 * p.ostride + p.ooff[2];
+  return (((uint32_t)m * p.Q[0] + q0) * p.Q[1] + q1) * p.Q[2] + q2;
+}
+
+// source pixel index for (row, tap) or 0xffffffff when the tap falls into the padding
+__host__ __device__ __forceinline__ uint32_t src_pixel(const GemmPlan& p, RowInfo r, int tap_pk) {
+  if (r.base == 0xffffffffu) return 0xffffffffu;
+  uint32_t s = r.pk + (uint32_t)tap_pk;
+  int u0 = (int)(s & 1023u) - 8, u1 = (int)((s >> 10) & 1023u) - 8, u2 = (int)(s >> 20) - 8;
+  bool ok = (unsigned)u0 < (unsigned)p.U[0] && (unsigned)u1 < (unsigned)p.U[1] && (unsigned)u2 < (unsigned)p.U[2];
+  if (!ok) return 0xffffffffu;
+  return r.base + (uint32_t)(((u0 >> p.ushift) * p.S[1] + (u1 >> p.ushift)) * p.S[2] + (u2 >> p.ushift));
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core implicit GEMM (fp32 FFMA)
+// ------------------------------------------------------------------------------------------------
+enum { MODE_PIXEL = 0, MODE_WGRAD = 1 };
+
+template <int MODE, int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+igemm_ffma_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ B,
+                  const float* __restrict__ bias, float* __restrict__ D, int act, float alpha,
+                  int kchunk, int use_atomic) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int BK = 16;
+  static_assert(NT % BM == 0 || BM % NT == 0, "row mapping");
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  __shared__ int2 s_taps[256];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < p.ntaps; i += NT) s_taps[i] = p.taps[i];
+  __syncthreads();
+  const int Mg = (MODE == MODE_PIXEL) ? p.M : p.Ktot;
+  const int Ng = p.Cn;
+  const int Kg = (MODE == MODE_PIXEL) ? p.Ktot : p.M;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kbeg = blockIdx.z * kchunk;
+  const int kend = min(Kg, kbeg + kchunk);
+
+  // per-thread fixed A row
+  const int arow = tid % BM;
+  RowInfo rinfo; rinfo.base = 0xffffffffu; rinfo.pk = 0;
+  int a_c = 0, a_tap_pk = 0; bool a_row_ok = false;
+  if (MODE == MODE_PIXEL) {
+    rinfo = decode_row(p, m0 + arow);
+  } else {
+    int r = m0 + arow;
+    a_row_ok = r < Mg;
+    if (a_row_ok) { int kt = r / p.Csrc; a_c = r - kt * p.Csrc; a_tap_pk = s_taps[kt].x; }
+  }
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  const int ty = tid / (BN / TN), tx = tid % (BN / TN);
+
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    // ---- A tile
+    for (int e = tid; e < BM * BK; e += NT) {
+      int kk = e / BM;
+      int k = k0 + kk;
+      float v = 0.f;
+      if (k < kend) {
+        if (MODE == MODE_PIXEL) {
+          int kt = k / p.Csrc; int c = k - kt * p.Csrc;
+          uint32_t sp = src_pixel(p, rinfo, s_taps[kt].x);
+          if (sp != 0xffffffffu) v = __ldg(A + (size_t)sp * p.Csrc + c);
+        } else if (a_row_ok) {
+          RowInfo ri = decode_row(p, k);
+          uint32_t sp = src_pixel(p, ri, a_tap_pk);
+          if (sp != 0xffffffffu) v = __ldg(A + (size_t)sp * p.Csrc + a_c);
+        }
+      }
+      As[kk][arow] = v;
+    }
+    // ---- B tile
+    for (int e = tid; e < BN * BK; e += NT) {
+      int col = e % BN, kk = e / BN;
+      int k = k0 + kk, n = n0 + col;
+      float v = 0.f;
+      if (k < kend && n < Ng) {
+        if (MODE == MODE_PIXEL) {
+          int kt = k / p.Csrc; int c = k - kt * p.Csrc;
+          v = __ldg(B + (size_t)s_taps[kt].y + (size_t)c * p.wsc + (size_t)n * p.wsn);
+        } else {
+          v = __ldg(B + (size_t)k * p.Cn + n);
+        }
+      }
+      Bs[kk][col] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  // ---- epilogue
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + ty * TM + i;
+    if (m >= Mg) continue;
+    size_t rowoff = (MODE == MODE_PIXEL) ? (size_t)dest_pixel(p, m) * p.Cn : (size_t)m * p.Cn;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int n = n0 + tx * TN + j;
+      if (n >= Ng) continue;
+      float v = acc[i][j];
+      if (use_atomic) {
+        if (bias != nullptr && blockIdx.z == 0) v += bias[n];
+        atomicAdd(D + rowoff + n, v);
+      } else {
+        if (bias != nullptr) v += bias[n];
+        D[rowoff + n] = cn_apply_act(v, act, alpha);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 helpers (inline PTX)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t f2tf32(float f) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
+  return r;
+}
+__device__ __forceinline__ void sts128_tf32(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(f2tf32(v.x)), "r"(f2tf32(v.y)), "r"(f2tf32(v.z)), "r"(f2tf32(v.w)) : "memory");
+}
+__device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// UMMA shared-memory descriptor, version 1 (sm_100).  addr/lbo/sbo in bytes.
+// layout: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only MN-major layout for tf32:
+// atoms of 4 k-rows x 128 B, 32-byte units XOR-ed with the k-row index; LBO = MN-atom stride, SBO = stride
+// between groups of 4 k-rows).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout = 2) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3ffffu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// instruction descriptor: tf32 x tf32 -> f32, M=128
+__host__ __device__ inline uint32_t umma_idesc_tf32(int n, int a_mn_major, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                      // D format f32
+  d |= 2u << 7;                      // A format tf32
+  d |= 2u << 10;                     // B format tf32
+  d |= (uint32_t)a_mn_major << 15;
+  d |= (uint32_t)b_mn_major << 16;
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(128 >> 4) << 24;
+  return d;
+}
+
+// byte offset of the 16-byte chunk (k-row r, chunk jn along MN) inside an MN-major tf32 tile whose
+// k-groups (4 rows) are `sbo` bytes apart and whose 32-column atoms (512 B) are contiguous
+__device__ __forceinline__ uint32_t mn_chunk_off(int r, int jn, uint32_t sbo) {
+  return (uint32_t)(r >> 2) * sbo + (uint32_t)(jn >> 3) * 512u + (uint32_t)(r & 3) * 128u +
+         ((uint32_t)(((jn & 7) >> 1) ^ (r & 3)) << 5) + ((uint32_t)(jn & 1) << 4);
+}
+
+constexpr int TC_BM = 128;        // GEMM rows per CTA (UMMA M)
+constexpr int TC_BK = 32;         // fp32 elements per K block = one 128-byte swizzle row
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;
+constexpr int TC_THREADS = 288;   // warps 0-3: A gather + epilogue, 4-7: B gather, 8: TMEM alloc + MMA issue
+
+struct TcSmemLayout {
+  // dynamic smem, 1024-byte aligned: [A stages][B stages][barriers][tmem ptr][taps]
+  uint32_t a_off, b_off, bar_off, tmem_off, taps_off, total;
+};
+__host__ __device__ inline TcSmemLayout tc_layout(int nstages, int bn_smem) {
+  TcSmemLayout l;
+  l.a_off = 0;
+  l.b_off = nstages * TC_A_BYTES;
+  l.bar_off = l.b_off + nstages * bn_smem * TC_BK * 4;
+  l.tmem_off = l.bar_off + (2 * nstages + 1) * 8;
+  l.taps_off = (l.tmem_off + 4 + 7) & ~7u;
+  l.total = l.taps_off + 256 * 8;
+  return l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 pixel-mode kernel (forward: B MN-major = Keras kernel as is; dgrad: B K-major)
+// ------------------------------------------------------------------------------------------------
+template <int B_MN>
+__global__ void __launch_bounds__(TC_THREADS)
+igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ W,
+                      const float* __restrict__ bias, float* __restrict__ D, int act, float alpha,
+                      int bn, int bn_smem, int nstages, int tmem_cols) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const TcSmemLayout L = tc_layout(nstages, bn_smem);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_full = sbase + L.bar_off, bar_empty = bar_full + 8 * nstages, bar_acc = bar_empty + 8 * nstages;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_off);
+  int2* s_taps = reinterpret_cast<int2*>(smem + L.taps_off);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * bn;
+  const int num_kb = (p.Ktot + TC_BK - 1) / TC_BK;
+  const uint32_t b_stage_bytes = bn_smem * TC_BK * 4;
+
+  for (int i = tid; i < p.ntaps; i += TC_THREADS) s_taps[i] = p.taps[i];
+  if (tid == 0) {
+    for (int s = 0; s < nstages; ++s) { mbar_init(bar_full + 8 * s, 256); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + L.tmem_off), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < 4) {
+    // ===== A gather: 8 threads per 128-byte row, 8 rows per thread =====
+    const int j = tid & 7;
+    RowInfo rows[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rows[i] = decode_row(p, m0 + (tid >> 3) + 16 * i);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % nstages;
+      if (kb >= nstages) mbar_wait(bar_empty + 8 * s, ((kb / nstages) - 1) & 1);
+      const int k = kb * TC_BK + 4 * j;
+      int tap_pk = 0, c = 0; bool kok = k < p.Ktot;
+      if (kok) { int kt = k / p.Csrc; c = k - kt * p.Csrc; tap_pk = s_taps[kt].x; }
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint32_t sp = kok ? src_pixel(p, rows[i], tap_pk) : 0xffffffffu;
+        v[i] = (sp != 0xffffffffu) ? ldg128(A + (size_t)sp * p.Csrc + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const uint32_t abase = sbase + L.a_off + s * TC_A_BYTES;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int r = (tid >> 3) + 16 * i;
+        sts128_tf32(abase + r * 128 + ((j ^ (r & 7)) << 4), v[i]);
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * s);
+    }
+    // ===== epilogue: TMEM -> registers -> global (warp w owns TMEM lanes 32w..32w+31) =====
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int m = m0 + warp * 32 + lane;
+    const bool mok = m < p.M;
+    const size_t rowoff = mok ? (size_t)dest_pixel(p, m) * p.Cn : 0;
+    for (int cb = 0; cb < bn; cb += 32) {
+      uint32_t v[32];
+      tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cb, v);
+      if (mok) {
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          int n = n0 + cb + q;
+          if (cb + q < bn && n < p.Cn) {
+            float4 o;
+            o.x = __uint_as_float(v[q]); o.y = __uint_as_float(v[q + 1]);
+            o.z = __uint_as_float(v[q + 2]); o.w = __uint_as_float(v[q + 3]);
+            if (bias != nullptr) { o.x += bias[n]; o.y += bias[n + 1]; o.z += bias[n + 2]; o.w += bias[n + 3]; }
+            o.x = cn_apply_act(o.x, act, alpha); o.y = cn_apply_act(o.y, act, alpha);
+            o.z = cn_apply_act(o.z, act, alpha); o.w = cn_apply_act(o.w, act, alpha);
+            *reinterpret_cast<float4*>(D + rowoff + n) = o;
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ===== B gather =====
+    const int t = tid - 128;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % nstages;
+      if (kb >= nstages) mbar_wait(bar_empty + 8 * s, ((kb / nstages) - 1) & 1);
+      const uint32_t bbase = sbase + L.b_off + s * b_stage_bytes;
+      if (B_MN) {
+        // 32 k-rows x bn_smem columns, MN-major (see mn_chunk_off)
+        const int cpr = bn_smem >> 2;                       // 16-byte chunks per k-row
+        const uint32_t sbo = (uint32_t)(bn_smem >> 5) * 512u;
+        for (int q = t; q < 32 * cpr; q += 128) {
+          int r = q / cpr, jn = q - r * cpr;
+          int k = kb * TC_BK + r, n = n0 + 4 * jn;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < p.Ktot && n < p.Cn && 4 * jn < bn) {
+            int kt = k / p.Csrc; int c = k - kt * p.Csrc;
+            v = ldg128(W + (size_t)s_taps[kt].y + (size_t)c * p.wsc + n);
+          }
+          sts128_tf32(bbase + mn_chunk_off(r, jn, sbo), v);
+        }
+      } else {
+        // bn_smem rows (n) x 32 k; K-major SW128
+        const int j = t & 7;
+        const int k = kb * TC_BK + 4 * j;
+        int c = 0, wb = 0; bool kok = k < p.Ktot;
+        if (kok) { int kt = k / p.Csrc; c = k - kt * p.Csrc; wb = s_taps[kt].y; }
+        for (int r = t >> 3; r < bn_smem; r += 16) {
+          int n = n0 + r;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kok && r < bn && n < p.Cn) v = ldg128(W + (size_t)wb + (size_t)n * p.wsn + c);
+          sts128_tf32(bbase + r * 128 + ((j ^ (r & 7)) << 4), v);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * s);
+    }
+  } else {
+    // ===== MMA issue (one lane) =====
+    const uint32_t idesc = umma_idesc_tf32(bn_smem, 0, B_MN);
+    const uint32_t sbo_b = B_MN ? (uint32_t)(bn_smem >> 5) * 512u : 1024u;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % nstages;
+      mbar_wait(bar_full + 8 * s, (kb / nstages) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t abase = sbase + L.a_off + s * TC_A_BYTES;
+        const uint32_t bbase = sbase + L.b_off + s * b_stage_bytes;
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 8; ++kk) {
+          uint64_t ad = umma_desc(abase + kk * 32, 16, 1024);
+          uint64_t bd = B_MN ? umma_desc(bbase + kk * 2 * sbo_b, 512, sbo_b, 1) : umma_desc(bbase + kk * 32, 16, 1024);
+          tc_mma_tf32(tmem_base, ad, bd, idesc, (kb | kk) != 0);
+        }
+        tc_commit(bar_empty + 8 * s);
+        if (kb == num_kb - 1) tc_commit(bar_acc);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 wgrad kernel: D[(tap,c)][n] = sum_m Src[pix(m,tap)][c] * G[m][n]; both operands MN-major
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS)
+igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ G,
+                      float* __restrict__ D, int bn, int bn_smem, int nstages, int tmem_cols,
+                      int kb_per_split, int use_atomic) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const TcSmemLayout L = tc_layout(nstages, bn_smem);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_full = sbase + L.bar_off, bar_empty = bar_full + 8 * nstages, bar_acc = bar_empty + 8 * nstages;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_off);
+  int2* s_taps = reinterpret_cast<int2*>(smem + L.taps_off);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r0 = blockIdx.x * TC_BM, n0 = blockIdx.y * bn;
+  const int total_kb = (p.M + TC_BK - 1) / TC_BK;
+  const int kb_beg = blockIdx.z * kb_per_split;
+  const int kb_end = min(total_kb, kb_beg + kb_per_split);
+  const int num_kb = kb_end - kb_beg;     // host guarantees >= 1
+  const uint32_t b_stage_bytes = bn_smem * TC_BK * 4;
+  const uint32_t sbo_b = (uint32_t)(bn_smem >> 5) * 512u;
+
+  for (int i = tid; i < p.ntaps; i += TC_THREADS) s_taps[i] = p.taps[i];
+  if (tid == 0) {
+    for (int s = 0; s < nstages; ++s) { mbar_init(bar_full + 8 * s, 256); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + L.tmem_off), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < 4) {
+    // ===== A gather: lane = 16-byte chunk of the 128 GEMM rows (fixed tap/channel per thread),
+    //       warp w fills pixel rows 8w..8w+7 of the K block =====
+    const int rr = r0 + 4 * lane;
+    const bool rok = rr < p.Ktot;
+    int c = 0, tap_pk = 0;
+    if (rok) { int kt = rr / p.Csrc; c = rr - kt * p.Csrc; tap_pk = s_taps[kt].x; }
+    for (int it = 0; it < num_kb; ++it) {
+      const int s = it % nstages;
+      if (it >= nstages) mbar_wait(bar_empty + 8 * s, ((it / nstages) - 1) & 1);
+      const int mbase = (kb_beg + it) * TC_BK + warp * 8;
+      RowInfo mine = decode_row(p, mbase + (lane & 7));
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        RowInfo ri;
+        ri.base = __shfl_sync(0xffffffffu, mine.base, i);
+        ri.pk = __shfl_sync(0xffffffffu, mine.pk, i);
+        uint32_t sp = rok ? src_pixel(p, ri, tap_pk) : 0xffffffffu;
+        v[i] = (sp != 0xffffffffu) ? ldg128(A + (size_t)sp * p.Csrc + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const uint32_t abase = sbase + L.a_off + s * TC_A_BYTES;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sts128_tf32(abase + mn_chunk_off(warp * 8 + i, lane, 2048u), v[i]);
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * s);
+    }
+    // ===== epilogue =====
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int r = r0 + warp * 32 + lane;
+    const bool ok = r < p.Ktot;
+    const size_t rowoff = (size_t)r * p.Cn;
+    for (int cb = 0; cb < bn; cb += 32) {
+      uint32_t v[32];
+      tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cb, v);
+      if (ok) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          int n = n0 + cb + q;
+          if (cb + q < bn && n < p.Cn) {
+            if (use_atomic) atomicAdd(D + rowoff + n, __uint_as_float(v[q]));
+            else D[rowoff + n] = __uint_as_float(v[q]);
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ===== B gather: 32 pixel rows x bn_smem columns of G =====
+    const int t = tid - 128;
+    const int cpr = bn_smem >> 2;
+    for (int it = 0; it < num_kb; ++it) {
+      const int s = it % nstages;
+      if (it >= nstages) mbar_wait(bar_empty + 8 * s, ((it / nstages) - 1) & 1);
+      const uint32_t bbase = sbase + L.b_off + s * b_stage_bytes;
+      const int mbase = (kb_beg + it) * TC_BK;
+      for (int q = t; q < 32 * cpr; q += 128) {
+        int r = q / cpr, jn = q - r * cpr;
+        int m = mbase + r, n = n0 + 4 * jn;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < p.M && n < p.Cn && 4 * jn < bn) v = ldg128(G + (size_t)m * p.Cn + n);
+        sts128_tf32(bbase + mn_chunk_off(r, jn, sbo_b), v);
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * s);
+    }
+  } else {
+    const uint32_t idesc = umma_idesc_tf32(bn_smem, 1, 1);
+    for (int it = 0; it < num_kb; ++it) {
+      const int s = it % nstages;
+      mbar_wait(bar_full + 8 * s, (it / nstages) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t abase = sbase + L.a_off + s * TC_A_BYTES;
+        const uint32_t bbase = sbase + L.b_off + s * b_stage_bytes;
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 8; ++kk) {
+          uint64_t ad = umma_desc(abase + kk * 4096u, 512, 2048, 1);
+          uint64_t bd = umma_desc(bbase + kk * 2 * sbo_b, 512, sbo_b, 1);
+          tc_mma_tf32(tmem_base, ad, bd, idesc, (it | kk) != 0);
+        }
+        tc_commit(bar_empty + 8 * s);
+        if (it == num_kb - 1) tc_commit(bar_acc);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// column sums of a (rows, n) matrix: bias gradient
+__global__ void colsum_kernel(const float* __restrict__ g, int rows, int n, float* __restrict__ out) {
+  // grid.x covers columns in groups of 32, grid.y splits rows; blockDim = (32, 8)
+  __shared__ float sm[8][33];
+  int col = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (col < n)
+    for (int r = blockIdx.y * 8 + threadIdx.y; r < rows; r += 8 * gridDim.y) acc += g[(size_t)r * n + col];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < n) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += sm[i][threadIdx.x];
+    atomicAdd(out + col, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host dispatch
+// ------------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+static int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+  CN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return CN_OK;
+}
+
+static bool tc_pixel_eligible(const GemmPlan& g, bool b_mn) {
+  if (g.M < 128 || g.ntaps == 0 || g.Ktot < 32) return false;
+  if (g.Csrc % 4 != 0) return false;
+  if (b_mn) return g.Cn % 4 == 0 && g.Cn >= 16;
+  return g.Cn % 16 == 0;
+}
+
+static void pick_bn_mn(int cn, int* bn, int* bn_smem) {
+  // MN-major B tiles are built from 32-column swizzle atoms
+  int padded = (cn + 31) / 32 * 32;
+  int best = 32;
+  for (int c = 32; c <= 128; c += 32) if (padded % c == 0) best = c;
+  *bn_smem = best;
+  *bn = best;
+}
+static void pick_bn_k(int cn, int* bn, int* bn_smem) {
+  int best = 16;
+  for (int c = 16; c <= 128; c += 16) if (cn % c == 0) best = c;
+  *bn = best; *bn_smem = best;
+}
+
+static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const float* w, const float* bias,
+                        float* dst, int act, float alpha, int impl, cudaStream_t st) {
+  if (g.M == 0) return CN_OK;
+  bool tc = tc_pixel_eligible(g, b_mn);
+  CN_REQUIRE(!(impl == CN_IMPL_TC && !tc), CN_ERR_UNSUPPORTED, "shape not eligible for the tcgen05 kernel");
+  if (impl == CN_IMPL_FFMA) tc = false;
+  if (tc) {
+    int bn, bn_smem;
+    if (b_mn) pick_bn_mn(g.Cn, &bn, &bn_smem); else pick_bn_k(g.Cn, &bn, &bn_smem);
+    int nstages = 3;
+    TcSmemLayout L = tc_layout(nstages, bn_smem);
+    int smem = L.total + 1024;
+    dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.Cn + bn - 1) / bn, 1);
+    int cols = pow2_cols((bn_smem + 31) / 32 * 32);
+    if (b_mn) {
+      if (set_smem(igemm_tc_pixel_kernel<1>, smem)) return CN_ERR_CUDA;
+      igemm_tc_pixel_kernel<1><<<grid, TC_THREADS, smem, st>>>(g, src, w, bias, dst, act, alpha, bn, bn_smem, nstages, cols);
+    } else {
+      if (set_smem(igemm_tc_pixel_kernel<0>, smem)) return CN_ERR_CUDA;
+      igemm_tc_pixel_kernel<0><<<grid, TC_THREADS, smem, st>>>(g, src, w, bias, dst, act, alpha, bn, bn_smem, nstages, cols);
+    }
+    CN_CHECK_LAUNCH();
+    return CN_OK;
+  }
+  // CUDA-core path
+  if (g.Cn <= 4) {
+    dim3 grid((g.M + 255) / 256, 1, 1);
+    igemm_ffma_kernel<MODE_PIXEL, 256, 4, 1, 4><<<grid, 256, 0, st>>>(g, src, w, bias, dst, act, alpha, g.Ktot > 0 ? g.Ktot : 1, 0);
+  } else {
+    int mt = (g.M + 63) / 64, nt = (g.Cn + 63) / 64;
+    int split = 1;
+    if (act == CN_ACT_NONE && mt * nt < num_sms() && g.Ktot >= 2048) {
+      split = (2 * num_sms() + mt * nt - 1) / (mt * nt);
+      int maxsplit = g.Ktot / 256; if (maxsplit < 1) maxsplit = 1;
+      if (split > maxsplit) split = maxsplit;
+    }
+    int kchunk = g.Ktot > 0 ? ((g.Ktot + split - 1) / split + 15) / 16 * 16 : 16;
+    split = g.Ktot > 0 ? (g.Ktot + kchunk - 1) / kchunk : 1;
+    if (split > 1) CN_CHECK_CUDA(cudaMemsetAsync(dst, 0, (size_t)g.n_img * g.Q[0] * g.Q[1] * g.Q[2] * g.Cn * sizeof(float), st));
+    dim3 grid(mt, nt, split);
+    igemm_ffma_kernel<MODE_PIXEL, 64, 64, 4, 4><<<grid, 256, 0, st>>>(g, src, w, bias, dst, act, alpha, kchunk, split > 1);
+  }
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
+static size_t conv_numel_x(const cn_conv_desc* d) {
+  return (size_t)d->batch * d->in_dims[0] * d->in_dims[1] * d->in_dims[2] * d->cin;
+}
+
+extern "C" int cn_conv_out_dims(const cn_conv_desc* d, int out_dims[3]) {
+  if (validate_desc(d)) return CN_ERR_BAD_SHAPE;
+  int U[3], O[3], pb[3];
+  same_geometry(d, U, O, pb);
+  for (int i = 0; i < 3; ++i) out_dims[i] = O[i];
+  return CN_OK;
+}
+
+extern "C" int cn_conv_fwd(const cn_conv_desc* d, const float* x, const float* w, const float* bias,
+                           int act, float alpha, float* y, int impl, void* stream) {
+  int rc = validate_desc(d); if (rc) return rc;
+  CN_REQUIRE(x && w && y, CN_ERR_BAD_SHAPE, "null tensor pointer");
+  GemmPlan g;
+  rc = get_plan(d, KIND_FWD, 0, &g); if (rc) return rc;
+  return launch_pixel(g, true, x, w, bias, y, act, alpha, impl, (cudaStream_t)stream);
+}
+
+extern "C" int cn_conv_dgrad(const cn_conv_desc* d, const float* gy, const float* w, float* gx,
+                             int impl, void* stream) {
+  int rc = validate_desc(d); if (rc) return rc;
+  CN_REQUIRE(gy && w && gx, CN_ERR_BAD_SHAPE, "null tensor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nphase = (d->stride == 2) ? (1 << d->nd) : 1;
+  for (int ph = 0; ph < nphase; ++ph) {
+    GemmPlan g;
+    rc = get_plan(d, KIND_DGRAD, ph, &g); if (rc) return rc;
+    if (g.M == 0) continue;
+    int use_impl = impl;
+    if (g.ntaps == 0) use_impl = CN_IMPL_FFMA;       // phase without taps: writes zeros
+    rc = launch_pixel(g, false, gy, w, nullptr, gx, CN_ACT_NONE, 0.f, use_impl, st);
+    if (rc) return rc;
+  }
+  return CN_OK;
+}
+
+extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float* gy, float* gw,
+                             float* gbias, int impl, void* stream) {
+  int rc = validate_desc(d); if (rc) return rc;
+  CN_REQUIRE(x && gy && gw, CN_ERR_BAD_SHAPE, "null tensor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmPlan g;
+  rc = get_plan(d, KIND_FWD, 0, &g); if (rc) return rc;
+  const size_t wn = (size_t)g.Ktot * g.Cn;
+  bool tc = g.M >= 256 && g.Csrc % 4 == 0 && g.Cn % 4 == 0 && g.Cn >= 16 && g.Ktot >= 64;
+  CN_REQUIRE(!(impl == CN_IMPL_TC && !tc), CN_ERR_UNSUPPORTED, "shape not eligible for the tcgen05 wgrad kernel");
+  if (impl == CN_IMPL_FFMA) tc = false;
+  if (tc) {
+    int bn, bn_smem; pick_bn_mn(g.Cn, &bn, &bn_smem);
+    int nstages = 3;
+    TcSmemLayout L = tc_layout(nstages, bn_smem);
+    int smem = L.total + 1024;
+    int mt = (g.Ktot + TC_BM - 1) / TC_BM, nt = (g.Cn + bn - 1) / bn;
+    int total_kb = (g.M + TC_BK - 1) / TC_BK;
+    int split = (2 * num_sms() + mt * nt - 1) / (mt * nt);
+    int maxsplit = total_kb / 8; if (maxsplit < 1) maxsplit = 1;
+    if (split > maxsplit) split = maxsplit;
+    if (split < 1) split = 1;
+    int per = (total_kb + split - 1) / split;
+    split = (total_kb + per - 1) / per;
+    if (split > 1) CN_CHECK_CUDA(cudaMemsetAsync(gw, 0, wn * sizeof(float), st));
+    if (set_smem(igemm_tc_wgrad_kernel, smem)) return CN_ERR_CUDA;
+    dim3 grid(mt, nt, split);
+    int cols = pow2_cols(bn_smem);
+    igemm_tc_wgrad_kernel<<<grid, TC_THREADS, smem, st>>>(g, x, gy, gw, bn, bn_smem, nstages, cols, per, split > 1);
+    CN_CHECK_LAUNCH();
+  } else {
+    int mt = (g.Ktot + 63) / 64, nt = (g.Cn + 63) / 64;
+    int split = (2 * num_sms() + mt * nt - 1) / (mt * nt);
+    int maxsplit = g.M / 128; if (maxsplit < 1) maxsplit = 1;
+    if (split > maxsplit) split = maxsplit;
+    int kchunk = ((g.M + split - 1) / split + 15) / 16 * 16;
+    split = (g.M + kchunk - 1) / kchunk;
+    if (split > 1) CN_CHECK_CUDA(cudaMemsetAsync(gw, 0, wn * sizeof(float), st));
+    dim3 grid(mt, nt, split);
+    igemm_ffma_kernel<MODE_WGRAD, 64, 64, 4, 4><<<grid, 256, 0, st>>>(g, x, gy, nullptr, gw, CN_ACT_NONE, 0.f, kchunk, split > 1);
+    CN_CHECK_LAUNCH();
+  }
+  if (gbias != nullptr) {
+    CN_CHECK_CUDA(cudaMemsetAsync(gbias, 0, (size_t)g.Cn * sizeof(float), st));
+    int ysplit = (g.M + 2047) / 2048; if (ysplit > 256) ysplit = 256; if (ysplit < 1) ysplit = 1;
+    dim3 grid((g.Cn + 31) / 32, ysplit), block(32, 8);
+    colsum_kernel<<<grid, block, 0, st>>>(gy, g.M, g.Cn, gbias);
+    CN_CHECK_LAUNCH();
+  }
+  (void)conv_numel_x;
+  return CN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host evaluation of a plan with scalar loops.  TEST HOOK ONLY (tests/test_plan_host.py): lets the
+// CPU-only test suite check the integer geometry (SAME padding, phases, fused upsample, tap tables)
+// that the kernels share, without a GPU.  Not used by any product path.
+// kind: 0 forward, 1 dgrad, 2 wgrad.  All pointers are HOST pointers here.
+// ------------------------------------------------------------------------------------------------
+extern "C" int cn_debug_conv_host(const cn_conv_desc* d, int kind, const float* a, const float* b, float* out) {
+  int rc = validate_desc(d); if (rc) return rc;
+  const int nphase = (kind == 1 && d->stride == 2) ? (1 << d->nd) : 1;
+  for (int ph = 0; ph < nphase; ++ph) {
+    GemmPlan p; std::vector<int2> taps;
+    rc = build_plan(d, kind == 1 ? KIND_DGRAD : KIND_FWD, ph, &p, taps); if (rc) return rc;
+    if (kind == 2) {
+      for (int r = 0; r < p.Ktot; ++r) {
+        int kt = r / p.Csrc, c = r % p.Csrc;
+        for (int n = 0; n < p.Cn; ++n) {
+          double acc = 0;
+          for (int m = 0; m < p.M; ++m) {
+            uint32_t sp = src_pixel(p, decode_row(p, m), taps[kt].x);
+            if (sp != 0xffffffffu) acc += (double)a[(size_t)sp * p.Csrc + c] * b[(size_t)m * p.Cn + n];
+          }
+          out[(size_t)r * p.Cn + n] = (float)acc;
+        }
+      }
+    } else {
+      for (int m = 0; m < p.M; ++m) {
+        RowInfo ri = decode_row(p, m);
+        size_t ro = (size_t)dest_pixel(p, m) * p.Cn;
+        for (int n = 0; n < p.Cn; ++n) {
+          double acc = 0;
+          for (int kt = 0; kt < p.ntaps; ++kt) {
+            uint32_t sp = src_pixel(p, ri, taps[kt].x);
+            if (sp == 0xffffffffu) continue;
+            for (int c = 0; c < p.Csrc; ++c)
+              acc += (double)a[(size_t)sp * p.Csrc + c] * b[(size_t)taps[kt].y + (size_t)c * p.wsc + (size_t)n * p.wsn];
+          }
+          out[ro + n] = (float)acc;
+        }
+      }
+    }
+  }
+  return CN_OK;
+}

@@ -1,0 +1,7 @@
+#include "common.cuh"
+static thread_local char g_err[512] = "";
+void cn_set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+extern "C" const char* cn_last_error(void) { return g_err; }
+extern "C" int cn_version(void) { return 1; }

@@ -1,0 +1,321 @@
+// Elementwise / gather / reduction kernels of the ConfigNet hot path that are not convolutions:
+// activations' backward, 2x2 max-pool (VGG), the rigid 3-D feature rotation, loss reductions,
+// uint8 <-> float image conversion, VGG preprocessing and the fused Keras-Adam + EMA update.
+// All HBM-bound: float4 accesses, grid-stride loops over a grid sized in multiples of the SM count.
+#include "common.cuh"
+
+static inline int grid_for(size_t n, int per_thread = 1) {
+  size_t b = (n + (size_t)256 * per_thread - 1) / ((size_t)256 * per_thread);
+  if (b > 148 * 16) b = 148 * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise
+__global__ void lrelu_fwd_kernel(const float* __restrict__ x, float alpha, float* __restrict__ y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = x[i]; y[i] = v > 0.f ? v : v * alpha;
+  }
+}
+__global__ void act_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ ref, int act, float alpha,
+                               float* __restrict__ gx, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float r = ref[i], g = gy[i];
+    if (act == CN_ACT_LRELU) g *= (r > 0.f ? 1.f : alpha);
+    else if (act == CN_ACT_RELU) g = r > 0.f ? g : 0.f;
+    else if (act == CN_ACT_TANH) g *= (1.f - r * r);
+    gx[i] = g;
+  }
+}
+__global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float a, float b,
+                             float* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = a * x[i] + (y ? b * y[i] : 0.f);
+}
+
+extern "C" int cn_lrelu_fwd(const float* x, float alpha, float* y, int64_t n, void* stream) {
+  if (n <= 0) return CN_OK;
+  lrelu_fwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, alpha, y, (size_t)n);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
+extern "C" int cn_act_bwd(const float* gy, const float* y, int act, float alpha, float* gx, int64_t n, void* stream) {
+  if (n <= 0) return CN_OK;
+  act_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(gy, y, act, alpha, gx, (size_t)n);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
+extern "C" int cn_axpby(const float* x, const float* y, float a, float b, float* out, int64_t n, void* stream) {
+  if (n <= 0) return CN_OK;
+  axpby_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, y, a, b, out, (size_t)n);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ max-pool 2x2/s2 (NHWC)
+__global__ void maxpool2_fwd_kernel(const float* __restrict__ x, int h, int w, int c, float* __restrict__ y, size_t total) {
+  const int oh = h / 2, ow = w / 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int ch = (int)(i % c); size_t t = i / c;
+    int ox = (int)(t % ow); t /= ow;
+    int oy = (int)(t % oh); size_t n = t / oh;
+    const float* p = x + ((n * h + 2 * oy) * w + 2 * ox) * c + ch;
+    float m = fmaxf(fmaxf(p[0], p[c]), fmaxf(p[(size_t)w * c], p[(size_t)w * c + c]));
+    y[i] = m;
+  }
+}
+// gradient goes to the first element equal to the maximum in (dy,dx) scan order
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy,
+                                    int h, int w, int c, float* __restrict__ gx, size_t total) {
+  const int oh = h / 2, ow = w / 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int ch = (int)(i % c); size_t t = i / c;
+    int ox = (int)(t % ow); t /= ow;
+    int oy = (int)(t % oh); size_t n = t / oh;
+    size_t base = ((n * h + 2 * oy) * w + 2 * ox) * c + ch;
+    float m = y[i], g = gy[i];
+    bool done = false;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        size_t j = base + ((size_t)dy * w + dx) * c;
+        bool hit = !done && x[j] == m;
+        gx[j] = hit ? g : 0.f;
+        done = done || hit;
+      }
+  }
+}
+extern "C" int cn_maxpool2_fwd(const float* x, int n, int h, int w, int c, float* y, void* stream) {
+  CN_REQUIRE(h % 2 == 0 && w % 2 == 0, CN_ERR_BAD_SHAPE, "maxpool2: odd spatial size");
+  size_t total = (size_t)n * (h / 2) * (w / 2) * c;
+  maxpool2_fwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, h, w, c, y, total);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
+extern "C" int cn_maxpool2_bwd(const float* x, const float* y, const float* gy, int n, int h, int w, int c,
+                               float* gx, void* stream) {
+  CN_REQUIRE(h % 2 == 0 && w % 2 == 0, CN_ERR_BAD_SHAPE, "maxpool2: odd spatial size");
+  size_t total = (size_t)n * (h / 2) * (w / 2) * c;
+  maxpool2_bwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, y, gy, h, w, c, gx, total);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ rotate3d
+// confignet_utils.py:63-120.  One warp per output voxel, lanes over channels.
+struct RotCorner { int idx[8]; float d0, d1, d2; };
+
+__device__ __forceinline__ RotCorner rot_corners(const float* __restrict__ R, int s, int x, int y, int z) {
+  const float ctr = (s - 1) * 0.5f, hi = (float)(s - 1);
+  const float px = x - ctr, py = y - ctr, pz = z - ctr;
+  float t0 = R[0] * px + R[1] * py + R[2] * pz + ctr;
+  float t1 = R[3] * px + R[4] * py + R[5] * pz + ctr;
+  float t2 = R[6] * px + R[7] * py + R[8] * pz + ctr;
+  t0 = fminf(fmaxf(t0, 0.f), hi); t1 = fminf(fmaxf(t1, 0.f), hi); t2 = fminf(fmaxf(t2, 0.f), hi);
+  const float f0 = floorf(t0), f1 = floorf(t1), f2 = floorf(t2);
+  const int i0 = (int)f0, i1 = (int)f1, i2 = (int)f2;
+  const int c0 = min(i0 + 1, s - 1), c1 = min(i1 + 1, s - 1), c2 = min(i2 + 1, s - 1);
+  RotCorner r;
+  r.d0 = t0 - f0; r.d1 = t1 - f1; r.d2 = t2 - f2;
+  // order: 000 100 010 110 001 101 011 111  (bit0 = axis0 ceil, bit1 = axis1 ceil, bit2 = axis2 ceil)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int a = (k & 1) ? c0 : i0, b = (k & 2) ? c1 : i1, c = (k & 4) ? c2 : i2;
+    r.idx[k] = (a * s + b) * s + c;
+  }
+  return r;
+}
+
+__global__ void rotate3d_fwd_kernel(const float* __restrict__ grid, const float* __restrict__ rot, int s, int c,
+                                    float* __restrict__ out, int nvox_total) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= nvox_total) return;
+  const int s3 = s * s * s;
+  const int b = warp / s3, v = warp % s3;
+  const int z = v % s, y = (v / s) % s, x = v / (s * s);
+  RotCorner rc = rot_corners(rot + b * 9, s, x, y, z);
+  const float* g = grid + (size_t)b * s3 * c;
+  float* o = out + (size_t)warp * c;
+  const float d0 = rc.d0, d1 = rc.d1, d2 = rc.d2;
+  for (int ch = lane; ch < c; ch += 32) {
+    float v000 = g[(size_t)rc.idx[0] * c + ch], v100 = g[(size_t)rc.idx[1] * c + ch];
+    float v010 = g[(size_t)rc.idx[2] * c + ch], v110 = g[(size_t)rc.idx[3] * c + ch];
+    float v001 = g[(size_t)rc.idx[4] * c + ch], v101 = g[(size_t)rc.idx[5] * c + ch];
+    float v011 = g[(size_t)rc.idx[6] * c + ch], v111 = g[(size_t)rc.idx[7] * c + ch];
+    float c00 = v000 * (1.f - d0) + v100 * d0, c01 = v001 * (1.f - d0) + v101 * d0;
+    float c10 = v010 * (1.f - d0) + v110 * d0, c11 = v011 * (1.f - d0) + v111 * d0;
+    float c0 = c00 * (1.f - d1) + c10 * d1, c1 = c01 * (1.f - d1) + c11 * d1;
+    o[ch] = c0 * (1.f - d2) + c1 * d2;
+  }
+}
+__global__ void rotate3d_bwd_grid_kernel(const float* __restrict__ gout, const float* __restrict__ rot, int s, int c,
+                                         float* __restrict__ ggrid, int nvox_total) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= nvox_total) return;
+  const int s3 = s * s * s;
+  const int b = warp / s3, v = warp % s3;
+  const int z = v % s, y = (v / s) % s, x = v / (s * s);
+  RotCorner rc = rot_corners(rot + b * 9, s, x, y, z);
+  float* g = ggrid + (size_t)b * s3 * c;
+  const float* go = gout + (size_t)warp * c;
+  float wt[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    wt[k] = ((k & 1) ? rc.d0 : 1.f - rc.d0) * ((k & 2) ? rc.d1 : 1.f - rc.d1) * ((k & 4) ? rc.d2 : 1.f - rc.d2);
+  for (int ch = lane; ch < c; ch += 32) {
+    float gv = go[ch];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(g + (size_t)rc.idx[k] * c + ch, gv * wt[k]);
+  }
+}
+extern "C" int cn_rotate3d_fwd(const float* grid, const float* rot, int b, int s, int c, float* out, void* stream) {
+  int nv = b * s * s * s;
+  rotate3d_fwd_kernel<<<(nv * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(grid, rot, s, c, out, nv);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
+extern "C" int cn_rotate3d_bwd_grid(const float* gout, const float* rot, int b, int s, int c, float* ggrid, void* stream) {
+  int nv = b * s * s * s;
+  rotate3d_bwd_grid_kernel<<<(nv * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gout, rot, s, c, ggrid, nv);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ reductions
+#define CN_RED_BLOCKS 592
+extern "C" int cn_reduce_ws_floats(void) { return CN_RED_BLOCKS; }
+
+__device__ __forceinline__ float red_term(int kind, float x, float y, float sign) {
+  if (kind == 0) { float z = sign * x; return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z))); }   // softplus
+  if (kind == 1) { float d = x - y; return d * d; }
+  if (kind == 2) return x * x;
+  return x;
+}
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float sm[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  v = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.f;
+  if (w == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  return v;   // valid in thread 0
+}
+// weighted variant: term *= wgt[i / wdiv] (eye loss mask broadcast over channels)
+__global__ void reduce_stage1_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ wgt,
+                                     int wdiv, size_t n, int kind, float sign, float* __restrict__ ws) {
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float t = red_term(kind, x[i], y ? y[i] : 0.f, sign);
+    if (wgt) t *= wgt[i / wdiv];
+    acc += t;
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) ws[blockIdx.x] = acc;
+}
+__global__ void reduce_stage2_kernel(const float* __restrict__ ws, int nb, float scale, float* __restrict__ result) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) acc += ws[i];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) result[0] = acc * scale;
+}
+extern "C" int cn_reduce(const float* x, const float* y, const float* wgt, int wdiv, int64_t n, int kind, float sign,
+                         float scale, float* ws, float* result, void* stream) {
+  CN_REQUIRE(x && ws && result && n > 0 && kind >= 0 && kind <= 3, CN_ERR_BAD_SHAPE, "cn_reduce: bad arguments");
+  int nb = grid_for(n, 4); if (nb > CN_RED_BLOCKS) nb = CN_RED_BLOCKS;
+  reduce_stage1_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(x, y, wgt, wdiv > 0 ? wdiv : 1, (size_t)n, kind, sign, ws);
+  CN_CHECK_LAUNCH();
+  reduce_stage2_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ws, nb, scale, result);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
+__global__ void reduce_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ wgt,
+                                  int wdiv, size_t n, int kind, float sign, float k, const float* __restrict__ gscale,
+                                  float* __restrict__ gx) {
+  const float gs = gscale[0] * k;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float xv = x[i], g;
+    if (kind == 0) { float z = sign * xv; g = sign / (1.f + expf(-z)); }
+    else if (kind == 1) g = 2.f * (xv - y[i]);
+    else if (kind == 2) g = 2.f * xv;
+    else g = 1.f;
+    if (wgt) g *= wgt[i / wdiv];
+    gx[i] = g * gs;
+  }
+}
+extern "C" int cn_reduce_bwd(const float* x, const float* y, const float* wgt, int wdiv, int64_t n, int kind, float sign,
+                             float k, const float* gscale, float* gx, void* stream) {
+  CN_REQUIRE(x && gscale && gx && n > 0, CN_ERR_BAD_SHAPE, "cn_reduce_bwd: bad arguments");
+  reduce_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, y, wgt, wdiv > 0 ? wdiv : 1, (size_t)n, kind, sign, k, gscale, gx);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ images
+__global__ void to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = fminf(fmaxf(x[i], -1.f), 1.f);
+    v = (v + 1.f) * 127.5f;            // same fp32 operation order as NumPy: (clip(x)+1)*127.5
+    out[i] = (uint8_t)v;               // truncation, like ndarray.astype(np.uint8) on [0,255]
+  }
+}
+__global__ void from_uint8_kernel(const uint8_t* __restrict__ x, float* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (float)x[i] / 127.5f - 1.f;
+}
+extern "C" int cn_to_uint8(const float* x, uint8_t* out, int64_t n, void* stream) {
+  if (n <= 0) return CN_OK;
+  to_uint8_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, out, (size_t)n);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
+extern "C" int cn_from_uint8(const uint8_t* x, float* out, int64_t n, void* stream) {
+  if (n <= 0) return CN_OK;
+  from_uint8_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, out, (size_t)n);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
+// (x+1)*127.5, channel flip, subtract caffe BGR means; backward: gx[..., 2-c] = 127.5 * g[..., c]
+__global__ void vgg_preprocess_kernel(const float* __restrict__ x, float* __restrict__ out, size_t npix, int backward) {
+  const float mean[3] = {103.939f, 116.779f, 123.68f};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const float* p = x + i * 3; float* o = out + i * 3;
+    if (!backward) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[c] = (p[2 - c] + 1.f) * 127.5f - mean[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[2 - c] = 127.5f * p[c];
+    }
+  }
+}
+extern "C" int cn_vgg_preprocess(const float* x, float* out, int64_t npix, int backward, void* stream) {
+  if (npix <= 0) return CN_OK;
+  vgg_preprocess_kernel<<<grid_for(npix), 256, 0, (cudaStream_t)stream>>>(x, out, (size_t)npix, backward);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ Adam + EMA
+__global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, float* __restrict__ ema, size_t n, float lr_t, float b1,
+                                float b2, float eps, float ema_alpha, float gscale) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    m[i] = mi; v[i] = vi; p[i] = pi;
+    if (ema) ema[i] = ema_alpha * ema[i] + (1.f - ema_alpha) * pi;
+  }
+}
+extern "C" int cn_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr_t,
+                                float b1, float b2, float eps, float ema_alpha, float gscale, void* stream) {
+  if (n <= 0) return CN_OK;
+  CN_REQUIRE(p && g && m && v, CN_ERR_BAD_SHAPE, "cn_adam_ema_step: null pointer");
+  adam_ema_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, (size_t)n, lr_t, b1, b2, eps, ema_alpha, gscale);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
+// EMA alone (generator_smoothed when the optimizer step is not fused)
+__global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ p, size_t n, float alpha) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    ema[i] = alpha * ema[i] + (1.f - alpha) * p[i];
+}
+extern "C" int cn_ema(float* ema, const float* p, int64_t n, float alpha, void* stream) {
+  if (n <= 0) return CN_OK;
+  ema_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(ema, p, (size_t)n, alpha);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}

@@ -1,0 +1,235 @@
+// Per-(sample, channel) statistics and broadcast-affine kernels over channels-last tensors, plus the
+// closed-form coefficient kernels of the three normalisations on ConfigNet's hot path and their
+// first- and second-order gradients (the R1 penalty differentiates the discriminator's backward
+// pass, losses.py:42-43,75-82).
+//
+//   AdaIN          building_blocks.py:135-149   (x-mu)*rsqrt(var+1e-3)*(1+s)+b
+//   InstanceNorm   instance_normalization.py:108-131   gamma*(x-mu)/(std+1e-3)+beta  (eps on the STD)
+//   layer style    confignet_utils.py:147-159   concat(mean, sqrt(var+1e-6))
+//
+// Every op is "7 sums per (n,c)" -> "a few scalars per (n,c)" -> "out = ka*a + kb*b + kc*c + k0".
+// HBM-bound: one read of each operand per pass, float4 along the channel axis, warp-shuffle-free
+// column reductions (threads own channels, so no cross-lane traffic until the 8-row smem fold).
+#include "common.cuh"
+
+#define CN_FLAG_LRELU_A 1   // a := lrelu(a, alpha) before use
+#define CN_FLAG_MASK_OUT 2  // affine result *= lrelu'(a_raw)
+#define CN_FLAG_MASK_C 4    // c := c * lrelu'(a_raw)
+
+__device__ __forceinline__ float lrelu_f(float v, float alpha) { return v > 0.f ? v : v * alpha; }
+__device__ __forceinline__ float lrelu_d(float v, float alpha) { return v > 0.f ? 1.f : alpha; }
+
+// grid: (ceil(ch/32), n, psplit)  block: (32, 8).  sums must be zero-filled (atomicAdd of block partials).
+template <int NT>
+__global__ void chan_sums_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                 int p, int ch, int flags, float alpha, float* __restrict__ sums) {
+  __shared__ float sm[7][8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int n = blockIdx.y;
+  float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < ch) {
+    const int per = (p + gridDim.z - 1) / gridDim.z;
+    const int pbeg = blockIdx.z * per, pend = min(p, pbeg + per);
+    const size_t base = (size_t)n * p * ch + col;
+    for (int r = pbeg + threadIdx.y; r < pend; r += 8) {
+      const size_t i = base + (size_t)r * ch;
+      float araw = a[i];
+      float av = (flags & CN_FLAG_LRELU_A) ? lrelu_f(araw, alpha) : araw;
+      s[0] += av; s[3] += av * av;
+      if (NT >= 2) { float bv = b[i]; s[1] += bv; s[4] += av * bv;
+        if (NT >= 3) { float cv = c[i]; if (flags & CN_FLAG_MASK_C) cv *= lrelu_d(araw, alpha);
+          s[2] += cv; s[5] += av * cv; s[6] += bv * cv; } }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 7; ++j) sm[j][threadIdx.y][threadIdx.x] = s[j];
+  __syncthreads();
+  if (threadIdx.y < 7 && col < ch) {
+    const int j = threadIdx.y;
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[j][i][threadIdx.x];
+    atomicAdd(sums + ((size_t)n * ch + col) * 7 + j, t);
+  }
+}
+
+extern "C" int cn_chan_sums(const float* a, const float* b, const float* c, int n, int p, int ch,
+                            int flags, float alpha, float* sums, void* stream) {
+  CN_REQUIRE(a && sums && n > 0 && p > 0 && ch > 0, CN_ERR_BAD_SHAPE, "cn_chan_sums: bad arguments");
+  CN_REQUIRE(!(c && !b), CN_ERR_BAD_SHAPE, "cn_chan_sums: c given without b");
+  cudaStream_t st = (cudaStream_t)stream;
+  CN_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)n * ch * 7 * sizeof(float), st));
+  int cb = (ch + 31) / 32;
+  int psplit = (4 * 148 + cb * n - 1) / (cb * n);
+  int maxsplit = (p + 63) / 64;
+  if (psplit > maxsplit) psplit = maxsplit;
+  if (psplit < 1) psplit = 1;
+  dim3 grid(cb, n, psplit), block(32, 8);
+  if (c) chan_sums_kernel<3><<<grid, block, 0, st>>>(a, b, c, p, ch, flags, alpha, sums);
+  else if (b) chan_sums_kernel<2><<<grid, block, 0, st>>>(a, b, c, p, ch, flags, alpha, sums);
+  else chan_sums_kernel<1><<<grid, block, 0, st>>>(a, b, c, p, ch, flags, alpha, sums);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
+// out[n,r,ch] = (ka*a + kb*b + kc*c + k0) [* lrelu'(a_raw)], coef (n, ch, 4)
+template <int VEC>
+__global__ void chan_affine_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                   const float4* __restrict__ coef, int p, int ch, int flags, float alpha,
+                                   float* __restrict__ out, size_t total_vec) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const int chv = ch / VEC;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += stride) {
+    const int cv = (int)(v % chv);
+    const size_t n = v / ((size_t)chv * p);
+    const size_t i = v * VEC;
+    float av[VEC], bv[VEC], cvv[VEC], ov[VEC];
+    if (VEC == 4) {
+      float4 t = *reinterpret_cast<const float4*>(a + i); av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
+      if (b) { t = *reinterpret_cast<const float4*>(b + i); bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w; }
+      if (c) { t = *reinterpret_cast<const float4*>(c + i); cvv[0] = t.x; cvv[1] = t.y; cvv[2] = t.z; cvv[3] = t.w; }
+    } else {
+      av[0] = a[i]; if (b) bv[0] = b[i]; if (c) cvv[0] = c[i];
+    }
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      const float4 k = coef[n * ch + cv * VEC + q];
+      const float araw = av[q];
+      const float aa = (flags & CN_FLAG_LRELU_A) ? lrelu_f(araw, alpha) : araw;
+      float r = fmaf(k.x, aa, k.w);
+      if (b) r = fmaf(k.y, bv[q], r);
+      if (c) { float cc = cvv[q]; if (flags & CN_FLAG_MASK_C) cc *= lrelu_d(araw, alpha); r = fmaf(k.z, cc, r); }
+      if (flags & CN_FLAG_MASK_OUT) r *= lrelu_d(araw, alpha);
+      ov[q] = r;
+    }
+    if (VEC == 4) *reinterpret_cast<float4*>(out + i) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    else out[i] = ov[0];
+  }
+}
+
+extern "C" int cn_chan_affine(const float* a, const float* b, const float* c, const float* coef,
+                              int n, int p, int ch, int flags, float alpha, float* out, void* stream) {
+  CN_REQUIRE(a && coef && out && n > 0 && p > 0 && ch > 0, CN_ERR_BAD_SHAPE, "cn_chan_affine: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)n * p * ch;
+  if (ch % 4 == 0) {
+    size_t tv = total / 4;
+    int blocks = (int)((tv + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    chan_affine_kernel<4><<<blocks, 256, 0, st>>>(a, b, c, (const float4*)coef, p, ch, flags, alpha, out, tv);
+  } else {
+    int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    chan_affine_kernel<1><<<blocks, 256, 0, st>>>(a, b, c, (const float4*)coef, p, ch, flags, alpha, out, total);
+  }
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Coefficient kernels: one thread per channel, loop over samples (so per-channel parameter
+// gradients need no second reduction).  S(n,c,j) = sums[(n*ch+c)*7+j], N = pixels per sample.
+// ------------------------------------------------------------------------------------------------
+enum {
+  CN_COEF_IN_FWD = 0,       // p0=gamma p1=beta            -> coef0
+  CN_COEF_IN_BWD = 1,       // sums(a,gy) p0=gamma         -> coef0 (input grad), out0=ggamma[c], out1=gbeta[c]
+  CN_COEF_IN_BWDBWD = 2,    // sums(a,gy,h) p0=gamma       -> coef0 (d/da), coef1 (d/dgy), out0=ggamma[c]
+  CN_COEF_STYLE_FWD = 3,    // sums(a)                     -> out0 = style (n,2ch)
+  CN_COEF_STYLE_BWD = 4,    // sums(a) p0=gstyle (n,2ch)   -> coef0
+  CN_COEF_STYLE_BWDBWD = 5, // sums(a,-,h)[b slot=h] p0=gstyle -> coef0 (d/da), out0 = d/dgstyle (n,2ch)
+  CN_COEF_ADAIN_FWD = 6,    // sums(a) p0=sb (n,2ch)       -> coef0
+  CN_COEF_ADAIN_BWD = 7,    // sums(a,gy) p0=sb            -> coef0, out0 = gsb (n,2ch)
+};
+
+__global__ void norm_coef_kernel(int kind, const float* __restrict__ sums, const float* __restrict__ p0,
+                                 const float* __restrict__ p1, int n, int ch, float N, float eps,
+                                 float4* __restrict__ coef0, float4* __restrict__ coef1,
+                                 float* __restrict__ out0, float* __restrict__ out1) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ch) return;
+  const float invN = 1.f / N;
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const float* S = sums + ((size_t)i * ch + c) * 7;
+    const size_t nc = (size_t)i * ch + c;
+    const float mu = S[0] * invN;
+    float var = S[3] * invN - mu * mu;
+    if (var < 0.f) var = 0.f;
+    switch (kind) {
+      case CN_COEF_IN_FWD: {
+        float d = sqrtf(var) + eps, g = p0[c];
+        coef0[nc] = make_float4(g / d, 0.f, 0.f, p1[c] - mu * g / d);
+      } break;
+      case CN_COEF_IN_BWD: {
+        float s = sqrtf(var), d = s + eps, g = p0[c];
+        float m1 = S[1] * invN, m2 = S[4] * invN - mu * m1;            // mean(gy), mean(gy*xc)
+        float ka = (s > 0.f) ? -g * m2 / (s * d * d) : 0.f;
+        coef0[nc] = make_float4(ka, g / d, 0.f, -g * m1 / d - ka * mu);
+        acc0 += N * m2 / d;                                            // sum gy*xhat
+        acc1 += S[1];
+      } break;
+      case CN_COEF_IN_BWDBWD: {
+        float s = sqrtf(var), d = s + eps, g = p0[c];
+        float m1 = S[1] * invN, mh = S[2] * invN;
+        float m2 = S[4] * invN - mu * m1, mh2 = S[5] * invN - mu * mh;  // mean(gy*xc), mean(h*xc)
+        float Ab = S[6] * invN - m1 * mh;                                // mean(h*gy) - mh*m1
+        float cx = 0.f, cg = 0.f, chh = 0.f, kb = 0.f;
+        if (s > 0.f) {
+          float isd2 = 1.f / (s * d * d);
+          cx = -g * Ab * isd2 + g * m2 * mh2 * (d + 2.f * s) / (s * s * s * d * d * d);
+          cg = -g * mh2 * isd2;
+          chh = -g * m2 * isd2;
+          kb = -g * mh2 * isd2;
+        }
+        coef0[nc] = make_float4(cx, cg, chh, -cx * mu - cg * m1 - chh * mh);
+        coef1[nc] = make_float4(kb, 0.f, g / d, -g * mh / d - kb * mu);
+        acc0 += N * (Ab / d - ((s > 0.f) ? m2 * mh2 / (s * d * d) : 0.f));
+      } break;
+      case CN_COEF_STYLE_FWD: {
+        out0[(size_t)i * 2 * ch + c] = mu;
+        out0[(size_t)i * 2 * ch + ch + c] = sqrtf(var + eps);
+      } break;
+      case CN_COEF_STYLE_BWD: {
+        float sd = sqrtf(var + eps);
+        float gm = p0[(size_t)i * 2 * ch + c], gs = p0[(size_t)i * 2 * ch + ch + c];
+        float ka = gs * invN / sd;
+        coef0[nc] = make_float4(ka, 0.f, 0.f, gm * invN - ka * mu);
+      } break;
+      case CN_COEF_STYLE_BWDBWD: {
+        float sd = sqrtf(var + eps);
+        float gs = p0[(size_t)i * 2 * ch + ch + c];
+        float mh = S[1] * invN, mhx = S[4] * invN - mu * mh;            // mean(h), mean(h*xc)
+        float ka = -gs * mhx * invN / (sd * sd * sd), kb = gs * invN / sd;
+        coef0[nc] = make_float4(ka, kb, 0.f, -kb * mh - ka * mu);
+        out0[(size_t)i * 2 * ch + c] = mh;
+        out0[(size_t)i * 2 * ch + ch + c] = mhx / sd;
+      } break;
+      case CN_COEF_ADAIN_FWD: {
+        float r = rsqrtf(var + eps);
+        float sc = p0[(size_t)i * 2 * ch + c], bi = p0[(size_t)i * 2 * ch + ch + c];
+        float ka = r * (1.f + sc);
+        coef0[nc] = make_float4(ka, 0.f, 0.f, bi - mu * ka);
+      } break;
+      case CN_COEF_ADAIN_BWD: {
+        float r = rsqrtf(var + eps);
+        float sc = p0[(size_t)i * 2 * ch + c];
+        float m1 = S[1] * invN, m2 = S[4] * invN - mu * m1;            // mean(gy), mean(gy*xc)
+        float A = r * (1.f + sc);
+        float ka = -A * r * r * m2;
+        coef0[nc] = make_float4(ka, A, 0.f, -A * m1 - ka * mu);
+        out0[(size_t)i * 2 * ch + c] = N * m2 * r;                      // d/ds = sum gy*xhat
+        out0[(size_t)i * 2 * ch + ch + c] = S[1];                       // d/db = sum gy
+      } break;
+    }
+  }
+  if (kind == CN_COEF_IN_BWD) { out0[c] = acc0; out1[c] = acc1; }
+  if (kind == CN_COEF_IN_BWDBWD) { out0[c] = acc0; }
+}
+
+extern "C" int cn_norm_coef(int kind, const float* sums, const float* p0, const float* p1, int n, int ch,
+                            int npix, float eps, float* coef0, float* coef1, float* out0, float* out1,
+                            void* stream) {
+  CN_REQUIRE(kind >= 0 && kind <= 7 && sums && n > 0 && ch > 0 && npix > 0, CN_ERR_BAD_SHAPE, "cn_norm_coef: bad arguments");
+  norm_coef_kernel<<<(ch + 63) / 64, 64, 0, (cudaStream_t)stream>>>(kind, sums, p0, p1, n, ch, (float)npix, eps,
+                                                                     (float4*)coef0, (float4*)coef1, out0, out1);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}

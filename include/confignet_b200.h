@@ -1,0 +1,138 @@
+/*
+ * confignet_b200.h - C ABI of libconfignet_b200.so (sm_100a only).
+ *
+ * The reference (microsoft/ConfigNet) has no FFI: its hot path is Keras layers -> TF 2.1 eager
+ * ops -> cuDNN/cuBLAS/Eigen kernels.  Every entry point below replaces one of those implicit
+ * kernel call sites; the "replaces" comment names the reference line that triggers it.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative CN_ERR_* code; cn_last_error() gives a
+ *     thread-local message.  Nothing throws, nothing falls back to the CPU.
+ *   - all tensor pointers are DEVICE pointers owned by the caller, fp32, channels-last
+ *     (NHWC / NDHWC), Keras kernel layouts ((k..., Cin, Cout), Dense (in, out)).
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous on it.
+ *   - TF "SAME" padding is computed inside from the descriptor.
+ */
+#ifndef CONFIGNET_B200_H
+#define CONFIGNET_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CN_OK 0
+#define CN_ERR_BAD_SHAPE (-1)
+#define CN_ERR_BAD_ALIGN (-2)
+#define CN_ERR_UNSUPPORTED (-3)
+#define CN_ERR_CUDA (-4)
+
+/* activation codes for fused epilogues */
+#define CN_ACT_NONE 0
+#define CN_ACT_LRELU 1
+#define CN_ACT_RELU 2
+#define CN_ACT_TANH 3
+
+/* kernel selection for the conv / dense family */
+#define CN_IMPL_AUTO 0   /* tcgen05 tensor-core kernel where the shape allows, else CUDA-core */
+#define CN_IMPL_FFMA 1   /* force the fp32 CUDA-core implicit GEMM */
+#define CN_IMPL_TC 2     /* force tcgen05 (error if the shape is not eligible) */
+
+const char* cn_last_error(void);
+int cn_version(void);
+
+/* Convolution geometry.  nd = 0 describes a Dense layer (batch rows, cin -> cout). */
+typedef struct {
+  int nd;          /* spatial dims: 0 (dense), 2 (Conv2D), 3 (Conv3D)                        */
+  int batch;
+  int in_dims[3];  /* spatial size of x BEFORE the fused upsample; unused entries = 1        */
+  int cin, cout;
+  int ksize[3];    /* unused entries = 1                                                     */
+  int stride;      /* 1 or 2, same on every axis                                             */
+  int upsample;    /* 1, or 2 = nearest-neighbour x2 (UpSampling2D/3D) fused on the input    */
+} cn_conv_desc;
+
+/* y spatial dims for `d` (TF SAME: ceil(in*upsample/stride)). */
+int cn_conv_out_dims(const cn_conv_desc* d, int out_dims[3]);
+
+/* y = act(conv_same(upsample(x), w) + bias).
+ * replaces keras.layers.Conv2D/Conv3D/Dense __call__: building_blocks.py:28-30,64-66,91,
+ * hologan_generator.py:24,50-56,101, hologan_discriminator.py:20,34,46,77,97,
+ * perceptual_loss.py:19-24 (VGG convs + ReLU), UpSampling hologan_generator.py:139-170. */
+int cn_conv_fwd(const cn_conv_desc* d, const float* x, const float* w, const float* bias,
+                int act, float alpha, float* y, int impl, void* stream);
+/* gx = d<gy, conv(x,w)>/dx  (x-shaped, i.e. before the fused upsample).
+ * replaces the Conv*BackpropInput ops tf.GradientTape emits (confignet_first_stage.py:472,556). */
+int cn_conv_dgrad(const cn_conv_desc* d, const float* gy, const float* w, float* gx,
+                  int impl, void* stream);
+/* gw = d<gy, conv(x,w)>/dw (overwrites gw, Keras layout); gbias (may be NULL) = column sums of gy.
+ * replaces Conv*BackpropFilter / BiasAddGrad. */
+int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float* gy, float* gw,
+                  float* gbias, int impl, void* stream);
+
+/* ---- per-(sample,channel) reductions and broadcasts over the spatial axes (NHWC) --------------
+ * replaces tf.nn.moments / K.mean / K.std and the broadcast arithmetic inside
+ * LayerNormalization (building_blocks.py:132-149), InstanceNormalization
+ * (instance_normalization.py:108-131) and get_layer_style (confignet_utils.py:147-159),
+ * and every term of their first- and second-order gradients. */
+/* sums[(n*C + c)*7 + j] over the P pixels of sample n:
+ *   j: 0 sum a, 1 sum b, 2 sum c, 3 sum a*a, 4 sum a*b, 5 sum a*c, 6 sum b*c  (b, c may be NULL) */
+int cn_chan_sums(const float* a, const float* b, const float* c, int n, int p, int ch,
+                 float* sums, void* stream);
+/* out = ka[n,c]*a + kb[n,c]*b + kc[n,c]*c + k0[n,c]; coef is (n, ch, 4) = (ka,kb,kc,k0).
+ * mode 0: plain.  mode 1: a is replaced by lrelu(a, alpha) before use.
+ * mode 2: result multiplied by lrelu'(mask_src, alpha) where mask_src = c and kc is ignored. */
+int cn_chan_affine(const float* a, const float* b, const float* c, const float* coef,
+                   int n, int p, int ch, int mode, float alpha, float* out, void* stream);
+
+/* elementwise helpers on flat fp32 buffers */
+int cn_lrelu_fwd(const float* x, float alpha, float* y, int64_t n, void* stream);
+/* gx = gy * (ref > 0 ? 1 : alpha); ref may be the pre- or post-activation tensor */
+int cn_lrelu_bwd(const float* gy, const float* ref, float alpha, float* gx, int64_t n, void* stream);
+/* act-specific backward from the OUTPUT y: relu, tanh (1-y^2), lrelu */
+int cn_act_bwd(const float* gy, const float* y, int act, float alpha, float* gx, int64_t n, void* stream);
+int cn_axpby(const float* x, const float* y, float a, float b, float* out, int64_t n, void* stream);
+
+/* 2x2/s2 VALID max-pool, NHWC (VGG pools, perceptual_loss.py:19-24) and its backward
+ * (gradient goes to the first maximum in window scan order, as TF's MaxPoolGrad). */
+int cn_maxpool2_fwd(const float* x, int n, int h, int w, int c, float* y, void* stream);
+int cn_maxpool2_bwd(const float* x, const float* y, const float* gy, int n, int h, int w, int c,
+                    float* gx, void* stream);
+
+/* transform_3d_grid_tf (confignet_utils.py:63-120): trilinear resample of (B,S,S,S,C) under a
+ * per-sample 3x3 matrix `rot` (B,9) about the volume centre, clamp-to-edge. */
+int cn_rotate3d_fwd(const float* grid, const float* rot, int b, int s, int c, float* out, void* stream);
+/* gradient wrt the grid (scatter-add; ggrid must be zero-filled by the caller) */
+int cn_rotate3d_bwd_grid(const float* gout, const float* rot, int b, int s, int c, float* ggrid, void* stream);
+/* gradient wrt the 3x3 matrix entries (B,9) (through `diffs` only, as tf.floor has zero gradient) */
+int cn_rotate3d_bwd_rot(const float* grid, const float* gout, const float* rot, int b, int s, int c,
+                        float* grot, void* stream);
+
+/* loss reductions (losses.py:7-18, perceptual_loss.py:76-80): deterministic two-stage sums.
+ * kind 0: sum softplus(sign*x)   kind 1: sum (x-y)^2   kind 2: sum x^2   kind 3: sum x
+ * result[0] = scale * sum.  ws must hold cn_reduce_ws_floats() floats. */
+int cn_reduce_ws_floats(void);
+int cn_reduce(const float* x, const float* y, int64_t n, int kind, float sign, float scale,
+              float* ws, float* result, void* stream);
+/* gx = gscale[0] * k * d(kind)/dx ; kind 0: sign*sigmoid(sign*x), kind 1: 2(x-y), kind 2: 2x */
+int cn_reduce_bwd(const float* x, const float* y, int64_t n, int kind, float sign, float k,
+                  const float* gscale, float* gx, void* stream);
+
+/* images: (x+1)*127.5 clipped to [0,255], truncated to uint8 (confignet_first_stage.py:636-637) */
+int cn_to_uint8(const float* x, uint8_t* out, int64_t n, void* stream);
+/* uint8 -> float /127.5 - 1 (confignet_first_stage.py:444, confignet_second_stage.py:303) */
+int cn_from_uint8(const uint8_t* x, float* out, int64_t n, void* stream);
+/* VGG 'caffe' preprocessing of [-1,1] RGB(BGR-flipped) images: out[..., c] = (x[..., 2-c]+1)*127.5 - mean[c]
+ * (perceptual_loss.py:50-59); bwd maps the gradient back. */
+int cn_vgg_preprocess(const float* x, float* out, int64_t npix, int backward, void* stream);
+
+/* Keras Adam + EMA over a flat parameter buffer (confignet_first_stage.py:393-400,601-602):
+ * m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr_t * m / (sqrt(v) + eps);
+ * if ema != NULL: ema = ema_alpha*ema + (1-ema_alpha)*p.  g is multiplied by gscale first. */
+int cn_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
+                     float lr_t, float b1, float b2, float eps, float ema_alpha, float gscale,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
