@@ -50,25 +50,27 @@ SIGNATURES = {
     "cn_conv_fwd": [_D, _V, _V, _V, _I, _f, _V, _I, _V],
     "cn_conv_dgrad": [_D, _V, _V, _V, _I, _V],
     "cn_conv_wgrad": [_D, _V, _V, _V, _V, _I, _V],
-    "cn_chan_sums": [_V, _V, _V, _I, _I, _I, _V, _V],
+    "cn_chan_sums": [_V, _V, _V, _I, _I, _I, _I, _f, _V, _V],
     "cn_chan_affine": [_V, _V, _V, _V, _I, _I, _I, _I, _f, _V, _V],
+    "cn_norm_coef": [_I, _V, _V, _V, _I, _I, _I, _f, _V, _V, _V, _V, _V],
     "cn_lrelu_fwd": [_V, _f, _V, _L, _V],
-    "cn_lrelu_bwd": [_V, _V, _f, _V, _L, _V],
     "cn_act_bwd": [_V, _V, _I, _f, _V, _L, _V],
     "cn_axpby": [_V, _V, _f, _f, _V, _L, _V],
     "cn_maxpool2_fwd": [_V, _I, _I, _I, _I, _V, _V],
     "cn_maxpool2_bwd": [_V, _V, _V, _I, _I, _I, _I, _V, _V],
     "cn_rotate3d_fwd": [_V, _V, _I, _I, _I, _V, _V],
     "cn_rotate3d_bwd_grid": [_V, _V, _I, _I, _I, _V, _V],
-    "cn_rotate3d_bwd_rot": [_V, _V, _V, _I, _I, _I, _V, _V],
-    "cn_reduce": [_V, _V, _L, _I, _f, _f, _V, _V, _V],
-    "cn_reduce_bwd": [_V, _V, _L, _I, _f, _f, _V, _V, _V],
+    "cn_reduce": [_V, _V, _V, _I, _L, _I, _f, _f, _V, _V, _V],
+    "cn_reduce_bwd": [_V, _V, _V, _I, _L, _I, _f, _f, _V, _V, _V],
     "cn_to_uint8": [_V, _V, _L, _V],
     "cn_from_uint8": [_V, _V, _L, _V],
     "cn_vgg_preprocess": [_V, _V, _L, _I, _V],
     "cn_adam_ema_step": [_V, _V, _V, _V, _V, _L, _f, _f, _f, _f, _f, _f, _V],
+    "cn_ema": [_V, _V, _L, _f, _V],
+    "cn_multi_copy": [_I, _V, _V, _V, _V, _V],
 }
-NO_STATUS = {"cn_last_error": ctypes.c_char_p, "cn_version": ctypes.c_int, "cn_reduce_ws_floats": ctypes.c_int}
+NO_STATUS = {"cn_last_error": ctypes.c_char_p, "cn_version": ctypes.c_int, "cn_reduce_ws_floats": ctypes.c_int,
+             "cn_launch_count": ctypes.c_longlong, "cn_last_conv_impl": ctypes.c_int}
 
 _lib = None
 

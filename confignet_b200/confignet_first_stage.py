@@ -1,0 +1,537 @@
+"""ConfigNetFirstStage on B200: the class surface of the reference
+(confignet/confignet_first_stage.py:86-679) over our CUDA networks.
+
+Same constructor / config merging / latent layout / method names / loss-dictionary keys, NumPy in and
+NumPy out at the public boundary, so train_confignet.py-style callers work unchanged.  What differs is
+underneath: every network call is a sequence of launches of libconfignet_b200.so, the optimizer is one
+fused kernel per network over a flat buffer, the EMA stays on the device, and with torch.distributed
+initialised each step all-reduces its flat gradient buffer over NCCL.
+
+Out of scope here: TensorBoard/AzureML logging, image and metric
+checkpoints.  ``train`` keeps the reference loop structure and loss history only.
+"""
+import os
+import json
+import pickle
+import time
+from collections import OrderedDict
+import numpy as np
+import torch
+
+from . import netspec, networks, ops
+from .runtime import ParamGroup, Network, KerasAdam, allreduce_grads, shard_rows, world
+
+DEFAULT_CONFIG = {
+    "model_type": None,
+    "latent_dim": 128,
+    "output_shape": (128, 128, 3),
+    "const_input_shape": (4, 4, 4, 512),
+    "n_adain_mlp_layers": 2,
+    "n_adain_mlp_units": 128,
+    "gen_output_activation": "tanh",
+    "n_discr_features_at_layer_0": 48,
+    "max_discr_filters": 512,
+    "n_discr_layers": 5,
+    "discr_conv_kernel_size": 3,
+    "latent_regression_weight": 10.0,
+    "use_style_discriminator": True,
+    "rotation_ranges": ((-30, 30), (-10, 10), (0, 0)),
+    "relu_before_in": True,
+    "initial_from_rgb_layer_in_discr": True,
+    "adain_on_learned_input": False,
+    "latent_regressor_rot_weight": 5.0,
+    "optimizer": {"lr": 0.0004, "beta_1": 0.0, "beta_2": 0.9, "amsgrad": False},
+    "batch_size": 24,
+    "n_discriminator_updates": 1,
+    "n_generator_updates": 1,
+    "latent_distribution": "normal",
+    "metrics_checkpoint_period": 1000,
+    "image_checkpoint_period": 500,
+    "facemodel_inputs": {
+        "texture_embedding": (None, 30),
+        "geometry_identity_params": (None, 30),
+        "blendshape_values": (None, 30),
+        "beard_style_embedding": (None, 7),
+        "eyebrow_style_embedding": (None, 7),
+        "lower_eyelash_style": (None, 2),
+        "upper_eyelash_style": (None, 2),
+        "head_hair_style_embedding": (None, 9),
+        "eye_color": (None, 3),
+        "head_hair_color": (None, 3),
+        "hdri_embedding": (None, 20),
+        "bone_rotations:left_eye": (None, 2),
+    },
+    "num_synth_encoder_layers": 2,
+    "n_latent_discr_layers": 4,
+    "image_loss_weight": 0.00005,
+    "eye_loss_weight": 5,
+    "domain_adverserial_loss_weight": 5.0,
+}
+
+
+def merge_configs(default_config, input_config):
+    """confignet_utils.py:39-61 (recursive dictionary merge, input wins)."""
+    result = {}
+    for name in default_config:
+        lhs = default_config[name]
+        if name in input_config:
+            rhs = input_config[name]
+            if isinstance(lhs, dict):
+                assert isinstance(rhs, dict)
+                result[name] = merge_configs(lhs, rhs)
+            else:
+                result[name] = rhs
+        else:
+            result[name] = lhs
+    for name in input_config:
+        rhs = input_config[name]
+        if isinstance(rhs, dict) and name in default_config.keys():
+            continue
+        result[name] = rhs
+    return result
+
+
+def update_loss_dict(main_loss_dict, new_loss_dict):
+    """confignet_utils.py:206-212."""
+    for key, val in new_loss_dict.items():
+        val = float(val)
+        main_loss_dict.setdefault(key, []).append(val)
+
+
+def flip_random_subset_of_images(images):
+    """confignet_utils.py:198-204 (same NumPy RNG consumption; flips a copy view per image)."""
+    flip_or_not = np.random.randint(0, 2, size=images.shape[0])
+    for i, flip in enumerate(flip_or_not):
+        if flip == 1:
+            images[i] = np.fliplr(images[i])
+    return images
+
+
+class _PerParamMLP:
+    """synthetic_encoder.per_facemodel_input_mlps[name] (synthetic_encoder.py:19-30): ``predict`` + ``num_in``."""
+
+    def __init__(self, owner, name, num_in, num_layers):
+        self.owner, self.name, self.num_in, self.num_layers = owner, name, num_in, num_layers
+
+    def __call__(self, x):
+        x = networks._as_dev(x, self.owner.group.device)
+        return networks.mlp_fused(x, self.owner.group.params, "mlp_" + self.name, self.num_layers, alpha=0.3)
+
+    def predict(self, x):
+        with torch.no_grad():
+            return self(x).cpu().numpy()
+
+
+class SyntheticEncoderNet(Network):
+    def __init__(self, group, facemodel_inputs, num_layers):
+        super().__init__(group, networks.synthetic_encoder_forward, facemodel_inputs=facemodel_inputs, num_layers=num_layers)
+        self.facemodel_param_names = list(facemodel_inputs.keys())
+        self.per_facemodel_input_mlps = {n: _PerParamMLP(self, n, facemodel_inputs[n][0], num_layers)
+                                         for n in self.facemodel_param_names}
+
+    def __call__(self, inputs):
+        dev = self.group.device
+        if isinstance(inputs, dict):
+            inputs = [inputs[n] for n in self.facemodel_param_names]
+        if isinstance(inputs, (list, tuple)):
+            inputs = [networks._as_dev(x, dev) for x in inputs]
+        else:
+            inputs = networks._as_dev(inputs, dev)
+        return super().__call__(inputs)
+
+
+class GeneratorNet(Network):
+    def build_input_dict(self, latent_vector, rotation):
+        """hologan_generator.py:109-127."""
+        d = {}
+        zs = latent_vector if isinstance(latent_vector, list) else [latent_vector] * 5
+        for k, z in zip(("z_3d_0", "z_3d_1", "z_2d_0", "z_2d_1", "z_2d_2"), zs):
+            d[k] = z
+        d["rotation"] = rotation
+        return d
+
+    def __call__(self, inputs):
+        if not isinstance(inputs, dict):
+            inputs = self.build_input_dict(inputs[0], inputs[1])
+        dev = self.group.device
+        zs = [networks._as_dev(inputs[k], dev) for k in ("z_3d_0", "z_3d_1", "z_2d_0", "z_2d_1", "z_2d_2")]
+        return super().__call__(None, inputs["rotation"], zs=zs)
+
+
+class ConfigNetFirstStage:
+    def __init__(self, config, initialize=True, device=None, seed=1234):
+        self.config = merge_configs(DEFAULT_CONFIG, config)
+        self.config["model_type"] = "ConfigNetFirstStage"
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self._seed = seed
+
+        self.generator = None
+        self.generator_smoothed = None
+        self.discriminator = None
+        self.latent_regressor = None
+        self.latent_discriminator = None
+        self.synth_discriminator = None
+        self.synthetic_encoder = None
+        self.perceptual_loss = None
+
+        self.g_losses, self.d_losses, self.metrics = {}, {}, {}
+        self.synth_d_losses, self.latent_d_losses = {}, {}
+        self.n_checkpoint_rotations = 6
+        self.n_checkpoint_samples = 10
+
+        # confignet_first_stage.py:114-120
+        self.config["facemodel_inputs"] = {k: tuple(v) for k, v in self.config["facemodel_inputs"].items() if v[0] is not None}
+        self.config["facemodel_inputs"] = OrderedDict(sorted(self.config["facemodel_inputs"].items(), key=lambda t: t[0]))
+        self.config["latent_dim"] = 0
+        for spec in self.config["facemodel_inputs"]:
+            self.config["latent_dim"] += self.config["facemodel_inputs"][spec][1]
+        self.facemodel_param_distributions = None
+        if initialize:
+            self.initialize_network()
+
+    # ---------------------------------------------------------------- construction
+    def _discr_args(self):
+        c = self.config
+        return dict(output_res=c["output_shape"][0], n_layers=c["n_discr_layers"], base=c["n_discr_features_at_layer_0"],
+                    max_maps=c["max_discr_filters"], ksize=c["discr_conv_kernel_size"],
+                    from_rgb=c["initial_from_rgb_layer_in_discr"])
+
+    def _make_group(self, spec, seed, vgg_like=False):
+        return ParamGroup(netspec.init_params(spec, seed, vgg_like=vgg_like), self.device)
+
+    def initialize_network(self):
+        """confignet_first_stage.py:251-287."""
+        c = self.config
+        s = self._seed
+        res = c["output_shape"][0]
+        nl = c["n_discr_layers"]
+        self.synthetic_encoder = SyntheticEncoderNet(
+            self._make_group(netspec.synthetic_encoder_spec(c["facemodel_inputs"], c["num_synth_encoder_layers"]), s + 1),
+            c["facemodel_inputs"], c["num_synth_encoder_layers"])
+        self.discriminator = Network(self._make_group(netspec.discriminator_spec(**self._discr_args()), s + 2),
+                                     networks.discriminator_forward, n_layers=nl)
+        self.synth_discriminator = Network(self._make_group(netspec.discriminator_spec(**self._discr_args()), s + 3),
+                                           networks.discriminator_forward, n_layers=nl)
+        self.latent_discriminator = Network(
+            self._make_group(netspec.latent_discriminator_spec(c["latent_dim"], c["n_latent_discr_layers"]), s + 4),
+            networks.latent_discriminator_forward, n_layers=c["n_latent_discr_layers"])
+        self.latent_regressor = Network(
+            self._make_group(netspec.latent_regressor_spec(c["latent_dim"], **self._discr_args()), s + 5),
+            networks.latent_regressor_forward, n_layers=nl)
+        gspec = netspec.generator_spec(c["latent_dim"], res, c["n_adain_mlp_units"], c["n_adain_mlp_layers"])
+        gkw = dict(output_res=res, n_mlp_layers=c["n_adain_mlp_layers"])
+        self.generator = GeneratorNet(self._make_group(gspec, s + 6), networks.generator_forward, **gkw)
+        self.generator_smoothed = GeneratorNet(self._make_group(gspec, s + 6), networks.generator_forward, **gkw)
+        self.generator_smoothed.group.copy_from(self.generator.group)
+        # VGG19 (perceptual_loss.py:19-24).  Pretrained ImageNet weights cannot be downloaded offline:
+        # seeded He-normal weights stand in; load real ones with perceptual_loss.set_weights().
+        self.perceptual_loss = Network(self._make_group(netspec.vgg19_spec(), s + 7, vgg_like=True),
+                                       networks.vgg19_activations)
+        for v in self.perceptual_loss.group.params.values():
+            v.requires_grad_(False)
+
+    # ---------------------------------------------------------------- weights / io
+    def get_weights(self, return_tensors=False):
+        """confignet_first_stage.py:129-140."""
+        w = {}
+        w["generator_weights"] = self.generator.get_weights()
+        w["generator_smoothed_weights"] = self.generator_smoothed.get_weights()
+        w["discriminator_weights"] = self.discriminator.get_weights()
+        w["latent_regressor_weights"] = self.latent_regressor.get_weights()
+        w["synthetic_encoder_weights"] = self.synthetic_encoder.get_weights()
+        w["latent_discriminator_weights"] = self.latent_discriminator.get_weights()
+        w["synth_discriminator_weights"] = self.synth_discriminator.get_weights()
+        return w
+
+    def set_weights(self, weights):
+        self.generator.set_weights(weights["generator_weights"])
+        self.generator_smoothed.set_weights(weights["generator_smoothed_weights"])
+        self.discriminator.set_weights(weights["discriminator_weights"])
+        self.latent_regressor.set_weights(weights["latent_regressor_weights"])
+        self.synthetic_encoder.set_weights(weights["synthetic_encoder_weights"])
+        self.latent_discriminator.set_weights(weights["latent_discriminator_weights"])
+        self.synth_discriminator.set_weights(weights["synth_discriminator_weights"])
+
+    def get_training_step_number(self):
+        return 0 if "loss_sum" not in self.g_losses else len(self.g_losses["loss_sum"]) - 1
+
+    def get_batch_size(self):
+        return self.config["batch_size"]
+
+    def get_log_dict(self):
+        return {"g_losses": self.g_losses, "d_losses": self.d_losses, "metrics": self.metrics}
+
+    def set_logs(self, log_dict):
+        self.g_losses, self.d_losses, self.metrics = log_dict["g_losses"], log_dict["d_losses"], log_dict["metrics"]
+
+    def save(self, output_dir, output_filename):
+        """confignet_first_stage.py:173-180: <name>.npz (lists of arrays), <name>.json, _facemodel_distr.pck."""
+        weights = {k: np.array(v, dtype=object) for k, v in self.get_weights().items()}
+        np.savez(os.path.join(output_dir, output_filename + ".npz"), **weights)
+        with open(os.path.join(output_dir, output_filename + ".json"), "w") as fp:
+            json.dump(self.config, fp, indent=4)
+        with open(os.path.join(output_dir, output_filename + "_facemodel_distr.pck"), "wb") as fp:
+            pickle.dump(self.facemodel_param_distributions, fp)
+
+    @classmethod
+    def load(cls, file_path, **kw):
+        with open(file_path, "r") as fp:
+            config = json.load(fp)
+        model = cls(config, **kw)
+        weights = np.load(os.path.splitext(file_path)[0] + ".npz", allow_pickle=True)
+        model.set_weights(weights)
+        log_file = os.path.splitext(file_path)[0] + "_log.json"
+        if os.path.exists(log_file):
+            with open(log_file, "r") as fp:
+                model.set_logs(json.load(fp))
+        distr = os.path.splitext(file_path)[0] + "_facemodel_distr.pck"
+        if os.path.exists(distr):
+            with open(distr, "rb") as fp:
+                model.facemodel_param_distributions = pickle.load(fp)
+        else:
+            print("WARNING: facemodel param distributions not loaded")
+        return model
+
+    # ---------------------------------------------------------------- latent layout (integer, bit-exact)
+    @property
+    def facemodel_input_dim(self):
+        return sum(d for d, _ in self.config["facemodel_inputs"].values())
+
+    def get_facemodel_param_idxs_in_latent(self, param_name):
+        """confignet_first_stage.py:217-227."""
+        dims = list(self.config["facemodel_inputs"].values())
+        names = list(self.config["facemodel_inputs"].keys())
+        idx = names.index(param_name)
+        start = int(np.sum([x[1] for x in dims[:idx]]))
+        return range(start, start + dims[idx][1])
+
+    def set_facemodel_param_in_latents(self, latents, param_name, param_value):
+        """confignet_first_stage.py:229-239."""
+        param_value = np.array(param_value)
+        if len(param_value.shape) == 1:
+            param_value = param_value[np.newaxis]
+        latents_for_param = self.synthetic_encoder.per_facemodel_input_mlps[param_name].predict(param_value)
+        idxs = self.get_facemodel_param_idxs_in_latent(param_name)
+        new_latents = np.copy(latents)
+        new_latents[:, idxs] = latents_for_param
+        return new_latents
+
+    # ---------------------------------------------------------------- samplers (host NumPy, reference RNG order)
+    def update_smoothed_weights(self, smoother_alpha=0.999):
+        """confignet_first_stage.py:393-400, on the device (one kernel over the flat buffer)."""
+        ops.ema_update(self.generator_smoothed.group.flat, self.generator.group.flat, smoother_alpha)
+
+    def sample_rotations(self, n_samples, axes=[0, 1, 2]):
+        r = np.zeros((n_samples, 3))
+        for axis in axes:
+            lo, hi = self.config["rotation_ranges"][axis]
+            r[:, axis] = np.pi * np.random.uniform(lo, hi, n_samples) / 180
+        return r.astype(np.float32)
+
+    def sample_latent_vector(self, n_samples):
+        if self.config["latent_distribution"] == "normal":
+            return np.random.normal(0, 1, (n_samples, self.config["latent_dim"]))
+        elif self.config["latent_distribution"] == "uniform":
+            return np.random.uniform(-1, 1, (n_samples, self.config["latent_dim"]))
+
+    def sample_facemodel_params(self, n_samples):
+        return [self.facemodel_param_distributions[n].sample(n_samples)[0] for n in self.config["facemodel_inputs"].keys()]
+
+    def sample_synthetic_dataset(self, dataset, n_samples):
+        """confignet_first_stage.py:425-435.  gt_imgs / eye_masks are returned as uint8 row gathers (host
+        arrays, or device tensors when the dataset lives in HBM); /127.5-1 happens on the device."""
+        idxs = np.random.randint(0, dataset.imgs.shape[0], n_samples)
+        facemodel_params = [dataset.metadata_inputs[n][idxs] for n in self.config["facemodel_inputs"].keys()]
+        render_rotations = dataset.metadata_inputs["rotations"][idxs].astype(np.float32)
+        gt_imgs = self._take_rows(dataset.imgs, idxs)
+        eye_masks = self._take_rows(dataset.eye_masks, idxs)
+        return facemodel_params, render_rotations, gt_imgs, eye_masks
+
+    # ---------------------------------------------------------------- host -> device staging
+    h2d_bytes = 0       # bytes copied host->device by the staging helpers (bench.py reads and resets it)
+
+    def _take_rows(self, store, idxs):
+        if isinstance(store, torch.Tensor):
+            return store[torch.as_tensor(idxs, device=store.device)]
+        return np.copy(store[idxs])
+
+    def _to_device(self, arr, dtype):
+        if isinstance(arr, torch.Tensor):
+            return arr.to(self.device, dtype)
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        ConfigNetFirstStage.h2d_bytes += t.numel() * t.element_size()
+        return t.pin_memory().to(self.device, non_blocking=True).to(dtype)
+
+    def _upload_images(self, imgs_u8, flip=None):
+        """uint8 (B,H,W,3) batch -> float32 [-1,1] device tensor; optional per-image left-right flip."""
+        t = self._to_device(imgs_u8, torch.uint8)
+        if t.dtype != torch.uint8:
+            raise ValueError("image batches are staged as uint8")
+        if flip is not None:
+            f = torch.as_tensor(np.asarray(flip).astype(bool), device=self.device)
+            t = torch.where(f[:, None, None, None], t.flip(2), t)
+        return ops.from_uint8(t)
+
+    def _rank_rows(self, *arrays):
+        """Data parallelism: every rank draws the same global batch from the same NumPy stream and keeps
+        its own row slice."""
+        lo, hi = shard_rows(arrays[0].shape[0]) if world()[1] > 1 else (0, arrays[0].shape[0])
+        return [a[lo:hi] for a in arrays]
+
+    def get_discriminator_batch(self, training_set):
+        """confignet_first_stage.py:438-450."""
+        B = self.get_batch_size()
+        img_idxs = np.random.randint(0, training_set.imgs.shape[0], B)
+        flips = np.random.randint(0, 2, size=B)          # flip_random_subset_of_images' draw (confignet_utils.py:199)
+        latent = self.sample_latent_vector(B).astype(np.float32)
+        rotation = self.sample_rotations(B)
+        img_idxs, flips, latent, rotation = self._rank_rows(img_idxs, flips, latent, rotation)
+        real_imgs = self._upload_images(self._take_rows(training_set.imgs, img_idxs), flips)
+        fake_imgs = self.generator.predict([self._to_device(latent, torch.float32), rotation])
+        return real_imgs, fake_imgs
+
+    def get_synth_discriminator_batch(self, training_set):
+        """confignet_first_stage.py:452-464."""
+        B = self.get_batch_size()
+        img_idxs = np.random.randint(0, training_set.imgs.shape[0], B)
+        flips = np.random.randint(0, 2, size=B)
+        facemodel_params, rotations = self._sample_synth_metadata(training_set, B)
+        sliced = self._rank_rows(img_idxs, flips, rotations, *facemodel_params)
+        img_idxs, flips, rotations, facemodel_params = sliced[0], sliced[1], sliced[2], sliced[3:]
+        real_imgs = self._upload_images(self._take_rows(training_set.imgs, img_idxs), flips)
+        with torch.no_grad():
+            latent = self.synthetic_encoder([self._to_device(a, torch.float32) for a in facemodel_params])
+            fake_imgs = self.generator([latent, rotations])
+        return real_imgs, fake_imgs
+
+    def _sample_synth_metadata(self, dataset, n_samples):
+        """sample_synthetic_dataset when only parameters and rotations are used (same single RNG draw);
+        avoids gathering images that the caller discards (confignet_first_stage.py:460,494)."""
+        idxs = np.random.randint(0, dataset.imgs.shape[0], n_samples)
+        facemodel_params = [dataset.metadata_inputs[n][idxs] for n in self.config["facemodel_inputs"].keys()]
+        return facemodel_params, dataset.metadata_inputs["rotations"][idxs].astype(np.float32)
+
+    # ---------------------------------------------------------------- training steps
+    def _apply(self, optimizer, loss, nets):
+        groups = [n.group for n in nets]
+        params = [p for g in groups for p in g.trainable_weights]
+        grads = torch.autograd.grad(loss, params, allow_unused=True)
+        keep, i = [], 0
+        for g in groups:
+            k = len(g.trainable_weights)
+            keep.append(g.pack_grads(grads[i:i + k]))
+            i += k
+        gscale = allreduce_grads(groups)
+        optimizer.apply_flat(groups, gscale)
+
+    @staticmethod
+    def _detached(losses):
+        """The loss dictionary handed back to the caller holds plain values (the tape is released)."""
+        return OrderedDict((k, v.detach()) for k, v in losses.items())
+
+    def discriminator_training_step(self, training_set, optimizer):
+        real_imgs, fake_imgs = self.get_discriminator_batch(training_set)
+        losses = networks.compute_discriminator_loss(self.discriminator.params, real_imgs, fake_imgs,
+                                                     self.config["n_discr_layers"])
+        self._apply(optimizer, losses["loss_sum"], [self.discriminator])
+        return self._detached(losses)
+
+    def synth_discriminator_training_step(self, synth_training_set, optimizer):
+        real_imgs, fake_imgs = self.get_synth_discriminator_batch(synth_training_set)
+        losses = networks.compute_discriminator_loss(self.synth_discriminator.params, real_imgs, fake_imgs,
+                                                     self.config["n_discr_layers"])
+        self._apply(optimizer, losses["loss_sum"], [self.synth_discriminator])
+        return self._detached(losses)
+
+    def latent_discriminator_training_step(self, synth_training_set, optimizer):
+        B = self.get_batch_size()
+        real_latents = self.sample_latent_vector(B).astype(np.float32)
+        facemodel_params, _ = self._sample_synth_metadata(synth_training_set, B)
+        sliced = self._rank_rows(real_latents, *facemodel_params)
+        real_latents, facemodel_params = sliced[0], sliced[1:]
+        with torch.no_grad():
+            fake_latents = self.synthetic_encoder([self._to_device(a, torch.float32) for a in facemodel_params])
+        losses = networks.compute_latent_discriminator_loss(
+            self.latent_discriminator.params, self._to_device(real_latents, torch.float32), fake_latents,
+            self.config["n_latent_discr_layers"])
+        self._apply(optimizer, losses["loss_sum"], [self.latent_discriminator])
+        return self._detached(losses)
+
+    def generator_training_step(self, real_training_set, synth_training_set, optimizer):
+        """confignet_first_stage.py:506-560."""
+        c = self.config
+        n_synth = self.get_batch_size() // 2
+        n_real = self.get_batch_size() - n_synth
+        idxs = np.random.randint(0, synth_training_set.imgs.shape[0], n_synth)     # sample_synthetic_dataset's draw
+        facemodel_params = [synth_training_set.metadata_inputs[n][idxs] for n in c["facemodel_inputs"].keys()]
+        synth_rot = synth_training_set.metadata_inputs["rotations"][idxs].astype(np.float32)
+        real_latents = self.sample_latent_vector(n_real).astype(np.float32)
+        real_rot = self.sample_rotations(n_real)
+        sliced = self._rank_rows(idxs, synth_rot, *facemodel_params)
+        idxs, synth_rot, facemodel_params = sliced[0], sliced[1], sliced[2:]
+        real_latents, real_rot = self._rank_rows(real_latents, real_rot)
+        gt_imgs = self._upload_images(self._take_rows(synth_training_set.imgs, idxs))
+        eye_masks = self._to_device(self._take_rows(synth_training_set.eye_masks, idxs), torch.float32)
+        real_latents_d = self._to_device(real_latents, torch.float32)
+
+        losses = OrderedDict()
+        synth_latents = self.synthetic_encoder([self._to_device(a, torch.float32) for a in facemodel_params])
+        out_synth = self.generator((synth_latents, synth_rot))
+        out_real = self.generator((real_latents_d, real_rot))
+        losses["image_loss"] = c["image_loss_weight"] * networks.perceptual_loss(self.perceptual_loss.params, gt_imgs, out_synth)
+        losses["eye_loss"] = c["eye_loss_weight"] * networks.eye_loss(gt_imgs, out_synth, eye_masks)
+        for i, o in enumerate(self.synth_discriminator(out_synth).values()):
+            losses["GAN_loss_synth_" + str(i)] = networks.gan_g_loss(o)
+        for i, o in enumerate(self.discriminator(out_real).values()):
+            losses["GAN_loss_real_" + str(i)] = networks.gan_g_loss(o)
+        losses["latent_GAN_loss"] = c["domain_adverserial_loss_weight"] * networks.gan_g_loss(self.latent_discriminator(synth_latents))
+        stacked_latents = torch.cat((synth_latents, real_latents_d), dim=0)
+        stacked_imgs = torch.cat((out_synth, out_real), dim=0)
+        stacked_rot = self._to_device(np.concatenate((synth_rot, real_rot), axis=0), torch.float32)
+        labels = torch.cat((stacked_latents, c["latent_regressor_rot_weight"] * stacked_rot), dim=-1)
+        losses["latent_regression_loss"] = c["latent_regression_weight"] * networks.latent_regression_loss(
+            self.latent_regressor.params, stacked_imgs, labels, c["n_discr_layers"])
+        losses["loss_sum"] = networks._sum(losses.values())
+        self._apply(optimizer, losses["loss_sum"], [self.generator, self.latent_regressor, self.synthetic_encoder])
+        return self._detached(losses)
+
+    def setup_training(self, log_dir, synth_training_set, n_samples_for_metrics, real_training_set=None):
+        if log_dir:
+            os.makedirs(log_dir, exist_ok=True)
+        self.facemodel_param_distributions = getattr(synth_training_set, "metadata_input_distributions", None)
+
+    def train(self, real_training_set, synth_training_set, output_dir, log_dir, n_steps=100000,
+              n_samples_for_metrics=1000, aml_run=None):
+        """confignet_first_stage.py:597-626 (loop structure and loss history; checkpoints out of scope)."""
+        self.setup_training(log_dir, synth_training_set, n_samples_for_metrics, real_training_set=real_training_set)
+        start_step = self.get_training_step_number()
+        discriminator_optimizer = KerasAdam(**self.config["optimizer"])
+        generator_optimizer = KerasAdam(**self.config["optimizer"])
+        for _ in range(start_step, n_steps):
+            t0 = time.perf_counter()
+            for _ in range(self.config["n_discriminator_updates"]):
+                d_loss = self.discriminator_training_step(real_training_set, discriminator_optimizer)
+                synth_d_loss = self.synth_discriminator_training_step(synth_training_set, discriminator_optimizer)
+                latent_d_loss = self.latent_discriminator_training_step(synth_training_set, discriminator_optimizer)
+            for _ in range(self.config["n_generator_updates"]):
+                g_loss = self.generator_training_step(real_training_set, synth_training_set, generator_optimizer)
+            self.update_smoothed_weights()
+            print("[D loss: %f] [synth_D loss: %f] [latent_D_loss: %f] [G loss: %f]" %
+                  (d_loss["loss_sum"], synth_d_loss["loss_sum"], latent_d_loss["loss_sum"], g_loss["loss_sum"]))
+            update_loss_dict(self.g_losses, g_loss)
+            update_loss_dict(self.d_losses, d_loss)
+            update_loss_dict(self.synth_d_losses, synth_d_loss)
+            update_loss_dict(self.latent_d_losses, latent_d_loss)
+            self.last_iteration_time = time.perf_counter() - t0
+
+    # ---------------------------------------------------------------- evaluation
+    def generate_images(self, latent_vector, rotations):
+        """confignet_first_stage.py:633-639 -> uint8 (B,H,W,3)."""
+        d = self.generator.build_input_dict(latent_vector, rotations)
+        imgs = self.generator_smoothed.predict(d)
+        return ops.to_uint8(imgs).cpu().numpy()
+
+    def generate_images_from_facemodel(self, facemodel_params, rotations):
+        with torch.no_grad():
+            latents = self.synthetic_encoder(facemodel_params)
+        return self.generate_images(latents, rotations)

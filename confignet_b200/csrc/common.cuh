@@ -7,6 +7,7 @@
 #include "../../include/confignet_b200.h"
 
 void cn_set_error(const char* fmt, ...);
+extern unsigned long long g_cn_launches;     // kernels launched by this library (bench.py reports it)
 
 #define CN_CHECK_CUDA(expr)                                                            \
   do {                                                                                 \
@@ -19,6 +20,7 @@ void cn_set_error(const char* fmt, ...);
 
 #define CN_CHECK_LAUNCH()                                                              \
   do {                                                                                 \
+    ++g_cn_launches;                                                                   \
     cudaError_t _e = cudaGetLastError();                                               \
     if (_e != cudaSuccess) {                                                           \
       cn_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

@@ -9,9 +9,10 @@
 //
 // Two kernels per mode:
 //   igemm_ffma_kernel : fp32 CUDA-core tiles, scalar gathers, any channel count (skinny layers, tiny M)
-//   igemm_tc_*_kernel : tcgen05.mma kind::tf32 (operands rounded RNA to tf32 by the loader warps),
-//                       fp32 accumulators in TMEM, 128B-swizzled smem stages filled by gather warps,
-//                       mbarrier full/empty pipeline, tcgen05.ld epilogue with fused bias+activation.
+//   igemm_tc_*_kernel : tcgen05.mma kind::tf32 on big/small tf32 splits of the fp32 operands (3xTF32: 3 products
+//                       per k-step, fp32-grade accuracy on the tensor pipe), fp32 accumulators in TMEM,
+//                       128B-swizzled smem stages filled by gather warps, mbarrier full/empty pipeline,
+//                       tcgen05.ld epilogue with fused bias+activation.
 //
 // Reference call sites: keras Conv2D/Conv3D/Dense in confignet/dnn_models/*.py (see include/confignet_b200.h).
 #include "common.cuh"
@@ -348,6 +349,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem], tf32 operands, fp32 accumulate, issued by ONE thread for the CTA
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -367,21 +369,47 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// 3xTF32 split: x = big + small with big = rna_tf32(x), small = rna_tf32(x - big) (residual ~2^-22 |x|).
+// small*big + big*small + big*big on the tf32 tensor pipe reproduces the fp32 product to ~5e-7, which the
+// ill-conditioned gradients of this network need: measured on B200, single tf32 is 3.6e-2 off on the
+// generator output and a bf16 hi/lo split (~1e-5 per product) 1e-2..5e-2 off on some parameter gradients.
 __device__ __forceinline__ uint32_t f2tf32(float f) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
   return r;
 }
-__device__ __forceinline__ void sts128_tf32(uint32_t addr, float4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(f2tf32(v.x)), "r"(f2tf32(v.y)), "r"(f2tf32(v.z)), "r"(f2tf32(v.w)) : "memory");
+__device__ __forceinline__ void sts_split4(uint32_t addr_big, uint32_t addr_small, float4 v) {
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  uint32_t bg[4], sm[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bg[i] = f2tf32(x[i]);
+    sm[i] = f2tf32(x[i] - __uint_as_float(bg[i]));
+  }
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr_big), "r"(bg[0]), "r"(bg[1]), "r"(bg[2]), "r"(bg[3]) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr_small), "r"(sm[0]), "r"(sm[1]), "r"(sm[2]), "r"(sm[3]) : "memory");
 }
-__device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // UMMA shared-memory descriptor, version 1 (sm_100).  addr/lbo/sbo in bytes.
-// layout: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only MN-major layout for tf32:
-// atoms of 4 k-rows x 128 B, 32-byte units XOR-ed with the k-row index; LBO = MN-atom stride, SBO = stride
-// between groups of 4 k-rows).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout = 2) {
+//   layout 2 = SWIZZLE_128B, K-major tiles: rows of 128 B (32 tf32 of K), 8-row groups SBO = 1024 B apart.
+//   layout 1 = SWIZZLE_128B_BASE32B, the only MN-major layout for tf32: atoms of 4 k-rows x 128 B (32 tf32
+//              along M/N), 32-byte units XOR-ed with the k-row index; LBO = stride between atoms along M/N,
+//              SBO = stride between groups of 4 k-rows.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((addr & 0x3ffffu) >> 4);
   d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
@@ -402,8 +430,7 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(int n, int a_mn_major, int b
   d |= (uint32_t)(128 >> 4) << 24;
   return d;
 }
-
-// byte offset of the 16-byte chunk (k-row r, chunk jn along MN) inside an MN-major tf32 tile whose
+// byte offset of the 16-byte chunk (k-row r, chunk jn = 4 fp32 along M/N) inside an MN-major tf32 tile whose
 // k-groups (4 rows) are `sbo` bytes apart and whose 32-column atoms (512 B) are contiguous
 __device__ __forceinline__ uint32_t mn_chunk_off(int r, int jn, uint32_t sbo) {
   return (uint32_t)(r >> 2) * sbo + (uint32_t)(jn >> 3) * 512u + (uint32_t)(r & 3) * 128u +
@@ -411,23 +438,99 @@ __device__ __forceinline__ uint32_t mn_chunk_off(int r, int jn, uint32_t sbo) {
 }
 
 constexpr int TC_BM = 128;        // GEMM rows per CTA (UMMA M)
-constexpr int TC_BK = 32;         // fp32 elements per K block = one 128-byte swizzle row
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;
-constexpr int TC_THREADS = 288;   // warps 0-3: A gather + epilogue, 4-7: B gather, 8: TMEM alloc + MMA issue
+constexpr int TC_BK = 32;         // K elements per stage = one 128-byte swizzle row of tf32
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // one of the big / small A tiles
+constexpr int TC_THREADS = 416;   // warps 0-3: A gather, 4-7: B gather, 8-11: accumulator promotion + epilogue,
+                                  // 12: TMEM alloc + MMA issue
+constexpr int TC_CHUNK_KB = 16;   // k-blocks (512 K elements) accumulated in the tensor core before promotion
+constexpr int TC_MMA_WARP = 12;
 
 struct TcSmemLayout {
-  // dynamic smem, 1024-byte aligned: [A stages][B stages][barriers][tmem ptr][taps]
-  uint32_t a_off, b_off, bar_off, tmem_off, taps_off, total;
+  // dynamic smem, 1024-byte aligned: per stage [A big][A small][B big][B small]; then barriers, tmem ptr, taps
+  uint32_t stage_bytes, b_off, b_bytes, bar_off, tmem_off, taps_off, total;
 };
 __host__ __device__ inline TcSmemLayout tc_layout(int nstages, int bn_smem) {
   TcSmemLayout l;
-  l.a_off = 0;
-  l.b_off = nstages * TC_A_BYTES;
-  l.bar_off = l.b_off + nstages * bn_smem * TC_BK * 4;
-  l.tmem_off = l.bar_off + (2 * nstages + 1) * 8;
+  l.b_off = 2 * TC_A_BYTES;
+  l.b_bytes = bn_smem * TC_BK * 4;
+  l.stage_bytes = l.b_off + 2 * l.b_bytes;
+  l.bar_off = nstages * l.stage_bytes;
+  l.tmem_off = l.bar_off + (2 * nstages + 4) * 8;      // full[], empty[], acc_full[2], acc_empty[2]
   l.taps_off = (l.tmem_off + 4 + 7) & ~7u;
   l.total = l.taps_off + 256 * 8;
   return l;
+}
+
+// issue the 4 k-steps x 3 split products of one stage (small cross terms first, big*big last)
+template <int A_MN, int B_MN>
+__device__ __forceinline__ void tc_issue_stage(uint32_t tmem_base, uint32_t abase, uint32_t bbase, uint32_t b_bytes,
+                                               uint32_t sbo_a, uint32_t sbo_b, uint32_t idesc, bool first) {
+#pragma unroll
+  for (int kk = 0; kk < TC_BK / 8; ++kk) {
+    const uint32_t ao = A_MN ? kk * 2 * sbo_a : kk * 32, bo = B_MN ? kk * 2 * sbo_b : kk * 32;
+    const uint32_t lbo_a = A_MN ? 512u : 16u, lbo_b = B_MN ? 512u : 16u;
+    const uint32_t la = A_MN ? 1u : 2u, lb = B_MN ? 1u : 2u;
+    uint64_t ab = umma_desc(abase + ao, lbo_a, sbo_a, la), as = umma_desc(abase + TC_A_BYTES + ao, lbo_a, sbo_a, la);
+    uint64_t bb = umma_desc(bbase + bo, lbo_b, sbo_b, lb), bs = umma_desc(bbase + b_bytes + bo, lbo_b, sbo_b, lb);
+    tc_mma_tf32(tmem_base, as, bb, idesc, !(first && kk == 0));
+    tc_mma_tf32(tmem_base, ab, bs, idesc, 1);
+    tc_mma_tf32(tmem_base, ab, bb, idesc, 1);
+  }
+}
+
+// The tensor core adds into its fp32 accumulator with truncation: measured on B200 the result drifts by
+// ~1.1e-8 * K relative (1.2e-4 at K = 18432), a bias that plain fp32 FMAs do not have.  So the MMA warp
+// accumulates at most TC_CHUNK_KB k-blocks into one of two ping-pong TMEM accumulators and warps 8-11 add
+// each finished chunk into a running fp32 total (round-to-nearest FADD on the CUDA cores), kept in a third
+// TMEM region, while the tensor core works on the next chunk.  store(cb, v) receives the final 32-column
+// groups of this thread's accumulator row.
+template <class StoreFn>
+__device__ __forceinline__ void tc_promote_and_store(uint32_t tmem_base, int pw, int bn, int bn_r, int nchunks,
+                                                     uint32_t bar_accfull, uint32_t bar_accempty, StoreFn store) {
+  const uint32_t lanebits = (uint32_t)(pw * 32) << 16;
+  for (int c = 0; c < nchunks; ++c) {
+    const int b = c & 1;
+    mbar_wait(bar_accfull + 8 * b, (c >> 1) & 1);
+    tc_fence_after();
+    const bool last = c == nchunks - 1;
+    for (int cb = 0; cb < bn; cb += 32) {
+      uint32_t v[32];
+      tc_ld32(tmem_base + lanebits + b * bn_r + cb, v);
+      if (c > 0) {
+        uint32_t t[32];
+        tc_ld32(tmem_base + lanebits + 2 * bn_r + cb, t);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(t[q]));
+      }
+      if (!last) tc_st32(tmem_base + lanebits + 2 * bn_r + cb, v);
+      else store(cb, v);
+    }
+    if (!last) { tc_fence_before(); mbar_arrive(bar_accempty + 8 * b); }
+  }
+}
+
+// MMA issue loop shared by both kernels (one warp; lane 0 issues)
+template <int A_MN, int B_MN>
+__device__ __forceinline__ void tc_mma_loop(uint32_t tmem_base, uint32_t sbase, const TcSmemLayout& L, int nstages,
+                                            int num_kb, int bn_r, uint32_t bar_full, uint32_t bar_empty,
+                                            uint32_t bar_accfull, uint32_t bar_accempty, uint32_t sbo_a,
+                                            uint32_t sbo_b, uint32_t idesc, int lane) {
+  for (int kb = 0; kb < num_kb; ++kb) {
+    const int s = kb % nstages;
+    const int c = kb / TC_CHUNK_KB, b = c & 1;
+    const bool chunk_first = (kb % TC_CHUNK_KB) == 0;
+    const bool chunk_last = (kb % TC_CHUNK_KB) == TC_CHUNK_KB - 1 || kb == num_kb - 1;
+    if (chunk_first && c >= 2) { mbar_wait(bar_accempty + 8 * b, ((c >> 1) - 1) & 1); }
+    mbar_wait(bar_full + 8 * s, (kb / nstages) & 1);
+    tc_fence_after();
+    if (lane == 0) {
+      const uint32_t abase = sbase + s * L.stage_bytes;
+      tc_issue_stage<A_MN, B_MN>(tmem_base + b * bn_r, abase, abase + L.b_off, L.b_bytes, sbo_a, sbo_b, idesc, chunk_first);
+      tc_commit(bar_empty + 8 * s);
+      if (chunk_last) tc_commit(bar_accfull + 8 * b);
+    }
+    __syncwarp();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -442,21 +545,23 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const TcSmemLayout L = tc_layout(nstages, bn_smem);
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_full = sbase + L.bar_off, bar_empty = bar_full + 8 * nstages, bar_acc = bar_empty + 8 * nstages;
+  const uint32_t bar_full = sbase + L.bar_off, bar_empty = bar_full + 8 * nstages;
+  const uint32_t bar_accfull = bar_empty + 8 * nstages, bar_accempty = bar_accfull + 16;
+  const int bn_r = (bn_smem + 31) / 32 * 32;
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_off);
   int2* s_taps = reinterpret_cast<int2*>(smem + L.taps_off);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * bn;
   const int num_kb = (p.Ktot + TC_BK - 1) / TC_BK;
-  const uint32_t b_stage_bytes = bn_smem * TC_BK * 4;
 
   for (int i = tid; i < p.ntaps; i += TC_THREADS) s_taps[i] = p.taps[i];
   if (tid == 0) {
     for (int s = 0; s < nstages; ++s) { mbar_init(bar_full + 8 * s, 256); mbar_init(bar_empty + 8 * s, 1); }
-    mbar_init(bar_acc, 1);
+    mbar_init(bar_accfull, 1); mbar_init(bar_accfull + 8, 1);
+    mbar_init(bar_accempty, 128); mbar_init(bar_accempty + 8, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == TC_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + L.tmem_off), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -466,7 +571,7 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < 4) {
-    // ===== A gather: 8 threads per 128-byte row, 8 rows per thread =====
+    // ===== A gather: 8 threads per 128-byte row (one 16-byte chunk each), 8 rows per thread =====
     const int j = tid & 7;
     RowInfo rows[8];
 #pragma unroll
@@ -483,24 +588,24 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
         uint32_t sp = kok ? src_pixel(p, rows[i], tap_pk) : 0xffffffffu;
         v[i] = (sp != 0xffffffffu) ? ldg128(A + (size_t)sp * p.Csrc + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const uint32_t abase = sbase + L.a_off + s * TC_A_BYTES;
+      const uint32_t abase = sbase + s * L.stage_bytes;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         int r = (tid >> 3) + 16 * i;
-        sts128_tf32(abase + r * 128 + ((j ^ (r & 7)) << 4), v[i]);
+        uint32_t off = r * 128 + ((j ^ (r & 7)) << 4);
+        sts_split4(abase + off, abase + TC_A_BYTES + off, v[i]);
       }
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * s);
     }
-    // ===== epilogue: TMEM -> registers -> global (warp w owns TMEM lanes 32w..32w+31) =====
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    const int m = m0 + warp * 32 + lane;
+  } else if (warp >= 8 && warp < 12) {
+    // ===== promotion + epilogue: TMEM -> registers -> global (warp pw owns TMEM lanes 32pw..32pw+31) =====
+    const int pw = warp - 8;
+    const int m = m0 + pw * 32 + lane;
     const bool mok = m < p.M;
     const size_t rowoff = mok ? (size_t)dest_pixel(p, m) * p.Cn : 0;
-    for (int cb = 0; cb < bn; cb += 32) {
-      uint32_t v[32];
-      tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cb, v);
+    const int nchunks = (num_kb + TC_CHUNK_KB - 1) / TC_CHUNK_KB;
+    tc_promote_and_store(tmem_base, pw, bn, bn_r, nchunks, bar_accfull, bar_accempty, [&](int cb, const uint32_t* v) {
       if (mok) {
 #pragma unroll
         for (int q = 0; q < 32; q += 4) {
@@ -516,30 +621,31 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
           }
         }
       }
-    }
+    });
   } else if (warp < 8) {
     // ===== B gather =====
     const int t = tid - 128;
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % nstages;
       if (kb >= nstages) mbar_wait(bar_empty + 8 * s, ((kb / nstages) - 1) & 1);
-      const uint32_t bbase = sbase + L.b_off + s * b_stage_bytes;
+      const uint32_t bbase = sbase + s * L.stage_bytes + L.b_off;
       if (B_MN) {
-        // 32 k-rows x bn_smem columns, MN-major (see mn_chunk_off)
-        const int cpr = bn_smem >> 2;                       // 16-byte chunks per k-row
+        // 32 k-rows x bn_smem columns, MN-major: chunks of 4 output channels
+        const int cpr = bn_smem >> 2;
         const uint32_t sbo = (uint32_t)(bn_smem >> 5) * 512u;
-        for (int q = t; q < 32 * cpr; q += 128) {
-          int r = q / cpr, jn = q - r * cpr;
-          int k = kb * TC_BK + r, n = n0 + 4 * jn;
+        for (int q = t; q < TC_BK * cpr; q += 128) {
+          int r = q / cpr, jc = q - r * cpr;
+          int k = kb * TC_BK + r, n = n0 + 4 * jc;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k < p.Ktot && n < p.Cn && 4 * jn < bn) {
+          if (k < p.Ktot && n < p.Cn && 4 * jc < bn) {
             int kt = k / p.Csrc; int c = k - kt * p.Csrc;
             v = ldg128(W + (size_t)s_taps[kt].y + (size_t)c * p.wsc + n);
           }
-          sts128_tf32(bbase + mn_chunk_off(r, jn, sbo), v);
+          uint32_t off = mn_chunk_off(r, jc, sbo);
+          sts_split4(bbase + off, bbase + L.b_bytes + off, v);
         }
       } else {
-        // bn_smem rows (n) x 32 k; K-major SW128
+        // bn_smem rows (n) x 32 k; K-major
         const int j = t & 7;
         const int k = kb * TC_BK + 4 * j;
         int c = 0, wb = 0; bool kok = k < p.Ktot;
@@ -548,7 +654,8 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
           int n = n0 + r;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (kok && r < bn && n < p.Cn) v = ldg128(W + (size_t)wb + (size_t)n * p.wsn + c);
-          sts128_tf32(bbase + r * 128 + ((j ^ (r & 7)) << 4), v);
+          uint32_t off = r * 128 + ((j ^ (r & 7)) << 4);
+          sts_split4(bbase + off, bbase + L.b_bytes + off, v);
         }
       }
       fence_proxy_async();
@@ -558,28 +665,12 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
     // ===== MMA issue (one lane) =====
     const uint32_t idesc = umma_idesc_tf32(bn_smem, 0, B_MN);
     const uint32_t sbo_b = B_MN ? (uint32_t)(bn_smem >> 5) * 512u : 1024u;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % nstages;
-      mbar_wait(bar_full + 8 * s, (kb / nstages) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t abase = sbase + L.a_off + s * TC_A_BYTES;
-        const uint32_t bbase = sbase + L.b_off + s * b_stage_bytes;
-#pragma unroll
-        for (int kk = 0; kk < TC_BK / 8; ++kk) {
-          uint64_t ad = umma_desc(abase + kk * 32, 16, 1024);
-          uint64_t bd = B_MN ? umma_desc(bbase + kk * 2 * sbo_b, 512, sbo_b, 1) : umma_desc(bbase + kk * 32, 16, 1024);
-          tc_mma_tf32(tmem_base, ad, bd, idesc, (kb | kk) != 0);
-        }
-        tc_commit(bar_empty + 8 * s);
-        if (kb == num_kb - 1) tc_commit(bar_acc);
-      }
-      __syncwarp();
-    }
+    tc_mma_loop<0, B_MN>(tmem_base, sbase, L, nstages, num_kb, bn_r, bar_full, bar_empty, bar_accfull, bar_accempty,
+                         1024u, sbo_b, idesc, lane);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == TC_MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
@@ -595,7 +686,9 @@ igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const TcSmemLayout L = tc_layout(nstages, bn_smem);
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_full = sbase + L.bar_off, bar_empty = bar_full + 8 * nstages, bar_acc = bar_empty + 8 * nstages;
+  const uint32_t bar_full = sbase + L.bar_off, bar_empty = bar_full + 8 * nstages;
+  const uint32_t bar_accfull = bar_empty + 8 * nstages, bar_accempty = bar_accfull + 16;
+  const int bn_r = (bn_smem + 31) / 32 * 32;
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_off);
   int2* s_taps = reinterpret_cast<int2*>(smem + L.taps_off);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -604,16 +697,16 @@ igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
   const int kb_beg = blockIdx.z * kb_per_split;
   const int kb_end = min(total_kb, kb_beg + kb_per_split);
   const int num_kb = kb_end - kb_beg;     // host guarantees >= 1
-  const uint32_t b_stage_bytes = bn_smem * TC_BK * 4;
   const uint32_t sbo_b = (uint32_t)(bn_smem >> 5) * 512u;
 
   for (int i = tid; i < p.ntaps; i += TC_THREADS) s_taps[i] = p.taps[i];
   if (tid == 0) {
     for (int s = 0; s < nstages; ++s) { mbar_init(bar_full + 8 * s, 256); mbar_init(bar_empty + 8 * s, 1); }
-    mbar_init(bar_acc, 1);
+    mbar_init(bar_accfull, 1); mbar_init(bar_accfull + 8, 1);
+    mbar_init(bar_accempty, 128); mbar_init(bar_accempty + 8, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == TC_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + L.tmem_off), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -623,8 +716,8 @@ igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < 4) {
-    // ===== A gather: lane = 16-byte chunk of the 128 GEMM rows (fixed tap/channel per thread),
-    //       warp w fills pixel rows 8w..8w+7 of the K block =====
+    // ===== A gather: lane = 16-byte chunk of the 128 GEMM rows (fixed tap, 4 channels per thread),
+    //       warp w fills pixel rows 8w..8w+7 of the 32-pixel K block =====
     const int rr = r0 + 4 * lane;
     const bool rok = rr < p.Ktot;
     int c = 0, tap_pk = 0;
@@ -643,21 +736,23 @@ igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
         uint32_t sp = rok ? src_pixel(p, ri, tap_pk) : 0xffffffffu;
         v[i] = (sp != 0xffffffffu) ? ldg128(A + (size_t)sp * p.Csrc + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const uint32_t abase = sbase + L.a_off + s * TC_A_BYTES;
+      const uint32_t abase = sbase + s * L.stage_bytes;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sts128_tf32(abase + mn_chunk_off(warp * 8 + i, lane, 2048u), v[i]);
+      for (int i = 0; i < 8; ++i) {
+        uint32_t off = mn_chunk_off(warp * 8 + i, lane, 2048u);
+        sts_split4(abase + off, abase + TC_A_BYTES + off, v[i]);
+      }
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * s);
     }
-    // ===== epilogue =====
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    const int r = r0 + warp * 32 + lane;
+  } else if (warp >= 8 && warp < 12) {
+    // ===== promotion + epilogue =====
+    const int pw = warp - 8;
+    const int r = r0 + pw * 32 + lane;
     const bool ok = r < p.Ktot;
     const size_t rowoff = (size_t)r * p.Cn;
-    for (int cb = 0; cb < bn; cb += 32) {
-      uint32_t v[32];
-      tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cb, v);
+    const int nchunks = (num_kb + TC_CHUNK_KB - 1) / TC_CHUNK_KB;
+    tc_promote_and_store(tmem_base, pw, bn, bn_r, nchunks, bar_accfull, bar_accempty, [&](int cb, const uint32_t* v) {
       if (ok) {
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
@@ -668,7 +763,7 @@ igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
           }
         }
       }
-    }
+    });
   } else if (warp < 8) {
     // ===== B gather: 32 pixel rows x bn_smem columns of G =====
     const int t = tid - 128;
@@ -676,42 +771,27 @@ igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
     for (int it = 0; it < num_kb; ++it) {
       const int s = it % nstages;
       if (it >= nstages) mbar_wait(bar_empty + 8 * s, ((it / nstages) - 1) & 1);
-      const uint32_t bbase = sbase + L.b_off + s * b_stage_bytes;
+      const uint32_t bbase = sbase + s * L.stage_bytes + L.b_off;
       const int mbase = (kb_beg + it) * TC_BK;
-      for (int q = t; q < 32 * cpr; q += 128) {
+      for (int q = t; q < TC_BK * cpr; q += 128) {
         int r = q / cpr, jn = q - r * cpr;
         int m = mbase + r, n = n0 + 4 * jn;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < p.M && n < p.Cn && 4 * jn < bn) v = ldg128(G + (size_t)m * p.Cn + n);
-        sts128_tf32(bbase + mn_chunk_off(r, jn, sbo_b), v);
+        uint32_t off = mn_chunk_off(r, jn, sbo_b);
+        sts_split4(bbase + off, bbase + L.b_bytes + off, v);
       }
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * s);
     }
   } else {
     const uint32_t idesc = umma_idesc_tf32(bn_smem, 1, 1);
-    for (int it = 0; it < num_kb; ++it) {
-      const int s = it % nstages;
-      mbar_wait(bar_full + 8 * s, (it / nstages) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t abase = sbase + L.a_off + s * TC_A_BYTES;
-        const uint32_t bbase = sbase + L.b_off + s * b_stage_bytes;
-#pragma unroll
-        for (int kk = 0; kk < TC_BK / 8; ++kk) {
-          uint64_t ad = umma_desc(abase + kk * 4096u, 512, 2048, 1);
-          uint64_t bd = umma_desc(bbase + kk * 2 * sbo_b, 512, sbo_b, 1);
-          tc_mma_tf32(tmem_base, ad, bd, idesc, (it | kk) != 0);
-        }
-        tc_commit(bar_empty + 8 * s);
-        if (it == num_kb - 1) tc_commit(bar_acc);
-      }
-      __syncwarp();
-    }
+    tc_mma_loop<1, 1>(tmem_base, sbase, L, nstages, num_kb, bn_r, bar_full, bar_empty, bar_accfull, bar_accempty,
+                      2048u, sbo_b, idesc, lane);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == TC_MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
@@ -736,6 +816,8 @@ __global__ void colsum_kernel(const float* __restrict__ g, int rows, int n, floa
 // ------------------------------------------------------------------------------------------------
 // Host dispatch
 // ------------------------------------------------------------------------------------------------
+static thread_local int g_last_impl = 0;     // 1 = CUDA-core, 2 = tcgen05: what the last conv call on this thread ran
+extern "C" int cn_last_conv_impl(void) { return g_last_impl; }
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -755,7 +837,7 @@ static int set_smem(K kernel, int bytes) {
 }
 
 static bool tc_pixel_eligible(const GemmPlan& g, bool b_mn) {
-  if (g.M < 128 || g.ntaps == 0 || g.Ktot < 32) return false;
+  if (g.M < 128 || g.ntaps == 0 || g.Ktot < 8) return false;
   if (g.Csrc % 4 != 0) return false;
   if (b_mn) return g.Cn % 4 == 0 && g.Cn >= 16;
   return g.Cn % 16 == 0;
@@ -781,6 +863,7 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
   bool tc = tc_pixel_eligible(g, b_mn);
   CN_REQUIRE(!(impl == CN_IMPL_TC && !tc), CN_ERR_UNSUPPORTED, "shape not eligible for the tcgen05 kernel");
   if (impl == CN_IMPL_FFMA) tc = false;
+  g_last_impl = tc ? 2 : 1;
   if (tc) {
     int bn, bn_smem;
     if (b_mn) pick_bn_mn(g.Cn, &bn, &bn_smem); else pick_bn_k(g.Cn, &bn, &bn_smem);
@@ -788,7 +871,8 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
     TcSmemLayout L = tc_layout(nstages, bn_smem);
     int smem = L.total + 1024;
     dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.Cn + bn - 1) / bn, 1);
-    int cols = pow2_cols((bn_smem + 31) / 32 * 32);
+    int cols = pow2_cols(3 * ((bn_smem + 31) / 32 * 32));
+    if (L.total + 1024 > 227 * 1024) { nstages = 2; L = tc_layout(nstages, bn_smem); smem = L.total + 1024; }
     if (b_mn) {
       if (set_smem(igemm_tc_pixel_kernel<1>, smem)) return CN_ERR_CUDA;
       igemm_tc_pixel_kernel<1><<<grid, TC_THREADS, smem, st>>>(g, src, w, bias, dst, act, alpha, bn, bn_smem, nstages, cols);
@@ -871,6 +955,7 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
   bool tc = g.M >= 256 && g.Csrc % 4 == 0 && g.Cn % 4 == 0 && g.Cn >= 16 && g.Ktot >= 64;
   CN_REQUIRE(!(impl == CN_IMPL_TC && !tc), CN_ERR_UNSUPPORTED, "shape not eligible for the tcgen05 wgrad kernel");
   if (impl == CN_IMPL_FFMA) tc = false;
+  g_last_impl = tc ? 2 : 1;
   if (tc) {
     int bn, bn_smem; pick_bn_mn(g.Cn, &bn, &bn_smem);
     int nstages = 3;
@@ -887,7 +972,7 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
     if (split > 1) CN_CHECK_CUDA(cudaMemsetAsync(gw, 0, wn * sizeof(float), st));
     if (set_smem(igemm_tc_wgrad_kernel, smem)) return CN_ERR_CUDA;
     dim3 grid(mt, nt, split);
-    int cols = pow2_cols(bn_smem);
+    int cols = pow2_cols(3 * ((bn_smem + 31) / 32 * 32));
     igemm_tc_wgrad_kernel<<<grid, TC_THREADS, smem, st>>>(g, x, gy, gw, bn, bn_smem, nstages, cols, per, split > 1);
     CN_CHECK_LAUNCH();
   } else {

@@ -5,3 +5,9 @@ void cn_set_error(const char* fmt, ...) {
 }
 extern "C" const char* cn_last_error(void) { return g_err; }
 extern "C" int cn_version(void) { return 1; }
+unsigned long long g_cn_launches = 0;
+extern "C" long long cn_launch_count(int reset) {
+  long long v = (long long)g_cn_launches;
+  if (reset) g_cn_launches = 0;
+  return v;
+}

@@ -319,3 +319,38 @@ extern "C" int cn_ema(float* ema, const float* p, int64_t n, float alpha, void* 
   ema_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(ema, p, (size_t)n, alpha);
   CN_CHECK_LAUNCH(); return CN_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ gradient gather
+// Packs up to CN_MULTI_MAX separately allocated gradient tensors into one flat buffer (the buffer the
+// NCCL all-reduce and the fused Adam kernel run on).  A NULL source zero-fills its slot (unused variable,
+// tape.gradient -> None).  blockIdx.y = tensor.
+struct MultiCopyArgs {
+  const float* src[CN_MULTI_MAX];
+  long long off[CN_MULTI_MAX];
+  long long n[CN_MULTI_MAX];
+};
+__global__ void multi_copy_kernel(MultiCopyArgs a, float* __restrict__ dst) {
+  const int t = blockIdx.y;
+  const float* s = a.src[t];
+  float* d = dst + a.off[t];
+  const long long n = a.n[t];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = s ? s[i] : 0.f;
+}
+extern "C" int cn_multi_copy(int count, const float* const* src, const int64_t* dst_off, const int64_t* n,
+                             float* dst, void* stream) {
+  CN_REQUIRE(count >= 0 && dst, CN_ERR_BAD_SHAPE, "cn_multi_copy: bad arguments");
+  for (int base = 0; base < count; base += CN_MULTI_MAX) {
+    MultiCopyArgs a;
+    int c = count - base < CN_MULTI_MAX ? count - base : CN_MULTI_MAX;
+    long long maxn = 1;
+    for (int i = 0; i < c; ++i) {
+      a.src[i] = src[base + i]; a.off[i] = dst_off[base + i]; a.n[i] = n[base + i];
+      if (a.n[i] > maxn) maxn = a.n[i];
+    }
+    int bx = (int)((maxn + 1023) / 1024); if (bx > 64) bx = 64; if (bx < 1) bx = 1;
+    multi_copy_kernel<<<dim3(bx, c), 256, 0, (cudaStream_t)stream>>>(a, dst);
+    CN_CHECK_LAUNCH();
+  }
+  return CN_OK;
+}

@@ -1,0 +1,166 @@
+"""Host-side runtime pieces: flat parameter groups, Keras-protocol network shims, Keras-Adam on flat
+buffers, and the data-parallel gradient exchange.
+
+  ParamGroup        one flat HBM buffer per network (+ flat gradient / Adam moments); the per-variable
+                    tensors are views, so get_weights()/set_weights() interchange is a memcpy and the
+                    optimizer / all-reduce each run as ONE launch per step.
+  Network           the slice of the Keras Model protocol the reference's classes use
+                    (``m(x)``, ``predict``, ``get_weights``, ``set_weights``, ``trainable_weights``, ``build``).
+  KerasAdam         keras.optimizers.Adam semantics [TF-2.1] (confignet_first_stage.py:601-602), incl. the
+                    per-optimizer ``iterations`` counter shared by the three discriminators (:608-610).
+"""
+import ctypes
+import math
+from collections import OrderedDict
+import numpy as np
+import torch
+import torch.distributed as dist
+from . import _lib as L
+from . import ops
+
+
+class ParamGroup:
+    def __init__(self, spec_or_arrays, device, init=None):
+        """spec_or_arrays: OrderedDict name -> ndarray (initial values, Keras layout)."""
+        arrays = spec_or_arrays
+        self.names = list(arrays.keys())
+        self.shapes = [tuple(np.shape(arrays[k])) for k in self.names]
+        self.sizes = [int(np.prod(s)) if len(s) else 1 for s in self.shapes]
+        # 16-byte aligned slots so every view can be read with float4
+        self.offsets, off = [], 0
+        for n in self.sizes:
+            self.offsets.append(off)
+            off += (n + 3) // 4 * 4
+        self.total = off
+        self.device = torch.device(device)
+        self.flat = torch.zeros(self.total, device=self.device, dtype=torch.float32)
+        self.grad = torch.zeros(self.total, device=self.device, dtype=torch.float32)
+        self.params = OrderedDict()
+        for name, shape, n, o in zip(self.names, self.shapes, self.sizes, self.offsets):
+            v = self.flat[o:o + n].view(shape)
+            self.params[name] = v
+        self.set_weights([arrays[k] for k in self.names])
+        for v in self.params.values():
+            v.requires_grad_(True)
+        self._off_arr = (ctypes.c_int64 * len(self.names))(*self.offsets)
+        self._n_arr = (ctypes.c_int64 * len(self.names))(*self.sizes)
+
+    # ---- Keras weight interchange
+    def get_weights(self):
+        host = self.flat.detach().cpu().numpy()
+        return [host[o:o + n].reshape(s).copy() for s, n, o in zip(self.shapes, self.sizes, self.offsets)]
+
+    def set_weights(self, weights):
+        if len(weights) != len(self.names):
+            raise ValueError("expected %d weight arrays, got %d" % (len(self.names), len(weights)))
+        host = np.zeros(self.total, np.float32)
+        for w, s, n, o, name in zip(weights, self.shapes, self.sizes, self.offsets, self.names):
+            w = np.asarray(w, np.float32)
+            if tuple(w.shape) != s:
+                raise ValueError("weight %s: expected shape %s, got %s" % (name, s, tuple(w.shape)))
+            host[o:o + n] = w.reshape(-1)
+        with torch.no_grad():
+            self.flat.copy_(torch.from_numpy(host))
+
+    def copy_from(self, other):
+        with torch.no_grad():
+            self.flat.copy_(other.flat)
+
+    @property
+    def trainable_weights(self):
+        return list(self.params.values())
+
+    # ---- gradients
+    def pack_grads(self, grads):
+        """grads: list aligned with ``trainable_weights`` (None = unused variable) -> self.grad (flat)."""
+        keep = [None if g is None else ops._chk(g) for g in grads]
+        ptrs = (ctypes.c_void_p * len(keep))(*[None if g is None else g.data_ptr() for g in keep])
+        L.call("cn_multi_copy", len(keep), ptrs, self._off_arr, self._n_arr, ops._p(self.grad), ops._stream())
+        return keep       # keeps the sources alive until the copy is enqueued
+
+
+class Network:
+    """Keras-Model-like shim around (ParamGroup, forward function)."""
+
+    def __init__(self, group, forward, **forward_kwargs):
+        self.group = group
+        self._forward = forward
+        self._kw = forward_kwargs
+
+    @property
+    def params(self):
+        return self.group.params
+
+    def __call__(self, *inputs, **kw):
+        k = dict(self._kw); k.update(kw)
+        return self._forward(self.group.params, *inputs, **k)
+
+    def predict(self, *inputs, **kw):
+        with torch.no_grad():
+            out = self(*inputs, **kw)
+        return out
+
+    def build(self, input_shape=None):
+        return None
+
+    def get_weights(self):
+        return self.group.get_weights()
+
+    def set_weights(self, weights):
+        self.group.set_weights(list(weights))
+
+    @property
+    def trainable_weights(self):
+        return self.group.trainable_weights
+
+
+class KerasAdam:
+    """[TF-2.1] Adam (non-amsgrad): t = iterations+1; lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
+    m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; theta -= lr_t*m/(sqrt(v)+eps), eps = 1e-7."""
+
+    def __init__(self, lr=0.0004, beta_1=0.0, beta_2=0.9, epsilon=1e-7, amsgrad=False, **_):
+        if amsgrad:
+            raise NotImplementedError("amsgrad is not used by ConfigNet (confignet_first_stage.py:50)")
+        self.lr, self.b1, self.b2, self.eps = lr, beta_1, beta_2, epsilon
+        self.iterations = 0
+        self.state = {}
+
+    def apply_flat(self, groups, gscale=1.0):
+        """One optimizer step over the flat gradient buffers of ``groups`` (already packed / reduced)."""
+        t = self.iterations + 1
+        lr_t = self.lr * math.sqrt(1 - self.b2 ** t) / (1 - self.b1 ** t)
+        for g in groups:
+            st = self.state.get(id(g))
+            if st is None:
+                st = (torch.zeros_like(g.flat), torch.zeros_like(g.flat))
+                self.state[id(g)] = st
+            ops.adam_ema_step(g.flat, g.grad, st[0], st[1], None, lr_t, self.b1, self.b2, self.eps, 0.0, gscale)
+        self.iterations += 1
+
+
+# ------------------------------------------------------------------------------------------------ data parallel
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def allreduce_grads(groups):
+    """Sum the flat gradient buffers over ranks (one NCCL all-reduce per network, fp32) and return the
+    1/world scale to fold into the optimizer kernel.  Losses are batch means over equal shards, so the
+    averaged gradient equals the single-process gradient of the global batch."""
+    rank, ws = world()
+    if ws == 1:
+        return 1.0
+    for g in groups:
+        dist.all_reduce(g.grad, op=dist.ReduceOp.SUM)
+    return 1.0 / ws
+
+
+def shard_rows(n_global):
+    """Row slice [lo, hi) of a globally sampled batch owned by this rank."""
+    rank, ws = world()
+    if n_global % ws != 0:
+        raise ValueError("global batch %d is not divisible by world size %d" % (n_global, ws))
+    per = n_global // ws
+    return rank * per, (rank + 1) * per

@@ -39,6 +39,8 @@ extern "C" {
 
 const char* cn_last_error(void);
 int cn_version(void);
+/* number of kernels this library has launched since load (or since the last reset != 0) */
+long long cn_launch_count(int reset);
 
 /* Convolution geometry.  nd = 0 describes a Dense layer (batch rows, cin -> cout). */
 typedef struct {
@@ -51,6 +53,8 @@ typedef struct {
   int upsample;    /* 1, or 2 = nearest-neighbour x2 (UpSampling2D/3D) fused on the input    */
 } cn_conv_desc;
 
+/* which kernel family the last conv call on this thread used: 1 CUDA-core, 2 tcgen05 */
+int cn_last_conv_impl(void);
 /* y spatial dims for `d` (TF SAME: ceil(in*upsample/stride)). */
 int cn_conv_out_dims(const cn_conv_desc* d, int out_dims[3]);
 
@@ -73,23 +77,35 @@ int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float* gy, float*
  * replaces tf.nn.moments / K.mean / K.std and the broadcast arithmetic inside
  * LayerNormalization (building_blocks.py:132-149), InstanceNormalization
  * (instance_normalization.py:108-131) and get_layer_style (confignet_utils.py:147-159),
- * and every term of their first- and second-order gradients. */
-/* sums[(n*C + c)*7 + j] over the P pixels of sample n:
+ * and every term of their first- and second-order gradients (R1: losses.py:42-43,75-82). */
+#define CN_FLAG_LRELU_A 1   /* a := lrelu(a, alpha) before use                    */
+#define CN_FLAG_MASK_OUT 2  /* affine result *= lrelu'(a_raw)                     */
+#define CN_FLAG_MASK_C 4    /* c := c * lrelu'(a_raw)                             */
+/* sums[(n*C + ch)*7 + j] over the P pixels of sample n:
  *   j: 0 sum a, 1 sum b, 2 sum c, 3 sum a*a, 4 sum a*b, 5 sum a*c, 6 sum b*c  (b, c may be NULL) */
 int cn_chan_sums(const float* a, const float* b, const float* c, int n, int p, int ch,
-                 float* sums, void* stream);
-/* out = ka[n,c]*a + kb[n,c]*b + kc[n,c]*c + k0[n,c]; coef is (n, ch, 4) = (ka,kb,kc,k0).
- * mode 0: plain.  mode 1: a is replaced by lrelu(a, alpha) before use.
- * mode 2: result multiplied by lrelu'(mask_src, alpha) where mask_src = c and kc is ignored. */
+                 int flags, float alpha, float* sums, void* stream);
+/* out = ka[n,ch]*a + kb[n,ch]*b + kc[n,ch]*c + k0[n,ch]; coef is (n, ch, 4) = (ka,kb,kc,k0). */
 int cn_chan_affine(const float* a, const float* b, const float* c, const float* coef,
-                   int n, int p, int ch, int mode, float alpha, float* out, void* stream);
+                   int n, int p, int ch, int flags, float alpha, float* out, void* stream);
+/* closed-form coefficients from the 7 sums.  kind:
+ *  0 IN fwd      p0=gamma p1=beta          -> coef0
+ *  1 IN bwd      sums(a,gy) p0=gamma       -> coef0 (input grad), out0=dgamma[ch], out1=dbeta[ch]
+ *  2 IN bwd-bwd  sums(a,gy,h) p0=gamma     -> coef0 (d/da), coef1 (d/dgy), out0=dgamma[ch]
+ *  3 style fwd   sums(a)                   -> out0 = style (n,2ch) = concat(mean, sqrt(var+eps))
+ *  4 style bwd   sums(a) p0=gstyle(n,2ch)  -> coef0
+ *  5 style bwd-bwd sums(a,h) p0=gstyle     -> coef0 (d/da), out0 = d/dgstyle (n,2ch)
+ *  6 AdaIN fwd   sums(a) p0=sb (n,2ch)     -> coef0
+ *  7 AdaIN bwd   sums(a,gy) p0=sb          -> coef0, out0 = dsb (n,2ch)                         */
+int cn_norm_coef(int kind, const float* sums, const float* p0, const float* p1, int n, int ch,
+                 int npix, float eps, float* coef0, float* coef1, float* out0, float* out1,
+                 void* stream);
 
 /* elementwise helpers on flat fp32 buffers */
 int cn_lrelu_fwd(const float* x, float alpha, float* y, int64_t n, void* stream);
-/* gx = gy * (ref > 0 ? 1 : alpha); ref may be the pre- or post-activation tensor */
-int cn_lrelu_bwd(const float* gy, const float* ref, float alpha, float* gx, int64_t n, void* stream);
-/* act-specific backward from the OUTPUT y: relu, tanh (1-y^2), lrelu */
-int cn_act_bwd(const float* gy, const float* y, int act, float alpha, float* gx, int64_t n, void* stream);
+/* gx = gy * act'(ref): lrelu (ref = pre- or post-activation), relu (ref = y), tanh (ref = y: 1-y^2) */
+int cn_act_bwd(const float* gy, const float* ref, int act, float alpha, float* gx, int64_t n, void* stream);
+/* out = a*x + b*y (y may be NULL) */
 int cn_axpby(const float* x, const float* y, float a, float b, float* out, int64_t n, void* stream);
 
 /* 2x2/s2 VALID max-pool, NHWC (VGG pools, perceptual_loss.py:19-24) and its backward
@@ -103,19 +119,16 @@ int cn_maxpool2_bwd(const float* x, const float* y, const float* gy, int n, int 
 int cn_rotate3d_fwd(const float* grid, const float* rot, int b, int s, int c, float* out, void* stream);
 /* gradient wrt the grid (scatter-add; ggrid must be zero-filled by the caller) */
 int cn_rotate3d_bwd_grid(const float* gout, const float* rot, int b, int s, int c, float* ggrid, void* stream);
-/* gradient wrt the 3x3 matrix entries (B,9) (through `diffs` only, as tf.floor has zero gradient) */
-int cn_rotate3d_bwd_rot(const float* grid, const float* gout, const float* rot, int b, int s, int c,
-                        float* grot, void* stream);
-
-/* loss reductions (losses.py:7-18, perceptual_loss.py:76-80): deterministic two-stage sums.
+/* loss reductions (losses.py:7-18,75-82, perceptual_loss.py:76-80): deterministic two-stage sums.
  * kind 0: sum softplus(sign*x)   kind 1: sum (x-y)^2   kind 2: sum x^2   kind 3: sum x
+ * each term optionally multiplied by wgt[i / wdiv] (eye-loss mask broadcast over channels).
  * result[0] = scale * sum.  ws must hold cn_reduce_ws_floats() floats. */
 int cn_reduce_ws_floats(void);
-int cn_reduce(const float* x, const float* y, int64_t n, int kind, float sign, float scale,
-              float* ws, float* result, void* stream);
-/* gx = gscale[0] * k * d(kind)/dx ; kind 0: sign*sigmoid(sign*x), kind 1: 2(x-y), kind 2: 2x */
-int cn_reduce_bwd(const float* x, const float* y, int64_t n, int kind, float sign, float k,
-                  const float* gscale, float* gx, void* stream);
+int cn_reduce(const float* x, const float* y, const float* wgt, int wdiv, int64_t n, int kind,
+              float sign, float scale, float* ws, float* result, void* stream);
+/* gx = gscale[0] * k * wgt * d(term)/dx */
+int cn_reduce_bwd(const float* x, const float* y, const float* wgt, int wdiv, int64_t n, int kind,
+                  float sign, float k, const float* gscale, float* gx, void* stream);
 
 /* images: (x+1)*127.5 clipped to [0,255], truncated to uint8 (confignet_first_stage.py:636-637) */
 int cn_to_uint8(const float* x, uint8_t* out, int64_t n, void* stream);
@@ -131,6 +144,15 @@ int cn_vgg_preprocess(const float* x, float* out, int64_t npix, int backward, vo
 int cn_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
                      float lr_t, float b1, float b2, float eps, float ema_alpha, float gscale,
                      void* stream);
+
+/* dst[dst_off[i] : dst_off[i]+n[i]] = src[i] (zeros when src[i] is NULL) for i < count: packs the
+ * per-variable gradients tape.gradient returns (confignet_first_stage.py:472-474,556-558) into the flat
+ * buffer the all-reduce and cn_adam_ema_step run on.  src/dst_off/n are HOST arrays. */
+#define CN_MULTI_MAX 48
+int cn_multi_copy(int count, const float* const* src, const int64_t* dst_off, const int64_t* n,
+                  float* dst, void* stream);
+/* ema = alpha*ema + (1-alpha)*p (update_smoothed_weights, confignet_first_stage.py:393-400) */
+int cn_ema(float* ema, const float* p, int64_t n, float alpha, void* stream);
 
 #ifdef __cplusplus
 }

@@ -481,3 +481,48 @@ def grads_of(loss, params):
     ps = list(params.values())
     gs = torch.autograd.grad(loss, ps, allow_unused=True)
     return [torch.zeros_like(p) if g is None else g for g, p in zip(gs, ps)]
+
+
+# ----------------------------------------------------------------------------- whole training iteration (CPU)
+
+
+class OracleFirstStage:
+    """CPU restatement of the first-stage step loop (confignet_first_stage.py:466-560,597-617) used as the
+    timed CPU baseline (bench.py) - same step functions, same synthetic inputs, torch-CPU fp32."""
+
+    def __init__(self, facemodel_inputs, output_res=256, seed=1234, dtype=torch.float32):
+        from confignet_b200 import netspec          # parameter tables only (pure NumPy, no CUDA)
+        self.fm, self.res, self.dtype = facemodel_inputs, output_res, dtype
+        mk = lambda spec, s, **kw: to_torch(netspec.init_params(spec, s, **kw), dtype=dtype, requires_grad=True)
+        self.p_se = mk(netspec.synthetic_encoder_spec(facemodel_inputs, 2), seed + 1)
+        self.p_d = mk(netspec.discriminator_spec(output_res), seed + 2)
+        self.p_sd = mk(netspec.discriminator_spec(output_res), seed + 3)
+        self.p_ld = mk(netspec.latent_discriminator_spec(145, 4), seed + 4)
+        self.p_lr = mk(netspec.latent_regressor_spec(145, output_res), seed + 5)
+        self.p_g = mk(netspec.generator_spec(145, output_res), seed + 6)
+        self.p_gs = to_torch({k: v.detach().numpy() for k, v in self.p_g.items()}, dtype=dtype)
+        self.p_vgg = to_torch(netspec.init_params(netspec.vgg19_spec(), seed + 7, vgg_like=True), dtype=dtype)
+        self.d_opt, self.g_opt = KerasAdam(), KerasAdam()
+
+    def _t(self, a):
+        return torch.as_tensor(np.asarray(a)).to(self.dtype)
+
+    def discriminator_step(self, real_u8, latents, rotations):
+        real = self._t(real_u8) / 127.5 - 1.0
+        losses = discriminator_step_losses(self.p_d, self.p_g, real, self._t(latents), self._t(rotations), self.res)
+        self.d_opt.apply_gradients(zip(grads_of(losses["loss_sum"], self.p_d), self.p_d.values()))
+        return losses
+
+    def generator_step(self, facemodel_params, synth_rot, gt_u8, eye_masks, real_latents, real_rot):
+        batch = dict(facemodel_params=[self._t(a) for a in facemodel_params], synth_rotations=self._t(synth_rot),
+                     gt_imgs=self._t(gt_u8) / 127.5 - 1.0, eye_masks=eye_masks, real_latents=self._t(real_latents),
+                     real_rotations=self._t(real_rot))
+        losses = generator_step_losses(self.p_g, self.p_lr, self.p_se, self.p_d, self.p_sd, self.p_ld, self.p_vgg,
+                                       self.fm, batch, output_res=self.res)
+        allp = OrderedDict()
+        for pre, p in (("g/", self.p_g), ("lr/", self.p_lr), ("se/", self.p_se)):
+            for k, v in p.items():
+                allp[pre + k] = v
+        self.g_opt.apply_gradients(zip(grads_of(losses["loss_sum"], allp), allp.values()))
+        update_smoothed_weights(self.p_gs, self.p_g)
+        return losses
