@@ -140,7 +140,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------ our arm
 def losses_to_host(*loss_dicts):
     """One D2H read of every loss term (the reference does ~40 float() syncs per iteration)."""
-    vals = [v.reshape(1) for d in loss_dicts for v in d.values()]
+    vals = [v.detach().reshape(1) for d in loss_dicts for v in d.values()]
     return torch.cat(vals).cpu().numpy()
 
 
@@ -211,10 +211,10 @@ def run_b200(args):
     value = PER_GPU_BATCH * world / (ms * 1e-3)
 
     # ---- roofline of the tcgen05 conv kernels (events recorded around each launch in the timed region)
-    tc_flops = sum(f for (_, f, _, _, impl) in prof if impl == 2)
-    tc_ms = sum(a.elapsed_time(b) for (_, _, a, b, impl) in prof if impl == 2)
-    cc_ms = sum(a.elapsed_time(b) for (_, _, a, b, impl) in prof if impl != 2)
-    all_flops = sum(f for (_, f, _, _, _) in prof)
+    tc_flops = sum(p[1] for p in prof if p[4] == 2)
+    tc_ms = sum(p[2].elapsed_time(p[3]) for p in prof if p[4] == 2)
+    cc_ms = sum(p[2].elapsed_time(p[3]) for p in prof if p[4] != 2)
+    all_flops = sum(p[1] for p in prof)
     hbm, tensor_peak, how = measured_peaks()
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
@@ -225,6 +225,23 @@ def run_b200(args):
                 "algorithmic_conv_tflop_per_step": all_flops / args.steps / 1e12,
                 "step_algorithmic_tflops": all_flops / args.steps / 1e12 / (ms * 1e-3)}
 
+    if args.breakdown and rank == 0:
+        agg = {}
+        for (op, f, a, b, impl, key) in prof:
+            k = (op, key, impl)
+            t = agg.setdefault(k, [0, 0.0, 0.0])
+            t[0] += 1; t[1] += a.elapsed_time(b); t[2] += f
+        rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
+        with open(args.breakdown, "w") as fp:
+            fp.write("per-step conv/dense launches, %d steps averaged; impl 2 = tcgen05, 1 = CUDA-core\n" % args.steps)
+            fp.write("%-6s %-62s impl calls   ms/step  TFLOP/s\n" % ("op", "(nd,batch,in_dims,cin,cout,ksize,stride,upsample)"))
+            for (op, key, impl), (n, t, f) in rows:
+                fp.write("%-6s %-62s %4d %5d %9.3f %8.2f\n" % (op, str(key), impl, n // args.steps, t / args.steps,
+                                                             f / (t * 1e-3) / 1e12 if t > 0 else 0))
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms, "note": "profiling run (no e2e leg)"}), flush=True)
+        return
     # ---- e2e: public API, host datasets, H2D + D2H inside the timed region
     for _ in range(2):
         d, g = step(host_real, host_synth)
@@ -273,6 +290,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
+    ap.add_argument("--breakdown", default=None, help="write a per-layer conv time table to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -105,7 +105,7 @@ def _timed(op, g, fn):
     e0.record()
     fn()
     e1.record()
-    prof.append((op, _flops(g), e0, e1, L.load().cn_last_conv_impl()))
+    prof.append((op, _flops(g), e0, e1, L.load().cn_last_conv_impl(), g.desc.key()))
 
 
 def _conv_fwd_raw(g, x, w, bias, act=L.ACT_NONE, alpha=0.0):

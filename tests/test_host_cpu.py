@@ -1,0 +1,271 @@
+"""CPU-only tests (-m "not gpu"): the oracle against golden vectors produced by the reference's own host
+logic, the integer geometry shared by all conv kernels, the hand-derived normalisation formulas, the C ABI
+surface, and the data-parallel host logic over gloo (world_size 2)."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from oracle import confignet_oracle as O
+from confignet_b200 import netspec
+import norm_formulas as F
+
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_host_logic.json")))
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from confignet_b200 import _lib as L
+    lib = L.load()
+    header = open(os.path.join(ROOT, "include", "confignet_b200.h")).read()
+    declared = set(re.findall(r"\b(cn_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(lib, name), "symbol %s declared in the header but not exported" % name
+    bound = set(L.SIGNATURES) | set(L.NO_STATUS)
+    assert declared <= bound | {"cn_debug_conv_host"}, declared - bound
+    assert lib.cn_version() >= 1
+
+
+def test_missing_cuda_fails_loudly():
+    """No CPU fallback: operators refuse CPU tensors instead of silently computing elsewhere."""
+    from confignet_b200 import ops, _lib as L
+    with pytest.raises(L.CnError):
+        ops.lrelu(torch.zeros(4), 0.3)
+
+
+# ------------------------------------------------------------------------------------------------ plan geometry
+CASES = [(2, 2, (8, 8), 3, 5, 4, 1, 1), (2, 2, (8, 8), 3, 5, 3, 2, 1), (2, 1, (7, 9), 2, 3, 3, 2, 1),
+         (2, 2, (4, 6), 3, 4, 4, 1, 2), (3, 1, (4, 4, 4), 2, 3, 3, 1, 2), (3, 1, (4, 5, 3), 2, 3, 3, 1, 1),
+         (2, 2, (8, 8), 3, 5, 1, 1, 1), (2, 1, (5, 5), 2, 2, 3, 1, 1), (0, 5, (), 7, 3, 1, 1, 1),
+         (2, 1, (1, 1), 2, 3, 3, 2, 1), (3, 1, (3, 3, 3), 1, 2, 3, 2, 1)]
+
+
+@pytest.mark.parametrize("cfg", CASES)
+def test_plan_geometry_matches_oracle(cfg):
+    """TF SAME padding, stride-2 dgrad phases, fused upsample, tap tables: the host evaluation of the very
+    plans the kernels consume must equal the oracle's conv / its autograd gradients."""
+    from confignet_b200 import _lib as L
+    lib = L.load()
+    lib.cn_debug_conv_host.restype = ctypes.c_int
+    nd, B, dims, cin, cout, k, s, up = cfg
+    rng = np.random.RandomState(0)
+    d = L.make_conv_desc(nd, B, dims, cin, cout, [k] * nd, s, up)
+    x = rng.randn(B, *dims, cin).astype(np.float32)
+    w = rng.randn(*([k] * nd), cin, cout).astype(np.float32)
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    wt = torch.tensor(w, dtype=torch.float64, requires_grad=True)
+    xu = O.upsample_nearest2(xt) if up == 2 else xt
+    y = xt @ wt if nd == 0 else O.conv_same(xu, wt, None, s)
+    gy = rng.randn(*y.shape).astype(np.float32)
+    gx, gw = torch.autograd.grad(y, (xt, wt), torch.tensor(gy, dtype=torch.float64))
+    fp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    out = np.zeros(y.shape, np.float32)
+    assert lib.cn_debug_conv_host(ctypes.byref(d), 0, fp(x), fp(w), fp(out)) == 0
+    ogx = np.full(x.shape, 7.0, np.float32)
+    assert lib.cn_debug_conv_host(ctypes.byref(d), 1, fp(gy), fp(w), fp(ogx)) == 0
+    ogw = np.zeros(w.shape, np.float32)
+    assert lib.cn_debug_conv_host(ctypes.byref(d), 2, fp(x), fp(gy), fp(ogw)) == 0
+    assert np.abs(out - y.detach().numpy()).max() < 1e-4
+    assert np.abs(ogx - gx.numpy()).max() < 1e-4
+    assert np.abs(ogw - gw.numpy()).max() < 1e-4
+
+
+def test_conv_desc_errors():
+    from confignet_b200 import _lib as L
+    lib = L.load()
+    od = (ctypes.c_int * 3)()
+    bad = L.make_conv_desc(2, 1, (8, 8), 4, 4, (3, 3), 2, 2)          # stride 2 + fused upsample
+    assert lib.cn_conv_out_dims(ctypes.byref(bad), od) != 0
+    assert b"unsupported" in lib.cn_last_error()
+    bad = L.make_conv_desc(1, 1, (8,), 4, 4, (3,), 1, 1)               # nd = 1
+    assert lib.cn_conv_out_dims(ctypes.byref(bad), od) != 0
+    ok = L.make_conv_desc(2, 1, (7, 9), 4, 4, (3, 3), 2, 1)
+    assert lib.cn_conv_out_dims(ctypes.byref(ok), od) == 0 and tuple(od[:2]) == (4, 5)
+
+
+# ------------------------------------------------------------------------------------------------ oracle vs reference goldens
+def test_oracle_latent_layout_matches_reference_golden():
+    fm = netspec.default_facemodel_inputs()
+    assert [[k, list(v)] for k, v in fm.items()] == GOLD["facemodel_inputs_sorted"]
+    for name, (lo, hi) in GOLD["latent_idxs"].items():
+        r = O.facemodel_param_idxs_in_latent(fm, name)
+        assert (r.start, r.stop) == (lo, hi)
+    assert sum(v[1] for v in fm.values()) == GOLD["latent_dim"] == 145
+
+
+def test_class_surface_host_logic_matches_reference_golden():
+    from confignet_b200.confignet_first_stage import ConfigNetFirstStage, merge_configs, flip_random_subset_of_images, DEFAULT_CONFIG
+    fm = {k: tuple(v) for k, v in netspec.default_facemodel_inputs().items()}
+    m = ConfigNetFirstStage({"output_shape": (256, 256, 3), "batch_size": 4, "facemodel_inputs": fm},
+                            initialize=False, device="cpu")
+    assert m.config["latent_dim"] == GOLD["latent_dim"] and m.facemodel_input_dim == GOLD["facemodel_input_dim"]
+    assert [[k, list(v)] for k, v in m.config["facemodel_inputs"].items()] == GOLD["facemodel_inputs_sorted"]
+    for name, (lo, hi) in GOLD["latent_idxs"].items():
+        r = m.get_facemodel_param_idxs_in_latent(name)
+        assert (r.start, r.stop) == (lo, hi)
+    for k, v in GOLD["merged_scalar_keys"].items():
+        assert m.config[k] == v
+    assert m.config["optimizer"] == GOLD["merged_optimizer"]
+    fm2 = {k: ((v[0] if k != "head_hair_color" else None), v[1]) for k, v in fm.items()}
+    m2 = ConfigNetFirstStage({"facemodel_inputs": fm2}, initialize=False, device="cpu")
+    assert m2.config["latent_dim"] == GOLD["layout2_latent_dim"]
+    for name, (lo, hi) in GOLD["layout2_idxs"].items():
+        r = m2.get_facemodel_param_idxs_in_latent(name)
+        assert (r.start, r.stop) == (lo, hi)
+    for case in GOLD["merge_cases"]:
+        assert merge_configs(case["default"], case["input"]) == case["result"]
+    np.random.seed(0)
+    assert np.array_equal(m.sample_rotations(5), np.array(GOLD["sample_rotations_seed0_n5"], np.float32))
+    assert np.array_equal(m.sample_latent_vector(2), np.array(GOLD["sample_latent_seed0_after_rot_n2"]))
+    np.random.seed(0)
+    imgs = np.arange(4 * 2 * 3 * 3, dtype=np.float32).reshape(4, 2, 3, 3)
+    assert np.array_equal(flip_random_subset_of_images(imgs.copy()), np.array(GOLD["flip_seed0_result"], np.float32))
+
+    class _FakeMLP:
+        def predict(self, v):
+            return np.full((v.shape[0], 30), 9.0, np.float32)
+
+    class _FakeEnc:
+        per_facemodel_input_mlps = {"blendshape_values": _FakeMLP()}
+    m.synthetic_encoder = _FakeEnc()
+    lat = np.zeros((2, 145), np.float32)
+    new = m.set_facemodel_param_in_latents(lat, "blendshape_values", np.zeros(62, np.float32))
+    assert np.nonzero(new[0])[0].tolist() == GOLD["set_param_changed_columns"] and (lat == 0).all()
+
+
+def test_reference_golden_npz_shapes_are_what_generate_images_returns():
+    g = GOLD["reference_golden_npz_shapes"]
+    assert g["confignet_basic_ref_256"]["decoded_image"] == [[1, 256, 256, 3], "uint8"]
+    assert g["confignet_basic_ref_256"]["rotation"][0] == [1, 3]
+    assert g["latentgan_ref_256"]["generated_imgs"] == [[1, 256, 256, 3], "uint8"]
+    # our uint8 conversion on the oracle side has the same dtype / truncation semantics
+    x = np.array([[-2.0, -1.0, -0.999, 0.0, 0.5, 0.9999, 1.0, 3.0]], np.float32)
+    assert O.to_uint8_images(x).tolist() == [[0, 0, 0, 127, 191, 254, 255, 255]]
+
+
+# ------------------------------------------------------------------------------------------------ oracle self-consistency
+def test_oracle_conv_same_against_numpy_loops():
+    rng = np.random.RandomState(1)
+    for (h, w, cin, cout, k, s) in [(5, 6, 2, 3, 4, 1), (6, 6, 2, 2, 3, 2), (5, 7, 1, 2, 3, 2), (4, 4, 3, 2, 1, 1)]:
+        x = rng.randn(1, h, w, cin); wt = rng.randn(k, k, cin, cout)
+        oh, ow = -(-h // s), -(-w // s)
+        ph = max((oh - 1) * s + k - h, 0) // 2; pw = max((ow - 1) * s + k - w, 0) // 2
+        ref = np.zeros((1, oh, ow, cout))
+        for i in range(oh):
+            for j in range(ow):
+                for a in range(k):
+                    for b in range(k):
+                        yy, xx = i * s + a - ph, j * s + b - pw
+                        if 0 <= yy < h and 0 <= xx < w:
+                            ref[0, i, j] += x[0, yy, xx] @ wt[a, b]
+        got = O.conv_same(torch.tensor(x), torch.tensor(wt), None, s).numpy()
+        assert np.abs(got - ref).max() < 1e-10
+    assert O.same_pad(16, 4, 1) == (1, 2) and O.same_pad(16, 3, 1) == (1, 1) and O.same_pad(16, 3, 2) == (0, 1)
+
+
+def test_oracle_rotation_and_generator_invariants():
+    g = torch.randn(2, 16, 16, 16, 4, dtype=torch.float64)
+    out = O.transform_3d_grid(g, O.euler_angles_to_matrix(torch.zeros(2, 3, dtype=torch.float64)))
+    assert torch.equal(out, g)                                  # zero rotation: diffs = 0, exact copy
+    R = O.euler_angles_to_matrix(torch.tensor([[0.3, -0.2, 0.1]], dtype=torch.float64))[0]
+    assert torch.allclose(R @ R.T, torch.eye(3, dtype=torch.float64), atol=1e-12)
+    p = O.to_torch(netspec.init_params(netspec.generator_spec(145, 256), 3))
+    assert float(p["learned_input/kernel"].abs().max()) == 0 and float(p["learned_input/bias"].min()) == 1
+    with torch.no_grad():
+        img = O.generator_forward(p, torch.randn(1, 145), torch.tensor([[0.1, 0.05, 0.0]]), 256)
+    assert img.shape == (1, 256, 256, 3) and torch.isfinite(img).all() and float(img.abs().max()) <= 1
+
+
+def test_oracle_keras_adam_first_step_is_sign_like():
+    """beta_1 = 0: the first update is lr * g / (|g| + eps') - the [TF-2.1] formula with eps outside the sqrt."""
+    p = torch.tensor([1.0, -2.0, 3.0], requires_grad=True)
+    g = torch.tensor([0.5, -0.25, 0.0])
+    opt = O.KerasAdam()
+    opt.apply_gradients([(g, p)])
+    lr_t = 0.0004 * np.sqrt(1 - 0.9) / (1 - 0.0)
+    v = 0.1 * g.numpy() ** 2
+    want = np.array([1.0, -2.0, 3.0]) - lr_t * g.numpy() / (np.sqrt(v) + 1e-7)
+    assert np.allclose(p.detach().numpy(), want, rtol=1e-6) and opt.iterations == 1
+
+
+# ------------------------------------------------------------------------------------------------ normalisation formulas
+def test_norm_formulas_first_and_second_order():
+    torch.manual_seed(0)
+    dt = torch.float64
+    n, H, W, ch, al = 3, 5, 4, 6, 0.3
+    N = H * W
+    c = torch.randn(n, H, W, ch, dtype=dt, requires_grad=True)
+    gam = torch.randn(ch, dtype=dt, requires_grad=True); bet = torch.randn(ch, dtype=dt, requires_grad=True)
+    y = O.instance_norm_std(O.lrelu(c, al), gam, bet)
+    S = F.sums7(c, flags=1, alpha=al)
+    assert (y - F.affine(c, None, None, F.coef(0, S, gam, bet, N, 1e-3)[0], 1, al)).abs().max() < 1e-12
+    gy = torch.randn_like(y, requires_grad=True)
+    gc, gg, gb = torch.autograd.grad(y, (c, gam, bet), gy, create_graph=True)
+    c0, _, dg, db = F.coef(1, F.sums7(c, gy, flags=1, alpha=al), gam, None, N, 1e-3)
+    assert (gc - F.affine(c, gy, None, c0, 3, al)).abs().max() < 1e-12 and (gg - dg).abs().max() < 1e-11 and (gb - db).abs().max() < 1e-11
+    h = torch.randn_like(gc)
+    d_c, d_g, d_gy = torch.autograd.grad(gc, (c, gam, gy), h)
+    cA, cB, dg2, _ = F.coef(2, F.sums7(c, gy, h, flags=5, alpha=al), gam, None, N, 1e-3)
+    assert (d_c - F.affine(c, gy, h, cA, 7, al)).abs().max() < 1e-11
+    assert (d_gy - F.affine(c, None, h, cB, 5, al)).abs().max() < 1e-11 and (d_g - dg2).abs().max() < 1e-10
+    st = O.layer_style(c)
+    S = F.sums7(c)
+    assert (st - F.coef(3, S, None, None, N, 1e-6)[2]).abs().max() < 1e-12
+    gs = torch.randn_like(st, requires_grad=True)
+    gc, = torch.autograd.grad(st, c, gs, create_graph=True)
+    assert (gc - F.affine(c, None, None, F.coef(4, S, gs, None, N, 1e-6)[0])).abs().max() < 1e-12
+    d_c, d_gs = torch.autograd.grad(gc, (c, gs), h)
+    c0, _, dgs, _ = F.coef(5, F.sums7(c, h), gs, None, N, 1e-6)
+    assert (d_c - F.affine(c, h, None, c0)).abs().max() < 1e-12 and (d_gs - dgs).abs().max() < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ data parallel (gloo, 2 ranks)
+_DP_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from collections import OrderedDict
+from confignet_b200 import netspec
+from confignet_b200.runtime import allreduce_grads, shard_rows, world
+from oracle import confignet_oracle as O
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, ws = world()
+arrays = netspec.perturb_params(netspec.init_params(netspec.latent_discriminator_spec(145, 4), 5), 6, 0.05)
+p = O.to_torch(arrays, dtype=torch.float64, requires_grad=True)
+rng = np.random.RandomState(0)                       # every rank draws the same global batch
+real, fake = rng.randn(8, 145), rng.randn(8, 145)
+lo, hi = shard_rows(8)
+assert (lo, hi) == (rank * 4, rank * 4 + 4)
+loss = O.compute_latent_discriminator_loss(p, torch.tensor(real[lo:hi]), torch.tensor(fake[lo:hi]))["loss_sum"]
+grads = O.grads_of(loss, p)
+class G: pass
+g = G(); g.grad = torch.cat([x.reshape(-1) for x in grads])
+scale = allreduce_grads([g])
+full = O.compute_latent_discriminator_loss(p, torch.tensor(real), torch.tensor(fake))["loss_sum"]
+want = torch.cat([x.reshape(-1) for x in O.grads_of(full, p)])
+err = float((g.grad * scale - want).abs().max() / want.abs().max())
+assert scale == 0.5 and err < 1e-12, err
+dist.destroy_process_group()
+print("rank", rank, "ok", err)
+'''
+
+
+def test_data_parallel_gradient_average_equals_global_batch(tmp_path):
+    script = tmp_path / "dp_worker.py"
+    script.write_text(_DP_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
