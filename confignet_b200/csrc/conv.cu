@@ -796,6 +796,132 @@ igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Skinny layers (HBM-bound): dedicated CUDA-core kernels
+// ------------------------------------------------------------------------------------------------
+// Pixel mode with Cn <= 4 outputs per pixel (map_final 32->3, dgrad into 3-channel images): one thread per
+// output pixel, weights in shared memory (broadcast reads), float4 walks over the source channels.
+__global__ void __launch_bounds__(256)
+pixel_smalln_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ W,
+                    const float* __restrict__ bias, float* __restrict__ D, int act, float alpha) {
+  extern __shared__ float s_w[];                 // [Ktot][4] (n padded to 4)
+  __shared__ int2 s_taps[256];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < p.ntaps; i += 256) s_taps[i] = p.taps[i];
+  __syncthreads();
+  for (int i = tid; i < p.Ktot * 4; i += 256) {
+    int k = i >> 2, n = i & 3;
+    int kt = k / p.Csrc, c = k - kt * p.Csrc;
+    s_w[i] = (n < p.Cn) ? W[(size_t)s_taps[kt].y + (size_t)c * p.wsc + (size_t)n * p.wsn] : 0.f;
+  }
+  __syncthreads();
+  const int m = blockIdx.x * 256 + tid;
+  if (m >= p.M) return;
+  const RowInfo ri = decode_row(p, m);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool vec = (p.Csrc & 3) == 0;
+  for (int kt = 0; kt < p.ntaps; ++kt) {
+    const uint32_t sp = src_pixel(p, ri, s_taps[kt].x);
+    if (sp == 0xffffffffu) continue;
+    const float* src = A + (size_t)sp * p.Csrc;
+    const float4* wv = reinterpret_cast<const float4*>(s_w) + (size_t)kt * p.Csrc;
+    if (vec) {
+      for (int c = 0; c < p.Csrc; c += 4) {
+        const float4 x = ldg128(src + c);
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w4 = wv[c + q];
+          acc[0] = fmaf(xs[q], w4.x, acc[0]); acc[1] = fmaf(xs[q], w4.y, acc[1]);
+          acc[2] = fmaf(xs[q], w4.z, acc[2]); acc[3] = fmaf(xs[q], w4.w, acc[3]);
+        }
+      }
+    } else {
+      for (int c = 0; c < p.Csrc; ++c) {
+        const float x = __ldg(src + c);
+        const float4 w4 = wv[c];
+        acc[0] = fmaf(x, w4.x, acc[0]); acc[1] = fmaf(x, w4.y, acc[1]);
+        acc[2] = fmaf(x, w4.z, acc[2]); acc[3] = fmaf(x, w4.w, acc[3]);
+      }
+    }
+  }
+  float* out = D + (size_t)dest_pixel(p, m) * p.Cn;
+  for (int n = 0; n < p.Cn; ++n) {
+    float v = acc[n] + (bias ? bias[n] : 0.f);
+    out[n] = cn_apply_act(v, act, alpha);
+  }
+}
+
+// Wgrad with few outputs (Ktot*Cn <= 2304: Cin = 3 or Cout = 3 layers): each block stages P pixels
+// (gathered source patch + gradient row) in shared memory, each thread owns up to 9 (k,n) outputs.
+constexpr int SKW_MAXOUT = 9;
+__global__ void __launch_bounds__(256)
+wgrad_skinny_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ G,
+                    float* __restrict__ D, int P, int pix_per_block) {
+  extern __shared__ float sm[];                  // xs[P][Ktot], gs[P][Cn]
+  __shared__ int2 s_taps[256];
+  __shared__ RowInfo s_rows[64];
+  float* xs = sm;
+  float* gs = sm + (size_t)P * p.Ktot;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < p.ntaps; i += 256) s_taps[i] = p.taps[i];
+  const int O = p.Ktot * p.Cn;
+  int ok[SKW_MAXOUT], on[SKW_MAXOUT];
+  float acc[SKW_MAXOUT];
+#pragma unroll
+  for (int j = 0; j < SKW_MAXOUT; ++j) {
+    int o = tid + 256 * j;
+    ok[j] = (o < O) ? o / p.Cn : -1;
+    on[j] = (o < O) ? o % p.Cn : 0;
+    acc[j] = 0.f;
+  }
+  const int mbeg = blockIdx.x * pix_per_block, mend = min(p.M, mbeg + pix_per_block);
+  for (int m0 = mbeg; m0 < mend; m0 += P) {
+    __syncthreads();
+    if (tid < P) s_rows[tid] = decode_row(p, (m0 + tid < mend) ? m0 + tid : p.M);
+    __syncthreads();
+    for (int i = tid; i < P * p.Ktot; i += 256) {
+      int pp = i / p.Ktot, k = i - pp * p.Ktot;
+      int kt = k / p.Csrc, c = k - kt * p.Csrc;
+      uint32_t sp = src_pixel(p, s_rows[pp], s_taps[kt].x);
+      xs[i] = (sp != 0xffffffffu) ? __ldg(A + (size_t)sp * p.Csrc + c) : 0.f;
+    }
+    for (int i = tid; i < P * p.Cn; i += 256) {
+      int pp = i / p.Cn;
+      gs[i] = (m0 + pp < mend) ? __ldg(G + (size_t)(m0 + pp) * p.Cn + (i - pp * p.Cn)) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SKW_MAXOUT; ++j) {
+      if (ok[j] < 0) continue;
+      const float* xk = xs + ok[j];
+      const float* gn = gs + on[j];
+      float a = acc[j];
+      for (int pp = 0; pp < P; ++pp) a = fmaf(xk[(size_t)pp * p.Ktot], gn[(size_t)pp * p.Cn], a);
+      acc[j] = a;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < SKW_MAXOUT; ++j)
+    if (ok[j] >= 0) atomicAdd(D + tid + 256 * j, acc[j]);
+}
+
+// column sums for narrow matrices (n < 32): flat coalesced walk, every thread stays on one column
+__global__ void __launch_bounds__(256)
+colsum_narrow_kernel(const float* __restrict__ g, size_t total, int n, int threads_used, float* __restrict__ out) {
+  __shared__ float s_acc[32];
+  if (threadIdx.x < 32) s_acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int gt = blockIdx.x * 256 + threadIdx.x;
+  if (gt < threads_used) {
+    float acc = 0.f;
+    for (size_t i = gt; i < total; i += threads_used) acc += g[i];
+    atomicAdd(&s_acc[gt % n], acc);
+  }
+  __syncthreads();
+  if (threadIdx.x < n) atomicAdd(out + threadIdx.x, s_acc[threadIdx.x]);
+}
+
 // column sums of a (rows, n) matrix: bias gradient
 __global__ void colsum_kernel(const float* __restrict__ g, int rows, int n, float* __restrict__ out) {
   // grid.x covers columns in groups of 32, grid.y splits rows; blockDim = (32, 8)
@@ -884,7 +1010,12 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
     return CN_OK;
   }
   // CUDA-core path
-  if (g.Cn <= 4) {
+  if (g.Cn <= 4 && g.M >= 4096 && g.Ktot * 16 <= 96 * 1024) {
+    dim3 grid((g.M + 255) / 256, 1, 1);
+    int smem = g.Ktot * 16;
+    if (smem > 48 * 1024 && set_smem(pixel_smalln_kernel, smem)) return CN_ERR_CUDA;
+    pixel_smalln_kernel<<<grid, 256, smem, st>>>(g, src, w, bias, dst, act, alpha);
+  } else if (g.Cn <= 4 && g.M >= 4096) {
     dim3 grid((g.M + 255) / 256, 1, 1);
     igemm_ffma_kernel<MODE_PIXEL, 256, 4, 1, 4><<<grid, 256, 0, st>>>(g, src, w, bias, dst, act, alpha, g.Ktot > 0 ? g.Ktot : 1, 0);
   } else {
@@ -975,6 +1106,16 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
     int cols = pow2_cols(3 * ((bn_smem + 31) / 32 * 32));
     igemm_tc_wgrad_kernel<<<grid, TC_THREADS, smem, st>>>(g, x, gy, gw, bn, bn_smem, nstages, cols, per, split > 1);
     CN_CHECK_LAUNCH();
+  } else if ((long long)g.Ktot * g.Cn <= 256 * SKW_MAXOUT && g.M >= 4096) {
+    int P = 8192 / (g.Ktot + g.Cn); if (P > 64) P = 64; if (P < 4) P = 4;
+    int smem = P * (g.Ktot + g.Cn) * (int)sizeof(float);
+    int blocks = 4 * num_sms();
+    int per = ((g.M + blocks - 1) / blocks + P - 1) / P * P;
+    blocks = (g.M + per - 1) / per;
+    CN_CHECK_CUDA(cudaMemsetAsync(gw, 0, wn * sizeof(float), st));
+    if (smem > 48 * 1024 && set_smem(wgrad_skinny_kernel, smem)) return CN_ERR_CUDA;
+    wgrad_skinny_kernel<<<blocks, 256, smem, st>>>(g, x, gy, gw, P, per);
+    CN_CHECK_LAUNCH();
   } else {
     int mt = (g.Ktot + 63) / 64, nt = (g.Cn + 63) / 64;
     int split = (2 * num_sms() + mt * nt - 1) / (mt * nt);
@@ -989,9 +1130,16 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
   }
   if (gbias != nullptr) {
     CN_CHECK_CUDA(cudaMemsetAsync(gbias, 0, (size_t)g.Cn * sizeof(float), st));
-    int ysplit = (g.M + 2047) / 2048; if (ysplit > 256) ysplit = 256; if (ysplit < 1) ysplit = 1;
-    dim3 grid((g.Cn + 31) / 32, ysplit), block(32, 8);
-    colsum_kernel<<<grid, block, 0, st>>>(gy, g.M, g.Cn, gbias);
+    if (g.Cn < 32) {
+      size_t total = (size_t)g.M * g.Cn;
+      int blocks = (int)((total / 16 + 255) / 256); if (blocks > 4 * num_sms()) blocks = 4 * num_sms(); if (blocks < 1) blocks = 1;
+      int used = blocks * 256 / g.Cn * g.Cn;
+      colsum_narrow_kernel<<<blocks, 256, 0, st>>>(gy, total, g.Cn, used, gbias);
+    } else {
+      int ysplit = (g.M + 511) / 512; if (ysplit > 8 * num_sms()) ysplit = 8 * num_sms(); if (ysplit < 1) ysplit = 1;
+      dim3 grid((g.Cn + 31) / 32, ysplit), block(32, 8);
+      colsum_kernel<<<grid, block, 0, st>>>(gy, g.M, g.Cn, gbias);
+    }
     CN_CHECK_LAUNCH();
   }
   (void)conv_numel_x;
