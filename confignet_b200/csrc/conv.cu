@@ -393,12 +393,14 @@ __device__ __forceinline__ uint32_t f2tf32(float f) {
   return r;
 }
 __device__ __forceinline__ void sts_split4(uint32_t addr_big, uint32_t addr_small, float4 v) {
+  // big = x with the 13 low mantissa bits cleared (exactly a tf32), small = tf32-truncated (x - big): the
+  // subtraction is exact, so x = big + small up to 2^-21 |x|; 3 ALU ops per element instead of 2 cvt + 1 sub.
   const float x[4] = {v.x, v.y, v.z, v.w};
   uint32_t bg[4], sm[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    bg[i] = f2tf32(x[i]);
-    sm[i] = f2tf32(x[i] - __uint_as_float(bg[i]));
+    bg[i] = __float_as_uint(x[i]) & 0xffffe000u;
+    sm[i] = __float_as_uint(x[i] - __uint_as_float(bg[i])) & 0xffffe000u;
   }
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr_big), "r"(bg[0]), "r"(bg[1]), "r"(bg[2]), "r"(bg[3]) : "memory");
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr_small), "r"(sm[0]), "r"(sm[1]), "r"(sm[2]), "r"(sm[3]) : "memory");
@@ -540,7 +542,7 @@ template <int B_MN>
 __global__ void __launch_bounds__(TC_THREADS)
 igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ W,
                       const float* __restrict__ bias, float* __restrict__ D, int act, float alpha,
-                      int bn, int bn_smem, int nstages, int tmem_cols) {
+                      int bn, int bn_smem, int nstages, int tmem_cols, int kb_per_split, int use_atomic) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const TcSmemLayout L = tc_layout(nstages, bn_smem);
@@ -552,7 +554,9 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
   int2* s_taps = reinterpret_cast<int2*>(smem + L.taps_off);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * bn;
-  const int num_kb = (p.Ktot + TC_BK - 1) / TC_BK;
+  const int total_kb = (p.Ktot + TC_BK - 1) / TC_BK;
+  const int kb_beg = blockIdx.z * kb_per_split;             // split-K over gridDim.z (atomic epilogue)
+  const int num_kb = min(total_kb, kb_beg + kb_per_split) - kb_beg;   // host guarantees >= 1
 
   for (int i = tid; i < p.ntaps; i += TC_THREADS) s_taps[i] = p.taps[i];
   if (tid == 0) {
@@ -571,32 +575,52 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < 4) {
-    // ===== A gather: 8 threads per 128-byte row (one 16-byte chunk each), 8 rows per thread =====
+    // ===== A gather: 8 threads per 128-byte row (one 16-byte chunk each), 8 rows per thread.
+    //       The loads of k-block kb+1 are issued before k-block kb is converted and stored, so one
+    //       memory latency is always overlapped with the split/STS work and the barrier wait. =====
     const int j = tid & 7;
     RowInfo rows[8];
+    uint32_t soff[8], spoff[8];          // smem offsets of this thread's 8 chunks; source element offsets
 #pragma unroll
-    for (int i = 0; i < 8; ++i) rows[i] = decode_row(p, m0 + (tid >> 3) + 16 * i);
+    for (int i = 0; i < 8; ++i) {
+      const int r = (tid >> 3) + 16 * i;
+      rows[i] = decode_row(p, m0 + r);
+      soff[i] = r * 128 + ((j ^ (r & 7)) << 4);
+      spoff[i] = 0xffffffffu;
+    }
+    // (tap, channel) of this thread's chunk advance by 32 channels per k-block; the 8 source pixels are
+    // recomputed only when the tap changes (every Csrc/32 k-blocks)
+    int kt_cur = (kb_beg * TC_BK + 4 * j) / p.Csrc, c_cur = kb_beg * TC_BK + 4 * j - kt_cur * p.Csrc, kt_have = -1;
+    auto load_a = [&](int it, float4* v) {
+      const bool kok = (kb_beg + it) * TC_BK + 4 * j < p.Ktot;
+      if (kok && kt_cur != kt_have) {
+        const int tap_pk = s_taps[kt_cur].x;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint32_t sp = src_pixel(p, rows[i], tap_pk);
+          spoff[i] = (sp != 0xffffffffu) ? sp * (uint32_t)p.Csrc : 0xffffffffu;
+        }
+        kt_have = kt_cur;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        v[i] = (kok && spoff[i] != 0xffffffffu) ? ldg128(A + (size_t)spoff[i] + c_cur) : make_float4(0.f, 0.f, 0.f, 0.f);
+      c_cur += TC_BK;
+      while (c_cur >= p.Csrc) { c_cur -= p.Csrc; ++kt_cur; }
+    };
+    float4 cur[8], nxt[8];
+    load_a(0, cur);
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % nstages;
+      if (kb + 1 < num_kb) load_a(kb + 1, nxt);
       if (kb >= nstages) mbar_wait(bar_empty + 8 * s, ((kb / nstages) - 1) & 1);
-      const int k = kb * TC_BK + 4 * j;
-      int tap_pk = 0, c = 0; bool kok = k < p.Ktot;
-      if (kok) { int kt = k / p.Csrc; c = k - kt * p.Csrc; tap_pk = s_taps[kt].x; }
-      float4 v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint32_t sp = kok ? src_pixel(p, rows[i], tap_pk) : 0xffffffffu;
-        v[i] = (sp != 0xffffffffu) ? ldg128(A + (size_t)sp * p.Csrc + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
       const uint32_t abase = sbase + s * L.stage_bytes;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int r = (tid >> 3) + 16 * i;
-        uint32_t off = r * 128 + ((j ^ (r & 7)) << 4);
-        sts_split4(abase + off, abase + TC_A_BYTES + off, v[i]);
-      }
+      for (int i = 0; i < 8; ++i) sts_split4(abase + soff[i], abase + TC_A_BYTES + soff[i], cur[i]);
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
     }
   } else if (warp >= 8 && warp < 12) {
     // ===== promotion + epilogue: TMEM -> registers -> global (warp pw owns TMEM lanes 32pw..32pw+31) =====
@@ -614,6 +638,11 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
             float4 o;
             o.x = __uint_as_float(v[q]); o.y = __uint_as_float(v[q + 1]);
             o.z = __uint_as_float(v[q + 2]); o.w = __uint_as_float(v[q + 3]);
+            if (use_atomic) {
+              atomicAdd(D + rowoff + n, o.x); atomicAdd(D + rowoff + n + 1, o.y);
+              atomicAdd(D + rowoff + n + 2, o.z); atomicAdd(D + rowoff + n + 3, o.w);
+              continue;
+            }
             if (bias != nullptr) { o.x += bias[n]; o.y += bias[n + 1]; o.z += bias[n + 2]; o.w += bias[n + 3]; }
             o.x = cn_apply_act(o.x, act, alpha); o.y = cn_apply_act(o.y, act, alpha);
             o.z = cn_apply_act(o.z, act, alpha); o.w = cn_apply_act(o.w, act, alpha);
@@ -623,43 +652,63 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
       }
     });
   } else if (warp < 8) {
-    // ===== B gather =====
+    // ===== B gather (batched loads + one k-block of register prefetch, like the A gather) =====
     const int t = tid - 128;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % nstages;
-      if (kb >= nstages) mbar_wait(bar_empty + 8 * s, ((kb / nstages) - 1) & 1);
-      const uint32_t bbase = sbase + s * L.stage_bytes + L.b_off;
+    // MN-major: 32 k-rows x bn_smem columns, chunk = 4 output channels; bn_smem in {32,64,128} so that every
+    // thread keeps one column chunk jc and walks rows r0, r0+rstep, ...  K-major: bn_smem rows (n) x 32 k.
+    const int cpr = bn_smem >> 2;
+    const int jc = B_MN ? (t % cpr) : (t & 7);
+    const int r0 = B_MN ? (t / cpr) : (t >> 3);
+    const int rstep = B_MN ? (128 / cpr) : 16;
+    const int nrows = B_MN ? TC_BK : bn_smem;
+    const uint32_t sbo = (uint32_t)(bn_smem >> 5) * 512u;
+    uint32_t boff[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + i * rstep;
+      boff[i] = B_MN ? mn_chunk_off(r, jc, sbo) : (uint32_t)(r * 128 + ((jc ^ (r & 7)) << 4));
+    }
+    auto load_b = [&](int it, float4* v) {
+      const int k0 = (kb_beg + it) * TC_BK;
       if (B_MN) {
-        // 32 k-rows x bn_smem columns, MN-major: chunks of 4 output channels
-        const int cpr = bn_smem >> 2;
-        const uint32_t sbo = (uint32_t)(bn_smem >> 5) * 512u;
-        for (int q = t; q < TC_BK * cpr; q += 128) {
-          int r = q / cpr, jc = q - r * cpr;
-          int k = kb * TC_BK + r, n = n0 + 4 * jc;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k < p.Ktot && n < p.Cn && 4 * jc < bn) {
-            int kt = k / p.Csrc; int c = k - kt * p.Csrc;
-            v = ldg128(W + (size_t)s_taps[kt].y + (size_t)c * p.wsc + n);
-          }
-          uint32_t off = mn_chunk_off(r, jc, sbo);
-          sts_split4(bbase + off, bbase + L.b_bytes + off, v);
+        const int n = n0 + 4 * jc;
+        const bool nok = n < p.Cn && 4 * jc < bn;
+        int kt = k0 / p.Csrc, c = k0 - kt * p.Csrc + r0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + i * rstep;
+          while (c >= p.Csrc) { c -= p.Csrc; ++kt; }
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < nrows && nok && k0 + r < p.Ktot) v[i] = ldg128(W + (size_t)s_taps[kt].y + (size_t)c * p.wsc + n);
+          c += rstep;
         }
       } else {
-        // bn_smem rows (n) x 32 k; K-major
-        const int j = t & 7;
-        const int k = kb * TC_BK + 4 * j;
-        int c = 0, wb = 0; bool kok = k < p.Ktot;
+        const int k = k0 + 4 * jc;
+        int c = 0, wb = 0; const bool kok = k < p.Ktot;
         if (kok) { int kt = k / p.Csrc; c = k - kt * p.Csrc; wb = s_taps[kt].y; }
-        for (int r = t >> 3; r < bn_smem; r += 16) {
-          int n = n0 + r;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kok && r < bn && n < p.Cn) v = ldg128(W + (size_t)wb + (size_t)n * p.wsn + c);
-          uint32_t off = r * 128 + ((j ^ (r & 7)) << 4);
-          sts_split4(bbase + off, bbase + L.b_bytes + off, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + i * rstep, n = n0 + r;
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < nrows && kok && r < bn && n < p.Cn) v[i] = ldg128(W + (size_t)wb + (size_t)n * p.wsn + c);
         }
+      }
+    };
+    float4 cur[8], nxt[8];
+    load_b(0, cur);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % nstages;
+      if (kb + 1 < num_kb) load_b(kb + 1, nxt);
+      if (kb >= nstages) mbar_wait(bar_empty + 8 * s, ((kb / nstages) - 1) & 1);
+      const uint32_t bbase = sbase + s * L.stage_bytes + L.b_off;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (r0 + i * rstep < nrows) sts_split4(bbase + boff[i], bbase + L.b_bytes + boff[i], cur[i]);
       }
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
     }
   } else {
     // ===== MMA issue (one lane) =====
@@ -717,17 +766,14 @@ igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
 
   if (warp < 4) {
     // ===== A gather: lane = 16-byte chunk of the 128 GEMM rows (fixed tap, 4 channels per thread),
-    //       warp w fills pixel rows 8w..8w+7 of the 32-pixel K block =====
+    //       warp w fills pixel rows 8w..8w+7 of the 32-pixel K block; one k-block of register prefetch =====
     const int rr = r0 + 4 * lane;
     const bool rok = rr < p.Ktot;
     int c = 0, tap_pk = 0;
     if (rok) { int kt = rr / p.Csrc; c = rr - kt * p.Csrc; tap_pk = s_taps[kt].x; }
-    for (int it = 0; it < num_kb; ++it) {
-      const int s = it % nstages;
-      if (it >= nstages) mbar_wait(bar_empty + 8 * s, ((it / nstages) - 1) & 1);
+    auto load_a = [&](int it, float4* v) {
       const int mbase = (kb_beg + it) * TC_BK + warp * 8;
       RowInfo mine = decode_row(p, mbase + (lane & 7));
-      float4 v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         RowInfo ri;
@@ -736,14 +782,23 @@ igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
         uint32_t sp = rok ? src_pixel(p, ri, tap_pk) : 0xffffffffu;
         v[i] = (sp != 0xffffffffu) ? ldg128(A + (size_t)sp * p.Csrc + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    uint32_t aoff[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) aoff[i] = mn_chunk_off(warp * 8 + i, lane, 2048u);
+    float4 cur[8], nxt[8];
+    load_a(0, cur);
+    for (int it = 0; it < num_kb; ++it) {
+      const int s = it % nstages;
+      if (it + 1 < num_kb) load_a(it + 1, nxt);
+      if (it >= nstages) mbar_wait(bar_empty + 8 * s, ((it / nstages) - 1) & 1);
       const uint32_t abase = sbase + s * L.stage_bytes;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint32_t off = mn_chunk_off(warp * 8 + i, lane, 2048u);
-        sts_split4(abase + off, abase + TC_A_BYTES + off, v[i]);
-      }
+      for (int i = 0; i < 8; ++i) sts_split4(abase + aoff[i], abase + TC_A_BYTES + aoff[i], cur[i]);
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
     }
   } else if (warp >= 8 && warp < 12) {
     // ===== promotion + epilogue =====
@@ -765,24 +820,38 @@ igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
       }
     });
   } else if (warp < 8) {
-    // ===== B gather: 32 pixel rows x bn_smem columns of G =====
+    // ===== B gather: 32 pixel rows x bn_smem columns of G (bn_smem in {32,64,128}) =====
     const int t = tid - 128;
     const int cpr = bn_smem >> 2;
+    const int jn = t % cpr, rb0 = t / cpr, rstep = 128 / cpr;
+    const int n = n0 + 4 * jn;
+    const bool nok = n < p.Cn && 4 * jn < bn;
+    auto load_b = [&](int it, float4* v) {
+      const int mbase = (kb_beg + it) * TC_BK;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rb0 + i * rstep, m = mbase + r;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < TC_BK && nok && m < p.M) v[i] = ldg128(G + (size_t)m * p.Cn + n);
+      }
+    };
+    uint32_t boff[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) boff[i] = mn_chunk_off(rb0 + i * rstep, jn, sbo_b);
+    float4 cur[8], nxt[8];
+    load_b(0, cur);
     for (int it = 0; it < num_kb; ++it) {
       const int s = it % nstages;
+      if (it + 1 < num_kb) load_b(it + 1, nxt);
       if (it >= nstages) mbar_wait(bar_empty + 8 * s, ((it / nstages) - 1) & 1);
       const uint32_t bbase = sbase + s * L.stage_bytes + L.b_off;
-      const int mbase = (kb_beg + it) * TC_BK;
-      for (int q = t; q < TC_BK * cpr; q += 128) {
-        int r = q / cpr, jn = q - r * cpr;
-        int m = mbase + r, n = n0 + 4 * jn;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < p.M && n < p.Cn && 4 * jn < bn) v = ldg128(G + (size_t)m * p.Cn + n);
-        uint32_t off = mn_chunk_off(r, jn, sbo_b);
-        sts_split4(bbase + off, bbase + L.b_bytes + off, v);
-      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (rb0 + i * rstep < TC_BK) sts_split4(bbase + boff[i], bbase + L.b_bytes + boff[i], cur[i]);
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
     }
   } else {
     const uint32_t idesc = umma_idesc_tf32(bn_smem, 1, 1);
@@ -970,12 +1039,10 @@ static bool tc_pixel_eligible(const GemmPlan& g, bool b_mn) {
 }
 
 static void pick_bn_mn(int cn, int* bn, int* bn_smem) {
-  // MN-major B tiles are built from 32-column swizzle atoms
-  int padded = (cn + 31) / 32 * 32;
-  int best = 32;
-  for (int c = 32; c <= 128; c += 32) if (padded % c == 0) best = c;
-  *bn_smem = best;
-  *bn = best;
+  // MN-major B tiles are built from 32-column swizzle atoms; {32,64,128} keeps the gather index math static
+  int c = cn > 64 ? 128 : (cn > 32 ? 64 : 32);
+  *bn_smem = c;
+  *bn = c;
 }
 static void pick_bn_k(int cn, int* bn, int* bn_smem) {
   int best = 16;
@@ -983,8 +1050,10 @@ static void pick_bn_k(int cn, int* bn, int* bn_smem) {
   *bn = best; *bn_smem = best;
 }
 
+// zero_mode: 0 = this launch covers all of dst and may zero it for a split-K run, 1 = dst was zeroed by the
+// caller (phased dgrad), 2 = no split-K allowed
 static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const float* w, const float* bias,
-                        float* dst, int act, float alpha, int impl, cudaStream_t st) {
+                        float* dst, int act, float alpha, int impl, cudaStream_t st, int zero_mode = 0) {
   if (g.M == 0) return CN_OK;
   bool tc = tc_pixel_eligible(g, b_mn);
   CN_REQUIRE(!(impl == CN_IMPL_TC && !tc), CN_ERR_UNSUPPORTED, "shape not eligible for the tcgen05 kernel");
@@ -997,14 +1066,26 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
     TcSmemLayout L = tc_layout(nstages, bn_smem);
     int smem = L.total + 1024;
     dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.Cn + bn - 1) / bn, 1);
+    const int total_kb = (g.Ktot + TC_BK - 1) / TC_BK;
+    int per = total_kb, split = 1;
+    if (act == CN_ACT_NONE && bias == nullptr && zero_mode != 2 && (int)(grid.x * grid.y) < num_sms() && total_kb >= 32) {
+      split = (2 * num_sms() + grid.x * grid.y - 1) / (grid.x * grid.y);
+      if (split > total_kb / 16) split = total_kb / 16;
+      if (split < 1) split = 1;
+      per = (total_kb + split - 1) / split;
+      split = (total_kb + per - 1) / per;
+      if (split > 1 && zero_mode == 0)
+        CN_CHECK_CUDA(cudaMemsetAsync(dst, 0, (size_t)g.n_img * g.Q[0] * g.Q[1] * g.Q[2] * g.Cn * sizeof(float), st));
+    }
+    grid.z = split;
     int cols = pow2_cols(3 * ((bn_smem + 31) / 32 * 32));
     if (L.total + 1024 > 227 * 1024) { nstages = 2; L = tc_layout(nstages, bn_smem); smem = L.total + 1024; }
     if (b_mn) {
       if (set_smem(igemm_tc_pixel_kernel<1>, smem)) return CN_ERR_CUDA;
-      igemm_tc_pixel_kernel<1><<<grid, TC_THREADS, smem, st>>>(g, src, w, bias, dst, act, alpha, bn, bn_smem, nstages, cols);
+      igemm_tc_pixel_kernel<1><<<grid, TC_THREADS, smem, st>>>(g, src, w, bias, dst, act, alpha, bn, bn_smem, nstages, cols, per, split > 1);
     } else {
       if (set_smem(igemm_tc_pixel_kernel<0>, smem)) return CN_ERR_CUDA;
-      igemm_tc_pixel_kernel<0><<<grid, TC_THREADS, smem, st>>>(g, src, w, bias, dst, act, alpha, bn, bn_smem, nstages, cols);
+      igemm_tc_pixel_kernel<0><<<grid, TC_THREADS, smem, st>>>(g, src, w, bias, dst, act, alpha, bn, bn_smem, nstages, cols, per, split > 1);
     }
     CN_CHECK_LAUNCH();
     return CN_OK;
@@ -1021,14 +1102,14 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
   } else {
     int mt = (g.M + 63) / 64, nt = (g.Cn + 63) / 64;
     int split = 1;
-    if (act == CN_ACT_NONE && mt * nt < num_sms() && g.Ktot >= 2048) {
+    if (act == CN_ACT_NONE && zero_mode != 2 && mt * nt < num_sms() && g.Ktot >= 2048) {
       split = (2 * num_sms() + mt * nt - 1) / (mt * nt);
       int maxsplit = g.Ktot / 256; if (maxsplit < 1) maxsplit = 1;
       if (split > maxsplit) split = maxsplit;
     }
     int kchunk = g.Ktot > 0 ? ((g.Ktot + split - 1) / split + 15) / 16 * 16 : 16;
     split = g.Ktot > 0 ? (g.Ktot + kchunk - 1) / kchunk : 1;
-    if (split > 1) CN_CHECK_CUDA(cudaMemsetAsync(dst, 0, (size_t)g.n_img * g.Q[0] * g.Q[1] * g.Q[2] * g.Cn * sizeof(float), st));
+    if (split > 1 && zero_mode == 0) CN_CHECK_CUDA(cudaMemsetAsync(dst, 0, (size_t)g.n_img * g.Q[0] * g.Q[1] * g.Q[2] * g.Cn * sizeof(float), st));
     dim3 grid(mt, nt, split);
     igemm_ffma_kernel<MODE_PIXEL, 64, 64, 4, 4><<<grid, 256, 0, st>>>(g, src, w, bias, dst, act, alpha, kchunk, split > 1);
   }
@@ -1063,13 +1144,20 @@ extern "C" int cn_conv_dgrad(const cn_conv_desc* d, const float* gy, const float
   CN_REQUIRE(gy && w && gx, CN_ERR_BAD_SHAPE, "null tensor pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int nphase = (d->stride == 2) ? (1 << d->nd) : 1;
+  int zero_mode = 0;
+  if (nphase > 1) {
+    // the phases write disjoint pixels of one tensor: zero it once so that each phase may use split-K
+    size_t n = (size_t)d->batch * d->in_dims[0] * d->in_dims[1] * d->in_dims[2] * d->cin;
+    if (n <= ((size_t)1 << 24)) { CN_CHECK_CUDA(cudaMemsetAsync(gx, 0, n * sizeof(float), st)); zero_mode = 1; }
+    else zero_mode = 2;
+  }
   for (int ph = 0; ph < nphase; ++ph) {
     GemmPlan g;
     rc = get_plan(d, KIND_DGRAD, ph, &g); if (rc) return rc;
     if (g.M == 0) continue;
     int use_impl = impl;
     if (g.ntaps == 0) use_impl = CN_IMPL_FFMA;       // phase without taps: writes zeros
-    rc = launch_pixel(g, false, gy, w, nullptr, gx, CN_ACT_NONE, 0.f, use_impl, st);
+    rc = launch_pixel(g, false, gy, w, nullptr, gx, CN_ACT_NONE, 0.f, use_impl, st, zero_mode);
     if (rc) return rc;
   }
   return CN_OK;
