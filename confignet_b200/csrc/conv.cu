@@ -343,6 +343,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   } while (!done);
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine, async proxy), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -535,12 +543,63 @@ __device__ __forceinline__ void tc_mma_loop(uint32_t tmem_base, uint32_t sbase, 
   }
 }
 
+// Weight pre-pack: writes, for every (n-tile, k-block), the exact shared-memory image of the B stage
+// (big tile then small tile, swizzled) so that the conv kernel fetches a whole B stage with ONE bulk copy
+// issued by one thread.  The split into tf32 big/small parts happens here once per layer call instead of
+// once per M-tile.  grid = (k-blocks, n-tiles), 256 threads.
+template <int B_MN>
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(GemmPlan p, const float* __restrict__ W, float* __restrict__ out, int bn, int bn_smem, int total_kb) {
+  __shared__ int2 s_taps[256];
+  for (int i = threadIdx.x; i < p.ntaps; i += 256) s_taps[i] = p.taps[i];
+  __syncthreads();
+  const int kb = blockIdx.x, nt = blockIdx.y;
+  const uint32_t b_bytes = (uint32_t)bn_smem * TC_BK * 4;
+  uint8_t* tile = reinterpret_cast<uint8_t*>(out) + ((size_t)nt * total_kb + kb) * 2 * b_bytes;
+  const int n0 = nt * bn, k0 = kb * TC_BK;
+  const int nchunks = 8 * bn_smem;
+  const uint32_t sbo = (uint32_t)(bn_smem >> 5) * 512u;
+  for (int q = threadIdx.x; q < nchunks; q += 256) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t off;
+    if (B_MN) {
+      const int cpr = bn_smem >> 2;
+      const int r = q / cpr, jc = q - r * cpr;
+      const int k = k0 + r, n = n0 + 4 * jc;
+      if (k < p.Ktot && n < p.Cn && 4 * jc < bn) {
+        const int kt = k / p.Csrc, c = k - kt * p.Csrc;
+        v = ldg128(W + (size_t)s_taps[kt].y + (size_t)c * p.wsc + n);
+      }
+      off = mn_chunk_off(r, jc, sbo);
+    } else {
+      const int r = q >> 3, j = q & 7;
+      const int k = k0 + 4 * j, n = n0 + r;
+      if (k < p.Ktot && r < bn && n < p.Cn) {
+        const int kt = k / p.Csrc, c = k - kt * p.Csrc;
+        v = ldg128(W + (size_t)s_taps[kt].y + (size_t)n * p.wsn + c);
+      }
+      off = (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
+    }
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    uint4 bg, sm;
+    uint32_t* pb = reinterpret_cast<uint32_t*>(&bg);
+    uint32_t* ps = reinterpret_cast<uint32_t*>(&sm);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pb[i] = __float_as_uint(x[i]) & 0xffffe000u;
+      ps[i] = __float_as_uint(x[i] - __uint_as_float(pb[i])) & 0xffffe000u;
+    }
+    *reinterpret_cast<uint4*>(tile + off) = bg;
+    *reinterpret_cast<uint4*>(tile + b_bytes + off) = sm;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // tcgen05 pixel-mode kernel (forward: B MN-major = Keras kernel as is; dgrad: B K-major)
 // ------------------------------------------------------------------------------------------------
 template <int B_MN>
 __global__ void __launch_bounds__(TC_THREADS)
-igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ W,
+igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ Wp,
                       const float* __restrict__ bias, float* __restrict__ D, int act, float alpha,
                       int bn, int bn_smem, int nstages, int tmem_cols, int kb_per_split, int use_atomic) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -560,7 +619,7 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
 
   for (int i = tid; i < p.ntaps; i += TC_THREADS) s_taps[i] = p.taps[i];
   if (tid == 0) {
-    for (int s = 0; s < nstages; ++s) { mbar_init(bar_full + 8 * s, 256); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < nstages; ++s) { mbar_init(bar_full + 8 * s, 129); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_accfull, 1); mbar_init(bar_accfull + 8, 1);
     mbar_init(bar_accempty, 128); mbar_init(bar_accempty + 8, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -652,63 +711,16 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
       }
     });
   } else if (warp < 8) {
-    // ===== B gather (batched loads + one k-block of register prefetch, like the A gather) =====
-    const int t = tid - 128;
-    // MN-major: 32 k-rows x bn_smem columns, chunk = 4 output channels; bn_smem in {32,64,128} so that every
-    // thread keeps one column chunk jc and walks rows r0, r0+rstep, ...  K-major: bn_smem rows (n) x 32 k.
-    const int cpr = bn_smem >> 2;
-    const int jc = B_MN ? (t % cpr) : (t & 7);
-    const int r0 = B_MN ? (t / cpr) : (t >> 3);
-    const int rstep = B_MN ? (128 / cpr) : 16;
-    const int nrows = B_MN ? TC_BK : bn_smem;
-    const uint32_t sbo = (uint32_t)(bn_smem >> 5) * 512u;
-    uint32_t boff[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = r0 + i * rstep;
-      boff[i] = B_MN ? mn_chunk_off(r, jc, sbo) : (uint32_t)(r * 128 + ((jc ^ (r & 7)) << 4));
-    }
-    auto load_b = [&](int it, float4* v) {
-      const int k0 = (kb_beg + it) * TC_BK;
-      if (B_MN) {
-        const int n = n0 + 4 * jc;
-        const bool nok = n < p.Cn && 4 * jc < bn;
-        int kt = k0 / p.Csrc, c = k0 - kt * p.Csrc + r0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + i * rstep;
-          while (c >= p.Csrc) { c -= p.Csrc; ++kt; }
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < nrows && nok && k0 + r < p.Ktot) v[i] = ldg128(W + (size_t)s_taps[kt].y + (size_t)c * p.wsc + n);
-          c += rstep;
-        }
-      } else {
-        const int k = k0 + 4 * jc;
-        int c = 0, wb = 0; const bool kok = k < p.Ktot;
-        if (kok) { int kt = k / p.Csrc; c = k - kt * p.Csrc; wb = s_taps[kt].y; }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + i * rstep, n = n0 + r;
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < nrows && kok && r < bn && n < p.Cn) v[i] = ldg128(W + (size_t)wb + (size_t)n * p.wsn + c);
-        }
+    // ===== B stage fetch: the pre-packed smem image of (n-tile, k-block) arrives with one bulk copy =====
+    if (warp == 4 && lane == 0) {
+      const uint32_t bytes = 2 * L.b_bytes;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(Wp) + ((size_t)blockIdx.y * total_kb + kb_beg) * bytes;
+      for (int it = 0; it < num_kb; ++it) {
+        const int s = it % nstages;
+        if (it >= nstages) mbar_wait(bar_empty + 8 * s, ((it / nstages) - 1) & 1);
+        mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
+        bulk_g2s(sbase + s * L.stage_bytes + L.b_off, src + (size_t)it * bytes, bytes, bar_full + 8 * s);
       }
-    };
-    float4 cur[8], nxt[8];
-    load_b(0, cur);
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % nstages;
-      if (kb + 1 < num_kb) load_b(kb + 1, nxt);
-      if (kb >= nstages) mbar_wait(bar_empty + 8 * s, ((kb / nstages) - 1) & 1);
-      const uint32_t bbase = sbase + s * L.stage_bytes + L.b_off;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (r0 + i * rstep < nrows) sts_split4(bbase + boff[i], bbase + L.b_bytes + boff[i], cur[i]);
-      }
-      fence_proxy_async();
-      mbar_arrive(bar_full + 8 * s);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
     }
   } else {
     // ===== MMA issue (one lane) =====
@@ -1050,6 +1062,8 @@ static void pick_bn_k(int cn, int* bn, int* bn_smem) {
   *bn = best; *bn_smem = best;
 }
 
+static std::map<const void*, std::pair<float*, size_t>> g_wpack;    // per plan (keyed by its tap table): packed-weight buffer
+
 // zero_mode: 0 = this launch covers all of dst and may zero it for a split-K run, 1 = dst was zeroed by the
 // caller (phased dgrad), 2 = no split-K allowed
 static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const float* w, const float* bias,
@@ -1078,14 +1092,34 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
         CN_CHECK_CUDA(cudaMemsetAsync(dst, 0, (size_t)g.n_img * g.Q[0] * g.Q[1] * g.Q[2] * g.Cn * sizeof(float), st));
     }
     grid.z = split;
+    // pre-pack the weights into per-(n-tile, k-block) stage images (buffer cached per plan)
+    const size_t pack_bytes = (size_t)grid.y * total_kb * 2 * bn_smem * TC_BK * 4;
+    float* wp = nullptr;
+    {
+      std::lock_guard<std::mutex> lock(g_plan_mutex);
+      auto it = g_wpack.find((const void*)g.taps);
+      if (it == g_wpack.end() || it->second.second < pack_bytes) {
+        if (it != g_wpack.end()) cudaFree(it->second.first);
+        CN_CHECK_CUDA(cudaMalloc(&wp, pack_bytes));
+        g_wpack[(const void*)g.taps] = std::make_pair(wp, pack_bytes);
+      } else {
+        wp = it->second.first;
+      }
+    }
+    {
+      dim3 pgrid(total_kb, grid.y);
+      if (b_mn) pack_weights_kernel<1><<<pgrid, 256, 0, st>>>(g, w, wp, bn, bn_smem, total_kb);
+      else pack_weights_kernel<0><<<pgrid, 256, 0, st>>>(g, w, wp, bn, bn_smem, total_kb);
+      CN_CHECK_LAUNCH();
+    }
     int cols = pow2_cols(3 * ((bn_smem + 31) / 32 * 32));
     if (L.total + 1024 > 227 * 1024) { nstages = 2; L = tc_layout(nstages, bn_smem); smem = L.total + 1024; }
     if (b_mn) {
       if (set_smem(igemm_tc_pixel_kernel<1>, smem)) return CN_ERR_CUDA;
-      igemm_tc_pixel_kernel<1><<<grid, TC_THREADS, smem, st>>>(g, src, w, bias, dst, act, alpha, bn, bn_smem, nstages, cols, per, split > 1);
+      igemm_tc_pixel_kernel<1><<<grid, TC_THREADS, smem, st>>>(g, src, wp, bias, dst, act, alpha, bn, bn_smem, nstages, cols, per, split > 1);
     } else {
       if (set_smem(igemm_tc_pixel_kernel<0>, smem)) return CN_ERR_CUDA;
-      igemm_tc_pixel_kernel<0><<<grid, TC_THREADS, smem, st>>>(g, src, w, bias, dst, act, alpha, bn, bn_smem, nstages, cols, per, split > 1);
+      igemm_tc_pixel_kernel<0><<<grid, TC_THREADS, smem, st>>>(g, src, wp, bias, dst, act, alpha, bn, bn_smem, nstages, cols, per, split > 1);
     }
     CN_CHECK_LAUNCH();
     return CN_OK;
