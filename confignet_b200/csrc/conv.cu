@@ -465,7 +465,7 @@ __host__ __device__ inline TcSmemLayout tc_layout(int nstages, int bn_smem) {
   l.b_bytes = bn_smem * TC_BK * 4;
   l.stage_bytes = l.b_off + 2 * l.b_bytes;
   l.bar_off = nstages * l.stage_bytes;
-  l.tmem_off = l.bar_off + (2 * nstages + 4) * 8;      // full[], empty[], acc_full[2], acc_empty[2]
+  l.tmem_off = l.bar_off + (3 * nstages + 4) * 8;      // full[], empty[], acc_full[2], acc_empty[2], empty_b[]
   l.taps_off = (l.tmem_off + 4 + 7) & ~7u;
   l.total = l.taps_off + 256 * 8;
   return l;
@@ -515,7 +515,37 @@ __device__ __forceinline__ void tc_promote_and_store(uint32_t tmem_base, int pw,
       if (!last) tc_st32(tmem_base + lanebits + 2 * bn_r + cb, v);
       else store(cb, v);
     }
-    if (!last) { tc_fence_before(); mbar_arrive(bar_accempty + 8 * b); }
+    if (!last) { tc_fence_before(); __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(bar_accempty + 8 * b); }
+  }
+}
+
+// Same promotion with the running total in shared memory ([column][128 rows] fp32: lane = row, so the accesses
+// are conflict-free), which leaves the tensor memory to the ping-pong accumulators and the A stages.
+template <class StoreFn>
+__device__ __forceinline__ void tc_promote_smem_and_store(uint32_t tmem_base, float* tot, int pw, int bn, int bn_r, int nchunks,
+                                                          uint32_t bar_accfull, uint32_t bar_accempty, StoreFn store) {
+  const uint32_t lanebits = (uint32_t)(pw * 32) << 16;
+  float* mine = tot + pw * 32 + (threadIdx.x & 31);
+  for (int c = 0; c < nchunks; ++c) {
+    const int b = c & 1;
+    mbar_wait(bar_accfull + 8 * b, (c >> 1) & 1);
+    tc_fence_after();
+    const bool last = c == nchunks - 1;
+    for (int cb = 0; cb < bn; cb += 32) {
+      uint32_t v[32];
+      tc_ld32(tmem_base + lanebits + b * bn_r + cb, v);
+      if (c > 0) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + mine[(cb + q) * 128]);
+      }
+      if (!last) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) mine[(cb + q) * 128] = __uint_as_float(v[q]);
+      } else {
+        store(cb, v);
+      }
+    }
+    if (!last) { tc_fence_before(); __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(bar_accempty + 8 * b); }
   }
 }
 
@@ -524,7 +554,7 @@ template <int A_MN, int B_MN>
 __device__ __forceinline__ void tc_mma_loop(uint32_t tmem_base, uint32_t sbase, const TcSmemLayout& L, int nstages,
                                             int num_kb, int bn_r, uint32_t bar_full, uint32_t bar_empty,
                                             uint32_t bar_accfull, uint32_t bar_accempty, uint32_t sbo_a,
-                                            uint32_t sbo_b, uint32_t idesc, int lane) {
+                                            uint32_t sbo_b, uint32_t idesc, int lane, int dbg = 0) {
   for (int kb = 0; kb < num_kb; ++kb) {
     const int s = kb % nstages;
     const int c = kb / TC_CHUNK_KB, b = c & 1;
@@ -535,7 +565,7 @@ __device__ __forceinline__ void tc_mma_loop(uint32_t tmem_base, uint32_t sbase, 
     tc_fence_after();
     if (lane == 0) {
       const uint32_t abase = sbase + s * L.stage_bytes;
-      tc_issue_stage<A_MN, B_MN>(tmem_base + b * bn_r, abase, abase + L.b_off, L.b_bytes, sbo_a, sbo_b, idesc, chunk_first);
+      if (!(dbg & 4)) tc_issue_stage<A_MN, B_MN>(tmem_base + b * bn_r, abase, abase + L.b_off, L.b_bytes, sbo_a, sbo_b, idesc, chunk_first);
       tc_commit(bar_empty + 8 * s);
       if (chunk_last) tc_commit(bar_accfull + 8 * b);
     }
@@ -596,19 +626,97 @@ pack_weights_kernel(GemmPlan p, const float* __restrict__ W, float* __restrict__
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 pixel-mode kernel (forward: B MN-major = Keras kernel as is; dgrad: B K-major)
+//
+// Measured on B200 (profiles/r01_layer_time_dbg.txt): with one CTA per SM every k-block pulls 16 KB of
+// activations and 32 KB of pre-split weights through L2, and at ~6.4 TB/s of L2->SM bandwidth that, not the
+// tensor pipe, bounds the kernel.  So the CTAs of a thread-block cluster (consecutive M tiles of the same
+// N tile) share the weight stream: each CTA fetches 1/C of every B stage and multicasts it to all C CTAs.
+// Warp roles (448 threads): 0-7 gather A, 8-11 promote + epilogue, 12 MMA issue, 13 B producer.
 // ------------------------------------------------------------------------------------------------
+// true in exactly one (converged) lane of the warp; ptxas recognises the pattern and issues the guarded
+// tcgen05 instructions without a per-operand uniformity loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+
+constexpr int TCP_THREADS = 448;
+constexpr int TCP_MMA_WARP = 12;
+constexpr int TCP_B_WARP = 13;
+constexpr int TCP_A_COLS = 64;       // TMEM columns of one A stage: 32 big + 32 small
+
+// D[tmem] (+)= A[tmem] * B[smem]: A is the 128 x 8 tf32 block at TMEM address `tmem_a` (lane = GEMM row,
+// column = k), K-major by construction
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st16_nowait(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
+constexpr int TCP_MAX_A = 6;         // A stages in tensor memory (as many as fit beside the two accumulators)
+struct TcpLayout {
+  // dynamic smem, 1024-byte aligned: nb B stages [B big][B small]; running total [bn_r][128] fp32; barriers, tmem ptr, taps
+  uint32_t stage_bytes, b_bytes, tot_off, bar_off, tmem_off, taps_off, total;
+};
+__host__ __device__ inline TcpLayout tcp_layout(int nb, int bn_smem) {
+  TcpLayout l;
+  l.b_bytes = bn_smem * TC_BK * 4;
+  l.stage_bytes = 2 * l.b_bytes;
+  l.tot_off = nb * l.stage_bytes;
+  l.bar_off = l.tot_off + ((bn_smem + 31) / 32 * 32) * 128 * 4;
+  l.tmem_off = l.bar_off + (2 * nb + 2 * TCP_MAX_A + 4) * 8;      // full_b[], empty_b[], full_a[], empty_a[], acc_full[2], acc_empty[2]
+  l.taps_off = (l.tmem_off + 4 + 7) & ~7u;
+  l.total = l.taps_off + 256 * 8;
+  return l;
+}
+
 template <int B_MN>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TCP_THREADS)
 igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ Wp,
                       const float* __restrict__ bias, float* __restrict__ D, int act, float alpha,
-                      int bn, int bn_smem, int nstages, int tmem_cols, int kb_per_split, int use_atomic) {
+                      int bn, int bn_smem, int nb, int tmem_cols, int kb_per_split, int use_atomic,
+                      int csize, int dbg, long long* prof) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const TcSmemLayout L = tc_layout(nstages, bn_smem);
+  const bool do_prof = prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  long long pt[6] = {0, 0, 0, 0, 0, 0};
+  const long long t_begin = clock64();
+  const TcpLayout L = tcp_layout(nb, bn_smem);
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_full = sbase + L.bar_off, bar_empty = bar_full + 8 * nstages;
-  const uint32_t bar_accfull = bar_empty + 8 * nstages, bar_accempty = bar_accfull + 16;
+  const uint32_t bar_fullb = sbase + L.bar_off, bar_emptyb = bar_fullb + 8 * nb;   // empty_b: free in EVERY CTA of the cluster
+  const uint32_t bar_fulla = bar_emptyb + 8 * nb, bar_emptya = bar_fulla + 8 * TCP_MAX_A;
+  const uint32_t bar_accfull = bar_emptya + 8 * TCP_MAX_A, bar_accempty = bar_accfull + 16;
   const int bn_r = (bn_smem + 31) / 32 * 32;
+  const uint32_t a_col0 = 2 * bn_r;       // TMEM: [acc ping][acc pong][A stage 0] .. [A stage na-1]
+  const int na = min(TCP_MAX_A, (512 - 2 * bn_r) / TCP_A_COLS) & ~1;   // even: a stage keeps the parity of its k-blocks
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_off);
   int2* s_taps = reinterpret_cast<int2*>(smem + L.taps_off);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -616,80 +724,129 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
   const int total_kb = (p.Ktot + TC_BK - 1) / TC_BK;
   const int kb_beg = blockIdx.z * kb_per_split;             // split-K over gridDim.z (atomic epilogue)
   const int num_kb = min(total_kb, kb_beg + kb_per_split) - kb_beg;   // host guarantees >= 1
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
-  for (int i = tid; i < p.ntaps; i += TC_THREADS) s_taps[i] = p.taps[i];
+  for (int i = tid; i < p.ntaps; i += TCP_THREADS) s_taps[i] = p.taps[i];
   if (tid == 0) {
-    for (int s = 0; s < nstages; ++s) { mbar_init(bar_full + 8 * s, 129); mbar_init(bar_empty + 8 * s, 1); }
-    mbar_init(bar_accfull, 1); mbar_init(bar_accfull + 8, 1);
-    mbar_init(bar_accempty, 128); mbar_init(bar_accempty + 8, 128);
+    for (int s = 0; s < nb; ++s) { mbar_init(bar_fullb + 8 * s, 1); mbar_init(bar_emptyb + 8 * s, csize); }
+    for (int s = 0; s < TCP_MAX_A; ++s) { mbar_init(bar_fulla + 8 * s, 4); mbar_init(bar_emptya + 8 * s, 1); }   // one arrival per gather warp
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accempty + 8 * s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == TC_MMA_WARP) {
+  if (warp == TCP_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + L.tmem_off), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();      // every CTA's barriers are initialised before a peer multicasts into them
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  // The kernel allocates all 512 columns, so the allocation starts at column 0 / lane 0.  Using the constant
+  // keeps every TMEM address in uniform registers (a base read back from shared memory costs an
+  // ELECT + R2UR round trip per tcgen05.mma: ~60 clk each, measured).
+  if (*tmem_ptr != 0u) { asm volatile("trap;"); }
+  constexpr uint32_t tmem_base = 0u;
 
-  if (warp < 4) {
-    // ===== A gather: 8 threads per 128-byte row (one 16-byte chunk each), 8 rows per thread.
-    //       The loads of k-block kb+1 are issued before k-block kb is converted and stored, so one
-    //       memory latency is always overlapped with the split/STS work and the barrier wait. =====
-    const int j = tid & 7;
-    RowInfo rows[8];
-    uint32_t soff[8], spoff[8];          // smem offsets of this thread's 8 chunks; source element offsets
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = (tid >> 3) + 16 * i;
-      rows[i] = decode_row(p, m0 + r);
-      soff[i] = r * 128 + ((j ^ (r & 7)) << 4);
-      spoff[i] = 0xffffffffu;
-    }
-    // (tap, channel) of this thread's chunk advance by 32 channels per k-block; the 8 source pixels are
-    // recomputed only when the tap changes (every Csrc/32 k-blocks)
-    int kt_cur = (kb_beg * TC_BK + 4 * j) / p.Csrc, c_cur = kb_beg * TC_BK + 4 * j - kt_cur * p.Csrc, kt_have = -1;
-    auto load_a = [&](int it, float4* v) {
-      const bool kok = (kb_beg + it) * TC_BK + 4 * j < p.Ktot;
-      if (kok && kt_cur != kt_have) {
-        const int tap_pk = s_taps[kt_cur].x;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint32_t sp = src_pixel(p, rows[i], tap_pk);
-          spoff[i] = (sp != 0xffffffffu) ? sp * (uint32_t)p.Csrc : 0xffffffffu;
-        }
-        kt_have = kt_cur;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        v[i] = (kok && spoff[i] != 0xffffffffu) ? ldg128(A + (size_t)spoff[i] + c_cur) : make_float4(0.f, 0.f, 0.f, 0.f);
-      c_cur += TC_BK;
-      while (c_cur >= p.Csrc) { c_cur -= p.Csrc; ++kt_cur; }
+  if (warp < 8) {
+    // ===== A gather straight into tensor memory: thread = GEMM row (TMEM lane), one k-block = the 128
+    //       contiguous bytes (32 channels) of that row's source pixel.  Warps w and w+4 share a lane quarter
+    //       and alternate k-blocks (A stage = k-block parity); the loads of a thread's next k-block are in
+    //       flight while the current one is split into its tf32 big/small parts and written with tcgen05.st. =====
+    const int q4 = warp & 3, par = warp >> 2;
+    const RowInfo row = decode_row(p, m0 + q4 * 32 + lane);
+    const uint32_t a_t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + a_col0;
+    auto src_off = [&](int kt) -> uint32_t {
+      if (kt >= p.ntaps) return 0xffffffffu;
+      const uint32_t sp = src_pixel(p, row, s_taps[kt].x);
+      return sp != 0xffffffffu ? sp * (uint32_t)p.Csrc : 0xffffffffu;
     };
-    float4 cur[8], nxt[8];
-    load_a(0, cur);
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % nstages;
-      if (kb + 1 < num_kb) load_a(kb + 1, nxt);
-      if (kb >= nstages) mbar_wait(bar_empty + 8 * s, ((kb / nstages) - 1) & 1);
-      const uint32_t abase = sbase + s * L.stage_bytes;
+    // position of this warp's next k-block to load: (tap, channel) and whether k is still inside Ktot;
+    // advanced by two k-blocks per load without divisions
+    int l_kt, l_c;
+    { const int k = (kb_beg + par) * TC_BK; l_kt = k / p.Csrc; l_c = k - l_kt * p.Csrc; }
+    uint32_t l_so = 0xffffffffu;
+    int l_so_kt = -1;
+    auto load_a = [&](float4* v) {
+      const long long t0 = clock64();
+      if (l_kt != l_so_kt) { l_so = src_off(l_kt); l_so_kt = l_kt; }
+      if (l_c + TC_BK <= p.Csrc) {
+        // common case: the 32 channels of this k-block lie inside one tap -> 8 loads off one base pointer
+        const float* src = A + (size_t)l_so + l_c;
+        const bool ok = l_so != 0xffffffffu && !(dbg & 1);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sts_split4(abase + soff[i], abase + TC_A_BYTES + soff[i], cur[i]);
-      fence_proxy_async();
-      mbar_arrive(bar_full + 8 * s);
+        for (int q = 0; q < 8; ++q) v[q] = ok ? ldg128(src + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        // the k-block straddles a tap boundary (Csrc not a multiple of 32) or the end of K
+        int kt = l_kt, c = l_c;
+        uint32_t so = l_so;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+        for (int q = 0; q < 8; ++q) {
+          v[q] = (so != 0xffffffffu && !(dbg & 1)) ? ldg128(A + (size_t)so + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          c += 4;
+          if (c >= p.Csrc) { c = 0; ++kt; so = src_off(kt); }
+        }
+      }
+      l_c += 2 * TC_BK;
+      while (l_c >= p.Csrc) { l_c -= p.Csrc; ++l_kt; }
+      pt[2] += clock64() - t0;
+    };
+    int s_sa = par, s_u = 0;                 // A stage and use count of this warp's next k-block to store
+    auto store_a = [&]() -> uint32_t {
+      const int sa = s_sa;
+      { const long long t0 = clock64(); if (s_u >= 1) mbar_wait(bar_emptya + 8 * sa, (s_u - 1) & 1); pt[0] += clock64() - t0; }
+      tc_fence_after();
+      s_sa += 2;
+      if (s_sa >= na) { s_sa -= na; ++s_u; }
+      return (uint32_t)sa;
+    };
+    auto put_a = [&](uint32_t sa, const float4* v) {
+      const long long t0 = clock64();
+      const uint32_t a_t = a_t0 + sa * TCP_A_COLS;
+      if (!(dbg & 8)) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t bg[16], sm[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float x[4] = {v[4 * h + q].x, v[4 * h + q].y, v[4 * h + q].z, v[4 * h + q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              bg[4 * q + e] = __float_as_uint(x[e]) & 0xffffe000u;
+              sm[4 * q + e] = __float_as_uint(x[e] - __uint_as_float(bg[4 * q + e])) & 0xffffe000u;
+            }
+          }
+          tc_st16_nowait(a_t + 16 * h, bg);
+          tc_st16_nowait(a_t + 32 + 16 * h, sm);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      tc_fence_before();
+      __syncwarp();                      // one arrival per warp: 128 per-thread arrivals on one barrier serialise
+      if (lane == 0) mbar_arrive(bar_fulla + 8 * sa);
+      pt[1] += clock64() - t0;
+    };
+    float4 va[8], vb[8];
+    int kb = par;
+    if (kb < num_kb) load_a(va);
+    for (; kb < num_kb; kb += 4) {
+      if (kb + 2 < num_kb) load_a(vb);
+      put_a(store_a(), va);
+      if (kb + 2 < num_kb) {
+        if (kb + 4 < num_kb) load_a(va);
+        put_a(store_a(), vb);
+      }
     }
-  } else if (warp >= 8 && warp < 12) {
+    if (do_prof && warp == 0 && lane == 0) { prof[0] = pt[0]; prof[1] = pt[1]; prof[2] = pt[2]; prof[3] = clock64() - t_begin; }
+  } else if (warp < 12) {
     // ===== promotion + epilogue: TMEM -> registers -> global (warp pw owns TMEM lanes 32pw..32pw+31) =====
     const int pw = warp - 8;
     const int m = m0 + pw * 32 + lane;
     const bool mok = m < p.M;
     const size_t rowoff = mok ? (size_t)dest_pixel(p, m) * p.Cn : 0;
     const int nchunks = (num_kb + TC_CHUNK_KB - 1) / TC_CHUNK_KB;
-    tc_promote_and_store(tmem_base, pw, bn, bn_r, nchunks, bar_accfull, bar_accempty, [&](int cb, const uint32_t* v) {
-      if (mok) {
+    tc_promote_smem_and_store(tmem_base, reinterpret_cast<float*>(smem + L.tot_off), pw, bn, bn_r, nchunks, bar_accfull, bar_accempty,
+                              [&](int cb, const uint32_t* v) {
+      if (mok && !(dbg & 16)) {
 #pragma unroll
         for (int q = 0; q < 32; q += 4) {
           int n = n0 + cb + q;
@@ -710,28 +867,79 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
         }
       }
     });
-  } else if (warp < 8) {
-    // ===== B stage fetch: the pre-packed smem image of (n-tile, k-block) arrives with one bulk copy =====
-    if (warp == 4 && lane == 0) {
-      const uint32_t bytes = 2 * L.b_bytes;
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(Wp) + ((size_t)blockIdx.y * total_kb + kb_beg) * bytes;
+  } else if (warp == TCP_B_WARP) {
+    // ===== B stage fetch: the pre-packed smem image of (n-tile, k-block) is one contiguous block; this CTA
+    //       fetches slice `rank` of it and multicasts it to the same offset in all CTAs of the cluster =====
+    if (lane == 0) {
+      const uint32_t bytes = L.stage_bytes;
+      const uint32_t slice = bytes / (uint32_t)csize;
+      const uint32_t rank = csize > 1 ? cluster_ctarank() : 0u;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(Wp) + ((size_t)blockIdx.y * total_kb + kb_beg) * bytes + rank * slice;
+      int s = 0, ph = 1;
       for (int it = 0; it < num_kb; ++it) {
-        const int s = it % nstages;
-        if (it >= nstages) mbar_wait(bar_empty + 8 * s, ((it / nstages) - 1) & 1);
-        mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
-        bulk_g2s(sbase + s * L.stage_bytes + L.b_off, src + (size_t)it * bytes, bytes, bar_full + 8 * s);
+        { const long long t0 = clock64(); if (it >= nb) mbar_wait(bar_emptyb + 8 * s, ph); pt[0] += clock64() - t0; }
+        mbar_arrive_expect_tx(bar_fullb + 8 * s, bytes);
+        const uint32_t dst = sbase + s * L.stage_bytes + rank * slice;
+        if (csize > 1) bulk_g2s_mc(dst, src + (size_t)it * bytes, slice, bar_fullb + 8 * s, cmask);
+        else bulk_g2s(dst, src + (size_t)it * bytes, bytes, bar_fullb + 8 * s);
+        if (++s == nb) { s = 0; ph ^= 1; }
       }
+      if (do_prof) { prof[10] = pt[0]; prof[11] = clock64() - t_begin; }
     }
   } else {
-    // ===== MMA issue (one lane) =====
+    // ===== MMA issue (one lane): per k-block 4 k-steps x 3 split products, A from TMEM, B from smem.
+    //       Stage indices / phases advance incrementally and the smem descriptors are a constant plus an
+    //       address field: the single issuing thread must stay far below one k-block of MMA time. =====
     const uint32_t idesc = umma_idesc_tf32(bn_smem, 0, B_MN);
     const uint32_t sbo_b = B_MN ? (uint32_t)(bn_smem >> 5) * 512u : 1024u;
-    tc_mma_loop<0, B_MN>(tmem_base, sbase, L, nstages, num_kb, bn_r, bar_full, bar_empty, bar_accfull, bar_accempty,
-                         1024u, sbo_b, idesc, lane);
+    const uint32_t lbo_b = B_MN ? 512u : 16u, lb = B_MN ? 1u : 2u;
+    const uint32_t desc_hi = ((sbo_b >> 4) & 0x3fffu) | (1u << 14) | (lb << 29);
+    const uint32_t desc_lo0 = ((lbo_b >> 4) & 0x3fffu) << 16;
+    const uint32_t stage16 = L.stage_bytes >> 4, plane16 = L.b_bytes >> 4, kk16 = (B_MN ? 2 * sbo_b : 32u) >> 4;
+    int sa = 0, pa = 0, sb = 0, pb = 0, b = 0, inchunk = 0, c = 0;
+    uint32_t b16 = sbase >> 4;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const bool chunk_first = inchunk == 0;
+      const bool chunk_last = inchunk == TC_CHUNK_KB - 1 || kb == num_kb - 1;
+      long long t0 = clock64();
+      if (chunk_first && c >= 2) { mbar_wait(bar_accempty + 8 * b, ((c >> 1) - 1) & 1); }
+      long long t1 = clock64(); pt[0] += t1 - t0;
+      mbar_wait(bar_fulla + 8 * sa, pa);
+      t0 = clock64(); pt[1] += t0 - t1;
+      mbar_wait(bar_fullb + 8 * sb, pb);
+      t1 = clock64(); pt[2] += t1 - t0;
+      tc_fence_after();
+      if (elect_one()) {
+        if (!(dbg & 4)) {
+          const uint32_t d_t = tmem_base + b * bn_r;
+          const uint32_t a_big = tmem_base + a_col0 + sa * TCP_A_COLS, a_small = a_big + 32;
+#pragma unroll
+          for (int kk = 0; kk < TC_BK / 8; ++kk) {
+            const uint32_t lo_big = desc_lo0 | ((b16 + kk * kk16) & 0x3fffu), lo_small = desc_lo0 | ((b16 + plane16 + kk * kk16) & 0x3fffu);
+            const uint64_t bb = ((uint64_t)desc_hi << 32) | lo_big, bs = ((uint64_t)desc_hi << 32) | lo_small;
+            tc_mma_tf32_ts(d_t, a_small + kk * 8, bb, idesc, !(chunk_first && kk == 0));
+            tc_mma_tf32_ts(d_t, a_big + kk * 8, bs, idesc, 1);
+            tc_mma_tf32_ts(d_t, a_big + kk * 8, bb, idesc, 1);
+          }
+        }
+        tc_commit(bar_emptya + 8 * sa);
+        if (csize > 1) tc_commit_mc(bar_emptyb + 8 * sb, cmask); else tc_commit(bar_emptyb + 8 * sb);
+        if (chunk_last) tc_commit(bar_accfull + 8 * b);
+      }
+      __syncwarp();
+      if (++sa == na) { sa = 0; pa ^= 1; }
+      b16 += stage16;
+      if (++sb == nb) { sb = 0; pb ^= 1; b16 = sbase >> 4; }
+      if (++inchunk == TC_CHUNK_KB) { inchunk = 0; ++c; b ^= 1; }
+      pt[3] += clock64() - t1;
+    }
+    if (do_prof && lane == 0) { prof[4] = pt[0]; prof[5] = pt[1]; prof[6] = pt[2]; prof[7] = pt[3]; prof[8] = clock64() - t_begin; prof[9] = num_kb; }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_MMA_WARP) {
+  if (csize > 1) cluster_sync_all();      // no CTA leaves while a peer may still signal its barriers
+  if (do_prof && tid == 0) prof[12] = clock64() - t_begin;
+  if (warp == TCP_MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
@@ -742,7 +950,7 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
 __global__ void __launch_bounds__(TC_THREADS)
 igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ G,
                       float* __restrict__ D, int bn, int bn_smem, int nstages, int tmem_cols,
-                      int kb_per_split, int use_atomic) {
+                      int kb_per_split, int use_atomic, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const TcSmemLayout L = tc_layout(nstages, bn_smem);
@@ -762,9 +970,9 @@ igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
 
   for (int i = tid; i < p.ntaps; i += TC_THREADS) s_taps[i] = p.taps[i];
   if (tid == 0) {
-    for (int s = 0; s < nstages; ++s) { mbar_init(bar_full + 8 * s, 256); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < nstages; ++s) { mbar_init(bar_full + 8 * s, 8); mbar_init(bar_empty + 8 * s, 1); }   // one arrival per gather warp
     mbar_init(bar_accfull, 1); mbar_init(bar_accfull + 8, 1);
-    mbar_init(bar_accempty, 128); mbar_init(bar_accempty + 8, 128);
+    mbar_init(bar_accempty, 4); mbar_init(bar_accempty + 8, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_MMA_WARP) {
@@ -792,7 +1000,7 @@ igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
         ri.base = __shfl_sync(0xffffffffu, mine.base, i);
         ri.pk = __shfl_sync(0xffffffffu, mine.pk, i);
         uint32_t sp = rok ? src_pixel(p, ri, tap_pk) : 0xffffffffu;
-        v[i] = (sp != 0xffffffffu) ? ldg128(A + (size_t)sp * p.Csrc + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = (sp != 0xffffffffu && !(dbg & 1)) ? ldg128(A + (size_t)sp * p.Csrc + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     uint32_t aoff[8];
@@ -806,9 +1014,10 @@ igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
       if (it >= nstages) mbar_wait(bar_empty + 8 * s, ((it / nstages) - 1) & 1);
       const uint32_t abase = sbase + s * L.stage_bytes;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sts_split4(abase + aoff[i], abase + TC_A_BYTES + aoff[i], cur[i]);
+      for (int i = 0; i < 8; ++i) if (!(dbg & 8)) sts_split4(abase + aoff[i], abase + TC_A_BYTES + aoff[i], cur[i]);
       fence_proxy_async();
-      mbar_arrive(bar_full + 8 * s);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
 #pragma unroll
       for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
     }
@@ -844,7 +1053,7 @@ igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
       for (int i = 0; i < 8; ++i) {
         const int r = rb0 + i * rstep, m = mbase + r;
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < TC_BK && nok && m < p.M) v[i] = ldg128(G + (size_t)m * p.Cn + n);
+        if (r < TC_BK && nok && m < p.M && !(dbg & 2)) v[i] = ldg128(G + (size_t)m * p.Cn + n);
       }
     };
     uint32_t boff[8];
@@ -859,16 +1068,17 @@ igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
       const uint32_t bbase = sbase + s * L.stage_bytes + L.b_off;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (rb0 + i * rstep < TC_BK) sts_split4(bbase + boff[i], bbase + L.b_bytes + boff[i], cur[i]);
+        if (rb0 + i * rstep < TC_BK && !(dbg & 8)) sts_split4(bbase + boff[i], bbase + L.b_bytes + boff[i], cur[i]);
       fence_proxy_async();
-      mbar_arrive(bar_full + 8 * s);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
 #pragma unroll
       for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
     }
   } else {
     const uint32_t idesc = umma_idesc_tf32(bn_smem, 1, 1);
     tc_mma_loop<1, 1>(tmem_base, sbase, L, nstages, num_kb, bn_r, bar_full, bar_empty, bar_accfull, bar_accempty,
-                      2048u, sbo_b, idesc, lane);
+                      2048u, sbo_b, idesc, lane, dbg);
   }
   tc_fence_before();
   __syncthreads();
@@ -1023,6 +1233,12 @@ __global__ void colsum_kernel(const float* __restrict__ g, int rows, int n, floa
 // ------------------------------------------------------------------------------------------------
 // Host dispatch
 // ------------------------------------------------------------------------------------------------
+static int g_cluster = 2;   // CTAs per cluster in the tcgen05 pixel kernel (cn_debug_set_cluster: 1, 2 or 4)
+extern "C" int cn_debug_set_cluster(int v) { g_cluster = (v == 4 || v == 2) ? v : 1; return CN_OK; }
+static long long* g_prof = nullptr;   // TEST HOOK: device buffer (16 x int64) receiving CTA 0's role timings
+extern "C" int cn_debug_set_prof(void* p) { g_prof = (long long*)p; return CN_OK; }
+static int g_dbg = 0;   // TEST HOOK (cn_debug_set): bit 0/1 skip A/B global loads, bit 2 skip MMA issue, bit 3 skip STS
+extern "C" int cn_debug_set(int v) { g_dbg = v; return CN_OK; }
 static thread_local int g_last_impl = 0;     // 1 = CUDA-core, 2 = tcgen05: what the last conv call on this thread ran
 extern "C" int cn_last_conv_impl(void) { return g_last_impl; }
 static int g_num_sms = 0;
@@ -1076,9 +1292,13 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
   if (tc) {
     int bn, bn_smem;
     if (b_mn) pick_bn_mn(g.Cn, &bn, &bn_smem); else pick_bn_k(g.Cn, &bn, &bn_smem);
-    int nstages = 3;
-    TcSmemLayout L = tc_layout(nstages, bn_smem);
+    // B stages fill the shared memory (A lives in tensor memory); >113 KB also keeps it at one CTA per SM,
+    // which the 512-column TMEM allocation needs
+    int nb = 6;
+    TcpLayout L = tcp_layout(nb, bn_smem);
+    while (nb > 2 && L.total + 1024 > 200 * 1024) { --nb; L = tcp_layout(nb, bn_smem); }
     int smem = L.total + 1024;
+    if (smem < 120 * 1024) smem = 120 * 1024;
     dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.Cn + bn - 1) / bn, 1);
     const int total_kb = (g.Ktot + TC_BK - 1) / TC_BK;
     int per = total_kb, split = 1;
@@ -1112,14 +1332,27 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
       else pack_weights_kernel<0><<<pgrid, 256, 0, st>>>(g, w, wp, bn, bn_smem, total_kb);
       CN_CHECK_LAUNCH();
     }
-    int cols = pow2_cols(3 * ((bn_smem + 31) / 32 * 32));
-    if (L.total + 1024 > 227 * 1024) { nstages = 2; L = tc_layout(nstages, bn_smem); smem = L.total + 1024; }
+    int cols = 512;
+    // thread-block cluster along M: the CTAs of a cluster share the B (weight) stream by multicast
+    int csize = g_cluster;
+    while (csize > 1 && (int)grid.x < csize) csize >>= 1;
+    grid.x = (grid.x + csize - 1) / csize * csize;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(TCP_THREADS, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const int use_atomic = split > 1;
     if (b_mn) {
       if (set_smem(igemm_tc_pixel_kernel<1>, smem)) return CN_ERR_CUDA;
-      igemm_tc_pixel_kernel<1><<<grid, TC_THREADS, smem, st>>>(g, src, wp, bias, dst, act, alpha, bn, bn_smem, nstages, cols, per, split > 1);
+      CN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc_pixel_kernel<1>, g, src, (const float*)wp, bias, dst, act, alpha, bn, bn_smem,
+                                       nb, cols, per, use_atomic, csize, g_dbg, g_prof));
     } else {
       if (set_smem(igemm_tc_pixel_kernel<0>, smem)) return CN_ERR_CUDA;
-      igemm_tc_pixel_kernel<0><<<grid, TC_THREADS, smem, st>>>(g, src, wp, bias, dst, act, alpha, bn, bn_smem, nstages, cols, per, split > 1);
+      CN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc_pixel_kernel<0>, g, src, (const float*)wp, bias, dst, act, alpha, bn, bn_smem,
+                                       nb, cols, per, use_atomic, csize, g_dbg, g_prof));
     }
     CN_CHECK_LAUNCH();
     return CN_OK;
@@ -1226,7 +1459,7 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
     if (set_smem(igemm_tc_wgrad_kernel, smem)) return CN_ERR_CUDA;
     dim3 grid(mt, nt, split);
     int cols = pow2_cols(3 * ((bn_smem + 31) / 32 * 32));
-    igemm_tc_wgrad_kernel<<<grid, TC_THREADS, smem, st>>>(g, x, gy, gw, bn, bn_smem, nstages, cols, per, split > 1);
+    igemm_tc_wgrad_kernel<<<grid, TC_THREADS, smem, st>>>(g, x, gy, gw, bn, bn_smem, nstages, cols, per, split > 1, g_dbg);
     CN_CHECK_LAUNCH();
   } else if ((long long)g.Ktot * g.Cn <= 256 * SKW_MAXOUT && g.M >= 4096) {
     int P = 8192 / (g.Ktot + g.Cn); if (P > 64) P = 64; if (P < 4) P = 4;
