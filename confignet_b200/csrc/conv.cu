@@ -449,78 +449,15 @@ __device__ __forceinline__ uint32_t mn_chunk_off(int r, int jn, uint32_t sbo) {
 
 constexpr int TC_BM = 128;        // GEMM rows per CTA (UMMA M)
 constexpr int TC_BK = 32;         // K elements per stage = one 128-byte swizzle row of tf32
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // one of the big / small A tiles
-constexpr int TC_THREADS = 416;   // warps 0-3: A gather, 4-7: B gather, 8-11: accumulator promotion + epilogue,
-                                  // 12: TMEM alloc + MMA issue
 constexpr int TC_CHUNK_KB = 16;   // k-blocks (512 K elements) accumulated in the tensor core before promotion
-constexpr int TC_MMA_WARP = 12;
-
-struct TcSmemLayout {
-  // dynamic smem, 1024-byte aligned: per stage [A big][A small][B big][B small]; then barriers, tmem ptr, taps
-  uint32_t stage_bytes, b_off, b_bytes, bar_off, tmem_off, taps_off, total;
-};
-__host__ __device__ inline TcSmemLayout tc_layout(int nstages, int bn_smem) {
-  TcSmemLayout l;
-  l.b_off = 2 * TC_A_BYTES;
-  l.b_bytes = bn_smem * TC_BK * 4;
-  l.stage_bytes = l.b_off + 2 * l.b_bytes;
-  l.bar_off = nstages * l.stage_bytes;
-  l.tmem_off = l.bar_off + (3 * nstages + 4) * 8;      // full[], empty[], acc_full[2], acc_empty[2], empty_b[]
-  l.taps_off = (l.tmem_off + 4 + 7) & ~7u;
-  l.total = l.taps_off + 256 * 8;
-  return l;
-}
-
-// issue the 4 k-steps x 3 split products of one stage (small cross terms first, big*big last)
-template <int A_MN, int B_MN>
-__device__ __forceinline__ void tc_issue_stage(uint32_t tmem_base, uint32_t abase, uint32_t bbase, uint32_t b_bytes,
-                                               uint32_t sbo_a, uint32_t sbo_b, uint32_t idesc, bool first) {
-#pragma unroll
-  for (int kk = 0; kk < TC_BK / 8; ++kk) {
-    const uint32_t ao = A_MN ? kk * 2 * sbo_a : kk * 32, bo = B_MN ? kk * 2 * sbo_b : kk * 32;
-    const uint32_t lbo_a = A_MN ? 512u : 16u, lbo_b = B_MN ? 512u : 16u;
-    const uint32_t la = A_MN ? 1u : 2u, lb = B_MN ? 1u : 2u;
-    uint64_t ab = umma_desc(abase + ao, lbo_a, sbo_a, la), as = umma_desc(abase + TC_A_BYTES + ao, lbo_a, sbo_a, la);
-    uint64_t bb = umma_desc(bbase + bo, lbo_b, sbo_b, lb), bs = umma_desc(bbase + b_bytes + bo, lbo_b, sbo_b, lb);
-    tc_mma_tf32(tmem_base, as, bb, idesc, !(first && kk == 0));
-    tc_mma_tf32(tmem_base, ab, bs, idesc, 1);
-    tc_mma_tf32(tmem_base, ab, bb, idesc, 1);
-  }
-}
 
 // The tensor core adds into its fp32 accumulator with truncation: measured on B200 the result drifts by
 // ~1.1e-8 * K relative (1.2e-4 at K = 18432), a bias that plain fp32 FMAs do not have.  So the MMA warp
-// accumulates at most TC_CHUNK_KB k-blocks into one of two ping-pong TMEM accumulators and warps 8-11 add
-// each finished chunk into a running fp32 total (round-to-nearest FADD on the CUDA cores), kept in a third
-// TMEM region, while the tensor core works on the next chunk.  store(cb, v) receives the final 32-column
-// groups of this thread's accumulator row.
-template <class StoreFn>
-__device__ __forceinline__ void tc_promote_and_store(uint32_t tmem_base, int pw, int bn, int bn_r, int nchunks,
-                                                     uint32_t bar_accfull, uint32_t bar_accempty, StoreFn store) {
-  const uint32_t lanebits = (uint32_t)(pw * 32) << 16;
-  for (int c = 0; c < nchunks; ++c) {
-    const int b = c & 1;
-    mbar_wait(bar_accfull + 8 * b, (c >> 1) & 1);
-    tc_fence_after();
-    const bool last = c == nchunks - 1;
-    for (int cb = 0; cb < bn; cb += 32) {
-      uint32_t v[32];
-      tc_ld32(tmem_base + lanebits + b * bn_r + cb, v);
-      if (c > 0) {
-        uint32_t t[32];
-        tc_ld32(tmem_base + lanebits + 2 * bn_r + cb, t);
-#pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(t[q]));
-      }
-      if (!last) tc_st32(tmem_base + lanebits + 2 * bn_r + cb, v);
-      else store(cb, v);
-    }
-    if (!last) { tc_fence_before(); __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(bar_accempty + 8 * b); }
-  }
-}
-
-// Same promotion with the running total in shared memory ([column][128 rows] fp32: lane = row, so the accesses
-// are conflict-free), which leaves the tensor memory to the ping-pong accumulators and the A stages.
+// accumulates at most TC_CHUNK_KB k-blocks into one of two ping-pong TMEM accumulators and the promotion
+// warps add each finished chunk into a running fp32 total (round-to-nearest FADD on the CUDA cores) while the
+// tensor core works on the next chunk.  store(cb, v) receives the final 32-column groups of this thread's
+// accumulator row.  The running total lives in shared memory ([column][128 rows] fp32: lane = row, so the
+// accesses are conflict-free), which leaves the tensor memory to the two accumulators and the A stages.
 template <class StoreFn>
 __device__ __forceinline__ void tc_promote_smem_and_store(uint32_t tmem_base, float* tot, int pw, int bn, int bn_r, int nchunks,
                                                           uint32_t bar_accfull, uint32_t bar_accempty, StoreFn store) {
@@ -546,30 +483,6 @@ __device__ __forceinline__ void tc_promote_smem_and_store(uint32_t tmem_base, fl
       }
     }
     if (!last) { tc_fence_before(); __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(bar_accempty + 8 * b); }
-  }
-}
-
-// MMA issue loop shared by both kernels (one warp; lane 0 issues)
-template <int A_MN, int B_MN>
-__device__ __forceinline__ void tc_mma_loop(uint32_t tmem_base, uint32_t sbase, const TcSmemLayout& L, int nstages,
-                                            int num_kb, int bn_r, uint32_t bar_full, uint32_t bar_empty,
-                                            uint32_t bar_accfull, uint32_t bar_accempty, uint32_t sbo_a,
-                                            uint32_t sbo_b, uint32_t idesc, int lane, int dbg = 0) {
-  for (int kb = 0; kb < num_kb; ++kb) {
-    const int s = kb % nstages;
-    const int c = kb / TC_CHUNK_KB, b = c & 1;
-    const bool chunk_first = (kb % TC_CHUNK_KB) == 0;
-    const bool chunk_last = (kb % TC_CHUNK_KB) == TC_CHUNK_KB - 1 || kb == num_kb - 1;
-    if (chunk_first && c >= 2) { mbar_wait(bar_accempty + 8 * b, ((c >> 1) - 1) & 1); }
-    mbar_wait(bar_full + 8 * s, (kb / nstages) & 1);
-    tc_fence_after();
-    if (lane == 0) {
-      const uint32_t abase = sbase + s * L.stage_bytes;
-      if (!(dbg & 4)) tc_issue_stage<A_MN, B_MN>(tmem_base + b * bn_r, abase, abase + L.b_off, L.b_bytes, sbo_a, sbo_b, idesc, chunk_first);
-      tc_commit(bar_empty + 8 * s);
-      if (chunk_last) tc_commit(bar_accfull + 8 * b);
-    }
-    __syncwarp();
   }
 }
 
@@ -698,7 +611,82 @@ __host__ __device__ inline TcpLayout tcp_layout(int nb, int bn_smem) {
   return l;
 }
 
-template <int B_MN>
+// Gradient pre-pack for the wgrad GEMM: the B operand tile of (n-tile, k-block) is 32 consecutive output pixels
+// x bn_smem channels of G, MN-major (channels contiguous, as in HBM).  Same stage image format as above.
+__global__ void __launch_bounds__(256)
+pack_grad_kernel(const float* __restrict__ G, int M, int Cn, float* __restrict__ out, int bn, int bn_smem, int total_kb) {
+  const int kb = blockIdx.x, nt = blockIdx.y;
+  const uint32_t b_bytes = (uint32_t)bn_smem * TC_BK * 4;
+  uint8_t* tile = reinterpret_cast<uint8_t*>(out) + ((size_t)nt * total_kb + kb) * 2 * b_bytes;
+  const int n0 = nt * bn, m0 = kb * TC_BK;
+  const int cpr = bn_smem >> 2, nchunks = 8 * bn_smem;
+  const uint32_t sbo = (uint32_t)(bn_smem >> 5) * 512u;
+  for (int q = threadIdx.x; q < nchunks; q += 256) {
+    const int r = q / cpr, jc = q - r * cpr;
+    const int m = m0 + r, n = n0 + 4 * jc;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < M && n < Cn && 4 * jc < bn) v = ldg128(G + (size_t)m * Cn + n);
+    const uint32_t off = mn_chunk_off(r, jc, sbo);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    uint4 bg, sm;
+    uint32_t* pb = reinterpret_cast<uint32_t*>(&bg);
+    uint32_t* ps = reinterpret_cast<uint32_t*>(&sm);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pb[i] = __float_as_uint(x[i]) & 0xffffe000u;
+      ps[i] = __float_as_uint(x[i] - __uint_as_float(pb[i])) & 0xffffe000u;
+    }
+    *reinterpret_cast<uint4*>(tile + off) = bg;
+    *reinterpret_cast<uint4*>(tile + b_bytes + off) = sm;
+  }
+}
+
+// wgrad A gather of one k-block (32 consecutive output pixels starting at (xn, x0, x1, x2)) for one (tap, channel)
+// row.  SEG = pixels per image-row segment inside the k-block: 32 when the row length E2 is a multiple of 32
+// (the k-block stays inside one image row), else SEG = E2 in {4, 8, 16} (32/SEG whole rows).  Straight-line
+// code per variant: the fully general per-pixel carry version is ~30 KB of SASS per call site and thrashes the
+// instruction cache (measured: 340 clk per pixel).
+struct WgGeom {                // plan geometry with the image row in position 2 (2-D plans carry it in position 1)
+  int E[3], U[3], S[3], n_img, mstride, ushift, Csrc;
+};
+__device__ __forceinline__ WgGeom wg_geom(const GemmPlan& p) {
+  WgGeom g;
+  const bool shift = p.E[2] == 1 && p.U[2] == 1 && p.S[2] == 1;
+  g.E[0] = shift ? 1 : p.E[0]; g.E[1] = shift ? p.E[0] : p.E[1]; g.E[2] = shift ? p.E[1] : p.E[2];
+  g.U[0] = shift ? 1 : p.U[0]; g.U[1] = shift ? p.U[0] : p.U[1]; g.U[2] = shift ? p.U[1] : p.U[2];
+  g.S[0] = shift ? 1 : p.S[0]; g.S[1] = shift ? p.S[0] : p.S[1]; g.S[2] = shift ? p.S[1] : p.S[2];
+  g.n_img = p.n_img; g.mstride = p.mstride; g.ushift = p.ushift; g.Csrc = p.Csrc;
+  return g;
+}
+template <int SEG>
+__device__ __forceinline__ void wg_load(const WgGeom& p, const float* __restrict__ Ac, bool wrok, int woff0, int woff1, int woff2,
+                                        int xn, int x0, int x1, int x2, uint32_t* v) {
+#pragma unroll
+  for (int s = 0; s < TC_BK / SEG; ++s) {
+    const int u0 = x0 * p.mstride + woff0, u1 = x1 * p.mstride + woff1;
+    const bool rowok = wrok && xn < p.n_img && (unsigned)u0 < (unsigned)p.U[0] && (unsigned)u1 < (unsigned)p.U[1];
+    const uint32_t rowbase = (((uint32_t)xn * p.S[0] + (uint32_t)(u0 >> p.ushift)) * p.S[1] + (uint32_t)(u1 >> p.ushift)) * p.S[2];
+    int u2 = x2 * p.mstride + woff2;
+#pragma unroll
+    for (int jj = 0; jj < SEG; ++jj) {
+      const bool ok = rowok && (unsigned)u2 < (unsigned)p.U[2];
+      v[s * SEG + jj] = ok ? __float_as_uint(__ldg(Ac + (size_t)(rowbase + (uint32_t)(u2 >> p.ushift)) * p.Csrc)) : 0u;
+      u2 += p.mstride;
+    }
+    if (SEG == 1) {             // any geometry: one pixel per segment, cursor advanced with uniform carries
+      if (++x2 == p.E[2]) { x2 = 0; if (++x1 == p.E[1]) { x1 = 0; if (++x0 == p.E[0]) { x0 = 0; ++xn; } } }
+    } else if (SEG < TC_BK) {   // SEG == E2: the next segment is the next image row
+      if (++x1 == p.E[1]) { x1 = 0; if (++x0 == p.E[0]) { x0 = 0; ++xn; } }
+    }
+  }
+}
+
+// WG = 1 is the weight-gradient GEMM D[(tap,c)][n] = sum_m Src[pix(m,tap)][c] * G[m][n] (K = output pixels):
+// the same pipeline with a different A gather - thread = GEMM row (tap, c), one k-block = that row's values
+// at 32 consecutive output pixels, which adjacent lanes (adjacent channels) read as coalesced lines; the pixel
+// cursor advances incrementally with warp-uniform carries - and B = the gradient, pre-split into stage images
+// by pack_grad_kernel (MN-major, as it lies in HBM).
+template <int B_MN, int WG>
 __global__ void __launch_bounds__(TCP_THREADS)
 igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ Wp,
                       const float* __restrict__ bias, float* __restrict__ D, int act, float alpha,
@@ -721,7 +709,7 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
   int2* s_taps = reinterpret_cast<int2*>(smem + L.taps_off);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * bn;
-  const int total_kb = (p.Ktot + TC_BK - 1) / TC_BK;
+  const int total_kb = ((WG ? p.M : p.Ktot) + TC_BK - 1) / TC_BK;
   const int kb_beg = blockIdx.z * kb_per_split;             // split-K over gridDim.z (atomic epilogue)
   const int num_kb = min(total_kb, kb_beg + kb_per_split) - kb_beg;   // host guarantees >= 1
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
@@ -753,8 +741,9 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
     //       and alternate k-blocks (A stage = k-block parity); the loads of a thread's next k-block are in
     //       flight while the current one is split into its tf32 big/small parts and written with tcgen05.st. =====
     const int q4 = warp & 3, par = warp >> 2;
-    const RowInfo row = decode_row(p, m0 + q4 * 32 + lane);
     const uint32_t a_t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + a_col0;
+    // ---- pixel mode state
+    const RowInfo row = decode_row(p, WG ? p.M : m0 + q4 * 32 + lane);
     auto src_off = [&](int kt) -> uint32_t {
       if (kt >= p.ntaps) return 0xffffffffu;
       const uint32_t sp = src_pixel(p, row, s_taps[kt].x);
@@ -790,6 +779,40 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
       while (l_c >= p.Csrc) { l_c -= p.Csrc; ++l_kt; }
       pt[2] += clock64() - t0;
     };
+    // ---- wgrad mode state: this thread's (tap, channel) row and the warp-uniform pixel cursor (n, e0, e1, e2)
+    const int wr = m0 + q4 * 32 + lane;
+    const bool wrok = WG && wr < p.Ktot;
+    int woff0 = 0, woff1 = 0, woff2 = 0, wc = 0;
+    int e2 = 0, e1 = 0, e0 = 0, en = 0;
+    const WgGeom wg = wg_geom(p);
+    if (WG) {
+      if (wrok) {
+        const int kt = wr / p.Csrc; wc = wr - kt * p.Csrc;
+        const int pk = s_taps[kt].x;
+        woff0 = (pk & 1023) - 8; woff1 = ((pk >> 10) & 1023) - 8; woff2 = (pk >> 20) - 8;
+        if (wg.E[2] != p.E[2] || wg.E[1] != p.E[1]) { woff2 = woff1; woff1 = woff0; woff0 = 0; }    // 2-D plan: row in position 1
+      }
+      int m = (kb_beg + par) * TC_BK;
+      e2 = m % wg.E[2]; m /= wg.E[2]; e1 = m % wg.E[1]; m /= wg.E[1]; e0 = m % wg.E[0]; en = m / wg.E[0];
+    }
+    const float* Ac = A + wc;
+    const float* Ac_ld = (dbg & 1) ? nullptr : Ac;
+    auto load_w = [&](float4* vv) {
+      uint32_t* v = reinterpret_cast<uint32_t*>(vv);
+      const bool ok = wrok && Ac_ld != nullptr;
+      const int seg = wg.E[2];
+      if (seg % TC_BK == 0) wg_load<32>(wg, Ac, ok, woff0, woff1, woff2, en, e0, e1, e2, v);
+      else if (seg == 16) wg_load<16>(wg, Ac, ok, woff0, woff1, woff2, en, e0, e1, e2, v);
+      else if (seg == 8) wg_load<8>(wg, Ac, ok, woff0, woff1, woff2, en, e0, e1, e2, v);
+      else if (seg == 4) wg_load<4>(wg, Ac, ok, woff0, woff1, woff2, en, e0, e1, e2, v);
+      else wg_load<1>(wg, Ac, ok, woff0, woff1, woff2, en, e0, e1, e2, v);
+      e2 += 2 * TC_BK;                                           // the sibling warp takes the next k-block
+      while (e2 >= wg.E[2]) {
+        e2 -= wg.E[2];
+        if (++e1 == wg.E[1]) { e1 = 0; if (++e0 == wg.E[0]) { e0 = 0; ++en; } }
+      }
+    };
+    auto load_any = [&](float4* v) { if (WG) load_w(v); else load_a(v); };
     int s_sa = par, s_u = 0;                 // A stage and use count of this warp's next k-block to store
     auto store_a = [&]() -> uint32_t {
       const int sa = s_sa;
@@ -827,12 +850,12 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
     };
     float4 va[8], vb[8];
     int kb = par;
-    if (kb < num_kb) load_a(va);
+    if (kb < num_kb) load_any(va);
     for (; kb < num_kb; kb += 4) {
-      if (kb + 2 < num_kb) load_a(vb);
+      if (kb + 2 < num_kb) load_any(vb);
       put_a(store_a(), va);
       if (kb + 2 < num_kb) {
-        if (kb + 4 < num_kb) load_a(va);
+        if (kb + 4 < num_kb) load_any(va);
         put_a(store_a(), vb);
       }
     }
@@ -841,8 +864,8 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
     // ===== promotion + epilogue: TMEM -> registers -> global (warp pw owns TMEM lanes 32pw..32pw+31) =====
     const int pw = warp - 8;
     const int m = m0 + pw * 32 + lane;
-    const bool mok = m < p.M;
-    const size_t rowoff = mok ? (size_t)dest_pixel(p, m) * p.Cn : 0;
+    const bool mok = m < (WG ? p.Ktot : p.M);
+    const size_t rowoff = mok ? (WG ? (size_t)m : (size_t)dest_pixel(p, m)) * p.Cn : 0;
     const int nchunks = (num_kb + TC_CHUNK_KB - 1) / TC_CHUNK_KB;
     tc_promote_smem_and_store(tmem_base, reinterpret_cast<float*>(smem + L.tot_off), pw, bn, bn_r, nchunks, bar_accfull, bar_accempty,
                               [&](int cb, const uint32_t* v) {
@@ -940,149 +963,6 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
   if (csize > 1) cluster_sync_all();      // no CTA leaves while a peer may still signal its barriers
   if (do_prof && tid == 0) prof[12] = clock64() - t_begin;
   if (warp == TCP_MMA_WARP) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// tcgen05 wgrad kernel: D[(tap,c)][n] = sum_m Src[pix(m,tap)][c] * G[m][n]; both operands MN-major
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS)
-igemm_tc_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ G,
-                      float* __restrict__ D, int bn, int bn_smem, int nstages, int tmem_cols,
-                      int kb_per_split, int use_atomic, int dbg) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const TcSmemLayout L = tc_layout(nstages, bn_smem);
-  const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_full = sbase + L.bar_off, bar_empty = bar_full + 8 * nstages;
-  const uint32_t bar_accfull = bar_empty + 8 * nstages, bar_accempty = bar_accfull + 16;
-  const int bn_r = (bn_smem + 31) / 32 * 32;
-  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_off);
-  int2* s_taps = reinterpret_cast<int2*>(smem + L.taps_off);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int r0 = blockIdx.x * TC_BM, n0 = blockIdx.y * bn;
-  const int total_kb = (p.M + TC_BK - 1) / TC_BK;
-  const int kb_beg = blockIdx.z * kb_per_split;
-  const int kb_end = min(total_kb, kb_beg + kb_per_split);
-  const int num_kb = kb_end - kb_beg;     // host guarantees >= 1
-  const uint32_t sbo_b = (uint32_t)(bn_smem >> 5) * 512u;
-
-  for (int i = tid; i < p.ntaps; i += TC_THREADS) s_taps[i] = p.taps[i];
-  if (tid == 0) {
-    for (int s = 0; s < nstages; ++s) { mbar_init(bar_full + 8 * s, 8); mbar_init(bar_empty + 8 * s, 1); }   // one arrival per gather warp
-    mbar_init(bar_accfull, 1); mbar_init(bar_accfull + 8, 1);
-    mbar_init(bar_accempty, 4); mbar_init(bar_accempty + 8, 4);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == TC_MMA_WARP) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + L.tmem_off), "r"(tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp < 4) {
-    // ===== A gather: lane = 16-byte chunk of the 128 GEMM rows (fixed tap, 4 channels per thread),
-    //       warp w fills pixel rows 8w..8w+7 of the 32-pixel K block; one k-block of register prefetch =====
-    const int rr = r0 + 4 * lane;
-    const bool rok = rr < p.Ktot;
-    int c = 0, tap_pk = 0;
-    if (rok) { int kt = rr / p.Csrc; c = rr - kt * p.Csrc; tap_pk = s_taps[kt].x; }
-    auto load_a = [&](int it, float4* v) {
-      const int mbase = (kb_beg + it) * TC_BK + warp * 8;
-      RowInfo mine = decode_row(p, mbase + (lane & 7));
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        RowInfo ri;
-        ri.base = __shfl_sync(0xffffffffu, mine.base, i);
-        ri.pk = __shfl_sync(0xffffffffu, mine.pk, i);
-        uint32_t sp = rok ? src_pixel(p, ri, tap_pk) : 0xffffffffu;
-        v[i] = (sp != 0xffffffffu && !(dbg & 1)) ? ldg128(A + (size_t)sp * p.Csrc + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    uint32_t aoff[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) aoff[i] = mn_chunk_off(warp * 8 + i, lane, 2048u);
-    float4 cur[8], nxt[8];
-    load_a(0, cur);
-    for (int it = 0; it < num_kb; ++it) {
-      const int s = it % nstages;
-      if (it + 1 < num_kb) load_a(it + 1, nxt);
-      if (it >= nstages) mbar_wait(bar_empty + 8 * s, ((it / nstages) - 1) & 1);
-      const uint32_t abase = sbase + s * L.stage_bytes;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) if (!(dbg & 8)) sts_split4(abase + aoff[i], abase + TC_A_BYTES + aoff[i], cur[i]);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * s);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-    }
-  } else if (warp >= 8 && warp < 12) {
-    // ===== promotion + epilogue =====
-    const int pw = warp - 8;
-    const int r = r0 + pw * 32 + lane;
-    const bool ok = r < p.Ktot;
-    const size_t rowoff = (size_t)r * p.Cn;
-    const int nchunks = (num_kb + TC_CHUNK_KB - 1) / TC_CHUNK_KB;
-    tc_promote_and_store(tmem_base, pw, bn, bn_r, nchunks, bar_accfull, bar_accempty, [&](int cb, const uint32_t* v) {
-      if (ok) {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          int n = n0 + cb + q;
-          if (cb + q < bn && n < p.Cn) {
-            if (use_atomic) atomicAdd(D + rowoff + n, __uint_as_float(v[q]));
-            else D[rowoff + n] = __uint_as_float(v[q]);
-          }
-        }
-      }
-    });
-  } else if (warp < 8) {
-    // ===== B gather: 32 pixel rows x bn_smem columns of G (bn_smem in {32,64,128}) =====
-    const int t = tid - 128;
-    const int cpr = bn_smem >> 2;
-    const int jn = t % cpr, rb0 = t / cpr, rstep = 128 / cpr;
-    const int n = n0 + 4 * jn;
-    const bool nok = n < p.Cn && 4 * jn < bn;
-    auto load_b = [&](int it, float4* v) {
-      const int mbase = (kb_beg + it) * TC_BK;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = rb0 + i * rstep, m = mbase + r;
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < TC_BK && nok && m < p.M && !(dbg & 2)) v[i] = ldg128(G + (size_t)m * p.Cn + n);
-      }
-    };
-    uint32_t boff[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) boff[i] = mn_chunk_off(rb0 + i * rstep, jn, sbo_b);
-    float4 cur[8], nxt[8];
-    load_b(0, cur);
-    for (int it = 0; it < num_kb; ++it) {
-      const int s = it % nstages;
-      if (it + 1 < num_kb) load_b(it + 1, nxt);
-      if (it >= nstages) mbar_wait(bar_empty + 8 * s, ((it / nstages) - 1) & 1);
-      const uint32_t bbase = sbase + s * L.stage_bytes + L.b_off;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (rb0 + i * rstep < TC_BK && !(dbg & 8)) sts_split4(bbase + boff[i], bbase + L.b_bytes + boff[i], cur[i]);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * s);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-    }
-  } else {
-    const uint32_t idesc = umma_idesc_tf32(bn_smem, 1, 1);
-    tc_mma_loop<1, 1>(tmem_base, sbase, L, nstages, num_kb, bn_r, bar_full, bar_empty, bar_accfull, bar_accempty,
-                      2048u, sbo_b, idesc, lane, dbg);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == TC_MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
@@ -1251,7 +1131,6 @@ static int num_sms() {
   return g_num_sms;
 }
 
-static int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
 
 template <typename K>
 static int set_smem(K kernel, int bytes) {
@@ -1279,6 +1158,66 @@ static void pick_bn_k(int cn, int* bn, int* bn_smem) {
 }
 
 static std::map<const void*, std::pair<float*, size_t>> g_wpack;    // per plan (keyed by its tap table): packed-weight buffer
+static float* g_gpack = nullptr;       // packed-gradient workspace of the wgrad GEMM (grow-only; launches on one stream serialise)
+static size_t g_gpack_bytes = 0;
+
+static int packed_buffer(const void* key, size_t bytes, float** out) {
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  if (key == nullptr) {
+    if (g_gpack_bytes < bytes) {
+      if (g_gpack) { CN_CHECK_CUDA(cudaDeviceSynchronize()); cudaFree(g_gpack); }
+      CN_CHECK_CUDA(cudaMalloc(&g_gpack, bytes));
+      g_gpack_bytes = bytes;
+    }
+    *out = g_gpack;
+    return CN_OK;
+  }
+  auto it = g_wpack.find(key);
+  if (it == g_wpack.end() || it->second.second < bytes) {
+    float* wp = nullptr;
+    if (it != g_wpack.end()) { CN_CHECK_CUDA(cudaDeviceSynchronize()); cudaFree(it->second.first); }
+    CN_CHECK_CUDA(cudaMalloc(&wp, bytes));
+    g_wpack[key] = std::make_pair(wp, bytes);
+    *out = wp;
+  } else {
+    *out = it->second.first;
+  }
+  return CN_OK;
+}
+
+// B stages fill the shared memory (A lives in tensor memory); >113 KB also keeps it at one CTA per SM, which
+// the 512-column TMEM allocation needs.
+static void tc_smem_config(int bn_smem, int* nb, int* smem) {
+  int n = 6;
+  TcpLayout L = tcp_layout(n, bn_smem);
+  while (n > 2 && L.total + 1024 > 200 * 1024) { --n; L = tcp_layout(n, bn_smem); }
+  *nb = n;
+  *smem = (int)L.total + 1024 < 120 * 1024 ? 120 * 1024 : (int)L.total + 1024;
+}
+
+template <int B_MN, int WG>
+static int launch_tc(const GemmPlan& g, const float* src, const float* packed, const float* bias, float* dst, int act,
+                     float alpha, int bn, int bn_smem, dim3 grid, int per, int split, cudaStream_t st) {
+  int nb, smem;
+  tc_smem_config(bn_smem, &nb, &smem);
+  // thread-block cluster along M: the CTAs of a cluster share the B stream by multicast
+  int csize = g_cluster;
+  while (csize > 1 && (int)grid.x < csize) csize >>= 1;
+  grid.x = (grid.x + csize - 1) / csize * csize;
+  grid.z = split;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(TCP_THREADS, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (set_smem(igemm_tc_pixel_kernel<B_MN, WG>, smem)) return CN_ERR_CUDA;
+  CN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc_pixel_kernel<B_MN, WG>, g, src, packed, bias, dst, act, alpha, bn, bn_smem,
+                                   nb, 512, per, (int)(split > 1), csize, g_dbg, g_prof));
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
 
 // zero_mode: 0 = this launch covers all of dst and may zero it for a split-K run, 1 = dst was zeroed by the
 // caller (phased dgrad), 2 = no split-K allowed
@@ -1292,13 +1231,6 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
   if (tc) {
     int bn, bn_smem;
     if (b_mn) pick_bn_mn(g.Cn, &bn, &bn_smem); else pick_bn_k(g.Cn, &bn, &bn_smem);
-    // B stages fill the shared memory (A lives in tensor memory); >113 KB also keeps it at one CTA per SM,
-    // which the 512-column TMEM allocation needs
-    int nb = 6;
-    TcpLayout L = tcp_layout(nb, bn_smem);
-    while (nb > 2 && L.total + 1024 > 200 * 1024) { --nb; L = tcp_layout(nb, bn_smem); }
-    int smem = L.total + 1024;
-    if (smem < 120 * 1024) smem = 120 * 1024;
     dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.Cn + bn - 1) / bn, 1);
     const int total_kb = (g.Ktot + TC_BK - 1) / TC_BK;
     int per = total_kb, split = 1;
@@ -1311,51 +1243,16 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
       if (split > 1 && zero_mode == 0)
         CN_CHECK_CUDA(cudaMemsetAsync(dst, 0, (size_t)g.n_img * g.Q[0] * g.Q[1] * g.Q[2] * g.Cn * sizeof(float), st));
     }
-    grid.z = split;
     // pre-pack the weights into per-(n-tile, k-block) stage images (buffer cached per plan)
-    const size_t pack_bytes = (size_t)grid.y * total_kb * 2 * bn_smem * TC_BK * 4;
     float* wp = nullptr;
-    {
-      std::lock_guard<std::mutex> lock(g_plan_mutex);
-      auto it = g_wpack.find((const void*)g.taps);
-      if (it == g_wpack.end() || it->second.second < pack_bytes) {
-        if (it != g_wpack.end()) cudaFree(it->second.first);
-        CN_CHECK_CUDA(cudaMalloc(&wp, pack_bytes));
-        g_wpack[(const void*)g.taps] = std::make_pair(wp, pack_bytes);
-      } else {
-        wp = it->second.first;
-      }
-    }
-    {
-      dim3 pgrid(total_kb, grid.y);
-      if (b_mn) pack_weights_kernel<1><<<pgrid, 256, 0, st>>>(g, w, wp, bn, bn_smem, total_kb);
-      else pack_weights_kernel<0><<<pgrid, 256, 0, st>>>(g, w, wp, bn, bn_smem, total_kb);
-      CN_CHECK_LAUNCH();
-    }
-    int cols = 512;
-    // thread-block cluster along M: the CTAs of a cluster share the B (weight) stream by multicast
-    int csize = g_cluster;
-    while (csize > 1 && (int)grid.x < csize) csize >>= 1;
-    grid.x = (grid.x + csize - 1) / csize * csize;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid; cfg.blockDim = dim3(TCP_THREADS, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    const int use_atomic = split > 1;
-    if (b_mn) {
-      if (set_smem(igemm_tc_pixel_kernel<1>, smem)) return CN_ERR_CUDA;
-      CN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc_pixel_kernel<1>, g, src, (const float*)wp, bias, dst, act, alpha, bn, bn_smem,
-                                       nb, cols, per, use_atomic, csize, g_dbg, g_prof));
-    } else {
-      if (set_smem(igemm_tc_pixel_kernel<0>, smem)) return CN_ERR_CUDA;
-      CN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc_pixel_kernel<0>, g, src, (const float*)wp, bias, dst, act, alpha, bn, bn_smem,
-                                       nb, cols, per, use_atomic, csize, g_dbg, g_prof));
-    }
+    int rc = packed_buffer((const void*)g.taps, (size_t)grid.y * total_kb * 2 * bn_smem * TC_BK * 4, &wp);
+    if (rc) return rc;
+    dim3 pgrid(total_kb, grid.y);
+    if (b_mn) pack_weights_kernel<1><<<pgrid, 256, 0, st>>>(g, w, wp, bn, bn_smem, total_kb);
+    else pack_weights_kernel<0><<<pgrid, 256, 0, st>>>(g, w, wp, bn, bn_smem, total_kb);
     CN_CHECK_LAUNCH();
-    return CN_OK;
+    if (b_mn) return launch_tc<1, 0>(g, src, wp, bias, dst, act, alpha, bn, bn_smem, grid, per, split, st);
+    return launch_tc<0, 0>(g, src, wp, bias, dst, act, alpha, bn, bn_smem, grid, per, split, st);
   }
   // CUDA-core path
   if (g.Cn <= 4 && g.M >= 4096 && g.Ktot * 16 <= 96 * 1024) {
@@ -1444,23 +1341,25 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
   g_last_impl = tc ? 2 : 1;
   if (tc) {
     int bn, bn_smem; pick_bn_mn(g.Cn, &bn, &bn_smem);
-    int nstages = 3;
-    TcSmemLayout L = tc_layout(nstages, bn_smem);
-    int smem = L.total + 1024;
     int mt = (g.Ktot + TC_BM - 1) / TC_BM, nt = (g.Cn + bn - 1) / bn;
     int total_kb = (g.M + TC_BK - 1) / TC_BK;
-    int split = (2 * num_sms() + mt * nt - 1) / (mt * nt);
+    // split-K over the pixels so that the CTAs fill whole waves of SMs (each CTA keeps >= 8 k-blocks)
+    int mtc = (mt + g_cluster - 1) / g_cluster * g_cluster;
+    int split = (2 * num_sms()) / (mtc * nt);
     int maxsplit = total_kb / 8; if (maxsplit < 1) maxsplit = 1;
     if (split > maxsplit) split = maxsplit;
     if (split < 1) split = 1;
     int per = (total_kb + split - 1) / split;
     split = (total_kb + per - 1) / per;
     if (split > 1) CN_CHECK_CUDA(cudaMemsetAsync(gw, 0, wn * sizeof(float), st));
-    if (set_smem(igemm_tc_wgrad_kernel, smem)) return CN_ERR_CUDA;
-    dim3 grid(mt, nt, split);
-    int cols = pow2_cols(3 * ((bn_smem + 31) / 32 * 32));
-    igemm_tc_wgrad_kernel<<<grid, TC_THREADS, smem, st>>>(g, x, gy, gw, bn, bn_smem, nstages, cols, per, split > 1, g_dbg);
+    // the gradient pre-split into per-(n-tile, k-block) stage images: every (tap,c)-tile CTA streams it
+    float* gp = nullptr;
+    rc = packed_buffer(nullptr, (size_t)nt * total_kb * 2 * bn_smem * TC_BK * 4, &gp);
+    if (rc) return rc;
+    pack_grad_kernel<<<dim3(total_kb, nt), 256, 0, st>>>(gy, g.M, g.Cn, gp, bn, bn_smem, total_kb);
     CN_CHECK_LAUNCH();
+    rc = launch_tc<1, 1>(g, x, gp, nullptr, gw, CN_ACT_NONE, 0.f, bn, bn_smem, dim3(mt, nt, 1), per, split, st);
+    if (rc) return rc;
   } else if ((long long)g.Ktot * g.Cn <= 256 * SKW_MAXOUT && g.M >= 4096) {
     int P = 8192 / (g.Ktot + g.Cn); if (P > 64) P = 64; if (P < 4) P = 4;
     int smem = P * (g.Ktot + g.Cn) * (int)sizeof(float);

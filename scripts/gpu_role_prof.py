@@ -9,16 +9,22 @@ P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
 lib.cn_debug_set_cluster(int(os.environ.get("CLUSTER", "1")))
 lib.cn_debug_set_prof.argtypes = [ctypes.c_void_p]
 buf = torch.zeros(16, dtype=torch.int64, device=dev)
-for (B, dims, cin, cout, k) in [(16, (64, 64), 256, 256, 3), (16, (64, 64), 256, 64, 3)]:
+OP = os.environ.get("OP", "fwd")
+for (B, dims, cin, cout, k) in [(16, (64, 64), 256, 256, 3), (16, (64, 64), 256, 64, 3), (16, (256, 256), 64, 64, 3)]:
     d = L.make_conv_desc(2, B, dims, cin, cout, [k, k], 1, 1)
     x = torch.randn(B, *dims, cin, device=dev); w = torch.randn(k, k, cin, cout, device=dev) * 0.05
-    y = torch.empty(B, *dims, cout, device=dev)
+    y = torch.empty(B, *dims, cout, device=dev); gy = torch.randn(B, *dims, cout, device=dev); gw = torch.empty_like(w)
+    def run():
+        if OP == "fwd":
+            L.call("cn_conv_fwd", ctypes.byref(d), P(x), P(w), None, 0, 0.0, P(y), 0, st())
+        else:
+            L.call("cn_conv_wgrad", ctypes.byref(d), P(x), P(gy), P(gw), None, 0, st())
     for dbg in [int(a) for a in sys.argv[1:]] or [0]:
         lib.cn_debug_set(dbg)
         for _ in range(2):
-            L.call("cn_conv_fwd", ctypes.byref(d), P(x), P(w), None, 0, 0.0, P(y), 0, st())
+            run()
         lib.cn_debug_set_prof(ctypes.c_void_p(buf.data_ptr()))
-        L.call("cn_conv_fwd", ctypes.byref(d), P(x), P(w), None, 0, 0.0, P(y), 0, st())
+        run()
         torch.cuda.synchronize()
         lib.cn_debug_set_prof(None)
         v = buf.cpu().numpy().astype(float); nkb = max(v[9], 1)
