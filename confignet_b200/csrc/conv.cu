@@ -1077,6 +1077,260 @@ wgrad_skinny_kernel(GemmPlan p, const float* __restrict__ A, const float* __rest
     if (ok[j] >= 0) atomicAdd(D + tid + 256 * j, acc[j]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Skinny layers, second generation (HBM-bound layers with 3 channels on one side: fromRGB 3->3, D.block0 3->48,
+// VGG block1_conv1 3->64, map_final 32->3).  A warp walks a contiguous range of GEMM rows (pixels) with a
+// warp-uniform cursor (no per-pixel divisions); its lanes span the WIDE channel dimension, so every global access
+// is a coalesced line, and the per-tap source addresses are computed lane-parallel (lane = tap or patch element)
+// and broadcast with shuffles.
+//   cfew wgrad: Csrc >= 8 wide, Cn <= 4   (lanes = source channels)
+//   kfew wgrad: K = ntaps*Csrc <= 32, Cn wide (lanes = output channels)
+// (The same warp-per-pixel formulation was measured 2-4x SLOWER than the thread-per-pixel kernels for the forward /
+// dgrad direction of these layers - too many instructions per output - so those keep pixel_smalln / igemm_ffma.)
+// ------------------------------------------------------------------------------------------------
+struct PixCursor { int n, e0, e1, e2; };
+__device__ __forceinline__ PixCursor cursor_at(const GemmPlan& p, int m) {
+  PixCursor c;
+  c.e2 = m % p.E[2]; m /= p.E[2];
+  c.e1 = m % p.E[1]; m /= p.E[1];
+  c.e0 = m % p.E[0]; c.n = m / p.E[0];
+  return c;
+}
+__device__ __forceinline__ void cursor_next(const GemmPlan& p, PixCursor& c) {
+  if (++c.e2 == p.E[2]) { c.e2 = 0; if (++c.e1 == p.E[1]) { c.e1 = 0; if (++c.e0 == p.E[0]) { c.e0 = 0; ++c.n; } } }
+}
+// source pixel of (cursor, tap offsets) or 0xffffffff in the padding
+__device__ __forceinline__ uint32_t cursor_src(const GemmPlan& p, const PixCursor& c, int o0, int o1, int o2) {
+  const int u0 = c.e0 * p.mstride + o0, u1 = c.e1 * p.mstride + o1, u2 = c.e2 * p.mstride + o2;
+  const bool ok = (unsigned)u0 < (unsigned)p.U[0] && (unsigned)u1 < (unsigned)p.U[1] && (unsigned)u2 < (unsigned)p.U[2];
+  if (!ok) return 0xffffffffu;
+  return (((uint32_t)c.n * p.S[0] + (uint32_t)(u0 >> p.ushift)) * p.S[1] + (uint32_t)(u1 >> p.ushift)) * p.S[2] + (uint32_t)(u2 >> p.ushift);
+}
+__device__ __forceinline__ uint32_t cursor_dst(const GemmPlan& p, const PixCursor& c) {
+  return (((uint32_t)c.n * p.Q[0] + (uint32_t)(c.e0 * p.ostride + p.ooff[0])) * p.Q[1] + (uint32_t)(c.e1 * p.ostride + p.ooff[1])) * p.Q[2] +
+         (uint32_t)(c.e2 * p.ostride + p.ooff[2]);
+}
+__device__ __forceinline__ void tap_offsets(int pk, int& o0, int& o1, int& o2) {
+  o0 = (pk & 1023) - 8; o1 = ((pk >> 10) & 1023) - 8; o2 = (pk >> 20) - 8;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// wgrad, Cn <= 4, ntaps <= 16, one 32-channel chunk per blockIdx.y: D[(tap,c)][n] += sum_pix Src[src(pix,tap)][c] * G[pix][n]
+__global__ void __launch_bounds__(256)
+skinny_cfew_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ G, float* __restrict__ D, int rows_per_warp) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int c = blockIdx.y * 32 + lane;
+  const bool cok = c < p.Csrc;
+  int o0 = 0, o1 = 0, o2 = 0;
+  const bool tapok = lane < p.ntaps;
+  if (tapok) tap_offsets(p.taps[lane].x, o0, o1, o2);
+  const int gw = blockIdx.x * 8 + (tid >> 5);
+  int m = gw * rows_per_warp;
+  const int mend = min(p.M, m + rows_per_warp);
+  float acc[16][4];
+#pragma unroll
+  for (int t = 0; t < 16; ++t)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) acc[t][n] = 0.f;
+  if (m < mend) {
+    PixCursor cur = cursor_at(p, m);
+    for (; m < mend; ++m) {
+      const uint32_t sp = tapok ? cursor_src(p, cur, o0, o1, o2) : 0xffffffffu;
+      const float gl = lane < p.Cn ? __ldg(G + (size_t)m * p.Cn + lane) : 0.f;
+      float g[4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) g[n] = __shfl_sync(0xffffffffu, gl, n);
+      float x[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        x[t] = 0.f;
+        if (t < p.ntaps) {
+          const uint32_t s = __shfl_sync(0xffffffffu, sp, t);
+          if (s != 0xffffffffu && cok) x[t] = __ldg(A + (size_t)s * p.Csrc + c);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 16; ++t)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[t][n] = fmaf(x[t], g[n], acc[t][n]);
+      cursor_next(p, cur);
+    }
+  }
+  // block reduction over the 8 warps, then one atomic per output and block
+  __shared__ float red[16 * 32 * 4];
+  for (int i = tid; i < 16 * 32 * 4; i += 256) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < 16; ++t)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+      if (t < p.ntaps && n < p.Cn) atomicAdd(&red[(t * 32 + lane) * 4 + n], acc[t][n]);
+  __syncthreads();
+  for (int i = tid; i < p.ntaps * 32 * 4; i += 256) {
+    const int t = i >> 7, l = (i >> 2) & 31, n = i & 3, cc = blockIdx.y * 32 + l;
+    if (n < p.Cn && cc < p.Csrc) atomicAdd(D + ((size_t)t * p.Csrc + cc) * p.Cn + n, red[i]);
+  }
+}
+
+// wgrad, K = ntaps*Csrc <= 32, Cn <= 64: D[k][n] += sum_pix patch[pix][k] * G[pix][n]
+__global__ void __launch_bounds__(256)
+skinny_kfew_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ G, float* __restrict__ D, int rows_per_warp) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int K = p.Ktot;
+  const bool n0ok = lane < p.Cn, n1ok = lane + 32 < p.Cn;
+  int o0 = 0, o1 = 0, o2 = 0, pc = 0;
+  const bool kok = lane < K;
+  if (kok) { const int t = lane / p.Csrc; pc = lane - t * p.Csrc; tap_offsets(p.taps[t].x, o0, o1, o2); }
+  float a0[32], a1[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
+  const int gw = blockIdx.x * 8 + (tid >> 5);
+  int m = gw * rows_per_warp;
+  const int mend = min(p.M, m + rows_per_warp);
+  if (m < mend) {
+    PixCursor cur = cursor_at(p, m);
+    auto patch = [&](const PixCursor& c) -> float {
+      const uint32_t sp = kok ? cursor_src(p, c, o0, o1, o2) : 0xffffffffu;
+      return sp != 0xffffffffu ? __ldg(A + (size_t)sp * p.Csrc + pc) : 0.f;
+    };
+    float pv_n = patch(cur);
+    float g0_n = n0ok ? __ldg(G + (size_t)m * p.Cn + lane) : 0.f, g1_n = n1ok ? __ldg(G + (size_t)m * p.Cn + lane + 32) : 0.f;
+    for (; m < mend; ++m) {
+      const float pv = pv_n, g0 = g0_n, g1 = g1_n;
+      cursor_next(p, cur);
+      if (m + 1 < mend) {                              // next pixel's loads in flight while this one is accumulated
+        pv_n = patch(cur);
+        g0_n = n0ok ? __ldg(G + (size_t)(m + 1) * p.Cn + lane) : 0.f;
+        g1_n = n1ok ? __ldg(G + (size_t)(m + 1) * p.Cn + lane + 32) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        if (k < K) {
+          const float x = __shfl_sync(0xffffffffu, pv, k);
+          a0[k] = fmaf(x, g0, a0[k]); a1[k] = fmaf(x, g1, a1[k]);
+        }
+      }
+    }
+  }
+  __shared__ float red[32 * 64];
+  for (int i = tid; i < 32 * 64; i += 256) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    if (k < K) {
+      if (n0ok) atomicAdd(&red[k * 64 + lane], a0[k]);
+      if (n1ok) atomicAdd(&red[k * 64 + 32 + lane], a1[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < K * 64; i += 256) {
+    const int k = i >> 6, n = i & 63;
+    if (n < p.Cn) atomicAdd(D + (size_t)k * p.Cn + n, red[i]);
+  }
+}
+
+// wgrad of a 1x1 / stride-1 layer with <= 4 channels on both sides (fromRGB 3->3): a flat reduction over the pixels
+__global__ void __launch_bounds__(256)
+wgrad_flat_kernel(const float* __restrict__ X, const float* __restrict__ G, int M, int cin, int cout, float* __restrict__ D) {
+  float acc[4][4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) acc[c][n] = 0.f;
+  for (int m = blockIdx.x * 256 + threadIdx.x; m < M; m += gridDim.x * 256) {
+    float x[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) if (c < cin) x[c] = __ldg(X + (size_t)m * cin + c);
+#pragma unroll
+    for (int n = 0; n < 4; ++n) if (n < cout) g[n] = __ldg(G + (size_t)m * cout + n);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) acc[c][n] = fmaf(x[c], g[n], acc[c][n]);
+  }
+  __shared__ float red[16];
+  if (threadIdx.x < 16) red[threadIdx.x] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const float v = warp_sum(acc[c][n]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&red[c * 4 + n], v);
+    }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    const int c = threadIdx.x >> 2, n = threadIdx.x & 3;
+    if (c < cin && n < cout) atomicAdd(D + c * cout + n, red[threadIdx.x]);
+  }
+}
+
+// Dense layers with a handful of rows (the AdaIN / latent MLPs, the style heads, disc_map, latent_predictor:
+// M = batch <= 64): y[m][n] = act(sum_k x[m][k] * W(k, n) + b[n]).  The weight matrix is read exactly once
+// (lane = output column), x is staged in shared memory and broadcast, the 8 warps of a block and the blocks of
+// gridDim.y split K.  W(k, n) = W[k*wsc + n*wsn] covers forward (Keras (in, out)) and dgrad (transposed).
+template <int MT>
+__global__ void __launch_bounds__(256)
+dense_small_kernel(const float* __restrict__ X, int M, int K, const float* __restrict__ W, int wsc, int wsn,
+                   const float* __restrict__ bias, float* __restrict__ Y, int N, int act, float alpha,
+                   int kchunk, int use_atomic) {
+  __shared__ __align__(16) float xs[MT][132];
+  __shared__ float outs[MT][32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.x * 32 + lane;
+  const bool nok = n < N;
+  const int kbeg = blockIdx.y * kchunk, kend = min(K, kbeg + kchunk);
+  for (int i = tid; i < MT * 32; i += 256) (&outs[0][0])[i] = 0.f;
+  float acc[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+  for (int k0 = kbeg; k0 < kend; k0 += 128) {
+    __syncthreads();
+    for (int i = tid; i < MT * 128; i += 256) {
+      const int m = i >> 7, kk = i & 127;
+      xs[m][kk] = (m < M && k0 + kk < kend) ? __ldg(X + (size_t)m * K + k0 + kk) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; q += 4) {
+      const int kk = warp * 16 + q, k = k0 + kk;
+      float wv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) wv[e] = (nok && k + e < kend) ? __ldg(W + (size_t)(k + e) * wsc + (size_t)n * wsn) : 0.f;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const float4 xv = *reinterpret_cast<const float4*>(&xs[m][kk]);
+        acc[m] = fmaf(xv.x, wv[0], acc[m]); acc[m] = fmaf(xv.y, wv[1], acc[m]);
+        acc[m] = fmaf(xv.z, wv[2], acc[m]); acc[m] = fmaf(xv.w, wv[3], acc[m]);
+      }
+    }
+  }
+  // deterministic cross-warp sum: the warps add their partials in a fixed order
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int m = 0; m < MT; ++m) outs[m][lane] += acc[m];
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < MT * 32; i += 256) {
+    const int m = i >> 5, nn = blockIdx.x * 32 + (i & 31);
+    if (m >= M || nn >= N) continue;
+    float v = outs[m][i & 31];
+    if (use_atomic) {
+      if (bias != nullptr && blockIdx.y == 0) v += bias[nn];
+      atomicAdd(Y + (size_t)m * N + nn, v);
+    } else {
+      if (bias != nullptr) v += bias[nn];
+      Y[(size_t)m * N + nn] = cn_apply_act(v, act, alpha);
+    }
+  }
+}
+
 // column sums for narrow matrices (n < 32): flat coalesced walk, every thread stays on one column
 __global__ void __launch_bounds__(256)
 colsum_narrow_kernel(const float* __restrict__ g, size_t total, int n, int threads_used, float* __restrict__ out) {
@@ -1255,7 +1509,25 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
     return launch_tc<0, 0>(g, src, wp, bias, dst, act, alpha, bn, bn_smem, grid, per, split, st);
   }
   // CUDA-core path
-  if (g.Cn <= 4 && g.M >= 4096 && g.Ktot * 16 <= 96 * 1024) {
+  const bool flat = g.ntaps == 1 && g.E[0] * g.E[1] * g.E[2] == 1 && g.S[0] * g.S[1] * g.S[2] == 1 && g.Q[0] * g.Q[1] * g.Q[2] == 1;
+  if (flat && g.M <= 64) {
+    // Dense layer on a few rows
+    int nt = (g.Cn + 31) / 32;
+    int split = 1;
+    if (act == CN_ACT_NONE && zero_mode != 2 && g.Ktot >= 1024) {
+      split = (num_sms() + nt - 1) / nt;
+      int maxsplit = g.Ktot / 256;
+      if (split > maxsplit) split = maxsplit;
+      if (split < 1) split = 1;
+    }
+    int kchunk = ((g.Ktot + split - 1) / split + 127) / 128 * 128;
+    split = (g.Ktot + kchunk - 1) / kchunk;
+    if (split > 1 && zero_mode == 0) CN_CHECK_CUDA(cudaMemsetAsync(dst, 0, (size_t)g.M * g.Cn * sizeof(float), st));
+    dim3 grid(nt, split);
+    if (g.M <= 16) dense_small_kernel<16><<<grid, 256, 0, st>>>(src, g.M, g.Ktot, w, g.wsc, g.wsn, bias, dst, g.Cn, act, alpha, kchunk, split > 1);
+    else if (g.M <= 32) dense_small_kernel<32><<<grid, 256, 0, st>>>(src, g.M, g.Ktot, w, g.wsc, g.wsn, bias, dst, g.Cn, act, alpha, kchunk, split > 1);
+    else dense_small_kernel<64><<<grid, 256, 0, st>>>(src, g.M, g.Ktot, w, g.wsc, g.wsn, bias, dst, g.Cn, act, alpha, kchunk, split > 1);
+  } else if (g.Cn <= 4 && g.M >= 4096 && g.Ktot * 16 <= 96 * 1024) {
     dim3 grid((g.M + 255) / 256, 1, 1);
     int smem = g.Ktot * 16;
     if (smem > 48 * 1024 && set_smem(pixel_smalln_kernel, smem)) return CN_ERR_CUDA;
@@ -1360,6 +1632,24 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
     CN_CHECK_LAUNCH();
     rc = launch_tc<1, 1>(g, x, gp, nullptr, gw, CN_ACT_NONE, 0.f, bn, bn_smem, dim3(mt, nt, 1), per, split, st);
     if (rc) return rc;
+  } else if (g.ntaps == 1 && g.Csrc <= 4 && g.Cn <= 4 && g.mstride == 1 && g.ushift == 0 && g.M >= 4096) {   // 1x1, stride 1: source pixel = output pixel
+    CN_CHECK_CUDA(cudaMemsetAsync(gw, 0, wn * sizeof(float), st));
+    wgrad_flat_kernel<<<4 * num_sms(), 256, 0, st>>>(x, gy, g.M, g.Csrc, g.Cn, gw);
+    CN_CHECK_LAUNCH();
+  } else if (g.Cn <= 4 && g.Csrc >= 8 && g.ntaps <= 16 && g.M >= 4096) {
+    int warps = 16 * num_sms();
+    int per = (g.M + warps - 1) / warps; if (per < 64) per = 64;
+    int blocks = ((g.M + per - 1) / per + 7) / 8;
+    CN_CHECK_CUDA(cudaMemsetAsync(gw, 0, wn * sizeof(float), st));
+    skinny_cfew_wgrad_kernel<<<dim3(blocks, (g.Csrc + 31) / 32), 256, 0, st>>>(g, x, gy, gw, per);
+    CN_CHECK_LAUNCH();
+  } else if (g.Ktot <= 32 && g.Cn <= 64 && g.M >= 4096) {
+    int warps = 16 * num_sms();
+    int per = (g.M + warps - 1) / warps;
+    int blocks = ((g.M + per - 1) / per + 7) / 8;
+    CN_CHECK_CUDA(cudaMemsetAsync(gw, 0, wn * sizeof(float), st));
+    skinny_kfew_wgrad_kernel<<<blocks, 256, 0, st>>>(g, x, gy, gw, per);
+    CN_CHECK_LAUNCH();
   } else if ((long long)g.Ktot * g.Cn <= 256 * SKW_MAXOUT && g.M >= 4096) {
     int P = 8192 / (g.Ktot + g.Cn); if (P > 64) P = 64; if (P < 4) P = 4;
     int smem = P * (g.Ktot + g.Cn) * (int)sizeof(float);
