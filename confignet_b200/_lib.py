@@ -20,18 +20,20 @@ class ConvDesc(ctypes.Structure):
     """cn_conv_desc (include/confignet_b200.h)."""
     _fields_ = [("nd", ctypes.c_int), ("batch", ctypes.c_int), ("in_dims", ctypes.c_int * 3),
                 ("cin", ctypes.c_int), ("cout", ctypes.c_int), ("ksize", ctypes.c_int * 3),
-                ("stride", ctypes.c_int), ("upsample", ctypes.c_int)]
+                ("stride", ctypes.c_int), ("upsample", ctypes.c_int), ("pad", ctypes.c_int)]
 
     def key(self):
-        return (self.nd, self.batch, tuple(self.in_dims), self.cin, self.cout, tuple(self.ksize),
-                self.stride, self.upsample)
+        k = (self.nd, self.batch, tuple(self.in_dims), self.cin, self.cout, tuple(self.ksize),
+             self.stride, self.upsample)
+        return k if self.pad < 0 else k + (self.pad,)
 
 
-def make_conv_desc(nd, batch, in_dims, cin, cout, ksize, stride=1, upsample=1):
+def make_conv_desc(nd, batch, in_dims, cin, cout, ksize, stride=1, upsample=1, pad=-1):
+    """pad = -1: TF "SAME"; pad >= 0: ZeroPadding(pad) + "VALID" (ResNet50 stem)."""
     in_dims = list(in_dims) + [1] * (3 - len(in_dims))
     ksize = list(ksize) + [1] * (3 - len(ksize))
     return ConvDesc(nd, batch, (ctypes.c_int * 3)(*in_dims), cin, cout, (ctypes.c_int * 3)(*ksize),
-                    stride, upsample)
+                    stride, upsample, pad)
 
 
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
@@ -68,6 +70,19 @@ SIGNATURES = {
     "cn_adam_ema_step": [_V, _V, _V, _V, _V, _L, _f, _f, _f, _f, _f, _f, _V],
     "cn_ema": [_V, _V, _L, _f, _V],
     "cn_multi_copy": [_I, _V, _V, _V, _V, _V],
+    "cn_bn_fold": [_V, _V, _V, _V, _f, _I, _V, _V, _V],
+    "cn_bn_act_fwd": [_V, _V, _V, _V, _I, _V, _L, _I, _V],
+    "cn_bn_act_bwd": [_V, _V, _V, _V, _V, _V, _f, _I, _V, _V, _V, _V, _L, _I, _V],
+    "cn_maxpool3s2_fwd": [_V, _I, _I, _I, _I, _V, _V],
+    "cn_maxpool3s2_bwd": [_V, _V, _V, _I, _I, _I, _I, _V, _V],
+    "cn_avgpool_fwd": [_V, _I, _I, _I, _V, _V],
+    "cn_avgpool_bwd": [_V, _I, _I, _I, _V, _V],
+    "cn_col_scale": [_V, _V, _I, _I, _V, _V],
+    "cn_euler_fwd": [_V, _I, _V, _V],
+    "cn_euler_bwd": [_V, _V, _I, _V, _V],
+    "cn_rotate3d_bwd_rot": [_V, _V, _V, _I, _I, _I, _V, _V],
+    "cn_norm_latent_loss_fwd": [_V, _V, _I, _I, _I, _f, _V, _V],
+    "cn_norm_latent_loss_bwd": [_V, _V, _I, _I, _I, _f, _V, _V, _V, _V],
 }
 NO_STATUS = {"cn_last_error": ctypes.c_char_p, "cn_version": ctypes.c_int, "cn_reduce_ws_floats": ctypes.c_int,
              "cn_launch_count": ctypes.c_longlong, "cn_last_conv_impl": ctypes.c_int}

@@ -266,7 +266,10 @@ class ConfigNetFirstStage:
 
     def save(self, output_dir, output_filename):
         """confignet_first_stage.py:173-180: <name>.npz (lists of arrays), <name>.json, _facemodel_distr.pck."""
-        weights = {k: np.array(v, dtype=object) for k, v in self.get_weights().items()}
+        weights = {}
+        for k, v in self.get_weights().items():
+            weights[k] = np.empty(len(v), dtype=object)
+            weights[k][:] = v
         np.savez(os.path.join(output_dir, output_filename + ".npz"), **weights)
         with open(os.path.join(output_dir, output_filename + ".json"), "w") as fp:
             json.dump(self.config, fp, indent=4)

@@ -1,0 +1,317 @@
+"""ConfigNet (second stage) on B200: the class surface of the reference
+(confignet/confignet_second_stage.py:19-403) over our CUDA networks.
+
+Adds to ConfigNetFirstStage: the RealEncoder (keras-applications ResNet50 + two Dense heads,
+dnn_models/real_encoder.py:9-34), the second-stage latent-discriminator / generator steps (:132-218) with the
+batch-normalised latent regression loss (:93-107), ``encode_images`` (:301-308), ``generate_images`` with the
+fine-tuned generator (:310-319) and ``fine_tune_on_img`` (:321-403) with its VGGFace (VGG16) perceptual term.
+
+Out of scope: image / metric checkpoints, ControllabilityMetrics, TensorBoard.
+"""
+import os
+import time
+from collections import OrderedDict
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import netspec, networks, ops
+from .confignet_first_stage import (ConfigNetFirstStage, DEFAULT_CONFIG, merge_configs, update_loss_dict, GeneratorNet)
+from .runtime import ParamGroup, Network, KerasAdam, allreduce_grads, shard_rows, world, gather_rows
+
+PREDICT_BATCH = 32       # keras Model.predict default batch size [TF-2.1]
+
+
+class RealEncoderNet(Network):
+    """RealEncoder (real_encoder.py:9-34): ``enc(imgs) -> (embedding, rotation)``; imgs float32 in [-1, 1]."""
+
+    def __init__(self, group, rotation_ranges):
+        self.rotation_range_multiplier = np.pi * np.array(
+            [rotation_ranges[0][1], rotation_ranges[1][1], rotation_ranges[2][1]], np.float64) / 180.0
+        mult = torch.tensor(self.rotation_range_multiplier, dtype=torch.float32, device=group.device)
+        super().__init__(group, networks.real_encoder_forward, rotation_range_multiplier=mult)
+
+    def __call__(self, imgs):
+        return super().__call__(networks._as_dev(imgs, self.group.device))
+
+    def predict(self, imgs):
+        """keras Model.predict: forward in batches of 32 without a tape -> (embeddings, rotations) device tensors."""
+        embs, rots = [], []
+        with torch.no_grad():
+            for i in range(0, imgs.shape[0], PREDICT_BATCH):
+                e, r = self(imgs[i:i + PREDICT_BATCH])
+                embs.append(e); rots.append(r)
+        if not embs:
+            dev = self.group.device
+            return torch.zeros((0, self.group.params["feature_to_latent_mlp/bias"].shape[0]), device=dev), torch.zeros((0, 3), device=dev)
+        return torch.cat(embs, dim=0), torch.cat(rots, dim=0)
+
+
+class ConfigNet(ConfigNetFirstStage):
+    def __init__(self, config, initialize=True, device=None, seed=1234):
+        self.config = merge_configs(DEFAULT_CONFIG, config)
+        super().__init__(self.config, initialize=False, device=device, seed=seed)
+        self.config["model_type"] = "ConfigNet"
+        self.encoder = None
+        self.generator_fine_tuned = None
+        self.controllability_metrics = None
+        self.perceptual_loss_face_reco = None
+        if initialize:
+            self.initialize_network()
+
+    # ---------------------------------------------------------------- construction / weights
+    def initialize_network(self):
+        """confignet_second_stage.py:45-49 (+ :29, the VGGFace perceptual model)."""
+        super().initialize_network()
+        c, s = self.config, self._seed
+        enc = ParamGroup(netspec.init_real_encoder_params(c["latent_dim"], s + 8), self.device, trainable=netspec.is_trainable)
+        self.encoder = RealEncoderNet(enc, c["rotation_ranges"])
+        # VGG16 with the VGGFace weights (perceptual_loss.py:26-41): not downloadable offline, seeded stand-in
+        self.perceptual_loss_face_reco = Network(self._make_group(netspec.vgg16_spec(), s + 9, vgg_like=True),
+                                                 networks.vggface_activations)
+        for v in self.perceptual_loss_face_reco.group.params.values():
+            v.requires_grad_(False)
+
+    def get_weights(self, return_tensors=False):
+        w = super().get_weights()
+        w["real_encoder_weights"] = self.encoder.get_weights()
+        return w
+
+    def set_weights(self, weights):
+        super().set_weights(weights)
+        self.encoder.set_weights(weights["real_encoder_weights"])
+
+    # ---------------------------------------------------------------- batch assembly (reference RNG draw order)
+    def _draw_image_rows(self, dataset, batch_size):
+        """sample_random_batch_of_images (confignet_second_stage.py:109-117): index draw, then the flip draw."""
+        idxs = np.random.randint(0, dataset.imgs.shape[0], batch_size)
+        flips = np.random.randint(0, 2, size=batch_size)
+        return idxs, flips
+
+    def sample_random_batch_of_images(self, dataset, batch_size=None):
+        if batch_size is None:
+            batch_size = self.get_batch_size()
+        idxs, flips = self._draw_image_rows(dataset, batch_size)
+        idxs, flips = self._rank_rows(idxs, flips)
+        return self._upload_images(self._take_rows(dataset.imgs, idxs), flips)
+
+    def get_discriminator_batch(self, training_set):
+        """confignet_second_stage.py:119-130: fakes are reconstructions of encoded training images."""
+        B = self.get_batch_size()
+        idxs, flips = self._draw_image_rows(training_set, B)
+        input_img_idxs = np.random.randint(0, training_set.imgs.shape[0], B)
+        idxs, flips, input_img_idxs = self._rank_rows(idxs, flips, input_img_idxs)
+        real_imgs = self._upload_images(self._take_rows(training_set.imgs, idxs), flips)
+        input_imgs = self._upload_images(self._take_rows(training_set.imgs, input_img_idxs))
+        with torch.no_grad():
+            latent_vector, rotation = self.encoder(input_imgs)
+            fake_imgs = self.generator([latent_vector, rotation])
+        return real_imgs, fake_imgs
+
+    # ---------------------------------------------------------------- training steps
+    def latent_discriminator_training_step(self, real_training_set, synth_training_set, optimizer):
+        """confignet_second_stage.py:132-147: real latents come from the encoder."""
+        B = self.get_batch_size()
+        idxs, flips = self._draw_image_rows(real_training_set, B)
+        facemodel_params, _ = self._sample_synth_metadata(synth_training_set, B)
+        sliced = self._rank_rows(idxs, flips, *facemodel_params)
+        idxs, flips, facemodel_params = sliced[0], sliced[1], sliced[2:]
+        real_imgs = self._upload_images(self._take_rows(real_training_set.imgs, idxs), flips)
+        with torch.no_grad():
+            real_latents, _ = self.encoder(real_imgs)
+            fake_latents = self.synthetic_encoder([self._to_device(a, torch.float32) for a in facemodel_params])
+        losses = networks.compute_latent_discriminator_loss(self.latent_discriminator.params, real_latents, fake_latents,
+                                                            self.config["n_latent_discr_layers"])
+        self._apply(optimizer, losses["loss_sum"], [self.latent_discriminator])
+        return self._detached(losses)
+
+    def compute_normalized_latent_regression_loss(self, generator_outputs, labels):
+        """confignet_second_stage.py:93-107.  The statistics are over the GLOBAL batch: with data parallelism the
+        regressor outputs and labels are all-gathered (B x 148 floats) before the loss kernel."""
+        c = self.config
+        out = networks.latent_regressor_forward(self.latent_regressor.params, generator_outputs, c["n_discr_layers"])
+        return ops.norm_latent_loss(gather_rows(out), gather_rows(labels), float(c["latent_regression_weight"]), 3)
+
+    def generator_training_step(self, real_training_set, synth_training_set, optimizer):
+        """confignet_second_stage.py:149-218."""
+        c = self.config
+        n_synth = self.get_batch_size() // 2
+        n_real = self.get_batch_size() - n_synth
+        idxs = np.random.randint(0, synth_training_set.imgs.shape[0], n_synth)     # sample_synthetic_dataset's draw
+        facemodel_params = [synth_training_set.metadata_inputs[n][idxs] for n in c["facemodel_inputs"].keys()]
+        synth_rot = synth_training_set.metadata_inputs["rotations"][idxs].astype(np.float32)
+        ridxs, rflips = self._draw_image_rows(real_training_set, n_real)
+        sliced = self._rank_rows(idxs, synth_rot, *facemodel_params)
+        idxs, synth_rot, facemodel_params = sliced[0], sliced[1], sliced[2:]
+        ridxs, rflips = self._rank_rows(ridxs, rflips)
+        synth_imgs = self._upload_images(self._take_rows(synth_training_set.imgs, idxs))
+        eye_masks = self._to_device(self._take_rows(synth_training_set.eye_masks, idxs), torch.float32)
+        real_imgs = self._upload_images(self._take_rows(real_training_set.imgs, ridxs), rflips)
+
+        losses = OrderedDict()
+        synth_latents = self.synthetic_encoder([self._to_device(a, torch.float32) for a in facemodel_params])
+        out_synth = self.generator((synth_latents, synth_rot))
+        real_latents, real_rot = self.encoder(real_imgs)
+        out_real = self.generator((real_latents, real_rot))
+        p_vgg = self.perceptual_loss.params
+        losses["image_loss_synth"] = c["image_loss_weight"] * networks.perceptual_loss(p_vgg, synth_imgs, out_synth)
+        losses["image_loss_real"] = c["image_loss_weight"] * networks.perceptual_loss(p_vgg, real_imgs, out_real)
+        losses["eye_loss"] = c["eye_loss_weight"] * networks.eye_loss(synth_imgs, out_synth, eye_masks)
+        for i, o in enumerate(self.synth_discriminator(out_synth).values()):
+            losses["GAN_loss_synth_" + str(i)] = networks.gan_g_loss(o)
+        for i, o in enumerate(self.discriminator(out_real).values()):
+            losses["GAN_loss_real_" + str(i)] = networks.gan_g_loss(o)
+        # domain-adversarial loss: labels 0 for the real latents, 1 for the synthetic ones (:157-161,192-199)
+        ld_synth = self.latent_discriminator(synth_latents)
+        ld_real = self.latent_discriminator(real_latents)
+        losses["latent_GAN_loss"] = c["domain_adverserial_loss_weight"] * networks.gan_d_loss_mixed(ld_real, ld_synth)
+        if c["latent_regression_weight"] > 0.0:
+            stacked_latents = torch.cat((synth_latents, real_latents), dim=0)
+            stacked_imgs = torch.cat((out_synth, out_real), dim=0)
+            stacked_rot = torch.cat((self._to_device(synth_rot, torch.float32), real_rot), dim=0)
+            labels = torch.cat((stacked_latents, c["latent_regressor_rot_weight"] * stacked_rot), dim=-1)
+            losses["latent_regression_loss"] = self.compute_normalized_latent_regression_loss(stacked_imgs, labels)
+        losses["loss_sum"] = networks._sum(losses.values())
+        self._apply(optimizer, losses["loss_sum"],
+                    [self.generator, self.latent_regressor, self.synthetic_encoder, self.encoder])
+        return self._detached(losses)
+
+    def setup_training(self, log_dir, synth_training_set, n_samples_for_metrics, attribute_classifier=None,
+                       real_training_set=None, validation_set=None):
+        super().setup_training(log_dir, synth_training_set, n_samples_for_metrics, real_training_set)
+
+    def train(self, real_training_set, synth_training_set, validation_set=None, attribute_classifier=None,
+              output_dir=None, log_dir=None, n_steps=100000, n_samples_for_metrics=1000, aml_run=None):
+        """confignet_second_stage.py:268-299 (loop structure and loss history; checkpoints out of scope)."""
+        self.setup_training(log_dir, synth_training_set, n_samples_for_metrics, attribute_classifier,
+                            real_training_set=real_training_set, validation_set=validation_set)
+        start_step = self.get_training_step_number()
+        discriminator_optimizer = KerasAdam(**self.config["optimizer"])
+        generator_optimizer = KerasAdam(**self.config["optimizer"])
+        for _ in range(start_step, n_steps):
+            t0 = time.perf_counter()
+            for _ in range(self.config["n_discriminator_updates"]):
+                d_loss = self.discriminator_training_step(real_training_set, discriminator_optimizer)
+                synth_d_loss = self.synth_discriminator_training_step(synth_training_set, discriminator_optimizer)
+                latent_d_loss = self.latent_discriminator_training_step(real_training_set, synth_training_set, discriminator_optimizer)
+            for _ in range(self.config["n_generator_updates"]):
+                g_loss = self.generator_training_step(real_training_set, synth_training_set, generator_optimizer)
+            self.update_smoothed_weights()
+            print("[D loss: %f] [synth_D loss: %f] [latent_D_loss: %f] [G loss: %f]" %
+                  (d_loss["loss_sum"], synth_d_loss["loss_sum"], latent_d_loss["loss_sum"], g_loss["loss_sum"]))
+            update_loss_dict(self.g_losses, g_loss)
+            update_loss_dict(self.d_losses, d_loss)
+            update_loss_dict(self.synth_d_losses, synth_d_loss)
+            update_loss_dict(self.latent_d_losses, latent_d_loss)
+            self.last_iteration_time = time.perf_counter() - t0
+
+    # ---------------------------------------------------------------- evaluation
+    def _images_to_device(self, input_images):
+        """uint8 -> /127.5 - 1 on the device; float images are taken as already in [-1, 1]."""
+        if isinstance(input_images, np.ndarray) and input_images.dtype == np.uint8:
+            return self._upload_images(input_images)
+        if isinstance(input_images, torch.Tensor) and input_images.dtype == torch.uint8:
+            return ops.from_uint8(input_images.to(self.device))
+        return self._to_device(np.asarray(input_images, np.float32) if not isinstance(input_images, torch.Tensor) else input_images,
+                               torch.float32)
+
+    def encode_images(self, input_images):
+        """confignet_second_stage.py:301-308 -> (embeddings (B, latent) f32, rotations (B, 3) f32) NumPy."""
+        embs, rots = [], []
+        for i in range(0, input_images.shape[0], PREDICT_BATCH):
+            e, r = self.encoder.predict(self._images_to_device(input_images[i:i + PREDICT_BATCH]))
+            embs.append(e); rots.append(r)
+        if not embs:
+            return np.zeros((0, self.config["latent_dim"]), np.float32), np.zeros((0, 3), np.float32)
+        return torch.cat(embs, dim=0).cpu().numpy(), torch.cat(rots, dim=0).cpu().numpy()
+
+    def generate_images(self, latent_vectors, rotations):
+        """confignet_second_stage.py:310-319 -> uint8 (B,H,W,3)."""
+        d = self.generator.build_input_dict(latent_vectors, rotations)
+        net = self.generator_fine_tuned if self.generator_fine_tuned is not None else self.generator_smoothed
+        return ops.to_uint8(net.predict(d)).cpu().numpy()
+
+    def fine_tune_on_img(self, input_images, n_iters=50, img_output_dir=None, force_neutral_expression=False):
+        """confignet_second_stage.py:321-403.  One shared fine-tuned generator and shared pre/post-expression
+        embeddings, per-image expression embeddings and rotations; Keras Adam(lr=1e-4) defaults.  With data
+        parallelism the images are sharded by rows: generator and pre/post gradients are all-reduced, the per-image
+        variables stay rank-local."""
+        c = self.config
+        if isinstance(input_images, np.ndarray) and input_images.ndim == 3:
+            input_images = input_images[np.newaxis]
+        rank, ws = world()
+        n_global = input_images.shape[0]
+        if ws > 1:
+            lo, hi = shard_rows(n_global)
+            input_images = input_images[lo:hi]
+        imgs = self._images_to_device(input_images)
+        n_imgs = imgs.shape[0]
+        pred_emb, pred_rot = self.encoder.predict(imgs)
+        pred_emb, pred_rot = pred_emb.cpu().numpy(), pred_rot.cpu().numpy()
+        if force_neutral_expression:
+            n_exp = c["facemodel_inputs"]["blendshape_values"][0]
+            pred_emb = self.set_facemodel_param_in_latents(pred_emb, "blendshape_values", np.zeros((1, n_exp), np.float32))
+
+        if self.generator_fine_tuned is None:
+            gspec = netspec.generator_spec(c["latent_dim"], c["output_shape"][0], c["n_adain_mlp_units"], c["n_adain_mlp_layers"])
+            self.generator_fine_tuned = GeneratorNet(self._make_group(gspec, self._seed + 6), networks.generator_forward,
+                                                     output_res=c["output_shape"][0], n_mlp_layers=c["n_adain_mlp_layers"])
+        self.generator_fine_tuned.group.copy_from(self.generator_smoothed.group)
+
+        expr_idxs = self.get_facemodel_param_idxs_in_latent("blendshape_values")
+        mean_emb = np.sum(pred_emb, axis=0, keepdims=True, dtype=np.float32)
+        if ws > 1:
+            t = torch.from_numpy(mean_emb).to(self.device)
+            dist.all_reduce(t)
+            mean_emb = t.cpu().numpy()
+        mean_emb = mean_emb / np.float32(n_global)
+        shared = ParamGroup(OrderedDict([("pre_expr_embeddings", mean_emb[:, :expr_idxs[0]]),
+                                         ("post_expr_embeddings", mean_emb[:, expr_idxs[-1] + 1:])]), self.device)
+        local_arrays = OrderedDict([("rotations", pred_rot), ("expr_embeddings", pred_emb[:, list(expr_idxs)])])
+        local = ParamGroup(local_arrays, self.device,
+                           trainable=(lambda k: k != "expr_embeddings") if force_neutral_expression else None)
+        pre, post = shared.params["pre_expr_embeddings"], shared.params["post_expr_embeddings"]
+        expr, rotations = local.params["expr_embeddings"], local.params["rotations"]
+        optimizer = KerasAdam(lr=0.0001, beta_1=0.9, beta_2=0.999)
+        gen = self.generator_fine_tuned
+        if img_output_dir is not None and rank == 0:
+            os.makedirs(img_output_dir, exist_ok=True)
+        self.fine_tune_losses = []
+
+        for step_number in range(n_iters):
+            losses = OrderedDict()
+            embeddings = torch.cat((pre.expand(n_imgs, -1), expr, post.expand(n_imgs, -1)), dim=1)
+            out = gen((embeddings, rotations))
+            losses["image_loss_real"] = 0.5 * c["image_loss_weight"] * networks.perceptual_loss(self.perceptual_loss.params, imgs, out)
+            losses["face_reco_loss"] = 0.5 * c["image_loss_weight"] * networks.perceptual_loss(
+                self.perceptual_loss_face_reco.params, out, imgs, model_type="VGGFace")
+            for i, o in enumerate(self.discriminator(out).values()):
+                losses["GAN_loss_real_" + str(i)] = networks.gan_g_loss(o)
+            losses["latent_GAN_loss"] = c["domain_adverserial_loss_weight"] * networks.gan_d_loss(1, self.latent_discriminator(embeddings))
+            labels = torch.cat((embeddings, c["latent_regressor_rot_weight"] * rotations), dim=-1)
+            losses["latent_regression_loss"] = self.compute_normalized_latent_regression_loss(out, labels)
+            losses["loss_sum"] = networks._sum(losses.values())
+
+            groups = [gen.group, shared, local]
+            params = [p for g in groups for p in g.trainable_weights]
+            grads = torch.autograd.grad(losses["loss_sum"], params, allow_unused=True)
+            keep, i = [], 0
+            for g in groups:
+                k = len(g.trainable_weights)
+                keep.append(g.pack_grads(grads[i:i + k]))
+                i += k
+            gscale = allreduce_grads([gen.group, shared])
+            optimizer.apply_flat(groups, gscale)
+            self.fine_tune_losses.append(self._detached(losses))
+            if img_output_dir is not None and rank == 0:
+                np.save(os.path.join(img_output_dir, "output_%02d.npy" % step_number), ops.to_uint8(out.detach()[:1]).cpu().numpy()[0])
+
+        with torch.no_grad():
+            embeddings = torch.cat((pre.expand(n_imgs, -1), expr, post.expand(n_imgs, -1)), dim=1)
+            emb_out, rot_out = embeddings.contiguous(), rotations.detach().contiguous()
+            if ws > 1:
+                eparts = [torch.empty_like(emb_out) for _ in range(ws)]
+                rparts = [torch.empty_like(rot_out) for _ in range(ws)]
+                dist.all_gather(eparts, emb_out); dist.all_gather(rparts, rot_out)
+                emb_out, rot_out = torch.cat(eparts, dim=0), torch.cat(rparts, dim=0)
+        return emb_out.cpu().numpy(), rot_out.cpu().numpy()

@@ -41,6 +41,11 @@ static void same_geometry(const cn_conv_desc* d, int U[3], int O[3], int pb[3]) 
   for (int i = 0; i < 3; ++i) {
     if (i < d->nd) {
       U[i] = d->in_dims[i] * d->upsample;
+      if (d->pad >= 0) {               // ZeroPadding(pad) + VALID
+        O[i] = (U[i] + 2 * d->pad - d->ksize[i]) / d->stride + 1;
+        pb[i] = d->pad;
+        continue;
+      }
       O[i] = (U[i] + d->stride - 1) / d->stride;
       int tot = (O[i] - 1) * d->stride + d->ksize[i] - U[i];
       if (tot < 0) tot = 0;
@@ -58,6 +63,9 @@ static int validate_desc(const cn_conv_desc* d) {
   CN_REQUIRE(d->stride == 1 || d->stride == 2, CN_ERR_UNSUPPORTED, "stride must be 1 or 2");
   CN_REQUIRE(d->upsample == 1 || d->upsample == 2, CN_ERR_UNSUPPORTED, "upsample must be 1 or 2");
   CN_REQUIRE(!(d->stride == 2 && d->upsample == 2), CN_ERR_UNSUPPORTED, "stride 2 with fused upsample is unsupported");
+  CN_REQUIRE(d->pad >= -1 && d->pad <= 7, CN_ERR_BAD_SHAPE, "pad must be -1 (SAME) or 0..7");
+  for (int i = 0; i < d->nd; ++i)
+    CN_REQUIRE(d->pad < 0 || d->in_dims[i] * d->upsample + 2 * d->pad >= d->ksize[i], CN_ERR_BAD_SHAPE, "kernel larger than the padded input");
   for (int i = 0; i < 3; ++i) {
     CN_REQUIRE(d->in_dims[i] >= 1 && d->ksize[i] >= 1 && d->ksize[i] <= 7, CN_ERR_BAD_SHAPE, "bad dims/ksize");
     if (i >= d->nd) CN_REQUIRE(d->in_dims[i] == 1 && d->ksize[i] == 1, CN_ERR_BAD_SHAPE, "unused dims must be 1");

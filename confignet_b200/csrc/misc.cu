@@ -270,21 +270,29 @@ extern "C" int cn_from_uint8(const uint8_t* x, float* out, int64_t n, void* stre
   CN_CHECK_LAUNCH(); return CN_OK;
 }
 // (x+1)*127.5, channel flip, subtract caffe BGR means; backward: gx[..., 2-c] = 127.5 * g[..., c]
-__global__ void vgg_preprocess_kernel(const float* __restrict__ x, float* __restrict__ out, size_t npix, int backward) {
+__global__ void vgg_preprocess_kernel(const float* __restrict__ x, float* __restrict__ out, size_t npix, int mode) {
   const float mean[3] = {103.939f, 116.779f, 123.68f};
+  const float face_mean[3] = {93.5940f, 104.7624f, 129.1863f};
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
     const float* p = x + i * 3; float* o = out + i * 3;
-    if (!backward) {
+    if (mode == 0) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) o[c] = (p[2 - c] + 1.f) * 127.5f - mean[c];
-    } else {
+    } else if (mode == 1) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) o[2 - c] = 127.5f * p[c];
+    } else if (mode == 2) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[c] = (p[c] + 1.f) * 127.5f - face_mean[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[c] = 127.5f * p[c];
     }
   }
 }
 extern "C" int cn_vgg_preprocess(const float* x, float* out, int64_t npix, int backward, void* stream) {
   if (npix <= 0) return CN_OK;
+  CN_REQUIRE(backward >= 0 && backward <= 3, CN_ERR_BAD_SHAPE, "cn_vgg_preprocess: mode must be 0..3");
   vgg_preprocess_kernel<<<grid_for(npix), 256, 0, (cudaStream_t)stream>>>(x, out, (size_t)npix, backward);
   CN_CHECK_LAUNCH(); return CN_OK;
 }

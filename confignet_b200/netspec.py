@@ -163,12 +163,18 @@ def init_params(spec, seed, vgg_like=False):
     """Seeded NumPy initialisation: Glorot-uniform kernels (Keras default), zero biases.
 
     ``vgg_like`` draws He-normal kernels and small positive biases so a random (non-pretrained)
-    VGG keeps activations alive through ReLUs; pretrained weights are unavailable offline.
+    VGG / ResNet keeps activations alive through ReLUs; pretrained weights are unavailable offline.
+    Names ending in moving_variance / moving_mean get mildly random positive / zero-centred values in
+    ``vgg_like`` mode so the inference BatchNorm is exercised with non-trivial statistics.
     """
     rng = np.random.RandomState(seed)
     out = OrderedDict()
     for name, (shape, kind) in spec.items():
-        if kind == "zeros":
+        if vgg_like and name.endswith("/moving_variance"):
+            a = rng.uniform(0.5, 1.5, shape).astype(np.float32)
+        elif vgg_like and name.endswith("/moving_mean"):
+            a = (0.1 * rng.standard_normal(shape)).astype(np.float32)
+        elif kind == "zeros":
             a = np.zeros(shape, np.float32)
         elif kind == "ones":
             a = np.ones(shape, np.float32)
@@ -193,3 +199,96 @@ def perturb_params(params, seed, scale=0.05):
     for k, v in params.items():
         out[k] = (v + scale * rng.standard_normal(v.shape)).astype(np.float32)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# second stage: RealEncoder = keras-applications ResNet50 (include_top=False, pooling="avg") + two Dense heads
+# (dnn_models/real_encoder.py:9-34); VGG16 (VGGFace weights) for the fine-tuning perceptual loss
+# (perceptual_loss.py:26-41); LatentGAN MLPs (latent_gan.py:88-109)
+# ------------------------------------------------------------------------------------------------
+RESNET50_STAGES = [(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)]     # (filters, blocks, stride of the first block)
+
+
+def _bn(spec, prefix, c):
+    spec[prefix + "/gamma"] = ((c,), "ones")
+    spec[prefix + "/beta"] = ((c,), "zeros")
+    spec[prefix + "/moving_mean"] = ((c,), "zeros")
+    spec[prefix + "/moving_variance"] = ((c,), "ones")
+
+
+def resnet50_spec():
+    """Layer order as keras lists it for ResNet50 v1 (conv / bn pairs; inside a block: 1, 2, then the shortcut
+    '0' next to '3').  Like the other tables this order is unverifiable offline and isolated here."""
+    s = OrderedDict()
+    _conv(s, "conv1_conv", (7, 7), 3, 64)
+    _bn(s, "conv1_bn", 64)
+    c_in = 64
+    for si, (f, blocks, _) in enumerate(RESNET50_STAGES, start=2):
+        for b in range(1, blocks + 1):
+            p = "conv%d_block%d" % (si, b)
+            _conv(s, p + "_1_conv", (1, 1), c_in, f); _bn(s, p + "_1_bn", f)
+            _conv(s, p + "_2_conv", (3, 3), f, f); _bn(s, p + "_2_bn", f)
+            if b == 1:
+                _conv(s, p + "_0_conv", (1, 1), c_in, 4 * f)
+            _conv(s, p + "_3_conv", (1, 1), f, 4 * f)
+            if b == 1:
+                _bn(s, p + "_0_bn", 4 * f)
+            _bn(s, p + "_3_bn", 4 * f)
+            c_in = 4 * f
+    return s
+
+
+def real_encoder_spec(latent_dim=145):
+    s = OrderedDict()
+    for k, v in resnet50_spec().items():
+        s["resnet/" + k] = v
+    _dense(s, "rotation_regressor", 2048, 3)
+    _dense(s, "feature_to_latent_mlp", 2048, latent_dim)
+    return s
+
+
+def is_trainable(name):
+    """keras: BatchNormalization moving statistics are non-trainable weights."""
+    return not (name.endswith("/moving_mean") or name.endswith("/moving_variance"))
+
+
+# Keras VGG16 layers up to block4_conv2 (layer idx 12; InputLayer is idx 0)
+VGG16_LAYERS = [
+    ("conv", "block1_conv1", 3, 64), ("conv", "block1_conv2", 64, 64), ("pool", "block1_pool"),
+    ("conv", "block2_conv1", 64, 128), ("conv", "block2_conv2", 128, 128), ("pool", "block2_pool"),
+    ("conv", "block3_conv1", 128, 256), ("conv", "block3_conv2", 256, 256), ("conv", "block3_conv3", 256, 256),
+    ("pool", "block3_pool"),
+    ("conv", "block4_conv1", 256, 512), ("conv", "block4_conv2", 512, 512),
+]
+VGG16_USED_LAYER_IDXS = [1, 2, 8, 12]   # perceptual_loss.py:35
+
+
+def vgg16_spec():
+    s = OrderedDict()
+    for l in VGG16_LAYERS:
+        if l[0] == "conv":
+            _conv(s, l[1], (3, 3), l[2], l[3])
+    return s
+
+
+def latent_gan_mlp_spec(latent_dim, num_layers=3, hidden_multiplier=1.5, num_out=None):
+    """MLPSimple(num_layers, latent_dim, int(latent_dim*multiplier), num_out) (latent_gan.py:88-109)."""
+    s = OrderedDict()
+    _mlp(s, "mlp", num_layers, latent_dim, int(latent_dim * hidden_multiplier), latent_dim if num_out is None else num_out)
+    return s
+
+
+def init_real_encoder_params(latent_dim, seed):
+    """Random stand-in for the ImageNet ResNet50 + freshly initialised heads (pretrained weights are unavailable
+    offline): He-normal kernels damped on the residual branches so activations neither die nor explode over the
+    16 blocks, non-trivial moving statistics, small head kernels so the tanh rotation head is not saturated."""
+    p = init_params(real_encoder_spec(latent_dim), seed, vgg_like=True)
+    for k in p:
+        if k.endswith("_3_conv/kernel"):
+            p[k] = (p[k] * 0.25).astype(np.float32)
+        elif k.endswith("conv1_conv/kernel"):
+            p[k] = (p[k] * 0.01).astype(np.float32)          # 'caffe' inputs are O(100)
+        elif k.endswith("_conv/kernel"):
+            p[k] = (p[k] * 0.8).astype(np.float32)
+    p["rotation_regressor/kernel"] = (p["rotation_regressor/kernel"] * 0.5).astype(np.float32)
+    return p

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 from . import ops
 from . import _lib as L
-from .netspec import VGG19_LAYERS, VGG19_USED_LAYER_IDXS
+from .netspec import (VGG19_LAYERS, VGG19_USED_LAYER_IDXS, VGG16_LAYERS, VGG16_USED_LAYER_IDXS, RESNET50_STAGES)
 
 
 # ------------------------------------------------------------------------------------------------ host helpers
@@ -74,8 +74,12 @@ def generator_forward(p, z, rotation, output_res=256, zs=None, n_mlp_layers=2):
         zs = [z] * 5
     dev = zs[0].device
     B = zs[0].shape[0]
-    rot = rotation.detach().cpu().numpy() if isinstance(rotation, torch.Tensor) else rotation
-    R = torch.from_numpy(euler_angles_to_matrix_np(rot)).to(dev)
+    if isinstance(rotation, torch.Tensor) and rotation.is_cuda:
+        # predicted / optimised rotations (confignet_second_stage.py:169-170,348): differentiable, on the device
+        R = ops.euler_to_matrix(rotation.reshape(-1, 3).to(torch.float32))
+    else:
+        rot = rotation.detach().cpu().numpy() if isinstance(rotation, torch.Tensor) else rotation
+        R = torch.from_numpy(euler_angles_to_matrix_np(rot)).to(dev)
     # Dense(1 -> 32768) applied to zeros (hologan_generator.py:24-27,133-136): the bias, broadcast
     x = p["learned_input/bias"].reshape(1, 4, 4, 4, 512).expand(B, 4, 4, 4, 512)
     x = conv_adain(x, zs[0], p, "map_3d_0", 2, n_mlp_layers)
@@ -144,28 +148,39 @@ def latent_discriminator_forward(p, z, n_layers=4):
 
 
 # ------------------------------------------------------------------------------------------------ perceptual loss
-def vgg19_activations(p, img):
-    """Activations of Keras VGG19 layers [1,2,8,13] for images in [-1,1] (perceptual_loss.py:43-59)."""
-    x = ops.vgg_preprocess(img)
+def _vgg_activations(p, img, layers, used, face):
+    x = ops.vgg_preprocess(img, face=face)
     acts = []
-    for idx, layer in enumerate(VGG19_LAYERS, start=1):
+    for idx, layer in enumerate(layers, start=1):
         if layer[0] == "conv":
             x = ops.conv_act(x, p[layer[1] + "/kernel"], p[layer[1] + "/bias"], act=L.ACT_RELU)
         else:
             x = ops.maxpool2(x)
-        if idx in VGG19_USED_LAYER_IDXS:
+        if idx in used:
             acts.append(x)
     return acts
 
 
-def perceptual_loss(p_vgg, predicted, data):
+def vgg19_activations(p, img):
+    """Activations of Keras VGG19 layers [1,2,8,13] for images in [-1,1] (perceptual_loss.py:43-59)."""
+    return _vgg_activations(p, img, VGG19_LAYERS, VGG19_USED_LAYER_IDXS, False)
+
+
+def vggface_activations(p, img):
+    """Activations of Keras VGG16 layers [1,2,8,12] with the VGGFace preprocessing (perceptual_loss.py:26-41,54-56)."""
+    return _vgg_activations(p, img, VGG16_LAYERS, VGG16_USED_LAYER_IDXS, True)
+
+
+def perceptual_loss(p_vgg, predicted, data, model_type="imagenet"):
     """PerceptualLoss.loss: sum over the 4 layers of the batch-wide MSE.  Gradient flows to both arguments
-    that require it (in ConfigNet only one of them does)."""
+    that require it (in ConfigNet only one of them does).  model_type "imagenet" = VGG19, "VGGFace" = VGG16."""
+    fwd = vgg19_activations if model_type == "imagenet" else vggface_activations
+
     def acts(t):
         if t.requires_grad:
-            return vgg19_activations(p_vgg, t)
+            return fwd(p_vgg, t)
         with torch.no_grad():
-            return vgg19_activations(p_vgg, t)
+            return fwd(p_vgg, t)
     a_p, a_d = acts(predicted), acts(data)
     total = None
     for x, y in zip(a_p, a_d):
@@ -240,3 +255,54 @@ def _sum(vals):
     for v in vals:
         total = v if total is None else total + v
     return total
+
+
+# ------------------------------------------------------------------------------------------------ second stage
+def resnet50_forward(p, x, prefix="resnet/"):
+    """keras-applications ResNet50 (include_top=False, pooling="avg") on 'caffe'-preprocessed images, BatchNorm with
+    its moving statistics (real_encoder.py:13,24-27).  Every conv is a launch of the implicit-GEMM family; BN, the
+    residual add and the ReLU are one fused kernel."""
+    def bn(t, name, residual=None, relu=True):
+        q = prefix + name
+        return ops.bn_act(t, p[q + "/gamma"], p[q + "/beta"], p[q + "/moving_mean"], p[q + "/moving_variance"], residual, relu)
+
+    def conv(t, name, stride=1, pad=-1):
+        q = prefix + name
+        return ops.conv_act(t, p[q + "/kernel"], p[q + "/bias"], stride=stride, pad=pad)
+
+    x = conv(x, "conv1_conv", stride=2, pad=3)          # ZeroPadding2D(3) + 7x7/s2 VALID
+    x = bn(x, "conv1_bn")
+    x = ops.maxpool3s2(x)                               # ZeroPadding2D(1) + 3x3/s2
+    for si, (f, blocks, stride) in enumerate(RESNET50_STAGES, start=2):
+        for b in range(1, blocks + 1):
+            q = "conv%d_block%d" % (si, b)
+            s = stride if b == 1 else 1
+            shortcut = bn(conv(x, q + "_0_conv", stride=s), q + "_0_bn", relu=False) if b == 1 else x
+            y = bn(conv(x, q + "_1_conv", stride=s), q + "_1_bn")
+            y = bn(conv(y, q + "_2_conv"), q + "_2_bn")
+            x = bn(conv(y, q + "_3_conv"), q + "_3_bn", residual=shortcut, relu=True)
+    return ops.global_avg_pool(x)
+
+
+def real_encoder_forward(p, img, rotation_range_multiplier):
+    """RealEncoder.call (real_encoder.py:23-34): img in [-1,1] -> (embedding (B, latent), rotation (B, 3) radians)."""
+    x = ops.vgg_preprocess(img)                          # resnet50.preprocess_input = 'caffe' mode
+    feat = resnet50_forward(p, x)
+    raw = ops.conv_act(feat, p["rotation_regressor/kernel"], p["rotation_regressor/bias"], act=L.ACT_TANH)
+    rotation = ops.col_scale(raw, rotation_range_multiplier)
+    embedding = ops.conv_act(feat, p["feature_to_latent_mlp/kernel"], p["feature_to_latent_mlp/bias"])
+    return embedding, rotation
+
+
+def gan_d_loss_mixed(scores_zero, scores_one):
+    """GAN_D_loss with labels 0 for the first group and 1 for the second (confignet_second_stage.py:163-199):
+    the mean over both groups of softplus(s) resp. softplus(-s)."""
+    n = scores_zero.numel() + scores_one.numel()
+    return (ops.reduce_sum(scores_zero, ops.RED_SOFTPLUS, sign=1.0, scale=1.0 / n) +
+            ops.reduce_sum(scores_one, ops.RED_SOFTPLUS, sign=-1.0, scale=1.0 / n))
+
+
+def normalized_latent_regression_loss(p_lr, imgs, labels, weight, n_layers=5):
+    """compute_normalized_latent_regression_loss (confignet_second_stage.py:93-107)."""
+    out = latent_regressor_forward(p_lr, imgs, n_layers)
+    return ops.norm_latent_loss(out, labels, weight, 3)

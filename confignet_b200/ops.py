@@ -56,8 +56,8 @@ class ConvGeom:
     """Geometry of one Keras Conv2D / Conv3D / Dense layer call (cn_conv_desc + cached shapes)."""
     _cache = {}
 
-    def __init__(self, nd, batch, in_dims, cin, cout, ksize, stride, upsample):
-        self.desc = L.make_conv_desc(nd, batch, in_dims, cin, cout, ksize, stride, upsample)
+    def __init__(self, nd, batch, in_dims, cin, cout, ksize, stride, upsample, pad=-1):
+        self.desc = L.make_conv_desc(nd, batch, in_dims, cin, cout, ksize, stride, upsample, pad)
         self.nd, self.batch, self.cin, self.cout = nd, batch, cin, cout
         self.in_dims, self.ksize = tuple(in_dims), tuple(ksize)
         od = (ctypes.c_int * 3)()
@@ -69,8 +69,8 @@ class ConvGeom:
         self.ref = ctypes.byref(self.desc)
 
     @classmethod
-    def get(cls, x_shape, w_shape, stride=1, upsample=1):
-        key = (tuple(x_shape), tuple(w_shape), stride, upsample)
+    def get(cls, x_shape, w_shape, stride=1, upsample=1, pad=-1):
+        key = (tuple(x_shape), tuple(w_shape), stride, upsample, pad)
         g = cls._cache.get(key)
         if g is None:
             nd = len(w_shape) - 2
@@ -78,7 +78,7 @@ class ConvGeom:
                 raise L.CnError("input rank %d does not match kernel rank %d" % (len(x_shape), len(w_shape)))
             if x_shape[-1] != w_shape[-2]:
                 raise L.CnError("channel mismatch: x %s kernel %s" % (tuple(x_shape), tuple(w_shape)))
-            g = cls(nd, x_shape[0], x_shape[1:-1], w_shape[-2], w_shape[-1], w_shape[:nd], stride, upsample)
+            g = cls(nd, x_shape[0], x_shape[1:-1], w_shape[-2], w_shape[-1], w_shape[:nd], stride, upsample, pad)
             cls._cache[key] = g
         return g
 
@@ -231,8 +231,9 @@ class ConvActFwd(torch.autograd.Function):
         return gx, gw, gb, None, None, None, None
 
 
-def conv_act(x, w, bias=None, stride=1, upsample=1, act=L.ACT_NONE, alpha=0.0, grad_is_preact=False):
-    g = ConvGeom.get(x.shape, w.shape, stride, upsample)
+def conv_act(x, w, bias=None, stride=1, upsample=1, act=L.ACT_NONE, alpha=0.0, grad_is_preact=False, pad=-1):
+    """pad = -1: TF "SAME"; pad >= 0: ZeroPadding(pad) + "VALID" (ResNet50 stem)."""
+    g = ConvGeom.get(x.shape, w.shape, stride, upsample, pad)
     return ConvActFwd.apply(x, w, bias, g, act, alpha, grad_is_preact)
 
 
@@ -483,11 +484,15 @@ def maxpool2(x):
 
 
 class VggPreprocess(torch.autograd.Function):
+    """mode 0: keras 'caffe' preprocessing (VGG19 / ResNet50); mode 2: VGGFace means, no channel flip
+    (perceptual_loss.py:50-59)."""
+
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, mode):
         x = _chk(x)
         out = torch.empty_like(x)
-        L.call("cn_vgg_preprocess", _p(x), _p(out), x.numel() // 3, 0, _stream())
+        ctx.mode = mode
+        L.call("cn_vgg_preprocess", _p(x), _p(out), x.numel() // 3, mode, _stream())
         return out
 
     @staticmethod
@@ -495,16 +500,17 @@ class VggPreprocess(torch.autograd.Function):
     def backward(ctx, g):
         g = _chk(g)
         out = torch.empty_like(g)
-        L.call("cn_vgg_preprocess", _p(g), _p(out), g.numel() // 3, 1, _stream())
-        return out
+        L.call("cn_vgg_preprocess", _p(g), _p(out), g.numel() // 3, ctx.mode + 1, _stream())
+        return out, None
 
 
-def vgg_preprocess(x):
-    return VggPreprocess.apply(x)
+def vgg_preprocess(x, face=False):
+    return VggPreprocess.apply(x, 2 if face else 0)
 
 
 class Rotate3D(torch.autograd.Function):
-    """transform_3d_grid_tf (confignet_utils.py:63-120); gradient wrt the volume only."""
+    """transform_3d_grid_tf (confignet_utils.py:63-120); gradients wrt the volume and, where the rotation is
+    predicted or optimised (confignet_second_stage.py:169-170,348,392), wrt the 3x3 matrix."""
 
     @staticmethod
     def forward(ctx, grid, rot):
@@ -512,19 +518,24 @@ class Rotate3D(torch.autograd.Function):
         b, s, c = grid.shape[0], grid.shape[1], grid.shape[-1]
         out = torch.empty_like(grid)
         L.call("cn_rotate3d_fwd", _p(grid), _p(rot), b, s, c, _p(out), _stream())
-        ctx.save_for_backward(rot)
+        ctx.save_for_backward(rot, grid if ctx.needs_input_grad[1] else None)
         ctx.dims = (b, s, c)
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gout):
-        (rot,) = ctx.saved_tensors
+        rot, grid = ctx.saved_tensors
         gout = _chk(gout)
         b, s, c = ctx.dims
-        gg = torch.zeros_like(gout)
-        L.call("cn_rotate3d_bwd_grid", _p(gout), _p(rot), b, s, c, _p(gg), _stream())
-        return gg, None
+        gg = grot = None
+        if ctx.needs_input_grad[0]:
+            gg = torch.zeros_like(gout)
+            L.call("cn_rotate3d_bwd_grid", _p(gout), _p(rot), b, s, c, _p(gg), _stream())
+        if ctx.needs_input_grad[1]:
+            grot = torch.empty((b, 9), device=gout.device, dtype=torch.float32)
+            L.call("cn_rotate3d_bwd_rot", _p(grid), _p(gout), _p(rot), b, s, c, _p(grot), _stream())
+        return gg, grot
 
 
 def rotate3d(grid, rot):
@@ -598,3 +609,184 @@ def adam_ema_step(p, g, m, v, ema, lr_t, b1, b2, eps, ema_alpha=0.999, gscale=1.
 
 def ema_update(ema, p, alpha):
     L.call("cn_ema", _p(ema), _p(p), p.numel(), alpha, _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# second stage / fine-tuning operators (csrc/stage2.cu)
+# ------------------------------------------------------------------------------------------------
+class EulerToMatrix(torch.autograd.Function):
+    """euler_angles_to_matrix (confignet_utils.py:122-145): (B,3) radians -> (B,9), differentiable."""
+
+    @staticmethod
+    def forward(ctx, angles):
+        angles = _chk(angles)
+        b = angles.shape[0]
+        rot = torch.empty((b, 9), device=angles.device, dtype=torch.float32)
+        L.call("cn_euler_fwd", _p(angles), b, _p(rot), _stream())
+        ctx.save_for_backward(angles)
+        return rot
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grot):
+        (angles,) = ctx.saved_tensors
+        grot = _chk(grot)
+        ga = torch.empty_like(angles)
+        L.call("cn_euler_bwd", _p(angles), _p(grot), angles.shape[0], _p(ga), _stream())
+        return ga
+
+
+def euler_to_matrix(angles):
+    return EulerToMatrix.apply(angles)
+
+
+BN_EPS = 1.001e-5       # keras-applications ResNet50 BatchNormalization epsilon [TF-2.1]
+
+
+class BnAct(torch.autograd.Function):
+    """relu?(BatchNorm_inference(x; gamma, beta, moving_mean, moving_var) + residual): the BN / Add / Activation
+    tail of a ResNet50 block.  gamma and beta are trainable, the moving statistics are constants (keras
+    BatchNormalization called without training=True, real_encoder.py:27)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, mean, var, residual, relu):
+        x, gamma, beta, mean, var, residual = [_chk(t) for t in (x, gamma, beta, mean, var, residual)]
+        c = x.shape[-1]
+        npix = x.numel() // c
+        scale = torch.empty(c, device=x.device, dtype=torch.float32)
+        shift = torch.empty_like(scale)
+        L.call("cn_bn_fold", _p(gamma), _p(beta), _p(mean), _p(var), BN_EPS, c, _p(scale), _p(shift), _stream())
+        out = torch.empty_like(x)
+        L.call("cn_bn_act_fwd", _p(x), _p(scale), _p(shift), _p(residual), int(relu), _p(out), npix, c, _stream())
+        ctx.relu, ctx.has_res = relu, residual is not None
+        ctx.save_for_backward(x, out if relu else None, scale, mean, var)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        x, out, scale, mean, var = ctx.saved_tensors
+        gout = _chk(gout)
+        c = x.shape[-1]
+        npix = x.numel() // c
+        gx = torch.empty_like(x)
+        gres = torch.empty_like(x) if ctx.has_res else None
+        dgamma = torch.empty(c, device=x.device, dtype=torch.float32)
+        dbeta = torch.empty_like(dgamma)
+        L.call("cn_bn_act_bwd", _p(gout), _p(out), _p(x), _p(scale), _p(mean), _p(var), BN_EPS, int(ctx.relu),
+               _p(gx), _p(gres), _p(dgamma), _p(dbeta), npix, c, _stream())
+        if not _want_param_grads():
+            dgamma = dbeta = None
+        return gx, dgamma, dbeta, None, None, gres, None
+
+
+def bn_act(x, gamma, beta, mean, var, residual=None, relu=True):
+    return BnAct.apply(x, gamma, beta, mean, var, residual, relu)
+
+
+class MaxPool3s2(torch.autograd.Function):
+    """ZeroPadding2D(1) + MaxPooling2D(3, strides=2) of the ResNet50 stem."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _chk(x)
+        n, h, w, c = x.shape
+        y = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), device=x.device, dtype=torch.float32)
+        L.call("cn_maxpool3s2_fwd", _p(x), n, h, w, c, _p(y), _stream())
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, y = ctx.saved_tensors
+        gy = _chk(gy)
+        n, h, w, c = x.shape
+        gx = torch.empty_like(x)
+        L.call("cn_maxpool3s2_bwd", _p(x), _p(y), _p(gy), n, h, w, c, _p(gx), _stream())
+        return gx
+
+
+def maxpool3s2(x):
+    return MaxPool3s2.apply(x)
+
+
+class GlobalAvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _chk(x)
+        n, c = x.shape[0], x.shape[-1]
+        p = x.numel() // (n * c)
+        y = torch.empty((n, c), device=x.device, dtype=torch.float32)
+        L.call("cn_avgpool_fwd", _p(x), n, p, c, _p(y), _stream())
+        ctx.shape = tuple(x.shape)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        gy = _chk(gy)
+        shape = ctx.shape
+        n, c = shape[0], shape[-1]
+        gx = torch.empty(shape, device=gy.device, dtype=torch.float32)
+        L.call("cn_avgpool_bwd", _p(gy), n, gx.numel() // (n * c), c, _p(gx), _stream())
+        return gx
+
+
+def global_avg_pool(x):
+    return GlobalAvgPool.apply(x)
+
+
+class ColScale(torch.autograd.Function):
+    """x * scale[column] with a constant scale (rotation_range_multiplier, real_encoder.py:20-21,30)."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        x, scale = _chk(x), _chk(scale)
+        out = torch.empty_like(x)
+        L.call("cn_col_scale", _p(x), _p(scale), x.shape[0], x.shape[1], _p(out), _stream())
+        ctx.save_for_backward(scale)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (scale,) = ctx.saved_tensors
+        g = _chk(g)
+        out = torch.empty_like(g)
+        L.call("cn_col_scale", _p(g), _p(scale), g.shape[0], g.shape[1], _p(out), _stream())
+        return out, None
+
+
+def col_scale(x, scale):
+    return ColScale.apply(x, scale)
+
+
+class NormLatentLoss(torch.autograd.Function):
+    """compute_normalized_latent_regression_loss (confignet_second_stage.py:93-107) on the regressor output and the
+    labels (both (B, latent+3)); gradients flow to both."""
+
+    @staticmethod
+    def forward(ctx, out, labels, weight, nrot):
+        out, labels = _chk(out), _chk(labels)
+        b, j = out.shape
+        res = torch.empty(1, device=out.device, dtype=torch.float32)
+        L.call("cn_norm_latent_loss_fwd", _p(out), _p(labels), b, j, nrot, weight, _p(res), _stream())
+        ctx.save_for_backward(out, labels)
+        ctx.args = (weight, nrot)
+        return res
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        out, labels = ctx.saved_tensors
+        weight, nrot = ctx.args
+        g = _chk(g)
+        b, j = out.shape
+        go, gl = torch.empty_like(out), torch.empty_like(labels)
+        L.call("cn_norm_latent_loss_bwd", _p(out), _p(labels), b, j, nrot, weight, _p(g), _p(go), _p(gl), _stream())
+        return (go if ctx.needs_input_grad[0] else None), (gl if ctx.needs_input_grad[1] else None), None, None
+
+
+def norm_latent_loss(out, labels, weight, nrot=3):
+    return NormLatentLoss.apply(out, labels, weight, nrot)

@@ -20,8 +20,10 @@ from . import ops
 
 
 class ParamGroup:
-    def __init__(self, spec_or_arrays, device, init=None):
-        """spec_or_arrays: OrderedDict name -> ndarray (initial values, Keras layout)."""
+    def __init__(self, spec_or_arrays, device, init=None, trainable=None):
+        """spec_or_arrays: OrderedDict name -> ndarray (initial values, Keras layout).
+        trainable: optional predicate name -> bool (keras non-trainable weights, e.g. BatchNorm moving statistics,
+        stay in the flat buffer for get_weights()/set_weights() but receive no gradient and no update)."""
         arrays = spec_or_arrays
         self.names = list(arrays.keys())
         self.shapes = [tuple(np.shape(arrays[k])) for k in self.names]
@@ -40,10 +42,12 @@ class ParamGroup:
             v = self.flat[o:o + n].view(shape)
             self.params[name] = v
         self.set_weights([arrays[k] for k in self.names])
-        for v in self.params.values():
+        self._train_idx = [i for i, k in enumerate(self.names) if trainable is None or trainable(k)]
+        self._trainable = [self.params[self.names[i]] for i in self._train_idx]
+        for v in self._trainable:
             v.requires_grad_(True)
-        self._off_arr = (ctypes.c_int64 * len(self.names))(*self.offsets)
-        self._n_arr = (ctypes.c_int64 * len(self.names))(*self.sizes)
+        self._off_arr = (ctypes.c_int64 * len(self._train_idx))(*[self.offsets[i] for i in self._train_idx])
+        self._n_arr = (ctypes.c_int64 * len(self._train_idx))(*[self.sizes[i] for i in self._train_idx])
 
     # ---- Keras weight interchange
     def get_weights(self):
@@ -68,11 +72,13 @@ class ParamGroup:
 
     @property
     def trainable_weights(self):
-        return list(self.params.values())
+        return list(self._trainable)
 
     # ---- gradients
     def pack_grads(self, grads):
         """grads: list aligned with ``trainable_weights`` (None = unused variable) -> self.grad (flat)."""
+        if len(grads) != len(self._train_idx):
+            raise ValueError("expected %d gradients, got %d" % (len(self._train_idx), len(grads)))
         keep = [None if g is None else ops._chk(g) for g in grads]
         ptrs = (ctypes.c_void_p * len(keep))(*[None if g is None else g.data_ptr() for g in keep])
         L.call("cn_multi_copy", len(keep), ptrs, self._off_arr, self._n_arr, ops._p(self.grad), ops._stream())
@@ -164,3 +170,28 @@ def shard_rows(n_global):
         raise ValueError("global batch %d is not divisible by world size %d" % (n_global, ws))
     per = n_global // ws
     return rank * per, (rank + 1) * per
+
+
+class _GatherRows(torch.autograd.Function):
+    """All-gather of row shards for the one loss on the path that uses batch statistics
+    (compute_normalized_latent_regression_loss, confignet_second_stage.py:96-101).
+    Every rank then evaluates the same global loss; the backward keeps this rank's rows and multiplies by the
+    world size, which the 1/world gradient averaging of allreduce_grads() undoes."""
+
+    @staticmethod
+    def forward(ctx, x):
+        rank, ws = world()
+        x = x.contiguous()
+        parts = [torch.empty_like(x) for _ in range(ws)]
+        dist.all_gather(parts, x)
+        ctx.rows = x.shape[0]
+        return torch.cat(parts, dim=0)
+
+    @staticmethod
+    def backward(ctx, g):
+        rank, ws = world()
+        return g[rank * ctx.rows:(rank + 1) * ctx.rows] * float(ws)
+
+
+def gather_rows(x):
+    return x if world()[1] == 1 else _GatherRows.apply(x)

@@ -51,11 +51,13 @@ typedef struct {
   int ksize[3];    /* unused entries = 1                                                     */
   int stride;      /* 1 or 2, same on every axis                                             */
   int upsample;    /* 1, or 2 = nearest-neighbour x2 (UpSampling2D/3D) fused on the input    */
+  int pad;         /* -1: TF "SAME"; p >= 0: ZeroPadding(p) on every spatial side + "VALID"
+                      (keras-applications ResNet50 stem: ZeroPadding2D(3) + 7x7/s2, real_encoder.py:13) */
 } cn_conv_desc;
 
 /* which kernel family the last conv call on this thread used: 1 CUDA-core, 2 tcgen05 */
 int cn_last_conv_impl(void);
-/* y spatial dims for `d` (TF SAME: ceil(in*upsample/stride)). */
+/* y spatial dims for `d` (TF SAME: ceil(in*upsample/stride); explicit pad p: (in + 2p - k)/stride + 1). */
 int cn_conv_out_dims(const cn_conv_desc* d, int out_dims[3]);
 
 /* y = act(conv_same(upsample(x), w) + bias).
@@ -135,8 +137,9 @@ int cn_to_uint8(const float* x, uint8_t* out, int64_t n, void* stream);
 /* uint8 -> float /127.5 - 1 (confignet_first_stage.py:444, confignet_second_stage.py:303) */
 int cn_from_uint8(const uint8_t* x, float* out, int64_t n, void* stream);
 /* VGG 'caffe' preprocessing of [-1,1] RGB(BGR-flipped) images: out[..., c] = (x[..., 2-c]+1)*127.5 - mean[c]
- * (perceptual_loss.py:50-59); bwd maps the gradient back. */
-int cn_vgg_preprocess(const float* x, float* out, int64_t npix, int backward, void* stream);
+ * (perceptual_loss.py:50-59); mode 1 maps the gradient back.  Modes 2 / 3: the VGGFace variant
+ * (perceptual_loss.py:54-56): out = (x+1)*127.5 - (93.5940, 104.7624, 129.1863), no channel flip, and its backward. */
+int cn_vgg_preprocess(const float* x, float* out, int64_t npix, int mode, void* stream);
 
 /* Keras Adam + EMA over a flat parameter buffer (confignet_first_stage.py:393-400,601-602):
  * m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr_t * m / (sqrt(v) + eps);
@@ -153,6 +156,38 @@ int cn_multi_copy(int count, const float* const* src, const int64_t* dst_off, co
                   float* dst, void* stream);
 /* ema = alpha*ema + (1-alpha)*p (update_smoothed_weights, confignet_first_stage.py:393-400) */
 int cn_ema(float* ema, const float* p, int64_t n, float alpha, void* stream);
+
+/* ---- second stage / fine-tuning (confignet_second_stage.py, dnn_models/real_encoder.py) -------------------- */
+/* inference-statistics BatchNorm of the ResNet50 encoder (keras BatchNormalization without training=True inside
+ * the manual tape, real_encoder.py:27), gamma/beta trainable: scale = gamma/sqrt(var+eps), shift = beta - mean*scale */
+int cn_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int c,
+               float* scale, float* shift, void* stream);
+/* out = relu?(x*scale[c] + shift[c] + residual)   (BN + Add + Activation of a ResNet block; residual may be NULL) */
+int cn_bn_act_fwd(const float* x, const float* scale, const float* shift, const float* residual, int relu,
+                  float* out, int64_t npix, int c, void* stream);
+/* g = relu ? gout*(out>0) : gout; gx = g*scale[c]; gres = g (may be NULL); dgamma/dbeta (overwritten) */
+int cn_bn_act_bwd(const float* gout, const float* out, const float* x, const float* scale, const float* mean,
+                  const float* var, float eps, int relu, float* gx, float* gres, float* dgamma, float* dbeta,
+                  int64_t npix, int c, void* stream);
+/* ZeroPadding2D(1) + MaxPool 3x3/s2 VALID (ResNet50 pool1) and its backward (first maximum in scan order) */
+int cn_maxpool3s2_fwd(const float* x, int n, int h, int w, int c, float* y, void* stream);
+int cn_maxpool3s2_bwd(const float* x, const float* y, const float* gy, int n, int h, int w, int c, float* gx, void* stream);
+/* GlobalAveragePooling2D over p pixels (resnet50 pooling="avg") */
+int cn_avgpool_fwd(const float* x, int n, int p, int c, float* y, void* stream);
+int cn_avgpool_bwd(const float* gy, int n, int p, int c, float* gx, void* stream);
+/* out[r][c] = x[r][c] * scale[c]  (rotation_range_multiplier, real_encoder.py:20-21,30) */
+int cn_col_scale(const float* x, const float* scale, int rows, int c, float* out, void* stream);
+/* euler_angles_to_matrix (confignet_utils.py:122-145) on the device and its backward: angles (b,3) -> rot (b,9) */
+int cn_euler_fwd(const float* angles, int b, float* rot, void* stream);
+int cn_euler_bwd(const float* angles, const float* grot, int b, float* gangles, void* stream);
+/* gradient of cn_rotate3d_fwd wrt the matrix (b,9): needed where the rotation is predicted / optimised
+ * (confignet_second_stage.py:169-170, 348, 392) */
+int cn_rotate3d_bwd_rot(const float* grid, const float* gout, const float* rot, int b, int s, int c, float* grot, void* stream);
+/* compute_normalized_latent_regression_loss (confignet_second_stage.py:93-107): out, labels (b, j); the last nrot
+ * columns are not normalised.  bwd writes the gradients wrt both tensors, scaled by gscale[0]. */
+int cn_norm_latent_loss_fwd(const float* out, const float* labels, int b, int j, int nrot, float weight, float* loss, void* stream);
+int cn_norm_latent_loss_bwd(const float* out, const float* labels, int b, int j, int nrot, float weight, const float* gscale,
+                            float* g_out, float* g_labels, void* stream);
 
 #ifdef __cplusplus
 }
