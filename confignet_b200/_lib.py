@@ -54,7 +54,8 @@ SIGNATURES = {
     "cn_conv_wgrad": [_D, _V, _V, _V, _V, _I, _V],
     "cn_chan_sums": [_V, _V, _V, _I, _I, _I, _I, _f, _V, _V],
     "cn_chan_affine": [_V, _V, _V, _V, _I, _I, _I, _I, _f, _V, _V],
-    "cn_norm_coef": [_I, _V, _V, _V, _I, _I, _I, _f, _V, _V, _V, _V, _V],
+    "cn_chan_sums_splits": [_I, _I, _I],
+    "cn_norm_coef": [_I, _V, _I, _V, _V, _I, _I, _I, _f, _V, _V, _V, _V, _V],
     "cn_lrelu_fwd": [_V, _f, _V, _L, _V],
     "cn_act_bwd": [_V, _V, _I, _f, _V, _L, _V],
     "cn_axpby": [_V, _V, _f, _f, _V, _L, _V],

@@ -1408,8 +1408,10 @@ static bool tc_pixel_eligible(const GemmPlan& g, bool b_mn) {
 }
 
 static void pick_bn_mn(int cn, int* bn, int* bn_smem) {
-  // MN-major B tiles are built from 32-column swizzle atoms; {32,64,128} keeps the gather index math static
+  // MN-major B tiles are built from 32-column swizzle atoms (any multiple of 32 up to 128); the discriminator
+  // widths 96 / 192 / 288 take 96-column tiles instead of padding to 128
   int c = cn > 64 ? 128 : (cn > 32 ? 64 : 32);
+  if (cn > 64 && cn % 96 == 0 && cn % 128 != 0) c = 96;
   *bn_smem = c;
   *bn = c;
 }
@@ -1561,6 +1563,13 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
   return CN_OK;
 }
 
+// skinny.cu: HBM-bound layers with three channels on one side (return 1 = launched, 0 = not such a layer)
+int cn_skinny_fwd(const cn_conv_desc* d, const float* x, const float* w, const float* bias, int act, float alpha,
+                  float* y, cudaStream_t st);
+int cn_skinny_dgrad(const cn_conv_desc* d, const float* gy, const float* w, float* gx, cudaStream_t st);
+size_t cn_skinny_wgrad_scratch(const cn_conv_desc* d);
+int cn_skinny_wgrad(const cn_conv_desc* d, const float* x, const float* gy, float* gw, float* scratch, cudaStream_t st);
+
 static size_t conv_numel_x(const cn_conv_desc* d) {
   return (size_t)d->batch * d->in_dims[0] * d->in_dims[1] * d->in_dims[2] * d->cin;
 }
@@ -1577,6 +1586,11 @@ extern "C" int cn_conv_fwd(const cn_conv_desc* d, const float* x, const float* w
                            int act, float alpha, float* y, int impl, void* stream) {
   int rc = validate_desc(d); if (rc) return rc;
   CN_REQUIRE(x && w && y, CN_ERR_BAD_SHAPE, "null tensor pointer");
+  if (impl != CN_IMPL_TC) {
+    rc = cn_skinny_fwd(d, x, w, bias, act, alpha, y, (cudaStream_t)stream);
+    if (rc < 0) return rc;
+    if (rc == 1) { g_last_impl = 1; return CN_OK; }
+  }
   GemmPlan g;
   rc = get_plan(d, KIND_FWD, 0, &g); if (rc) return rc;
   return launch_pixel(g, true, x, w, bias, y, act, alpha, impl, (cudaStream_t)stream);
@@ -1587,6 +1601,11 @@ extern "C" int cn_conv_dgrad(const cn_conv_desc* d, const float* gy, const float
   int rc = validate_desc(d); if (rc) return rc;
   CN_REQUIRE(gy && w && gx, CN_ERR_BAD_SHAPE, "null tensor pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (impl != CN_IMPL_TC) {
+    rc = cn_skinny_dgrad(d, gy, w, gx, st);
+    if (rc < 0) return rc;
+    if (rc == 1) { g_last_impl = 1; return CN_OK; }
+  }
   const int nphase = (d->stride == 2) ? (1 << d->nd) : 1;
   int zero_mode = 0;
   if (nphase > 1) {
@@ -1619,7 +1638,16 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
   CN_REQUIRE(!(impl == CN_IMPL_TC && !tc), CN_ERR_UNSUPPORTED, "shape not eligible for the tcgen05 wgrad kernel");
   if (impl == CN_IMPL_FFMA) tc = false;
   g_last_impl = tc ? 2 : 1;
-  if (tc) {
+  const size_t skinny_ws = tc ? 0 : cn_skinny_wgrad_scratch(d);
+  if (skinny_ws > 0) {
+    float* ws = nullptr;
+    rc = packed_buffer(nullptr, skinny_ws, &ws); if (rc) return rc;
+    rc = cn_skinny_wgrad(d, x, gy, gw, ws, st);
+    if (rc < 0) return rc;
+  }
+  if (skinny_ws > 0 && rc == 1) {
+    // launched by skinny.cu
+  } else if (tc) {
     int bn, bn_smem; pick_bn_mn(g.Cn, &bn, &bn_smem);
     int mt = (g.Ktot + TC_BM - 1) / TC_BM, nt = (g.Cn + bn - 1) / bn;
     int total_kb = (g.M + TC_BK - 1) / TC_BK;

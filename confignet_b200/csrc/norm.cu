@@ -19,7 +19,9 @@
 __device__ __forceinline__ float lrelu_f(float v, float alpha) { return v > 0.f ? v : v * alpha; }
 __device__ __forceinline__ float lrelu_d(float v, float alpha) { return v > 0.f ? 1.f : alpha; }
 
-// grid: (ceil(ch/32), n, psplit)  block: (32, 8).  sums must be zero-filled (atomicAdd of block partials).
+// grid: (ceil(ch/32), n, psplit)  block: (32, 8).  Every block writes its own slice sums[z][n][col][0..6]
+// (no atomics, no zero-fill); the coefficient kernel adds the psplit slices in a fixed order, so the
+// statistics - and with them generate_images / encode_images - are bit-reproducible from run to run.
 template <int NT>
 __global__ void chan_sums_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                                  int p, int ch, int flags, float alpha, float* __restrict__ sums) {
@@ -49,8 +51,18 @@ __global__ void chan_sums_kernel(const float* __restrict__ a, const float* __res
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += sm[j][i][threadIdx.x];
-    atomicAdd(sums + ((size_t)n * ch + col) * 7 + j, t);
+    sums[(((size_t)blockIdx.z * gridDim.y + n) * ch + col) * 7 + j] = t;
   }
+}
+
+extern "C" int cn_chan_sums_splits(int n, int p, int ch) {
+  if (n <= 0 || p <= 0 || ch <= 0) return 1;
+  int cb = (ch + 31) / 32;
+  int psplit = (4 * 148 + cb * n - 1) / (cb * n);
+  int maxsplit = (p + 63) / 64;
+  if (psplit > maxsplit) psplit = maxsplit;
+  if (psplit < 1) psplit = 1;
+  return psplit;
 }
 
 extern "C" int cn_chan_sums(const float* a, const float* b, const float* c, int n, int p, int ch,
@@ -58,12 +70,8 @@ extern "C" int cn_chan_sums(const float* a, const float* b, const float* c, int 
   CN_REQUIRE(a && sums && n > 0 && p > 0 && ch > 0, CN_ERR_BAD_SHAPE, "cn_chan_sums: bad arguments");
   CN_REQUIRE(!(c && !b), CN_ERR_BAD_SHAPE, "cn_chan_sums: c given without b");
   cudaStream_t st = (cudaStream_t)stream;
-  CN_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)n * ch * 7 * sizeof(float), st));
   int cb = (ch + 31) / 32;
-  int psplit = (4 * 148 + cb * n - 1) / (cb * n);
-  int maxsplit = (p + 63) / 64;
-  if (psplit > maxsplit) psplit = maxsplit;
-  if (psplit < 1) psplit = 1;
+  int psplit = cn_chan_sums_splits(n, p, ch);
   dim3 grid(cb, n, psplit), block(32, 8);
   if (c) chan_sums_kernel<3><<<grid, block, 0, st>>>(a, b, c, p, ch, flags, alpha, sums);
   else if (b) chan_sums_kernel<2><<<grid, block, 0, st>>>(a, b, c, p, ch, flags, alpha, sums);
@@ -139,16 +147,26 @@ enum {
   CN_COEF_ADAIN_BWD = 7,    // sums(a,gy) p0=sb            -> coef0, out0 = gsb (n,2ch)
 };
 
-__global__ void norm_coef_kernel(int kind, const float* __restrict__ sums, const float* __restrict__ p0,
+__global__ void __launch_bounds__(256)
+norm_coef_kernel(int kind, const float* __restrict__ sums, int nsplit, const float* __restrict__ p0,
                                  const float* __restrict__ p1, int n, int ch, float N, float eps,
                                  float4* __restrict__ coef0, float4* __restrict__ coef1,
                                  float* __restrict__ out0, float* __restrict__ out1) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ch) return;
+  // block (32, 8): lane = channel, the 8 rows take every 8th sample
+  __shared__ float red[2][8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool cok = c < ch;
   const float invN = 1.f / N;
   float acc0 = 0.f, acc1 = 0.f;
-  for (int i = 0; i < n; ++i) {
-    const float* S = sums + ((size_t)i * ch + c) * 7;
+  for (int i = threadIdx.y; cok && i < n; i += 8) {
+    float S[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) S[j] = 0.f;
+    for (int z = 0; z < nsplit; ++z) {
+      const float* Sz = sums + (((size_t)z * n + i) * ch + c) * 7;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) S[j] += Sz[j];
+    }
     const size_t nc = (size_t)i * ch + c;
     const float mu = S[0] * invN;
     float var = S[3] * invN - mu * mu;
@@ -220,16 +238,26 @@ __global__ void norm_coef_kernel(int kind, const float* __restrict__ sums, const
       } break;
     }
   }
-  if (kind == CN_COEF_IN_BWD) { out0[c] = acc0; out1[c] = acc1; }
-  if (kind == CN_COEF_IN_BWDBWD) { out0[c] = acc0; }
+  if (kind == CN_COEF_IN_BWD || kind == CN_COEF_IN_BWDBWD) {     // per-channel parameter gradients: fold the 8 rows in order
+    red[0][threadIdx.y][threadIdx.x] = acc0;
+    red[1][threadIdx.y][threadIdx.x] = acc1;
+    __syncthreads();
+    if (threadIdx.y == 0 && cok) {
+      float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { t0 += red[0][i][threadIdx.x]; t1 += red[1][i][threadIdx.x]; }
+      out0[c] = t0;
+      if (kind == CN_COEF_IN_BWD) out1[c] = t1;
+    }
+  }
 }
 
-extern "C" int cn_norm_coef(int kind, const float* sums, const float* p0, const float* p1, int n, int ch,
+extern "C" int cn_norm_coef(int kind, const float* sums, int nsplit, const float* p0, const float* p1, int n, int ch,
                             int npix, float eps, float* coef0, float* coef1, float* out0, float* out1,
                             void* stream) {
-  CN_REQUIRE(kind >= 0 && kind <= 7 && sums && n > 0 && ch > 0 && npix > 0, CN_ERR_BAD_SHAPE, "cn_norm_coef: bad arguments");
-  norm_coef_kernel<<<(ch + 63) / 64, 64, 0, (cudaStream_t)stream>>>(kind, sums, p0, p1, n, ch, (float)npix, eps,
-                                                                     (float4*)coef0, (float4*)coef1, out0, out1);
+  CN_REQUIRE(kind >= 0 && kind <= 7 && sums && nsplit >= 1 && n > 0 && ch > 0 && npix > 0, CN_ERR_BAD_SHAPE, "cn_norm_coef: bad arguments");
+  norm_coef_kernel<<<(ch + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(kind, sums, nsplit, p0, p1, n, ch, (float)npix, eps,
+                                                                              (float4*)coef0, (float4*)coef1, out0, out1);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

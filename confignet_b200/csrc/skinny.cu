@@ -1,0 +1,602 @@
+// Skinny convolution layers of ConfigNet's hot path: three channels on one side, so the layer is bound by
+// the HBM traffic of its WIDE tensor (D.block0 3->48 AI 11, VGG block1_conv1 3->64 AI 13,
+// G.map_final 32->3 AI 70 FLOP/B), not by the tensor pipe.  Every kernel here follows one recipe:
+//   * a block owns one image row (or row pair) and stages the rows it needs in shared memory with coalesced
+//     128-bit loads, each HBM byte read once per block (neighbouring rows come from L2);
+//   * threads own register tiles chosen so that FFMA issue, not shared-memory wavefronts, bounds the inner loop;
+//   * stores are whole 32-byte sectors;
+//   * weight gradients are accumulated in registers by persistent blocks (grid = 2 x SM count), written as
+//     per-block partials and summed in a fixed order by a second kernel: deterministic, no atomics.
+//
+//   c3_*    : Conv2D(3 -> 48|64, k3, stride 1|2, SAME)            hologan_discriminator.py:28-40 (DiscrBlock 0),
+//                                                                  hologan_discriminator.py:77-97 (regressor trunk),
+//                                                                  perceptual_loss.py:19-24 (VGG block1_conv1)
+//   up4c3_* : UpSampling2D(2) + Conv2D(32 -> 3, k4, SAME) + tanh   hologan_generator.py:101,170-172 (map_final)
+//             evaluated on the LOW-resolution tensor: output pixel (2R+dy, 2C+dx) only sees source pixels
+//             (R+sy, C+sx), sy,sx in {-1,0,1}, and the taps that land on the same source pixel are pre-summed
+//             (sub-pixel folding, SURVEY.md section 7 hard part 5): 25 folded taps per 2x2 output cell instead of 64.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void fma4(float4& a, float x, const float4& w) {
+  a.x = fmaf(x, w.x, a.x); a.y = fmaf(x, w.y, a.y); a.z = fmaf(x, w.z, a.z); a.w = fmaf(x, w.w, a.w);
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+  return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// c3 forward: block = (128 output pixels of one output row); thread = (pixel pair, channel quarter)
+// ------------------------------------------------------------------------------------------------
+template <int S, int COUT>
+__global__ void __launch_bounds__(256)
+c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+              float* __restrict__ y, int H, int W, int OH, int OW, int pby, int pbx, int act, float alpha) {
+  constexpr int CPT = COUT / 16;          // float4 channel groups per thread
+  constexpr int C4 = COUT / 4;
+  constexpr int NCOL = 127 * S + 3;       // input columns under 128 output pixels
+  constexpr int RS = NCOL * 3;
+  __shared__ __align__(16) float s_w[27 * COUT];
+  __shared__ float s_x[3 * RS];
+  const int tid = threadIdx.x, n = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * 128;
+  for (int i = tid; i < 27 * C4; i += 256) reinterpret_cast<float4*>(s_w)[i] = ldg4(w + 4 * i);
+  const int ix0 = ox0 * S - pbx;
+  for (int i = tid; i < 3 * RS; i += 256) {
+    const int r = i / RS, j = i - r * RS, col = j / 3;
+    const int iy = oy * S + r - pby, ix = ix0 + col;
+    float v = 0.f;
+    if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) v = __ldg(x + ((long long)(n * H + iy) * W + ix0) * 3 + j);
+    s_x[i] = v;
+  }
+  __syncthreads();
+  const int q = tid & 3, pp = tid >> 2, la = 2 * pp * S;
+  float4 acc[2][CPT];
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[p][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* w4 = reinterpret_cast<const float4*>(s_w);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {           // e = kx*3 + ci: 9 contiguous floats of the input row
+      const float xa = s_x[ky * RS + la * 3 + e], xb = s_x[ky * RS + (la + S) * 3 + e];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const float4 wv = w4[(ky * 9 + e) * C4 + q + 4 * j];
+        fma4(acc[0][j], xa, wv);
+        fma4(acc[1][j], xb, wv);
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int ox = ox0 + 2 * pp + p;
+    if (ox >= OW) continue;
+    float* out = y + ((size_t)(n * OH + oy) * OW + ox) * COUT;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const int f = q + 4 * j;
+      float4 v = acc[p][j];
+      if (bias != nullptr) { const float4 b = ldg4(bias + 4 * f); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+      v.x = cn_apply_act(v.x, act, alpha); v.y = cn_apply_act(v.y, act, alpha);
+      v.z = cn_apply_act(v.z, act, alpha); v.w = cn_apply_act(v.w, act, alpha);
+      *reinterpret_cast<float4*>(out + 4 * f) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// c3 input gradient: gx[iy][ix][ci] = sum_{ky,kx,co} gy[(iy+pb-ky)/S][(ix+pb-kx)/S][co] * w[ky][kx][ci][co]
+// (terms whose division is not exact do not exist).  stride 2 (even H, W; pb = 0): thread = 2x2 cell of gx;
+// stride 1 (pb = 1): thread = 1x2 pixels.  The four lanes of a cell split the output channels of gy and are
+// summed with two shuffles.  PS = padded pixel stride of the staged gy rows (conflict-free float4 reads).
+// ------------------------------------------------------------------------------------------------
+template <int S, int COUT, int PS>
+__global__ void __launch_bounds__(256)
+c3_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ w, float* __restrict__ gx,
+                int H, int W, int OH, int OW) {
+  constexpr int TY = (S == 2) ? 2 : 1, TX = 2;
+  constexpr int PB = (S == 2) ? 0 : 1;
+  constexpr int CELLS = 64, GXW = CELLS * TX;
+  constexpr int GYW = (S == 2) ? CELLS + 1 : GXW + 2;
+  constexpr int GYR = (S == 2) ? 2 : 3;
+  constexpr int CPT = COUT / 16, C4 = COUT / 4, PS4 = PS / 4;
+  extern __shared__ __align__(16) float sm[];
+  float* s_w = sm;                          // [27][COUT]
+  float* s_gy = sm + 27 * COUT;             // [GYR][GYW][PS]
+  const int tid = threadIdx.x, n = blockIdx.z, by = blockIdx.y, x0 = blockIdx.x * GXW;
+  const int iy0 = by * TY;
+  const int gr0 = (S == 2) ? by - 1 : iy0 - 1, gc0 = (S == 2) ? x0 / 2 - 1 : x0 - 1;
+  for (int i = tid; i < 27 * C4; i += 256) reinterpret_cast<float4*>(s_w)[i] = ldg4(w + 4 * i);
+  for (int i = tid; i < GYR * GYW * C4; i += 256) {
+    const int f = i % C4, pc = i / C4, col = pc % GYW, row = pc / GYW;
+    const int gr = gr0 + row, gc = gc0 + col;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((unsigned)gr < (unsigned)OH && (unsigned)gc < (unsigned)OW) v = ldg4(gy + ((size_t)(n * OH + gr) * OW + gc) * COUT + 4 * f);
+    reinterpret_cast<float4*>(s_gy)[(row * GYW + col) * PS4 + f] = v;
+  }
+  __syncthreads();
+  const int q = tid & 3, cell = tid >> 2;
+  float acc[TY][TX][3];
+#pragma unroll
+  for (int a = 0; a < TY; ++a)
+#pragma unroll
+    for (int b = 0; b < TX; ++b)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[a][b][c] = 0.f;
+  const float4* w4 = reinterpret_cast<const float4*>(s_w);
+  const float4* g4 = reinterpret_cast<const float4*>(s_gy);
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) {
+    const int f = q + 4 * j;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int dy = 0; dy < TY; ++dy) {
+        if (((dy + PB - ky + 2 * S) % S) != 0) continue;
+        const int lrow = (S == 2) ? (dy - ky) / 2 + 1 : 2 - ky;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+          for (int dx = 0; dx < TX; ++dx) {
+            if (((dx + PB - kx + 2 * S) % S) != 0) continue;
+            const int lcol = (S == 2) ? cell + (dx - kx) / 2 + 1 : cell * TX + dx + 2 - kx;
+            const float4 g = g4[(lrow * GYW + lcol) * PS4 + f];
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci)
+              acc[dy][dx][ci] = dot4(g, w4[((ky * 3 + kx) * 3 + ci) * C4 + f], acc[dy][dx][ci]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < TY; ++a)
+#pragma unroll
+    for (int b = 0; b < TX; ++b)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = acc[a][b][c];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        acc[a][b][c] = v;
+      }
+  // lane q of the cell writes pixel (dy, dx) = (q >> 1, q & 1) (stride 2) or (0, q) for q < 2 (stride 1)
+  const int dy = (S == 2) ? (q >> 1) : 0, dx = q & 1;
+  if (S == 2 || q < 2) {
+    const int iy = iy0 + dy, ix = x0 + cell * TX + dx;
+    if (iy < H && ix < W) {
+      float* out = gx + ((size_t)(n * H + iy) * W + ix) * 3;
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+#pragma unroll
+      for (int a = 0; a < TY; ++a)
+#pragma unroll
+        for (int b = 0; b < TX; ++b)
+          if (a == dy && b == dx) { v0 = acc[a][b][0]; v1 = acc[a][b][1]; v2 = acc[a][b][2]; }
+      out[0] = v0; out[1] = v1; out[2] = v2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// c3 weight gradient: gw[ky][kx][ci][co] = sum_pixels x[S*oy+ky-pb][S*ox+kx-pb][ci] * gy[oy][ox][co].
+// Persistent blocks walk output rows; thread = (pixel group g, kernel row ky, 8 output channels) holds a
+// 9 x 8 register tile; the 14 pixel groups of a block are folded in a fixed order at the end.
+// ------------------------------------------------------------------------------------------------
+template <int S, int COUT>
+__global__ void __launch_bounds__(256, 2)
+c3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ part,
+                int B, int H, int W, int OH, int OW, int pby, int pbx) {
+  constexpr int NC8 = COUT / 8, ITEMS = 3 * NC8, GROUPS = 256 / ITEMS, C4 = COUT / 4;
+  constexpr int NCOL = 127 * S + 3, RS = NCOL * 3;
+  __shared__ __align__(16) float s_gy[128 * COUT];
+  __shared__ float s_x[3 * RS + 8];
+  const int tid = threadIdx.x;
+  const int g = tid / ITEMS, item = tid - g * ITEMS, ky = item / NC8, c8 = item - ky * NC8;
+  const bool active = g < GROUPS;
+  float acc[9][8];
+#pragma unroll
+  for (int a = 0; a < 9; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+  const int nseg = (OW + 127) / 128;
+  const int nrows = B * OH * nseg;
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int seg = row % nseg, r2 = row / nseg, oy = r2 % OH, n = r2 / OH;
+    const int ox0 = seg * 128, npx = min(128, OW - ox0);
+    __syncthreads();
+    const float* grow = gy + ((size_t)(n * OH + oy) * OW + ox0) * COUT;
+    for (int i = tid; i < npx * C4; i += 256) reinterpret_cast<float4*>(s_gy)[i] = ldg4(grow + 4 * i);
+    const int ix0 = ox0 * S - pbx;
+    for (int i = tid; i < 3 * RS; i += 256) {
+      const int r = i / RS, j = i - r * RS, col = j / 3;
+      const int iy = oy * S + r - pby, ix = ix0 + col;
+      float v = 0.f;
+      if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) v = __ldg(x + ((long long)(n * H + iy) * W + ix0) * 3 + j);
+      s_x[i] = v;
+    }
+    __syncthreads();
+    if (active) {
+      for (int p = g; p < npx; p += GROUPS) {
+        const float4 ga = reinterpret_cast<const float4*>(s_gy)[p * C4 + 2 * c8];
+        const float4 gb = reinterpret_cast<const float4*>(s_gy)[p * C4 + 2 * c8 + 1];
+        const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const float* xr = s_x + ky * RS + p * S * 3;
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+          const float xv = xr[a];
+#pragma unroll
+          for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(xv, gv[b], acc[a][b]);
+        }
+      }
+    }
+  }
+  // fixed-order fold of the pixel groups, then one partial per block
+  __syncthreads();
+  float* s_acc = s_gy;                      // 27*COUT floats
+  for (int g2 = 0; g2 < GROUPS; ++g2) {
+    if (active && g == g2) {
+#pragma unroll
+      for (int a = 0; a < 9; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const int o = (ky * 9 + a) * COUT + c8 * 8 + b;
+          s_acc[o] = (g2 == 0) ? acc[a][b] : s_acc[o] + acc[a][b];
+        }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < 27 * COUT; i += 256) part[(size_t)blockIdx.x * 27 * COUT + i] = s_acc[i];
+}
+
+// out[i] = sum_b part[b][i] in block order (deterministic)
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(const float* __restrict__ part, int nblocks, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int b = 0; b < nblocks; ++b) a += part[(size_t)b * n + i];
+  out[i] = a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// up4c3: UpSampling2D(2) + Conv2D(CIN -> 3, k4, SAME), folded onto the low-resolution tensor.
+// With lr = 2 - 2*sy + dy (0..4):  y[2R+dy][2C+dx] = sum_{sy,sx} x[R+sy][C+sx] . Wd[lr][lc]
+//                                   gx[r][c]       = sum_{lr,lc} gy[2r-2+lr][2c-2+lc] . Wd[lr][lc]
+// Wd[lr][lc] = sum_{ty in T(lr), tx in T(lc)} w[ty][tx],  T = {3}, {2,3}, {1,2}, {0,1}, {0}.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fold_taps(int l, int& t0, int& t1) {   // T(l) as [t0, t1]
+  t0 = l == 0 ? 3 : (l == 1 ? 2 : (l == 2 ? 1 : 0));
+  t1 = l == 0 ? 3 : (l == 1 ? 3 : (l == 2 ? 2 : (l == 3 ? 1 : 0)));
+}
+
+// s_wd[(lr*5+lc)][ci] = float4(Wd[..][ci][0..2], 0)
+template <int CIN>
+__device__ __forceinline__ void build_folded(const float* __restrict__ w, float4* s_wd, int tid, int nthreads) {
+  for (int i = tid; i < 25 * CIN; i += nthreads) {
+    const int ci = i % CIN, l = i / CIN, lr = l / 5, lc = l - lr * 5;
+    int y0, y1, x0, x1;
+    fold_taps(lr, y0, y1); fold_taps(lc, x0, x1);
+    float a[3] = {0.f, 0.f, 0.f};
+    for (int ty = y0; ty <= y1; ++ty)
+      for (int tx = x0; tx <= x1; ++tx)
+        for (int co = 0; co < 3; ++co) a[co] += __ldg(w + ((size_t)(ty * 4 + tx) * CIN + ci) * 3 + co);
+    s_wd[i] = make_float4(a[0], a[1], a[2], 0.f);
+  }
+}
+
+// forward: block = one source row (128 cells); warp parity = dy; thread = (cell, dy) -> 2 output pixels x 3 channels
+template <int CIN>
+__global__ void __launch_bounds__(256)
+up4c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                 float* __restrict__ y, int H, int W, int act, float alpha) {
+  constexpr int PS = CIN + 4, PS4 = PS / 4, XW = 130, CI4 = CIN / 4;
+  extern __shared__ __align__(16) float sm[];
+  float4* s_wd = reinterpret_cast<float4*>(sm);               // [25][CIN]
+  float4* s_x = s_wd + 25 * CIN;                              // [3][XW][PS4]
+  const int tid = threadIdx.x, n = blockIdx.z, R = blockIdx.y, c0 = blockIdx.x * 128;
+  build_folded<CIN>(w, s_wd, tid, 256);
+  for (int i = tid; i < 3 * XW * CI4; i += 256) {
+    const int f = i % CI4, pc = i / CI4, col = pc % XW, row = pc / XW;
+    const int r = R - 1 + row, c = c0 - 1 + col;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((unsigned)r < (unsigned)H && (unsigned)c < (unsigned)W) v = ldg4(x + ((size_t)(n * H + r) * W + c) * CIN + 4 * f);
+    s_x[(row * XW + col) * PS4 + f] = v;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int dy = warp & 1, cell = (warp >> 1) * 32 + lane;
+  float acc[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+  for (int sy = -1; sy <= 1; ++sy) {
+    const int lr = 2 - 2 * sy + dy;
+    if (lr > 4) continue;                                      // warp-uniform (dy = warp parity)
+#pragma unroll
+    for (int sx = -1; sx <= 1; ++sx) {
+      const float4* xp = s_x + ((sy + 1) * XW + cell + 1 + sx) * PS4;
+      const float4* w0 = s_wd + (lr * 5 + 2 - 2 * sx) * CIN;         // dx = 0: lc = 2 - 2 sx
+      const float4* w1 = s_wd + (lr * 5 + 3 - 2 * sx) * CIN;         // dx = 1: lc = 3 - 2 sx (sx = -1 -> 5: absent)
+#pragma unroll
+      for (int f = 0; f < CI4; ++f) {
+        const float4 xv = xp[f];
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4 a = w0[4 * f + e];
+          acc[0][0] = fmaf(xs[e], a.x, acc[0][0]); acc[0][1] = fmaf(xs[e], a.y, acc[0][1]); acc[0][2] = fmaf(xs[e], a.z, acc[0][2]);
+          if (sx >= 0) {
+            const float4 b = w1[4 * f + e];
+            acc[1][0] = fmaf(xs[e], b.x, acc[1][0]); acc[1][1] = fmaf(xs[e], b.y, acc[1][1]); acc[1][2] = fmaf(xs[e], b.z, acc[1][2]);
+          }
+        }
+      }
+    }
+  }
+  const int C = c0 + cell;
+  if (C < W) {
+    float* out = y + ((size_t)(n * 2 * H + 2 * R + dy) * (2 * W) + 2 * C) * 3;
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+      for (int co = 0; co < 3; ++co) {
+        float v = acc[dx][co] + (bias != nullptr ? __ldg(bias + co) : 0.f);
+        out[dx * 3 + co] = cn_apply_act(v, act, alpha);
+      }
+  }
+}
+
+// input gradient: block = one source row, 64 pixels; thread = (pixel, 8 source channels)
+template <int CIN>
+__global__ void __launch_bounds__(256)
+up4c3_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ w, float* __restrict__ gx, int H, int W) {
+  constexpr int NG = CIN / 8;               // channel groups per pixel
+  constexpr int PXB = 256 / NG;             // pixels per block
+  constexpr int GW = 2 * PXB + 3;           // gy columns 2c0-2 .. 2(c0+PXB-1)+2
+  extern __shared__ __align__(16) float sm[];
+  float* s_wt = sm;                         // [25][3][CIN]  (transposed: source channels contiguous)
+  float* s_gy = sm + 25 * 3 * CIN;          // [5][GW][3]
+  const int tid = threadIdx.x, n = blockIdx.z, r = blockIdx.y, c0 = blockIdx.x * PXB;
+  for (int i = tid; i < 25 * CIN; i += 256) {
+    const int ci = i % CIN, l = i / CIN, lr = l / 5, lc = l - lr * 5;
+    int y0, y1, x0, x1;
+    fold_taps(lr, y0, y1); fold_taps(lc, x0, x1);
+    float a[3] = {0.f, 0.f, 0.f};
+    for (int ty = y0; ty <= y1; ++ty)
+      for (int tx = x0; tx <= x1; ++tx)
+        for (int co = 0; co < 3; ++co) a[co] += __ldg(w + ((size_t)(ty * 4 + tx) * CIN + ci) * 3 + co);
+    for (int co = 0; co < 3; ++co) s_wt[(l * 3 + co) * CIN + ci] = a[co];
+  }
+  const int OHh = 2 * H, OWw = 2 * W;
+  for (int i = tid; i < 5 * GW * 3; i += 256) {
+    const int row = i / (GW * 3), j = i - row * GW * 3, col = j / 3;
+    const int oy = 2 * r - 2 + row, ox = 2 * c0 - 2 + col;
+    float v = 0.f;
+    if ((unsigned)oy < (unsigned)OHh && (unsigned)ox < (unsigned)OWw) v = __ldg(gy + ((long long)(n * OHh + oy) * OWw + (2 * c0 - 2)) * 3 + j);
+    s_gy[i] = v;
+  }
+  __syncthreads();
+  const int grp = tid % NG, px = tid / NG;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+#pragma unroll
+  for (int lr = 0; lr < 5; ++lr) {
+#pragma unroll
+    for (int lc = 0; lc < 5; ++lc) {
+      const float* gp = s_gy + (lr * GW + 2 * px + lc) * 3;
+#pragma unroll
+      for (int co = 0; co < 3; ++co) {
+        const float g = gp[co];
+        const float4* wp = reinterpret_cast<const float4*>(s_wt + ((lr * 5 + lc) * 3 + co) * CIN + grp * 8);
+        fma4(a0, g, wp[0]);
+        fma4(a1, g, wp[1]);
+      }
+    }
+  }
+  const int c = c0 + px;
+  if (c < W) {
+    float4* out = reinterpret_cast<float4*>(gx + ((size_t)(n * H + r) * W + c) * CIN + grp * 8);
+    out[0] = a0; out[1] = a1;
+  }
+}
+
+// weight gradient, folded: gWd[lr][lc][ci][co] = sum_{n,r,c} x[r][c][ci] * gy[2r-2+lr][2c-2+lc][co].
+// Persistent blocks walk source rows; lane = source channel (CIN = 32), warp wv owns folded taps wv, wv+8, ...
+template <int CIN>
+__global__ void __launch_bounds__(256, 2)
+up4c3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ part, int B, int H, int W) {
+  static_assert(CIN == 32, "lane = source channel");
+  constexpr int SEG = 128, GW = 2 * SEG + 3;
+  __shared__ __align__(16) float s_x[SEG * CIN];
+  __shared__ __align__(16) float4 s_gy[5 * GW];              // gy pixel padded to float4
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float acc[4][3];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) { acc[a][0] = 0.f; acc[a][1] = 0.f; acc[a][2] = 0.f; }
+  const int nseg = (W + SEG - 1) / SEG, nrows = B * H * nseg;
+  const int OHh = 2 * H, OWw = 2 * W;
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int seg = row % nseg, r2 = row / nseg, r = r2 % H, n = r2 / H;
+    const int c0 = seg * SEG, npx = min(SEG, W - c0);
+    __syncthreads();
+    const float* xrow = x + ((size_t)(n * H + r) * W + c0) * CIN;
+    for (int i = tid; i < npx * (CIN / 4); i += 256) reinterpret_cast<float4*>(s_x)[i] = ldg4(xrow + 4 * i);
+    for (int i = tid; i < 5 * GW; i += 256) {
+      const int rr = i / GW, col = i - rr * GW;
+      const int oy = 2 * r - 2 + rr, ox = 2 * c0 - 2 + col;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((unsigned)oy < (unsigned)OHh && (unsigned)ox < (unsigned)OWw) {
+        const float* gp = gy + ((size_t)(n * OHh + oy) * OWw + ox) * 3;
+        v = make_float4(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), 0.f);
+      }
+      s_gy[i] = v;
+    }
+    __syncthreads();
+    for (int p = 0; p < npx; ++p) {
+      const float xv = s_x[p * CIN + lane];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int l = warp + 8 * a;
+        if (l < 25) {
+          const int lr = l / 5, lc = l - lr * 5;
+          const float4 g = s_gy[lr * GW + 2 * p + lc];
+          acc[a][0] = fmaf(xv, g.x, acc[a][0]); acc[a][1] = fmaf(xv, g.y, acc[a][1]); acc[a][2] = fmaf(xv, g.z, acc[a][2]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int l = warp + 8 * a;
+    if (l < 25)
+      for (int co = 0; co < 3; ++co) part[(size_t)blockIdx.x * 25 * CIN * 3 + (l * CIN + lane) * 3 + co] = acc[a][co];
+  }
+}
+
+// gw[ty][tx][ci][co] = sum over the folded taps that contain (ty, tx), partials summed in block order
+template <int CIN>
+__global__ void __launch_bounds__(256)
+up4c3_unfold_kernel(const float* __restrict__ part, int nblocks, float* __restrict__ gw) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= 16 * CIN * 3) return;
+  const int e = i % (CIN * 3), t = i / (CIN * 3), ty = t >> 2, tx = t & 3;
+  // T^-1: tap 0 -> {3,4}, 1 -> {2,3}, 2 -> {1,2}, 3 -> {0,1}
+  const int lr0 = 3 - ty, lc0 = 3 - tx;
+  float a = 0.f;
+  for (int b = 0; b < nblocks; ++b) {
+    const float* p = part + (size_t)b * 25 * CIN * 3;
+    a += (p[((lr0 * 5 + lc0)) * CIN * 3 + e] + p[((lr0 * 5 + lc0 + 1)) * CIN * 3 + e]) +
+         (p[(((lr0 + 1) * 5 + lc0)) * CIN * 3 + e] + p[(((lr0 + 1) * 5 + lc0 + 1)) * CIN * 3 + e]);
+  }
+  gw[i] = a;
+}
+
+int g_sms = 0;
+int sm_count() {
+  if (g_sms == 0) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  return g_sms;
+}
+
+void same_pad(int in, int k, int s, int* out, int* pb) {
+  *out = (in + s - 1) / s;
+  int tot = (*out - 1) * s + k - in;
+  if (tot < 0) tot = 0;
+  *pb = tot / 2;
+}
+
+bool is_c3(const cn_conv_desc* d) {
+  return d->nd == 2 && d->cin == 3 && d->ksize[0] == 3 && d->ksize[1] == 3 && d->upsample == 1 && d->pad < 0 &&
+         (d->cout == 48 || d->cout == 64);
+}
+bool is_up4c3(const cn_conv_desc* d) {
+  return d->nd == 2 && d->cin == 32 && d->cout == 3 && d->ksize[0] == 4 && d->ksize[1] == 4 && d->upsample == 2 &&
+         d->stride == 1 && d->pad < 0;
+}
+
+template <typename K>
+int opt_in_smem(K kernel, int bytes) {
+  if (bytes > 48 * 1024) CN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return CN_OK;
+}
+
+}  // namespace
+
+// Each cn_skinny_* returns 1 when it launched the layer, 0 when the shape is not one of the skinny layers,
+// or a negative CN_ERR_* code.
+int cn_skinny_fwd(const cn_conv_desc* d, const float* x, const float* w, const float* bias, int act, float alpha,
+                  float* y, cudaStream_t st) {
+  const int H = d->in_dims[0], W = d->in_dims[1];
+  if (is_c3(d)) {
+    int OH, OW, pby, pbx;
+    same_pad(H, 3, d->stride, &OH, &pby); same_pad(W, 3, d->stride, &OW, &pbx);
+    dim3 grid((OW + 127) / 128, OH, d->batch);
+    if (d->stride == 2 && d->cout == 48) c3_fwd_kernel<2, 48><<<grid, 256, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+    else if (d->stride == 2) c3_fwd_kernel<2, 64><<<grid, 256, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+    else if (d->cout == 48) c3_fwd_kernel<1, 48><<<grid, 256, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+    else c3_fwd_kernel<1, 64><<<grid, 256, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+    CN_CHECK_LAUNCH();
+    return 1;
+  }
+  if (is_up4c3(d)) {
+    const int smem = (25 * 32 + 3 * 130 * 9) * 16;
+    int rc = opt_in_smem(up4c3_fwd_kernel<32>, smem); if (rc) return rc;
+    dim3 grid((W + 127) / 128, H, d->batch);
+    up4c3_fwd_kernel<32><<<grid, 256, smem, st>>>(x, w, bias, y, H, W, act, alpha);
+    CN_CHECK_LAUNCH();
+    return 1;
+  }
+  return 0;
+}
+
+int cn_skinny_dgrad(const cn_conv_desc* d, const float* gy, const float* w, float* gx, cudaStream_t st) {
+  const int H = d->in_dims[0], W = d->in_dims[1];
+  if (is_c3(d)) {
+    int OH, OW, pby, pbx;
+    same_pad(H, 3, d->stride, &OH, &pby); same_pad(W, 3, d->stride, &OW, &pbx);
+    if (d->stride == 2 && d->cout == 48 && H % 2 == 0 && W % 2 == 0) {
+      constexpr int PS = 48;
+      const int smem = (27 * 48 + 2 * 65 * PS) * 4;
+      int rc = opt_in_smem(c3_dgrad_kernel<2, 48, PS>, smem); if (rc) return rc;
+      dim3 grid((W + 127) / 128, H / 2, d->batch);
+      c3_dgrad_kernel<2, 48, PS><<<grid, 256, smem, st>>>(gy, w, gx, H, W, OH, OW);
+      CN_CHECK_LAUNCH();
+      return 1;
+    }
+    if (d->stride == 1 && d->cout == 64) {
+      constexpr int PS = 72;
+      const int smem = (27 * 64 + 3 * 130 * PS) * 4;
+      int rc = opt_in_smem(c3_dgrad_kernel<1, 64, PS>, smem); if (rc) return rc;
+      dim3 grid((W + 127) / 128, H, d->batch);
+      c3_dgrad_kernel<1, 64, PS><<<grid, 256, smem, st>>>(gy, w, gx, H, W, OH, OW);
+      CN_CHECK_LAUNCH();
+      return 1;
+    }
+    return 0;
+  }
+  if (is_up4c3(d)) {
+    const int smem = (25 * 3 * 32 + 5 * (2 * 64 + 3) * 3) * 4;
+    dim3 grid((W + 63) / 64, H, d->batch);
+    up4c3_dgrad_kernel<32><<<grid, 256, smem, st>>>(gy, w, gx, H, W);
+    CN_CHECK_LAUNCH();
+    return 1;
+  }
+  return 0;
+}
+
+size_t cn_skinny_wgrad_scratch(const cn_conv_desc* d) {
+  if (is_c3(d)) return (size_t)2 * sm_count() * 27 * d->cout * sizeof(float);
+  if (is_up4c3(d)) return (size_t)2 * sm_count() * 25 * 32 * 3 * sizeof(float);
+  return 0;
+}
+
+int cn_skinny_wgrad(const cn_conv_desc* d, const float* x, const float* gy, float* gw, float* scratch, cudaStream_t st) {
+  const int H = d->in_dims[0], W = d->in_dims[1];
+  if (is_c3(d) && d->cout == 48) {
+    int OH, OW, pby, pbx;
+    same_pad(H, 3, d->stride, &OH, &pby); same_pad(W, 3, d->stride, &OW, &pbx);
+    int rows = d->batch * OH * ((OW + 127) / 128);
+    int blocks = 2 * sm_count(); if (blocks > rows) blocks = rows;
+    if (d->stride == 2) c3_wgrad_kernel<2, 48><<<blocks, 256, 0, st>>>(x, gy, scratch, d->batch, H, W, OH, OW, pby, pbx);
+    else c3_wgrad_kernel<1, 48><<<blocks, 256, 0, st>>>(x, gy, scratch, d->batch, H, W, OH, OW, pby, pbx);
+    CN_CHECK_LAUNCH();
+    sum_partials_kernel<<<(27 * 48 + 255) / 256, 256, 0, st>>>(scratch, blocks, 27 * 48, gw);
+    CN_CHECK_LAUNCH();
+    return 1;
+  }
+  if (is_up4c3(d)) {
+    int rows = d->batch * H * ((W + 127) / 128);
+    int blocks = 2 * sm_count(); if (blocks > rows) blocks = rows;
+    up4c3_wgrad_kernel<32><<<blocks, 256, 0, st>>>(x, gy, scratch, d->batch, H, W);
+    CN_CHECK_LAUNCH();
+    up4c3_unfold_kernel<32><<<(16 * 32 * 3 + 255) / 256, 256, 0, st>>>(scratch, blocks, gw);
+    CN_CHECK_LAUNCH();
+    return 1;
+  }
+  return 0;
+}

@@ -245,6 +245,9 @@ FLAG_LRELU_A, FLAG_MASK_OUT, FLAG_MASK_C = 1, 2, 4
  COEF_ADAIN_FWD, COEF_ADAIN_BWD) = range(8)
 
 
+_SPLITS = {}     # (n, p, ch) -> pixel slices cn_chan_sums writes
+
+
 def _npc(x):
     n, c = x.shape[0], x.shape[-1]
     return n, x.numel() // (n * c), c
@@ -252,7 +255,10 @@ def _npc(x):
 
 def _sums(a, b=None, c=None, flags=0, alpha=0.0):
     n, p, ch = _npc(a)
-    s = torch.empty((n, ch, 7), device=a.device, dtype=torch.float32)
+    ns = _SPLITS.get((n, p, ch))
+    if ns is None:
+        ns = _SPLITS[(n, p, ch)] = int(L.load().cn_chan_sums_splits(n, p, ch))
+    s = torch.empty((ns, n, ch, 7), device=a.device, dtype=torch.float32)
     L.call("cn_chan_sums", _p(a), _p(b), _p(c), n, p, ch, flags, alpha, _p(s), _stream())
     return s
 
@@ -269,7 +275,7 @@ def _coef(kind, sums, p0, p1, n, ch, npix, eps, ncoef=1, out0_shape=None, out1_s
     coefs = [torch.empty((n, ch, 4), device=dev, dtype=torch.float32) for _ in range(ncoef)]
     out0 = torch.empty(out0_shape, device=dev, dtype=torch.float32) if out0_shape else None
     out1 = torch.empty(out1_shape, device=dev, dtype=torch.float32) if out1_shape else None
-    L.call("cn_norm_coef", kind, _p(sums), _p(p0), _p(p1), n, ch, npix, eps,
+    L.call("cn_norm_coef", kind, _p(sums), sums.shape[0], _p(p0), _p(p1), n, ch, npix, eps,
            _p(coefs[0]) if ncoef > 0 else None, _p(coefs[1]) if ncoef > 1 else None, _p(out0), _p(out1), _stream())
     return coefs, out0, out1
 

@@ -83,8 +83,11 @@ int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float* gy, float*
 #define CN_FLAG_LRELU_A 1   /* a := lrelu(a, alpha) before use                    */
 #define CN_FLAG_MASK_OUT 2  /* affine result *= lrelu'(a_raw)                     */
 #define CN_FLAG_MASK_C 4    /* c := c * lrelu'(a_raw)                             */
-/* sums[(n*C + ch)*7 + j] over the P pixels of sample n:
+/* sums[((z*n + i)*C + ch)*7 + j]: partial sums of pixel slice z (0 <= z < cn_chan_sums_splits(n, p, ch)) of
+ * sample i; the caller provides splits*n*C*7 floats, no zero-fill needed; cn_norm_coef adds the slices in a
+ * fixed order (bit-reproducible statistics).
  *   j: 0 sum a, 1 sum b, 2 sum c, 3 sum a*a, 4 sum a*b, 5 sum a*c, 6 sum b*c  (b, c may be NULL) */
+int cn_chan_sums_splits(int n, int p, int ch);
 int cn_chan_sums(const float* a, const float* b, const float* c, int n, int p, int ch,
                  int flags, float alpha, float* sums, void* stream);
 /* out = ka[n,ch]*a + kb[n,ch]*b + kc[n,ch]*c + k0[n,ch]; coef is (n, ch, 4) = (ka,kb,kc,k0). */
@@ -99,7 +102,7 @@ int cn_chan_affine(const float* a, const float* b, const float* c, const float* 
  *  5 style bwd-bwd sums(a,h) p0=gstyle     -> coef0 (d/da), out0 = d/dgstyle (n,2ch)
  *  6 AdaIN fwd   sums(a) p0=sb (n,2ch)     -> coef0
  *  7 AdaIN bwd   sums(a,gy) p0=sb          -> coef0, out0 = dsb (n,2ch)                         */
-int cn_norm_coef(int kind, const float* sums, const float* p0, const float* p1, int n, int ch,
+int cn_norm_coef(int kind, const float* sums, int nsplit, const float* p0, const float* p1, int n, int ch,
                  int npix, float eps, float* coef0, float* coef1, float* out0, float* out1,
                  void* stream);
 
