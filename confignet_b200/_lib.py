@@ -55,6 +55,9 @@ SIGNATURES = {
     "cn_chan_sums": [_V, _V, _V, _I, _I, _I, _I, _f, _V, _V],
     "cn_chan_affine": [_V, _V, _V, _V, _I, _I, _I, _I, _f, _V, _V],
     "cn_chan_sums_splits": [_I, _I, _I],
+    "cn_register_params": [_V, ctypes.c_size_t],
+    "cn_unregister_params": [_V],
+    "cn_weights_changed": [],
     "cn_norm_coef": [_I, _V, _I, _V, _V, _I, _I, _I, _f, _V, _V, _V, _V, _V],
     "cn_lrelu_fwd": [_V, _f, _V, _L, _V],
     "cn_act_bwd": [_V, _V, _I, _f, _V, _L, _V],
@@ -109,6 +112,15 @@ def load():
         if not hasattr(lib, name) and os.environ.get("CN_ALLOW_PARTIAL") == "1":
             continue
         getattr(lib, name).restype = restype
+    if os.environ.get("CN_CHUNK_KB"):          # measurement knob: k-blocks per tensor-core accumulation chunk
+        lib.cn_debug_set_chunk(int(os.environ["CN_CHUNK_KB"]))
+    if os.environ.get("CN_FOLD"):               # "fold,s2all" e.g. "0,1": folded upsample+conv plans / merged stride-2 dgrad phases
+        a, b = (os.environ["CN_FOLD"].split(",") + ["1"])[:2]
+        lib.cn_debug_set_fold(int(a), int(b))
+    if os.environ.get("CN_WCACHE"):
+        lib.cn_debug_set_wcache(int(os.environ["CN_WCACHE"]))
+    if os.environ.get("CN_CLUSTER"):
+        lib.cn_debug_set_cluster(int(os.environ["CN_CLUSTER"]))
     _lib = lib
     return lib
 

@@ -7,6 +7,7 @@
 #include "../../include/confignet_b200.h"
 
 void cn_set_error(const char* fmt, ...);
+extern unsigned long long g_cn_weight_epoch;  // see error.cu
 extern unsigned long long g_cn_launches;     // kernels launched by this library (bench.py reports it)
 
 #define CN_CHECK_CUDA(expr)                                                            \
@@ -54,7 +55,32 @@ struct GemmPlan {
   int Ktot;         // ntaps*Csrc
   int wsc, wsn;     // weight element strides for the source-channel and N index
   const int2* taps; // device: {packed (off_d+8) in 10-bit fields, weight base offset}
+  // Phased plans (nphase > 1): several GEMMs that share everything but their tap list and output offset run
+  // in ONE launch, blockIdx.y = phase * n_tiles + n_tile.  Used by the sub-pixel phases of the folded
+  // upsample+conv forward and by the parity phases of the stride-2 input gradient.
+  int nphase;
+  int kb_stride;    // k-blocks per (phase, n-tile) slot of the packed-weight buffer (max over phases)
+  int ph_ntaps[8];  // taps of phase ph are taps[ph_tap0[ph] .. ph_tap0[ph] + ph_ntaps[ph])
+  int ph_tap0[8];
+  int ph_ooff[8];   // ooff bits of the phase: bit d = ooff[d]
 };
+
+// Select the phase of a phased plan from blockIdx.y; returns the n-tile index.  (Select chains instead of
+// indexed reads: a dynamically indexed kernel parameter would be copied to local memory.)
+__device__ __forceinline__ int cn_select_phase(GemmPlan& p, int by, int grid_y) {
+  if (p.nphase <= 1) return by;
+  const int ntn = grid_y / p.nphase;
+  const int ph = by / ntn;
+  int tap0 = 0, nt = 0, bits = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i == ph) { tap0 = p.ph_tap0[i]; nt = p.ph_ntaps[i]; bits = p.ph_ooff[i]; }
+  p.taps += tap0;
+  p.ntaps = nt;
+  p.Ktot = nt * p.Csrc;
+  p.ooff[0] = bits & 1; p.ooff[1] = (bits >> 1) & 1; p.ooff[2] = (bits >> 2) & 1;
+  return by - ph * ntn;
+}
 
 __device__ __forceinline__ float cn_apply_act(float v, int act, float alpha) {
   if (act == CN_ACT_LRELU) return v >= 0.f ? v : v * alpha;

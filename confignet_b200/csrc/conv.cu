@@ -20,6 +20,7 @@
 #include <string>
 #include <vector>
 #include <mutex>
+#include <algorithm>
 #include <string.h>
 
 // ------------------------------------------------------------------------------------------------
@@ -174,6 +175,264 @@ static int get_plan(const cn_conv_desc* d, int kind, int phase, GemmPlan* out) {
   g_plans[key] = hp;
   *out = g;
   return CN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Folded plans: nearest x2 upsample followed by a k-tap SAME conv, evaluated on the LOW-resolution tensor
+// (hard part 5).  Per axis, output o = 2R+d reads upsampled u = o + t - pb, i.e. source
+// R + floor((d + t - pb)/2): the taps t that land on the same source pixel are pre-summed.
+//   forward : 2^nd sub-pixel phases (d per axis), each a conv with 2 (k3) or 3|2 (k4) taps per axis on the
+//             low-resolution input, written at stride 2 - ONE phased launch.  27 -> 8 taps (3-D k3), 16 -> 6.25 (2-D k4).
+//   dgrad   : gx[r] = sum_l gy[2r + l] . Wd[l],  l = pb-(k-1) .. pb+1 per axis, Wd[l] = sum of the taps
+//             t in [pb-l, pb-l+1]: one pixel-mode GEMM with (k+1)^nd taps instead of 2^nd * k^nd.
+//   wgrad   : gWd[l] = sum_r gy[2r + l] (x) x[r] with the dgrad plan (gy gathered, x dense), then
+//             gw[t] = sum of the gWd[l] whose tap set contains t.
+// A fold spec packs, per folded tap, the [lo, hi] tap range of each axis (3 bits each).
+// ------------------------------------------------------------------------------------------------
+enum { KIND_FWD_FOLD = 2, KIND_DGRAD_FOLD = 3, KIND_DGRAD_S2ALL = 4 };
+
+struct FoldInfo {
+  std::vector<int> spec;          // per folded tap
+  std::vector<int> unfold;        // [kvol][8] folded-tap indices containing original tap t (-1 = none)
+  int* d_spec = nullptr;
+  int* d_unfold = nullptr;
+  int nfold = 0;
+};
+static std::map<std::string, FoldInfo> g_folds;
+
+__host__ __device__ __forceinline__ void fold_decode(int sp, int lo[3], int hi[3]) {
+  lo[0] = sp & 7; hi[0] = (sp >> 3) & 7; lo[1] = (sp >> 6) & 7; hi[1] = (sp >> 9) & 7; lo[2] = (sp >> 12) & 7; hi[2] = (sp >> 15) & 7;
+}
+static int fold_encode(const int lo[3], const int hi[3]) {
+  return lo[0] | (hi[0] << 3) | (lo[1] << 6) | (hi[1] << 9) | (lo[2] << 12) | (hi[2] << 15);
+}
+static inline int floordiv2(int v) { return (v >= 0) ? v / 2 : -((-v + 1) / 2); }
+
+static bool fold_ok(const cn_conv_desc* d) {
+  if (d->upsample != 2 || d->stride != 1 || d->pad >= 0 || (d->nd != 2 && d->nd != 3)) return false;
+  for (int i = 0; i < d->nd; ++i) if (d->ksize[i] < 2 || d->ksize[i] > 5) return false;
+  return true;
+}
+
+struct AxisOpt { int off, lo, hi; };   // source offset (forward) or gradient offset l (dgrad), tap range
+
+static int build_fold_plan(const cn_conv_desc* d, int kind, GemmPlan* out, std::vector<int2>& taps, FoldInfo* fi) {
+  int U[3], O[3], pb[3];
+  same_geometry(d, U, O, pb);
+  GemmPlan g;
+  memset(&g, 0, sizeof(g));
+  g.n_img = d->batch;
+  taps.clear();
+  fi->spec.clear();
+  const int cc = d->cin * d->cout;
+  if (kind == KIND_FWD_FOLD) {
+    for (int i = 0; i < 3; ++i) {
+      g.E[i] = d->in_dims[i]; g.U[i] = d->in_dims[i]; g.S[i] = d->in_dims[i]; g.Q[i] = O[i]; g.ooff[i] = 0;
+    }
+    g.mstride = 1; g.ushift = 0; g.ostride = 2;
+    g.Csrc = d->cin; g.Cn = d->cout; g.wsc = d->cout; g.wsn = 1;
+    const int nph = 1 << d->nd;
+    struct Ph { int bits; std::vector<int2> taps; std::vector<int> spec; };
+    std::vector<Ph> phases;
+    for (int ph = 0; ph < nph; ++ph) {
+      std::vector<AxisOpt> opt[3];
+      for (int a = 0; a < 3; ++a) {
+        if (a >= d->nd) { opt[a].push_back({0, 0, 0}); continue; }
+        const int dd = (ph >> a) & 1;
+        for (int t = 0; t < d->ksize[a]; ++t) {
+          const int so = floordiv2(dd + t - pb[a]);
+          if (!opt[a].empty() && opt[a].back().off == so) opt[a].back().hi = t;
+          else opt[a].push_back({so, t, t});
+        }
+      }
+      Ph P; P.bits = ph;
+      for (auto& a0 : opt[0]) for (auto& a1 : opt[1]) for (auto& a2 : opt[2]) {
+        int off[3] = {a0.off, a1.off, a2.off}, lo[3] = {a0.lo, a1.lo, a2.lo}, hi[3] = {a0.hi, a1.hi, a2.hi};
+        P.taps.push_back(make_int2(pack_off(off), 0));
+        P.spec.push_back(fold_encode(lo, hi));
+      }
+      phases.push_back(P);
+    }
+    // longest phases first: CTAs are dispatched in blockIdx order
+    std::stable_sort(phases.begin(), phases.end(), [](const Ph& a, const Ph& b) { return a.taps.size() > b.taps.size(); });
+    g.nphase = nph;
+    int maxt = 0;
+    for (int ph = 0; ph < nph; ++ph) {
+      g.ph_tap0[ph] = (int)taps.size(); g.ph_ntaps[ph] = (int)phases[ph].taps.size(); g.ph_ooff[ph] = phases[ph].bits;
+      if (g.ph_ntaps[ph] > maxt) maxt = g.ph_ntaps[ph];
+      for (size_t i = 0; i < phases[ph].taps.size(); ++i) {
+        int2 t = phases[ph].taps[i];
+        t.y = (int)fi->spec.size() * cc;
+        taps.push_back(t);
+        fi->spec.push_back(phases[ph].spec[i]);
+      }
+    }
+    g.ntaps = maxt;
+  } else {   // KIND_DGRAD_FOLD: rows = low-resolution x pixels, source = gy at 2r + l
+    for (int i = 0; i < 3; ++i) {
+      g.E[i] = d->in_dims[i]; g.U[i] = O[i]; g.S[i] = O[i]; g.Q[i] = d->in_dims[i]; g.ooff[i] = 0;
+    }
+    g.mstride = 2; g.ushift = 0; g.ostride = 1;
+    g.Csrc = d->cout; g.Cn = d->cin; g.wsc = 1; g.wsn = d->cout;
+    std::vector<AxisOpt> opt[3];
+    for (int a = 0; a < 3; ++a) {
+      if (a >= d->nd) { opt[a].push_back({0, 0, 0}); continue; }
+      for (int l = pb[a] - (d->ksize[a] - 1); l <= pb[a] + 1; ++l) {
+        int lo = pb[a] - l, hi = pb[a] - l + 1;
+        if (lo < 0) lo = 0;
+        if (hi > d->ksize[a] - 1) hi = d->ksize[a] - 1;
+        if (lo <= hi) opt[a].push_back({l, lo, hi});
+      }
+    }
+    for (auto& a0 : opt[0]) for (auto& a1 : opt[1]) for (auto& a2 : opt[2]) {
+      int off[3] = {a0.off, a1.off, a2.off}, lo[3] = {a0.lo, a1.lo, a2.lo}, hi[3] = {a0.hi, a1.hi, a2.hi};
+      taps.push_back(make_int2(pack_off(off), (int)fi->spec.size() * cc));
+      fi->spec.push_back(fold_encode(lo, hi));
+    }
+    g.ntaps = (int)taps.size();
+    g.nphase = 1;
+    // unfold lists: original tap t -> the folded taps whose ranges contain it
+    const int kvol = d->ksize[0] * d->ksize[1] * d->ksize[2];
+    fi->unfold.assign((size_t)kvol * 8, -1);
+    for (int t = 0; t < kvol; ++t) {
+      int tt[3] = {t / (d->ksize[2] * d->ksize[1]), (t / d->ksize[2]) % d->ksize[1], t % d->ksize[2]};
+      int cnt = 0;
+      for (size_t f = 0; f < fi->spec.size(); ++f) {
+        int lo[3], hi[3]; fold_decode(fi->spec[f], lo, hi);
+        bool in = true;
+        for (int a = 0; a < 3; ++a) in = in && tt[a] >= lo[a] && tt[a] <= hi[a];
+        if (in) { CN_REQUIRE(cnt < 8, CN_ERR_UNSUPPORTED, "unfold list overflow"); fi->unfold[(size_t)t * 8 + cnt++] = (int)f; }
+      }
+    }
+  }
+  fi->nfold = (int)fi->spec.size();
+  CN_REQUIRE(taps.size() <= 256, CN_ERR_UNSUPPORTED, "too many folded taps (%d)", (int)taps.size());
+  for (size_t i = 0; i < taps.size(); ++i) {
+    int px = taps[i].x;
+    int o0 = (px & 1023), o1 = (px >> 10) & 1023, o2 = (px >> 20) & 1023;
+    CN_REQUIRE(o0 < 24 && o1 < 24 && o2 < 24, CN_ERR_UNSUPPORTED, "tap offset out of packed range");
+  }
+  g.Ktot = g.ntaps * g.Csrc;
+  g.kb_stride = (g.Ktot + 31) / 32;
+  long long M = (long long)g.n_img * g.E[0] * g.E[1] * g.E[2];
+  CN_REQUIRE(M < (1ll << 31), CN_ERR_UNSUPPORTED, "too many output rows");
+  g.M = (int)M;
+  CN_REQUIRE((long long)g.n_img * g.S[0] * g.S[1] * g.S[2] * g.Csrc < (1ll << 32) &&
+             (long long)g.n_img * g.Q[0] * g.Q[1] * g.Q[2] * g.Cn < (1ll << 32), CN_ERR_UNSUPPORTED, "tensor too large for 32-bit element offsets");
+  g.taps = nullptr;
+  *out = g;
+  return CN_OK;
+}
+
+// All parity phases of a stride-2 input gradient as one phased plan (even input dims, every phase has taps).
+static int build_s2all_plan(const cn_conv_desc* d, GemmPlan* out, std::vector<int2>& taps) {
+  const int nph = 1 << d->nd;
+  struct Ph { int bits; std::vector<int2> taps; };
+  std::vector<Ph> phases;
+  GemmPlan g0;
+  for (int ph = 0; ph < nph; ++ph) {
+    GemmPlan g; std::vector<int2> t;
+    int rc = build_plan(d, KIND_DGRAD, ph, &g, t); if (rc) return rc;
+    if (ph == 0) g0 = g;
+    CN_REQUIRE(!t.empty() && g.M == g0.M && g.E[0] == g0.E[0] && g.E[1] == g0.E[1] && g.E[2] == g0.E[2], CN_ERR_UNSUPPORTED,
+               "stride-2 phases are not uniform");
+    Ph P; P.bits = ph; P.taps = t;
+    phases.push_back(P);
+  }
+  std::stable_sort(phases.begin(), phases.end(), [](const Ph& a, const Ph& b) { return a.taps.size() > b.taps.size(); });
+  taps.clear();
+  GemmPlan g = g0;
+  g.nphase = nph;
+  int maxt = 0;
+  for (int ph = 0; ph < nph; ++ph) {
+    g.ph_tap0[ph] = (int)taps.size(); g.ph_ntaps[ph] = (int)phases[ph].taps.size(); g.ph_ooff[ph] = phases[ph].bits;
+    if (g.ph_ntaps[ph] > maxt) maxt = g.ph_ntaps[ph];
+    taps.insert(taps.end(), phases[ph].taps.begin(), phases[ph].taps.end());
+  }
+  CN_REQUIRE(taps.size() <= 256, CN_ERR_UNSUPPORTED, "too many taps");
+  g.ntaps = maxt; g.Ktot = maxt * g.Csrc; g.kb_stride = (g.Ktot + 31) / 32;
+  g.taps = nullptr;
+  *out = g;
+  return CN_OK;
+}
+
+static int get_special_plan(const cn_conv_desc* d, int kind, GemmPlan* out, FoldInfo** fold) {
+  std::string key((const char*)d, sizeof(*d));
+  key.push_back((char)kind);
+  key.push_back((char)0);
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  auto it = g_plans.find(key);
+  if (it != g_plans.end()) {
+    if (!it->second.valid) return CN_ERR_UNSUPPORTED;
+    *out = it->second.g;
+    if (fold) *fold = &g_folds[key];
+    return CN_OK;
+  }
+  GemmPlan g;
+  std::vector<int2> taps;
+  FoldInfo fi;
+  int rc = (kind == KIND_DGRAD_S2ALL) ? build_s2all_plan(d, &g, taps) : build_fold_plan(d, kind, &g, taps, &fi);
+  if (rc) { HostPlan hp; memset(&hp.g, 0, sizeof(hp.g)); hp.valid = false; g_plans[key] = hp; return rc; }
+  int2* dtaps = nullptr;
+  CN_CHECK_CUDA(cudaMalloc(&dtaps, taps.size() * sizeof(int2)));
+  CN_CHECK_CUDA(cudaMemcpy(dtaps, taps.data(), taps.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  g.taps = dtaps;
+  if (fi.nfold > 0) {
+    CN_CHECK_CUDA(cudaMalloc(&fi.d_spec, fi.spec.size() * sizeof(int)));
+    CN_CHECK_CUDA(cudaMemcpy(fi.d_spec, fi.spec.data(), fi.spec.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!fi.unfold.empty()) {
+      CN_CHECK_CUDA(cudaMalloc(&fi.d_unfold, fi.unfold.size() * sizeof(int)));
+      CN_CHECK_CUDA(cudaMemcpy(fi.d_unfold, fi.unfold.data(), fi.unfold.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+  }
+  g_folds[key] = fi;
+  HostPlan hp; hp.g = g; hp.valid = true;
+  g_plans[key] = hp;
+  *out = g;
+  if (fold) *fold = &g_folds[key];
+  return CN_OK;
+}
+
+// Wf[f][ci][co] = sum of w[t][ci][co] over the tap box of folded tap f.  grid (ceil(cc/4/256), nfold)
+__global__ void __launch_bounds__(256)
+fold_weights_kernel(const float* __restrict__ w, const int* __restrict__ spec, int k1, int k2, int cc4, float* __restrict__ out) {
+  const int f = blockIdx.y;
+  int lo[3], hi[3];
+  fold_decode(spec[f], lo, hi);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= cc4) return;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t0 = lo[0]; t0 <= hi[0]; ++t0)
+    for (int t1 = lo[1]; t1 <= hi[1]; ++t1)
+      for (int t2 = lo[2]; t2 <= hi[2]; ++t2) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(w) + (size_t)((t0 * k1 + t1) * k2 + t2) * cc4 + i);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+  reinterpret_cast<float4*>(out)[(size_t)f * cc4 + i] = a;
+}
+
+// gw[t][ci][co] = sum_{f in unfold[t]} Dp[(f*cout + co)*cin + ci]   (32x32 transpose tiles; grid (cin/32, cout/32, kvol), block (32, 8))
+__global__ void unfold_wgrad_kernel(const float* __restrict__ Dp, const int* __restrict__ unfold, int cin, int cout, float* __restrict__ gw) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z, ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  int fl[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) fl[j] = unfold[t * 8 + j];
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    float a = 0.f;
+    if (co < cout && ci < cin) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (fl[j] >= 0) a += Dp[((size_t)fl[j] * cout + co) * cin + ci];
+    }
+    tile[r][threadIdx.x] = a;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    if (ci < cin && co < cout) gw[((size_t)t * cin + ci) * cout + co] = tile[threadIdx.x][r];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -457,7 +716,7 @@ __device__ __forceinline__ uint32_t mn_chunk_off(int r, int jn, uint32_t sbo) {
 
 constexpr int TC_BM = 128;        // GEMM rows per CTA (UMMA M)
 constexpr int TC_BK = 32;         // K elements per stage = one 128-byte swizzle row of tf32
-constexpr int TC_CHUNK_KB = 16;   // k-blocks (512 K elements) accumulated in the tensor core before promotion
+constexpr int TC_CHUNK_KB = 8;    // k-blocks (256 K elements) accumulated in the tensor core before promotion
 
 // The tensor core adds into its fp32 accumulator with truncation: measured on B200 the result drifts by
 // ~1.1e-8 * K relative (1.2e-4 at K = 18432), a bias that plain fp32 FMAs do not have.  So the MMA warp
@@ -500,14 +759,17 @@ __device__ __forceinline__ void tc_promote_smem_and_store(uint32_t tmem_base, fl
 // once per M-tile.  grid = (k-blocks, n-tiles), 256 threads.
 template <int B_MN>
 __global__ void __launch_bounds__(256)
-pack_weights_kernel(GemmPlan p, const float* __restrict__ W, float* __restrict__ out, int bn, int bn_smem, int total_kb) {
+pack_weights_kernel(const GemmPlan pin, const float* __restrict__ W, float* __restrict__ out, int bn, int bn_smem, int total_kb) {
   __shared__ int2 s_taps[256];
+  GemmPlan p = pin;
+  const int ntile = cn_select_phase(p, blockIdx.y, gridDim.y);     // total_kb = slot stride of the buffer
+  if ((int)blockIdx.x * TC_BK >= p.Ktot) return;                    // beyond this phase's K: the slot is never read
   for (int i = threadIdx.x; i < p.ntaps; i += 256) s_taps[i] = p.taps[i];
   __syncthreads();
   const int kb = blockIdx.x, nt = blockIdx.y;
   const uint32_t b_bytes = (uint32_t)bn_smem * TC_BK * 4;
   uint8_t* tile = reinterpret_cast<uint8_t*>(out) + ((size_t)nt * total_kb + kb) * 2 * b_bytes;
-  const int n0 = nt * bn, k0 = kb * TC_BK;
+  const int n0 = ntile * bn, k0 = kb * TC_BK;
   const int nchunks = 8 * bn_smem;
   const uint32_t sbo = (uint32_t)(bn_smem >> 5) * 512u;
   for (int q = threadIdx.x; q < nchunks; q += 256) {
@@ -696,12 +958,14 @@ __device__ __forceinline__ void wg_load(const WgGeom& p, const float* __restrict
 // by pack_grad_kernel (MN-major, as it lies in HBM).
 template <int B_MN, int WG>
 __global__ void __launch_bounds__(TCP_THREADS)
-igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ Wp,
+igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const float* __restrict__ Wp,
                       const float* __restrict__ bias, float* __restrict__ D, int act, float alpha,
                       int bn, int bn_smem, int nb, int tmem_cols, int kb_per_split, int use_atomic,
                       int csize, int dbg, long long* prof) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  GemmPlan p = pin;
+  const int ntile = cn_select_phase(p, blockIdx.y, gridDim.y);
   const bool do_prof = prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   long long pt[6] = {0, 0, 0, 0, 0, 0};
   const long long t_begin = clock64();
@@ -716,8 +980,9 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_off);
   int2* s_taps = reinterpret_cast<int2*>(smem + L.taps_off);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * bn;
+  const int m0 = blockIdx.x * TC_BM, n0 = ntile * bn;
   const int total_kb = ((WG ? p.M : p.Ktot) + TC_BK - 1) / TC_BK;
+  const int kb_stride = pin.nphase > 1 ? pin.kb_stride : total_kb;   // slot stride of the packed B buffer
   const int kb_beg = blockIdx.z * kb_per_split;             // split-K over gridDim.z (atomic epilogue)
   const int num_kb = min(total_kb, kb_beg + kb_per_split) - kb_beg;   // host guarantees >= 1
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
@@ -874,7 +1139,8 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
     const int m = m0 + pw * 32 + lane;
     const bool mok = m < (WG ? p.Ktot : p.M);
     const size_t rowoff = mok ? (WG ? (size_t)m : (size_t)dest_pixel(p, m)) * p.Cn : 0;
-    const int nchunks = (num_kb + TC_CHUNK_KB - 1) / TC_CHUNK_KB;
+    const int chunk_kb = (dbg >> 8) ? (dbg >> 8) : TC_CHUNK_KB;
+    const int nchunks = (num_kb + chunk_kb - 1) / chunk_kb;
     tc_promote_smem_and_store(tmem_base, reinterpret_cast<float*>(smem + L.tot_off), pw, bn, bn_r, nchunks, bar_accfull, bar_accempty,
                               [&](int cb, const uint32_t* v) {
       if (mok && !(dbg & 16)) {
@@ -886,6 +1152,7 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
             o.x = __uint_as_float(v[q]); o.y = __uint_as_float(v[q + 1]);
             o.z = __uint_as_float(v[q + 2]); o.w = __uint_as_float(v[q + 3]);
             if (use_atomic) {
+              if (bias != nullptr && blockIdx.z == 0) { o.x += bias[n]; o.y += bias[n + 1]; o.z += bias[n + 2]; o.w += bias[n + 3]; }
               atomicAdd(D + rowoff + n, o.x); atomicAdd(D + rowoff + n + 1, o.y);
               atomicAdd(D + rowoff + n + 2, o.z); atomicAdd(D + rowoff + n + 3, o.w);
               continue;
@@ -905,7 +1172,7 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
       const uint32_t bytes = L.stage_bytes;
       const uint32_t slice = bytes / (uint32_t)csize;
       const uint32_t rank = csize > 1 ? cluster_ctarank() : 0u;
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(Wp) + ((size_t)blockIdx.y * total_kb + kb_beg) * bytes + rank * slice;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(Wp) + ((size_t)blockIdx.y * kb_stride + kb_beg) * bytes + rank * slice;
       int s = 0, ph = 1;
       for (int it = 0; it < num_kb; ++it) {
         { const long long t0 = clock64(); if (it >= nb) mbar_wait(bar_emptyb + 8 * s, ph); pt[0] += clock64() - t0; }
@@ -928,10 +1195,11 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
     const uint32_t desc_lo0 = ((lbo_b >> 4) & 0x3fffu) << 16;
     const uint32_t stage16 = L.stage_bytes >> 4, plane16 = L.b_bytes >> 4, kk16 = (B_MN ? 2 * sbo_b : 32u) >> 4;
     int sa = 0, pa = 0, sb = 0, pb = 0, b = 0, inchunk = 0, c = 0;
+    const int chunk_kb = (dbg >> 8) ? (dbg >> 8) : TC_CHUNK_KB;
     uint32_t b16 = sbase >> 4;
     for (int kb = 0; kb < num_kb; ++kb) {
       const bool chunk_first = inchunk == 0;
-      const bool chunk_last = inchunk == TC_CHUNK_KB - 1 || kb == num_kb - 1;
+      const bool chunk_last = inchunk == chunk_kb - 1 || kb == num_kb - 1;
       long long t0 = clock64();
       if (chunk_first && c >= 2) { mbar_wait(bar_accempty + 8 * b, ((c >> 1) - 1) & 1); }
       long long t1 = clock64(); pt[0] += t1 - t0;
@@ -961,7 +1229,7 @@ igemm_tc_pixel_kernel(GemmPlan p, const float* __restrict__ A, const float* __re
       if (++sa == na) { sa = 0; pa ^= 1; }
       b16 += stage16;
       if (++sb == nb) { sb = 0; pb ^= 1; b16 = sbase >> 4; }
-      if (++inchunk == TC_CHUNK_KB) { inchunk = 0; ++c; b ^= 1; }
+      if (++inchunk == chunk_kb) { inchunk = 0; ++c; b ^= 1; }
       pt[3] += clock64() - t1;
     }
     if (do_prof && lane == 0) { prof[4] = pt[0]; prof[5] = pt[1]; prof[6] = pt[2]; prof[7] = pt[3]; prof[8] = clock64() - t_begin; prof[9] = num_kb; }
@@ -1381,6 +1649,11 @@ static long long* g_prof = nullptr;   // TEST HOOK: device buffer (16 x int64) r
 extern "C" int cn_debug_set_prof(void* p) { g_prof = (long long*)p; return CN_OK; }
 static int g_dbg = 0;   // TEST HOOK (cn_debug_set): bit 0/1 skip A/B global loads, bit 2 skip MMA issue, bit 3 skip STS
 extern "C" int cn_debug_set(int v) { g_dbg = v; return CN_OK; }
+static int g_fold = 1;     // folded upsample+conv plans (cn_debug_set_fold)
+static int g_s2all = 1;    // all parity phases of a stride-2 dgrad in one launch
+extern "C" int cn_debug_set_fold(int fold, int s2all) { g_fold = fold; g_s2all = s2all; return CN_OK; }
+static int g_chunk_kb = 0;   // k-blocks per tensor-core accumulation chunk (0 = TC_CHUNK_KB); cn_debug_set_chunk
+extern "C" int cn_debug_set_chunk(int v) { g_chunk_kb = (v >= 1 && v <= 64) ? v : 0; return CN_OK; }
 static thread_local int g_last_impl = 0;     // 1 = CUDA-core, 2 = tcgen05: what the last conv call on this thread ran
 extern "C" int cn_last_conv_impl(void) { return g_last_impl; }
 static int g_num_sms = 0;
@@ -1425,6 +1698,66 @@ static std::map<const void*, std::pair<float*, size_t>> g_wpack;    // per plan 
 static float* g_gpack = nullptr;       // packed-gradient workspace of the wgrad GEMM (grow-only; launches on one stream serialise)
 static size_t g_gpack_bytes = 0;
 
+// Registered parameter buffers (ParamGroup flat buffers): their packed stage images are cached per (plan, weight
+// pointer) and reused until the parameter epoch changes - VGG19's frozen weights are packed once, a discriminator
+// kernel once per optimizer step instead of once per conv call.
+struct ParamRange { const char* lo; const char* hi; };
+static std::vector<ParamRange> g_param_ranges;
+struct PackedEntry { float* buf; size_t bytes; unsigned long long epoch; };
+static std::map<std::pair<const void*, const void*>, PackedEntry> g_wcache;
+
+static void drop_wcache_locked() {
+  if (g_wcache.empty()) return;
+  cudaDeviceSynchronize();
+  for (auto& kv : g_wcache) cudaFree(kv.second.buf);
+  g_wcache.clear();
+}
+extern "C" int cn_register_params(const void* p, size_t bytes) {
+  CN_REQUIRE(p != nullptr && bytes > 0, CN_ERR_BAD_SHAPE, "cn_register_params: bad range");
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  for (auto& r : g_param_ranges) if (r.lo == (const char*)p) { r.hi = r.lo + bytes; ++g_cn_weight_epoch; drop_wcache_locked(); return CN_OK; }
+  g_param_ranges.push_back({(const char*)p, (const char*)p + bytes});
+  ++g_cn_weight_epoch;           // a new buffer may reuse the address of a dead one
+  drop_wcache_locked();
+  return CN_OK;
+}
+extern "C" int cn_unregister_params(const void* p) {
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  for (size_t i = 0; i < g_param_ranges.size(); ++i)
+    if (g_param_ranges[i].lo == (const char*)p) { g_param_ranges.erase(g_param_ranges.begin() + i); break; }
+  ++g_cn_weight_epoch;
+  drop_wcache_locked();
+  return CN_OK;
+}
+static bool is_registered_param(const void* w) {
+  for (auto& r : g_param_ranges) if ((const char*)w >= r.lo && (const char*)w < r.hi) return true;
+  return false;
+}
+static bool g_wcache_on = true;
+extern "C" int cn_debug_set_wcache(int on) { g_wcache_on = on != 0; return CN_OK; }
+// -> *hit: the cached image is current (skip the pack).  Otherwise the caller packs into *out on the launch stream.
+static int cached_packed(const void* plan_key, const void* w, size_t bytes, float** out, bool* hit) {
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  auto key = std::make_pair(plan_key, w);
+  auto it = g_wcache.find(key);
+  if (it == g_wcache.end() || it->second.bytes < bytes) {
+    if (it != g_wcache.end()) { CN_CHECK_CUDA(cudaDeviceSynchronize()); cudaFree(it->second.buf); g_wcache.erase(it); }
+    PackedEntry e; e.bytes = bytes; e.epoch = 0; e.buf = nullptr;
+    CN_CHECK_CUDA(cudaMalloc(&e.buf, bytes));
+    it = g_wcache.insert(std::make_pair(key, e)).first;
+  }
+  *hit = it->second.epoch == g_cn_weight_epoch;
+  it->second.epoch = g_cn_weight_epoch;
+  *out = it->second.buf;
+  return CN_OK;
+}
+static bool packed_is_current(const void* plan_key, const void* w) {
+  if (!g_wcache_on || !is_registered_param(w)) return false;
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  auto it = g_wcache.find(std::make_pair(plan_key, w));
+  return it != g_wcache.end() && it->second.epoch == g_cn_weight_epoch;
+}
+
 static int packed_buffer(const void* key, size_t bytes, float** out) {
   std::lock_guard<std::mutex> lock(g_plan_mutex);
   if (key == nullptr) {
@@ -1447,6 +1780,21 @@ static int packed_buffer(const void* key, size_t bytes, float** out) {
     *out = it->second.first;
   }
   return CN_OK;
+}
+
+// Split-K factor for `tiles` output tiles of `total_kb` k-blocks: minimise waves x (k-blocks per CTA + fixed
+// per-CTA cost), i.e. fill whole waves of SMs without shredding K.  OVH ~ prologue + epilogue in k-block units.
+static int pick_split(int tiles, int total_kb, int maxsplit) {
+  const int sms = num_sms(), OVH = 6;
+  int best = 1; long long best_cost = -1;
+  int cap = (4 * sms + tiles - 1) / tiles;
+  if (cap > maxsplit) cap = maxsplit;
+  for (int s = 1; s <= cap; ++s) {
+    const long long waves = ((long long)tiles * s + sms - 1) / sms;
+    const long long cost = waves * ((total_kb + s - 1) / s + OVH + (s > 1 ? 1 : 0));
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
 }
 
 // B stages fill the shared memory (A lives in tensor memory); >113 KB also keeps it at one CTA per SM, which
@@ -1478,7 +1826,7 @@ static int launch_tc(const GemmPlan& g, const float* src, const float* packed, c
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (set_smem(igemm_tc_pixel_kernel<B_MN, WG>, smem)) return CN_ERR_CUDA;
   CN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc_pixel_kernel<B_MN, WG>, g, src, packed, bias, dst, act, alpha, bn, bn_smem,
-                                   nb, 512, per, (int)(split > 1), csize, g_dbg, g_prof));
+                                   nb, 512, per, (int)(split > 1), csize, (g_dbg & 0xff) | (g_chunk_kb << 8), g_prof));
   CN_CHECK_LAUNCH();
   return CN_OK;
 }
@@ -1486,7 +1834,8 @@ static int launch_tc(const GemmPlan& g, const float* src, const float* packed, c
 // zero_mode: 0 = this launch covers all of dst and may zero it for a split-K run, 1 = dst was zeroed by the
 // caller (phased dgrad), 2 = no split-K allowed
 static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const float* w, const float* bias,
-                        float* dst, int act, float alpha, int impl, cudaStream_t st, int zero_mode = 0) {
+                        float* dst, int act, float alpha, int impl, cudaStream_t st, int zero_mode = 0,
+                        const float* w_ident = nullptr) {
   if (g.M == 0) return CN_OK;
   bool tc = tc_pixel_eligible(g, b_mn);
   CN_REQUIRE(!(impl == CN_IMPL_TC && !tc), CN_ERR_UNSUPPORTED, "shape not eligible for the tcgen05 kernel");
@@ -1495,13 +1844,12 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
   if (tc) {
     int bn, bn_smem;
     if (b_mn) pick_bn_mn(g.Cn, &bn, &bn_smem); else pick_bn_k(g.Cn, &bn, &bn_smem);
-    dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.Cn + bn - 1) / bn, 1);
-    const int total_kb = (g.Ktot + TC_BK - 1) / TC_BK;
+    const int nph = g.nphase > 1 ? g.nphase : 1;
+    dim3 grid((g.M + TC_BM - 1) / TC_BM, ((g.Cn + bn - 1) / bn) * nph, 1);
+    const int total_kb = (g.Ktot + TC_BK - 1) / TC_BK;      // phased plans: Ktot is the longest phase (= kb_stride)
     int per = total_kb, split = 1;
-    if (act == CN_ACT_NONE && bias == nullptr && zero_mode != 2 && (int)(grid.x * grid.y) < num_sms() && total_kb >= 32) {
-      split = (2 * num_sms() + grid.x * grid.y - 1) / (grid.x * grid.y);
-      if (split > total_kb / 16) split = total_kb / 16;
-      if (split < 1) split = 1;
+    if (nph == 1 && act == CN_ACT_NONE && zero_mode != 2 && (int)(grid.x * grid.y) < 4 * num_sms() && total_kb >= 32) {
+      split = pick_split((int)(grid.x * grid.y), total_kb, total_kb / 16);     // split 0 adds the bias
       per = (total_kb + split - 1) / split;
       split = (total_kb + per - 1) / per;
       if (split > 1 && zero_mode == 0)
@@ -1509,12 +1857,19 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
     }
     // pre-pack the weights into per-(n-tile, k-block) stage images (buffer cached per plan)
     float* wp = nullptr;
-    int rc = packed_buffer((const void*)g.taps, (size_t)grid.y * total_kb * 2 * bn_smem * TC_BK * 4, &wp);
+    bool hit = false;
+    const size_t pbytes = (size_t)grid.y * total_kb * 2 * bn_smem * TC_BK * 4;
+    const float* ident = w_ident ? w_ident : w;       // folded plans: identity = the original Keras kernel
+    int rc;
+    if (g_wcache_on && is_registered_param(ident)) rc = cached_packed((const void*)g.taps, ident, pbytes, &wp, &hit);
+    else rc = packed_buffer((const void*)g.taps, pbytes, &wp);
     if (rc) return rc;
-    dim3 pgrid(total_kb, grid.y);
-    if (b_mn) pack_weights_kernel<1><<<pgrid, 256, 0, st>>>(g, w, wp, bn, bn_smem, total_kb);
-    else pack_weights_kernel<0><<<pgrid, 256, 0, st>>>(g, w, wp, bn, bn_smem, total_kb);
-    CN_CHECK_LAUNCH();
+    if (!hit) {
+      dim3 pgrid(total_kb, grid.y);
+      if (b_mn) pack_weights_kernel<1><<<pgrid, 256, 0, st>>>(g, w, wp, bn, bn_smem, total_kb);
+      else pack_weights_kernel<0><<<pgrid, 256, 0, st>>>(g, w, wp, bn, bn_smem, total_kb);
+      CN_CHECK_LAUNCH();
+    }
     if (b_mn) return launch_tc<1, 0>(g, src, wp, bias, dst, act, alpha, bn, bn_smem, grid, per, split, st);
     return launch_tc<0, 0>(g, src, wp, bias, dst, act, alpha, bn, bn_smem, grid, per, split, st);
   }
@@ -1592,6 +1947,22 @@ extern "C" int cn_conv_fwd(const cn_conv_desc* d, const float* x, const float* w
     if (rc == 1) { g_last_impl = 1; return CN_OK; }
   }
   GemmPlan g;
+  if (impl != CN_IMPL_FFMA && g_fold && fold_ok(d)) {
+    // nearest x2 upsample + conv on the low-resolution tensor: sub-pixel phases with pre-summed taps
+    FoldInfo* fi = nullptr;
+    rc = get_special_plan(d, KIND_FWD_FOLD, &g, &fi);
+    if (rc == CN_OK && tc_pixel_eligible(g, true)) {
+      cudaStream_t st = (cudaStream_t)stream;
+      float* wf = nullptr;
+      const int cc = d->cin * d->cout;
+      if (!packed_is_current((const void*)g.taps, w)) {
+        rc = packed_buffer((const char*)g.taps + 1, (size_t)fi->nfold * cc * sizeof(float), &wf); if (rc) return rc;
+        fold_weights_kernel<<<dim3((cc / 4 + 255) / 256, fi->nfold), 256, 0, st>>>(w, fi->d_spec, d->ksize[1], d->ksize[2], cc / 4, wf);
+        CN_CHECK_LAUNCH();
+      }
+      return launch_pixel(g, true, x, wf, bias, y, act, alpha, CN_IMPL_TC, st, 2, w);
+    }
+  }
   rc = get_plan(d, KIND_FWD, 0, &g); if (rc) return rc;
   return launch_pixel(g, true, x, w, bias, y, act, alpha, impl, (cudaStream_t)stream);
 }
@@ -1605,6 +1976,27 @@ extern "C" int cn_conv_dgrad(const cn_conv_desc* d, const float* gy, const float
     rc = cn_skinny_dgrad(d, gy, w, gx, st);
     if (rc < 0) return rc;
     if (rc == 1) { g_last_impl = 1; return CN_OK; }
+  }
+  if (impl != CN_IMPL_FFMA && g_fold && fold_ok(d)) {
+    GemmPlan g; FoldInfo* fi = nullptr;
+    rc = get_special_plan(d, KIND_DGRAD_FOLD, &g, &fi);
+    if (rc == CN_OK && tc_pixel_eligible(g, false)) {
+      float* wf = nullptr;
+      const int cc = d->cin * d->cout;
+      if (!packed_is_current((const void*)g.taps, w)) {
+        rc = packed_buffer((const char*)g.taps + 1, (size_t)fi->nfold * cc * sizeof(float), &wf); if (rc) return rc;
+        fold_weights_kernel<<<dim3((cc / 4 + 255) / 256, fi->nfold), 256, 0, st>>>(w, fi->d_spec, d->ksize[1], d->ksize[2], cc / 4, wf);
+        CN_CHECK_LAUNCH();
+      }
+      return launch_pixel(g, false, gy, wf, nullptr, gx, CN_ACT_NONE, 0.f, CN_IMPL_TC, st, 0, w);
+    }
+  }
+  if (impl != CN_IMPL_FFMA && g_s2all && d->stride == 2 && d->nd >= 2) {
+    bool even = true;
+    for (int i = 0; i < d->nd; ++i) even = even && (d->in_dims[i] % 2 == 0) && d->ksize[i] >= 2;
+    GemmPlan g;
+    if (even && get_special_plan(d, KIND_DGRAD_S2ALL, &g, nullptr) == CN_OK && tc_pixel_eligible(g, false))
+      return launch_pixel(g, false, gy, w, nullptr, gx, CN_ACT_NONE, 0.f, CN_IMPL_TC, st, 2);   // one launch, all parity phases
   }
   const int nphase = (d->stride == 2) ? (1 << d->nd) : 1;
   int zero_mode = 0;
@@ -1626,6 +2018,32 @@ extern "C" int cn_conv_dgrad(const cn_conv_desc* d, const float* gy, const float
   return CN_OK;
 }
 
+static bool wgrad_tc_eligible(const GemmPlan& g) {
+  return g.M >= 256 && g.Csrc % 4 == 0 && g.Cn % 4 == 0 && g.Cn >= 16 && g.Ktot >= 64;
+}
+
+// Weight-gradient GEMM on the tensor cores: out[(tap,c)][n] = sum_m src[pix(m,tap)][c] * G[m][n]
+static int launch_wgrad_tc(const GemmPlan& g, const float* src, const float* G, float* out, cudaStream_t st) {
+  const size_t wn = (size_t)g.Ktot * g.Cn;
+  int bn, bn_smem; pick_bn_mn(g.Cn, &bn, &bn_smem);
+  int mt = (g.Ktot + TC_BM - 1) / TC_BM, nt = (g.Cn + bn - 1) / bn;
+  int total_kb = (g.M + TC_BK - 1) / TC_BK;
+  // split-K over the pixels so that the CTAs fill whole waves of SMs (each CTA keeps >= 8 k-blocks)
+  int mtc = (mt + g_cluster - 1) / g_cluster * g_cluster;
+  int maxsplit = total_kb / 8; if (maxsplit < 1) maxsplit = 1;
+  int split = pick_split(mtc * nt, total_kb, maxsplit);
+  int per = (total_kb + split - 1) / split;
+  split = (total_kb + per - 1) / per;
+  if (split > 1) CN_CHECK_CUDA(cudaMemsetAsync(out, 0, wn * sizeof(float), st));
+  // the gradient pre-split into per-(n-tile, k-block) stage images: every (tap,c)-tile CTA streams it
+  float* gp = nullptr;
+  int rc = packed_buffer(nullptr, (size_t)nt * total_kb * 2 * bn_smem * TC_BK * 4, &gp);
+  if (rc) return rc;
+  pack_grad_kernel<<<dim3(total_kb, nt), 256, 0, st>>>(G, g.M, g.Cn, gp, bn, bn_smem, total_kb);
+  CN_CHECK_LAUNCH();
+  return launch_tc<1, 1>(g, src, gp, nullptr, out, CN_ACT_NONE, 0.f, bn, bn_smem, dim3(mt, nt, 1), per, split, st);
+}
+
 extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float* gy, float* gw,
                              float* gbias, int impl, void* stream) {
   int rc = validate_desc(d); if (rc) return rc;
@@ -1645,28 +2063,28 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
     rc = cn_skinny_wgrad(d, x, gy, gw, ws, st);
     if (rc < 0) return rc;
   }
-  if (skinny_ws > 0 && rc == 1) {
+  bool folded = false;
+  if (skinny_ws == 0 && impl != CN_IMPL_FFMA && g_fold && fold_ok(d)) {
+    // folded weight gradient: gWd[l] = sum_r gy[2r+l] (x) x[r] on the low-resolution grid, then unfold to the k^nd taps
+    GemmPlan gf; FoldInfo* fi = nullptr;
+    int rf = get_special_plan(d, KIND_DGRAD_FOLD, &gf, &fi);
+    if (rf == CN_OK && wgrad_tc_eligible(gf)) {
+      float* dp = nullptr;
+      rc = packed_buffer((const char*)gf.taps + 2, (size_t)gf.Ktot * gf.Cn * sizeof(float), &dp); if (rc) return rc;
+      rc = launch_wgrad_tc(gf, gy, x, dp, st); if (rc) return rc;
+      const int kvol = d->ksize[0] * d->ksize[1] * d->ksize[2];
+      unfold_wgrad_kernel<<<dim3((d->cin + 31) / 32, (d->cout + 31) / 32, kvol), dim3(32, 8), 0, st>>>(dp, fi->d_unfold, d->cin, d->cout, gw);
+      CN_CHECK_LAUNCH();
+      folded = true;
+      g_last_impl = 2;
+    }
+  }
+  if (folded) {
+    // done above
+  } else if (skinny_ws > 0 && rc == 1) {
     // launched by skinny.cu
   } else if (tc) {
-    int bn, bn_smem; pick_bn_mn(g.Cn, &bn, &bn_smem);
-    int mt = (g.Ktot + TC_BM - 1) / TC_BM, nt = (g.Cn + bn - 1) / bn;
-    int total_kb = (g.M + TC_BK - 1) / TC_BK;
-    // split-K over the pixels so that the CTAs fill whole waves of SMs (each CTA keeps >= 8 k-blocks)
-    int mtc = (mt + g_cluster - 1) / g_cluster * g_cluster;
-    int split = (2 * num_sms()) / (mtc * nt);
-    int maxsplit = total_kb / 8; if (maxsplit < 1) maxsplit = 1;
-    if (split > maxsplit) split = maxsplit;
-    if (split < 1) split = 1;
-    int per = (total_kb + split - 1) / split;
-    split = (total_kb + per - 1) / per;
-    if (split > 1) CN_CHECK_CUDA(cudaMemsetAsync(gw, 0, wn * sizeof(float), st));
-    // the gradient pre-split into per-(n-tile, k-block) stage images: every (tap,c)-tile CTA streams it
-    float* gp = nullptr;
-    rc = packed_buffer(nullptr, (size_t)nt * total_kb * 2 * bn_smem * TC_BK * 4, &gp);
-    if (rc) return rc;
-    pack_grad_kernel<<<dim3(total_kb, nt), 256, 0, st>>>(gy, g.M, g.Cn, gp, bn, bn_smem, total_kb);
-    CN_CHECK_LAUNCH();
-    rc = launch_tc<1, 1>(g, x, gp, nullptr, gw, CN_ACT_NONE, 0.f, bn, bn_smem, dim3(mt, nt, 1), per, split, st);
+    rc = launch_wgrad_tc(g, x, gy, gw, st);
     if (rc) return rc;
   } else if (g.ntaps == 1 && g.Csrc <= 4 && g.Cn <= 4 && g.mstride == 1 && g.ushift == 0 && g.M >= 4096) {   // 1x1, stride 1: source pixel = output pixel
     CN_CHECK_CUDA(cudaMemsetAsync(gw, 0, wn * sizeof(float), st));
@@ -1732,8 +2150,82 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
 // that the kernels share, without a GPU.  Not used by any product path.
 // kind: 0 forward, 1 dgrad, 2 wgrad.  All pointers are HOST pointers here.
 // ------------------------------------------------------------------------------------------------
+// host evaluation of one (possibly phased) pixel-mode plan
+static void host_eval_pixel(const GemmPlan& p0, const std::vector<int2>& taps, const float* a, const float* b, float* out) {
+  const int nph = p0.nphase > 1 ? p0.nphase : 1;
+  for (int ph = 0; ph < nph; ++ph) {
+    GemmPlan p = p0;
+    int t0 = 0;
+    if (p0.nphase > 1) {
+      t0 = p0.ph_tap0[ph]; p.ntaps = p0.ph_ntaps[ph];
+      p.ooff[0] = p0.ph_ooff[ph] & 1; p.ooff[1] = (p0.ph_ooff[ph] >> 1) & 1; p.ooff[2] = (p0.ph_ooff[ph] >> 2) & 1;
+    }
+    for (int m = 0; m < p.M; ++m) {
+      RowInfo ri = decode_row(p, m);
+      size_t ro = (size_t)dest_pixel(p, m) * p.Cn;
+      for (int n = 0; n < p.Cn; ++n) {
+        double acc = 0;
+        for (int kt = 0; kt < p.ntaps; ++kt) {
+          uint32_t sp = src_pixel(p, ri, taps[t0 + kt].x);
+          if (sp == 0xffffffffu) continue;
+          for (int c = 0; c < p.Csrc; ++c)
+            acc += (double)a[(size_t)sp * p.Csrc + c] * b[(size_t)taps[t0 + kt].y + (size_t)c * p.wsc + (size_t)n * p.wsn];
+        }
+        out[ro + n] = (float)acc;
+      }
+    }
+  }
+}
+
+static void host_fold_weights(const cn_conv_desc* d, const FoldInfo& fi, const float* w, std::vector<float>& wf) {
+  const int cc = d->cin * d->cout;
+  wf.assign((size_t)fi.nfold * cc, 0.f);
+  for (int f = 0; f < fi.nfold; ++f) {
+    int lo[3], hi[3]; fold_decode(fi.spec[f], lo, hi);
+    for (int t0 = lo[0]; t0 <= hi[0]; ++t0) for (int t1 = lo[1]; t1 <= hi[1]; ++t1) for (int t2 = lo[2]; t2 <= hi[2]; ++t2)
+      for (int i = 0; i < cc; ++i) wf[(size_t)f * cc + i] += w[(size_t)((t0 * d->ksize[1] + t1) * d->ksize[2] + t2) * cc + i];
+  }
+}
+
+// kind: 0 forward, 1 dgrad (per-phase plans), 2 wgrad, 3 folded forward, 4 folded dgrad, 5 folded wgrad,
+//       6 stride-2 dgrad with all parity phases in one phased plan
 extern "C" int cn_debug_conv_host(const cn_conv_desc* d, int kind, const float* a, const float* b, float* out) {
   int rc = validate_desc(d); if (rc) return rc;
+  if (kind >= 3 && kind <= 5) {
+    CN_REQUIRE(fold_ok(d), CN_ERR_UNSUPPORTED, "descriptor has no folded form");
+    GemmPlan p; std::vector<int2> taps; FoldInfo fi;
+    rc = build_fold_plan(d, kind == 3 ? KIND_FWD_FOLD : KIND_DGRAD_FOLD, &p, taps, &fi); if (rc) return rc;
+    if (kind == 5) {       // a = x, b = gy -> out = gw
+      std::vector<double> dp((size_t)p.Ktot * p.Cn, 0.0);
+      for (int r = 0; r < p.Ktot; ++r) {
+        const int kt = r / p.Csrc, c = r % p.Csrc;
+        for (int m = 0; m < p.M; ++m) {
+          uint32_t sp = src_pixel(p, decode_row(p, m), taps[kt].x);
+          if (sp == 0xffffffffu) continue;
+          for (int n = 0; n < p.Cn; ++n) dp[(size_t)r * p.Cn + n] += (double)b[(size_t)sp * p.Csrc + c] * a[(size_t)m * p.Cn + n];
+        }
+      }
+      const int kvol = d->ksize[0] * d->ksize[1] * d->ksize[2];
+      for (int t = 0; t < kvol; ++t)
+        for (int ci = 0; ci < d->cin; ++ci)
+          for (int co = 0; co < d->cout; ++co) {
+            double acc = 0;
+            for (int j = 0; j < 8; ++j) { int f = fi.unfold[(size_t)t * 8 + j]; if (f >= 0) acc += dp[((size_t)f * d->cout + co) * d->cin + ci]; }
+            out[((size_t)t * d->cin + ci) * d->cout + co] = (float)acc;
+          }
+      return CN_OK;
+    }
+    std::vector<float> wf;
+    host_fold_weights(d, fi, b, wf);
+    host_eval_pixel(p, taps, a, wf.data(), out);
+    return CN_OK;
+  }
+  if (kind == 6) {
+    GemmPlan p; std::vector<int2> taps;
+    rc = build_s2all_plan(d, &p, taps); if (rc) return rc;
+    host_eval_pixel(p, taps, a, b, out);
+    return CN_OK;
+  }
   const int nphase = (kind == 1 && d->stride == 2) ? (1 << d->nd) : 1;
   for (int ph = 0; ph < nphase; ++ph) {
     GemmPlan p; std::vector<int2> taps;

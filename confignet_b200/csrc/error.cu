@@ -11,3 +11,7 @@ extern "C" long long cn_launch_count(int reset) {
   if (reset) g_cn_launches = 0;
   return v;
 }
+// Parameter epoch: bumped whenever a registered parameter buffer may have changed (optimizer / EMA kernels,
+// set_weights, registration).  conv.cu keeps the tensor-core stage images of registered weights until then.
+unsigned long long g_cn_weight_epoch = 1;
+extern "C" int cn_weights_changed(void) { ++g_cn_weight_epoch; return CN_OK; }

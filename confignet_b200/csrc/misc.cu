@@ -314,6 +314,7 @@ extern "C" int cn_adam_ema_step(float* p, const float* g, float* m, float* v, fl
                                 float b1, float b2, float eps, float ema_alpha, float gscale, void* stream) {
   if (n <= 0) return CN_OK;
   CN_REQUIRE(p && g && m && v, CN_ERR_BAD_SHAPE, "cn_adam_ema_step: null pointer");
+  ++g_cn_weight_epoch;
   adam_ema_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, (size_t)n, lr_t, b1, b2, eps, ema_alpha, gscale);
   CN_CHECK_LAUNCH(); return CN_OK;
 }
@@ -323,6 +324,7 @@ __global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ p,
     ema[i] = alpha * ema[i] + (1.f - alpha) * p[i];
 }
 extern "C" int cn_ema(float* ema, const float* p, int64_t n, float alpha, void* stream) {
+  ++g_cn_weight_epoch;
   if (n <= 0) return CN_OK;
   ema_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(ema, p, (size_t)n, alpha);
   CN_CHECK_LAUNCH(); return CN_OK;

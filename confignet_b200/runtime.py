@@ -41,6 +41,8 @@ class ParamGroup:
         for name, shape, n, o in zip(self.names, self.shapes, self.sizes, self.offsets):
             v = self.flat[o:o + n].view(shape)
             self.params[name] = v
+        if self.flat.is_cuda:      # the conv kernels keep packed images of registered kernels (include/confignet_b200.h)
+            L.call("cn_register_params", ops._p(self.flat), self.total * 4)
         self.set_weights([arrays[k] for k in self.names])
         self._train_idx = [i for i, k in enumerate(self.names) if trainable is None or trainable(k)]
         self._trainable = [self.params[self.names[i]] for i in self._train_idx]
@@ -65,10 +67,23 @@ class ParamGroup:
             host[o:o + n] = w.reshape(-1)
         with torch.no_grad():
             self.flat.copy_(torch.from_numpy(host))
+        self._changed()
 
     def copy_from(self, other):
         with torch.no_grad():
             self.flat.copy_(other.flat)
+        self._changed()
+
+    def _changed(self):
+        if self.flat.is_cuda:
+            L.call("cn_weights_changed")
+
+    def __del__(self):
+        try:
+            if self.flat.is_cuda:
+                L.call("cn_unregister_params", ops._p(self.flat))
+        except Exception:
+            pass
 
     @property
     def trainable_weights(self):

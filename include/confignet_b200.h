@@ -16,6 +16,7 @@
 #ifndef CONFIGNET_B200_H
 #define CONFIGNET_B200_H
 #include <stdint.h>
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -41,6 +42,15 @@ const char* cn_last_error(void);
 int cn_version(void);
 /* number of kernels this library has launched since load (or since the last reset != 0) */
 long long cn_launch_count(int reset);
+
+/* Parameter buffers.  A caller that keeps its Keras kernels in long-lived device buffers (the ParamGroup flat
+ * buffers behind model.get_weights()/set_weights(), confignet_first_stage.py:129-206) registers them once; the conv
+ * entry points then keep the tensor-core stage images of those kernels until the buffer changes.  The optimizer and
+ * EMA entry points below mark the change themselves; any OTHER writer (set_weights, a memcpy) must call
+ * cn_weights_changed().  Unregistered weight pointers are re-packed on every call. */
+int cn_register_params(const void* base, size_t bytes);
+int cn_unregister_params(const void* base);
+int cn_weights_changed(void);
 
 /* Convolution geometry.  nd = 0 describes a Dense layer (batch rows, cin -> cout). */
 typedef struct {

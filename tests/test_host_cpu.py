@@ -81,6 +81,61 @@ def test_plan_geometry_matches_oracle(cfg):
     assert np.abs(ogw - gw.numpy()).max() < 1e-4
 
 
+FOLD_CASES = [(2, 2, (4, 6), 3, 4, 4, 1, 2), (3, 1, (4, 4, 4), 2, 3, 3, 1, 2), (2, 1, (5, 3), 2, 2, 3, 1, 2),
+              (3, 2, (2, 3, 4), 2, 2, 3, 1, 2), (2, 1, (1, 1), 2, 3, 4, 1, 2)]
+
+
+@pytest.mark.parametrize("cfg", FOLD_CASES)
+def test_folded_upsample_conv_plans_match_oracle(cfg):
+    """Sub-pixel folding of UpSampling(2) + conv (hologan_generator.py:139-172): the phased forward plan, the
+    folded input-gradient plan and the folded weight gradient (+ unfold lists), evaluated on the host exactly as the
+    kernels consume them, equal the oracle's upsample -> conv_same and its autograd gradients."""
+    from confignet_b200 import _lib as L
+    lib = L.load()
+    lib.cn_debug_conv_host.restype = ctypes.c_int
+    nd, B, dims, cin, cout, k, s, up = cfg
+    rng = np.random.RandomState(1)
+    d = L.make_conv_desc(nd, B, dims, cin, cout, [k] * nd, s, up)
+    x = rng.randn(B, *dims, cin).astype(np.float32)
+    w = rng.randn(*([k] * nd), cin, cout).astype(np.float32)
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    wt = torch.tensor(w, dtype=torch.float64, requires_grad=True)
+    y = O.conv_same(O.upsample_nearest2(xt), wt, None, s)
+    gy = rng.randn(*y.shape).astype(np.float32)
+    gx, gw = torch.autograd.grad(y, (xt, wt), torch.tensor(gy, dtype=torch.float64))
+    fp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    out = np.full(y.shape, 7.0, np.float32)
+    assert lib.cn_debug_conv_host(ctypes.byref(d), 3, fp(x), fp(w), fp(out)) == 0
+    ogx = np.full(x.shape, 7.0, np.float32)
+    assert lib.cn_debug_conv_host(ctypes.byref(d), 4, fp(gy), fp(w), fp(ogx)) == 0
+    ogw = np.full(w.shape, 7.0, np.float32)
+    assert lib.cn_debug_conv_host(ctypes.byref(d), 5, fp(x), fp(gy), fp(ogw)) == 0
+    assert np.abs(out - y.detach().numpy()).max() < 1e-4
+    assert np.abs(ogx - gx.numpy()).max() < 1e-4
+    assert np.abs(ogw - gw.numpy()).max() < 1e-4
+
+
+@pytest.mark.parametrize("cfg", [(2, 2, (8, 8), 3, 5, 3, 2, 1), (3, 1, (4, 4, 2), 2, 3, 3, 2, 1), (2, 1, (6, 4), 2, 3, 4, 2, 1)])
+def test_stride2_dgrad_single_phased_plan(cfg):
+    """All parity phases of the stride-2 input gradient as ONE phased plan (the discriminator blocks' dgrad)."""
+    from confignet_b200 import _lib as L
+    lib = L.load()
+    lib.cn_debug_conv_host.restype = ctypes.c_int
+    nd, B, dims, cin, cout, k, s, up = cfg
+    rng = np.random.RandomState(2)
+    d = L.make_conv_desc(nd, B, dims, cin, cout, [k] * nd, s, up)
+    x = rng.randn(B, *dims, cin).astype(np.float32)
+    w = rng.randn(*([k] * nd), cin, cout).astype(np.float32)
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    y = O.conv_same(xt, torch.tensor(w, dtype=torch.float64), None, s)
+    gy = rng.randn(*y.shape).astype(np.float32)
+    gx, = torch.autograd.grad(y, (xt,), torch.tensor(gy, dtype=torch.float64))
+    fp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    ogx = np.full(x.shape, 7.0, np.float32)
+    assert lib.cn_debug_conv_host(ctypes.byref(d), 6, fp(gy), fp(w), fp(ogx)) == 0
+    assert np.abs(ogx - gx.numpy()).max() < 1e-4
+
+
 def test_conv_desc_errors():
     from confignet_b200 import _lib as L
     lib = L.load()

@@ -58,7 +58,10 @@ SMALL = [(2, 2, (8, 8), 3, 5, 4, 1, 1), (2, 2, (8, 8), 3, 5, 3, 2, 1), (2, 1, (7
 TCS = [(2, 2, (16, 16), 64, 64, 3, 1, 1), (2, 2, (16, 16), 32, 32, 4, 1, 1), (2, 4, (16, 16), 48, 96, 3, 2, 1),
        (2, 2, (8, 8), 64, 32, 4, 1, 2), (3, 2, (4, 4, 4), 64, 32, 3, 1, 2), (3, 1, (8, 8, 8), 32, 64, 3, 1, 1),
        (2, 1, (16, 16), 128, 256, 1, 1, 1), (2, 2, (32, 32), 96, 192, 3, 2, 1), (2, 4, (15, 17), 64, 48, 3, 2, 1),
-       (2, 4, (16, 16), 512, 256, 4, 1, 1), (0, 256, (), 256, 512, 1, 1, 1)]
+       (2, 4, (16, 16), 512, 256, 4, 1, 1), (0, 256, (), 256, 512, 1, 1, 1),
+       # folded upsample+conv (phased forward, folded dgrad, folded wgrad + unfold) at sizes the tensor-core path takes
+       (2, 4, (16, 16), 64, 32, 4, 1, 2), (3, 4, (4, 4, 4), 64, 32, 3, 1, 2), (3, 2, (8, 8, 8), 32, 64, 3, 1, 2),
+       (2, 3, (16, 32), 32, 32, 4, 1, 2), (2, 2, (32, 32), 192, 384, 3, 2, 1)]
 
 
 @pytest.mark.parametrize("cfg", SMALL)
