@@ -1643,7 +1643,8 @@ __global__ void colsum_kernel(const float* __restrict__ g, int rows, int n, floa
 // ------------------------------------------------------------------------------------------------
 // Host dispatch
 // ------------------------------------------------------------------------------------------------
-static int g_cluster = 2;   // CTAs per cluster in the tcgen05 pixel kernel (cn_debug_set_cluster: 1, 2 or 4)
+static int g_cluster = 1;   // CTAs per cluster in the tcgen05 pixel kernel (cn_debug_set_cluster: 1, 2 or 4); measured per layer in
+                            // profiles/r01_cluster_ab_v5.txt: sharing the weight stream by multicast no longer pays (c2/c1 = 1.00..1.06)
 extern "C" int cn_debug_set_cluster(int v) { g_cluster = (v == 4 || v == 2) ? v : 1; return CN_OK; }
 static long long* g_prof = nullptr;   // TEST HOOK: device buffer (16 x int64) receiving CTA 0's role timings
 extern "C" int cn_debug_set_prof(void* p) { g_prof = (long long*)p; return CN_OK; }
