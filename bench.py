@@ -211,15 +211,30 @@ def run_b200(args):
     value = PER_GPU_BATCH * world / (ms * 1e-3)
 
     # ---- roofline of the tcgen05 conv kernels (events recorded around each launch in the timed region)
+    tc_exec = sum(p[6] for p in prof if p[4] == 2)
     tc_flops = sum(p[1] for p in prof if p[4] == 2)
     tc_ms = sum(p[2].elapsed_time(p[3]) for p in prof if p[4] == 2)
     cc_ms = sum(p[2].elapsed_time(p[3]) for p in prof if p[4] != 2)
     all_flops = sum(p[1] for p in prof)
     hbm, tensor_peak, how = measured_peaks()
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "tc_dram_traffic.json")      # written by scripts/summarize_launches.py from ncu
+    if os.path.exists(tpath):
+        with open(tpath) as fp:
+            t = json.load(fp)
+        traffic, traffic_src = t.get("dram_bytes_per_launch"), t.get("source")
+    n_tc = sum(1 for p in prof if p[4] == 2)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": achieved / tensor_peak, "traffic": None, "peak_source": how + " cuBLAS bf16 dense (sustained)",
-                "kernel": "igemm_tc_pixel_kernel / igemm_tc_wgrad_kernel (tcgen05 kind::tf32, 3 MMAs per product)",
+                "frac": achieved / tensor_peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": how + " cuBLAS bf16 dense (sustained); kind::tf32 runs at half of it and every fp32 product "
+                               "takes 3 tf32 MMAs (3xTF32), so frac <= 1/6 on executed FLOPs",
+                "kernel": "igemm_tc_pixel_kernel<B_MN,WG> (tcgen05 kind::tf32 fwd/dgrad/wgrad, 3 MMAs per product)",
+                "algorithmic_gflop_per_launch": tc_flops / max(n_tc, 1) / 1e9,
+                "avg_launch_us": tc_ms * 1e3 / max(n_tc, 1),
+                "executed_tflops": tc_exec / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0,
+                "executed_note": "FLOPs executed after sub-pixel folding of UpSampling(2)+conv; achieved counts the "
+                                 "reference formulation (convs on the upsampled grid)",
                 "launches": sum(1 for p in prof if p[4] == 2) // max(args.steps, 1),
                 "tc_ms_per_step": tc_ms / args.steps, "cuda_core_conv_ms_per_step": cc_ms / args.steps,
                 "algorithmic_conv_tflop_per_step": all_flops / args.steps / 1e12,
@@ -227,7 +242,7 @@ def run_b200(args):
 
     if args.breakdown and rank == 0:
         agg = {}
-        for (op, f, a, b, impl, key) in prof:
+        for (op, f, a, b, impl, key, _fx) in prof:
             k = (op, key, impl)
             t = agg.setdefault(k, [0, 0.0, 0.0])
             t[0] += 1; t[1] += a.elapsed_time(b); t[2] += f

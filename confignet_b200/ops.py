@@ -97,6 +97,16 @@ def _flops(g):
     return 2.0 * m * k * g.cout
 
 
+def _exec_flops(g):
+    """FLOPs actually executed: the sub-pixel folded plans of UpSampling(2)+conv (csrc/conv.cu, csrc/skinny.cu) sum the
+    taps that land on the same low-resolution pixel, so a k-tap axis costs (k+1)/2 taps per output instead of k."""
+    f = _flops(g)
+    if g.desc.upsample == 2:
+        for k in g.ksize:
+            f *= (k + 1) / (2.0 * k)
+    return f
+
+
 def _timed(op, g, fn):
     prof = PROFILE[0]
     if prof is None:
@@ -105,7 +115,7 @@ def _timed(op, g, fn):
     e0.record()
     fn()
     e1.record()
-    prof.append((op, _flops(g), e0, e1, L.load().cn_last_conv_impl(), g.desc.key()))
+    prof.append((op, _flops(g), e0, e1, L.load().cn_last_conv_impl(), g.desc.key(), _exec_flops(g)))
 
 
 def _conv_fwd_raw(g, x, w, bias, act=L.ACT_NONE, alpha=0.0):
