@@ -117,6 +117,8 @@ def load():
     if os.environ.get("CN_FOLD"):               # "fold,s2all" e.g. "0,1": folded upsample+conv plans / merged stride-2 dgrad phases
         a, b = (os.environ["CN_FOLD"].split(",") + ["1"])[:2]
         lib.cn_debug_set_fold(int(a), int(b))
+    if os.environ.get("CN_PERSISTENT"):
+        lib.cn_debug_set_persistent(int(os.environ["CN_PERSISTENT"]))
     if os.environ.get("CN_WCACHE"):
         lib.cn_debug_set_wcache(int(os.environ["CN_WCACHE"]))
     if os.environ.get("CN_CLUSTER"):

@@ -60,6 +60,7 @@ struct GemmPlan {
   // upsample+conv forward and by the parity phases of the stride-2 input gradient.
   int nphase;
   int kb_stride;    // k-blocks per (phase, n-tile) slot of the packed-weight buffer (max over phases)
+  int taps_total;   // entries of the tap table (all phases)
   int ph_ntaps[8];  // taps of phase ph are taps[ph_tap0[ph] .. ph_tap0[ph] + ph_ntaps[ph])
   int ph_tap0[8];
   int ph_ooff[8];   // ooff bits of the phase: bit d = ooff[d]

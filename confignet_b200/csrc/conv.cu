@@ -149,6 +149,7 @@ static int build_plan(const cn_conv_desc* d, int kind, int phase, GemmPlan* out,
   CN_REQUIRE(srcpix * g.Csrc < (1ll << 32) && (long long)g.n_img * g.Q[0] * g.Q[1] * g.Q[2] * g.Cn < (1ll << 32),
              CN_ERR_UNSUPPORTED, "tensor too large for 32-bit element offsets");
   g.taps = nullptr;
+  g.taps_total = g.ntaps;
   *out = g;
   return CN_OK;
 }
@@ -314,6 +315,7 @@ static int build_fold_plan(const cn_conv_desc* d, int kind, GemmPlan* out, std::
   }
   g.Ktot = g.ntaps * g.Csrc;
   g.kb_stride = (g.Ktot + 31) / 32;
+  g.taps_total = (int)taps.size();
   long long M = (long long)g.n_img * g.E[0] * g.E[1] * g.E[2];
   CN_REQUIRE(M < (1ll << 31), CN_ERR_UNSUPPORTED, "too many output rows");
   g.M = (int)M;
@@ -351,6 +353,7 @@ static int build_s2all_plan(const cn_conv_desc* d, GemmPlan* out, std::vector<in
   }
   CN_REQUIRE(taps.size() <= 256, CN_ERR_UNSUPPORTED, "too many taps");
   g.ntaps = maxt; g.Ktot = maxt * g.Csrc; g.kb_stride = (g.Ktot + 31) / 32;
+  g.taps_total = (int)taps.size();
   g.taps = nullptr;
   *out = g;
   return CN_OK;
@@ -726,13 +729,17 @@ constexpr int TC_CHUNK_KB = 8;    // k-blocks (256 K elements) accumulated in th
 // accumulator row.  The running total lives in shared memory ([column][128 rows] fp32: lane = row, so the
 // accesses are conflict-free), which leaves the tensor memory to the two accumulators and the A stages.
 template <class StoreFn>
-__device__ __forceinline__ void tc_promote_smem_and_store(uint32_t tmem_base, float* tot, int pw, int bn, int bn_r, int nchunks,
+__device__ __forceinline__ void tc_promote_smem_and_store(uint32_t tmem_base, float* tot, int pw, int bn, int bn_r, int c0, int nchunks,
                                                           uint32_t bar_accfull, uint32_t bar_accempty, StoreFn store) {
+  // c0 = accumulation chunks this CTA has consumed before this item (persistent CTAs): the ping-pong accumulator
+  // and the barrier phases follow the GLOBAL chunk index; every chunk, the last of an item included, releases its
+  // accumulator so that a later item can reuse it.
   const uint32_t lanebits = (uint32_t)(pw * 32) << 16;
   float* mine = tot + pw * 32 + (threadIdx.x & 31);
   for (int c = 0; c < nchunks; ++c) {
-    const int b = c & 1;
-    mbar_wait(bar_accfull + 8 * b, (c >> 1) & 1);
+    const int gc = c0 + c;
+    const int b = gc & 1;
+    mbar_wait(bar_accfull + 8 * b, (gc >> 1) & 1);
     tc_fence_after();
     const bool last = c == nchunks - 1;
     for (int cb = 0; cb < bn; cb += 32) {
@@ -749,7 +756,7 @@ __device__ __forceinline__ void tc_promote_smem_and_store(uint32_t tmem_base, fl
         store(cb, v);
       }
     }
-    if (!last) { tc_fence_before(); __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(bar_accempty + 8 * b); }
+    tc_fence_before(); __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(bar_accempty + 8 * b);
   }
 }
 
@@ -961,11 +968,18 @@ __global__ void __launch_bounds__(TCP_THREADS)
 igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const float* __restrict__ Wp,
                       const float* __restrict__ bias, float* __restrict__ D, int act, float alpha,
                       int bn, int bn_smem, int nb, int tmem_cols, int kb_per_split, int use_atomic,
-                      int csize, int dbg, long long* prof) {
+                      int csize, int ny, int dbg, long long* prof) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  GemmPlan p = pin;
-  const int ntile = cn_select_phase(p, blockIdx.y, gridDim.y);
+  // Work items.  ny == 0 (wgrad, clusters): one item per CTA, (blockIdx.x, blockIdx.y) = (M tile, n-tile/phase).
+  // ny > 0: PERSISTENT - items w = (M tile, y) with y = w % ny (n-tile and phase) fastest; CTA i takes w = i, i + G, ...
+  // (G = gridDim.x, coprime with ny so that every CTA sees all phases).  All pipeline state - stage indices,
+  // barrier phases, the accumulator ping-pong - runs on across items, so the epilogue stores of item j (measured:
+  // 15-33 % of a one-item CTA, profiles/r01_role_prof_v7_dbg.txt) overlap the main loop of item j+1 and the
+  // prologue (barrier init, TMEM allocation, pipeline fill) is paid once per SM.
+  const int tiles_m = ((WG ? pin.Ktot : pin.M) + TC_BM - 1) / TC_BM;
+  const int n_items = ny > 0 ? tiles_m * ny : 1;
+  const int w_first = ny > 0 ? (int)blockIdx.x : 0, w_step = ny > 0 ? (int)gridDim.x : 1;
   const bool do_prof = prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   long long pt[6] = {0, 0, 0, 0, 0, 0};
   const long long t_begin = clock64();
@@ -980,14 +994,22 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_off);
   int2* s_taps = reinterpret_cast<int2*>(smem + L.taps_off);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * TC_BM, n0 = ntile * bn;
-  const int total_kb = ((WG ? p.M : p.Ktot) + TC_BK - 1) / TC_BK;
-  const int kb_stride = pin.nphase > 1 ? pin.kb_stride : total_kb;   // slot stride of the packed B buffer
+  const int kb_stride = pin.nphase > 1 ? pin.kb_stride : ((WG ? pin.M : pin.Ktot) + TC_BK - 1) / TC_BK;   // slot stride of the packed B buffer
   const int kb_beg = blockIdx.z * kb_per_split;             // split-K over gridDim.z (atomic epilogue)
-  const int num_kb = min(total_kb, kb_beg + kb_per_split) - kb_beg;   // host guarantees >= 1
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+  // item w -> plan of its phase, tile origin, index of its B slot row, offset of its taps in s_taps, its k-blocks
+  auto item = [&](int w, GemmPlan& p, int& m0, int& n0, int& y, int& tap0, int& num_kb) {
+    p = pin;
+    int tile;
+    if (ny > 0) { y = w % ny; tile = w / ny; } else { y = blockIdx.y; tile = blockIdx.x; }
+    const int ntile = cn_select_phase(p, y, ny > 0 ? ny : (int)gridDim.y);
+    tap0 = (int)(p.taps - pin.taps);
+    m0 = tile * TC_BM; n0 = ntile * bn;
+    const int total_kb = ((WG ? p.M : p.Ktot) + TC_BK - 1) / TC_BK;
+    num_kb = min(total_kb, kb_beg + kb_per_split) - kb_beg;   // host guarantees >= 1
+  };
 
-  for (int i = tid; i < p.ntaps; i += TCP_THREADS) s_taps[i] = p.taps[i];
+  for (int i = tid; i < pin.taps_total; i += TCP_THREADS) s_taps[i] = pin.taps[i];     // the taps of ALL phases
   if (tid == 0) {
     for (int s = 0; s < nb; ++s) { mbar_init(bar_fullb + 8 * s, 1); mbar_init(bar_emptyb + 8 * s, csize); }
     for (int s = 0; s < TCP_MAX_A; ++s) { mbar_init(bar_fulla + 8 * s, 4); mbar_init(bar_emptya + 8 * s, 1); }   // one arrival per gather warp
@@ -1015,17 +1037,24 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
     //       flight while the current one is split into its tf32 big/small parts and written with tcgen05.st. =====
     const int q4 = warp & 3, par = warp >> 2;
     const uint32_t a_t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + a_col0;
+    int s_sa = par, s_u = 0;                 // A stage and use count of this warp's next k-block to store (run on across items)
+    int gk_base = 0;                         // k-blocks of this CTA's earlier items: the two warp sets alternate GLOBAL k-blocks
+   for (int w = w_first; w < n_items; w += w_step) {
+    GemmPlan p; int m0, n0, ysel, tap0, num_kb;
+    item(w, p, m0, n0, ysel, tap0, num_kb);
+    const int kb_first = (par - gk_base) & 1;
+    gk_base += num_kb;
     // ---- pixel mode state
     const RowInfo row = decode_row(p, WG ? p.M : m0 + q4 * 32 + lane);
     auto src_off = [&](int kt) -> uint32_t {
       if (kt >= p.ntaps) return 0xffffffffu;
-      const uint32_t sp = src_pixel(p, row, s_taps[kt].x);
+      const uint32_t sp = src_pixel(p, row, s_taps[tap0 + kt].x);
       return sp != 0xffffffffu ? sp * (uint32_t)p.Csrc : 0xffffffffu;
     };
     // position of this warp's next k-block to load: (tap, channel) and whether k is still inside Ktot;
     // advanced by two k-blocks per load without divisions
     int l_kt, l_c;
-    { const int k = (kb_beg + par) * TC_BK; l_kt = k / p.Csrc; l_c = k - l_kt * p.Csrc; }
+    { const int k = (kb_beg + kb_first) * TC_BK; l_kt = k / p.Csrc; l_c = k - l_kt * p.Csrc; }
     uint32_t l_so = 0xffffffffu;
     int l_so_kt = -1;
     auto load_a = [&](float4* v) {
@@ -1061,11 +1090,11 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
     if (WG) {
       if (wrok) {
         const int kt = wr / p.Csrc; wc = wr - kt * p.Csrc;
-        const int pk = s_taps[kt].x;
+        const int pk = s_taps[tap0 + kt].x;
         woff0 = (pk & 1023) - 8; woff1 = ((pk >> 10) & 1023) - 8; woff2 = (pk >> 20) - 8;
         if (wg.E[2] != p.E[2] || wg.E[1] != p.E[1]) { woff2 = woff1; woff1 = woff0; woff0 = 0; }    // 2-D plan: row in position 1
       }
-      int m = (kb_beg + par) * TC_BK;
+      int m = (kb_beg + kb_first) * TC_BK;
       e2 = m % wg.E[2]; m /= wg.E[2]; e1 = m % wg.E[1]; m /= wg.E[1]; e0 = m % wg.E[0]; en = m / wg.E[0];
     }
     const float* Ac = A + wc;
@@ -1086,7 +1115,6 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
       }
     };
     auto load_any = [&](float4* v) { if (WG) load_w(v); else load_a(v); };
-    int s_sa = par, s_u = 0;                 // A stage and use count of this warp's next k-block to store
     auto store_a = [&]() -> uint32_t {
       const int sa = s_sa;
       { const long long t0 = clock64(); if (s_u >= 1) mbar_wait(bar_emptya + 8 * sa, (s_u - 1) & 1); pt[0] += clock64() - t0; }
@@ -1122,7 +1150,7 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
       pt[1] += clock64() - t0;
     };
     float4 va[8], vb[8];
-    int kb = par;
+    int kb = kb_first;
     if (kb < num_kb) load_any(va);
     for (; kb < num_kb; kb += 4) {
       if (kb + 2 < num_kb) load_any(vb);
@@ -1132,16 +1160,21 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
         put_a(store_a(), vb);
       }
     }
+   }
     if (do_prof && warp == 0 && lane == 0) { prof[0] = pt[0]; prof[1] = pt[1]; prof[2] = pt[2]; prof[3] = clock64() - t_begin; }
   } else if (warp < 12) {
     // ===== promotion + epilogue: TMEM -> registers -> global (warp pw owns TMEM lanes 32pw..32pw+31) =====
     const int pw = warp - 8;
+    const int chunk_kb = (dbg >> 8) ? (dbg >> 8) : TC_CHUNK_KB;
+    int c0 = 0;                              // accumulation chunks of this CTA's earlier items
+   for (int w = w_first; w < n_items; w += w_step) {
+    GemmPlan p; int m0, n0, ysel, tap0, num_kb;
+    item(w, p, m0, n0, ysel, tap0, num_kb);
     const int m = m0 + pw * 32 + lane;
     const bool mok = m < (WG ? p.Ktot : p.M);
     const size_t rowoff = mok ? (WG ? (size_t)m : (size_t)dest_pixel(p, m)) * p.Cn : 0;
-    const int chunk_kb = (dbg >> 8) ? (dbg >> 8) : TC_CHUNK_KB;
     const int nchunks = (num_kb + chunk_kb - 1) / chunk_kb;
-    tc_promote_smem_and_store(tmem_base, reinterpret_cast<float*>(smem + L.tot_off), pw, bn, bn_r, nchunks, bar_accfull, bar_accempty,
+    tc_promote_smem_and_store(tmem_base, reinterpret_cast<float*>(smem + L.tot_off), pw, bn, bn_r, c0, nchunks, bar_accfull, bar_accempty,
                               [&](int cb, const uint32_t* v) {
       if (mok && !(dbg & 16)) {
 #pragma unroll
@@ -1165,6 +1198,8 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
         }
       }
     });
+    c0 += nchunks;
+   }
   } else if (warp == TCP_B_WARP) {
     // ===== B stage fetch: the pre-packed smem image of (n-tile, k-block) is one contiguous block; this CTA
     //       fetches slice `rank` of it and multicasts it to the same offset in all CTAs of the cluster =====
@@ -1172,16 +1207,20 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
       const uint32_t bytes = L.stage_bytes;
       const uint32_t slice = bytes / (uint32_t)csize;
       const uint32_t rank = csize > 1 ? cluster_ctarank() : 0u;
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(Wp) + ((size_t)blockIdx.y * kb_stride + kb_beg) * bytes + rank * slice;
-      int s = 0, ph = 1;
-      for (int it = 0; it < num_kb; ++it) {
-        { const long long t0 = clock64(); if (it >= nb) mbar_wait(bar_emptyb + 8 * s, ph); pt[0] += clock64() - t0; }
+      int s = 0, ph = 1, git = 0;            // stage, phase and fetch count run on across items
+     for (int w = w_first; w < n_items; w += w_step) {
+      GemmPlan p; int m0, n0, ysel, tap0, num_kb;
+      item(w, p, m0, n0, ysel, tap0, num_kb);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(Wp) + ((size_t)ysel * kb_stride + kb_beg) * bytes + rank * slice;
+      for (int it = 0; it < num_kb; ++it, ++git) {
+        { const long long t0 = clock64(); if (git >= nb) mbar_wait(bar_emptyb + 8 * s, ph); pt[0] += clock64() - t0; }
         mbar_arrive_expect_tx(bar_fullb + 8 * s, bytes);
         const uint32_t dst = sbase + s * L.stage_bytes + rank * slice;
         if (csize > 1) bulk_g2s_mc(dst, src + (size_t)it * bytes, slice, bar_fullb + 8 * s, cmask);
         else bulk_g2s(dst, src + (size_t)it * bytes, bytes, bar_fullb + 8 * s);
         if (++s == nb) { s = 0; ph ^= 1; }
       }
+     }
       if (do_prof) { prof[10] = pt[0]; prof[11] = clock64() - t_begin; }
     }
   } else {
@@ -1197,6 +1236,11 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
     int sa = 0, pa = 0, sb = 0, pb = 0, b = 0, inchunk = 0, c = 0;
     const int chunk_kb = (dbg >> 8) ? (dbg >> 8) : TC_CHUNK_KB;
     uint32_t b16 = sbase >> 4;
+    int last_num_kb = 0;
+   for (int w = w_first; w < n_items; w += w_step) {
+    GemmPlan p; int m0, n0, ysel, tap0, num_kb;
+    item(w, p, m0, n0, ysel, tap0, num_kb);
+    last_num_kb = num_kb;
     for (int kb = 0; kb < num_kb; ++kb) {
       const bool chunk_first = inchunk == 0;
       const bool chunk_last = inchunk == chunk_kb - 1 || kb == num_kb - 1;
@@ -1232,7 +1276,9 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
       if (++inchunk == chunk_kb) { inchunk = 0; ++c; b ^= 1; }
       pt[3] += clock64() - t1;
     }
-    if (do_prof && lane == 0) { prof[4] = pt[0]; prof[5] = pt[1]; prof[6] = pt[2]; prof[7] = pt[3]; prof[8] = clock64() - t_begin; prof[9] = num_kb; }
+    if (inchunk != 0) { inchunk = 0; ++c; b ^= 1; }      // the item's last chunk was committed short: the next item starts a new one
+   }
+    if (do_prof && lane == 0) { prof[4] = pt[0]; prof[5] = pt[1]; prof[6] = pt[2]; prof[7] = pt[3]; prof[8] = clock64() - t_begin; prof[9] = last_num_kb; }
   }
   tc_fence_before();
   __syncthreads();
@@ -1650,6 +1696,8 @@ static long long* g_prof = nullptr;   // TEST HOOK: device buffer (16 x int64) r
 extern "C" int cn_debug_set_prof(void* p) { g_prof = (long long*)p; return CN_OK; }
 static int g_dbg = 0;   // TEST HOOK (cn_debug_set): bit 0/1 skip A/B global loads, bit 2 skip MMA issue, bit 3 skip STS
 extern "C" int cn_debug_set(int v) { g_dbg = v; return CN_OK; }
+static int g_persistent = 1;   // persistent CTAs in the tcgen05 pixel kernel (cn_debug_set_persistent)
+extern "C" int cn_debug_set_persistent(int v) { g_persistent = v; return CN_OK; }
 static int g_fold = 1;     // folded upsample+conv plans (cn_debug_set_fold)
 static int g_s2all = 1;    // all parity phases of a stride-2 dgrad in one launch
 extern "C" int cn_debug_set_fold(int fold, int s2all) { g_fold = fold; g_s2all = s2all; return CN_OK; }
@@ -1818,6 +1866,19 @@ static int launch_tc(const GemmPlan& g, const float* src, const float* packed, c
   while (csize > 1 && (int)grid.x < csize) csize >>= 1;
   grid.x = (grid.x + csize - 1) / csize * csize;
   grid.z = split;
+  int ny = 0;
+  if (!WG && csize == 1 && g_persistent) {
+    // persistent CTAs over the (M tile, n-tile/phase) items: one CTA per SM, G coprime with ny (see the kernel)
+    ny = (int)grid.y;
+    const int n_items = (int)grid.x * ny;
+    int G = n_items;
+    if (split == 1 && n_items > num_sms()) {
+      G = num_sms();
+      auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+      while (G > 1 && gcd(G, ny) != 1) --G;
+    }
+    grid.x = G; grid.y = 1;
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = dim3(TCP_THREADS, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -1827,7 +1888,7 @@ static int launch_tc(const GemmPlan& g, const float* src, const float* packed, c
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (set_smem(igemm_tc_pixel_kernel<B_MN, WG>, smem)) return CN_ERR_CUDA;
   CN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc_pixel_kernel<B_MN, WG>, g, src, packed, bias, dst, act, alpha, bn, bn_smem,
-                                   nb, 512, per, (int)(split > 1), csize, (g_dbg & 0xff) | (g_chunk_kb << 8), g_prof));
+                                   nb, 512, per, (int)(split > 1), csize, ny, (g_dbg & 0xff) | (g_chunk_kb << 8), g_prof));
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

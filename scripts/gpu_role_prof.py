@@ -29,8 +29,9 @@ for (nd, B, dims, cin, cout, k, s, up, op) in SHAPES:
             L.call("cn_conv_dgrad", ctypes.byref(d), P(gy), P(w), P(gx), 0, st())
         else:
             L.call("cn_conv_wgrad", ctypes.byref(d), P(x), P(gy), P(gw), None, 0, st())
-    for cl in (1, 2):
+    for cl, dbgmask in ((1, 0), (1, 16), (1, 4), (1, 20)):
         lib.cn_debug_set_cluster(cl)
+        lib.cn_debug_set(dbgmask)
         for _ in range(2):
             run()
         torch.cuda.synchronize()
@@ -42,10 +43,11 @@ for (nd, B, dims, cin, cout, k, s, up, op) in SHAPES:
         torch.cuda.synchronize()
         lib.cn_debug_set_prof(None)
         v = buf.cpu().numpy().astype(float); nkb = max(v[9], 1)
-        print("%s %s cluster=%d: %.1f us/call, CTA0: %d k-blocks, total %.0f clk (%.0f clk per k-block)" %
-              (op, (nd, B, dims, cin, cout, k, s, up), cl, us, nkb, v[12], v[12] / nkb))
+        print("%s %s cluster=%d dbg=%d (16 = no epilogue stores, 4 = no MMA issue): %.1f us/call, CTA0: %d k-blocks, total %.0f clk (%.0f clk per k-block)" %
+              (op, (nd, B, dims, cin, cout, k, s, up), cl, dbgmask, us, nkb, v[12], v[12] / nkb))
         print("   gather warp0 per own k-block: wait_free_stage %.0f  split+st(+load wait) %.0f  issue_loads %.0f | role total %.0f" %
               (tuple(2 * v[i] / nkb for i in (0, 1, 2)) + (v[3],)))
         print("   mma per k-block: wait_acc %.0f  wait_A %.0f  wait_B %.0f  issue %.0f | role total %.0f" %
               (v[4] / nkb, v[5] / nkb, v[6] / nkb, v[7] / nkb, v[8]))
         print("   B producer: wait_free_stage %.0f per k-block | role total %.0f" % (v[10] / nkb, v[11]), flush=True)
+    lib.cn_debug_set(0)
