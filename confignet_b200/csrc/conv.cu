@@ -963,7 +963,9 @@ __device__ __forceinline__ void wg_load(const WgGeom& p, const float* __restrict
 // at 32 consecutive output pixels, which adjacent lanes (adjacent channels) read as coalesced lines; the pixel
 // cursor advances incrementally with warp-uniform carries - and B = the gradient, pre-split into stage images
 // by pack_grad_kernel (MN-major, as it lies in HBM).
-template <int B_MN, int WG>
+// PROF = 1 compiles the (PROF ? clock64() : 0ll) role timers in (scripts/gpu_role_prof.py); the production instantiation has
+// none - they cost a dozen registers in a kernel that sits at the 128-register limit.
+template <int B_MN, int WG, int PROF>
 __global__ void __launch_bounds__(TCP_THREADS)
 igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const float* __restrict__ Wp,
                       const float* __restrict__ bias, float* __restrict__ D, int act, float alpha,
@@ -980,9 +982,9 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
   const int tiles_m = ((WG ? pin.Ktot : pin.M) + TC_BM - 1) / TC_BM;
   const int n_items = ny > 0 ? tiles_m * ny : 1;
   const int w_first = ny > 0 ? (int)blockIdx.x : 0, w_step = ny > 0 ? (int)gridDim.x : 1;
-  const bool do_prof = prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const bool do_prof = PROF && prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   long long pt[6] = {0, 0, 0, 0, 0, 0};
-  const long long t_begin = clock64();
+  const long long t_begin = (PROF ? clock64() : 0ll);
   const TcpLayout L = tcp_layout(nb, bn_smem);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_fullb = sbase + L.bar_off, bar_emptyb = bar_fullb + 8 * nb;   // empty_b: free in EVERY CTA of the cluster
@@ -1058,7 +1060,7 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
     uint32_t l_so = 0xffffffffu;
     int l_so_kt = -1;
     auto load_a = [&](float4* v) {
-      const long long t0 = clock64();
+      const long long t0 = (PROF ? clock64() : 0ll);
       if (l_kt != l_so_kt) { l_so = src_off(l_kt); l_so_kt = l_kt; }
       if (l_c + TC_BK <= p.Csrc) {
         // common case: the 32 channels of this k-block lie inside one tap -> 8 loads off one base pointer
@@ -1079,7 +1081,7 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
       }
       l_c += 2 * TC_BK;
       while (l_c >= p.Csrc) { l_c -= p.Csrc; ++l_kt; }
-      pt[2] += clock64() - t0;
+      pt[2] += (PROF ? clock64() : 0ll) - t0;
     };
     // ---- wgrad mode state: this thread's (tap, channel) row and the warp-uniform pixel cursor (n, e0, e1, e2)
     const int wr = m0 + q4 * 32 + lane;
@@ -1117,14 +1119,14 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
     auto load_any = [&](float4* v) { if (WG) load_w(v); else load_a(v); };
     auto store_a = [&]() -> uint32_t {
       const int sa = s_sa;
-      { const long long t0 = clock64(); if (s_u >= 1) mbar_wait(bar_emptya + 8 * sa, (s_u - 1) & 1); pt[0] += clock64() - t0; }
+      { const long long t0 = (PROF ? clock64() : 0ll); if (s_u >= 1) mbar_wait(bar_emptya + 8 * sa, (s_u - 1) & 1); pt[0] += (PROF ? clock64() : 0ll) - t0; }
       tc_fence_after();
       s_sa += 2;
       if (s_sa >= na) { s_sa -= na; ++s_u; }
       return (uint32_t)sa;
     };
     auto put_a = [&](uint32_t sa, const float4* v) {
-      const long long t0 = clock64();
+      const long long t0 = (PROF ? clock64() : 0ll);
       const uint32_t a_t = a_t0 + sa * TCP_A_COLS;
       if (!(dbg & 8)) {
 #pragma unroll
@@ -1147,7 +1149,7 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
       tc_fence_before();
       __syncwarp();                      // one arrival per warp: 128 per-thread arrivals on one barrier serialise
       if (lane == 0) mbar_arrive(bar_fulla + 8 * sa);
-      pt[1] += clock64() - t0;
+      pt[1] += (PROF ? clock64() : 0ll) - t0;
     };
     float4 va[8], vb[8];
     int kb = kb_first;
@@ -1161,7 +1163,7 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
       }
     }
    }
-    if (do_prof && warp == 0 && lane == 0) { prof[0] = pt[0]; prof[1] = pt[1]; prof[2] = pt[2]; prof[3] = clock64() - t_begin; }
+    if (do_prof && warp == 0 && lane == 0) { prof[0] = pt[0]; prof[1] = pt[1]; prof[2] = pt[2]; prof[3] = (PROF ? clock64() : 0ll) - t_begin; }
   } else if (warp < 12) {
     // ===== promotion + epilogue: TMEM -> registers -> global (warp pw owns TMEM lanes 32pw..32pw+31) =====
     const int pw = warp - 8;
@@ -1213,7 +1215,7 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
       item(w, p, m0, n0, ysel, tap0, num_kb);
       const uint8_t* src = reinterpret_cast<const uint8_t*>(Wp) + ((size_t)ysel * kb_stride + kb_beg) * bytes + rank * slice;
       for (int it = 0; it < num_kb; ++it, ++git) {
-        { const long long t0 = clock64(); if (git >= nb) mbar_wait(bar_emptyb + 8 * s, ph); pt[0] += clock64() - t0; }
+        { const long long t0 = (PROF ? clock64() : 0ll); if (git >= nb) mbar_wait(bar_emptyb + 8 * s, ph); pt[0] += (PROF ? clock64() : 0ll) - t0; }
         mbar_arrive_expect_tx(bar_fullb + 8 * s, bytes);
         const uint32_t dst = sbase + s * L.stage_bytes + rank * slice;
         if (csize > 1) bulk_g2s_mc(dst, src + (size_t)it * bytes, slice, bar_fullb + 8 * s, cmask);
@@ -1221,7 +1223,7 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
         if (++s == nb) { s = 0; ph ^= 1; }
       }
      }
-      if (do_prof) { prof[10] = pt[0]; prof[11] = clock64() - t_begin; }
+      if (do_prof) { prof[10] = pt[0]; prof[11] = (PROF ? clock64() : 0ll) - t_begin; }
     }
   } else {
     // ===== MMA issue (one lane): per k-block 4 k-steps x 3 split products, A from TMEM, B from smem.
@@ -1244,13 +1246,13 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
     for (int kb = 0; kb < num_kb; ++kb) {
       const bool chunk_first = inchunk == 0;
       const bool chunk_last = inchunk == chunk_kb - 1 || kb == num_kb - 1;
-      long long t0 = clock64();
+      long long t0 = (PROF ? clock64() : 0ll);
       if (chunk_first && c >= 2) { mbar_wait(bar_accempty + 8 * b, ((c >> 1) - 1) & 1); }
-      long long t1 = clock64(); pt[0] += t1 - t0;
+      long long t1 = (PROF ? clock64() : 0ll); pt[0] += t1 - t0;
       mbar_wait(bar_fulla + 8 * sa, pa);
-      t0 = clock64(); pt[1] += t0 - t1;
+      t0 = (PROF ? clock64() : 0ll); pt[1] += t0 - t1;
       mbar_wait(bar_fullb + 8 * sb, pb);
-      t1 = clock64(); pt[2] += t1 - t0;
+      t1 = (PROF ? clock64() : 0ll); pt[2] += t1 - t0;
       tc_fence_after();
       if (elect_one()) {
         if (!(dbg & 4)) {
@@ -1274,16 +1276,16 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
       b16 += stage16;
       if (++sb == nb) { sb = 0; pb ^= 1; b16 = sbase >> 4; }
       if (++inchunk == chunk_kb) { inchunk = 0; ++c; b ^= 1; }
-      pt[3] += clock64() - t1;
+      pt[3] += (PROF ? clock64() : 0ll) - t1;
     }
     if (inchunk != 0) { inchunk = 0; ++c; b ^= 1; }      // the item's last chunk was committed short: the next item starts a new one
    }
-    if (do_prof && lane == 0) { prof[4] = pt[0]; prof[5] = pt[1]; prof[6] = pt[2]; prof[7] = pt[3]; prof[8] = clock64() - t_begin; prof[9] = last_num_kb; }
+    if (do_prof && lane == 0) { prof[4] = pt[0]; prof[5] = pt[1]; prof[6] = pt[2]; prof[7] = pt[3]; prof[8] = (PROF ? clock64() : 0ll) - t_begin; prof[9] = last_num_kb; }
   }
   tc_fence_before();
   __syncthreads();
   if (csize > 1) cluster_sync_all();      // no CTA leaves while a peer may still signal its barriers
-  if (do_prof && tid == 0) prof[12] = clock64() - t_begin;
+  if (do_prof && tid == 0) prof[12] = (PROF ? clock64() : 0ll) - t_begin;
   if (warp == TCP_MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -1886,8 +1888,9 @@ static int launch_tc(const GemmPlan& g, const float* src, const float* packed, c
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (set_smem(igemm_tc_pixel_kernel<B_MN, WG>, smem)) return CN_ERR_CUDA;
-  CN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc_pixel_kernel<B_MN, WG>, g, src, packed, bias, dst, act, alpha, bn, bn_smem,
+  auto kern = g_prof ? igemm_tc_pixel_kernel<B_MN, WG, 1> : igemm_tc_pixel_kernel<B_MN, WG, 0>;
+  if (set_smem(kern, smem)) return CN_ERR_CUDA;
+  CN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, g, src, packed, bias, dst, act, alpha, bn, bn_smem,
                                    nb, 512, per, (int)(split > 1), csize, ny, (g_dbg & 0xff) | (g_chunk_kb << 8), g_prof));
   CN_CHECK_LAUNCH();
   return CN_OK;
