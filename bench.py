@@ -200,7 +200,9 @@ def run_b200(args):
     prof = []
     if inline:
         ops.PROFILE[0] = prof
+    from confignet_b200.runtime import GraphedFn
     lib.cn_launch_count(1)
+    replayed0 = GraphedFn.REPLAYED_LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -208,7 +210,7 @@ def run_b200(args):
         step(dev_real, dev_synth)
     e1.record()
     barrier()
-    launches = int(lib.cn_launch_count(0))
+    launches = int(lib.cn_launch_count(0)) + (GraphedFn.REPLAYED_LAUNCHES - replayed0)     # eager launches + launches replayed from CUDA graphs
     ops.PROFILE[0] = None
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     clocks = sampler.summary()
@@ -320,7 +322,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
-    ap.add_argument("--roofline-pass", default="inline", choices=["inline", "separate"])
+    ap.add_argument("--roofline-pass", default="separate", choices=["inline", "separate"],
+                    help="separate (default): the timed region runs the product path as is (CUDA-graph replays), the "
+                         "per-launch event pairs of the roofline run over extra eager steps right after it; inline: event "
+                         "pairs inside the timed region (forces eager execution)")
     ap.add_argument("--breakdown", default=None, help="write a per-layer conv time table to this file")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -58,6 +58,7 @@ SIGNATURES = {
     "cn_register_params": [_V, ctypes.c_size_t],
     "cn_unregister_params": [_V],
     "cn_weights_changed": [],
+    "cn_graphs_captured": [],
     "cn_norm_coef": [_I, _V, _I, _V, _V, _I, _I, _I, _f, _V, _V, _V, _V, _V],
     "cn_lrelu_fwd": [_V, _f, _V, _L, _V],
     "cn_act_bwd": [_V, _V, _I, _f, _V, _L, _V],
@@ -72,6 +73,7 @@ SIGNATURES = {
     "cn_from_uint8": [_V, _V, _L, _V],
     "cn_vgg_preprocess": [_V, _V, _L, _I, _V],
     "cn_adam_ema_step": [_V, _V, _V, _V, _V, _L, _f, _f, _f, _f, _f, _f, _V],
+    "cn_adam_ema_step_dev": [_V, _V, _V, _V, _V, _L, _V, _f, _f, _f, _f, _f, _V],
     "cn_ema": [_V, _V, _L, _f, _V],
     "cn_multi_copy": [_I, _V, _V, _V, _V, _V],
     "cn_bn_fold": [_V, _V, _V, _V, _f, _I, _V, _V, _V],
@@ -89,7 +91,7 @@ SIGNATURES = {
     "cn_norm_latent_loss_bwd": [_V, _V, _I, _I, _I, _f, _V, _V, _V, _V],
 }
 NO_STATUS = {"cn_last_error": ctypes.c_char_p, "cn_version": ctypes.c_int, "cn_reduce_ws_floats": ctypes.c_int,
-             "cn_launch_count": ctypes.c_longlong, "cn_last_conv_impl": ctypes.c_int}
+             "cn_launch_count": ctypes.c_longlong, "cn_launch_count_add": ctypes.c_longlong, "cn_last_conv_impl": ctypes.c_int}
 
 _lib = None
 
@@ -108,6 +110,9 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = ctypes.c_int
+    if hasattr(lib, "cn_launch_count_add"):
+        lib.cn_launch_count_add.argtypes = [ctypes.c_longlong]
+    lib.cn_launch_count.argtypes = [ctypes.c_int]
     for name, restype in NO_STATUS.items():
         if not hasattr(lib, name) and os.environ.get("CN_ALLOW_PARTIAL") == "1":
             continue

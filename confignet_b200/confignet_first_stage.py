@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import netspec, networks, ops
-from .runtime import ParamGroup, Network, KerasAdam, allreduce_grads, shard_rows, world
+from .runtime import ParamGroup, Network, KerasAdam, GraphedFn, allreduce_grads, shard_rows, world
 
 DEFAULT_CONFIG = {
     "model_type": None,
@@ -165,6 +165,7 @@ class ConfigNetFirstStage:
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self._seed = seed
 
+        self._graphs = {}                 # (step name, optimizer id) -> runtime.GraphedFn
         self.generator = None
         self.generator_smoothed = None
         self.discriminator = None
@@ -415,7 +416,8 @@ class ConfigNetFirstStage:
         return facemodel_params, dataset.metadata_inputs["rotations"][idxs].astype(np.float32)
 
     # ---------------------------------------------------------------- training steps
-    def _apply(self, optimizer, loss, nets):
+    def _apply(self, optimizer, loss, nets, device_lr=False):
+        """device_lr: the host half of the optimizer step (KerasAdam.begin_step) already ran; this is the device half."""
         groups = [n.group for n in nets]
         params = [p for g in groups for p in g.trainable_weights]
         grads = torch.autograd.grad(loss, params, allow_unused=True)
@@ -425,26 +427,83 @@ class ConfigNetFirstStage:
             keep.append(g.pack_grads(grads[i:i + k]))
             i += k
         gscale = allreduce_grads(groups)
-        optimizer.apply_flat(groups, gscale)
+        if device_lr:
+            optimizer.apply_flat_device_lr(groups, gscale)
+        else:
+            optimizer.apply_flat(groups, gscale)
+
+    def _graphed(self, name, optimizer, fn):
+        """One CUDA-graph wrapper per (step, optimizer): the captured region holds that optimizer's moment buffers."""
+        if not self.config.get("cuda_graphs", True):
+            return fn
+        key = (name, id(optimizer))
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = GraphedFn(fn)
+        return g
+
+    def _real_from_u8(self, imgs_u8, flips):
+        """device half of _upload_images: optional per-image left-right flip, uint8 -> float32 [-1, 1]"""
+        if flips is not None:
+            imgs_u8 = torch.where(flips[:, None, None, None], imgs_u8.flip(2), imgs_u8)
+        return ops.from_uint8(imgs_u8)
 
     @staticmethod
     def _detached(losses):
         """The loss dictionary handed back to the caller holds plain values (the tape is released)."""
         return OrderedDict((k, v.detach()) for k, v in losses.items())
 
+    # The three big steps are split into a host half (NumPy sampling in the reference's draw order, uploads, the
+    # optimizer's iteration count / bias-corrected learning rate) and a device half on device tensors only (forward,
+    # losses, backward, gradient packing, all-reduce, Adam) that runs as a CUDA-graph replay after two eager steps
+    # (runtime.GraphedFn): ~2000 launches per iteration otherwise leave the GPU idle ~9 % of the time.
     def discriminator_training_step(self, training_set, optimizer):
-        real_imgs, fake_imgs = self.get_discriminator_batch(training_set)
-        losses = networks.compute_discriminator_loss(self.discriminator.params, real_imgs, fake_imgs,
-                                                     self.config["n_discr_layers"])
-        self._apply(optimizer, losses["loss_sum"], [self.discriminator])
-        return self._detached(losses)
+        """confignet_first_stage.py:466-476 (batch assembly :438-450)."""
+        B = self.get_batch_size()
+        img_idxs = np.random.randint(0, training_set.imgs.shape[0], B)
+        flips = np.random.randint(0, 2, size=B)          # flip_random_subset_of_images' draw (confignet_utils.py:199)
+        latent = self.sample_latent_vector(B).astype(np.float32)
+        rotation = self.sample_rotations(B)
+        img_idxs, flips, latent, rotation = self._rank_rows(img_idxs, flips, latent, rotation)
+        real_u8 = self._to_device(self._take_rows(training_set.imgs, img_idxs), torch.uint8)
+        flips_d = self._to_device(np.asarray(flips).astype(np.bool_), torch.bool)
+        latent_d = self._to_device(latent, torch.float32)
+        rot_d = self._to_device(np.asarray(rotation, np.float32), torch.float32)
+        optimizer.begin_step(self.device)
+
+        def device_half(real_u8, flips_d, latent_d, rot_d):
+            real_imgs = self._real_from_u8(real_u8, flips_d)
+            with torch.no_grad():
+                fake_imgs = self.generator((latent_d, rot_d))
+            losses = networks.compute_discriminator_loss(self.discriminator.params, real_imgs, fake_imgs,
+                                                         self.config["n_discr_layers"])
+            self._apply(optimizer, losses["loss_sum"], [self.discriminator], device_lr=True)
+            return self._detached(losses)
+        return self._graphed("d", optimizer, device_half)(real_u8, flips_d, latent_d, rot_d)
 
     def synth_discriminator_training_step(self, synth_training_set, optimizer):
-        real_imgs, fake_imgs = self.get_synth_discriminator_batch(synth_training_set)
-        losses = networks.compute_discriminator_loss(self.synth_discriminator.params, real_imgs, fake_imgs,
-                                                     self.config["n_discr_layers"])
-        self._apply(optimizer, losses["loss_sum"], [self.synth_discriminator])
-        return self._detached(losses)
+        """confignet_first_stage.py:478-488 (batch assembly :452-464)."""
+        B = self.get_batch_size()
+        img_idxs = np.random.randint(0, synth_training_set.imgs.shape[0], B)
+        flips = np.random.randint(0, 2, size=B)
+        facemodel_params, rotations = self._sample_synth_metadata(synth_training_set, B)
+        sliced = self._rank_rows(img_idxs, flips, rotations, *facemodel_params)
+        img_idxs, flips, rotations, facemodel_params = sliced[0], sliced[1], sliced[2], sliced[3:]
+        real_u8 = self._to_device(self._take_rows(synth_training_set.imgs, img_idxs), torch.uint8)
+        flips_d = self._to_device(np.asarray(flips).astype(np.bool_), torch.bool)
+        rot_d = self._to_device(np.asarray(rotations, np.float32), torch.float32)
+        fm_d = [self._to_device(a, torch.float32) for a in facemodel_params]
+        optimizer.begin_step(self.device)
+
+        def device_half(real_u8, flips_d, rot_d, *fm_d):
+            real_imgs = self._real_from_u8(real_u8, flips_d)
+            with torch.no_grad():
+                fake_imgs = self.generator((self.synthetic_encoder(list(fm_d)), rot_d))
+            losses = networks.compute_discriminator_loss(self.synth_discriminator.params, real_imgs, fake_imgs,
+                                                         self.config["n_discr_layers"])
+            self._apply(optimizer, losses["loss_sum"], [self.synth_discriminator], device_lr=True)
+            return self._detached(losses)
+        return self._graphed("synth_d", optimizer, device_half)(real_u8, flips_d, rot_d, *fm_d)
 
     def latent_discriminator_training_step(self, synth_training_set, optimizer):
         B = self.get_batch_size()
@@ -473,12 +532,22 @@ class ConfigNetFirstStage:
         sliced = self._rank_rows(idxs, synth_rot, *facemodel_params)
         idxs, synth_rot, facemodel_params = sliced[0], sliced[1], sliced[2:]
         real_latents, real_rot = self._rank_rows(real_latents, real_rot)
-        gt_imgs = self._upload_images(self._take_rows(synth_training_set.imgs, idxs))
-        eye_masks = self._to_device(self._take_rows(synth_training_set.eye_masks, idxs), torch.float32)
+        gt_u8 = self._to_device(self._take_rows(synth_training_set.imgs, idxs), torch.uint8)
+        masks_f = self._to_device(self._take_rows(synth_training_set.eye_masks, idxs), torch.float32)
         real_latents_d = self._to_device(real_latents, torch.float32)
+        synth_rot_d = self._to_device(np.asarray(synth_rot, np.float32), torch.float32)
+        real_rot_d = self._to_device(np.asarray(real_rot, np.float32), torch.float32)
+        fm_d = [self._to_device(a, torch.float32) for a in facemodel_params]
+        optimizer.begin_step(self.device)
+        fn = self._graphed("g", optimizer, lambda *t: self._generator_step_device(optimizer, *t))
+        return fn(gt_u8, masks_f, real_latents_d, synth_rot_d, real_rot_d, *fm_d)
 
+    def _generator_step_device(self, optimizer, gt_u8, eye_masks, real_latents_d, synth_rot, real_rot, *fm_d):
+        """device half of generator_training_step (confignet_first_stage.py:514-557)"""
+        c = self.config
+        gt_imgs = self._real_from_u8(gt_u8, None)
         losses = OrderedDict()
-        synth_latents = self.synthetic_encoder([self._to_device(a, torch.float32) for a in facemodel_params])
+        synth_latents = self.synthetic_encoder(list(fm_d))
         out_synth = self.generator((synth_latents, synth_rot))
         out_real = self.generator((real_latents_d, real_rot))
         losses["image_loss"] = c["image_loss_weight"] * networks.perceptual_loss(self.perceptual_loss.params, gt_imgs, out_synth)
@@ -490,12 +559,13 @@ class ConfigNetFirstStage:
         losses["latent_GAN_loss"] = c["domain_adverserial_loss_weight"] * networks.gan_g_loss(self.latent_discriminator(synth_latents))
         stacked_latents = torch.cat((synth_latents, real_latents_d), dim=0)
         stacked_imgs = torch.cat((out_synth, out_real), dim=0)
-        stacked_rot = self._to_device(np.concatenate((synth_rot, real_rot), axis=0), torch.float32)
+        stacked_rot = torch.cat((synth_rot, real_rot), dim=0)
         labels = torch.cat((stacked_latents, c["latent_regressor_rot_weight"] * stacked_rot), dim=-1)
         losses["latent_regression_loss"] = c["latent_regression_weight"] * networks.latent_regression_loss(
             self.latent_regressor.params, stacked_imgs, labels, c["n_discr_layers"])
         losses["loss_sum"] = networks._sum(losses.values())
-        self._apply(optimizer, losses["loss_sum"], [self.generator, self.latent_regressor, self.synthetic_encoder])
+        self._apply(optimizer, losses["loss_sum"], [self.generator, self.latent_regressor, self.synthetic_encoder],
+                    device_lr=True)
         return self._detached(losses)
 
     def setup_training(self, log_dir, synth_training_set, n_samples_for_metrics, real_training_set=None):

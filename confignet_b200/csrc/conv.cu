@@ -1720,7 +1720,13 @@ static int num_sms() {
 
 template <typename K>
 static int set_smem(K kernel, int bytes) {
+  // once per (kernel, size): keeps the attribute call out of captured CUDA graphs
+  static std::map<const void*, int> done;
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  int& have = done[(const void*)kernel];
+  if (have >= bytes) return CN_OK;
   CN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  have = bytes;
   return CN_OK;
 }
 
@@ -1757,10 +1763,15 @@ static std::vector<ParamRange> g_param_ranges;
 struct PackedEntry { float* buf; size_t bytes; unsigned long long epoch; };
 static std::map<std::pair<const void*, const void*>, PackedEntry> g_wcache;
 
+// Once a CUDA graph has been captured over these launches (cn_graphs_captured), buffers the graph may reference
+// are never freed: growth / invalidation abandons them instead.
+static bool g_no_free = false;
+extern "C" int cn_graphs_captured(void) { g_no_free = true; return CN_OK; }
+static void cn_free(void* p) { if (!g_no_free && p) cudaFree(p); }
 static void drop_wcache_locked() {
   if (g_wcache.empty()) return;
   cudaDeviceSynchronize();
-  for (auto& kv : g_wcache) cudaFree(kv.second.buf);
+  for (auto& kv : g_wcache) cn_free(kv.second.buf);
   g_wcache.clear();
 }
 extern "C" int cn_register_params(const void* p, size_t bytes) {
@@ -1792,7 +1803,7 @@ static int cached_packed(const void* plan_key, const void* w, size_t bytes, floa
   auto key = std::make_pair(plan_key, w);
   auto it = g_wcache.find(key);
   if (it == g_wcache.end() || it->second.bytes < bytes) {
-    if (it != g_wcache.end()) { CN_CHECK_CUDA(cudaDeviceSynchronize()); cudaFree(it->second.buf); g_wcache.erase(it); }
+    if (it != g_wcache.end()) { CN_CHECK_CUDA(cudaDeviceSynchronize()); cn_free(it->second.buf); g_wcache.erase(it); }
     PackedEntry e; e.bytes = bytes; e.epoch = 0; e.buf = nullptr;
     CN_CHECK_CUDA(cudaMalloc(&e.buf, bytes));
     it = g_wcache.insert(std::make_pair(key, e)).first;
@@ -1813,7 +1824,7 @@ static int packed_buffer(const void* key, size_t bytes, float** out) {
   std::lock_guard<std::mutex> lock(g_plan_mutex);
   if (key == nullptr) {
     if (g_gpack_bytes < bytes) {
-      if (g_gpack) { CN_CHECK_CUDA(cudaDeviceSynchronize()); cudaFree(g_gpack); }
+      if (g_gpack) { CN_CHECK_CUDA(cudaDeviceSynchronize()); cn_free(g_gpack); }
       CN_CHECK_CUDA(cudaMalloc(&g_gpack, bytes));
       g_gpack_bytes = bytes;
     }
@@ -1823,7 +1834,7 @@ static int packed_buffer(const void* key, size_t bytes, float** out) {
   auto it = g_wpack.find(key);
   if (it == g_wpack.end() || it->second.second < bytes) {
     float* wp = nullptr;
-    if (it != g_wpack.end()) { CN_CHECK_CUDA(cudaDeviceSynchronize()); cudaFree(it->second.first); }
+    if (it != g_wpack.end()) { CN_CHECK_CUDA(cudaDeviceSynchronize()); cn_free(it->second.first); }
     CN_CHECK_CUDA(cudaMalloc(&wp, bytes));
     g_wpack[key] = std::make_pair(wp, bytes);
     *out = wp;

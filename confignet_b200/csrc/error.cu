@@ -11,6 +11,7 @@ extern "C" long long cn_launch_count(int reset) {
   if (reset) g_cn_launches = 0;
   return v;
 }
+extern "C" long long cn_launch_count_add(long long d) { g_cn_launches += (unsigned long long)d; return (long long)g_cn_launches; }
 // Parameter epoch: bumped whenever a registered parameter buffer may have changed (optimizer / EMA kernels,
 // set_weights, registration).  conv.cu keeps the tensor-core stage images of registered weights until then.
 unsigned long long g_cn_weight_epoch = 1;

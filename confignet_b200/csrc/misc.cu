@@ -310,6 +310,29 @@ __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__
     if (ema) ema[i] = ema_alpha * ema[i] + (1.f - ema_alpha) * pi;
   }
 }
+// same update with lr_t read from device memory: the launch can then live in a captured CUDA graph while the host
+// advances Keras' bias-corrected learning rate between replays
+__global__ void adam_ema_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                    float* __restrict__ v, float* __restrict__ ema, size_t n, const float* __restrict__ lr_dev,
+                                    float b1, float b2, float eps, float ema_alpha, float gscale) {
+  const float lr_t = *lr_dev;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    m[i] = mi; v[i] = vi; p[i] = pi;
+    if (ema) ema[i] = ema_alpha * ema[i] + (1.f - ema_alpha) * pi;
+  }
+}
+extern "C" int cn_adam_ema_step_dev(float* p, const float* g, float* m, float* v, float* ema, int64_t n, const float* lr_t_dev,
+                                    float b1, float b2, float eps, float ema_alpha, float gscale, void* stream) {
+  if (n <= 0) return CN_OK;
+  CN_REQUIRE(p && g && m && v && lr_t_dev, CN_ERR_BAD_SHAPE, "cn_adam_ema_step_dev: null pointer");
+  ++g_cn_weight_epoch;
+  adam_ema_dev_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, (size_t)n, lr_t_dev, b1, b2, eps, ema_alpha, gscale);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
 extern "C" int cn_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr_t,
                                 float b1, float b2, float eps, float ema_alpha, float gscale, void* stream) {
   if (n <= 0) return CN_OK;

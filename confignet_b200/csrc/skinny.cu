@@ -501,7 +501,11 @@ bool is_up4c3(const cn_conv_desc* d) {
 
 template <typename K>
 int opt_in_smem(K kernel, int bytes) {
-  if (bytes > 48 * 1024) CN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  static int have = 0;            // per instantiation: keeps the attribute call out of captured CUDA graphs
+  if (bytes > 48 * 1024 && have < bytes) {
+    CN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    have = bytes;
+  }
   return CN_OK;
 }
 

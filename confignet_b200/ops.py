@@ -623,6 +623,10 @@ def adam_ema_step(p, g, m, v, ema, lr_t, b1, b2, eps, ema_alpha=0.999, gscale=1.
     L.call("cn_adam_ema_step", _p(p), _p(g), _p(m), _p(v), _p(ema), p.numel(), lr_t, b1, b2, eps, ema_alpha, gscale, _stream())
 
 
+def adam_ema_step_dev(p, g, m, v, ema, lr_dev, b1, b2, eps, ema_alpha=0.999, gscale=1.0):
+    L.call("cn_adam_ema_step_dev", _p(p), _p(g), _p(m), _p(v), _p(ema), p.numel(), _p(lr_dev), b1, b2, eps, ema_alpha, gscale, _stream())
+
+
 def ema_update(ema, p, alpha):
     L.call("cn_ema", _p(ema), _p(p), p.numel(), alpha, _stream())
 

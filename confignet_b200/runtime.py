@@ -11,6 +11,7 @@ buffers, and the data-parallel gradient exchange.
 """
 import ctypes
 import math
+import os
 from collections import OrderedDict
 import numpy as np
 import torch
@@ -146,17 +147,92 @@ class KerasAdam:
         self.iterations = 0
         self.state = {}
 
+    def _lr_t(self, t):
+        return self.lr * math.sqrt(1 - self.b2 ** t) / (1 - self.b1 ** t)
+
+    def _state(self, g):
+        st = self.state.get(id(g))
+        if st is None:
+            st = (torch.zeros_like(g.flat), torch.zeros_like(g.flat))
+            self.state[id(g)] = st
+        return st
+
     def apply_flat(self, groups, gscale=1.0):
         """One optimizer step over the flat gradient buffers of ``groups`` (already packed / reduced)."""
-        t = self.iterations + 1
-        lr_t = self.lr * math.sqrt(1 - self.b2 ** t) / (1 - self.b1 ** t)
+        lr_t = self._lr_t(self.iterations + 1)
         for g in groups:
-            st = self.state.get(id(g))
-            if st is None:
-                st = (torch.zeros_like(g.flat), torch.zeros_like(g.flat))
-                self.state[id(g)] = st
+            st = self._state(g)
             ops.adam_ema_step(g.flat, g.grad, st[0], st[1], None, lr_t, self.b1, self.b2, self.eps, 0.0, gscale)
         self.iterations += 1
+
+    # ---- split form for captured steps: the host half advances `iterations` and refreshes the bias-corrected
+    #      learning rate in a device scalar; the device half (which may be a CUDA-graph replay) reads it
+    def begin_step(self, device):
+        if getattr(self, "lr_dev", None) is None:
+            self.lr_dev = torch.zeros(1, device=device, dtype=torch.float32)
+            self._lr_ring = torch.zeros(16, dtype=torch.float32).pin_memory()
+        slot = self.iterations % 16
+        self._lr_ring[slot] = self._lr_t(self.iterations + 1)
+        self.lr_dev.copy_(self._lr_ring[slot:slot + 1], non_blocking=True)
+        self.iterations += 1
+
+    def apply_flat_device_lr(self, groups, gscale=1.0):
+        for g in groups:
+            st = self._state(g)
+            ops.adam_ema_step_dev(g.flat, g.grad, st[0], st[1], None, self.lr_dev, self.b1, self.b2, self.eps, 0.0, gscale)
+
+
+class GraphedFn:
+    """Runs ``fn(*tensors) -> OrderedDict of scalar tensors`` (the device half of a training step: forward, losses,
+    backward, gradient packing, all-reduce, Adam) as a CUDA-graph replay.  The first ``warm`` calls run eagerly (they
+    are real steps and let the library create its plans and buffers), the next call is captured and replayed, later
+    calls copy their inputs into the captured input tensors and replay.  Any capture error switches the wrapper
+    back to eager execution for good.  Shapes must not change between calls (a new shape -> eager)."""
+    ENABLED = os.environ.get("CN_GRAPHS", "1") != "0"
+    REPLAYED_LAUNCHES = 0          # library kernels launched through graph replays (cn_launch_count only sees eager ones)
+
+    def __init__(self, fn, warm=2):
+        self.fn, self.warm = fn, warm
+        self.calls, self.graph, self.failed = 0, None, False
+        self.static_in, self.static_out, self.sig = None, None, None
+
+    @staticmethod
+    def _sig(tensors):
+        return tuple((tuple(t.shape), t.dtype) for t in tensors)
+
+    def __call__(self, *tensors):
+        if not GraphedFn.ENABLED or self.failed or ops.PROFILE[0] is not None or not tensors[0].is_cuda:
+            return self.fn(*tensors)
+        self.calls += 1
+        if self.calls <= self.warm:
+            return self.fn(*tensors)
+        if self.graph is None:
+            try:
+                self.sig = self._sig(tensors)
+                self.static_in = [t.clone() for t in tensors]
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = int(L.load().cn_launch_count(0))
+                with torch.cuda.graph(g):
+                    out = self.fn(*self.static_in)
+                self.launches = int(L.load().cn_launch_count(0)) - n0       # recorded, not executed
+                L.load().cn_launch_count_add(-self.launches)
+                self.graph, self.static_out = g, out
+                L.call("cn_graphs_captured")
+            except Exception as e:                                   # pragma: no cover - depends on the driver
+                self.failed, self.graph = True, None
+                torch.cuda.synchronize()
+                import warnings
+                warnings.warn("CUDA-graph capture of a training step failed (%s); running eagerly" % (str(e)[:200],))
+                return self.fn(*tensors)
+        elif self._sig(tensors) != self.sig:
+            return self.fn(*tensors)
+        else:
+            for s, t in zip(self.static_in, tensors):
+                s.copy_(t, non_blocking=True)
+        self.graph.replay()
+        GraphedFn.REPLAYED_LAUNCHES += self.launches
+        return OrderedDict((k, v.clone()) for k, v in self.static_out.items())
 
 
 # ------------------------------------------------------------------------------------------------ data parallel

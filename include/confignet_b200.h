@@ -42,6 +42,8 @@ const char* cn_last_error(void);
 int cn_version(void);
 /* number of kernels this library has launched since load (or since the last reset != 0) */
 long long cn_launch_count(int reset);
+/* adjusts the counter (a CUDA-graph capture records launches without executing them; replays are added by the caller) */
+long long cn_launch_count_add(long long delta);
 
 /* Parameter buffers.  A caller that keeps its Keras kernels in long-lived device buffers (the ParamGroup flat
  * buffers behind model.get_weights()/set_weights(), confignet_first_stage.py:129-206) registers them once; the conv
@@ -51,6 +53,9 @@ long long cn_launch_count(int reset);
 int cn_register_params(const void* base, size_t bytes);
 int cn_unregister_params(const void* base);
 int cn_weights_changed(void);
+/* call once a CUDA graph has been captured over this library's launches: internal scratch / cache buffers are then
+ * never freed (a graph may still reference them), growth abandons the old buffer instead */
+int cn_graphs_captured(void);
 
 /* Convolution geometry.  nd = 0 describes a Dense layer (batch rows, cin -> cout). */
 typedef struct {
@@ -160,6 +165,10 @@ int cn_vgg_preprocess(const float* x, float* out, int64_t npix, int mode, void* 
 int cn_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
                      float lr_t, float b1, float b2, float eps, float ema_alpha, float gscale,
                      void* stream);
+/* the same step with lr_t read from device memory (CUDA-graph friendly: the host updates the scalar between replays) */
+int cn_adam_ema_step_dev(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
+                         const float* lr_t_dev, float b1, float b2, float eps, float ema_alpha, float gscale,
+                         void* stream);
 
 /* dst[dst_off[i] : dst_off[i]+n[i]] = src[i] (zeros when src[i] is NULL) for i < count: packs the
  * per-variable gradients tape.gradient returns (confignet_first_stage.py:472-474,556-558) into the flat
