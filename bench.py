@@ -47,6 +47,14 @@ def measured_peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+def bench_config(world):
+    return {"workload": "generator+discriminator train_step, synthetic 256x256 batch=32 per GPU (BASELINE.json configs[1])",
+            "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * world, "resolution": RES,
+            "parallelism": "dp%d" % world,
+            "l2": "inputs larger than L2: >1 GB of activations per step, no flush needed",
+            "resident": "image and mask stores in HBM; per-step RNG draws (<100 KB) made by the step"}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -128,9 +136,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "256x256 face images/sec (G+D step)", "value": val, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "generator+discriminator train_step, synthetic 256x256, bounded CPU sample",
-                       "per_gpu_batch": PER_GPU_BATCH, "sample_batch": b,
-                       "note": "CPU restatement of the reference (TensorFlow 2.1 not installable)"},
+            "config": dict(bench_config(args.gpus), reference_sample_batch=b,
+                           note="CPU restatement of the reference (TensorFlow 2.1 not installable), bounded sample of the workload"),
             "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -304,12 +311,7 @@ def run_b200(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 split on tcgen05, fp32 accumulate)",
                 "data": "synthetic",
-                "config": {"workload": "generator+discriminator train_step, synthetic 256x256 batch=32 per GPU "
-                                       "(BASELINE.json configs[1])",
-                           "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * world, "resolution": RES,
-                           "parallelism": "dp%d" % world,
-                           "l2": "inputs larger than L2: >1 GB of activations per step, no flush needed",
-                           "resident": "image and mask stores in HBM; per-step RNG draws (<100 KB) made by the step"},
+                "config": bench_config(world),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
