@@ -25,6 +25,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CN_GRAPHS_DP", "1")      # CUDA-graph replay of the steps under data parallelism too (see finish())
 
 import numpy as np
 import torch
@@ -164,9 +165,20 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda:%d" % local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keeps NCCL's version banner off stdout (one JSON line only)
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created: park stdout on stderr meanwhile
+        # (rank 0's stdout carries ONE JSON line)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     lib = L.load()
 
     cfg = {"output_shape": (RES, RES, 3), "batch_size": PER_GPU_BATCH * world, "facemodel_inputs": facemodel_cfg()}
@@ -278,9 +290,24 @@ def run_b200(args):
             for (op, key, impl), (n, t, f) in rows:
                 fp.write("%-6s %-62s %4d %5d %9.3f %8.2f\n" % (op, str(key), impl, n // prof_steps, t / prof_steps,
                                                              f / (t * 1e-3) / 1e12 if t > 0 else 0))
+    def finish():
+        if world > 1:
+            # The captured step graphs hold NCCL work: tearing the communicator down under them hangs (measured: the
+            # 2-GPU run sat in destroy_process_group until its timeout).  Everything is measured and printed - drop
+            # the graphs, meet the other ranks once more and leave without the teardown.
+            sys.stdout.flush()
+            model._graphs.clear()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
     if args.no_e2e:
         if rank == 0:
             print(json.dumps({"value": value, "ms_per_step": ms, "note": "profiling run (no e2e leg)"}), flush=True)
+        finish()
         return
     # ---- e2e: public API, host datasets, H2D + D2H inside the timed region
     for _ in range(2):
@@ -315,8 +342,7 @@ def run_b200(args):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():

@@ -203,6 +203,10 @@ class GraphedFn:
     def __call__(self, *tensors):
         if not GraphedFn.ENABLED or self.failed or ops.PROFILE[0] is not None or not tensors[0].is_cuda:
             return self.fn(*tensors)
+        if world()[1] > 1 and os.environ.get("CN_GRAPHS_DP", "0") != "1":
+            # a captured NCCL all-reduce keeps the communicator busy at teardown (destroy_process_group hangs unless the
+            # graphs are dropped first): opt-in under data parallelism (bench.py does, and leaves without the teardown)
+            return self.fn(*tensors)
         self.calls += 1
         if self.calls <= self.warm:
             return self.fn(*tensors)
