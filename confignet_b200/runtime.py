@@ -170,7 +170,9 @@ class KerasAdam:
     def begin_step(self, device):
         if getattr(self, "lr_dev", None) is None:
             self.lr_dev = torch.zeros(1, device=device, dtype=torch.float32)
-            self._lr_ring = torch.zeros(16, dtype=torch.float32).pin_memory()
+            self._lr_ring = torch.zeros(16, dtype=torch.float32)
+            if self.lr_dev.is_cuda:
+                self._lr_ring = self._lr_ring.pin_memory()
         slot = self.iterations % 16
         self._lr_ring[slot] = self._lr_t(self.iterations + 1)
         self.lr_dev.copy_(self._lr_ring[slot:slot + 1], non_blocking=True)

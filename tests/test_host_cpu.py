@@ -324,3 +324,26 @@ def test_data_parallel_gradient_average_equals_global_batch(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_keras_adam_host_half_and_graph_wrapper_fallback():
+    """KerasAdam.begin_step is the host half of a (possibly graph-replayed) optimizer step: it must advance
+    `iterations` and publish Keras' bias-corrected lr_t = lr*sqrt(1-b2^t)/(1-b1^t) [TF-2.1] for t = iterations+1.
+    GraphedFn must run plain functions untouched when its inputs are not CUDA tensors."""
+    import math
+    from collections import OrderedDict
+    from confignet_b200.runtime import KerasAdam, GraphedFn
+    opt = KerasAdam(lr=4e-4, beta_1=0.0, beta_2=0.9)
+    for t in (1, 2, 3):
+        opt.begin_step(torch.device("cpu"))
+        assert opt.iterations == t
+        assert abs(float(opt.lr_dev[0]) - 4e-4 * math.sqrt(1 - 0.9 ** t)) <= 1e-10
+    opt2 = KerasAdam(lr=1e-3, beta_1=0.5, beta_2=0.99)
+    opt2.begin_step(torch.device("cpu"))
+    assert abs(float(opt2.lr_dev[0]) - 1e-3 * math.sqrt(1 - 0.99) / (1 - 0.5)) <= 1e-9
+    calls = []
+    g = GraphedFn(lambda a, b: (calls.append(1), OrderedDict(s=(a + b).sum()))[1])
+    for _ in range(4):
+        out = g(torch.ones(3), torch.ones(3))
+        assert float(out["s"]) == 6.0
+    assert len(calls) == 4 and g.graph is None
