@@ -147,18 +147,20 @@ enum {
   CN_COEF_ADAIN_BWD = 7,    // sums(a,gy) p0=sb            -> coef0, out0 = gsb (n,2ch)
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 norm_coef_kernel(int kind, const float* __restrict__ sums, int nsplit, const float* __restrict__ p0,
                                  const float* __restrict__ p1, int n, int ch, float N, float eps,
                                  float4* __restrict__ coef0, float4* __restrict__ coef1,
                                  float* __restrict__ out0, float* __restrict__ out1) {
-  // block (32, 8): lane = channel, the 8 rows take every 8th sample
-  __shared__ float red[2][8][33];
+  // block (32, R): lane = channel, the R = 8 | 32 rows take every R-th sample (R = 32: one sample per thread at the
+  // batch sizes of the training step - the kernel is a chain of dependent L2 round trips, not bandwidth)
+  __shared__ float red[2][32][33];
+  const int R = blockDim.y;
   const int c = blockIdx.x * 32 + threadIdx.x;
   const bool cok = c < ch;
   const float invN = 1.f / N;
   float acc0 = 0.f, acc1 = 0.f;
-  for (int i = threadIdx.y; cok && i < n; i += 8) {
+  for (int i = threadIdx.y; cok && i < n; i += R) {
     float S[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) S[j] = 0.f;
@@ -244,8 +246,7 @@ norm_coef_kernel(int kind, const float* __restrict__ sums, int nsplit, const flo
     __syncthreads();
     if (threadIdx.y == 0 && cok) {
       float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { t0 += red[0][i][threadIdx.x]; t1 += red[1][i][threadIdx.x]; }
+      for (int i = 0; i < R; ++i) { t0 += red[0][i][threadIdx.x]; t1 += red[1][i][threadIdx.x]; }
       out0[c] = t0;
       if (kind == CN_COEF_IN_BWD) out1[c] = t1;
     }
@@ -256,7 +257,7 @@ extern "C" int cn_norm_coef(int kind, const float* sums, int nsplit, const float
                             int npix, float eps, float* coef0, float* coef1, float* out0, float* out1,
                             void* stream) {
   CN_REQUIRE(kind >= 0 && kind <= 7 && sums && nsplit >= 1 && n > 0 && ch > 0 && npix > 0, CN_ERR_BAD_SHAPE, "cn_norm_coef: bad arguments");
-  norm_coef_kernel<<<(ch + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(kind, sums, nsplit, p0, p1, n, ch, (float)npix, eps,
+  norm_coef_kernel<<<(ch + 31) / 32, dim3(32, n >= 16 ? 32 : 8), 0, (cudaStream_t)stream>>>(kind, sums, nsplit, p0, p1, n, ch, (float)npix, eps,
                                                                               (float4*)coef0, (float4*)coef1, out0, out1);
   CN_CHECK_LAUNCH();
   return CN_OK;
