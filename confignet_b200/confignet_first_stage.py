@@ -364,7 +364,17 @@ class ConfigNetFirstStage:
             return arr.to(self.device, dtype)
         t = torch.from_numpy(np.ascontiguousarray(arr))
         ConfigNetFirstStage.h2d_bytes += t.numel() * t.element_size()
-        return t.pin_memory().to(self.device, non_blocking=True).to(dtype)
+        if self.device.type != "cuda":
+            return t.to(self.device).to(dtype)
+        # pinned staging + copy on a side stream: the next step's batch goes up while the current step computes
+        if getattr(self, "_upload_stream", None) is None:
+            self._upload_stream = torch.cuda.Stream(self.device)
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._upload_stream):
+            d = t.pin_memory().to(self.device, non_blocking=True)
+        cur.wait_stream(self._upload_stream)
+        d.record_stream(cur)
+        return d.to(dtype)
 
     def _upload_images(self, imgs_u8, flip=None):
         """uint8 (B,H,W,3) batch -> float32 [-1,1] device tensor; optional per-image left-right flip."""
