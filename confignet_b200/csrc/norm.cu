@@ -229,7 +229,8 @@ norm_coef_kernel(int kind, const float* __restrict__ sums, int nsplit, const flo
     float S[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) S[j] = 0.f;
-    for (int z = 0; z < nsplit; ++z) {
+#pragma unroll 4
+    for (int z = 0; z < nsplit; ++z) {          // independent loads: let several slices be in flight
       const float* Sz = sums + (((size_t)z * n + i) * ch + c) * 7;
 #pragma unroll
       for (int j = 0; j < 7; ++j) S[j] += Sz[j];
