@@ -214,7 +214,8 @@ def run_b200(args):
 
     # ---- value: stores resident in HBM, CUDA events around the K steps
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:                  # one nvidia-smi poller per job (8 of them would compete with the ranks' host halves)
+        sampler.start()
     # roofline: a CUDA-event pair around every conv-family launch INSIDE the timed region (default), or - with
     # --roofline-pass separate - over extra steps right after it (to measure what the ~1200 event records cost)
     inline = args.roofline_pass == "inline"

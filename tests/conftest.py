@@ -10,3 +10,12 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_sessionstart(session):
+    """The suites load confignet_b200/lib/libconfignet_b200.so; build it when a fresh checkout has none
+    (nvcc cross-compiles sm_100a without a GPU)."""
+    lib = os.path.join(ROOT, "confignet_b200", "lib", "libconfignet_b200.so")
+    if not os.path.exists(lib):
+        import __graft_entry__
+        __graft_entry__.build()
