@@ -7,12 +7,20 @@
 // That covers TF-SAME asymmetric padding, stride 2, the fused nearest x2 upsample (ushift=1 in
 // forward; extra (delta,tap) generalized taps in dgrad) and the parity phases of the stride-2 dgrad.
 //
-// Two kernels per mode:
-//   igemm_ffma_kernel : fp32 CUDA-core tiles, scalar gathers, any channel count (skinny layers, tiny M)
-//   igemm_tc_*_kernel : tcgen05.mma kind::tf32 on big/small tf32 splits of the fp32 operands (3xTF32: 3 products
-//                       per k-step, fp32-grade accuracy on the tensor pipe), fp32 accumulators in TMEM,
-//                       128B-swizzled smem stages filled by gather warps, mbarrier full/empty pipeline,
-//                       tcgen05.ld epilogue with fused bias+activation.
+// Plans beyond the plain ones: PHASED plans (several GEMMs that differ only in tap list and output offset in one
+// launch: the parity phases of the stride-2 dgrad, the sub-pixel phases of the folded forward) and FOLDED plans
+// (nearest x2 upsample + conv evaluated on the low-resolution tensor with pre-summed taps).
+//
+// Kernels:
+//   igemm_tc_pixel_kernel : tcgen05.mma kind::tf32 on big/small tf32 splits of the fp32 operands (3xTF32: 3 products
+//                       per k-step, fp32-grade accuracy on the tensor pipe), fp32 accumulators in TMEM with
+//                       chunked promotion, A gathered straight into tensor memory, B streamed as pre-packed
+//                       128B-swizzled stage images by bulk async copies, mbarrier full/empty pipeline, persistent
+//                       CTAs over (M tile, n-tile/phase) items, tcgen05.ld epilogue with fused bias+activation.
+//                       <B_MN, WG, PROF>: forward / dgrad / weight gradient, role timers on or off.
+//   igemm_ffma_kernel, dense_small_kernel, pixel_smalln_kernel, skinny wgrad kernels, colsum*: fp32 CUDA-core
+//                       kernels for tiny-M Dense layers and shapes the tensor-core kernel does not take
+//                       (skinny.cu has the dedicated kernels of the 3-channel layers).
 //
 // Reference call sites: keras Conv2D/Conv3D/Dense in confignet/dnn_models/*.py (see include/confignet_b200.h).
 #include "common.cuh"

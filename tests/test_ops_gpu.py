@@ -1,6 +1,6 @@
 """-m gpu: every CUDA operator against the CPU oracle (oracle/confignet_oracle.py) on the same seeded
 inputs, through the C ABI.  Tolerances: 1e-4 for fp32 CUDA-core kernels, 1e-3 (the north-star parity
-bar is 1e-3, measured as max|a-b|/max|b|) 2e-4 for the tcgen05 kernels (bf16 hi/lo split, 3 products)."""
+bar is 1e-3, measured as max|a-b|/max|b|) 2e-4 for the tcgen05 kernels (3xTF32: tf32 big/small split, 3 products)."""
 import numpy as np
 import pytest
 import torch
