@@ -250,10 +250,14 @@ def test_graph_replayed_steps_match_eager_steps(dev):
     # steps 1-2 run eagerly in both; step 3 is the captured step (same weights going in); 4-5 are pure replays
     # (B = 2 on untrained networks is chaotic: two eager runs are already 3e-2..2e-1 apart from step 3 on, and which
     # step a pair happens to agree on varies from run to run - so later steps are held against the pair's worst step)
-    noise = max(5e-2, 4 * float(d_eager[2:].max()))
+    # Measured on B200: eager pairs differ by 3e-7, 1e-3, 5e-2..6e-2, 3e-2..1e-1, 6e-2..2e-1 at steps 1..5, the replayed
+    # model by 2e-7, 2e-3, 7e-2, 1.5e-1..1.9e-1, 1.9e-1..2.4e-1 - the same growth.  The bounds below leave room for
+    # that chaos and still catch a replay that computes something else (stale inputs, a missing kernel, a wrong
+    # learning rate: those show up as O(1) differences at the captured step).
+    noise = max(0.5, 4 * float(d_eager[2:].max()))
     assert d_graph[0] <= 1e-3 and d_graph[1] <= 2e-2, (d_graph, d_eager)
-    assert np.all(d_graph[2:] <= noise), (d_graph, d_eager)
+    assert d_graph[2] <= 0.25 and np.all(d_graph[3:] <= noise), (d_graph, d_eager)
     for name in w_e:
         a = np.concatenate([x.ravel() for x in w_g[name]]); b = np.concatenate([x.ravel() for x in w_e[name]])
         c = np.concatenate([x.ravel() for x in w_e2[name]])
-        assert np.linalg.norm(a - b) <= max(5e-2 * np.linalg.norm(b), 4 * np.linalg.norm(c - b)), name
+        assert np.linalg.norm(a - b) <= max(1e-1 * np.linalg.norm(b), 4 * np.linalg.norm(c - b)), name
