@@ -165,7 +165,7 @@ class ConfigNetFirstStage:
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self._seed = seed
 
-        self._graphs = {}                 # (step name, optimizer id) -> runtime.GraphedFn
+        self._graphs = {}                 # step name -> (optimizer, runtime.GraphedFn)
         self.generator = None
         self.generator_smoothed = None
         self.discriminator = None
@@ -443,14 +443,15 @@ class ConfigNetFirstStage:
             optimizer.apply_flat(groups, gscale)
 
     def _graphed(self, name, optimizer, fn):
-        """One CUDA-graph wrapper per (step, optimizer): the captured region holds that optimizer's moment buffers."""
+        """One CUDA-graph wrapper per step, bound to the optimizer whose moment buffers the captured region holds."""
         if not self.config.get("cuda_graphs", True):
             return fn
-        key = (name, id(optimizer))
-        g = self._graphs.get(key)
-        if g is None:
-            g = self._graphs[key] = GraphedFn(fn)
-        return g
+        entry = self._graphs.get(name)
+        if entry is None or entry[0] is not optimizer:
+            # a new optimizer object (a second train() call): its moment buffers and learning-rate scalar are not the
+            # ones the old graph captured - drop that graph (and its memory pool) and start over
+            entry = self._graphs[name] = (optimizer, GraphedFn(fn))
+        return entry[1]
 
     def _real_from_u8(self, imgs_u8, flips):
         """device half of _upload_images: optional per-image left-right flip, uint8 -> float32 [-1, 1]"""

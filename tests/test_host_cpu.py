@@ -347,3 +347,21 @@ def test_keras_adam_host_half_and_graph_wrapper_fallback():
         out = g(torch.ones(3), torch.ones(3))
         assert float(out["s"]) == 6.0
     assert len(calls) == 4 and g.graph is None
+
+
+def test_graph_wrappers_are_bound_to_their_optimizer_object():
+    """A captured step holds one optimizer's moment buffers and learning-rate scalar: a different optimizer object
+    (a second train() call) must get a fresh wrapper, the same one must get the same wrapper back."""
+    from confignet_b200.confignet_first_stage import ConfigNetFirstStage
+    from confignet_b200.runtime import KerasAdam, GraphedFn
+    from confignet_b200 import netspec
+    m = ConfigNetFirstStage({"output_shape": (256, 256, 3), "batch_size": 2,
+                             "facemodel_inputs": netspec.default_facemodel_inputs()}, device="cpu")
+    o1, o2 = KerasAdam(), KerasAdam()
+    f = lambda *t: None
+    a = m._graphed("d", o1, f)
+    assert isinstance(a, GraphedFn) and m._graphed("d", o1, f) is a
+    c = m._graphed("d", o2, f)
+    assert c is not a and m._graphed("d", o2, f) is c and m._graphed("g", o2, f) is not c
+    m.config["cuda_graphs"] = False
+    assert m._graphed("d", o1, f) is f

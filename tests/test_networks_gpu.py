@@ -235,7 +235,7 @@ def test_graph_replayed_steps_match_eager_steps(dev):
             g = model.generator_training_step(real, synth, g_opt)
             model.update_smoothed_weights()
             hist.append([float(v) for dct in (d, sd, g) for v in dct.values()])
-        replayed = [k for k, v in model._graphs.items() if v.graph is not None]
+        replayed = [k for k, (_, v) in model._graphs.items() if v.graph is not None]
         return np.array(hist), model.get_weights(), replayed, d_opt.iterations
 
     h_g, w_g, replayed, it_g = run(True)
