@@ -365,3 +365,204 @@ def test_graph_wrappers_are_bound_to_their_optimizer_object():
     assert c is not a and m._graphed("d", o2, f) is c and m._graphed("g", o2, f) is not c
     m.config["cuda_graphs"] = False
     assert m._graphed("d", o1, f) is f
+
+
+def test_oracle_matches_reference_float_code():
+    """tests/golden/reference_float_logic.npz holds the outputs of the REFERENCE's own functions - the 3-D resampler,
+    the Euler matrix, get_layer_style, the GAN / eye / R1 / regression losses, the batch-normalised regression loss and
+    InstanceNormalization.call - executed from /root/reference with TensorFlow replaced by a NumPy shim
+    (scripts/make_golden_float_from_reference.py).  The oracle, an independent restatement, must reproduce them."""
+    from oracle import confignet_oracle_stage2 as O2
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_float_logic.npz"))
+    T = lambda k: torch.tensor(g[k], dtype=torch.float64)
+    close = lambda a, b: np.abs(np.asarray(a.detach() if isinstance(a, torch.Tensor) else a, np.float64) - g[b]).max() <= 1e-12 * max(1.0, np.abs(g[b]).max())
+    R = O.euler_angles_to_matrix(T("euler_angles"))
+    assert close(R, "euler_matrix")                                              # confignet_utils.py:122-145
+    assert close(O.transform_3d_grid(T("rot_grid"), R), "rot_out")               # confignet_utils.py:63-120
+    for name in ("style4", "style5"):                                            # confignet_utils.py:147-159
+        st = O.layer_style(T(name + "_in"))
+        C = st.shape[-1] // 2
+        assert np.abs(st[:, :C].numpy() - g[name + "_mean"].reshape(-1, C)).max() <= 1e-12
+        assert np.abs(st[:, C:].numpy() - g[name + "_std"].reshape(-1, C)).max() <= 1e-12
+    assert close(O.gan_g_loss(T("scores")), "gan_g_loss")                        # losses.py:7-11
+    assert close(O.gan_d_loss(torch.ones(6, 1, dtype=torch.float64), T("scores")), "gan_d_loss_ones")
+    assert close(O.gan_d_loss(torch.zeros(6, 1, dtype=torch.float64), T("scores")), "gan_d_loss_zeros")
+    assert close(O.eye_loss(T("eye_gt"), T("eye_gen"), g["eye_masks"]), "eye_loss")       # losses.py:13-18
+    x = torch.zeros(3, 8, 8, 3, dtype=torch.float64, requires_grad=True)         # losses.py:75-82 with d(out)/dx = r1_grad
+    assert close(O.gradient_regularization((x * T("r1_grad")).sum(dim=(1, 2, 3)), x), "r1_penalty")
+    lab, out = T("lr_labels"), T("lr_out")
+    assert close(((lab - out) ** 2).mean(dim=-1).mean(), "latent_regression_loss")        # the formula of O.latent_regression_loss
+    assert close(O2.normalized_regression(out, lab, 10.0), "normalized_latent_regression_loss")   # confignet_second_stage.py:93-107
+    assert close(O.instance_norm_std(T("in_x"), T("in_gamma"), T("in_beta")), "in_out")   # instance_normalization.py:108-131
+
+
+def test_oracle_matches_reference_models():
+    """tests/golden/reference_models.npz holds outputs of the REFERENCE's own model classes (HologanGenerator,
+    HologanDiscriminator, HologanLatentRegressor, MLPSimple latent discriminator, SyntheticDataEncoder) and of
+    losses.compute_discriminator_loss incl. the R1 terms and a second-order parameter gradient, executed from
+    /root/reference on a torch-backed TensorFlow stand-in (scripts/make_golden_models_from_reference.py,
+    scripts/tf_torch_shim.py) with the seeded parameters regenerated here.  The oracle must reproduce them."""
+    from confignet_b200 import netspec
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_models.npz"))
+
+    def params(spec, seed):
+        arrays = netspec.perturb_params(netspec.init_params(spec, seed), seed + 1000, 0.05)
+        return O.to_torch(arrays, dtype=torch.float64, requires_grad=True)
+
+    def close(a, ref, tol=1e-9):
+        a = np.asarray(a.detach() if isinstance(a, torch.Tensor) else a, np.float64)
+        return np.abs(a - ref).max() <= tol * max(1.0, np.abs(ref).max())
+
+    FM = netspec.default_facemodel_inputs()
+    p_g = params(netspec.generator_spec(145, 256), 101)
+    with torch.no_grad():
+        img = O.generator_forward(p_g, torch.tensor(g["gen_z"]), torch.tensor(g["gen_rot"]), 256)
+    assert close(img[0, ::8, ::8], g["gen_out_sub8"])                    # hologan_generator.py:129-174, building_blocks.py
+
+    p_d = params(netspec.discriminator_spec(256), 102)
+    real = torch.tensor(np.random.RandomState(12).rand(1, 256, 256, 3) * 2 - 1)
+    with torch.no_grad():
+        d = O.discriminator_forward(p_d, real)
+    assert list(d.keys()) == [str(k) for k in g["disc_keys"]]            # hologan_discriminator.py:48-64
+    assert close(torch.stack([v.reshape(()) for v in d.values()]), g["disc_out"])
+    losses = O.compute_discriminator_loss(p_d, real.clone(), img.detach().clone())       # losses.py:20-47,75-82
+    assert list(losses.keys()) == [str(k) for k in g["dloss_keys"]]
+    assert close(torch.stack([v.reshape(()) for v in losses.values()]), g["dloss_vals"])
+    gk, gg = torch.autograd.grad(losses["loss_sum"], [p_d["block0/conv/kernel"], p_d["block2/in/gamma"]])
+    assert close(gk, g["dloss_grad_block0_kernel"]) and close(gg, g["dloss_grad_block2_gamma"])     # through the R1 terms
+
+    p_lr = params(netspec.latent_regressor_spec(145, 256), 103)
+    with torch.no_grad():
+        assert close(O.latent_regressor_forward(p_lr, real), g["lr_out"])                # hologan_discriminator.py:99-113
+    p_ld = params(netspec.latent_discriminator_spec(145, 4), 104)
+    with torch.no_grad():
+        assert close(O.latent_discriminator_forward(p_ld, torch.tensor(g["ld_in"])), g["ld_out"], 1e-12)
+    p_se = params(netspec.synthetic_encoder_spec(FM, 2), 105)
+    se_in, off, parts = torch.tensor(g["se_in"]), 0, []
+    for dims in FM.values():                                             # synthetic_encoder.py:41-46: column ranges in key order
+        parts.append(se_in[:, off:off + dims[0]])
+        off += dims[0]
+    with torch.no_grad():
+        assert close(O.synthetic_encoder_forward(p_se, parts, FM), g["se_out"], 1e-12)
+
+
+def test_oracle_steps_match_reference_steps():
+    """tests/golden/reference_steps.npz: loss dictionaries and (strided samples of) the weights AFTER one optimizer step
+    of the REFERENCE's own discriminator / synth-discriminator / latent-discriminator / generator training steps
+    (confignet_first_stage.py:438-560: NumPy batch assembly, nested tapes, apply_gradients), executed from /root/reference
+    on the torch-backed TensorFlow stand-in (scripts/make_golden_steps_from_reference.py).  The oracle's step functions and
+    Keras-Adam, fed by replaying the NumPy draws in the reference's order, must reproduce them.  (The perceptual loss -
+    keras.applications VGG19 - is replaced on both sides by the same stand-in, see the script.)"""
+    import types
+    from confignet_b200 import netspec
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_steps.npz"))
+    FM = netspec.default_facemodel_inputs()
+    B, RES, N = 2, 256, 5
+    T64 = lambda a: torch.as_tensor(np.asarray(a)).to(torch.float64)
+
+    def params(spec, seed):
+        return O.to_torch(netspec.perturb_params(netspec.init_params(spec, seed), seed + 1000, 0.05), dtype=torch.float64,
+                          requires_grad=True)
+
+    def dataset(seed):
+        r = np.random.RandomState(seed)
+        ds = types.SimpleNamespace()
+        ds.imgs = r.randint(0, 256, (N, RES, RES, 3)).astype(np.uint8)
+        ds.eye_masks = (r.rand(N, RES, RES) < 0.01).astype(np.uint8)
+        ds.meta = {k: r.rand(N, d[0]).astype(np.float32) for k, d in FM.items()}
+        rot = np.zeros((N, 3), np.float32)
+        rot[:, 0] = r.uniform(-0.5, 0.5, N); rot[:, 1] = r.uniform(-0.17, 0.17, N)
+        ds.meta["rotations"] = rot
+        return ds
+
+    def flipped_real(ds):                                  # confignet_first_stage.py:440-443, confignet_utils.py:198-204
+        idx = np.random.randint(0, N, B)
+        real = np.copy(ds.imgs[idx]).astype(np.float32) / 127.5 - 1.0
+        flips = np.random.randint(0, 2, size=B)
+        for i in range(B):
+            if flips[i]:
+                real[i] = real[i][:, ::-1]
+        return real
+
+    def synth(ds, n):                                      # confignet_first_stage.py:425-435
+        idx = np.random.randint(0, N, n)
+        return ([ds.meta[k][idx] for k in FM], ds.meta["rotations"][idx].astype(np.float32),
+                np.copy(ds.imgs[idx]).astype(np.float32), np.copy(ds.eye_masks[idx]))
+
+    def rotations(n):                                      # confignet_first_stage.py:404-409 with the default ranges
+        out = np.zeros((n, 3))
+        for axis, (lo, hi) in enumerate(((-30, 30), (-10, 10), (0, 0))):
+            out[:, axis] = np.pi * np.random.uniform(lo, hi, n) / 180
+        return out.astype(np.float32)
+
+    def sub(t):
+        v = t.detach().numpy().ravel()
+        return v[::max(1, -(-v.size // 2048))]
+
+    def check(tag, losses, weights):
+        assert list(losses.keys()) == [str(k) for k in g[tag + "_keys"]]
+        vals = np.array([float(v.detach()) for v in losses.values()])
+        assert np.abs(vals - g[tag + "_vals"]).max() <= 1e-9 * max(1.0, np.abs(g[tag + "_vals"]).max()), tag
+        for i, w in enumerate(weights):
+            assert np.abs(sub(w) - g["%s_w%d" % (tag, i)]).max() <= 1e-10, (tag, i)
+
+    real_set, synth_set = dataset(31), dataset(32)
+    P = dict(g=params(netspec.generator_spec(145, RES), 201), d=params(netspec.discriminator_spec(RES), 202),
+             sd=params(netspec.discriminator_spec(RES), 203), ld=params(netspec.latent_discriminator_spec(145, 4), 204),
+             lr=params(netspec.latent_regressor_spec(145, RES), 205), se=params(netspec.synthetic_encoder_spec(FM, 2), 206))
+    d_opt, g_opt = O.KerasAdam(), O.KerasAdam()
+    saved = O.perceptual_loss
+    O.perceptual_loss = lambda p_vgg, gt, gen: 1e4 * ((gt - gen) ** 2).mean()
+    try:
+        np.random.seed(41)                                 # discriminator_training_step
+        real = flipped_real(real_set)
+        lat = np.random.normal(0, 1, (B, 145))
+        rot = rotations(B)
+        l = O.discriminator_step_losses(P["d"], P["g"], T64(real), T64(lat), T64(rot), RES)
+        d_opt.apply_gradients(zip(O.grads_of(l["loss_sum"], P["d"]), P["d"].values()))
+        check("d", l, [P["d"][n] for n in ("block0/conv/kernel", "block3/in/gamma", "style2/kernel")])
+        np.random.seed(42)                                 # synth_discriminator_training_step (same optimizer object)
+        real = flipped_real(synth_set)
+        fm_p, srot, _, _ = synth(synth_set, B)
+        l = O.synth_discriminator_step_losses(P["sd"], P["g"], P["se"], FM, T64(real), [T64(a) for a in fm_p], T64(srot), RES)
+        d_opt.apply_gradients(zip(O.grads_of(l["loss_sum"], P["sd"]), P["sd"].values()))
+        check("synth_d", l, [P["sd"][n] for n in ("block0/conv/kernel", "block3/in/gamma", "style2/kernel")])
+        np.random.seed(43)                                 # latent_discriminator_training_step (same optimizer object)
+        real_lat = np.random.normal(0, 1, (B, 145))
+        fm_p, _, _, _ = synth(synth_set, B)
+        l = O.latent_discriminator_step_losses(P["ld"], P["se"], FM, T64(real_lat), [T64(a) for a in fm_p])
+        d_opt.apply_gradients(zip(O.grads_of(l["loss_sum"], P["ld"]), P["ld"].values()))
+        check("latent_d", l, [P["ld"]["mlp/dense0/kernel"], P["ld"]["mlp/dense3/bias"]])
+        assert d_opt.iterations == 3
+        np.random.seed(44)                                 # generator_training_step
+        fm_p, srot, gt, masks = synth(synth_set, B // 2)
+        real_lat = np.random.normal(0, 1, (B - B // 2, 145))
+        real_rot = rotations(B - B // 2)
+        batch = dict(facemodel_params=[T64(a) for a in fm_p], synth_rotations=T64(srot), gt_imgs=T64(gt / 127.5 - 1.0),
+                     eye_masks=masks, real_latents=T64(real_lat), real_rotations=T64(real_rot))
+        l = O.generator_step_losses(P["g"], P["lr"], P["se"], P["d"], P["sd"], P["ld"], None, FM, batch, output_res=RES)
+        allp = OrderedDict()
+        for pre, p in (("g/", P["g"]), ("lr/", P["lr"]), ("se/", P["se"])):
+            for k, v in p.items():
+                allp[pre + k] = v
+        g_opt.apply_gradients(zip(O.grads_of(l["loss_sum"], allp), allp.values()))
+        check("g", l, [P["g"]["map_3d_1/conv/kernel"], P["g"]["map_final/kernel"], P["g"]["map_2d_1/adain/dense1/bias"],
+                       P["g"]["learned_input/bias"], P["lr"]["latent_predictor/bias"], P["se"]["mlp_blendshape_values/dense1/kernel"]])
+    finally:
+        O.perceptual_loss = saved
+    # LatentGAN.discriminator_training_step / generator_training_step (latent_gan.py:117-165), batch 8, lr 5e-5
+    from oracle import confignet_oracle_stage2 as O2
+    p_lg = params(netspec.latent_gan_mlp_spec(145), 211)
+    p_ldg = params(netspec.latent_gan_mlp_spec(145, num_out=1), 212)
+    gt_emb = np.random.RandomState(51).randn(40, 145)
+    o_d, o_g = O.KerasAdam(lr=5e-5), O.KerasAdam(lr=5e-5)
+    np.random.seed(45)
+    zin = np.random.normal(0, 1, (8, 145))
+    idx = np.random.randint(0, gt_emb.shape[0], 8)
+    l = O2.latent_gan_discriminator_losses(p_ldg, p_lg, T64(gt_emb[idx]), T64(zin))
+    o_d.apply_gradients(zip(O.grads_of(l["loss_sum"], p_ldg), p_ldg.values()))
+    check("lgan_d", l, [p_ldg["mlp/dense0/kernel"], p_ldg["mlp/dense2/bias"]])
+    np.random.seed(46)
+    l = O2.latent_gan_generator_losses(p_ldg, p_lg, T64(np.random.normal(0, 1, (8, 145))))
+    o_g.apply_gradients(zip(O.grads_of(l["loss_sum"], p_lg), p_lg.values()))
+    check("lgan_g", l, [p_lg["mlp/dense0/kernel"], p_lg["mlp/dense2/kernel"]])
