@@ -5,12 +5,17 @@ latent regressor, synthetic encoder, VGG19 perceptual loss, losses, Keras-Adam, 
 D / G training steps), following the reference files cited on each function plus the
 TensorFlow-2.1 semantics listed in SURVEY.md section 8c (marked [TF-2.1] below).
 
-PARITY UNPINNED: TensorFlow 2.1 is not installable in this environment and the released
-``models/`` directory (needed by every golden .npz in /root/reference/tests/test_assets) is
-absent, so no reference-authored vector can be executed against this oracle.  It is validated
-instead by (i) independent NumPy-loop restatements of conv-SAME / rotate / norms on tiny shapes
-(oracle/naive_numpy.py), (ii) invariants readable from the reference source and the golden
-.npz shapes (tests/test_oracle.py), (iii) fp64 finite differences of its gradients.
+PINNING: TensorFlow 2.1 is not installable in this environment and the released ``models/`` directory (needed by
+every golden .npz in /root/reference/tests/test_assets) is absent, so parity is UNPINNED AGAINST TENSORFLOW ITSELF.
+The oracle is pinned instead to the reference's own code EXECUTED here on stand-ins for TensorFlow (scripts/
+make_golden_*_from_reference.py, vectors under tests/golden/, checked by tests/test_host_cpu.py): the host logic
+bit-exactly; transform_3d_grid_tf, euler_angles_to_matrix, get_layer_style, the loss formulas and
+InstanceNormalization.call to 1e-12; HologanGenerator / HologanDiscriminator / HologanLatentRegressor / MLPSimple /
+SyntheticDataEncoder and compute_discriminator_loss (nested tape, R1) to 1e-13; the discriminator, synth-discriminator,
+latent-discriminator and generator training steps incl. the Adam update to 3e-13.  The stand-ins restate (do not
+execute) the elementary tf / Keras semantics marked [TF-2.1] below and the keras-applications networks.  Further
+checks: NumPy-loop restatements of conv-SAME / rotate / norms on tiny shapes, invariants readable from the reference
+source, fp64 autograd of the hand-derived formulas.
 
 Gradients come from torch.autograd on CPU (fp32 for the timed baseline, fp64 as gold).
 Allowed importers: tests/, __graft_entry__.smoke(), bench.py (cpu_baseline / --impl reference).

@@ -10,8 +10,10 @@ torch-CPU restatement of the second-stage / fine-tuning / LatentGAN pieces of th
   fine_tune_losses                         confignet_second_stage.py:360-390
   latent_gan_*                             latent_gan.py:117-165
 
-PARITY UNPINNED (see oracle/confignet_oracle.py): TensorFlow 2.1 cannot be run here; the [TF-2.1] semantics are
-restated from SURVEY.md section 8c items 9-11.  Allowed importers: tests/, __graft_entry__.smoke(), bench.py.
+PINNING (see oracle/confignet_oracle.py): unpinned against TensorFlow itself; normalized_regression and the latent_gan_*
+steps are pinned to the reference's own code executed on TensorFlow stand-ins (tests/golden/reference_float_logic.npz,
+reference_steps.npz); the ResNet50 / VGG16 pieces (keras-applications, not reference code) restate SURVEY.md section 8c
+items 9-11.  Allowed importers: tests/, __graft_entry__.smoke(), bench.py.
 """
 from collections import OrderedDict
 import numpy as np
