@@ -10,8 +10,8 @@ torch-CPU restatement of the second-stage / fine-tuning / LatentGAN pieces of th
   fine_tune_losses                         confignet_second_stage.py:360-390
   latent_gan_*                             latent_gan.py:117-165
 
-PINNING (see oracle/confignet_oracle.py): unpinned against TensorFlow itself; normalized_regression and the latent_gan_*
-steps are pinned to the reference's own code executed on TensorFlow stand-ins (tests/golden/reference_float_logic.npz,
+PINNING (see oracle/confignet_oracle.py): unpinned against TensorFlow itself; normalized_regression, the stage-2
+latent-discriminator / generator steps (with a stand-in encoder) and the latent_gan_* steps are pinned to the reference's own code executed on TensorFlow stand-ins (tests/golden/reference_float_logic.npz,
 reference_steps.npz); the ResNet50 / VGG16 pieces (keras-applications, not reference code) restate SURVEY.md section 8c
 items 9-11.  Allowed importers: tests/, __graft_entry__.smoke(), bench.py.
 """

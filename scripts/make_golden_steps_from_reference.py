@@ -335,6 +335,92 @@ check("g", l_ref, l_orc, [(ref_weight("g", "map_3d_1/conv/kernel"), P["g"]["map_
                           (ref_weight("lr", "latent_predictor/bias"), P["lr"]["latent_predictor/bias"]),
                           (se_layers[1].kernel, P["se"]["mlp_blendshape_values/dense1/kernel"])])
 
+# ------------------------------------------------------------------------------------------------ stage-2 steps (confignet_second_stage.py:132-218)
+# ConfigNet's own latent-discriminator and generator steps on the SAME network objects (their weights now differ from
+# the seeds by one update - the oracle's dictionaries moved in lockstep) and the same optimizers (second / fourth
+# iteration: Keras' bias correction is exercised at t > 1).  RealEncoder is keras-applications ResNet50 + two Dense
+# heads and cannot run here: both sides get the same small differentiable stand-in encoder
+#   f = 2x2 average-pooled image (12 values); latent = f A; rotation = tanh(f Br) * (pi/180 * [30, 10, 0]).
+sys.modules.setdefault("cv2", _Stub("cv2"))
+sys.modules["confignet"].ConfigNetFirstStage = fs.ConfigNetFirstStage        # what confignet/__init__.py exports
+second = importlib.import_module("confignet.confignet_second_stage")
+from oracle import confignet_oracle_stage2 as O2                  # noqa: E402
+m2 = second.ConfigNet(dict(cfg, image_loss_weight=5e-4), initialize=False)
+for attr in ("generator", "discriminator", "synth_discriminator", "latent_regressor", "latent_discriminator",
+             "synthetic_encoder", "perceptual_loss"):
+    setattr(m2, attr, getattr(model, attr))
+MULT = torch.tensor(np.pi * np.array([30.0, 10.0, 0.0]) / 180.0)
+
+
+def enc_fn(A, Br, imgs):
+    f = imgs.reshape(imgs.shape[0], 2, RES // 2, 2, RES // 2, 3).mean(dim=(2, 4)).reshape(imgs.shape[0], 12)
+    return f @ A, torch.tanh(f @ Br) * MULT
+
+
+class EncStandIn(S.Model):
+    def __init__(self):
+        S.Model.__init__(self)
+        r = np.random.RandomState(61)
+        self.A = self.add_weight(shape=(12, 145), name="A")
+        self.Br = self.add_weight(shape=(12, 3), name="Br")
+        with torch.no_grad():
+            self.A.copy_(torch.tensor(r.randn(12, 145))); self.Br.copy_(torch.tensor(r.randn(12, 3)))
+
+    def call(self, imgs):
+        return enc_fn(self.A, self.Br, S.T(imgs))
+
+
+m2.encoder = EncStandIn()
+p_enc = OrderedDict((("A", m2.encoder.A.detach().clone().requires_grad_(True)), ("Br", m2.encoder.Br.detach().clone().requires_grad_(True))))
+O2.real_encoder_forward = lambda p, imgs, *a, **k: enc_fn(p["A"], p["Br"], imgs)
+W2 = dict(O.DEFAULT_LOSS_WEIGHTS)
+for k in W2:
+    W2[k] = m2.config[k]
+assert W2["image_loss_weight"] == 5e-4
+
+
+def draw_random_batch(ds, n):
+    """sample_random_batch_of_images (confignet_second_stage.py:108-116)"""
+    idx = np.random.randint(0, ds.imgs.shape[0], n)
+    imgs = np.copy(ds.imgs[idx]).astype(np.float32) / 127.5 - 1.0
+    flips = np.random.randint(0, 2, size=n)
+    for i in range(n):
+        if flips[i]:
+            imgs[i] = imgs[i][:, ::-1]
+    return imgs
+
+
+np.random.seed(47)
+l_ref = m2.latent_discriminator_training_step(real_set, synth_set, d_opt_ref)
+np.random.seed(47)
+rimgs = draw_random_batch(real_set, B)
+fm_p, _, _, _ = draw_synth(synth_set, B)
+l_orc = O2.stage2_latent_discriminator_step_losses(P["ld"], p_enc, P["se"], FM, T64(rimgs), [T64(a) for a in fm_p])
+d_opt_orc.apply_gradients(zip(O.grads_of(l_orc["loss_sum"], P["ld"]), P["ld"].values()))
+check("s2_latent_d", l_ref, l_orc, [(ld_layers[0].kernel, P["ld"]["mlp/dense0/kernel"]), (ld_layers[3].bias, P["ld"]["mlp/dense3/bias"])])
+
+np.random.seed(48)
+l_ref = m2.generator_training_step(real_set, synth_set, g_opt_ref)
+np.random.seed(48)
+fm_p, srot, simgs, masks = draw_synth(synth_set, B // 2)
+simgs = simgs / 127.5 - 1.0
+rimgs = draw_random_batch(real_set, B - B // 2)
+batch = dict(facemodel_params=[T64(a) for a in fm_p], synth_rotations=T64(srot), synth_imgs=T64(simgs), eye_masks=masks,
+             real_imgs=T64(rimgs))
+l_orc = O2.stage2_generator_step_losses(P["g"], P["lr"], P["se"], p_enc, P["d"], P["sd"], P["ld"], None, FM, batch, weights=W2,
+                                        output_res=RES)
+allp = OrderedDict()
+for pre, p in (("g/", P["g"]), ("lr/", P["lr"]), ("se/", P["se"]), ("enc/", p_enc)):
+    for k, v in p.items():
+        allp[pre + k] = v
+g_opt_orc.apply_gradients(zip(O.grads_of(l_orc["loss_sum"], allp), allp.values()))
+check("s2_g", l_ref, l_orc, [(ref_weight("g", "map_3d_1/conv/kernel"), P["g"]["map_3d_1/conv/kernel"]),
+                             (ref_weight("g", "map_final/kernel"), P["g"]["map_final/kernel"]),
+                             (ref_weight("lr", "latent_predictor/bias"), P["lr"]["latent_predictor/bias"]),
+                             (se_layers[1].kernel, P["se"]["mlp_blendshape_values/dense1/kernel"]),
+                             (m2.encoder.A, p_enc["A"]), (m2.encoder.Br, p_enc["Br"])])
+assert g_opt_ref.iterations == g_opt_orc.iterations == 2 and d_opt_ref.iterations == d_opt_orc.iterations == 4
+
 # ------------------------------------------------------------------------------------------------ LatentGAN steps (latent_gan.py:117-165)
 S.Model.predict = lambda self, x: self(x).detach().numpy()          # keras Model.predict: forward without a tape -> NumPy
 S.Model.get_weights = lambda self: [w.detach().numpy().copy() for w in self.trainable_weights]       # (unbuilt here: empty)
@@ -350,7 +436,6 @@ S.Model.set_weights = _set_weights
 sys.modules["confignet.metrics"] = _Stub("confignet.metrics"); sys.modules["confignet.metrics.metrics"] = _Stub("confignet.metrics.metrics")
 lg = importlib.import_module("confignet.latent_gan")
 gan = lg.LatentGAN({"latent_dim": 145, "batch_size": 8})
-from oracle import confignet_oracle_stage2 as O2                  # noqa: E402
 p_lg = seeded_params(netspec.latent_gan_mlp_spec(145), 211)
 p_ldg = seeded_params(netspec.latent_gan_mlp_spec(145, num_out=1), 212)
 with torch.no_grad():
