@@ -278,8 +278,13 @@ class ConfigNet(ConfigNetFirstStage):
             os.makedirs(img_output_dir, exist_ok=True)
         self.fine_tune_losses = []
 
+        pre_tiled, post_tiled = pre.detach().clone(), post.detach().clone()
         for step_number in range(n_iters):
             losses = OrderedDict()
+            # the reference returns the tiled pre/post parts it built INSIDE the last tape, i.e. their values before the
+            # last optimizer update, next to the updated expression part (confignet_second_stage.py:361-364,402):
+            # found by executing the reference's fine_tune_on_img (tests/golden/reference_steps.npz) and kept
+            pre_tiled, post_tiled = pre.detach().clone(), post.detach().clone()
             embeddings = torch.cat((pre.expand(n_imgs, -1), expr, post.expand(n_imgs, -1)), dim=1)
             out = gen((embeddings, rotations))
             losses["image_loss_real"] = 0.5 * c["image_loss_weight"] * networks.perceptual_loss(self.perceptual_loss.params, imgs, out)
@@ -307,7 +312,7 @@ class ConfigNet(ConfigNetFirstStage):
                 np.save(os.path.join(img_output_dir, "output_%02d.npy" % step_number), ops.to_uint8(out.detach()[:1]).cpu().numpy()[0])
 
         with torch.no_grad():
-            embeddings = torch.cat((pre.expand(n_imgs, -1), expr, post.expand(n_imgs, -1)), dim=1)
+            embeddings = torch.cat((pre_tiled.expand(n_imgs, -1), expr, post_tiled.expand(n_imgs, -1)), dim=1)
             emb_out, rot_out = embeddings.contiguous(), rotations.detach().contiguous()
             if ws > 1:
                 eparts = [torch.empty_like(emb_out) for _ in range(ws)]

@@ -421,18 +421,67 @@ check("s2_g", l_ref, l_orc, [(ref_weight("g", "map_3d_1/conv/kernel"), P["g"]["m
                              (m2.encoder.A, p_enc["A"]), (m2.encoder.Br, p_enc["Br"])])
 assert g_opt_ref.iterations == g_opt_orc.iterations == 2 and d_opt_ref.iterations == d_opt_orc.iterations == 4
 
-# ------------------------------------------------------------------------------------------------ LatentGAN steps (latent_gan.py:117-165)
-S.Model.predict = lambda self, x: self(x).detach().numpy()          # keras Model.predict: forward without a tape -> NumPy
-S.Model.get_weights = lambda self: [w.detach().numpy().copy() for w in self.trainable_weights]       # (unbuilt here: empty)
+# ------------------------------------------------------------------------------------------------ fine_tune_on_img (confignet_second_stage.py:321-403)
+# Two iterations on two images: the embedding slicing (shared pre/post-expression parts from the MEAN embedding,
+# per-image expression part), the loss terms, the list of trained variables and Adam(lr=1e-4, Keras defaults).  The two
+# perceptual networks are asymmetric stand-ins here (so that swapped arguments would show):
+#   perceptual_loss.loss(gt, gen) = 1e4 mean((gt - 0.7 gen)^2);  perceptual_loss_face_reco.loss(gen, gt) = 2e3 mean((gen - 0.5 gt)^2)
+S.Model.predict = lambda self, x: tuple(v.detach().numpy() for v in self(x)) if isinstance(self(x), tuple) else self(x).detach().numpy()
+S.Model.get_weights = lambda self: [w.detach().numpy().copy() for w in self.trainable_weights]
 
 
 def _set_weights(self, ws):
-    for w, v in zip(self.trainable_weights, ws):
+    tw = self.trainable_weights
+    assert len(tw) == len(ws)
+    for w, v in zip(tw, ws):
         with torch.no_grad():
             w.copy_(torch.as_tensor(v))
 
 
 S.Model.set_weights = _set_weights
+tf.keras.optimizers = types.SimpleNamespace(Adam=Adam)
+second.keras = tf.keras
+m2.perceptual_loss = types.SimpleNamespace(loss=lambda gt, gen: 1e4 * ((S.T(gt) - 0.7 * S.T(gen)) ** 2).mean())
+m2.perceptual_loss_face_reco = types.SimpleNamespace(loss=lambda gen, gt: 2e3 * ((S.T(gen) - 0.5 * S.T(gt)) ** 2).mean())
+O.perceptual_loss = lambda p_vgg, gt, gen: 1e4 * ((gt - 0.7 * gen) ** 2).mean()
+O2.face_reco_loss = lambda p_vgg16, gen, gt: 2e3 * ((gen - 0.5 * gt) ** 2).mean()
+m2.generator_smoothed = gen_mod.HologanGenerator(**m2._get_generator_kwargs())
+with torch.no_grad():
+    m2.generator_smoothed([z0, r0])
+p_gs = seeded_params(netspec.generator_spec(145, RES), 221)
+load_generator(m2.generator_smoothed, p_gs)
+ft_imgs = np.random.RandomState(62).randint(0, 256, (2, RES, RES, 3)).astype(np.uint8)
+emb_ref, rot_ref = m2.fine_tune_on_img(ft_imgs, n_iters=2)
+# the oracle's loop
+imgs = T64(ft_imgs / 127.5 - 1.0)
+with torch.no_grad():
+    e0, r0_ = enc_fn(p_enc["A"], p_enc["Br"], imgs)
+lo, hi = 7, 37                                                     # blendshape_values in the sorted latent layout
+mean_e = e0.mean(dim=0, keepdim=True)
+pre, expr, post, rots = [t.clone().requires_grad_(True) for t in (mean_e[:, :lo], e0[:, lo:hi], mean_e[:, hi:], r0_)]
+opt = O.KerasAdam(lr=1e-4, beta_1=0.9, beta_2=0.999)
+p_ft = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in p_gs.items())
+for _ in range(2):
+    # the reference returns the tiled pre / post parts built inside the LAST tape (before the last update) next to the
+    # updated expression part (confignet_second_stage.py:361-364,402)
+    pre_t, post_t = pre.detach().clone(), post.detach().clone()
+    l_orc = O2.fine_tune_losses(p_ft, P["lr"], P["d"], P["ld"], None, None, imgs, pre, expr, post, rots, weights=W2, output_res=RES)
+    tv = list(p_ft.values()) + [pre, post, rots, expr]
+    gs = torch.autograd.grad(l_orc["loss_sum"], tv, allow_unused=True)
+    opt.apply_gradients(zip([torch.zeros_like(v) if g_ is None else g_ for g_, v in zip(gs, tv)], tv))
+emb_orc = torch.cat((pre_t.expand(2, -1), expr, post_t.expand(2, -1)), dim=1).detach().numpy()
+e_emb, e_rot = np.abs(emb_ref - emb_orc).max(), np.abs(rot_ref - rots.detach().numpy()).max()
+e_w = float((m2.generator_fine_tuned.map_final.kernel.detach() - p_ft["map_final/kernel"].detach()).abs().max())
+print("fine_tune 2 iterations on 2 images: embeddings max abs diff %.2e, rotations %.2e, map_final kernel %.2e; last loss_sum %.6f"
+      % (e_emb, e_rot, e_w, float(l_orc["loss_sum"])))
+assert e_emb < 1e-10 and e_rot < 1e-10 and e_w < 1e-10
+out["ft_emb"], out["ft_rot"] = emb_ref, rot_ref
+out["ft_w_map_final"] = sub(m2.generator_fine_tuned.map_final.kernel)
+out["ft_w_map_3d_0"] = sub(m2.generator_fine_tuned.map_3d_0.map_3d.layers[0].kernel)
+
+# ------------------------------------------------------------------------------------------------ LatentGAN steps (latent_gan.py:117-165)
+S.Model.predict = lambda self, x: self(x).detach().numpy()          # keras Model.predict: forward without a tape -> NumPy
+S.Model.set_weights = lambda self, ws: [w.data.copy_(torch.as_tensor(v)) for w, v in zip(self.trainable_weights, ws)] and None
 sys.modules["confignet.metrics"] = _Stub("confignet.metrics"); sys.modules["confignet.metrics.metrics"] = _Stub("confignet.metrics.metrics")
 lg = importlib.import_module("confignet.latent_gan")
 gan = lg.LatentGAN({"latent_dim": 145, "batch_size": 8})

@@ -49,6 +49,9 @@ class NT(torch.Tensor):
     def __truediv__(self, o):
         return torch.Tensor.__truediv__(self, T(o).to(DT) if isinstance(o, np.ndarray) else o)
 
+    def numpy(self):                       # tf.Tensor.numpy() / tf.Variable.numpy(): the value, whatever the tape state
+        return self.detach().as_subclass(torch.Tensor).numpy()
+
 
 def _ints(shape):
     return tuple(int(s) for s in shape)
@@ -125,6 +128,7 @@ class GradientTape:
 
 
 tf.GradientTape = GradientTape
+tf.Variable = lambda x, **kw: T(np.asarray(x, np.float64)).clone().requires_grad_(True).as_subclass(NT)
 
 
 # ------------------------------------------------------------------------------------------------ keras

@@ -594,6 +594,33 @@ def test_oracle_steps_match_reference_steps():
             check("s2_g", l, [P["g"]["map_3d_1/conv/kernel"], P["g"]["map_final/kernel"], P["lr"]["latent_predictor/bias"],
                               P["se"]["mlp_blendshape_values/dense1/kernel"], p_enc["A"], p_enc["Br"]])
             assert g_opt.iterations == 2 and d_opt.iterations == 4
+            # ---- ConfigNet.fine_tune_on_img (confignet_second_stage.py:321-403), 2 iterations on 2 images, asymmetric
+            #      stand-ins for the two perceptual networks (see the generating script)
+            saved_fr = O2s.face_reco_loss
+            O.perceptual_loss = lambda p_vgg, gt, gen: 1e4 * ((gt - 0.7 * gen) ** 2).mean()
+            O2s.face_reco_loss = lambda p_vgg16, gen, gt: 2e3 * ((gen - 0.5 * gt) ** 2).mean()
+            try:
+                imgs = T64(np.random.RandomState(62).randint(0, 256, (2, RES, RES, 3)).astype(np.uint8) / 127.5 - 1.0)
+                with torch.no_grad():
+                    e0, r0 = enc_fn(p_enc, imgs)
+                lo, hi = 7, 37                             # blendshape_values in the sorted latent layout
+                mean_e = e0.mean(dim=0, keepdim=True)
+                pre, expr, post, rots = [t.clone().requires_grad_(True) for t in (mean_e[:, :lo], e0[:, lo:hi], mean_e[:, hi:], r0)]
+                opt = O.KerasAdam(lr=1e-4, beta_1=0.9, beta_2=0.999)             # keras.optimizers.Adam(lr=0.0001) defaults
+                p_ft = params(netspec.generator_spec(145, RES), 221)             # generator_smoothed's weights
+                for _ in range(2):
+                    pre_t, post_t = pre.detach().clone(), post.detach().clone()  # the reference returns these (pre-update) parts
+                    l = O2s.fine_tune_losses(p_ft, P["lr"], P["d"], P["ld"], None, None, imgs, pre, expr, post, rots, weights=W2,
+                                             output_res=RES)
+                    tv = list(p_ft.values()) + [pre, post, rots, expr]
+                    gs = torch.autograd.grad(l["loss_sum"], tv, allow_unused=True)
+                    opt.apply_gradients(zip([torch.zeros_like(v) if q is None else q for q, v in zip(gs, tv)], tv))
+                emb = torch.cat((pre_t.expand(2, -1), expr, post_t.expand(2, -1)), dim=1).detach().numpy()
+                assert np.abs(emb - g["ft_emb"]).max() <= 1e-10 and np.abs(rots.detach().numpy() - g["ft_rot"]).max() <= 1e-10
+                assert np.abs(sub(p_ft["map_final/kernel"]) - g["ft_w_map_final"]).max() <= 1e-10
+                assert np.abs(sub(p_ft["map_3d_0/conv/kernel"]) - g["ft_w_map_3d_0"]).max() <= 1e-10
+            finally:
+                O2s.face_reco_loss = saved_fr
         finally:
             O2s.real_encoder_forward = saved_enc
     finally:
