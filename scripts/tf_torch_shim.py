@@ -38,13 +38,13 @@ class NT(torch.Tensor):
         return torch.Tensor.__neg__(torch.Tensor.__sub__(self, T(o)))
 
     def __mul__(self, o):
-        return torch.Tensor.__mul__(self, T(o) if isinstance(o, np.ndarray) else o)
+        return torch.Tensor.__mul__(self, T(o) if isinstance(o, (np.ndarray, tuple, list)) else o)
 
     def __add__(self, o):
-        return torch.Tensor.__add__(self, T(o) if isinstance(o, np.ndarray) else o)
+        return torch.Tensor.__add__(self, T(o) if isinstance(o, (np.ndarray, tuple, list)) else o)
 
     def __sub__(self, o):
-        return torch.Tensor.__sub__(self, T(o) if isinstance(o, np.ndarray) else o)
+        return torch.Tensor.__sub__(self, T(o) if isinstance(o, (np.ndarray, tuple, list)) else o)
 
     def __truediv__(self, o):
         return torch.Tensor.__truediv__(self, T(o).to(DT) if isinstance(o, np.ndarray) else o)

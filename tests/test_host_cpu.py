@@ -444,6 +444,16 @@ def test_oracle_matches_reference_models():
         off += dims[0]
     with torch.no_grad():
         assert close(O.synthetic_encoder_forward(p_se, parts, FM), g["se_out"], 1e-12)
+    # PerceptualLoss.loss / _loss_terms / _preprocess_input (perceptual_loss.py:43-82) for both model types, the wrapped
+    # keras-applications network played by the oracle's VGG restatement with seeded weights
+    from oracle import confignet_oracle_stage2 as O2
+    p19 = O.to_torch(netspec.init_params(netspec.vgg19_spec(), 106, vgg_like=True), dtype=torch.float64)
+    p16 = O.to_torch(netspec.init_params(netspec.vgg16_spec(), 107, vgg_like=True), dtype=torch.float64)
+    pr = torch.tensor(np.random.RandomState(13).rand(2, 32, 32, 3) * 2 - 1)
+    da = torch.tensor(np.random.RandomState(14).rand(2, 32, 32, 3) * 2 - 1)
+    with torch.no_grad():
+        assert abs(float(O.perceptual_loss(p19, pr, da)) - float(g["perc19"])) <= 1e-10 * float(g["perc19"])
+        assert abs(float(O2.face_reco_loss(p16, pr, da)) - float(g["perc16"])) <= 1e-10 * float(g["perc16"])
 
 
 def test_oracle_steps_match_reference_steps():
