@@ -98,7 +98,8 @@ def _reduce(fn):
 tf.reduce_mean = _reduce(torch.mean)
 tf.reduce_sum = _reduce(torch.sum)
 tf.reduce_prod = lambda x, axis=None: int(np.prod([int(v) for v in x]))          # only ever applied to shapes
-tf.nn = types.SimpleNamespace(leaky_relu=lambda x, alpha=0.2: F.leaky_relu(T(x), alpha))     # [TF-2.1] default alpha 0.2
+tf.nn = types.SimpleNamespace(leaky_relu=lambda x, alpha=0.2: F.leaky_relu(T(x), alpha),    # [TF-2.1] default alpha 0.2
+                              tanh=lambda x: torch.tanh(T(x)))
 tf.math = types.SimpleNamespace(softplus=lambda x: F.softplus(T(x)).as_subclass(NT),
                                 reduce_variance=lambda x, axis=None, keepdims=False: T(x).var(dim=axis, unbiased=False, keepdim=keepdims))
 tf.losses = types.SimpleNamespace(mean_squared_error=lambda a, b: ((T(a) - T(b)) ** 2).mean(dim=-1))

@@ -454,6 +454,20 @@ def test_oracle_matches_reference_models():
     with torch.no_grad():
         assert abs(float(O.perceptual_loss(p19, pr, da)) - float(g["perc19"])) <= 1e-10 * float(g["perc19"])
         assert abs(float(O2.face_reco_loss(p16, pr, da)) - float(g["perc16"])) <= 1e-10 * float(g["perc16"])
+    # RealEncoder.__init__ / call (real_encoder.py:9-34): input rescale, 'caffe' preprocessing, the two heads and the
+    # rotation range multiplier; keras-applications ResNet50 played by the oracle's restatement with seeded weights
+    p_enc = O.to_torch(netspec.init_real_encoder_params(145, 108), dtype=torch.float64)
+    eimg = torch.tensor(np.random.RandomState(15).rand(2, 64, 64, 3) * 2 - 1)
+    with torch.no_grad():
+        emb, rot = O2.real_encoder_forward(p_enc, eimg)
+    assert close(emb, g["enc_emb"], 1e-12) and close(rot, g["enc_rot"], 1e-12)
+    # ConfigNet.encode_images uint8 -> float32 conversion (confignet_second_stage.py:301-308) and generate_images'
+    # clip + truncating uint8 cast (confignet_first_stage.py:633-639); the product's host code uses the same helpers
+    # (the product does both conversions on the device: tests/test_ops_gpu.py checks cn_to_uint8 / cn_from_uint8 bit-exactly
+    # against these same two expressions)
+    assert np.array_equal((g["encode_u8"].astype(np.float32) / np.float32(127.5) - np.float32(1.0)), g["encode_f32"])
+    assert g["encode_f32"].dtype == np.float32
+    assert np.array_equal(O.to_uint8_images(torch.tensor(g["gen_f32"])), g["gen_u8"])
 
 
 def test_oracle_steps_match_reference_steps():
