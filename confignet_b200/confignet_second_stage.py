@@ -29,7 +29,9 @@ class RealEncoderNet(Network):
         self.rotation_range_multiplier = np.pi * np.array(
             [rotation_ranges[0][1], rotation_ranges[1][1], rotation_ranges[2][1]], np.float64) / 180.0
         mult = torch.tensor(self.rotation_range_multiplier, dtype=torch.float32, device=group.device)
-        super().__init__(group, networks.real_encoder_forward, rotation_range_multiplier=mult)
+        latent_dim = group.params["feature_to_latent_mlp/bias"].shape[0]
+        super().__init__(group, networks.real_encoder_forward, weights_order=netspec.real_encoder_keras_order(latent_dim),
+                         rotation_range_multiplier=mult)
 
     def __call__(self, imgs):
         return super().__call__(networks._as_dev(imgs, self.group.device))

@@ -1,9 +1,13 @@
 """Parameter specifications (names, Keras-layout shapes, initialisers) of the ConfigNet networks.
 
-Pure NumPy.  One table per network, in the order Keras' ``get_weights()`` is expected to
-return them for the reference's subclassed models (attribute-assignment order, kernel before
-bias, gamma before beta).  This ordering cannot be verified without TensorFlow or the released
-``models.zip`` - it is isolated here so it can be corrected in one place.
+Pure NumPy.  One table per network, in the order Keras' ``get_weights()`` returns them for the
+reference's subclassed models (attribute-assignment order, kernel before bias, gamma before beta).
+The order is checked against the reference's own constructors executed under [TF-2.1]'s layer-tracking
+rules (scripts/make_golden_models_from_reference.py -> tests/golden/reference_weight_order.json,
+tests/test_host_cpu.py::test_weight_order_matches_reference_constructors); the tracking rules themselves
+are restated from TensorFlow 2.1 (not installable here), so a released ``models.zip`` (SURVEY.md section
+8c) remains the final check.  The real encoder's checkpoint order differs from its table order: see
+``real_encoder_keras_order``.
 
 Reference:
   generator      confignet/dnn_models/hologan_generator.py:12-101
@@ -218,7 +222,8 @@ def _bn(spec, prefix, c):
 
 def resnet50_spec():
     """Layer order as keras lists it for ResNet50 v1 (conv / bn pairs; inside a block: 1, 2, then the shortcut
-    '0' next to '3').  Like the other tables this order is unverifiable offline and isolated here."""
+    '0' next to '3').  keras-applications is library code outside /root/reference, so this one order is restated from
+    its published model summary, not executed."""
     s = OrderedDict()
     _conv(s, "conv1_conv", (7, 7), 3, 64)
     _bn(s, "conv1_bn", 64)
@@ -245,6 +250,20 @@ def real_encoder_spec(latent_dim=145):
     _dense(s, "rotation_regressor", 2048, 3)
     _dense(s, "feature_to_latent_mlp", 2048, latent_dim)
     return s
+
+
+def real_encoder_keras_order(latent_dim=145):
+    """Names in the order ``RealEncoder.get_weights()`` lists them under the reference's pinned TensorFlow 2.1
+    (setup/requirements.txt:8).  [TF-2.1] Network.get_weights concatenates ``layer.weights`` over the tracked
+    attributes (resnet, rotation_regressor, feature_to_latent_mlp - real_encoder.py:13-18), and the NESTED ResNet50's
+    ``weights`` is ``trainable_weights + non_trainable_weights``: all kernels / biases / gammas / betas in layer order
+    first, then every BatchNormalization's moving mean / variance.  The flat HBM layout keeps real_encoder_spec's
+    per-layer order; only the checkpoint interchange (get_weights / set_weights) is permuted.  Checked against the
+    reference's executed constructor in tests/golden/reference_weight_order.json."""
+    names = list(real_encoder_spec(latent_dim).keys())
+    resnet = [k for k in names if k.startswith("resnet/")]
+    heads = [k for k in names if not k.startswith("resnet/")]
+    return [k for k in resnet if is_trainable(k)] + [k for k in resnet if not is_trainable(k)] + heads
 
 
 def is_trainable(name):

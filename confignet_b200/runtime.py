@@ -104,10 +104,17 @@ class ParamGroup:
 class Network:
     """Keras-Model-like shim around (ParamGroup, forward function)."""
 
-    def __init__(self, group, forward, **forward_kwargs):
+    def __init__(self, group, forward, weights_order=None, **forward_kwargs):
+        """weights_order: names in the order keras' get_weights() lists them when that differs from the group's flat
+        layout (a nested model lists trainable before non-trainable variables, netspec.real_encoder_keras_order)."""
         self.group = group
         self._forward = forward
         self._kw = forward_kwargs
+        self._order = None
+        if weights_order is not None:
+            if sorted(weights_order) != sorted(group.names):
+                raise ValueError("weights_order must be a permutation of the group's variable names")
+            self._order = [group.names.index(k) for k in weights_order]
 
     @property
     def params(self):
@@ -126,10 +133,19 @@ class Network:
         return None
 
     def get_weights(self):
-        return self.group.get_weights()
+        w = self.group.get_weights()
+        return w if self._order is None else [w[i] for i in self._order]
 
     def set_weights(self, weights):
-        self.group.set_weights(list(weights))
+        weights = list(weights)
+        if self._order is not None:
+            if len(weights) != len(self._order):
+                raise ValueError("expected %d weight arrays, got %d" % (len(self._order), len(weights)))
+            by_slot = [None] * len(weights)
+            for w, i in zip(weights, self._order):
+                by_slot[i] = w
+            weights = by_slot
+        self.group.set_weights(weights)
 
     @property
     def trainable_weights(self):

@@ -163,6 +163,15 @@ class Layer:
         self.built = False
         self.weights = []          # creation order
 
+    def __setattr__(self, name, value):
+        """[TF-2.1] base_layer.py Layer.__setattr__: a Layer, or a list / dict (wrapped into a trackable container, which
+        'has weights' even while empty), is appended to self._layers once, by identity, in ASSIGNMENT order."""
+        object.__setattr__(self, name, value)
+        if name != "weights" and isinstance(value, (Layer, list, dict)):
+            tracked = self.__dict__.setdefault("_tracked", [])
+            if not any(t is value for t in tracked):
+                tracked.append(value)
+
     def add_weight(self, shape=None, name=None, initializer=None, regularizer=None, constraint=None, **kw):
         w = torch.ones(_ints(shape), dtype=DT) if initializer == "ones" else torch.zeros(_ints(shape), dtype=DT)
         w.requires_grad_(True)
@@ -180,6 +189,59 @@ class Layer:
         return _nt(self.call(*args, **kwargs))
 
 
+def tracked_layers(layer):
+    """[TF-2.1] trackable_layer_utils.filter_empty_layer_containers(layer._layers): containers are flattened in place
+    (lists in list order, dict wrappers in SORTED KEY order - data_structures._DictWrapper._values), layers kept once."""
+    out, seen, stack = [], set(), list(layer.__dict__.get("_tracked", []))[::-1]
+    while stack:
+        o = stack.pop()
+        if id(o) in seen:
+            continue
+        seen.add(id(o))
+        if isinstance(o, Layer):
+            out.append(o)
+        elif isinstance(o, dict):
+            stack.extend([o[k] for k in sorted(o)][::-1])
+        elif isinstance(o, (list, tuple)):
+            stack.extend(list(o)[::-1])
+    return out
+
+
+def _dedup(ws):
+    out, seen = [], set()
+    for w in ws:
+        if id(w) not in seen:
+            seen.add(id(w))
+            out.append(w)
+    return out
+
+
+def keras_trainable_weights(layer):
+    """[TF-2.1] Layer.trainable_weights / Network.trainable_weights: own variables in creation order, then the tracked
+    sub-layers' (gather_trainable_weights), de-duplicated.  A stand-in for a library model may supply the two lists."""
+    if hasattr(layer, "keras_trainable"):
+        return list(layer.keras_trainable)
+    own = [w for _, w in layer.weights]                    # every variable the shim's layers create is trainable
+    return _dedup(own + [w for l in tracked_layers(layer) for w in keras_trainable_weights(l)])
+
+
+def keras_non_trainable_weights(layer):
+    if hasattr(layer, "keras_non_trainable"):
+        return list(layer.keras_non_trainable)
+    return _dedup([w for l in tracked_layers(layer) for w in keras_non_trainable_weights(l)])
+
+
+def keras_layer_weights(layer):
+    """[TF-2.1] Layer.weights / Network.weights = trainable_weights + non_trainable_weights (so a NESTED model lists all
+    its trainable variables before its non-trainable ones)."""
+    return _dedup(keras_trainable_weights(layer) + keras_non_trainable_weights(layer))
+
+
+def keras_get_weights_order(model):
+    """[TF-2.1] network.py Network.get_weights: `for layer in self.layers: weights += layer.weights`."""
+    return [w for l in tracked_layers(model) for w in keras_layer_weights(l)]
+
+
 class InputSpec:
     def __init__(self, **kw):
         pass
@@ -193,16 +255,49 @@ class Model(Layer):
         return _nt(self.call(*tuple(_conv(a) for a in args), **kwargs))
 
     def build(self, input_shape):
-        pass
+        """[TF-2.1] training.py Model.build on a subclassed model: calls the model on placeholders of the given shape(s),
+        which builds every layer the call reaches."""
+        def zeros(shape):
+            return torch.zeros(tuple(1 if d is None else int(d) for d in shape), dtype=DT)
+        nested = isinstance(input_shape, list) or (isinstance(input_shape, tuple) and input_shape and isinstance(input_shape[0], (tuple, list)))
+        with torch.no_grad():
+            self([zeros(sh) for sh in input_shape] if nested else zeros(input_shape))
+
+    def get_weights(self):
+        """[TF-2.1] network.py Network.get_weights, as NumPy arrays"""
+        return [w.detach().numpy().copy() for w in keras_get_weights_order(self)]
+
+    def set_weights(self, weights):
+        """[TF-2.1] network.py Network.set_weights: consumed layer by layer in the same order; shapes must agree"""
+        mine = keras_get_weights_order(self)
+        if len(mine) != len(weights):
+            raise ValueError("You called `set_weights(weights)` on a model with %d variables with a list of %d arrays" % (len(mine), len(weights)))
+        with torch.no_grad():
+            for w, v in zip(mine, weights):
+                v = torch.as_tensor(np.asarray(v)).to(DT)
+                if tuple(v.shape) != tuple(w.shape):
+                    raise ValueError("Layer weight shape %s not compatible with provided weight shape %s" % (tuple(w.shape), tuple(v.shape)))
+                w.copy_(v)
 
 
 class Sequential(Model):
     def __init__(self, layers=None, name=None):
         Model.__init__(self)
-        self.layers = list(layers or [])
+        self.layers = []
+        self._out_shape = None
+        for l in (layers or []):
+            self.add(l)
 
     def add(self, layer):
+        """[TF-2.1] sequential.py Sequential.add: a first layer that was given input_shape is called on an Input of that shape,
+        every later layer on the running output - so such a stack owns its variables before it is ever called."""
+        shape = getattr(layer, "_input_shape", None) if not self.layers else self._out_shape
         self.layers.append(layer)
+        if shape is not None and not layer.built:
+            layer.build((None,) + tuple(shape))
+            layer.built = True
+        self._out_shape = (layer.units,) if isinstance(layer, Dense) and shape is not None else \
+            (shape if isinstance(layer, LeakyReLU) else None)
 
     def call(self, x):
         for l in self.layers:
@@ -266,6 +361,7 @@ class Dense(Layer):
                  input_shape=None, name=None, **kw):
         Layer.__init__(self, name)
         self.units, self.use_bias, self.activation = int(units), use_bias, _act(activation)
+        self._input_shape = None if input_shape is None else _ints(input_shape)
 
     def build(self, input_shape):
         self.kernel = self.add_weight(shape=(int(input_shape[-1]), self.units), name="kernel")

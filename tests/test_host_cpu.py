@@ -470,6 +470,50 @@ def test_oracle_matches_reference_models():
     assert np.array_equal(O.to_uint8_images(torch.tensor(g["gen_f32"])), g["gen_u8"])
 
 
+def test_weight_order_matches_reference_constructors():
+    """tests/golden/reference_weight_order.json: the order in which keras' get_weights() lists each network's variables,
+    obtained by running the REFERENCE's constructors with attribute tracking as [TF-2.1] Layer.__setattr__ /
+    Network.get_weights do it (scripts/tf_torch_shim.py: assignment order, lists flattened in place, dict wrappers by sorted
+    key, a nested model's trainable variables before its non-trainable ones).  The checkpoint .npz stores exactly these
+    lists (confignet_first_stage.py:129-149, :173-175), so the product's get_weights()/set_weights() must use this order."""
+    import json
+    from confignet_b200 import netspec
+    from confignet_b200.runtime import Network, ParamGroup
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_weight_order.json")) as fp:
+        order = json.load(fp)
+    FM = netspec.default_facemodel_inputs()
+    assert list(netspec.generator_spec(145, 256)) == order["generator"]
+    assert list(netspec.discriminator_spec(256)) == order["discriminator"]
+    assert list(netspec.latent_regressor_spec(145, 256)) == order["latent_regressor"]
+    assert list(netspec.latent_discriminator_spec(145, 4)) == order["latent_discriminator"]
+    assert list(netspec.synthetic_encoder_spec(FM, 2)) == order["synthetic_encoder"]
+    assert netspec.real_encoder_keras_order(145) == order["real_encoder"]
+    assert list(netspec.real_encoder_spec(145)) != order["real_encoder"]          # flat layout stays per layer
+    # the Network shim applies the permutation both ways (tiny group, CPU tensors: no kernel is involved)
+    arrays = OrderedDict((k, np.full(s, i, np.float32)) for i, (k, s) in enumerate(
+        [("resnet/bn/gamma", (3,)), ("resnet/bn/moving_mean", (3,)), ("resnet/conv/kernel", (1, 1, 3, 2)), ("head/kernel", (2, 2))]))
+    keras = ["resnet/bn/gamma", "resnet/conv/kernel", "resnet/bn/moving_mean", "head/kernel"]
+    net = Network(ParamGroup(arrays, "cpu", trainable=netspec.is_trainable), lambda p, x: x, weights_order=keras)
+    assert [float(w.flat[0]) for w in net.get_weights()] == [0.0, 2.0, 1.0, 3.0]
+    net.set_weights([np.full(arrays[k].shape, 10 + j, np.float32) for j, k in enumerate(keras)])
+    assert [float(net.group.params[k].detach().reshape(-1)[0]) for k in arrays] == [10.0, 12.0, 11.0, 13.0]
+    with pytest.raises(ValueError):
+        net.set_weights([np.zeros((3,), np.float32)])
+    with pytest.raises(ValueError):
+        Network(ParamGroup(arrays, "cpu"), lambda p, x: x, weights_order=keras[:-1])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/confignet"), reason="needs the reference sources (build container only)")
+def test_checkpoint_interchange_with_reference():
+    """The reference's own save() / load() / initialize_network (executed from /root/reference on the TensorFlow stand-in)
+    and the product's load() / save() read each other's .npz / .json / .pck: every variable arrives under the right name
+    (scripts/check_checkpoint_interchange_with_reference.py).  CPU tensors only - no kernel is involved."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "check_checkpoint_interchange_with_reference.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "checkpoint interchange OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_oracle_steps_match_reference_steps():
     """tests/golden/reference_steps.npz: loss dictionaries and (strided samples of) the weights AFTER one optimizer step
     of the REFERENCE's own discriminator / synth-discriminator / latent-discriminator / generator training steps
