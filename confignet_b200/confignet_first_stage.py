@@ -98,6 +98,16 @@ def update_loss_dict(main_loss_dict, new_loss_dict):
         main_loss_dict.setdefault(key, []).append(val)
 
 
+def _log_loss_vals(loss_dict, output_dir, prefix):
+    """the text half of confignet_utils.py:214-241: one row per step, one column per loss term, names in the header"""
+    if not loss_dict:
+        return
+    os.makedirs(output_dir, exist_ok=True)
+    names = list(loss_dict.keys())
+    np.savetxt(os.path.join(output_dir, prefix + "losses.txt"), np.stack(list(loss_dict.values()), axis=1),
+               header="\t".join(names))
+
+
 def flip_random_subset_of_images(images):
     """confignet_utils.py:198-204 (same NumPy RNG consumption; flips a copy view per image)."""
     flip_or_not = np.random.randint(0, 2, size=images.shape[0])
@@ -580,13 +590,54 @@ class ConfigNetFirstStage:
         return self._detached(losses)
 
     def setup_training(self, log_dir, synth_training_set, n_samples_for_metrics, real_training_set=None):
+        """confignet_first_stage.py:562-595.  Draws from NumPy's global stream what the reference's set-up draws, in its
+        order - the InceptionMetrics sample rows (metrics/metrics.py:206; always 1000), the metric latents / rotations,
+        the checkpoint latents and the checkpoint rows of the synthetic set - so a seeded run enters its first training
+        step at the reference's stream position, and keeps the same checkpoint / metric inputs.  KID / FID themselves
+        (InceptionV3 with ImageNet weights) and TensorBoard are out of scope."""
+        if real_training_set is None:
+            real_training_set = synth_training_set
         if log_dir:
             os.makedirs(log_dir, exist_ok=True)
+        self._metric_sample_idxs = np.random.randint(0, real_training_set.imgs.shape[0], 1000)
+        self._generator_input_for_metrics = {"latent": self.sample_latent_vector(n_samples_for_metrics),
+                                             "rotation": self.sample_rotations(n_samples_for_metrics)}
+        n_rot, n_smp = self.n_checkpoint_rotations, self.n_checkpoint_samples
+        latent = np.vstack([self.sample_latent_vector(n_smp)] * n_rot)          # samples 0..n-1, repeated per rotation
+        lo, hi = self.config["rotation_ranges"][0]
+        rotation = np.zeros((n_rot, 3))
+        rotation[:, 0] = np.pi * np.linspace(lo, hi, n_rot) / 180
+        rotation = np.reshape(np.hstack([rotation] * n_smp), (-1, 3))           # each yaw n_samples times in a row
+        self._checkpoint_visualization_input = {"latent": latent, "rotation": rotation}
         self.facemodel_param_distributions = getattr(synth_training_set, "metadata_input_distributions", None)
+        facemodel_params, _, gt_imgs, _ = self.sample_synthetic_dataset(synth_training_set, n_smp)
+        self._checkpoint_visualization_input["facemodel_params"] = [np.tile(p, (n_rot, 1)) for p in facemodel_params]
+        self._checkpoint_visualization_input["gt_imgs"] = gt_imgs               # uint8 rows (the reference keeps float32 copies)
+
+    def run_checkpoints(self, output_dir, iteration_time, aml_run=None):
+        """confignet_first_stage.py:332-375: the cadence and the files a resumed run needs - the loss histories as
+        <prefix>losses.txt (confignet_utils.py:239-241) every image_checkpoint_period steps, a checkpoint under
+        <output_dir>/checkpoints/<step, 6 digits> every metrics_checkpoint_period steps (step 0 included).  Image grids
+        (OpenCV), loss plots (matplotlib), TensorBoard / AzureML scalars and KID / FID are out of scope."""
+        if not output_dir or world()[0] != 0:
+            return
+        step_number = self.get_training_step_number()
+        image_period = step_number % self.config["image_checkpoint_period"] == 0
+        if image_period:
+            _log_loss_vals(self.synth_d_losses, output_dir, "synth_discriminator_")
+            _log_loss_vals(self.latent_d_losses, output_dir, "latent_discriminator_")
+        if step_number % self.config["metrics_checkpoint_period"] == 0:
+            checkpoint_output_dir = os.path.join(output_dir, "checkpoints")
+            os.makedirs(checkpoint_output_dir, exist_ok=True)
+            self.save(checkpoint_output_dir, str(step_number).zfill(6))
+        if image_period:
+            _log_loss_vals(self.g_losses, output_dir, "generator_")
+            _log_loss_vals(self.d_losses, output_dir, "discriminator_")
+            print("Training iteration time: %f" % iteration_time)
 
     def train(self, real_training_set, synth_training_set, output_dir, log_dir, n_steps=100000,
               n_samples_for_metrics=1000, aml_run=None):
-        """confignet_first_stage.py:597-626 (loop structure and loss history; checkpoints out of scope)."""
+        """confignet_first_stage.py:597-626: loop structure, optimizer sharing, loss history, checkpoint cadence."""
         self.setup_training(log_dir, synth_training_set, n_samples_for_metrics, real_training_set=real_training_set)
         start_step = self.get_training_step_number()
         discriminator_optimizer = KerasAdam(**self.config["optimizer"])
@@ -607,6 +658,7 @@ class ConfigNetFirstStage:
             update_loss_dict(self.synth_d_losses, synth_d_loss)
             update_loss_dict(self.latent_d_losses, latent_d_loss)
             self.last_iteration_time = time.perf_counter() - t0
+            self.run_checkpoints(output_dir, self.last_iteration_time, aml_run=aml_run)
 
     # ---------------------------------------------------------------- evaluation
     def generate_images(self, latent_vector, rotations):

@@ -180,11 +180,19 @@ class ConfigNet(ConfigNetFirstStage):
 
     def setup_training(self, log_dir, synth_training_set, n_samples_for_metrics, attribute_classifier=None,
                        real_training_set=None, validation_set=None):
+        """confignet_second_stage.py:255-266: + the checkpoint / metric rows of the validation set (two more draws from
+        the NumPy stream; skipped, like the reference would fail, when there is no validation set).  The controllability
+        metrics (CelebA attribute classifier) are out of scope."""
         super().setup_training(log_dir, synth_training_set, n_samples_for_metrics, real_training_set)
+        if validation_set is not None:
+            idxs = np.random.randint(0, validation_set.imgs.shape[0], self.n_checkpoint_samples)
+            self._checkpoint_visualization_input["input_images"] = self._take_rows(validation_set.imgs, idxs)
+            idxs = np.random.randint(0, validation_set.imgs.shape[0], n_samples_for_metrics)
+            self._generator_input_for_metrics["input_images"] = self._take_rows(validation_set.imgs, idxs)
 
     def train(self, real_training_set, synth_training_set, validation_set=None, attribute_classifier=None,
               output_dir=None, log_dir=None, n_steps=100000, n_samples_for_metrics=1000, aml_run=None):
-        """confignet_second_stage.py:268-299 (loop structure and loss history; checkpoints out of scope)."""
+        """confignet_second_stage.py:268-299: loop structure, optimizer sharing, loss history, checkpoint cadence."""
         self.setup_training(log_dir, synth_training_set, n_samples_for_metrics, attribute_classifier,
                             real_training_set=real_training_set, validation_set=validation_set)
         start_step = self.get_training_step_number()
@@ -206,6 +214,7 @@ class ConfigNet(ConfigNetFirstStage):
             update_loss_dict(self.synth_d_losses, synth_d_loss)
             update_loss_dict(self.latent_d_losses, latent_d_loss)
             self.last_iteration_time = time.perf_counter() - t0
+            self.run_checkpoints(output_dir, self.last_iteration_time, aml_run=aml_run)
 
     # ---------------------------------------------------------------- evaluation
     def _images_to_device(self, input_images):

@@ -154,8 +154,33 @@ class LatentGAN:
             embeddings[begin:end], _ = confignet_model.encode_images(training_set.imgs[begin:end])
         return embeddings
 
+    def setup_logs(self, log_dir, training_set, confignet_model):
+        """latent_gan.py:200-212.  Draws from NumPy's global stream what the reference's set-up draws, in its order (the
+        logging latents, the InceptionMetrics sample rows - metrics/metrics.py:206 -, the metric latents and rotations), so a
+        seeded run enters its first step at the reference's stream position.  TensorBoard and KID / FID are out of scope."""
+        if log_dir:
+            os.makedirs(log_dir, exist_ok=True)
+        n_logged_images = self.config["logging_img_square_size"] ** 2
+        self.inputs_for_logs = {"latents": self.sample_input_latent_vector(n_logged_images),
+                                "rotations": np.zeros((n_logged_images, 3), np.float32)}
+        n = self.config["n_samples_for_metrics"]
+        self._metric_sample_idxs = np.random.randint(0, training_set.imgs.shape[0], n)
+        self.inputs_for_metrics = {"latents": self.sample_input_latent_vector(n),
+                                   "rotations": confignet_model.sample_rotations(n)}
+
+    def write_logs(self, output_dir, step_number, d_loss, g_loss, confignet_model):
+        """latent_gan.py:176-198: the checkpoint cadence (<output_dir>/checkpoints/<step, 6 digits> every
+        verbose_log_period steps, step 0 included); image grids, TensorBoard scalars and KID / FID are out of scope."""
+        if not output_dir or world()[0] != 0:
+            return
+        if step_number % self.config["verbose_log_period"] == 0:
+            checkpoint_output_dir = os.path.join(output_dir, "checkpoints")
+            os.makedirs(checkpoint_output_dir, exist_ok=True)
+            self.save(checkpoint_output_dir, str(step_number).zfill(6))
+
     def train(self, training_set, confignet_model, output_dir, log_dir, n_iters):
-        """latent_gan.py:232-247 (loop structure; logs / Inception metrics out of scope)."""
+        """latent_gan.py:232-247: set-up draws, loop structure, one optimizer for both networks, checkpoint cadence."""
+        self.setup_logs(log_dir, training_set, confignet_model)
         gt_embeddings = self.extract_embeddings(confignet_model, training_set)
         optimizer = KerasAdam(**self.config["optimizer"])
         for step_number in range(n_iters):
@@ -166,6 +191,7 @@ class LatentGAN:
             for hist, l in ((self.d_losses, d_loss), (self.g_losses, g_loss)):
                 for k, v in l.items():
                     hist.setdefault(k, []).append(float(v))
+            self.write_logs(output_dir, step_number, d_loss, g_loss, confignet_model)
 
     def generate_latents(self, n_samples, truncation=1.0):
         """latent_gan.py:249-253 -> (n, latent_dim) float32 NumPy."""

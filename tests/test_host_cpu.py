@@ -199,6 +199,186 @@ def test_class_surface_host_logic_matches_reference_golden():
     assert np.nonzero(new[0])[0].tolist() == GOLD["set_param_changed_columns"] and (lat == 0).all()
 
 
+def _tiny_set(n, seed, fm):
+    """the dataset the golden script fed the reference's setup_training (scripts/make_golden_from_reference.py make_set)"""
+    import types
+    r = np.random.RandomState(seed)
+    ds = types.SimpleNamespace()
+    ds.imgs = r.randint(0, 256, (n, 4, 4, 3)).astype(np.uint8)
+    ds.eye_masks = np.zeros((n, 4, 4), np.uint8)
+    ds.inception_features = r.rand(n, 5).astype(np.float32)
+    ds.metadata_inputs = {k: r.rand(n, d[0]).astype(np.float32) for k, d in fm.items()}
+    ds.metadata_inputs["rotations"] = r.rand(n, 3).astype(np.float32)
+    ds.metadata_input_distributions = {"tag": seed}
+    return ds
+
+
+def test_setup_training_and_train_loop_match_reference(tmp_path):
+    """The reference's own setup_training / train (confignet_first_stage.py:562-626, metrics.py:202-207) were executed
+    with recording step methods (scripts/make_golden_from_reference.py): the product must leave NumPy's global stream at
+    the same position after set-up (so a seeded run draws the reference's batches), build the same checkpoint / metric
+    inputs, call the steps in the same order with the same optimizer sharing, keep the same loss history - including the
+    reference's resume arithmetic (start = completed - 1) - and checkpoint at the same steps."""
+    from confignet_b200.confignet_first_stage import ConfigNetFirstStage
+    from confignet_b200 import runtime
+    G, T = GOLD["setup_training"], GOLD["train_loop"]
+    fm = {k: tuple(v) for k, v in netspec.default_facemodel_inputs().items()}
+    m = ConfigNetFirstStage({"output_shape": (256, 256, 3), "batch_size": 4, "facemodel_inputs": fm}, initialize=False, device="cpu")
+    real, synth = _tiny_set(13, 41, m.config["facemodel_inputs"]), _tiny_set(11, 42, m.config["facemodel_inputs"])
+    np.random.seed(G["seed"])
+    m.setup_training(str(tmp_path / "log"), synth, G["n_samples_for_metrics"], real_training_set=real)
+    ck, gm = m._checkpoint_visualization_input, m._generator_input_for_metrics
+    assert np.array_equal(gm["latent"], np.array(G["metric_latent"])) and np.array_equal(gm["rotation"], np.array(G["metric_rotation"], np.float32))
+    assert list(ck["latent"].shape) == G["checkpoint_latent_shape"]
+    assert np.array_equal(ck["latent"][[0, 10, 59]], np.array(G["checkpoint_latent_rows_0_10_59"]))
+    assert np.array_equal(ck["rotation"], np.array(G["checkpoint_rotation"]))
+    assert [list(p.shape) for p in ck["facemodel_params"]] == G["checkpoint_facemodel_param_shapes"]
+    assert np.array_equal(ck["facemodel_params"][0], np.array(G["checkpoint_facemodel_param0"], np.float32))
+    assert np.asarray(ck["gt_imgs"]).reshape(10, -1).sum(axis=1, dtype=np.float64).tolist() == G["checkpoint_gt_imgs_sum_per_image"]
+    assert m.facemodel_param_distributions == G["distributions"]
+    assert int(np.random.randint(0, 2 ** 31 - 1)) == G["next_draw_after_setup"]
+
+    calls, made = [], []
+
+    class Opt:
+        def __init__(self, **kw):
+            self.tag, self.kw = "optimizer%d" % len(made), kw
+            made.append(self)
+
+    def recorder(name, n_sets):
+        def f(*args):
+            sets, opt = args[:n_sets], args[n_sets]
+            calls.append([name] + ["real" if s is real else "synth" for s in sets] + [opt.tag])
+            return {"loss_sum": float(len(calls)), "extra": 0.5}
+        return f
+    import confignet_b200.confignet_first_stage as fs_mod
+    keep = fs_mod.KerasAdam
+    fs_mod.KerasAdam = Opt
+    try:
+        m.discriminator_training_step = recorder("discriminator_training_step", 1)
+        m.synth_discriminator_training_step = recorder("synth_discriminator_training_step", 1)
+        m.latent_discriminator_training_step = recorder("latent_discriminator_training_step", 1)
+        m.generator_training_step = recorder("generator_training_step", 2)
+        m.update_smoothed_weights = lambda: calls.append(["update_smoothed_weights"])
+        m.run_checkpoints = lambda output_dir, iteration_time, aml_run=None: calls.append(["run_checkpoints", m.get_training_step_number()])
+        m.config["n_discriminator_updates"], m.config["n_generator_updates"] = 2, 1
+        np.random.seed(G["seed"])
+        m.train(real, synth, str(tmp_path), str(tmp_path / "log"), n_steps=2, n_samples_for_metrics=G["n_samples_for_metrics"])
+        assert int(np.random.randint(0, 2 ** 31 - 1)) == T["next_draw_after_train"]
+        n_before = len(calls)
+        m.train(real, synth, str(tmp_path), str(tmp_path / "log"), n_steps=3, n_samples_for_metrics=G["n_samples_for_metrics"])
+    finally:
+        fs_mod.KerasAdam = keep
+    assert calls == T["calls"] and [o.kw for o in made[:2]] == T["optimizer_kwargs"] and len(made) == 4     # two per train()
+    assert sum(1 for c in calls[n_before:] if c[0] == "update_smoothed_weights") == T["resumed_iterations"]
+    for name in ("g_losses", "d_losses", "synth_d_losses", "latent_d_losses"):
+        assert getattr(m, name) == T[name], name
+
+    # run_checkpoints itself (confignet_first_stage.py:332-375): cadence, file names, the loss table format
+    m2 = ConfigNetFirstStage({"output_shape": (256, 256, 3), "batch_size": 4, "facemodel_inputs": fm, "image_checkpoint_period": 2,
+                              "metrics_checkpoint_period": 4}, initialize=False, device="cpu")
+    saved = []
+    m2.save = lambda d, name: saved.append((os.path.relpath(d, str(tmp_path)), name))
+    for step in range(6):
+        for hist in (m2.g_losses, m2.d_losses, m2.synth_d_losses, m2.latent_d_losses):
+            hist.setdefault("a_loss", []).append(0.25 * step)
+            hist.setdefault("loss_sum", []).append(float(step))
+        m2.run_checkpoints(str(tmp_path / "out"), 0.1)
+    assert saved == [("out/checkpoints", "000000"), ("out/checkpoints", "000004")]
+    table = np.loadtxt(str(tmp_path / "out" / "generator_losses.txt"))
+    assert table.shape == (5, 2) and table[-1].tolist() == [1.0, 4.0]                  # last written at step 4
+    with open(str(tmp_path / "out" / "latent_discriminator_losses.txt")) as fp:
+        assert fp.readline().strip() == "# a_loss\tloss_sum"
+    assert sorted(os.listdir(str(tmp_path / "out"))) == ["checkpoints", "discriminator_losses.txt", "generator_losses.txt",
+                                                         "latent_discriminator_losses.txt", "synth_discriminator_losses.txt"]
+
+
+def test_stage2_setup_training_and_train_loop_match_reference(tmp_path):
+    """ConfigNet.setup_training / train (confignet_second_stage.py:255-299) executed from the reference with recording step
+    methods: two more draws for the validation rows, the latent-discriminator step is handed the real set too."""
+    from confignet_b200.confignet_second_stage import ConfigNet
+    import confignet_b200.confignet_second_stage as s2_mod
+    G, T = GOLD["stage2_setup_training"], GOLD["stage2_train_loop"]
+    fm = {k: tuple(v) for k, v in netspec.default_facemodel_inputs().items()}
+    m = ConfigNet({"output_shape": (256, 256, 3), "batch_size": 4, "facemodel_inputs": fm}, initialize=False, device="cpu")
+    real, synth, val = (_tiny_set(n, sd, m.config["facemodel_inputs"]) for n, sd in ((13, 41), (11, 42), (9, 43)))
+    np.random.seed(G["seed"])
+    m.setup_training(str(tmp_path / "log2"), synth, 7, None, real_training_set=real, validation_set=val)
+    sums = lambda a, n: np.asarray(a).reshape(n, -1).sum(axis=1, dtype=np.float64).tolist()           # rows kept as uint8 here
+    assert sums(m._checkpoint_visualization_input["input_images"], 10) == G["checkpoint_input_images_sum_per_image"]
+    assert sums(m._generator_input_for_metrics["input_images"], 7) == G["metric_input_images_sum_per_image"]
+    assert int(np.random.randint(0, 2 ** 31 - 1)) == G["next_draw_after_setup"]
+
+    calls, made = [], []
+
+    class Opt:
+        def __init__(self, **kw):
+            self.tag = "optimizer%d" % len(made)
+            made.append(self)
+
+    def recorder(name, n_sets):
+        def f(*args):
+            sets, opt = args[:n_sets], args[n_sets]
+            calls.append([name] + ["real" if s is real else "synth" for s in sets] + [opt.tag])
+            return {"loss_sum": float(len(calls))}
+        return f
+    keep = s2_mod.KerasAdam
+    s2_mod.KerasAdam = Opt
+    try:
+        m.discriminator_training_step = recorder("discriminator_training_step", 1)
+        m.synth_discriminator_training_step = recorder("synth_discriminator_training_step", 1)
+        m.latent_discriminator_training_step = recorder("latent_discriminator_training_step", 2)
+        m.generator_training_step = recorder("generator_training_step", 2)
+        m.update_smoothed_weights = lambda: calls.append(["update_smoothed_weights"])
+        m.run_checkpoints = lambda output_dir, iteration_time, aml_run=None: calls.append(["run_checkpoints", m.get_training_step_number()])
+        m.train(real, synth, val, None, str(tmp_path), str(tmp_path / "log2"), n_steps=2, n_samples_for_metrics=7)
+    finally:
+        s2_mod.KerasAdam = keep
+    assert calls == T["calls"]
+
+
+def test_latent_gan_setup_and_train_loop_match_reference(tmp_path):
+    """LatentGAN.setup_logs / train (latent_gan.py:200-247) executed from the reference with recording step methods: same
+    stream position after set-up, same logging / metric inputs, set-up before the embedding extraction, one optimizer for
+    both networks, a checkpoint every verbose_log_period steps."""
+    import types
+    from confignet_b200.latent_gan import LatentGAN
+    from confignet_b200.confignet_first_stage import ConfigNetFirstStage
+    import confignet_b200.latent_gan as lg_mod
+    G, T = GOLD["latent_gan_setup"], GOLD["latent_gan_train"]
+    fm = {k: tuple(v) for k, v in netspec.default_facemodel_inputs().items()}
+    cn = ConfigNetFirstStage({"output_shape": (256, 256, 3), "batch_size": 4, "facemodel_inputs": fm}, initialize=False, device="cpu")
+    real = _tiny_set(13, 41, cn.config["facemodel_inputs"])
+    gan = LatentGAN({"latent_dim": 145, "n_samples_for_metrics": 9, "verbose_log_period": 2}, device="cpu")
+    np.random.seed(G["seed"])
+    gan.setup_logs(str(tmp_path / "gan_log"), real, cn)
+    assert list(gan.inputs_for_logs["latents"].shape) == G["log_latents_shape"]
+    assert np.array_equal(gan.inputs_for_logs["latents"][[0, 35]], np.array(G["log_latents_rows_0_35"]))
+    assert (gan.inputs_for_logs["rotations"] == 0).all() == G["log_rotations_all_zero"]
+    assert np.array_equal(gan.inputs_for_metrics["latents"], np.array(G["metric_latents"]))
+    assert np.array_equal(gan.inputs_for_metrics["rotations"], np.array(G["metric_rotations"], np.float32))
+    assert int(np.random.randint(0, 2 ** 31 - 1)) == G["next_draw_after_setup"]
+
+    calls, made = [], []
+
+    class Opt:
+        def __init__(self, **kw):
+            self.tag, self.kw = "optimizer%d" % len(made), kw
+            made.append(self)
+    gan.extract_embeddings = lambda confignet_model, training_set: calls.append(["extract_embeddings"]) or "embeddings"
+    gan.discriminator_training_step = lambda emb, opt: calls.append(["discriminator_training_step", emb, opt.tag]) or {"loss_sum": 1.0}
+    gan.generator_training_step = lambda opt: calls.append(["generator_training_step", opt.tag]) or {"loss_sum": 2.0}
+    gan.update_smoothed_weights = lambda: calls.append(["update_smoothed_weights"])
+    gan.save = lambda d, name: calls.append(["save", os.path.relpath(d, str(tmp_path)), name])
+    keep = lg_mod.KerasAdam
+    lg_mod.KerasAdam = Opt
+    try:
+        gan.train(real, cn, str(tmp_path), str(tmp_path / "gan_log"), 3)
+    finally:
+        lg_mod.KerasAdam = keep
+    assert calls == T["calls"] and [o.kw for o in made] == T["optimizer_kwargs"]
+
+
 def test_reference_golden_npz_shapes_are_what_generate_images_returns():
     g = GOLD["reference_golden_npz_shapes"]
     assert g["confignet_basic_ref_256"]["decoded_image"] == [[1, 256, 256, 3], "uint8"]
