@@ -372,7 +372,10 @@ class ConfigNetFirstStage:
     def _to_device(self, arr, dtype):
         if isinstance(arr, torch.Tensor):
             return arr.to(self.device, dtype)
-        t = torch.from_numpy(np.ascontiguousarray(arr))
+        arr = np.ascontiguousarray(arr)
+        if not arr.flags.writeable:            # a slice of the dataset's read-only np.memmap (neural_renderer_dataset.py:346)
+            arr = np.array(arr)
+        t = torch.from_numpy(arr)
         ConfigNetFirstStage.h2d_bytes += t.numel() * t.element_size()
         if self.device.type != "cuda":
             return t.to(self.device).to(dtype)

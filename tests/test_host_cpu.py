@@ -599,6 +599,12 @@ def test_oracle_matches_reference_models():
         img = O.generator_forward(p_g, torch.tensor(g["gen_z"]), torch.tensor(g["gen_rot"]), 256)
     assert close(img[0, ::8, ::8], g["gen_out_sub8"])                    # hologan_generator.py:129-174, building_blocks.py
 
+    for res, seed in ((128, 111), (512, 112)):                          # hologan_generator.py:84-101: without map_2d_2b / with map_2d_2c
+        p_r = params(netspec.generator_spec(145, res), seed)
+        with torch.no_grad():
+            img_r = O.generator_forward(p_r, torch.tensor(g["gen_z"]), torch.tensor(g["gen_rot"]), res)
+        assert img_r.shape == (1, res, res, 3) and close(img_r[0, ::res // 32, ::res // 32], g["gen%d_out_sub" % res])
+
     p_d = params(netspec.discriminator_spec(256), 102)
     real = torch.tensor(np.random.RandomState(12).rand(1, 256, 256, 3) * 2 - 1)
     with torch.no_grad():
@@ -663,6 +669,8 @@ def test_weight_order_matches_reference_constructors():
         order = json.load(fp)
     FM = netspec.default_facemodel_inputs()
     assert list(netspec.generator_spec(145, 256)) == order["generator"]
+    assert list(netspec.generator_spec(145, 128)) == order["generator_128"] and len(order["generator_128"]) == 40
+    assert list(netspec.generator_spec(145, 512)) == order["generator_512"] and len(order["generator_512"]) == 52
     assert list(netspec.discriminator_spec(256)) == order["discriminator"]
     assert list(netspec.latent_regressor_spec(145, 256)) == order["latent_regressor"]
     assert list(netspec.latent_discriminator_spec(145, 4)) == order["latent_discriminator"]
@@ -692,6 +700,18 @@ def test_checkpoint_interchange_with_reference():
     r = subprocess.run([sys.executable, os.path.join(root, "scripts", "check_checkpoint_interchange_with_reference.py")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "checkpoint interchange OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/confignet"), reason="needs the reference sources (build container only)")
+def test_reference_training_scripts_run_on_the_product():
+    """The reference's own train_confignet.py and train_latent_gan.py (the bodies of its tests/training_test.py) on its own
+    test dataset, with `confignet` exporting the product's classes (the one-import switch of INTEGRATION.md): they must get
+    to the first kernel and fail loudly there (no CPU fallback), and - with the step methods recorded - run to the end and
+    leave the reference's output layout (scripts/run_reference_training_script_on_product.py)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "run_reference_training_script_on_product.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "reference training script OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
 def test_oracle_steps_match_reference_steps():
