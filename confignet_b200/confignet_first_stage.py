@@ -210,6 +210,13 @@ class ConfigNetFirstStage:
     def _make_group(self, spec, seed, vgg_like=False):
         return ParamGroup(netspec.init_params(spec, seed, vgg_like=vgg_like), self.device)
 
+    def _get_generator_kwargs(self):
+        """confignet_first_stage.py:240-248."""
+        c = self.config
+        return {"latent_dim": c["latent_dim"], "output_shape": tuple(c["output_shape"][:2]),
+                "n_adain_mlp_units": c["n_adain_mlp_units"], "n_adain_mlp_layers": c["n_adain_mlp_layers"],
+                "gen_output_activation": c["gen_output_activation"]}
+
     def initialize_network(self):
         """confignet_first_stage.py:251-287."""
         c = self.config
@@ -617,7 +624,7 @@ class ConfigNetFirstStage:
         self._checkpoint_visualization_input["facemodel_params"] = [np.tile(p, (n_rot, 1)) for p in facemodel_params]
         self._checkpoint_visualization_input["gt_imgs"] = gt_imgs               # uint8 rows (the reference keeps float32 copies)
 
-    def run_checkpoints(self, output_dir, iteration_time, aml_run=None):
+    def run_checkpoints(self, output_dir, iteration_time, aml_run=None, checkpoint_start=None):
         """confignet_first_stage.py:332-375: the cadence and the files a resumed run needs - the loss histories as
         <prefix>losses.txt (confignet_utils.py:239-241) every image_checkpoint_period steps, a checkpoint under
         <output_dir>/checkpoints/<step, 6 digits> every metrics_checkpoint_period steps (step 0 included).  Image grids

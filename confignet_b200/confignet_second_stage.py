@@ -74,6 +74,13 @@ class ConfigNet(ConfigNetFirstStage):
         for v in self.perceptual_loss_face_reco.group.params.values():
             v.requires_grad_(False)
 
+    def face_reco_loss(self, gt_imgs, gen_imgs):
+        """confignet_second_stage.py:88-91: the VGGFace perceptual loss with (generated, ground truth) in the reference's
+        argument order; device tensors (or arrays) in [-1, 1]."""
+        dev = self.device
+        return networks.perceptual_loss(self.perceptual_loss_face_reco.params, networks._as_dev(gen_imgs, dev),
+                                        networks._as_dev(gt_imgs, dev), model_type="VGGFace")
+
     def get_weights(self, return_tensors=False):
         w = super().get_weights()
         w["real_encoder_weights"] = self.encoder.get_weights()
