@@ -402,6 +402,35 @@ def test_class_surface_covers_reference_methods():
                 assert mine[m][:len(args)] == args                      # + device / seed keywords after them
 
 
+def test_committed_bench_lines_keep_the_contract():
+    """profiles/r01_bench_final.json / _n2_final / _reference_final: the JSON lines bench.py printed on the B200 box carry every
+    key of the bench contract, the metric BASELINE.json names, a roofline measured on the tensor-core kernel and a bounded CPU
+    baseline; the reference arm says so."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def line(name):
+        with open(os.path.join(root, "profiles", name)) as fp:
+            return json.loads(fp.read().strip().splitlines()[-1])
+    with open(os.path.join(root, "BASELINE.json")) as fp:
+        base = json.load(fp)
+    keys = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+            "dtype", "data", "config", "e2e", "gpu_launches", "cpu_baseline"}
+    for name, n in (("r01_bench_final.json", 1), ("r01_bench_n2_final.json", 2)):
+        d = line(name)
+        assert keys | {"clocks", "roofline"} <= set(d), (name, keys - set(d))
+        assert d["n_gpus"] == n and d["higher_is_better"] is True and d["scaling"] == "weak" and d["data"] == "synthetic"
+        assert d["metric"].split(" (")[0] in base["metric"].replace("\u00d7", "x").replace("×", "x") and d["unit"] == "images/s"
+        assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and "workload" in d["config"] and "model" not in d["config"]
+        assert abs(d["value"] - n * d["config"]["per_gpu_batch"] / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+        r = d["roofline"]
+        assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0 < r["frac"] <= 1.0 / 6
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    d = line("r01_bench_reference_final.json")
+    assert keys | {"impl"} <= set(d) and d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
 def test_reference_golden_npz_shapes_are_what_generate_images_returns():
     g = GOLD["reference_golden_npz_shapes"]
     assert g["confignet_basic_ref_256"]["decoded_image"] == [[1, 256, 256, 3], "uint8"]
