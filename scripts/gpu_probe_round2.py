@@ -1,0 +1,141 @@
+"""Runs the round-2 design probes (confignet_b200/csrc/experiments/round2_probes.cu, built by __graft_entry__.build()
+into confignet_b200/lib/libcn_probes.so) on a B200 and writes gpurun_out/round2_probes.txt:
+
+    gpurun --timeout 300 -- 'timeout 240 python scripts/gpu_probe_round2.py'
+
+  1. what kind::tf32 does with the low 13 mantissa bits of a raw fp32 operand (truncate / round-to-nearest);
+  2. whether a tiled (C, W, H, N) tensor map with negative / overhanging start coordinates and element strides delivers the
+     SAME-padded im2col rows of one (tap, 32-channel) k-block in the swizzled K-major layout the UMMA descriptor reads;
+  3. a 3x3 SAME convolution (stride 1 and 2) whose A operand is fetched only by TMA and read by the MMA from shared memory.
+
+The product library is not involved; nothing here is on the bench or test path.
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "confignet_b200", "lib", "libcn_probes.so")
+OUT = os.path.join(ROOT, "gpurun_out", "round2_probes.txt")
+lines = []
+
+
+def say(*a):
+    s = " ".join(str(x) for x in a)
+    print(s, flush=True)
+    lines.append(s)
+
+
+def swz_off(row, k):
+    return (row >> 3) * 1024 + (row & 7) * 128 + (((k >> 2) ^ (row & 7)) << 4) + (k & 3) * 4
+
+
+def trunc13(a):
+    return (np.asarray(a, np.float32).view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
+
+
+def round13(a, ties_away):
+    u = np.asarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    if ties_away:
+        u = (u + 0x1000) & 0xffffe000
+    else:
+        u = (u + 0xfff + ((u >> 13) & 1)) & 0xffffe000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def main():
+    assert torch.cuda.is_available(), "needs a GPU"
+    lib = ctypes.CDLL(LIB)
+    dev = torch.device("cuda:0")
+    P = ctypes.c_void_p
+    lib.probe_tf32_operands.argtypes = [P, P, P]
+    lib.probe_tma_tile.argtypes = [P] + [ctypes.c_int] * 11 + [P]
+    lib.probe_conv_tma.argtypes = [P, P, P] + [ctypes.c_int] * 5
+    rng = np.random.RandomState(0)
+
+    # ---------------------------------------------------------------- 1. operand handling
+    A = (rng.rand(128, 32).astype(np.float32) + 1.0)
+    A[0, :] = np.float32(1 + 2.0 ** -11)                      # midpoint: trunc 1, ties-away 1+2^-10, ties-even 1
+    A[1, :] = np.float32(1 + 2.0 ** -11 + 2.0 ** -20)         # just above the midpoint: both roundings 1+2^-10, trunc 1
+    A[2, :] = np.float32(1 + 3 * 2.0 ** -11)                  # midpoint: trunc 1+2^-10, both roundings 1+2^-9
+    B = (rng.rand(16, 32).astype(np.float32) + 1.0)
+    B[0, :] = 1.0
+    dA, dB, dD = torch.tensor(A, device=dev), torch.tensor(B, device=dev), torch.zeros(128, 16, device=dev)
+    r = lib.probe_tf32_operands(dA.data_ptr(), dB.data_ptr(), dD.data_ptr())
+    say("1. probe_tf32_operands ->", r)
+    if r == 0:
+        D = dD.cpu().numpy().astype(np.float64)
+        models = {"truncate": (trunc13(A), trunc13(B)), "round-nearest-away": (round13(A, True), round13(B, True)),
+                  "round-nearest-even": (round13(A, False), round13(B, False))}
+        for name, (a, b) in models.items():
+            ref = a.astype(np.float64) @ b.astype(np.float64).T
+            say("   model %-20s max rel err %.3e   (rows 0..2, col 0: %s)" % (name, np.abs(D - ref).max() / np.abs(ref).max(),
+                                                                         (ref[:3, 0] / 32).tolist()))
+        say("   measured rows 0..2, col 0 / 32:", (D[:3, 0] / 32).tolist())
+
+    # ---------------------------------------------------------------- 2. TMA tile with OOB fill / element strides
+    def tile_case(N, H, W, C, bw, bh, stride, c, xs, ys, n):
+        x = np.arange(N * H * W * C, dtype=np.float32).reshape(N, H, W, C) + 1.0
+        dx, out = torch.tensor(x, device=dev), torch.zeros(128 * 32, device=dev)
+        r = lib.probe_tma_tile(dx.data_ptr(), N, H, W, C, bw, bh, stride, c, xs, ys, n, out.data_ptr())
+        if r:
+            say("   tile N%d H%d W%d C%d box %dx%d stride %d start (c%d,x%d,y%d,n%d) -> error %d" % (N, H, W, C, bw, bh, stride, c, xs, ys, n, r))
+            return
+        raw = out.cpu().numpy()
+        got, want = np.zeros((128, 32), np.float32), np.zeros((128, 32), np.float32)
+        for row in range(128):
+            xl, yl = row % bw, row // bw
+            px, py = xs + xl * stride, ys + yl * stride
+            for k in range(32):
+                got[row, k] = raw[swz_off(row, k) // 4]
+                if 0 <= px < W and 0 <= py < H and 0 <= n < N and c + k < C:
+                    want[row, k] = x[n, py, px, c + k]
+        bad = int((got != want).sum())
+        say("   tile N%d H%d W%d C%d box %dx%d stride %d start (c%d,x%d,y%d,n%d): %d of 4096 elements differ%s" %
+            (N, H, W, C, bw, bh, stride, c, xs, ys, n, bad, "" if not bad else "  first rows got %s want %s" % (got[:2, :4].tolist(), want[:2, :4].tolist())))
+
+    say("2. probe_tma_tile (zero fill = SAME padding, swizzled K-major rows)")
+    tile_case(2, 16, 16, 64, 16, 8, 1, 32, -1, -1, 1)
+    tile_case(2, 16, 16, 64, 16, 8, 1, 0, 1, 9, 0)            # overhang right / bottom
+    tile_case(1, 32, 32, 32, 16, 8, 2, 0, 0, 0, 0)            # stride 2, tap 0 of a pad-0-in-front SAME conv
+    tile_case(1, 32, 32, 32, 16, 8, 2, 0, 2, 18, 0)           # stride 2, last tap, bottom rows overhang
+    tile_case(1, 4, 128, 32, 128, 1, 1, 0, -1, 3, 0)          # one image row per tile
+
+    # ---------------------------------------------------------------- 3. conv through TMA + SS-form MMA
+    def conv_case(N, H, W, C, stride):
+        x = rng.randint(-2, 3, (N, H, W, C)).astype(np.float32)
+        w = rng.randint(-2, 3, (3, 3, C, 16)).astype(np.float32)
+        cblocks = C // 32
+        wp = np.zeros((9 * cblocks, 16 * 32), np.float32)
+        for tap in range(9):
+            for cb in range(cblocks):
+                for nn in range(16):
+                    for k in range(32):
+                        wp[tap * cblocks + cb, swz_off(nn, k) // 4] = w[tap // 3, tap % 3, cb * 32 + k, nn]
+        Ho, Wo = -(-H // stride), -(-W // stride)
+        y = torch.zeros(N, Ho, Wo, 16, device=dev)
+        r = lib.probe_conv_tma(torch.tensor(x, device=dev).data_ptr(), torch.tensor(wp, device=dev).data_ptr(), y.data_ptr(), N, H, W, C, stride)
+        if r:
+            say("   conv N%d H%d W%d C%d stride %d -> error %d" % (N, H, W, C, stride, r))
+            return
+        tot = max((Ho - 1) * stride + 3 - H, 0)
+        xp = torch.nn.functional.pad(torch.tensor(x).permute(0, 3, 1, 2).double(), (tot // 2, tot - tot // 2, tot // 2, tot - tot // 2))
+        ref = torch.nn.functional.conv2d(xp, torch.tensor(w).permute(3, 2, 0, 1).double(), stride=stride).permute(0, 2, 3, 1).numpy()
+        say("   conv N%d H%d W%d C%d stride %d: max abs diff %.3g (exact integers expected: 0)" %
+            (N, H, W, C, stride, float(np.abs(y.cpu().numpy() - ref).max())))
+
+    say("3. probe_conv_tma (A fetched by TMA only, MMA reads it from shared memory)")
+    conv_case(2, 16, 16, 64, 1)
+    conv_case(1, 32, 32, 32, 2)
+    conv_case(1, 4, 128, 32, 1)
+    conv_case(1, 64, 64, 96, 2)
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    with open(OUT, "w") as fp:
+        fp.write("\n".join(lines) + "\n")
+
+
+if __name__ == "__main__":
+    sys.exit(main())
