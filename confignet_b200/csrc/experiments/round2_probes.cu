@@ -1,7 +1,7 @@
 // Round-2 probes for the tcgen05 convolution kernel.  NOT part of
-// libconfignet_b200.so: built into confignet_b200/lib/libcn_probes.so by scripts/build_probes.sh and driven by
+// libconfignet_b200.so: built into confignet_b200/lib/libcn_probes.so by __graft_entry__.build() and driven by
 // scripts/gpu_probe_round2.py.  Three questions that decide the next kernel design, each answered by a tiny
-// single-purpose kernel that is checked against a host model:
+// single-purpose kernel that is checked against a host model, and the candidate kernel they lead to:
 //
 //   1. probe_tf32_operands   what does kind::tf32 do with the 13 low mantissa bits of a raw fp32 operand -
 //                            ignore them (truncate) or round?  If it truncates, the two "big" products of the
@@ -14,6 +14,8 @@
 //   3. probe_conv_tma        both together: a 3x3 SAME convolution (stride 1 or 2, Cout = 16) whose A operand is
 //                            fetched ONLY by TMA (no per-thread gathers) and fed to the MMA straight from shared
 //                            memory (SS form, one tf32 product - integer test data keep it exact).
+//   4. probe_conv_tma_fast   the candidate: persistent, pipelined, 3xTF32, TMA-fed A with only a_small built by threads,
+//                            coalesced channel-major epilogue; timed against the production kernel on the same layer.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -200,6 +202,231 @@ __global__ void __launch_bounds__(128) conv_tma_kernel(const __grid_constant__ C
   tmem_free32(tmem, warp);
 }
 
+// ---- 4. the candidate: pipelined, persistent, 3xTF32 forward 3x3 SAME convolution (stride 1 / 2, Cout = BN <= 128)
+//         * A: raw fp32 tile by TMA (no per-thread gathers).  The two products that use a_big read the RAW tile from shared
+//           memory (SS form; kind::tf32 is assumed to ignore the 13 low mantissa bits - probe 1 decides), only a_small is
+//           built (4 warps: ld.shared of the swizzled rows, 3 ALU ops per element, tcgen05.st into a tensor-memory stage).
+//         * B: pre-split, pre-swizzled stage images (big plane, small plane) by one bulk copy per k-block, as in production.
+//         * two ping-pong accumulators, a chunk of CH k-blocks each, promoted into an fp32 running total in shared memory
+//           ([column][129] floats: lane = row for the promotion, lane = column for the final pass - both conflict-free).
+//         * epilogue: bias + LeakyReLU, lanes along the CHANNELS so that every store instruction writes one 128-byte line
+//           (production stores one row per thread: 32 lines per instruction).
+//         warps: 0 TMA producer, 1 MMA issue, 2-5 a_small builders, 6-9 promotion / epilogue.
+constexpr int F_THREADS = 320;
+constexpr int F_CH = 8;                    // k-blocks per accumulation chunk (production: TC_CHUNK_KB)
+constexpr int F_TOT_LD = 129;              // leading dimension of the running total
+
+struct FastCfg { int stages, stage_bytes, b_plane, tot_off, bar_off, tmem_off, smem_bytes, a_col0; };
+__host__ __device__ inline FastCfg fast_cfg(int bn) {
+  FastCfg c;
+  c.b_plane = bn * 128;
+  c.stage_bytes = A_BYTES + 2 * c.b_plane;
+  const int tot_bytes = ((bn * F_TOT_LD * 4) + 1023) & ~1023;
+  int st = (226 * 1024 - tot_bytes) / c.stage_bytes;      // 227 KB per CTA minus the alignment slack and the barriers
+  if (st > 6) st = 6;
+  while (2 * bn + st * 32 > 512) --st;
+  c.stages = st;
+  c.tot_off = st * c.stage_bytes;
+  c.bar_off = c.tot_off + tot_bytes;
+  c.tmem_off = c.bar_off + 8 * (3 * 6 + 4);
+  c.smem_bytes = c.tmem_off + 16;
+  c.a_col0 = 2 * bn;
+  return c;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_constant__ CUtensorMap map, const float* __restrict__ wp,
+                                                                  const float* __restrict__ bias, float* __restrict__ y, int N, int Ho, int Wo,
+                                                                  int C, int bn, int stride, int pad, int bw, int bh, float alpha) {
+  extern __shared__ unsigned char raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  const FastCfg L = fast_cfg(bn);
+  const uint32_t sbase = smem_u32(sm);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = L.stages;
+  const uint32_t bar_full = sbase + L.bar_off, bar_small = bar_full + 8 * 6, bar_empty = bar_small + 8 * 6,
+                 bar_accfull = bar_empty + 8 * 6, bar_accempty = bar_accfull + 8 * 2;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_small + 8 * s, 128); mbar_init(bar_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_accfull + 8 * b, 1); mbar_init(bar_accempty + 8 * b, 128); }
+  }
+  fence_proxy_async();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + L.tmem_off), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_off);
+  const int tiles_x = Wo / bw, tiles_y = Ho / bh, n_tiles = N * tiles_x * tiles_y;
+  const int cblocks = C / 32, num_kb = 9 * cblocks;
+  const uint32_t stage_tx = (uint32_t)L.stage_bytes;
+
+  if (warp == 0) {
+    // ===== producer: one TMA tile (A) + one bulk copy (B big + small planes) per k-block =====
+    if (lane == 0) {
+      int s = 0, ph = 0; long git = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int n = t / (tiles_x * tiles_y), ty = (t / tiles_x) % tiles_y, tx = t % tiles_x;
+        for (int kb = 0; kb < num_kb; ++kb, ++git) {
+          if (git >= S) mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const int tap = kb / cblocks, cb = kb % cblocks;
+          const uint32_t dst = sbase + s * L.stage_bytes;
+          mbar_arrive_expect_tx(bar_full + 8 * s, stage_tx);
+          tma_load_4d(dst, &map, cb * 32, tx * bw * stride + tap % 3 - pad, ty * bh * stride + tap / 3 - pad, n, bar_full + 8 * s);
+          bulk_g2s(dst + A_BYTES, wp + (size_t)kb * (2 * L.b_plane / 4), 2 * L.b_plane, bar_full + 8 * s);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issue: per k-step (a_small [tmem] x b_big), (a_big x b_small), (a_big x b_big) =====
+    const uint32_t idesc = umma_idesc_tf32(bn);
+    int s = 0, ph = 0, b = 0, inchunk = 0, c = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const bool chunk_first = inchunk == 0, chunk_last = inchunk == F_CH - 1 || kb == num_kb - 1;
+        if (chunk_first && c >= 2) mbar_wait(bar_accempty + 8 * b, ((c >> 1) - 1) & 1);
+        mbar_wait(bar_full + 8 * s, ph);
+        mbar_wait(bar_small + 8 * s, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = sbase + s * L.stage_bytes;
+          const uint64_t ad = umma_desc_k128(a_addr), bb = umma_desc_k128(a_addr + A_BYTES), bs = umma_desc_k128(a_addr + A_BYTES + L.b_plane);
+          const uint32_t d_t = tmem + b * bn, a_small = tmem + L.a_col0 + s * 32;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            tc_mma_tf32_ts(d_t, a_small + kk * 8, bb + kk * 2, idesc, !(chunk_first && kk == 0));
+            tc_mma_tf32_ss(d_t, ad + kk * 2, bs + kk * 2, idesc, 1);
+            tc_mma_tf32_ss(d_t, ad + kk * 2, bb + kk * 2, idesc, 1);
+          }
+          tc_commit(bar_empty + 8 * s);
+          if (chunk_last) tc_commit(bar_accfull + 8 * b);
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1; }
+        if (++inchunk == F_CH || kb == num_kb - 1) { inchunk = 0; ++c; b ^= 1; }
+      }
+    }
+  } else if (warp < 6) {
+    // ===== a_small builders: row = tensor-memory lane; the raw row is read from the swizzled stage =====
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u, x7 = (uint32_t)(row & 7);
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    int s = 0, ph = 0; long git = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb, ++git) {
+        mbar_wait(bar_full + 8 * s, ph);
+        if (git >= S) mbar_wait(bar_empty + 8 * s, ph ^ 1);          // the tensor-memory stage was read by the MMAs of its last use
+        tc_fence_after();
+        uint32_t v[32];
+        const uint32_t a_addr = sbase + s * L.stage_bytes + row_off;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t q0, q1, q2, q3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q0), "=r"(q1), "=r"(q2), "=r"(q3) : "r"(a_addr + ((j ^ x7) << 4)));
+          const uint32_t q[4] = {q0, q1, q2, q3};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float xv = __uint_as_float(q[i]);
+            v[4 * j + i] = __float_as_uint(xv - __uint_as_float(q[i] & 0xffffe000u)) & 0xffffe000u;
+          }
+        }
+        tc_st32(tmem + lane_addr + L.a_col0 + s * 32, v);
+        tc_fence_before();
+        mbar_arrive(bar_small + 8 * s);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===== promotion + epilogue =====
+    const int q = warp & 3, row = q * 32 + lane;
+    float* tot = reinterpret_cast<float*>(sm + L.tot_off);
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    int b = 0, c = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int nchunks = (num_kb + F_CH - 1) / F_CH;
+      for (int ch = 0; ch < nchunks; ++ch, ++c) {
+        mbar_wait(bar_accfull + 8 * b, (c >> 1) & 1);
+        tc_fence_after();
+        for (int c0 = 0; c0 < bn; c0 += 32) {
+          float* dst = tot + c0 * F_TOT_LD + row;
+          if (bn - c0 >= 32) {
+            uint32_t v[32];
+            tc_ld32(tmem + lane_addr + b * bn + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[j * F_TOT_LD] = ch == 0 ? __uint_as_float(v[j]) : dst[j * F_TOT_LD] + __uint_as_float(v[j]);
+          } else {
+            uint32_t v[16];
+            tc_ld16(tmem + lane_addr + b * bn + c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[j * F_TOT_LD] = ch == 0 ? __uint_as_float(v[j]) : dst[j * F_TOT_LD] + __uint_as_float(v[j]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_accempty + 8 * b);
+        b ^= 1;
+      }
+      __syncwarp();                               // a warp finishes the 32 rows it promoted itself: no cross-warp dependency
+      const int n = t / (tiles_x * tiles_y), ty = (t / tiles_x) % tiles_y, tx = t % tiles_x;
+      float bz[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bz[i] = lane + 32 * i < bn ? bias[lane + 32 * i] : 0.f;
+      for (int r = q * 32; r < q * 32 + 32; ++r) {
+        const int px = tx * bw + r % bw, py = ty * bh + r / bw;
+        float* dst = y + (((size_t)n * Ho + py) * Wo + px) * bn;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c0 = lane + 32 * i;
+          if (c0 < bn) {
+            const float v = tot[c0 * F_TOT_LD + r] + bz[i];
+            dst[c0] = v > 0.f ? v : alpha * v;
+          }
+        }
+      }
+      __syncwarp();                               // the rows may be overwritten by the next tile's first chunk
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -250,6 +477,39 @@ extern "C" int probe_tma_tile(const float* x, int N, int H, int W, int C, int bw
   if (prep(tma_tile_kernel)) return -2;
   tma_tile_kernel<<<1, 128, sizeof(ProbeSmem) + 1024>>>(map, c, xs, ys, n, out);
   return finish();
+}
+
+// wp: per k-block (tap-major, then 32-channel block) the big plane then the small plane, each bn rows x 128 B in the swizzled
+// K-major layout.  Launches `iters` times on the default stream; *avg_us receives the mean launch time (CUDA events).
+extern "C" int probe_conv_tma_fast(const float* x, const float* wp, const float* bias, float* y, int N, int H, int W, int C, int bn,
+                                   int stride, float alpha, int iters, float* avg_us) {
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  const int bw = Wo < 128 ? Wo : 128, bh = 128 / bw;
+  if (C % 32 || bn % 16 || bn > 128 || 128 % bw || Wo % bw || Ho % bh) return -2;
+  const int total = (Ho - 1) * stride + 3 - H, pad = (total > 0 ? total : 0) / 2;
+  CUtensorMap map;
+  const int r = make_map(&map, x, N, H, W, C, bw, bh, stride);
+  if (r) return r;
+  const FastCfg L = fast_cfg(bn);
+  if (L.stages < 2) return -2;
+  if (cudaFuncSetAttribute(conv_tma_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes + 1024) != cudaSuccess) return -2;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n_tiles = N * (Ho / bh) * (Wo / bw), grid = n_tiles < sms ? n_tiles : sms;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int it = 0; it < iters + 1; ++it) {
+    if (it == 1) cudaEventRecord(e0);
+    conv_tma_fast_kernel<<<grid, F_THREADS, L.smem_bytes + 1024>>>(map, wp, bias, y, N, Ho, Wo, C, bn, stride, pad, bw, bh, alpha);
+  }
+  cudaEventRecord(e1);
+  const int f = finish();
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (avg_us) *avg_us = iters > 0 ? ms * 1000.f / iters : 0.f;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return f;
 }
 
 extern "C" int probe_conv_tma(const float* x, const float* wp, float* y, int N, int H, int W, int C, int stride) {

@@ -6,7 +6,9 @@ into confignet_b200/lib/libcn_probes.so) on a B200 and writes gpurun_out/round2_
   1. what kind::tf32 does with the low 13 mantissa bits of a raw fp32 operand (truncate / round-to-nearest);
   2. whether a tiled (C, W, H, N) tensor map with negative / overhanging start coordinates and element strides delivers the
      SAME-padded im2col rows of one (tap, 32-channel) k-block in the swizzled K-major layout the UMMA descriptor reads;
-  3. a 3x3 SAME convolution (stride 1 and 2) whose A operand is fetched only by TMA and read by the MMA from shared memory.
+  3. a 3x3 SAME convolution (stride 1 and 2) whose A operand is fetched only by TMA and read by the MMA from shared memory;
+  4. the candidate built on 1-3 (persistent, pipelined, 3xTF32 with the raw tile as a_big, coalesced epilogue): parity against
+     an fp64 reference and its launch time next to the production kernel's on the same layers.
 
 The product library is not involved; nothing here is on the bench or test path.
 """
@@ -132,6 +134,64 @@ def main():
     conv_case(1, 32, 32, 32, 2)
     conv_case(1, 4, 128, 32, 1)
     conv_case(1, 64, 64, 96, 2)
+    # ---------------------------------------------------------------- 4. the candidate kernel against production
+    lib.probe_conv_tma_fast.argtypes = [P, P, P, P] + [ctypes.c_int] * 6 + [ctypes.c_float, ctypes.c_int, P]
+
+    def fast_case(N, H, W, C, cout, stride, iters=20):
+        x = rng.standard_normal((N, H, W, C)).astype(np.float32)
+        w = (rng.standard_normal((3, 3, C, cout)) / np.sqrt(9 * C)).astype(np.float32)
+        bias = rng.standard_normal(cout).astype(np.float32) * 0.1
+        cblocks = C // 32
+        big = trunc13(w)
+        small = trunc13(w - big)
+        rows, ks = np.meshgrid(np.arange(cout), np.arange(32), indexing="ij")
+        idx = (np.vectorize(swz_off)(rows, ks) // 4).ravel()
+        wp = np.zeros((9 * cblocks, 2, cout * 32), np.float32)
+        for tap in range(9):
+            for cb in range(cblocks):
+                for plane, src in enumerate((big, small)):
+                    wp[tap * cblocks + cb, plane, idx] = src[tap // 3, tap % 3, cb * 32:cb * 32 + 32, :].T.ravel()
+        Ho, Wo = -(-H // stride), -(-W // stride)
+        dx, dw, db = torch.tensor(x, device=dev), torch.tensor(wp, device=dev), torch.tensor(bias, device=dev)
+        y = torch.zeros(N, Ho, Wo, cout, device=dev)
+        us = ctypes.c_float(0)
+        r = lib.probe_conv_tma_fast(dx.data_ptr(), dw.data_ptr(), db.data_ptr(), y.data_ptr(), N, H, W, C, cout, stride, 0.3, iters, ctypes.byref(us))
+        if r:
+            say("   fast N%d H%d W%d C%d->%d stride %d -> error %d" % (N, H, W, C, cout, stride, r))
+            return
+        tot = max((Ho - 1) * stride + 3 - H, 0)
+        nb = min(N, 2)                                                 # the fp64 reference on two samples is enough
+        xp = torch.nn.functional.pad(torch.tensor(x[:nb]).permute(0, 3, 1, 2).double(), (tot // 2, tot - tot // 2, tot // 2, tot - tot // 2))
+        ref = torch.nn.functional.conv2d(xp, torch.tensor(w).permute(3, 2, 0, 1).double(), torch.tensor(bias).double(), stride=stride)
+        ref = torch.nn.functional.leaky_relu(ref, 0.3).permute(0, 2, 3, 1).numpy()
+        err = float(np.abs(y[:nb].cpu().numpy() - ref).max() / np.abs(ref).max())
+        flops = 2.0 * N * Ho * Wo * cout * 9 * C
+        line = "   fast N%d H%d W%d C%d->%d stride %d: max rel err %.2e (3xTF32 expects ~1e-6; ~1e-4 means the raw operand is ROUNDED), %.1f us, %.1f TFLOP/s" % (
+            N, H, W, C, cout, stride, err, us.value, flops / us.value * 1e-6)
+        try:                                                           # the production kernel on the same layer
+            sys.path.insert(0, ROOT)
+            from confignet_b200 import ops, _lib as L
+            wt = torch.tensor(w, device=dev)
+            for _ in range(3):
+                yp = ops.conv_act(dx, wt, db, stride=stride, act=L.ACT_LRELU, alpha=0.3)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                yp = ops.conv_act(dx, wt, db, stride=stride, act=L.ACT_LRELU, alpha=0.3)
+            e1.record()
+            torch.cuda.synchronize()
+            pus = e0.elapsed_time(e1) * 1000 / iters
+            perr = float(np.abs(yp[:nb].detach().cpu().numpy() - ref).max() / np.abs(ref).max())
+            line += " | production %.1f us, %.1f TFLOP/s, err %.2e" % (pus, flops / pus * 1e-6, perr)
+        except Exception as e:                                         # noqa: BLE001
+            line += " | production not timed: %r" % (e,)
+        say(line)
+
+    say("4. probe_conv_tma_fast (candidate) against the production kernel")
+    fast_case(2, 32, 32, 64, 64, 1, iters=3)
+    fast_case(32, 128, 128, 64, 96, 2)              # a discriminator block shape (Cin padded to a multiple of 32 here)
+    fast_case(16, 256, 256, 64, 64, 1)              # the 64 -> 64 layer at 256 x 256 of the role profile
+    fast_case(32, 64, 64, 96, 128, 2)
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     with open(OUT, "w") as fp:
         fp.write("\n".join(lines) + "\n")

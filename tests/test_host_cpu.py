@@ -405,12 +405,12 @@ def test_class_surface_covers_reference_methods():
 def test_round2_probe_library_builds_and_exports():
     """csrc/experiments/round2_probes.cu (design probes for the next kernel: tf32 operand handling, TMA tiles with zero fill as
     SAME padding, a TMA-fed convolution) cross-compiles for sm_100a into its own library - the product library does not
-    contain it - and exports the three entry points scripts/gpu_probe_round2.py binds."""
+    contain it - and exports the entry points scripts/gpu_probe_round2.py binds."""
     import __graft_entry__ as g
     g.build()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     lib = ctypes.CDLL(os.path.join(root, "confignet_b200", "lib", "libcn_probes.so"))
-    for name in ("probe_tf32_operands", "probe_tma_tile", "probe_conv_tma"):
+    for name in ("probe_tf32_operands", "probe_tma_tile", "probe_conv_tma", "probe_conv_tma_fast"):
         assert hasattr(lib, name), name
     main = ctypes.CDLL(os.path.join(root, "confignet_b200", "lib", "libconfignet_b200.so"))
     assert not hasattr(main, "probe_conv_tma")
