@@ -271,7 +271,7 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* v) {
 
 __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_constant__ CUtensorMap map, const float* __restrict__ wp,
                                                                   const float* __restrict__ bias, float* __restrict__ y, int N, int Ho, int Wo,
-                                                                  int C, int bn, int stride, int pad, int bw, int bh, float alpha) {
+                                                                  int C, int bn, int cout, int stride, int pad, int bw, int bh, float alpha) {
   extern __shared__ unsigned char raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   const FastCfg L = fast_cfg(bn);
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_off);
-  const int tiles_x = Wo / bw, tiles_y = Ho / bh, n_tiles = N * tiles_x * tiles_y;
+  const int tiles_x = Wo / bw, tiles_y = Ho / bh, n_nt = cout / bn, n_tiles = N * tiles_x * tiles_y * n_nt;   // item = (pixel tile, channel tile), channel tile inner
   const int cblocks = C / 32, num_kb = 9 * cblocks;
   const uint32_t stage_tx = (uint32_t)L.stage_bytes;
 
@@ -301,15 +301,17 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
     // ===== producer: one TMA tile (A) + one bulk copy (B big + small planes) per k-block =====
     if (lane == 0) {
       int s = 0, ph = 0; long git = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
+        const int t = w / n_nt, nt = w % n_nt;
         const int n = t / (tiles_x * tiles_y), ty = (t / tiles_x) % tiles_y, tx = t % tiles_x;
+        const float* wsrc = wp + (size_t)nt * num_kb * (2 * L.b_plane / 4);
         for (int kb = 0; kb < num_kb; ++kb, ++git) {
           if (git >= S) mbar_wait(bar_empty + 8 * s, ph ^ 1);
           const int tap = kb / cblocks, cb = kb % cblocks;
           const uint32_t dst = sbase + s * L.stage_bytes;
           mbar_arrive_expect_tx(bar_full + 8 * s, stage_tx);
           tma_load_4d(dst, &map, cb * 32, tx * bw * stride + tap % 3 - pad, ty * bh * stride + tap / 3 - pad, n, bar_full + 8 * s);
-          bulk_g2s(dst + A_BYTES, wp + (size_t)kb * (2 * L.b_plane / 4), 2 * L.b_plane, bar_full + 8 * s);
+          bulk_g2s(dst + A_BYTES, wsrc + (size_t)kb * (2 * L.b_plane / 4), 2 * L.b_plane, bar_full + 8 * s);
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
@@ -403,13 +405,14 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
         b ^= 1;
       }
       __syncwarp();                               // a warp finishes the 32 rows it promoted itself: no cross-warp dependency
-      const int n = t / (tiles_x * tiles_y), ty = (t / tiles_x) % tiles_y, tx = t % tiles_x;
+      const int pt = t / n_nt, n0 = (t % n_nt) * bn;
+      const int n = pt / (tiles_x * tiles_y), ty = (pt / tiles_x) % tiles_y, tx = pt % tiles_x;
       float bz[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) bz[i] = lane + 32 * i < bn ? bias[lane + 32 * i] : 0.f;
+      for (int i = 0; i < 4; ++i) bz[i] = lane + 32 * i < bn ? bias[n0 + lane + 32 * i] : 0.f;
       for (int r = q * 32; r < q * 32 + 32; ++r) {
         const int px = tx * bw + r % bw, py = ty * bh + r / bw;
-        float* dst = y + (((size_t)n * Ho + py) * Wo + px) * bn;
+        float* dst = y + (((size_t)n * Ho + py) * Wo + px) * cout + n0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int c0 = lane + 32 * i;
@@ -479,10 +482,12 @@ extern "C" int probe_tma_tile(const float* x, int N, int H, int W, int C, int bw
   return finish();
 }
 
-// wp: per k-block (tap-major, then 32-channel block) the big plane then the small plane, each bn rows x 128 B in the swizzled
-// K-major layout.  Launches `iters` times on the default stream; *avg_us receives the mean launch time (CUDA events).
-extern "C" int probe_conv_tma_fast(const float* x, const float* wp, const float* bias, float* y, int N, int H, int W, int C, int bn,
+// wp: per channel tile (bn = min(cout, 128) output channels), per k-block (tap-major, then 32-channel block) the big plane then
+// the small plane, each bn rows x 128 B in the swizzled K-major layout.  Launches `iters` times on the default stream; *avg_us receives the mean launch time (CUDA events).
+extern "C" int probe_conv_tma_fast(const float* x, const float* wp, const float* bias, float* y, int N, int H, int W, int C, int cout,
                                    int stride, float alpha, int iters, float* avg_us) {
+  const int bn = cout <= 128 ? cout : 128;         // channel tile; wp holds cout / bn groups of k-block stages, one after the other
+  if (cout % bn) return -2;
   const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
   const int bw = Wo < 128 ? Wo : 128, bh = 128 / bw;
   if (C % 32 || bn % 16 || bn > 128 || 128 % bw || Wo % bw || Ho % bh) return -2;
@@ -496,12 +501,12 @@ extern "C" int probe_conv_tma_fast(const float* x, const float* wp, const float*
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int n_tiles = N * (Ho / bh) * (Wo / bw), grid = n_tiles < sms ? n_tiles : sms;
+  const int n_tiles = N * (Ho / bh) * (Wo / bw) * (cout / bn), grid = n_tiles < sms ? n_tiles : sms;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < iters + 1; ++it) {
     if (it == 1) cudaEventRecord(e0);
-    conv_tma_fast_kernel<<<grid, F_THREADS, L.smem_bytes + 1024>>>(map, wp, bias, y, N, Ho, Wo, C, bn, stride, pad, bw, bh, alpha);
+    conv_tma_fast_kernel<<<grid, F_THREADS, L.smem_bytes + 1024>>>(map, wp, bias, y, N, Ho, Wo, C, bn, cout, stride, pad, bw, bh, alpha);
   }
   cudaEventRecord(e1);
   const int f = finish();

@@ -144,13 +144,15 @@ def main():
         cblocks = C // 32
         big = trunc13(w)
         small = trunc13(w - big)
-        rows, ks = np.meshgrid(np.arange(cout), np.arange(32), indexing="ij")
+        bn = min(cout, 128)                                            # the kernel's channel tile
+        rows, ks = np.meshgrid(np.arange(bn), np.arange(32), indexing="ij")
         idx = (np.vectorize(swz_off)(rows, ks) // 4).ravel()
-        wp = np.zeros((9 * cblocks, 2, cout * 32), np.float32)
-        for tap in range(9):
-            for cb in range(cblocks):
-                for plane, src in enumerate((big, small)):
-                    wp[tap * cblocks + cb, plane, idx] = src[tap // 3, tap % 3, cb * 32:cb * 32 + 32, :].T.ravel()
+        wp = np.zeros((cout // bn, 9 * cblocks, 2, bn * 32), np.float32)
+        for nt in range(cout // bn):
+            for tap in range(9):
+                for cb in range(cblocks):
+                    for plane, src in enumerate((big, small)):
+                        wp[nt, tap * cblocks + cb, plane, idx] = src[tap // 3, tap % 3, cb * 32:cb * 32 + 32, nt * bn:nt * bn + bn].T.ravel()
         Ho, Wo = -(-H // stride), -(-W // stride)
         dx, dw, db = torch.tensor(x, device=dev), torch.tensor(wp, device=dev), torch.tensor(bias, device=dev)
         y = torch.zeros(N, Ho, Wo, cout, device=dev)
@@ -192,6 +194,9 @@ def main():
     fast_case(32, 128, 128, 64, 96, 2)              # a discriminator block shape (Cin padded to a multiple of 32 here)
     fast_case(16, 256, 256, 64, 64, 1)              # the 64 -> 64 layer at 256 x 256 of the role profile
     fast_case(32, 64, 64, 96, 128, 2)
+    fast_case(16, 64, 64, 256, 256, 1)              # the heaviest line of profiles/r01_conv_breakdown_final.txt (VGG block3)
+    fast_case(16, 128, 128, 128, 128, 1)
+    fast_case(16, 32, 32, 512, 512, 1)
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     with open(OUT, "w") as fp:
         fp.write("\n".join(lines) + "\n")
