@@ -416,6 +416,21 @@ def test_round2_probe_library_builds_and_exports():
     assert not hasattr(main, "probe_conv_tma")
 
 
+def test_candidate_kernel_protocol_model():
+    """scripts/sim_candidate_protocol.py: the mbarrier protocol of the round-2 candidate kernel (ring stages, a_small stages,
+    ping-pong accumulators) under random interleavings - no deadlock, none of the hazards the barriers guard against."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("sim_candidate_protocol", os.path.join(root, "scripts", "sim_candidate_protocol.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for S, num_kb, tiles in ((2, 9, 3), (3, 18, 2), (6, 72, 2), (4, 1, 5), (3, 8, 3)):
+        mod.run(S, num_kb, tiles, seed=S + num_kb)
+    # the model does catch a broken protocol: a producer that ignores the empty barrier overwrites a live stage
+    with pytest.raises(AssertionError):
+        mod.run(2, 18, 2, seed=1, producer_waits_empty=False)
+
+
 def test_committed_bench_lines_keep_the_contract():
     """profiles/r01_bench_final.json / _n2_final / _reference_final: the JSON lines bench.py printed on the B200 box carry every
     key of the bench contract, the metric BASELINE.json names, a roofline measured on the tensor-core kernel and a bounded CPU
