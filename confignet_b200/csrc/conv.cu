@@ -669,7 +669,8 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* v) {
 }
 __device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-// 3xTF32 split: x = big + small with big = rna_tf32(x), small = rna_tf32(x - big) (residual ~2^-22 |x|).
+// 3xTF32 split: x = big + small, both exactly representable in tf32 (built by masking the 13 low mantissa bits, see
+// sts_split4; f2tf32 is the cvt.rna form the first version used, kept for experiments).  Residual ~2^-21 |x|.
 // small*big + big*small + big*big on the tf32 tensor pipe reproduces the fp32 product to ~5e-7, which the
 // ill-conditioned gradients of this network need: measured on B200, single tf32 is 3.6e-2 off on the
 // generator output and a bf16 hi/lo split (~1e-5 per product) 1e-2..5e-2 off on some parameter gradients.
