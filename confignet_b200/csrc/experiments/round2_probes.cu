@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(128) conv_tma_kernel(const __grid_constant__ C
   if (tid == 0) { mbar_init(smem_u32(&s->bar_full), 1); mbar_init(smem_u32(&s->bar_mma), 1); }
   fence_proxy_async();
   const uint32_t tmem = tmem_alloc32(smem_u32(&s->tmem), &s->tmem, warp);
-  const int cblocks = C / 32, num_kb = 9 * cblocks;
+  const int cblocks = (C + 31) / 32, num_kb = 9 * cblocks;   // a partial last block: the TMA zero-fills the missing channels
   for (int kb = 0; kb < num_kb; ++kb) {
     const int tap = kb / cblocks, cb = kb % cblocks, dy = tap / 3, dx = tap % 3;
     if (tid == 0) {
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_off);
   const int tiles_x = Wo / bw, tiles_y = Ho / bh, n_nt = cout / bn, n_tiles = N * tiles_x * tiles_y * n_nt;   // item = (pixel tile, channel tile), channel tile inner
-  const int cblocks = C / 32, num_kb = 9 * cblocks;
+  const int cblocks = (C + 31) / 32, num_kb = 9 * cblocks;   // a partial last block: the TMA zero-fills the missing channels
   const uint32_t stage_tx = (uint32_t)L.stage_bytes;
 
   if (warp == 0) {
@@ -490,7 +490,7 @@ extern "C" int probe_conv_tma_fast(const float* x, const float* wp, const float*
   if (cout % bn) return -2;
   const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
   const int bw = Wo < 128 ? Wo : 128, bh = 128 / bw;
-  if (C % 32 || bn % 16 || bn > 128 || 128 % bw || Wo % bw || Ho % bh) return -2;
+  if (C % 4 || bn % 16 || bn > 128 || 128 % bw || Wo % bw || Ho % bh) return -2;      // C * 4 bytes: the tensor map's 16-byte stride rule
   const int total = (Ho - 1) * stride + 3 - H, pad = (total > 0 ? total : 0) / 2;
   CUtensorMap map;
   const int r = make_map(&map, x, N, H, W, C, bw, bh, stride);

@@ -141,7 +141,7 @@ def main():
         x = rng.standard_normal((N, H, W, C)).astype(np.float32)
         w = (rng.standard_normal((3, 3, C, cout)) / np.sqrt(9 * C)).astype(np.float32)
         bias = rng.standard_normal(cout).astype(np.float32) * 0.1
-        cblocks = C // 32
+        cblocks = -(-C // 32)                                          # a partial last block is zero-padded (the TMA zero-fills A)
         big = trunc13(w)
         small = trunc13(w - big)
         bn = min(cout, 128)                                            # the kernel's channel tile
@@ -152,7 +152,10 @@ def main():
             for tap in range(9):
                 for cb in range(cblocks):
                     for plane, src in enumerate((big, small)):
-                        wp[nt, tap * cblocks + cb, plane, idx] = src[tap // 3, tap % 3, cb * 32:cb * 32 + 32, nt * bn:nt * bn + bn].T.ravel()
+                        blk = np.zeros((32, bn), np.float32)
+                        part = src[tap // 3, tap % 3, cb * 32:cb * 32 + 32, nt * bn:nt * bn + bn]
+                        blk[:part.shape[0]] = part
+                        wp[nt, tap * cblocks + cb, plane, idx] = blk.T.ravel()
         Ho, Wo = -(-H // stride), -(-W // stride)
         dx, dw, db = torch.tensor(x, device=dev), torch.tensor(wp, device=dev), torch.tensor(bias, device=dev)
         y = torch.zeros(N, Ho, Wo, cout, device=dev)
@@ -191,7 +194,7 @@ def main():
 
     say("4. probe_conv_tma_fast (candidate) against the production kernel")
     fast_case(2, 32, 32, 64, 64, 1, iters=3)
-    fast_case(32, 128, 128, 64, 96, 2)              # a discriminator block shape (Cin padded to a multiple of 32 here)
+    fast_case(32, 128, 128, 48, 96, 2)              # discriminator block 1: 48 channels = one and a half k-blocks per tap
     fast_case(16, 256, 256, 64, 64, 1)              # the 64 -> 64 layer at 256 x 256 of the role profile
     fast_case(32, 64, 64, 96, 128, 2)
     fast_case(16, 64, 64, 256, 256, 1)              # the heaviest line of profiles/r01_conv_breakdown_final.txt (VGG block3)
