@@ -587,6 +587,67 @@ def test_data_parallel_gradient_average_equals_global_batch(tmp_path):
         assert p.returncode == 0, o
 
 
+_DP_TRAIN_WORKER = r'''
+import os, sys, types, json, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from confignet_b200 import netspec
+from confignet_b200.confignet_first_stage import ConfigNetFirstStage
+from confignet_b200.runtime import world
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, ws = world()
+out_dir = sys.argv[4]
+fm = {k: tuple(v) for k, v in netspec.default_facemodel_inputs().items()}
+m = ConfigNetFirstStage({"output_shape": (256, 256, 3), "batch_size": 4, "facemodel_inputs": fm}, initialize=False, device="cpu")
+r = np.random.RandomState(7)
+ds = types.SimpleNamespace(imgs=r.randint(0, 256, (9, 4, 4, 3)).astype(np.uint8), eye_masks=np.zeros((9, 4, 4), np.uint8),
+                           metadata_inputs={k: r.rand(9, d[0]).astype(np.float32) for k, d in m.config["facemodel_inputs"].items()},
+                           metadata_input_distributions=None)
+ds.metadata_inputs["rotations"] = r.rand(9, 3).astype(np.float32)
+seen = []
+def step(name):
+    def f(*a):
+        # what every step does first: draw the GLOBAL batch from the shared stream, keep this rank's rows
+        idx = np.random.randint(0, 9, m.get_batch_size())
+        mine, = m._rank_rows(idx)
+        seen.append((name, idx.tolist(), mine.tolist()))
+        return {"loss_sum": 1.0}
+    return f
+for n in ("discriminator_training_step", "synth_discriminator_training_step", "latent_discriminator_training_step", "generator_training_step"):
+    setattr(m, n, step(n))
+m.update_smoothed_weights = lambda: None
+m.save = lambda d, name: open(os.path.join(d, name + ".saved_by_rank%d" % rank), "w").close()
+np.random.seed(0)                                   # training_utils.initialize_random_seed(0) on every rank
+m.train(ds, ds, out_dir, None, n_steps=2, n_samples_for_metrics=5)
+gathered = [None, None]
+dist.all_gather_object(gathered, seen)
+assert [g[1] for g in gathered[0]] == [g[1] for g in gathered[1]], "ranks drew different global batches"
+for a, b in zip(gathered[0], gathered[1]):
+    assert a[2] + b[2] == a[1], "row slices do not tile the global batch"
+dist.barrier()
+if rank == 0:
+    files = sorted(os.listdir(os.path.join(out_dir, "checkpoints")))
+    assert files == ["000000.saved_by_rank0"], files            # rank 0 alone writes checkpoints and loss tables
+    assert os.path.exists(os.path.join(out_dir, "generator_losses.txt"))
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_data_parallel_training_loop_host_logic(tmp_path):
+    """world size 2 (gloo): with the same NumPy seed every rank's setup_training / train() draws the same global batches
+    and keeps complementary row slices; only rank 0 writes checkpoints and loss tables."""
+    script = tmp_path / "dp_train_worker.py"
+    script.write_text(_DP_TRAIN_WORKER)
+    out_dir = tmp_path / "out"
+    out_dir.mkdir()
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), str(out_dir)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+
+
 def test_keras_adam_host_half_and_graph_wrapper_fallback():
     """KerasAdam.begin_step is the host half of a (possibly graph-replayed) optimizer step: it must advance
     `iterations` and publish Keras' bias-corrected lr_t = lr*sqrt(1-b2^t)/(1-b1^t) [TF-2.1] for t = iterations+1.
