@@ -48,14 +48,22 @@ def round13(a, ties_away):
     return u.astype(np.uint32).view(np.float32)
 
 
-def main():
-    assert torch.cuda.is_available(), "needs a GPU"
+def load():
     lib = ctypes.CDLL(LIB)
-    dev = torch.device("cuda:0")
     P = ctypes.c_void_p
     lib.probe_tf32_operands.argtypes = [P, P, P]
     lib.probe_tma_tile.argtypes = [P] + [ctypes.c_int] * 11 + [P]
     lib.probe_conv_tma.argtypes = [P, P, P] + [ctypes.c_int] * 5
+    lib.probe_conv_tma_fast.argtypes = [P, P, P, P] + [ctypes.c_int] * 6 + [ctypes.c_float, ctypes.c_int, P]
+    return lib
+
+
+def main(lib=None, dev=None, quick=False):
+    """lib / dev / quick exist for tests/test_host_cpu.py, which runs this host logic against a NumPy emulation of the four
+    entry points (CPU tensors) so that a GPU visit is not spent on a packing or indexing slip in this script."""
+    if lib is None:
+        assert torch.cuda.is_available(), "needs a GPU"
+        lib, dev = load(), torch.device("cuda:0")
     rng = np.random.RandomState(0)
 
     # ---------------------------------------------------------------- 1. operand handling
@@ -119,7 +127,8 @@ def main():
                         wp[tap * cblocks + cb, swz_off(nn, k) // 4] = w[tap // 3, tap % 3, cb * 32 + k, nn]
         Ho, Wo = -(-H // stride), -(-W // stride)
         y = torch.zeros(N, Ho, Wo, 16, device=dev)
-        r = lib.probe_conv_tma(torch.tensor(x, device=dev).data_ptr(), torch.tensor(wp, device=dev).data_ptr(), y.data_ptr(), N, H, W, C, stride)
+        dx, dw = torch.tensor(x, device=dev), torch.tensor(wp, device=dev)          # named: they must outlive the call
+        r = lib.probe_conv_tma(dx.data_ptr(), dw.data_ptr(), y.data_ptr(), N, H, W, C, stride)
         if r:
             say("   conv N%d H%d W%d C%d stride %d -> error %d" % (N, H, W, C, stride, r))
             return
@@ -135,8 +144,6 @@ def main():
     conv_case(1, 4, 128, 32, 1)
     conv_case(1, 64, 64, 96, 2)
     # ---------------------------------------------------------------- 4. the candidate kernel against production
-    lib.probe_conv_tma_fast.argtypes = [P, P, P, P] + [ctypes.c_int] * 6 + [ctypes.c_float, ctypes.c_int, P]
-
     def fast_case(N, H, W, C, cout, stride, iters=20):
         x = rng.standard_normal((N, H, W, C)).astype(np.float32)
         w = (rng.standard_normal((3, 3, C, cout)) / np.sqrt(9 * C)).astype(np.float32)
@@ -172,8 +179,10 @@ def main():
         err = float(np.abs(y[:nb].cpu().numpy() - ref).max() / np.abs(ref).max())
         flops = 2.0 * N * Ho * Wo * cout * 9 * C
         line = "   fast N%d H%d W%d C%d->%d stride %d: max rel err %.2e (3xTF32 expects ~1e-6; ~1e-4 means the raw operand is ROUNDED), %.1f us, %.1f TFLOP/s" % (
-            N, H, W, C, cout, stride, err, us.value, flops / us.value * 1e-6)
+            N, H, W, C, cout, stride, err, us.value, flops / max(us.value, 1e-3) * 1e-6)
         try:                                                           # the production kernel on the same layer
+            if dev.type != "cuda":
+                raise RuntimeError("emulated device")
             sys.path.insert(0, ROOT)
             from confignet_b200 import ops, _lib as L
             wt = torch.tensor(w, device=dev)
@@ -194,6 +203,10 @@ def main():
 
     say("4. probe_conv_tma_fast (candidate) against the production kernel")
     fast_case(2, 32, 32, 64, 64, 1, iters=3)
+    if quick:
+        fast_case(1, 32, 32, 48, 96, 2, iters=1)
+        fast_case(1, 16, 16, 32, 256, 1, iters=1)
+        return lines
     fast_case(32, 128, 128, 48, 96, 2)              # discriminator block 1: 48 channels = one and a half k-blocks per tap
     fast_case(16, 256, 256, 64, 64, 1)              # the 64 -> 64 layer at 256 x 256 of the role profile
     fast_case(32, 64, 64, 96, 128, 2)
@@ -203,7 +216,8 @@ def main():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     with open(OUT, "w") as fp:
         fp.write("\n".join(lines) + "\n")
+    return lines
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    main()

@@ -416,6 +416,109 @@ def test_round2_probe_library_builds_and_exports():
     assert not hasattr(main, "probe_conv_tma")
 
 
+def test_probe_script_host_logic_against_emulated_kernels():
+    """scripts/gpu_probe_round2.py run on CPU tensors against a NumPy emulation of the four probe entry points that follows
+    the kernels' own index arithmetic (tile -> TMA start coordinates, box order, swizzled stage layout, weight-stage order,
+    3xTF32 with the raw tile as a_big): the script's packers, references and de-swizzling must agree with it, so a GPU
+    visit is not spent on a slip in the script.  (What the hardware really does is what the probes are for.)"""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gpu_probe_round2", os.path.join(root, "scripts", "gpu_probe_round2.py"))
+    pr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pr)
+
+    def arr(ptr, *shape):
+        n = int(np.prod(shape))
+        return np.frombuffer((ctypes.c_float * n).from_address(ptr), np.float32).reshape(shape)
+
+    def tma(x, c, xs, ys, n, bw, stride):                       # one 128 x 32 tile, box order x fastest, zero fill
+        N, H, W, C = x.shape
+        t = np.zeros((128, 32), np.float32)
+        for row in range(128):
+            px, py = xs + (row % bw) * stride, ys + (row // bw) * stride
+            if 0 <= px < W and 0 <= py < H and 0 <= n < N:
+                k = max(0, min(32, C - c))
+                t[row, :k] = x[n, py, px, c:c + k]
+        return t
+
+    def unswz(raw, rows):                                       # raw stage (floats) -> [rows][32]
+        out = np.zeros((rows, 32), np.float32)
+        for r in range(rows):
+            for k in range(32):
+                out[r, k] = raw[pr.swz_off(r, k) // 4]
+        return out
+
+    class Fake:
+        @staticmethod
+        def probe_tf32_operands(A, B, D):
+            a, b = pr.trunc13(arr(A, 128, 32)), pr.trunc13(arr(B, 16, 32))
+            arr(D, 128, 16)[:] = (a.astype(np.float64) @ b.astype(np.float64).T).astype(np.float32)
+            return 0
+
+        @staticmethod
+        def probe_tma_tile(x, N, H, W, C, bw, bh, stride, c, xs, ys, n, out):
+            t = tma(arr(x, N, H, W, C), c, xs, ys, n, bw, stride)
+            raw = arr(out, 128 * 32)
+            for r in range(128):
+                for k in range(32):
+                    raw[pr.swz_off(r, k) // 4] = t[r, k]
+            return 0
+
+        @staticmethod
+        def _conv(x, wp_of, y, N, H, W, C, cout, bn, stride, planes, post):
+            Ho, Wo = -(-H // stride), -(-W // stride)
+            bw = min(Wo, 128); bh = 128 // bw
+            pad = max((Ho - 1) * stride + 3 - H, 0) // 2
+            cblocks = -(-C // 32)
+            xa, ya = arr(x, N, H, W, C), arr(y, N, Ho, Wo, cout)
+            for n in range(N):
+                for ty in range(Ho // bh):
+                    for tx in range(Wo // bw):
+                        for nt in range(cout // bn):
+                            acc = np.zeros((128, bn), np.float64)
+                            for kb in range(9 * cblocks):
+                                tap, cb = kb // cblocks, kb % cblocks
+                                a = tma(xa, cb * 32, tx * bw * stride + tap % 3 - pad, ty * bh * stride + tap // 3 - pad, n, bw, stride)
+                                acc += planes(a, wp_of(nt, kb))
+                            for r in range(128):
+                                ya[n, ty * bh + r // bw, tx * bw + r % bw, nt * bn:(nt + 1) * bn] = post(acc[r], nt * bn)
+            return 0
+
+        @staticmethod
+        def probe_conv_tma(x, wp, y, N, H, W, C, stride):
+            cblocks = -(-C // 32)
+            w = arr(wp, 9 * cblocks, 16 * 32)
+            return Fake._conv(x, lambda nt, kb: unswz(w[kb], 16), y, N, H, W, C, 16, 16, stride,
+                              lambda a, b: a.astype(np.float64) @ b.astype(np.float64).T, lambda v, n0: v.astype(np.float32))
+
+        @staticmethod
+        def probe_conv_tma_fast(x, wp, bias, y, N, H, W, C, cout, stride, alpha, iters, avg_us):
+            bn, cblocks = min(cout, 128), -(-C // 32)
+            w = arr(wp, cout // bn, 9 * cblocks, 2, bn * 32)
+            bz = arr(bias, cout)
+
+            def planes(a, st):
+                big, small = unswz(st[0], bn).astype(np.float64), unswz(st[1], bn).astype(np.float64)
+                a_big = pr.trunc13(a)
+                a_small = pr.trunc13(a - a_big)
+                return a_small.astype(np.float64) @ big.T + a_big.astype(np.float64) @ small.T + a_big.astype(np.float64) @ big.T
+
+            def post(v, n0):
+                v = v + bz[n0:n0 + bn]
+                return np.where(v > 0, v, alpha * v).astype(np.float32)
+            avg_us._obj.value = 1.0
+            return Fake._conv(x, lambda nt, kb: w[nt, kb], y, N, H, W, C, cout, bn, stride, planes, post)
+
+    lines = pr.main(lib=Fake, dev=torch.device("cpu"), quick=True)
+    text = "\n".join(lines)
+    model_err = {l.split()[1]: float(l.split("max rel err ")[1].split()[0]) for l in lines if l.strip().startswith("model ")}
+    assert model_err["truncate"] < 1e-6 and min(model_err["round-nearest-away"], model_err["round-nearest-even"]) > 1e-5, text
+    assert text.count(": 0 of 4096 elements differ") == 5, text
+    assert text.count("max abs diff 0 (exact integers expected: 0)") == 4, text
+    errs = [float(l.split("max rel err ")[1].split(" ")[0]) for l in lines if l.strip().startswith("fast ")]
+    assert len(errs) == 3 and max(errs) < 5e-6, text
+
+
 def test_candidate_kernel_protocol_model():
     """scripts/sim_candidate_protocol.py: the mbarrier protocol of the round-2 candidate kernel (ring stages, a_small stages,
     ping-pong accumulators) under random interleavings - no deadlock, none of the hazards the barriers guard against."""
