@@ -10,6 +10,9 @@ want = [("Kernel Name", "kernel"), ("Grid Size", "grid"), ("launch__cluster_dim_
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor_pipe_pct"),
         ("smsp__sass_inst_executed_op_utcmma.sum", "utcmma_inst"),
         ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct"),
+        ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lsu_data_pipe_pct"),
+        ("l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed", "lsu_writeback_pct"),
+        ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1_pct"),
         ("launch__registers_per_thread", "regs"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy_pct")]
 for r in rows[2:]:
     out = []
