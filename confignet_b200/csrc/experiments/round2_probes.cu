@@ -216,6 +216,8 @@ constexpr int F_THREADS = 320;
 constexpr int F_CH = 8;                    // k-blocks per accumulation chunk (production: TC_CHUNK_KB)
 constexpr int F_TOT_LD = 129;              // leading dimension of the running total
 
+struct TapList { int n; short dx[16], dy[16]; };     // source offset of every tap, in source pixels (SAME padding folded in)
+
 struct FastCfg { int stages, stage_bytes, b_plane, tot_off, bar_off, tmem_off, smem_bytes, a_col0; };
 __host__ __device__ inline FastCfg fast_cfg(int bn) {
   FastCfg c;
@@ -271,7 +273,11 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* v) {
 
 __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_constant__ CUtensorMap map, const float* __restrict__ wp,
                                                                   const float* __restrict__ bias, float* __restrict__ y, int N, int Ho, int Wo,
-                                                                  int C, int bn, int cout, int stride, int pad, int bw, int bh, float alpha) {
+                                                                  int C, int bn, int cout, int stride, const __grid_constant__ TapList taps, int bw, int bh, float alpha,
+                                                                  int oh, int ow, int ostride, int oy, int ox) {
+  // GEMM rows = the Ho x Wo pixel grid of this launch; row (py, px) reads source pixel (py * stride + dy, px * stride + dx)
+  // for tap (dx, dy) and writes output pixel (py * ostride + oy, px * ostride + ox) of an oh x ow image: a forward
+  // convolution has ostride 1, a parity phase of a stride-2 input gradient / a sub-pixel phase of a folded upsample has 2.
   extern __shared__ unsigned char raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   const FastCfg L = fast_cfg(bn);
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_off);
   const int tiles_x = Wo / bw, tiles_y = Ho / bh, n_nt = cout / bn, n_tiles = N * tiles_x * tiles_y * n_nt;   // item = (pixel tile, channel tile), channel tile inner
-  const int cblocks = (C + 31) / 32, num_kb = 9 * cblocks;   // a partial last block: the TMA zero-fills the missing channels
+  const int cblocks = (C + 31) / 32, num_kb = taps.n * cblocks;   // a partial last block: the TMA zero-fills the missing channels
   const uint32_t stage_tx = (uint32_t)L.stage_bytes;
 
   if (warp == 0) {
@@ -310,7 +316,7 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
           const int tap = kb / cblocks, cb = kb % cblocks;
           const uint32_t dst = sbase + s * L.stage_bytes;
           mbar_arrive_expect_tx(bar_full + 8 * s, stage_tx);
-          tma_load_4d(dst, &map, cb * 32, tx * bw * stride + tap % 3 - pad, ty * bh * stride + tap / 3 - pad, n, bar_full + 8 * s);
+          tma_load_4d(dst, &map, cb * 32, tx * bw * stride + taps.dx[tap], ty * bh * stride + taps.dy[tap], n, bar_full + 8 * s);
           bulk_g2s(dst + A_BYTES, wsrc + (size_t)kb * (2 * L.b_plane / 4), 2 * L.b_plane, bar_full + 8 * s);
           if (++s == S) { s = 0; ph ^= 1; }
         }
@@ -409,10 +415,10 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
       const int n = pt / (tiles_x * tiles_y), ty = (pt / tiles_x) % tiles_y, tx = pt % tiles_x;
       float bz[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) bz[i] = lane + 32 * i < bn ? bias[n0 + lane + 32 * i] : 0.f;
+      for (int i = 0; i < 4; ++i) bz[i] = (bias != nullptr && lane + 32 * i < bn) ? bias[n0 + lane + 32 * i] : 0.f;
       for (int r = q * 32; r < q * 32 + 32; ++r) {
-        const int px = tx * bw + r % bw, py = ty * bh + r / bw;
-        float* dst = y + (((size_t)n * Ho + py) * Wo + px) * cout + n0;
+        const int px = (tx * bw + r % bw) * ostride + ox, py = (ty * bh + r / bw) * ostride + oy;
+        float* dst = y + (((size_t)n * oh + py) * ow + px) * cout + n0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int c0 = lane + 32 * i;
@@ -482,16 +488,22 @@ extern "C" int probe_tma_tile(const float* x, int N, int H, int W, int C, int bw
   return finish();
 }
 
+// The general entry.  x: source (N, H, W, C); the launch covers a gh x gw grid of GEMM pixels; tap t reads source pixel
+// (py * stride + dy[t], px * stride + dx[t]) (zero outside) and the result goes to output pixel (py * ostride + oy,
+// px * ostride + ox) of y (N, oh, ow, cout).  alpha: LeakyReLU slope (1 = no activation); bias may be null.
 // wp: per channel tile (bn = min(cout, 128) output channels), per k-block (tap-major, then 32-channel block) the big plane then
-// the small plane, each bn rows x 128 B in the swizzled K-major layout.  Launches `iters` times on the default stream; *avg_us receives the mean launch time (CUDA events).
-extern "C" int probe_conv_tma_fast(const float* x, const float* wp, const float* bias, float* y, int N, int H, int W, int C, int cout,
-                                   int stride, float alpha, int iters, float* avg_us) {
-  const int bn = cout <= 128 ? cout : 128;         // channel tile; wp holds cout / bn groups of k-block stages, one after the other
-  if (cout % bn) return -2;
-  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
-  const int bw = Wo < 128 ? Wo : 128, bh = 128 / bw;
-  if (C % 4 || bn % 16 || bn > 128 || 128 % bw || Wo % bw || Ho % bh) return -2;      // C * 4 bytes: the tensor map's 16-byte stride rule
-  const int total = (Ho - 1) * stride + 3 - H, pad = (total > 0 ? total : 0) / 2;
+// the small plane, each bn rows x 128 B in the swizzled K-major layout.  Launches `iters` times (after one warm-up) on the
+// default stream; *avg_us receives the mean launch time (CUDA events).
+extern "C" int probe_conv_tma_taps(const float* x, int N, int H, int W, int C, const float* wp, const float* bias, float* y, int gh, int gw,
+                                   int cout, int stride, int ntaps, const int* dx, const int* dy, int oh, int ow, int ostride, int oy, int ox,
+                                   float alpha, int iters, float* avg_us) {
+  const int bn = cout <= 128 ? cout : 128;
+  if (cout % bn || ntaps < 1 || ntaps > 16) return -2;
+  const int bw = gw < 128 ? gw : 128, bh = 128 / bw;
+  if (C % 4 || bn % 16 || 128 % bw || gw % bw || gh % bh) return -2;      // C * 4 bytes: the tensor map's 16-byte stride rule
+  TapList taps;
+  taps.n = ntaps;
+  for (int t = 0; t < 16; ++t) { taps.dx[t] = (short)(t < ntaps ? dx[t] : 0); taps.dy[t] = (short)(t < ntaps ? dy[t] : 0); }
   CUtensorMap map;
   const int r = make_map(&map, x, N, H, W, C, bw, bh, stride);
   if (r) return r;
@@ -501,12 +513,13 @@ extern "C" int probe_conv_tma_fast(const float* x, const float* wp, const float*
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int n_tiles = N * (Ho / bh) * (Wo / bw) * (cout / bn), grid = n_tiles < sms ? n_tiles : sms;
+  const int n_tiles = N * (gh / bh) * (gw / bw) * (cout / bn), grid = n_tiles < sms ? n_tiles : sms;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < iters + 1; ++it) {
     if (it == 1) cudaEventRecord(e0);
-    conv_tma_fast_kernel<<<grid, F_THREADS, L.smem_bytes + 1024>>>(map, wp, bias, y, N, Ho, Wo, C, bn, cout, stride, pad, bw, bh, alpha);
+    conv_tma_fast_kernel<<<grid, F_THREADS, L.smem_bytes + 1024>>>(map, wp, bias, y, N, gh, gw, C, bn, cout, stride, taps, bw, bh, alpha,
+                                                                   oh, ow, ostride, oy, ox);
   }
   cudaEventRecord(e1);
   const int f = finish();
@@ -515,6 +528,16 @@ extern "C" int probe_conv_tma_fast(const float* x, const float* wp, const float*
   if (avg_us) *avg_us = iters > 0 ? ms * 1000.f / iters : 0.f;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return f;
+}
+
+// forward 3x3 SAME convolution, stride 1 or 2, + bias + LeakyReLU(alpha)
+extern "C" int probe_conv_tma_fast(const float* x, const float* wp, const float* bias, float* y, int N, int H, int W, int C, int cout,
+                                   int stride, float alpha, int iters, float* avg_us) {
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  const int total = (Ho - 1) * stride + 3 - H, pad = (total > 0 ? total : 0) / 2;       // TF SAME: the smaller half in front
+  int dx[9], dy[9];
+  for (int t = 0; t < 9; ++t) { dx[t] = t % 3 - pad; dy[t] = t / 3 - pad; }
+  return probe_conv_tma_taps(x, N, H, W, C, wp, bias, y, Ho, Wo, cout, stride, 9, dx, dy, Ho, Wo, 1, 0, 0, alpha, iters, avg_us);
 }
 
 extern "C" int probe_conv_tma(const float* x, const float* wp, float* y, int N, int H, int W, int C, int stride) {

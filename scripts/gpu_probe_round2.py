@@ -55,7 +55,36 @@ def load():
     lib.probe_tma_tile.argtypes = [P] + [ctypes.c_int] * 11 + [P]
     lib.probe_conv_tma.argtypes = [P, P, P] + [ctypes.c_int] * 5
     lib.probe_conv_tma_fast.argtypes = [P, P, P, P] + [ctypes.c_int] * 6 + [ctypes.c_float, ctypes.c_int, P]
+    lib.probe_conv_tma_taps.argtypes = [P] + [ctypes.c_int] * 4 + [P, P, P] + [ctypes.c_int] * 5 + [P, P] + [ctypes.c_int] * 5 + \
+        [ctypes.c_float, ctypes.c_int, P]
     return lib
+
+
+def pack_stages(mats, bn):
+    """mats: list over k-blocks of (32, cout) fp32 matrices [k][n] -> (cout // bn, len(mats), 2, bn * 32) stage images:
+    big plane, small plane, each bn rows of 128 B in the swizzled K-major layout"""
+    cout = mats[0].shape[1]
+    rows, ks = np.meshgrid(np.arange(bn), np.arange(32), indexing="ij")
+    idx = (np.vectorize(swz_off)(rows, ks) // 4).ravel()
+    wp = np.zeros((cout // bn, len(mats), 2, bn * 32), np.float32)
+    for kb, m in enumerate(mats):
+        big = trunc13(m)
+        small = trunc13(m - big)
+        for nt in range(cout // bn):
+            for plane, src in enumerate((big, small)):
+                wp[nt, kb, plane, idx] = src[:, nt * bn:nt * bn + bn].T.ravel()
+    return wp
+
+
+def k_blocks(w_taps):
+    """w_taps: list over taps of (K, cout) matrices -> list over (tap, 32-row block) of zero-padded (32, cout) matrices"""
+    out = []
+    for m in w_taps:
+        for c0 in range(0, m.shape[0], 32):
+            blk = np.zeros((32, m.shape[1]), np.float32)
+            blk[:min(32, m.shape[0] - c0)] = m[c0:c0 + 32]
+            out.append(blk)
+    return out
 
 
 def main(lib=None, dev=None, quick=False):
@@ -148,21 +177,7 @@ def main(lib=None, dev=None, quick=False):
         x = rng.standard_normal((N, H, W, C)).astype(np.float32)
         w = (rng.standard_normal((3, 3, C, cout)) / np.sqrt(9 * C)).astype(np.float32)
         bias = rng.standard_normal(cout).astype(np.float32) * 0.1
-        cblocks = -(-C // 32)                                          # a partial last block is zero-padded (the TMA zero-fills A)
-        big = trunc13(w)
-        small = trunc13(w - big)
-        bn = min(cout, 128)                                            # the kernel's channel tile
-        rows, ks = np.meshgrid(np.arange(bn), np.arange(32), indexing="ij")
-        idx = (np.vectorize(swz_off)(rows, ks) // 4).ravel()
-        wp = np.zeros((cout // bn, 9 * cblocks, 2, bn * 32), np.float32)
-        for nt in range(cout // bn):
-            for tap in range(9):
-                for cb in range(cblocks):
-                    for plane, src in enumerate((big, small)):
-                        blk = np.zeros((32, bn), np.float32)
-                        part = src[tap // 3, tap % 3, cb * 32:cb * 32 + 32, nt * bn:nt * bn + bn]
-                        blk[:part.shape[0]] = part
-                        wp[nt, tap * cblocks + cb, plane, idx] = blk.T.ravel()
+        wp = pack_stages(k_blocks([w[t // 3, t % 3] for t in range(9)]), min(cout, 128))     # tap-major, zero-padded channel blocks
         Ho, Wo = -(-H // stride), -(-W // stride)
         dx, dw, db = torch.tensor(x, device=dev), torch.tensor(wp, device=dev), torch.tensor(bias, device=dev)
         y = torch.zeros(N, Ho, Wo, cout, device=dev)
@@ -201,6 +216,42 @@ def main(lib=None, dev=None, quick=False):
             line += " | production not timed: %r" % (e,)
         say(line)
 
+    def dgrad_s2_case(N, H, W, cin, cout, iters=20):
+        """input gradient of a 3x3 stride-2 SAME convolution (cin -> cout on an H x W input) as four parity phases: phase
+        (py, px) is a stride-1 tap-list convolution over gy (N, H/2, W/2, cout) whose results land on gx[:, py::2, px::2]"""
+        w = (rng.standard_normal((3, 3, cin, cout)) / np.sqrt(9 * cin)).astype(np.float32)
+        gy = rng.standard_normal((N, H // 2, W // 2, cout)).astype(np.float32)
+        dgy, gx = torch.tensor(gy, device=dev), torch.zeros(N, H, W, cin, device=dev)
+        total_us, keep = 0.0, []
+        for py in range(2):
+            for px in range(2):
+                # y[i] = sum_t x[2 i + t] w[t] (SAME: no padding in front for even sizes)  =>  gx[2 q] = gy[q] w[0] + gy[q - 1] w[2],
+                # gx[2 q + 1] = gy[q] w[1]
+                ty = [(0, 0), (2, -1)] if py == 0 else [(1, 0)]
+                tx = [(0, 0), (2, -1)] if px == 0 else [(1, 0)]
+                taps = [(a, b, oa, ob) for a, oa in ty for b, ob in tx]
+                wp = pack_stages(k_blocks([w[a, b].T.copy() for a, b, _, _ in taps]), min(cin, 128))      # K = cout, N = cin
+                dw = torch.tensor(wp, device=dev)
+                keep.append(dw)
+                dxs = (ctypes.c_int * len(taps))(*[ob for _, _, _, ob in taps])
+                dys = (ctypes.c_int * len(taps))(*[oa for _, _, oa, _ in taps])
+                us = ctypes.c_float(0)
+                r = lib.probe_conv_tma_taps(dgy.data_ptr(), N, H // 2, W // 2, cout, dw.data_ptr(), None, gx.data_ptr(), H // 2, W // 2, cin, 1,
+                                            len(taps), dxs, dys, H, W, 2, py, px, 1.0, iters, ctypes.byref(us))
+                if r:
+                    say("   dgrad-s2 N%d H%d W%d %d->%d phase (%d,%d) -> error %d" % (N, H, W, cin, cout, py, px, r))
+                    return
+                total_us += us.value
+        nb = min(N, 2)
+        xr = torch.zeros(nb, cin, H, W, dtype=torch.float64, requires_grad=True)
+        yr = torch.nn.functional.conv2d(torch.nn.functional.pad(xr, (0, 1, 0, 1)), torch.tensor(w).permute(3, 2, 0, 1).double(), stride=2)
+        ref, = torch.autograd.grad(yr, xr, torch.tensor(gy[:nb]).permute(0, 3, 1, 2).double())
+        ref = ref.permute(0, 2, 3, 1).numpy()
+        err = float(np.abs(gx[:nb].cpu().numpy() - ref).max() / np.abs(ref).max())
+        flops = 2.0 * N * (H // 2) * (W // 2) * cout * 9 * cin
+        say("   dgrad-s2 N%d H%d W%d %d->%d (4 phase launches): max rel err %.2e, %.1f us, %.1f TFLOP/s" %
+            (N, H, W, cin, cout, err, total_us, flops / max(total_us, 1e-3) * 1e-6))
+
     say("4. probe_conv_tma_fast (candidate) against the production kernel")
     if os.environ.get("CN_PROBE_NCU"):              # under ncu: one heavy layer, one launch of each kernel
         fast_case(16, 64, 64, 256, 256, 1, iters=1)
@@ -209,6 +260,7 @@ def main(lib=None, dev=None, quick=False):
     if quick:
         fast_case(1, 32, 32, 48, 96, 2, iters=1)
         fast_case(1, 16, 16, 32, 256, 1, iters=1)
+        dgrad_s2_case(1, 32, 32, 48, 96, iters=1)
         return lines
     fast_case(32, 128, 128, 48, 96, 2)              # discriminator block 1: 48 channels = one and a half k-blocks per tap
     fast_case(16, 256, 256, 64, 64, 1)              # the 64 -> 64 layer at 256 x 256 of the role profile
@@ -216,6 +268,8 @@ def main(lib=None, dev=None, quick=False):
     fast_case(16, 64, 64, 256, 256, 1)              # the heaviest line of profiles/r01_conv_breakdown_final.txt (VGG block3)
     fast_case(16, 128, 128, 128, 128, 1)
     fast_case(16, 32, 32, 512, 512, 1)
+    dgrad_s2_case(32, 128, 128, 48, 96)             # the worst line of the breakdown: 52 TFLOP/s in production (1.68 ms per 8 calls)
+    dgrad_s2_case(32, 64, 64, 96, 192)
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     with open(OUT, "w") as fp:
         fp.write("\n".join(lines) + "\n")

@@ -492,22 +492,37 @@ def test_probe_script_host_logic_against_emulated_kernels():
                               lambda a, b: a.astype(np.float64) @ b.astype(np.float64).T, lambda v, n0: v.astype(np.float32))
 
         @staticmethod
-        def probe_conv_tma_fast(x, wp, bias, y, N, H, W, C, cout, stride, alpha, iters, avg_us):
+        def probe_conv_tma_taps(x, N, H, W, C, wp, bias, y, gh, gw, cout, stride, ntaps, dx, dy, oh, ow, ostride, oy, ox, alpha, iters, avg_us):
             bn, cblocks = min(cout, 128), -(-C // 32)
-            w = arr(wp, cout // bn, 9 * cblocks, 2, bn * 32)
-            bz = arr(bias, cout)
-
-            def planes(a, st):
-                big, small = unswz(st[0], bn).astype(np.float64), unswz(st[1], bn).astype(np.float64)
-                a_big = pr.trunc13(a)
-                a_small = pr.trunc13(a - a_big)
-                return a_small.astype(np.float64) @ big.T + a_big.astype(np.float64) @ small.T + a_big.astype(np.float64) @ big.T
-
-            def post(v, n0):
-                v = v + bz[n0:n0 + bn]
-                return np.where(v > 0, v, alpha * v).astype(np.float32)
+            bw = min(gw, 128); bh = 128 // bw
+            w = arr(wp, cout // bn, ntaps * cblocks, 2, bn * 32)
+            bz = arr(bias, cout) if bias is not None else np.zeros(cout, np.float32)
+            xa, ya = arr(x, N, H, W, C), arr(y, N, oh, ow, cout)
+            for n in range(N):
+                for ty in range(gh // bh):
+                    for tx in range(gw // bw):
+                        for nt in range(cout // bn):
+                            acc = np.zeros((128, bn), np.float64)
+                            for kb in range(ntaps * cblocks):
+                                tap, cb = kb // cblocks, kb % cblocks
+                                a = tma(xa, cb * 32, tx * bw * stride + dx[tap], ty * bh * stride + dy[tap], n, bw, stride)
+                                big, small = unswz(w[nt, kb, 0], bn).astype(np.float64), unswz(w[nt, kb, 1], bn).astype(np.float64)
+                                a_big = pr.trunc13(a)
+                                a_small = pr.trunc13(a - a_big)
+                                acc += a_small.astype(np.float64) @ big.T + a_big.astype(np.float64) @ small.T + a_big.astype(np.float64) @ big.T
+                            for r in range(128):
+                                v = acc[r] + bz[nt * bn:(nt + 1) * bn]
+                                ya[n, (ty * bh + r // bw) * ostride + oy, (tx * bw + r % bw) * ostride + ox, nt * bn:(nt + 1) * bn] = \
+                                    np.where(v > 0, v, alpha * v).astype(np.float32)
             avg_us._obj.value = 1.0
-            return Fake._conv(x, lambda nt, kb: w[nt, kb], y, N, H, W, C, cout, bn, stride, planes, post)
+            return 0
+
+        @staticmethod
+        def probe_conv_tma_fast(x, wp, bias, y, N, H, W, C, cout, stride, alpha, iters, avg_us):
+            Ho, Wo = -(-H // stride), -(-W // stride)
+            pad = max((Ho - 1) * stride + 3 - H, 0) // 2
+            return Fake.probe_conv_tma_taps(x, N, H, W, C, wp, bias, y, Ho, Wo, cout, stride, 9, [t % 3 - pad for t in range(9)],
+                                            [t // 3 - pad for t in range(9)], Ho, Wo, 1, 0, 0, alpha, iters, avg_us)
 
     lines = pr.main(lib=Fake, dev=torch.device("cpu"), quick=True)
     text = "\n".join(lines)
@@ -515,8 +530,8 @@ def test_probe_script_host_logic_against_emulated_kernels():
     assert model_err["truncate"] < 1e-6 and min(model_err["round-nearest-away"], model_err["round-nearest-even"]) > 1e-5, text
     assert text.count(": 0 of 4096 elements differ") == 5, text
     assert text.count("max abs diff 0 (exact integers expected: 0)") == 4, text
-    errs = [float(l.split("max rel err ")[1].split(" ")[0]) for l in lines if l.strip().startswith("fast ")]
-    assert len(errs) == 3 and max(errs) < 5e-6, text
+    errs = [float(l.split("max rel err ")[1].split(" ")[0].rstrip(",")) for l in lines if l.strip().startswith(("fast ", "dgrad-s2 "))]
+    assert len(errs) == 4 and max(errs) < 5e-6, text
 
 
 def test_candidate_kernel_protocol_model():
