@@ -50,6 +50,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c), "r"(x), "r"(y), "r"(n), "r"(bar) : "memory");
 }
+// 5-D tiled TMA load, coordinates (c, x, y, z, n): volumes, and images as volumes of depth 1
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c, int x, int y, int z, int n, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c), "r"(x), "r"(y), "r"(z), "r"(n), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -216,7 +222,7 @@ constexpr int F_THREADS = 320;
 constexpr int F_CH = 8;                    // k-blocks per accumulation chunk (production: TC_CHUNK_KB)
 constexpr int F_TOT_LD = 129;              // leading dimension of the running total
 
-struct TapList { int n; short dx[16], dy[16]; };     // source offset of every tap, in source pixels (SAME padding folded in)
+struct TapList { int n; short dx[32], dy[32], dz[32]; };     // source offset of every tap, in source pixels / voxels (SAME padding folded in)
 
 struct FastCfg { int stages, stage_bytes, b_plane, tot_off, bar_off, tmem_off, smem_bytes, a_col0; };
 __host__ __device__ inline FastCfg fast_cfg(int bn) {
@@ -272,10 +278,11 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* v) {
 }
 
 __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_constant__ CUtensorMap map, const float* __restrict__ wp,
-                                                                  const float* __restrict__ bias, float* __restrict__ y, int N, int Ho, int Wo,
-                                                                  int C, int bn, int cout, int stride, const __grid_constant__ TapList taps, int bw, int bh, float alpha,
-                                                                  int oh, int ow, int ostride, int oy, int ox) {
-  // GEMM rows = the Ho x Wo pixel grid of this launch; row (py, px) reads source pixel (py * stride + dy, px * stride + dx)
+                                                                  const float* __restrict__ bias, float* __restrict__ y, int N, int Do, int Ho, int Wo,
+                                                                  int C, int bn, int cout, int stride, const __grid_constant__ TapList taps, int bw, int bh, int bd,
+                                                                  float alpha, int od, int oh, int ow, int ostride, int oz, int oy, int ox) {
+  // `map` is always 5-D (C, W, H, D, N); images are volumes of depth 1 (Do = bd = od = 1, dz = oz = 0).
+  // GEMM rows = the (Do x) Ho x Wo grid of this launch; row (py, px) reads source pixel (py * stride + dy, px * stride + dx)
   // for tap (dx, dy) and writes output pixel (py * ostride + oy, px * ostride + ox) of an oh x ow image: a forward
   // convolution has ostride 1, a parity phase of a stride-2 input gradient / a sub-pixel phase of a folded upsample has 2.
   extern __shared__ unsigned char raw[];
@@ -299,7 +306,8 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_off);
-  const int tiles_x = Wo / bw, tiles_y = Ho / bh, n_nt = cout / bn, n_tiles = N * tiles_x * tiles_y * n_nt;   // item = (pixel tile, channel tile), channel tile inner
+  const int tiles_x = Wo / bw, tiles_y = Ho / bh, tiles_z = Do / bd, tiles_img = tiles_x * tiles_y * tiles_z;
+  const int n_nt = cout / bn, n_tiles = N * tiles_img * n_nt;   // item = (pixel tile, channel tile), channel tile inner
   const int cblocks = (C + 31) / 32, num_kb = taps.n * cblocks;   // a partial last block: the TMA zero-fills the missing channels
   const uint32_t stage_tx = (uint32_t)L.stage_bytes;
 
@@ -309,14 +317,15 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
       int s = 0, ph = 0; long git = 0;
       for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
         const int t = w / n_nt, nt = w % n_nt;
-        const int n = t / (tiles_x * tiles_y), ty = (t / tiles_x) % tiles_y, tx = t % tiles_x;
+        const int n = t / tiles_img, tz = (t / (tiles_x * tiles_y)) % tiles_z, ty = (t / tiles_x) % tiles_y, tx = t % tiles_x;
         const float* wsrc = wp + (size_t)nt * num_kb * (2 * L.b_plane / 4);
         for (int kb = 0; kb < num_kb; ++kb, ++git) {
           if (git >= S) mbar_wait(bar_empty + 8 * s, ph ^ 1);
           const int tap = kb / cblocks, cb = kb % cblocks;
           const uint32_t dst = sbase + s * L.stage_bytes;
           mbar_arrive_expect_tx(bar_full + 8 * s, stage_tx);
-          tma_load_4d(dst, &map, cb * 32, tx * bw * stride + taps.dx[tap], ty * bh * stride + taps.dy[tap], n, bar_full + 8 * s);
+          tma_load_5d(dst, &map, cb * 32, tx * bw * stride + taps.dx[tap], ty * bh * stride + taps.dy[tap], tz * bd * stride + taps.dz[tap], n,
+                      bar_full + 8 * s);
           bulk_g2s(dst + A_BYTES, wsrc + (size_t)kb * (2 * L.b_plane / 4), 2 * L.b_plane, bar_full + 8 * s);
           if (++s == S) { s = 0; ph ^= 1; }
         }
@@ -412,13 +421,13 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
       }
       __syncwarp();                               // a warp finishes the 32 rows it promoted itself: no cross-warp dependency
       const int pt = t / n_nt, n0 = (t % n_nt) * bn;
-      const int n = pt / (tiles_x * tiles_y), ty = (pt / tiles_x) % tiles_y, tx = pt % tiles_x;
+      const int n = pt / tiles_img, tz = (pt / (tiles_x * tiles_y)) % tiles_z, ty = (pt / tiles_x) % tiles_y, tx = pt % tiles_x;
       float bz[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) bz[i] = (bias != nullptr && lane + 32 * i < bn) ? bias[n0 + lane + 32 * i] : 0.f;
       for (int r = q * 32; r < q * 32 + 32; ++r) {
-        const int px = (tx * bw + r % bw) * ostride + ox, py = (ty * bh + r / bw) * ostride + oy;
-        float* dst = y + (((size_t)n * oh + py) * ow + px) * cout + n0;
+        const int px = (tx * bw + r % bw) * ostride + ox, py = (ty * bh + (r / bw) % bh) * ostride + oy, pz = (tz * bd + r / (bw * bh)) * ostride + oz;
+        float* dst = y + ((((size_t)n * od + pz) * oh + py) * ow + px) * cout + n0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int c0 = lane + 32 * i;
@@ -458,6 +467,21 @@ int make_map(CUtensorMap* map, const float* x, int N, int H, int W, int C, int b
   return r == CUDA_SUCCESS ? 0 : -(int)r - 100;
 }
 
+int make_map5(CUtensorMap* map, const float* x, int N, int D, int H, int W, int C, int bw, int bh, int bd, int stride) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return -1;
+  const EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(fn);
+  const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  const cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, (cuuint64_t)D * H * W * C * 4};
+  const cuuint32_t box[5] = {32, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)(bd * stride), 1};
+  const cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(x), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 100;
+}
+
 template <typename K>
 int prep(K kernel) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeSmem) + 1024) == cudaSuccess ? 0 : -2;
@@ -488,24 +512,29 @@ extern "C" int probe_tma_tile(const float* x, int N, int H, int W, int C, int bw
   return finish();
 }
 
-// The general entry.  x: source (N, H, W, C); the launch covers a gh x gw grid of GEMM pixels; tap t reads source pixel
-// (py * stride + dy[t], px * stride + dx[t]) (zero outside) and the result goes to output pixel (py * ostride + oy,
-// px * ostride + ox) of y (N, oh, ow, cout).  alpha: LeakyReLU slope (1 = no activation); bias may be null.
+// The general entry.  x: source (N, D, H, W, C) (D = 1 for images); the launch covers a gd x gh x gw grid of GEMM pixels; tap t
+// reads source voxel (pz * stride + dz[t], py * stride + dy[t], px * stride + dx[t]) (zero outside) and the result goes to output
+// voxel (pz * ostride + oz, py * ostride + oy, px * ostride + ox) of y (N, od, oh, ow, cout).  alpha: LeakyReLU slope (1 = no
+// activation); bias may be null.  geom = {D, H, W, gd, gh, gw, od, oh, ow, oz, oy, ox}.
 // wp: per channel tile (bn = min(cout, 128) output channels), per k-block (tap-major, then 32-channel block) the big plane then
 // the small plane, each bn rows x 128 B in the swizzled K-major layout.  Launches `iters` times (after one warm-up) on the
 // default stream; *avg_us receives the mean launch time (CUDA events).
-extern "C" int probe_conv_tma_taps(const float* x, int N, int H, int W, int C, const float* wp, const float* bias, float* y, int gh, int gw,
-                                   int cout, int stride, int ntaps, const int* dx, const int* dy, int oh, int ow, int ostride, int oy, int ox,
+extern "C" int probe_conv_tma_taps(const float* x, int N, int C, const int* geom, const float* wp, const float* bias, float* y,
+                                   int cout, int stride, int ntaps, const int* dx, const int* dy, const int* dz, int ostride,
                                    float alpha, int iters, float* avg_us) {
+  const int D = geom[0], H = geom[1], W = geom[2], gd = geom[3], gh = geom[4], gw = geom[5], od = geom[6], oh = geom[7], ow = geom[8],
+            oz = geom[9], oy = geom[10], ox = geom[11];
   const int bn = cout <= 128 ? cout : 128;
-  if (cout % bn || ntaps < 1 || ntaps > 16) return -2;
-  const int bw = gw < 128 ? gw : 128, bh = 128 / bw;
-  if (C % 4 || bn % 16 || 128 % bw || gw % bw || gh % bh) return -2;      // C * 4 bytes: the tensor map's 16-byte stride rule
+  if (cout % bn || ntaps < 1 || ntaps > 32) return -2;
+  const int bw = gw < 128 ? gw : 128, bh = gh < 128 / bw ? gh : 128 / bw, bd = 128 / (bw * bh);
+  if (C % 4 || bn % 16 || 128 % bw || (128 / bw) % bh || gw % bw || gh % bh || gd % bd) return -2;      // C * 4 bytes: the tensor map's 16-byte stride rule
   TapList taps;
   taps.n = ntaps;
-  for (int t = 0; t < 16; ++t) { taps.dx[t] = (short)(t < ntaps ? dx[t] : 0); taps.dy[t] = (short)(t < ntaps ? dy[t] : 0); }
+  for (int t = 0; t < 32; ++t) {
+    taps.dx[t] = (short)(t < ntaps ? dx[t] : 0); taps.dy[t] = (short)(t < ntaps ? dy[t] : 0); taps.dz[t] = (short)(t < ntaps && dz ? dz[t] : 0);
+  }
   CUtensorMap map;
-  const int r = make_map(&map, x, N, H, W, C, bw, bh, stride);
+  const int r = make_map5(&map, x, N, D, H, W, C, bw, bh, bd, stride);
   if (r) return r;
   const FastCfg L = fast_cfg(bn);
   if (L.stages < 2) return -2;
@@ -513,13 +542,13 @@ extern "C" int probe_conv_tma_taps(const float* x, int N, int H, int W, int C, c
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int n_tiles = N * (gh / bh) * (gw / bw) * (cout / bn), grid = n_tiles < sms ? n_tiles : sms;
+  const int n_tiles = N * (gd / bd) * (gh / bh) * (gw / bw) * (cout / bn), grid = n_tiles < sms ? n_tiles : sms;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < iters + 1; ++it) {
     if (it == 1) cudaEventRecord(e0);
-    conv_tma_fast_kernel<<<grid, F_THREADS, L.smem_bytes + 1024>>>(map, wp, bias, y, N, gh, gw, C, bn, cout, stride, taps, bw, bh, alpha,
-                                                                   oh, ow, ostride, oy, ox);
+    conv_tma_fast_kernel<<<grid, F_THREADS, L.smem_bytes + 1024>>>(map, wp, bias, y, N, gd, gh, gw, C, bn, cout, stride, taps, bw, bh, bd, alpha,
+                                                                   od, oh, ow, ostride, oz, oy, ox);
   }
   cudaEventRecord(e1);
   const int f = finish();
@@ -537,7 +566,8 @@ extern "C" int probe_conv_tma_fast(const float* x, const float* wp, const float*
   const int total = (Ho - 1) * stride + 3 - H, pad = (total > 0 ? total : 0) / 2;       // TF SAME: the smaller half in front
   int dx[9], dy[9];
   for (int t = 0; t < 9; ++t) { dx[t] = t % 3 - pad; dy[t] = t / 3 - pad; }
-  return probe_conv_tma_taps(x, N, H, W, C, wp, bias, y, Ho, Wo, cout, stride, 9, dx, dy, Ho, Wo, 1, 0, 0, alpha, iters, avg_us);
+  const int geom[12] = {1, H, W, 1, Ho, Wo, 1, Ho, Wo, 0, 0, 0};
+  return probe_conv_tma_taps(x, N, C, geom, wp, bias, y, cout, stride, 9, dx, dy, nullptr, 1, alpha, iters, avg_us);
 }
 
 extern "C" int probe_conv_tma(const float* x, const float* wp, float* y, int N, int H, int W, int C, int stride) {

@@ -55,8 +55,8 @@ def load():
     lib.probe_tma_tile.argtypes = [P] + [ctypes.c_int] * 11 + [P]
     lib.probe_conv_tma.argtypes = [P, P, P] + [ctypes.c_int] * 5
     lib.probe_conv_tma_fast.argtypes = [P, P, P, P] + [ctypes.c_int] * 6 + [ctypes.c_float, ctypes.c_int, P]
-    lib.probe_conv_tma_taps.argtypes = [P] + [ctypes.c_int] * 4 + [P, P, P] + [ctypes.c_int] * 5 + [P, P] + [ctypes.c_int] * 5 + \
-        [ctypes.c_float, ctypes.c_int, P]
+    lib.probe_conv_tma_taps.argtypes = [P, ctypes.c_int, ctypes.c_int, P, P, P, P] + [ctypes.c_int] * 3 + [P, P, P, ctypes.c_int,
+                                                                                                      ctypes.c_float, ctypes.c_int, P]
     return lib
 
 
@@ -235,9 +235,10 @@ def main(lib=None, dev=None, quick=False):
                 keep.append(dw)
                 dxs = (ctypes.c_int * len(taps))(*[ob for _, _, _, ob in taps])
                 dys = (ctypes.c_int * len(taps))(*[oa for _, _, oa, _ in taps])
+                geom = (ctypes.c_int * 12)(1, H // 2, W // 2, 1, H // 2, W // 2, 1, H, W, 0, py, px)
                 us = ctypes.c_float(0)
-                r = lib.probe_conv_tma_taps(dgy.data_ptr(), N, H // 2, W // 2, cout, dw.data_ptr(), None, gx.data_ptr(), H // 2, W // 2, cin, 1,
-                                            len(taps), dxs, dys, H, W, 2, py, px, 1.0, iters, ctypes.byref(us))
+                r = lib.probe_conv_tma_taps(dgy.data_ptr(), N, cout, geom, dw.data_ptr(), None, gx.data_ptr(), cin, 1,
+                                            len(taps), dxs, dys, None, 2, 1.0, iters, ctypes.byref(us))
                 if r:
                     say("   dgrad-s2 N%d H%d W%d %d->%d phase (%d,%d) -> error %d" % (N, H, W, cin, cout, py, px, r))
                     return
@@ -252,6 +253,32 @@ def main(lib=None, dev=None, quick=False):
         say("   dgrad-s2 N%d H%d W%d %d->%d (4 phase launches): max rel err %.2e, %.1f us, %.1f TFLOP/s" %
             (N, H, W, cin, cout, err, total_us, flops / max(total_us, 1e-3) * 1e-6))
 
+    def conv3d_case(N, S, C, cout, iters=20):
+        """forward 3x3x3 SAME convolution on an S^3 volume (the generator's post-rotation layers), 27 taps through a 5-D map"""
+        x = rng.standard_normal((N, S, S, S, C)).astype(np.float32)
+        w = (rng.standard_normal((3, 3, 3, C, cout)) / np.sqrt(27 * C)).astype(np.float32)
+        bias = rng.standard_normal(cout).astype(np.float32) * 0.1
+        wp = pack_stages(k_blocks([w[t // 9, (t // 3) % 3, t % 3] for t in range(27)]), min(cout, 128))
+        dx, dw, db = torch.tensor(x, device=dev), torch.tensor(wp, device=dev), torch.tensor(bias, device=dev)
+        y = torch.zeros(N, S, S, S, cout, device=dev)
+        I = ctypes.c_int * 27
+        geom = (ctypes.c_int * 12)(S, S, S, S, S, S, S, S, S, 0, 0, 0)
+        us = ctypes.c_float(0)
+        r = lib.probe_conv_tma_taps(dx.data_ptr(), N, C, geom, dw.data_ptr(), db.data_ptr(), y.data_ptr(), cout, 1, 27,
+                                    I(*[t % 3 - 1 for t in range(27)]), I(*[(t // 3) % 3 - 1 for t in range(27)]), I(*[t // 9 - 1 for t in range(27)]),
+                                    1, 0.3, iters, ctypes.byref(us))
+        if r:
+            say("   conv3d N%d %d^3 %d->%d -> error %d" % (N, S, C, cout, r))
+            return
+        nb = min(N, 1)
+        ref = torch.nn.functional.conv3d(torch.tensor(x[:nb]).permute(0, 4, 1, 2, 3).double(), torch.tensor(w).permute(4, 3, 0, 1, 2).double(),
+                                         torch.tensor(bias).double(), padding=1)
+        ref = torch.nn.functional.leaky_relu(ref, 0.3).permute(0, 2, 3, 4, 1).numpy()
+        err = float(np.abs(y[:nb].cpu().numpy() - ref).max() / np.abs(ref).max())
+        flops = 2.0 * N * S ** 3 * cout * 27 * C
+        say("   conv3d N%d %d^3 %d->%d: max rel err %.2e, %.1f us, %.1f TFLOP/s (production: 92 / 82 TFLOP/s on the 128->64 / 64->64 layers)" %
+            (N, S, C, cout, err, us.value, flops / max(us.value, 1e-3) * 1e-6))
+
     say("4. probe_conv_tma_fast (candidate) against the production kernel")
     if os.environ.get("CN_PROBE_NCU"):              # under ncu: one heavy layer, one launch of each kernel
         fast_case(16, 64, 64, 256, 256, 1, iters=1)
@@ -261,6 +288,7 @@ def main(lib=None, dev=None, quick=False):
         fast_case(1, 32, 32, 48, 96, 2, iters=1)
         fast_case(1, 16, 16, 32, 256, 1, iters=1)
         dgrad_s2_case(1, 32, 32, 48, 96, iters=1)
+        conv3d_case(1, 8, 32, 16, iters=1)
         return lines
     fast_case(32, 128, 128, 48, 96, 2)              # discriminator block 1: 48 channels = one and a half k-blocks per tap
     fast_case(16, 256, 256, 64, 64, 1)              # the 64 -> 64 layer at 256 x 256 of the role profile
@@ -270,6 +298,8 @@ def main(lib=None, dev=None, quick=False):
     fast_case(16, 32, 32, 512, 512, 1)
     dgrad_s2_case(32, 128, 128, 48, 96)             # the worst line of the breakdown: 52 TFLOP/s in production (1.68 ms per 8 calls)
     dgrad_s2_case(32, 64, 64, 96, 192)
+    conv3d_case(16, 16, 128, 64)                    # map_3d_post conv0 / conv1 of the generator
+    conv3d_case(16, 16, 64, 64)
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     with open(OUT, "w") as fp:
         fp.write("\n".join(lines) + "\n")

@@ -410,7 +410,7 @@ def test_round2_probe_library_builds_and_exports():
     g.build()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     lib = ctypes.CDLL(os.path.join(root, "confignet_b200", "lib", "libcn_probes.so"))
-    for name in ("probe_tf32_operands", "probe_tma_tile", "probe_conv_tma", "probe_conv_tma_fast"):
+    for name in ("probe_tf32_operands", "probe_tma_tile", "probe_conv_tma", "probe_conv_tma_fast", "probe_conv_tma_taps"):
         assert hasattr(lib, name), name
     main = ctypes.CDLL(os.path.join(root, "confignet_b200", "lib", "libconfignet_b200.so"))
     assert not hasattr(main, "probe_conv_tma")
@@ -492,28 +492,40 @@ def test_probe_script_host_logic_against_emulated_kernels():
                               lambda a, b: a.astype(np.float64) @ b.astype(np.float64).T, lambda v, n0: v.astype(np.float32))
 
         @staticmethod
-        def probe_conv_tma_taps(x, N, H, W, C, wp, bias, y, gh, gw, cout, stride, ntaps, dx, dy, oh, ow, ostride, oy, ox, alpha, iters, avg_us):
+        def probe_conv_tma_taps(x, N, C, geom, wp, bias, y, cout, stride, ntaps, dx, dy, dz, ostride, alpha, iters, avg_us):
+            D, H, W, gd, gh, gw, od, oh, ow, oz, oy, ox = list(geom)
+            dz = dz if dz is not None else [0] * ntaps
             bn, cblocks = min(cout, 128), -(-C // 32)
-            bw = min(gw, 128); bh = 128 // bw
+            bw = min(gw, 128); bh = min(gh, 128 // bw); bd = 128 // (bw * bh)
             w = arr(wp, cout // bn, ntaps * cblocks, 2, bn * 32)
             bz = arr(bias, cout) if bias is not None else np.zeros(cout, np.float32)
-            xa, ya = arr(x, N, H, W, C), arr(y, N, oh, ow, cout)
+            xa, ya = arr(x, N, D, H, W, C), arr(y, N, od, oh, ow, cout)
+
+            def tma5(c, xs, ys, zs, n):                       # box order: x fastest, then y, then z; zero fill
+                t = np.zeros((128, 32), np.float32)
+                for row in range(128):
+                    px, py, pz = xs + (row % bw) * stride, ys + ((row // bw) % bh) * stride, zs + (row // (bw * bh)) * stride
+                    if 0 <= px < W and 0 <= py < H and 0 <= pz < D:
+                        k = max(0, min(32, C - c))
+                        t[row, :k] = xa[n, pz, py, px, c:c + k]
+                return t
             for n in range(N):
-                for ty in range(gh // bh):
-                    for tx in range(gw // bw):
-                        for nt in range(cout // bn):
-                            acc = np.zeros((128, bn), np.float64)
-                            for kb in range(ntaps * cblocks):
-                                tap, cb = kb // cblocks, kb % cblocks
-                                a = tma(xa, cb * 32, tx * bw * stride + dx[tap], ty * bh * stride + dy[tap], n, bw, stride)
-                                big, small = unswz(w[nt, kb, 0], bn).astype(np.float64), unswz(w[nt, kb, 1], bn).astype(np.float64)
-                                a_big = pr.trunc13(a)
-                                a_small = pr.trunc13(a - a_big)
-                                acc += a_small.astype(np.float64) @ big.T + a_big.astype(np.float64) @ small.T + a_big.astype(np.float64) @ big.T
-                            for r in range(128):
-                                v = acc[r] + bz[nt * bn:(nt + 1) * bn]
-                                ya[n, (ty * bh + r // bw) * ostride + oy, (tx * bw + r % bw) * ostride + ox, nt * bn:(nt + 1) * bn] = \
-                                    np.where(v > 0, v, alpha * v).astype(np.float32)
+                for tz in range(gd // bd):
+                    for ty in range(gh // bh):
+                        for tx in range(gw // bw):
+                            for nt in range(cout // bn):
+                                acc = np.zeros((128, bn), np.float64)
+                                for kb in range(ntaps * cblocks):
+                                    tap, cb = kb // cblocks, kb % cblocks
+                                    a = tma5(cb * 32, tx * bw * stride + dx[tap], ty * bh * stride + dy[tap], tz * bd * stride + dz[tap], n)
+                                    big, small = unswz(w[nt, kb, 0], bn).astype(np.float64), unswz(w[nt, kb, 1], bn).astype(np.float64)
+                                    a_big = pr.trunc13(a)
+                                    a_small = pr.trunc13(a - a_big)
+                                    acc += a_small.astype(np.float64) @ big.T + a_big.astype(np.float64) @ small.T + a_big.astype(np.float64) @ big.T
+                                for r in range(128):
+                                    v = acc[r] + bz[nt * bn:(nt + 1) * bn]
+                                    ya[n, (tz * bd + r // (bw * bh)) * ostride + oz, (ty * bh + (r // bw) % bh) * ostride + oy,
+                                       (tx * bw + r % bw) * ostride + ox, nt * bn:(nt + 1) * bn] = np.where(v > 0, v, alpha * v).astype(np.float32)
             avg_us._obj.value = 1.0
             return 0
 
@@ -521,8 +533,8 @@ def test_probe_script_host_logic_against_emulated_kernels():
         def probe_conv_tma_fast(x, wp, bias, y, N, H, W, C, cout, stride, alpha, iters, avg_us):
             Ho, Wo = -(-H // stride), -(-W // stride)
             pad = max((Ho - 1) * stride + 3 - H, 0) // 2
-            return Fake.probe_conv_tma_taps(x, N, H, W, C, wp, bias, y, Ho, Wo, cout, stride, 9, [t % 3 - pad for t in range(9)],
-                                            [t // 3 - pad for t in range(9)], Ho, Wo, 1, 0, 0, alpha, iters, avg_us)
+            return Fake.probe_conv_tma_taps(x, N, C, [1, H, W, 1, Ho, Wo, 1, Ho, Wo, 0, 0, 0], wp, bias, y, cout, stride, 9,
+                                            [t % 3 - pad for t in range(9)], [t // 3 - pad for t in range(9)], None, 1, alpha, iters, avg_us)
 
     lines = pr.main(lib=Fake, dev=torch.device("cpu"), quick=True)
     text = "\n".join(lines)
@@ -530,8 +542,8 @@ def test_probe_script_host_logic_against_emulated_kernels():
     assert model_err["truncate"] < 1e-6 and min(model_err["round-nearest-away"], model_err["round-nearest-even"]) > 1e-5, text
     assert text.count(": 0 of 4096 elements differ") == 5, text
     assert text.count("max abs diff 0 (exact integers expected: 0)") == 4, text
-    errs = [float(l.split("max rel err ")[1].split(" ")[0].rstrip(",")) for l in lines if l.strip().startswith(("fast ", "dgrad-s2 "))]
-    assert len(errs) == 4 and max(errs) < 5e-6, text
+    errs = [float(l.split("max rel err ")[1].split(" ")[0].rstrip(",")) for l in lines if l.strip().startswith(("fast ", "dgrad-s2 ", "conv3d "))]
+    assert len(errs) == 5 and max(errs) < 5e-6, text
 
 
 def test_candidate_kernel_protocol_model():
