@@ -279,6 +279,47 @@ def main(lib=None, dev=None, quick=False):
         say("   conv3d N%d %d^3 %d->%d: max rel err %.2e, %.1f us, %.1f TFLOP/s (production: 92 / 82 TFLOP/s on the 128->64 / 64->64 layers)" %
             (N, S, C, cout, err, us.value, flops / max(us.value, 1e-3) * 1e-6))
 
+    def folded_up3d_case(N, S, C, cout, iters=20):
+        """nearest x2 upsample + 3x3x3 SAME convolution evaluated on the S^3 source (sub-pixel folding): output parity phase r
+        of an axis reads source offsets {-1: w0, 0: w1 + w2} (r = 0) or {0: w0 + w1, +1: w2} (r = 1), so each of the 8 phases is
+        an 8-tap convolution with pre-summed weights whose results land on y[:, rz::2, ry::2, rx::2] - 64 tap GEMMs for 216"""
+        x = rng.standard_normal((N, S, S, S, C)).astype(np.float32)
+        w = (rng.standard_normal((3, 3, 3, C, cout)) / np.sqrt(27 * C)).astype(np.float32)
+        bias = rng.standard_normal(cout).astype(np.float32) * 0.1
+        dx, db = torch.tensor(x, device=dev), torch.tensor(bias, device=dev)
+        y = torch.zeros(N, 2 * S, 2 * S, 2 * S, cout, device=dev)
+        axis = {0: [(-1, (0,)), (0, (1, 2))], 1: [(0, (0, 1)), (1, (2,))]}          # phase -> [(source offset, summed kernel taps)]
+        total_us, keep = 0.0, []
+        for rz in range(2):
+            for ry in range(2):
+                for rx in range(2):
+                    taps, mats = [], []
+                    for oz_, kz in axis[rz]:
+                        for oy_, ky in axis[ry]:
+                            for ox_, kx in axis[rx]:
+                                taps.append((ox_, oy_, oz_))
+                                mats.append(sum(w[a, b, c] for a in kz for b in ky for c in kx).astype(np.float32))
+                    dw = torch.tensor(pack_stages(k_blocks(mats), min(cout, 128)), device=dev)
+                    keep.append(dw)
+                    I = ctypes.c_int * 8
+                    geom = (ctypes.c_int * 12)(S, S, S, S, S, S, 2 * S, 2 * S, 2 * S, rz, ry, rx)
+                    us = ctypes.c_float(0)
+                    r = lib.probe_conv_tma_taps(dx.data_ptr(), N, C, geom, dw.data_ptr(), db.data_ptr(), y.data_ptr(), cout, 1, 8,
+                                                I(*[t[0] for t in taps]), I(*[t[1] for t in taps]), I(*[t[2] for t in taps]), 2, 0.3, iters,
+                                                ctypes.byref(us))
+                    if r:
+                        say("   folded up3d N%d %d^3 %d->%d phase (%d,%d,%d) -> error %d" % (N, S, C, cout, rz, ry, rx, r))
+                        return
+                    total_us += us.value
+        nb = min(N, 1)
+        up = torch.tensor(x[:nb]).permute(0, 4, 1, 2, 3).double().repeat_interleave(2, 2).repeat_interleave(2, 3).repeat_interleave(2, 4)
+        ref = torch.nn.functional.conv3d(up, torch.tensor(w).permute(4, 3, 0, 1, 2).double(), torch.tensor(bias).double(), padding=1)
+        ref = torch.nn.functional.leaky_relu(ref, 0.3).permute(0, 2, 3, 4, 1).numpy()
+        err = float(np.abs(y[:nb].cpu().numpy() - ref).max() / np.abs(ref).max())
+        flops = 2.0 * N * (2 * S) ** 3 * cout * 27 * C                  # the reference formulation (on the upsampled grid)
+        say("   folded up3d N%d %d^3 %d->%d (8 phase launches): max rel err %.2e, %.1f us, %.1f TFLOP/s algorithmic (production: 498 / 587)" %
+            (N, S, C, cout, err, total_us, flops / max(total_us, 1e-3) * 1e-6))
+
     say("4. probe_conv_tma_fast (candidate) against the production kernel")
     if os.environ.get("CN_PROBE_NCU"):              # under ncu: one heavy layer, one launch of each kernel
         fast_case(16, 64, 64, 256, 256, 1, iters=1)
@@ -289,6 +330,7 @@ def main(lib=None, dev=None, quick=False):
         fast_case(1, 16, 16, 32, 256, 1, iters=1)
         dgrad_s2_case(1, 32, 32, 48, 96, iters=1)
         conv3d_case(1, 8, 32, 16, iters=1)
+        folded_up3d_case(1, 8, 32, 16, iters=1)
         return lines
     fast_case(32, 128, 128, 48, 96, 2)              # discriminator block 1: 48 channels = one and a half k-blocks per tap
     fast_case(16, 256, 256, 64, 64, 1)              # the 64 -> 64 layer at 256 x 256 of the role profile
@@ -300,6 +342,7 @@ def main(lib=None, dev=None, quick=False):
     dgrad_s2_case(32, 64, 64, 96, 192)
     conv3d_case(16, 16, 128, 64)                    # map_3d_post conv0 / conv1 of the generator
     conv3d_case(16, 16, 64, 64)
+    folded_up3d_case(16, 8, 256, 128)               # map_3d_1 of the generator (Up3D + Conv3D 256 -> 128 on 8^3 -> 16^3)
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     with open(OUT, "w") as fp:
         fp.write("\n".join(lines) + "\n")

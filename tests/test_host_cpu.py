@@ -542,8 +542,8 @@ def test_probe_script_host_logic_against_emulated_kernels():
     assert model_err["truncate"] < 1e-6 and min(model_err["round-nearest-away"], model_err["round-nearest-even"]) > 1e-5, text
     assert text.count(": 0 of 4096 elements differ") == 5, text
     assert text.count("max abs diff 0 (exact integers expected: 0)") == 4, text
-    errs = [float(l.split("max rel err ")[1].split(" ")[0].rstrip(",")) for l in lines if l.strip().startswith(("fast ", "dgrad-s2 ", "conv3d "))]
-    assert len(errs) == 5 and max(errs) < 5e-6, text
+    errs = [float(l.split("max rel err ")[1].split(" ")[0].rstrip(",")) for l in lines if l.strip().startswith(("fast ", "dgrad-s2 ", "conv3d ", "folded up3d "))]
+    assert len(errs) == 6 and max(errs) < 5e-6, text
 
 
 def test_candidate_kernel_protocol_model():
