@@ -317,8 +317,11 @@ def main(lib=None, dev=None, quick=False):
         ref = torch.nn.functional.leaky_relu(ref, 0.3).permute(0, 2, 3, 4, 1).numpy()
         err = float(np.abs(y[:nb].cpu().numpy() - ref).max() / np.abs(ref).max())
         flops = 2.0 * N * (2 * S) ** 3 * cout * 27 * C                  # the reference formulation (on the upsampled grid)
-        say("   folded up3d N%d %d^3 %d->%d (8 phase launches): max rel err %.2e, %.1f us, %.1f TFLOP/s algorithmic (production: 498 / 587)" %
-            (N, S, C, cout, err, total_us, flops / max(total_us, 1e-3) * 1e-6))
+        tiles = N * S ** 3 // 128 * max(1, cout // 128)
+        say("   folded up3d N%d %d^3 %d->%d (8 phase launches of %d tiles each - %s): max rel err %.2e, %.1f us, %.1f TFLOP/s algorithmic "
+            "(production, all phases in one launch: 498 / 587)" %
+            (N, S, C, cout, tiles, "fewer than the 148 SMs, so merge the phases before comparing" if tiles < 148 else "enough to fill the GPU",
+             err, total_us, flops / max(total_us, 1e-3) * 1e-6))
 
     say("4. probe_conv_tma_fast (candidate) against the production kernel")
     if os.environ.get("CN_PROBE_NCU"):              # under ncu: one heavy layer, one launch of each kernel
