@@ -1,7 +1,7 @@
 """Runs the round-2 design probes (confignet_b200/csrc/experiments/round2_probes.cu, built by __graft_entry__.build()
 into confignet_b200/lib/libcn_probes.so) on a B200 and writes gpurun_out/round2_probes.txt:
 
-    gpurun --timeout 300 -- 'timeout 240 python scripts/gpu_probe_round2.py'
+    gpurun --timeout 1000 -- 'timeout 900 python scripts/gpu_probe_round2.py'      (one process per section, 120 s each at most)
 
   1. what kind::tf32 does with the low 13 mantissa bits of a raw fp32 operand (truncate / round-to-nearest);
   2. whether a tiled (C, W, H, N) tensor map with negative / overhanging start coordinates and element strides delivers the
@@ -87,33 +87,39 @@ def k_blocks(w_taps):
     return out
 
 
-def main(lib=None, dev=None, quick=False):
+SECTIONS = ("1", "2", "3", "4a", "4b", "4c", "4d")
+
+
+def main(lib=None, dev=None, quick=False, sections=SECTIONS):
     """lib / dev / quick exist for tests/test_host_cpu.py, which runs this host logic against a NumPy emulation of the four
-    entry points (CPU tensors) so that a GPU visit is not spent on a packing or indexing slip in this script."""
+    entry points (CPU tensors) so that a GPU visit is not spent on a packing or indexing slip in this script.  On the GPU
+    the sections run in separate processes (see run_sections): a faulting kernel poisons only its own CUDA context."""
     if lib is None:
         assert torch.cuda.is_available(), "needs a GPU"
         lib, dev = load(), torch.device("cuda:0")
     rng = np.random.RandomState(0)
+    want = lambda sec: sec in sections
 
     # ---------------------------------------------------------------- 1. operand handling
-    A = (rng.rand(128, 32).astype(np.float32) + 1.0)
-    A[0, :] = np.float32(1 + 2.0 ** -11)                      # midpoint: trunc 1, ties-away 1+2^-10, ties-even 1
-    A[1, :] = np.float32(1 + 2.0 ** -11 + 2.0 ** -20)         # just above the midpoint: both roundings 1+2^-10, trunc 1
-    A[2, :] = np.float32(1 + 3 * 2.0 ** -11)                  # midpoint: trunc 1+2^-10, both roundings 1+2^-9
-    B = (rng.rand(16, 32).astype(np.float32) + 1.0)
-    B[0, :] = 1.0
-    dA, dB, dD = torch.tensor(A, device=dev), torch.tensor(B, device=dev), torch.zeros(128, 16, device=dev)
-    r = lib.probe_tf32_operands(dA.data_ptr(), dB.data_ptr(), dD.data_ptr())
-    say("1. probe_tf32_operands ->", r)
-    if r == 0:
-        D = dD.cpu().numpy().astype(np.float64)
-        models = {"truncate": (trunc13(A), trunc13(B)), "round-nearest-away": (round13(A, True), round13(B, True)),
-                  "round-nearest-even": (round13(A, False), round13(B, False))}
-        for name, (a, b) in models.items():
-            ref = a.astype(np.float64) @ b.astype(np.float64).T
-            say("   model %-20s max rel err %.3e   (rows 0..2, col 0: %s)" % (name, np.abs(D - ref).max() / np.abs(ref).max(),
-                                                                         (ref[:3, 0] / 32).tolist()))
-        say("   measured rows 0..2, col 0 / 32:", (D[:3, 0] / 32).tolist())
+    if want("1"):
+        A = (rng.rand(128, 32).astype(np.float32) + 1.0)
+        A[0, :] = np.float32(1 + 2.0 ** -11)                      # midpoint: trunc 1, ties-away 1+2^-10, ties-even 1
+        A[1, :] = np.float32(1 + 2.0 ** -11 + 2.0 ** -20)         # just above the midpoint: both roundings 1+2^-10, trunc 1
+        A[2, :] = np.float32(1 + 3 * 2.0 ** -11)                  # midpoint: trunc 1+2^-10, both roundings 1+2^-9
+        B = (rng.rand(16, 32).astype(np.float32) + 1.0)
+        B[0, :] = 1.0
+        dA, dB, dD = torch.tensor(A, device=dev), torch.tensor(B, device=dev), torch.zeros(128, 16, device=dev)
+        r = lib.probe_tf32_operands(dA.data_ptr(), dB.data_ptr(), dD.data_ptr())
+        say("1. probe_tf32_operands ->", r)
+        if r == 0:
+            D = dD.cpu().numpy().astype(np.float64)
+            models = {"truncate": (trunc13(A), trunc13(B)), "round-nearest-away": (round13(A, True), round13(B, True)),
+                      "round-nearest-even": (round13(A, False), round13(B, False))}
+            for name, (a, b) in models.items():
+                ref = a.astype(np.float64) @ b.astype(np.float64).T
+                say("   model %-20s max rel err %.3e   (rows 0..2, col 0: %s)" % (name, np.abs(D - ref).max() / np.abs(ref).max(),
+                                                                             (ref[:3, 0] / 32).tolist()))
+            say("   measured rows 0..2, col 0 / 32:", (D[:3, 0] / 32).tolist())
 
     # ---------------------------------------------------------------- 2. TMA tile with OOB fill / element strides
     def tile_case(N, H, W, C, bw, bh, stride, c, xs, ys, n):
@@ -136,12 +142,13 @@ def main(lib=None, dev=None, quick=False):
         say("   tile N%d H%d W%d C%d box %dx%d stride %d start (c%d,x%d,y%d,n%d): %d of 4096 elements differ%s" %
             (N, H, W, C, bw, bh, stride, c, xs, ys, n, bad, "" if not bad else "  first rows got %s want %s" % (got[:2, :4].tolist(), want[:2, :4].tolist())))
 
-    say("2. probe_tma_tile (zero fill = SAME padding, swizzled K-major rows)")
-    tile_case(2, 16, 16, 64, 16, 8, 1, 32, -1, -1, 1)
-    tile_case(2, 16, 16, 64, 16, 8, 1, 0, 1, 9, 0)            # overhang right / bottom
-    tile_case(1, 32, 32, 32, 16, 8, 2, 0, 0, 0, 0)            # stride 2, tap 0 of a pad-0-in-front SAME conv
-    tile_case(1, 32, 32, 32, 16, 8, 2, 0, 2, 18, 0)           # stride 2, last tap, bottom rows overhang
-    tile_case(1, 4, 128, 32, 128, 1, 1, 0, -1, 3, 0)          # one image row per tile
+    if want("2"):
+        say("2. probe_tma_tile (zero fill = SAME padding, swizzled K-major rows)")
+        tile_case(2, 16, 16, 64, 16, 8, 1, 32, -1, -1, 1)
+        tile_case(2, 16, 16, 64, 16, 8, 1, 0, 1, 9, 0)            # overhang right / bottom
+        tile_case(1, 32, 32, 32, 16, 8, 2, 0, 0, 0, 0)            # stride 2, tap 0 of a pad-0-in-front SAME conv
+        tile_case(1, 32, 32, 32, 16, 8, 2, 0, 2, 18, 0)           # stride 2, last tap, bottom rows overhang
+        tile_case(1, 4, 128, 32, 128, 1, 1, 0, -1, 3, 0)          # one image row per tile
 
     # ---------------------------------------------------------------- 3. conv through TMA + SS-form MMA
     def conv_case(N, H, W, C, stride):
@@ -167,11 +174,12 @@ def main(lib=None, dev=None, quick=False):
         say("   conv N%d H%d W%d C%d stride %d: max abs diff %.3g (exact integers expected: 0)" %
             (N, H, W, C, stride, float(np.abs(y.cpu().numpy() - ref).max())))
 
-    say("3. probe_conv_tma (A fetched by TMA only, MMA reads it from shared memory)")
-    conv_case(2, 16, 16, 64, 1)
-    conv_case(1, 32, 32, 32, 2)
-    conv_case(1, 4, 128, 32, 1)
-    conv_case(1, 64, 64, 96, 2)
+    if want("3"):
+        say("3. probe_conv_tma (A fetched by TMA only, MMA reads it from shared memory)")
+        conv_case(2, 16, 16, 64, 1)
+        conv_case(1, 32, 32, 32, 2)
+        conv_case(1, 4, 128, 32, 1)
+        conv_case(1, 64, 64, 96, 2)
     # ---------------------------------------------------------------- 4. the candidate kernel against production
     def fast_case(N, H, W, C, cout, stride, iters=20):
         x = rng.standard_normal((N, H, W, C)).astype(np.float32)
@@ -323,34 +331,60 @@ def main(lib=None, dev=None, quick=False):
             (N, S, C, cout, tiles, "fewer than the 148 SMs, so merge the phases before comparing" if tiles < 148 else "enough to fill the GPU",
              err, total_us, flops / max(total_us, 1e-3) * 1e-6))
 
-    say("4. probe_conv_tma_fast (candidate) against the production kernel")
+    if any(want(x) for x in ("4a", "4b", "4c", "4d")):
+        say("4. probe_conv_tma_fast (candidate) against the production kernel [%s]" % ",".join(x for x in sections if x.startswith("4")))
     if os.environ.get("CN_PROBE_NCU"):              # under ncu: one heavy layer, one launch of each kernel
         fast_case(16, 64, 64, 256, 256, 1, iters=1)
         return lines
-    fast_case(2, 32, 32, 64, 64, 1, iters=3)
     if quick:
+        fast_case(2, 32, 32, 64, 64, 1, iters=3)
         fast_case(1, 32, 32, 48, 96, 2, iters=1)
         fast_case(1, 16, 16, 32, 256, 1, iters=1)
         dgrad_s2_case(1, 32, 32, 48, 96, iters=1)
         conv3d_case(1, 8, 32, 16, iters=1)
         folded_up3d_case(1, 8, 32, 16, iters=1)
         return lines
-    fast_case(32, 128, 128, 48, 96, 2)              # discriminator block 1: 48 channels = one and a half k-blocks per tap
-    fast_case(16, 256, 256, 64, 64, 1)              # the 64 -> 64 layer at 256 x 256 of the role profile
-    fast_case(32, 64, 64, 96, 128, 2)
-    fast_case(16, 64, 64, 256, 256, 1)              # the heaviest line of profiles/r01_conv_breakdown_final.txt (VGG block3)
-    fast_case(16, 128, 128, 128, 128, 1)
-    fast_case(16, 32, 32, 512, 512, 1)
-    dgrad_s2_case(32, 128, 128, 48, 96)             # the worst line of the breakdown: 52 TFLOP/s in production (1.68 ms per 8 calls)
-    dgrad_s2_case(32, 64, 64, 96, 192)
-    conv3d_case(16, 16, 128, 64)                    # map_3d_post conv0 / conv1 of the generator
-    conv3d_case(16, 16, 64, 64)
-    folded_up3d_case(16, 8, 256, 128)               # map_3d_1 of the generator (Up3D + Conv3D 256 -> 128 on 8^3 -> 16^3)
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    with open(OUT, "w") as fp:
-        fp.write("\n".join(lines) + "\n")
+    if want("4a"):
+        fast_case(2, 32, 32, 64, 64, 1, iters=3)
+        fast_case(32, 128, 128, 48, 96, 2)              # discriminator block 1: 48 channels = one and a half k-blocks per tap
+        fast_case(16, 256, 256, 64, 64, 1)              # the 64 -> 64 layer at 256 x 256 of the role profile
+        fast_case(32, 64, 64, 96, 128, 2)
+    if want("4b"):
+        fast_case(16, 64, 64, 256, 256, 1)              # the heaviest line of profiles/r01_conv_breakdown_final.txt (VGG block3)
+        fast_case(16, 128, 128, 128, 128, 1)
+        fast_case(16, 32, 32, 512, 512, 1)
+    if want("4c"):
+        dgrad_s2_case(32, 128, 128, 48, 96)             # the worst line of the breakdown: 52 TFLOP/s in production (1.68 ms per 8 calls)
+        dgrad_s2_case(32, 64, 64, 96, 192)
+    if want("4d"):
+        conv3d_case(16, 16, 128, 64)                    # map_3d_post conv0 / conv1 of the generator
+        conv3d_case(16, 16, 64, 64)
+        folded_up3d_case(16, 8, 256, 128)               # map_3d_1 of the generator (Up3D + Conv3D 256 -> 128 on 8^3 -> 16^3)
     return lines
 
 
+def run_sections():
+    """one process per section, each under its own timeout; the collected lines go to gpurun_out/round2_probes.txt"""
+    import subprocess
+    collected = []
+    for sec in SECTIONS:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--section", sec], capture_output=True, text=True, timeout=120)
+            out, tail = r.stdout, ("" if r.returncode == 0 else "   [section %s exited with %d] %s" % (sec, r.returncode, r.stderr.strip().splitlines()[-1:] or ""))
+        except subprocess.TimeoutExpired as e:
+            out, tail = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or ""), "   [section %s timed out after 120 s]" % sec
+        for l in out.splitlines() + ([tail] if tail else []):
+            print(l, flush=True)
+            collected.append(l)
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    with open(OUT, "w") as fp:
+        fp.write("\n".join(collected) + "\n")
+
+
 if __name__ == "__main__":
-    main()
+    if "--section" in sys.argv:
+        main(sections=(sys.argv[sys.argv.index("--section") + 1],))
+    elif os.environ.get("CN_PROBE_NCU"):
+        main()
+    else:
+        run_sections()
