@@ -559,6 +559,15 @@ extern "C" int probe_conv_tma_taps(const float* x, int N, int C, const int* geom
   return f;
 }
 
+// the candidate's shared / tensor memory plan for a channel tile of bn columns (host only; checked by the CPU suite):
+// out = {stages, stage_bytes, b_plane, tot_off, bar_off, tmem_off, smem_bytes, a_col0}
+extern "C" int probe_fast_cfg(int bn, int* out) {
+  const FastCfg c = fast_cfg(bn);
+  const int v[8] = {c.stages, c.stage_bytes, c.b_plane, c.tot_off, c.bar_off, c.tmem_off, c.smem_bytes, c.a_col0};
+  for (int i = 0; i < 8; ++i) out[i] = v[i];
+  return 0;
+}
+
 // forward 3x3 SAME convolution, stride 1 or 2, + bias + LeakyReLU(alpha)
 extern "C" int probe_conv_tma_fast(const float* x, const float* wp, const float* bias, float* y, int N, int H, int W, int C, int cout,
                                    int stride, float alpha, int iters, float* avg_us) {

@@ -414,6 +414,17 @@ def test_round2_probe_library_builds_and_exports():
         assert hasattr(lib, name), name
     main = ctypes.CDLL(os.path.join(root, "confignet_b200", "lib", "libconfignet_b200.so"))
     assert not hasattr(main, "probe_conv_tma")
+    # the candidate's memory plan for every channel-tile width: fits 227 KB of shared memory and 512 tensor-memory columns,
+    # every swizzled tile starts on a 1024-byte boundary
+    for bn in range(16, 129, 16):
+        out = (ctypes.c_int * 8)()
+        assert lib.probe_fast_cfg(bn, out) == 0
+        stages, stage_bytes, b_plane, tot_off, bar_off, tmem_off, smem_bytes, a_col0 = list(out)
+        assert 2 <= stages <= 6 and smem_bytes + 1024 <= 227 * 1024, (bn, list(out))
+        assert a_col0 == 2 * bn and a_col0 + 32 * stages <= 512
+        assert stage_bytes == 128 * 128 + 2 * b_plane and stage_bytes % 1024 == 0 and b_plane % 1024 == 0
+        assert tot_off == stages * stage_bytes and tot_off % 1024 == 0 and bar_off - tot_off >= bn * 129 * 4
+        assert tmem_off - bar_off >= 8 * (3 * stages + 4) and smem_bytes >= tmem_off + 4
 
 
 def test_probe_script_host_logic_against_emulated_kernels():
