@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace {
 
@@ -222,7 +223,11 @@ constexpr int F_THREADS = 320;
 constexpr int F_CH = 8;                    // k-blocks per accumulation chunk (production: TC_CHUNK_KB)
 constexpr int F_TOT_LD = 129;              // leading dimension of the running total
 
-struct TapList { int n; short dx[32], dy[32], dz[32]; };     // source offset of every tap, in source pixels / voxels (SAME padding folded in)
+// Phases of one launch: GEMMs over the same pixel grid that differ in tap list, weights and output offset (the parity phases
+// of a stride-2 input gradient, the sub-pixel phases of a folded upsample + conv; a plain convolution is one phase).
+// Taps of phase p: [tap0[p], tap0[p] + ntaps[p]); dx/dy/dz = source offset in source pixels / voxels (SAME padding folded in);
+// (oz, oy, ox)[p] = offset of the phase's outputs on the ostride-spaced output grid.
+struct PhaseList { int nphase; int ntaps[8], tap0[8]; short dx[64], dy[64], dz[64]; short oz[8], oy[8], ox[8]; };
 
 struct FastCfg { int stages, stage_bytes, b_plane, tot_off, bar_off, tmem_off, smem_bytes, a_col0; };
 __host__ __device__ inline FastCfg fast_cfg(int bn) {
@@ -279,8 +284,8 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* v) {
 
 __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_constant__ CUtensorMap map, const float* __restrict__ wp,
                                                                   const float* __restrict__ bias, float* __restrict__ y, int N, int Do, int Ho, int Wo,
-                                                                  int C, int bn, int cout, int stride, const __grid_constant__ TapList taps, int bw, int bh, int bd,
-                                                                  float alpha, int od, int oh, int ow, int ostride, int oz, int oy, int ox) {
+                                                                  int C, int bn, int cout, int stride, const __grid_constant__ PhaseList P, int bw, int bh, int bd,
+                                                                  float alpha, int od, int oh, int ow, int ostride) {
   // `map` is always 5-D (C, W, H, D, N); images are volumes of depth 1 (Do = bd = od = 1, dz = oz = 0).
   // GEMM rows = the (Do x) Ho x Wo grid of this launch; row (py, px) reads source pixel (py * stride + dy, px * stride + dx)
   // for tap (dx, dy) and writes output pixel (py * ostride + oy, px * ostride + ox) of an oh x ow image: a forward
@@ -307,8 +312,8 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_off);
   const int tiles_x = Wo / bw, tiles_y = Ho / bh, tiles_z = Do / bd, tiles_img = tiles_x * tiles_y * tiles_z;
-  const int n_nt = cout / bn, n_tiles = N * tiles_img * n_nt;   // item = (pixel tile, channel tile), channel tile inner
-  const int cblocks = (C + 31) / 32, num_kb = taps.n * cblocks;   // a partial last block: the TMA zero-fills the missing channels
+  const int n_nt = cout / bn, nph = P.nphase, n_tiles = N * tiles_img * nph * n_nt;   // item = (pixel tile, phase, channel tile), channel tile innermost
+  const int cblocks = (C + 31) / 32;                              // a partial last block: the TMA zero-fills the missing channels
   const uint32_t stage_tx = (uint32_t)L.stage_bytes;
 
   if (warp == 0) {
@@ -316,15 +321,17 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
     if (lane == 0) {
       int s = 0, ph = 0; long git = 0;
       for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
-        const int t = w / n_nt, nt = w % n_nt;
+        const int nt = w % n_nt, ph_i = (w / n_nt) % nph, t = w / (n_nt * nph);
         const int n = t / tiles_img, tz = (t / (tiles_x * tiles_y)) % tiles_z, ty = (t / tiles_x) % tiles_y, tx = t % tiles_x;
-        const float* wsrc = wp + (size_t)nt * num_kb * (2 * L.b_plane / 4);
+        const int num_kb = P.ntaps[ph_i] * cblocks, tap_base = P.tap0[ph_i];
+        // weight stages: phase after phase; inside a phase channel tile after channel tile, k-blocks tap-major
+        const float* wsrc = wp + ((size_t)tap_base * cblocks * n_nt + (size_t)nt * num_kb) * (2 * L.b_plane / 4);
         for (int kb = 0; kb < num_kb; ++kb, ++git) {
           if (git >= S) mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          const int tap = kb / cblocks, cb = kb % cblocks;
+          const int tap = tap_base + kb / cblocks, cb = kb % cblocks;
           const uint32_t dst = sbase + s * L.stage_bytes;
           mbar_arrive_expect_tx(bar_full + 8 * s, stage_tx);
-          tma_load_5d(dst, &map, cb * 32, tx * bw * stride + taps.dx[tap], ty * bh * stride + taps.dy[tap], tz * bd * stride + taps.dz[tap], n,
+          tma_load_5d(dst, &map, cb * 32, tx * bw * stride + P.dx[tap], ty * bh * stride + P.dy[tap], tz * bd * stride + P.dz[tap], n,
                       bar_full + 8 * s);
           bulk_g2s(dst + A_BYTES, wsrc + (size_t)kb * (2 * L.b_plane / 4), 2 * L.b_plane, bar_full + 8 * s);
           if (++s == S) { s = 0; ph ^= 1; }
@@ -336,6 +343,7 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
     const uint32_t idesc = umma_idesc_tf32(bn);
     int s = 0, ph = 0, b = 0, inchunk = 0, c = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int num_kb = P.ntaps[(t / n_nt) % nph] * cblocks;
       for (int kb = 0; kb < num_kb; ++kb) {
         const bool chunk_first = inchunk == 0, chunk_last = inchunk == F_CH - 1 || kb == num_kb - 1;
         if (chunk_first && c >= 2) mbar_wait(bar_accempty + 8 * b, ((c >> 1) - 1) & 1);
@@ -367,6 +375,7 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     int s = 0, ph = 0; long git = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int num_kb = P.ntaps[(t / n_nt) % nph] * cblocks;
       for (int kb = 0; kb < num_kb; ++kb, ++git) {
         mbar_wait(bar_full + 8 * s, ph);
         if (git >= S) mbar_wait(bar_empty + 8 * s, ph ^ 1);          // the tensor-memory stage was read by the MMAs of its last use
@@ -397,6 +406,7 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     int b = 0, c = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int ph_i = (t / n_nt) % nph, num_kb = P.ntaps[ph_i] * cblocks;
       const int nchunks = (num_kb + F_CH - 1) / F_CH;
       for (int ch = 0; ch < nchunks; ++ch, ++c) {
         mbar_wait(bar_accfull + 8 * b, (c >> 1) & 1);
@@ -420,7 +430,8 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
         b ^= 1;
       }
       __syncwarp();                               // a warp finishes the 32 rows it promoted itself: no cross-warp dependency
-      const int pt = t / n_nt, n0 = (t % n_nt) * bn;
+      const int pt = t / (n_nt * nph), n0 = (t % n_nt) * bn;
+      const int ox = P.ox[ph_i], oy = P.oy[ph_i], oz = P.oz[ph_i];
       const int n = pt / tiles_img, tz = (pt / (tiles_x * tiles_y)) % tiles_z, ty = (pt / tiles_x) % tiles_y, tx = pt % tiles_x;
       float bz[4];
 #pragma unroll
@@ -512,27 +523,33 @@ extern "C" int probe_tma_tile(const float* x, int N, int H, int W, int C, int bw
   return finish();
 }
 
-// The general entry.  x: source (N, D, H, W, C) (D = 1 for images); the launch covers a gd x gh x gw grid of GEMM pixels; tap t
-// reads source voxel (pz * stride + dz[t], py * stride + dy[t], px * stride + dx[t]) (zero outside) and the result goes to output
-// voxel (pz * ostride + oz, py * ostride + oy, px * ostride + ox) of y (N, od, oh, ow, cout).  alpha: LeakyReLU slope (1 = no
-// activation); bias may be null.  geom = {D, H, W, gd, gh, gw, od, oh, ow, oz, oy, ox}.
-// wp: per channel tile (bn = min(cout, 128) output channels), per k-block (tap-major, then 32-channel block) the big plane then
-// the small plane, each bn rows x 128 B in the swizzled K-major layout.  Launches `iters` times (after one warm-up) on the
-// default stream; *avg_us receives the mean launch time (CUDA events).
-extern "C" int probe_conv_tma_taps(const float* x, int N, int C, const int* geom, const float* wp, const float* bias, float* y,
-                                   int cout, int stride, int ntaps, const int* dx, const int* dy, const int* dz, int ostride,
-                                   float alpha, int iters, float* avg_us) {
-  const int D = geom[0], H = geom[1], W = geom[2], gd = geom[3], gh = geom[4], gw = geom[5], od = geom[6], oh = geom[7], ow = geom[8],
-            oz = geom[9], oy = geom[10], ox = geom[11];
+// The general entry.  x: source (N, D, H, W, C) (D = 1 for images); the launch covers a gd x gh x gw grid of GEMM pixels and
+// nphase phases; tap t of phase p (taps [tap0, tap0 + ntaps[p]) in dx / dy / dz, phases one after the other) reads source voxel
+// (pz * stride + dz[t], py * stride + dy[t], px * stride + dx[t]) (zero outside) and the phase's result goes to output voxel
+// (pz * ostride + oz[p], py * ostride + oy[p], px * ostride + ox[p]) of y (N, od, oh, ow, cout).  alpha: LeakyReLU slope
+// (1 = no activation); bias may be null.  geom = {D, H, W, gd, gh, gw, od, oh, ow}.
+// wp: phase after phase; inside a phase per channel tile (bn = min(cout, 128) output channels), per k-block (tap-major, then
+// 32-channel block) the big plane then the small plane, each bn rows x 128 B in the swizzled K-major layout.  Launches `iters`
+// times (after one warm-up) on the default stream; *avg_us receives the mean launch time (CUDA events).
+extern "C" int probe_conv_tma_phases(const float* x, int N, int C, const int* geom, const float* wp, const float* bias, float* y,
+                                     int cout, int stride, int nphase, const int* ntaps, const int* dx, const int* dy, const int* dz,
+                                     const int* oz, const int* oy, const int* ox, int ostride, float alpha, int iters, float* avg_us) {
+  const int D = geom[0], H = geom[1], W = geom[2], gd = geom[3], gh = geom[4], gw = geom[5], od = geom[6], oh = geom[7], ow = geom[8];
   const int bn = cout <= 128 ? cout : 128;
-  if (cout % bn || ntaps < 1 || ntaps > 32) return -2;
+  if (cout % bn || nphase < 1 || nphase > 8) return -2;
   const int bw = gw < 128 ? gw : 128, bh = gh < 128 / bw ? gh : 128 / bw, bd = 128 / (bw * bh);
   if (C % 4 || bn % 16 || 128 % bw || (128 / bw) % bh || gw % bw || gh % bh || gd % bd) return -2;      // C * 4 bytes: the tensor map's 16-byte stride rule
-  TapList taps;
-  taps.n = ntaps;
-  for (int t = 0; t < 32; ++t) {
-    taps.dx[t] = (short)(t < ntaps ? dx[t] : 0); taps.dy[t] = (short)(t < ntaps ? dy[t] : 0); taps.dz[t] = (short)(t < ntaps && dz ? dz[t] : 0);
+  PhaseList P;
+  memset(&P, 0, sizeof(P));
+  P.nphase = nphase;
+  int total = 0;
+  for (int p = 0; p < nphase; ++p) {
+    if (ntaps[p] < 1) return -2;
+    P.ntaps[p] = ntaps[p]; P.tap0[p] = total; total += ntaps[p];
+    P.oz[p] = (short)(oz ? oz[p] : 0); P.oy[p] = (short)(oy ? oy[p] : 0); P.ox[p] = (short)(ox ? ox[p] : 0);
   }
+  if (total > 64) return -2;
+  for (int t = 0; t < total; ++t) { P.dx[t] = (short)dx[t]; P.dy[t] = (short)dy[t]; P.dz[t] = (short)(dz ? dz[t] : 0); }
   CUtensorMap map;
   const int r = make_map5(&map, x, N, D, H, W, C, bw, bh, bd, stride);
   if (r) return r;
@@ -542,13 +559,13 @@ extern "C" int probe_conv_tma_taps(const float* x, int N, int C, const int* geom
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int n_tiles = N * (gd / bd) * (gh / bh) * (gw / bw) * (cout / bn), grid = n_tiles < sms ? n_tiles : sms;
+  const int n_tiles = N * (gd / bd) * (gh / bh) * (gw / bw) * nphase * (cout / bn), grid = n_tiles < sms ? n_tiles : sms;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < iters + 1; ++it) {
     if (it == 1) cudaEventRecord(e0);
-    conv_tma_fast_kernel<<<grid, F_THREADS, L.smem_bytes + 1024>>>(map, wp, bias, y, N, gd, gh, gw, C, bn, cout, stride, taps, bw, bh, bd, alpha,
-                                                                   od, oh, ow, ostride, oz, oy, ox);
+    conv_tma_fast_kernel<<<grid, F_THREADS, L.smem_bytes + 1024>>>(map, wp, bias, y, N, gd, gh, gw, C, bn, cout, stride, P, bw, bh, bd, alpha,
+                                                                   od, oh, ow, ostride);
   }
   cudaEventRecord(e1);
   const int f = finish();
@@ -568,15 +585,16 @@ extern "C" int probe_fast_cfg(int bn, int* out) {
   return 0;
 }
 
-// forward 3x3 SAME convolution, stride 1 or 2, + bias + LeakyReLU(alpha)
+// forward 3x3 SAME convolution, stride 1 or 2, + bias + LeakyReLU(alpha): one phase of 9 taps
 extern "C" int probe_conv_tma_fast(const float* x, const float* wp, const float* bias, float* y, int N, int H, int W, int C, int cout,
                                    int stride, float alpha, int iters, float* avg_us) {
   const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
   const int total = (Ho - 1) * stride + 3 - H, pad = (total > 0 ? total : 0) / 2;       // TF SAME: the smaller half in front
   int dx[9], dy[9];
   for (int t = 0; t < 9; ++t) { dx[t] = t % 3 - pad; dy[t] = t / 3 - pad; }
-  const int geom[12] = {1, H, W, 1, Ho, Wo, 1, Ho, Wo, 0, 0, 0};
-  return probe_conv_tma_taps(x, N, C, geom, wp, bias, y, cout, stride, 9, dx, dy, nullptr, 1, alpha, iters, avg_us);
+  const int geom[9] = {1, H, W, 1, Ho, Wo, 1, Ho, Wo}, ntaps = 9;
+  return probe_conv_tma_phases(x, N, C, geom, wp, bias, y, cout, stride, 1, &ntaps, dx, dy, nullptr, nullptr, nullptr, nullptr, 1, alpha,
+                               iters, avg_us);
 }
 
 extern "C" int probe_conv_tma(const float* x, const float* wp, float* y, int N, int H, int W, int C, int stride) {

@@ -55,8 +55,8 @@ def load():
     lib.probe_tma_tile.argtypes = [P] + [ctypes.c_int] * 11 + [P]
     lib.probe_conv_tma.argtypes = [P, P, P] + [ctypes.c_int] * 5
     lib.probe_conv_tma_fast.argtypes = [P, P, P, P] + [ctypes.c_int] * 6 + [ctypes.c_float, ctypes.c_int, P]
-    lib.probe_conv_tma_taps.argtypes = [P, ctypes.c_int, ctypes.c_int, P, P, P, P] + [ctypes.c_int] * 3 + [P, P, P, ctypes.c_int,
-                                                                                                      ctypes.c_float, ctypes.c_int, P]
+    lib.probe_conv_tma_phases.argtypes = [P, ctypes.c_int, ctypes.c_int, P, P, P, P] + [ctypes.c_int] * 3 + [P] * 7 + \
+        [ctypes.c_int, ctypes.c_float, ctypes.c_int, P]
     return lib
 
 
@@ -74,6 +74,21 @@ def pack_stages(mats, bn):
             for plane, src in enumerate((big, small)):
                 wp[nt, kb, plane, idx] = src[:, nt * bn:nt * bn + bn].T.ravel()
     return wp
+
+
+def run_phases(lib, dx, N, C, geom9, phases, bias, y, cout, stride, ostride, alpha, iters):
+    """phases: list of (taps [(dx, dy, dz)], mats [(K, cout) per tap], (oz, oy, ox)) -> (return code, microseconds, keep-alive)"""
+    dev = dx.device
+    wp = np.concatenate([pack_stages(k_blocks(m), min(cout, 128)).ravel() for _, m, _ in phases])
+    dw = torch.tensor(wp, device=dev)
+    flat = [t for taps, _, _ in phases for t in taps]
+    I = lambda v: (ctypes.c_int * len(v))(*v)
+    us = ctypes.c_float(0)
+    r = lib.probe_conv_tma_phases(dx.data_ptr(), N, C, I(geom9), dw.data_ptr(), None if bias is None else bias.data_ptr(), y.data_ptr(),
+                                  cout, stride, len(phases), I([len(t) for t, _, _ in phases]), I([t[0] for t in flat]), I([t[1] for t in flat]),
+                                  I([t[2] for t in flat]), I([o[0] for _, _, o in phases]), I([o[1] for _, _, o in phases]),
+                                  I([o[2] for _, _, o in phases]), ostride, alpha, iters, ctypes.byref(us))
+    return r, us.value, dw
 
 
 def k_blocks(w_taps):
@@ -230,7 +245,7 @@ def main(lib=None, dev=None, quick=False, sections=SECTIONS):
         w = (rng.standard_normal((3, 3, cin, cout)) / np.sqrt(9 * cin)).astype(np.float32)
         gy = rng.standard_normal((N, H // 2, W // 2, cout)).astype(np.float32)
         dgy, gx = torch.tensor(gy, device=dev), torch.zeros(N, H, W, cin, device=dev)
-        total_us, keep = 0.0, []
+        phases = []
         for py in range(2):
             for px in range(2):
                 # y[i] = sum_t x[2 i + t] w[t] (SAME: no padding in front for even sizes)  =>  gx[2 q] = gy[q] w[0] + gy[q - 1] w[2],
@@ -238,19 +253,11 @@ def main(lib=None, dev=None, quick=False, sections=SECTIONS):
                 ty = [(0, 0), (2, -1)] if py == 0 else [(1, 0)]
                 tx = [(0, 0), (2, -1)] if px == 0 else [(1, 0)]
                 taps = [(a, b, oa, ob) for a, oa in ty for b, ob in tx]
-                wp = pack_stages(k_blocks([w[a, b].T.copy() for a, b, _, _ in taps]), min(cin, 128))      # K = cout, N = cin
-                dw = torch.tensor(wp, device=dev)
-                keep.append(dw)
-                dxs = (ctypes.c_int * len(taps))(*[ob for _, _, _, ob in taps])
-                dys = (ctypes.c_int * len(taps))(*[oa for _, _, oa, _ in taps])
-                geom = (ctypes.c_int * 12)(1, H // 2, W // 2, 1, H // 2, W // 2, 1, H, W, 0, py, px)
-                us = ctypes.c_float(0)
-                r = lib.probe_conv_tma_taps(dgy.data_ptr(), N, cout, geom, dw.data_ptr(), None, gx.data_ptr(), cin, 1,
-                                            len(taps), dxs, dys, None, 2, 1.0, iters, ctypes.byref(us))
-                if r:
-                    say("   dgrad-s2 N%d H%d W%d %d->%d phase (%d,%d) -> error %d" % (N, H, W, cin, cout, py, px, r))
-                    return
-                total_us += us.value
+                phases.append(([(ob, oa, 0) for _, _, oa, ob in taps], [w[a, b].T.copy() for a, b, _, _ in taps], (0, py, px)))   # K = cout, N = cin
+        r, total_us, keep = run_phases(lib, dgy, N, cout, [1, H // 2, W // 2, 1, H // 2, W // 2, 1, H, W], phases, None, gx, cin, 1, 2, 1.0, iters)
+        if r:
+            say("   dgrad-s2 N%d H%d W%d %d->%d -> error %d" % (N, H, W, cin, cout, r))
+            return
         nb = min(N, 2)
         xr = torch.zeros(nb, cin, H, W, dtype=torch.float64, requires_grad=True)
         yr = torch.nn.functional.conv2d(torch.nn.functional.pad(xr, (0, 1, 0, 1)), torch.tensor(w).permute(3, 2, 0, 1).double(), stride=2)
@@ -258,7 +265,7 @@ def main(lib=None, dev=None, quick=False, sections=SECTIONS):
         ref = ref.permute(0, 2, 3, 1).numpy()
         err = float(np.abs(gx[:nb].cpu().numpy() - ref).max() / np.abs(ref).max())
         flops = 2.0 * N * (H // 2) * (W // 2) * cout * 9 * cin
-        say("   dgrad-s2 N%d H%d W%d %d->%d (4 phase launches): max rel err %.2e, %.1f us, %.1f TFLOP/s" %
+        say("   dgrad-s2 N%d H%d W%d %d->%d (4 parity phases, one launch): max rel err %.2e, %.1f us, %.1f TFLOP/s" %
             (N, H, W, cin, cout, err, total_us, flops / max(total_us, 1e-3) * 1e-6))
 
     def conv3d_case(N, S, C, cout, iters=20):
@@ -266,15 +273,11 @@ def main(lib=None, dev=None, quick=False, sections=SECTIONS):
         x = rng.standard_normal((N, S, S, S, C)).astype(np.float32)
         w = (rng.standard_normal((3, 3, 3, C, cout)) / np.sqrt(27 * C)).astype(np.float32)
         bias = rng.standard_normal(cout).astype(np.float32) * 0.1
-        wp = pack_stages(k_blocks([w[t // 9, (t // 3) % 3, t % 3] for t in range(27)]), min(cout, 128))
-        dx, dw, db = torch.tensor(x, device=dev), torch.tensor(wp, device=dev), torch.tensor(bias, device=dev)
+        dx, db = torch.tensor(x, device=dev), torch.tensor(bias, device=dev)
         y = torch.zeros(N, S, S, S, cout, device=dev)
-        I = ctypes.c_int * 27
-        geom = (ctypes.c_int * 12)(S, S, S, S, S, S, S, S, S, 0, 0, 0)
-        us = ctypes.c_float(0)
-        r = lib.probe_conv_tma_taps(dx.data_ptr(), N, C, geom, dw.data_ptr(), db.data_ptr(), y.data_ptr(), cout, 1, 27,
-                                    I(*[t % 3 - 1 for t in range(27)]), I(*[(t // 3) % 3 - 1 for t in range(27)]), I(*[t // 9 - 1 for t in range(27)]),
-                                    1, 0.3, iters, ctypes.byref(us))
+        phase = ([(t % 3 - 1, (t // 3) % 3 - 1, t // 9 - 1) for t in range(27)], [w[t // 9, (t // 3) % 3, t % 3] for t in range(27)], (0, 0, 0))
+        r, us_v, keep = run_phases(lib, dx, N, C, [S] * 9, [phase], db, y, cout, 1, 1, 0.3, iters)
+        us = ctypes.c_float(us_v)
         if r:
             say("   conv3d N%d %d^3 %d->%d -> error %d" % (N, S, C, cout, r))
             return
@@ -297,7 +300,7 @@ def main(lib=None, dev=None, quick=False, sections=SECTIONS):
         dx, db = torch.tensor(x, device=dev), torch.tensor(bias, device=dev)
         y = torch.zeros(N, 2 * S, 2 * S, 2 * S, cout, device=dev)
         axis = {0: [(-1, (0,)), (0, (1, 2))], 1: [(0, (0, 1)), (1, (2,))]}          # phase -> [(source offset, summed kernel taps)]
-        total_us, keep = 0.0, []
+        phases = []
         for rz in range(2):
             for ry in range(2):
                 for rx in range(2):
@@ -307,29 +310,19 @@ def main(lib=None, dev=None, quick=False, sections=SECTIONS):
                             for ox_, kx in axis[rx]:
                                 taps.append((ox_, oy_, oz_))
                                 mats.append(sum(w[a, b, c] for a in kz for b in ky for c in kx).astype(np.float32))
-                    dw = torch.tensor(pack_stages(k_blocks(mats), min(cout, 128)), device=dev)
-                    keep.append(dw)
-                    I = ctypes.c_int * 8
-                    geom = (ctypes.c_int * 12)(S, S, S, S, S, S, 2 * S, 2 * S, 2 * S, rz, ry, rx)
-                    us = ctypes.c_float(0)
-                    r = lib.probe_conv_tma_taps(dx.data_ptr(), N, C, geom, dw.data_ptr(), db.data_ptr(), y.data_ptr(), cout, 1, 8,
-                                                I(*[t[0] for t in taps]), I(*[t[1] for t in taps]), I(*[t[2] for t in taps]), 2, 0.3, iters,
-                                                ctypes.byref(us))
-                    if r:
-                        say("   folded up3d N%d %d^3 %d->%d phase (%d,%d,%d) -> error %d" % (N, S, C, cout, rz, ry, rx, r))
-                        return
-                    total_us += us.value
+                    phases.append((taps, mats, (rz, ry, rx)))
+        r, total_us, keep = run_phases(lib, dx, N, C, [S, S, S, S, S, S, 2 * S, 2 * S, 2 * S], phases, db, y, cout, 1, 2, 0.3, iters)
+        if r:
+            say("   folded up3d N%d %d^3 %d->%d -> error %d" % (N, S, C, cout, r))
+            return
         nb = min(N, 1)
         up = torch.tensor(x[:nb]).permute(0, 4, 1, 2, 3).double().repeat_interleave(2, 2).repeat_interleave(2, 3).repeat_interleave(2, 4)
         ref = torch.nn.functional.conv3d(up, torch.tensor(w).permute(4, 3, 0, 1, 2).double(), torch.tensor(bias).double(), padding=1)
         ref = torch.nn.functional.leaky_relu(ref, 0.3).permute(0, 2, 3, 4, 1).numpy()
         err = float(np.abs(y[:nb].cpu().numpy() - ref).max() / np.abs(ref).max())
         flops = 2.0 * N * (2 * S) ** 3 * cout * 27 * C                  # the reference formulation (on the upsampled grid)
-        tiles = N * S ** 3 // 128 * max(1, cout // 128)
-        say("   folded up3d N%d %d^3 %d->%d (8 phase launches of %d tiles each - %s): max rel err %.2e, %.1f us, %.1f TFLOP/s algorithmic "
-            "(production, all phases in one launch: 498 / 587)" %
-            (N, S, C, cout, tiles, "fewer than the 148 SMs, so merge the phases before comparing" if tiles < 148 else "enough to fill the GPU",
-             err, total_us, flops / max(total_us, 1e-3) * 1e-6))
+        say("   folded up3d N%d %d^3 %d->%d (8 sub-pixel phases of 8 taps, one launch): max rel err %.2e, %.1f us, %.1f TFLOP/s algorithmic "
+            "(production: 498 / 587)" % (N, S, C, cout, err, total_us, flops / max(total_us, 1e-3) * 1e-6))
 
     if any(want(x) for x in ("4a", "4b", "4c", "4d")):
         say("4. probe_conv_tma_fast (candidate) against the production kernel [%s]" % ",".join(x for x in sections if x.startswith("4")))

@@ -18,6 +18,7 @@ class Bar:
     def passed(s, parity): return (s.done & 1) != parity
 def run(S, num_kb, tiles, CH=8, seed=0, producer_waits_empty=True):
     rnd=random.Random(seed)
+    kbs = list(num_kb) if isinstance(num_kb, (list, tuple)) else [num_kb]      # per item, cycled: phases differ in tap count
     full=[Bar(1) for _ in range(S)]; small=[Bar(1) for _ in range(S)]; empty=[Bar(1) for _ in range(S)]
     accfull=[Bar(1),Bar(1)]; accempty=[Bar(1),Bar(1)]
     stage_owner=[None]*S      # (tile,kb) currently loaded in smem stage
@@ -27,7 +28,7 @@ def run(S, num_kb, tiles, CH=8, seed=0, producer_waits_empty=True):
     def producer():
         s=0;ph=0;git=0
         for t in range(tiles):
-            for kb in range(num_kb):
+            for kb in range(kbs[t % len(kbs)]):
                 if git>=S and producer_waits_empty:
                     while not empty[s].passed(ph^1): yield
                 assert stage_owner[s] is None or stage_owner[s][2]=='consumed', ('overwrite smem', t,kb,s,stage_owner[s])
@@ -38,7 +39,7 @@ def run(S, num_kb, tiles, CH=8, seed=0, producer_waits_empty=True):
     def builder():
         s=0;ph=0;git=0
         for t in range(tiles):
-            for kb in range(num_kb):
+            for kb in range(kbs[t % len(kbs)]):
                 while not full[s].passed(ph): yield
                 if git>=S:
                     while not empty[s].passed(ph^1): yield
@@ -51,6 +52,7 @@ def run(S, num_kb, tiles, CH=8, seed=0, producer_waits_empty=True):
     def mma():
         s=0;ph=0;b=0;inchunk=0;c=0
         for t in range(tiles):
+            num_kb = kbs[t % len(kbs)]
             for kb in range(num_kb):
                 chunk_first = inchunk==0; chunk_last = inchunk==CH-1 or kb==num_kb-1
                 if chunk_first and c>=2:
@@ -74,6 +76,7 @@ def run(S, num_kb, tiles, CH=8, seed=0, producer_waits_empty=True):
     def epilogue():
         b=0;c=0
         for t in range(tiles):
+            num_kb = kbs[t % len(kbs)]
             nchunks=(num_kb+CH-1)//CH; total=0
             for ch in range(nchunks):
                 while not accfull[b].passed((c>>1)&1): yield
@@ -98,6 +101,9 @@ def run(S, num_kb, tiles, CH=8, seed=0, producer_waits_empty=True):
 def main():
     for S, num_kb, tiles, seed in itertools.product((2, 3, 4, 6), (1, 7, 8, 9, 17, 18, 72), (1, 2, 5), (0, 1, 2)):
         run(S, num_kb, tiles, seed=seed)
+    for S, seed in itertools.product((2, 3, 6), (0, 1)):
+        run(S, (12, 6, 6, 3), 9, seed=seed)                     # the four parity phases of a stride-2 input gradient, 96 channels
+        run(S, (64,), 4, seed=seed)
     print("protocol ok")
 
 

@@ -410,7 +410,7 @@ def test_round2_probe_library_builds_and_exports():
     g.build()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     lib = ctypes.CDLL(os.path.join(root, "confignet_b200", "lib", "libcn_probes.so"))
-    for name in ("probe_tf32_operands", "probe_tma_tile", "probe_conv_tma", "probe_conv_tma_fast", "probe_conv_tma_taps"):
+    for name in ("probe_tf32_operands", "probe_tma_tile", "probe_conv_tma", "probe_conv_tma_fast", "probe_conv_tma_phases"):
         assert hasattr(lib, name), name
     main = ctypes.CDLL(os.path.join(root, "confignet_b200", "lib", "libconfignet_b200.so"))
     assert not hasattr(main, "probe_conv_tma")
@@ -503,12 +503,14 @@ def test_probe_script_host_logic_against_emulated_kernels():
                               lambda a, b: a.astype(np.float64) @ b.astype(np.float64).T, lambda v, n0: v.astype(np.float32))
 
         @staticmethod
-        def probe_conv_tma_taps(x, N, C, geom, wp, bias, y, cout, stride, ntaps, dx, dy, dz, ostride, alpha, iters, avg_us):
-            D, H, W, gd, gh, gw, od, oh, ow, oz, oy, ox = list(geom)
-            dz = dz if dz is not None else [0] * ntaps
-            bn, cblocks = min(cout, 128), -(-C // 32)
+        def probe_conv_tma_phases(x, N, C, geom, wp, bias, y, cout, stride, nphase, ntaps, dx, dy, dz, oz, oy, ox, ostride, alpha, iters, avg_us):
+            D, H, W, gd, gh, gw, od, oh, ow = list(geom)
+            ntaps = list(ntaps)
+            tap0 = [sum(ntaps[:p]) for p in range(nphase)]
+            bn, cblocks, n_nt = min(cout, 128), -(-C // 32), cout // min(cout, 128)
             bw = min(gw, 128); bh = min(gh, 128 // bw); bd = 128 // (bw * bh)
-            w = arr(wp, cout // bn, ntaps * cblocks, 2, bn * 32)
+            stage = 2 * bn * 32                                   # floats per k-block stage (big + small plane)
+            w = arr(wp, sum(ntaps) * cblocks * n_nt * stage)
             bz = arr(bias, cout) if bias is not None else np.zeros(cout, np.float32)
             xa, ya = arr(x, N, D, H, W, C), arr(y, N, od, oh, ow, cout)
 
@@ -520,23 +522,27 @@ def test_probe_script_host_logic_against_emulated_kernels():
                         k = max(0, min(32, C - c))
                         t[row, :k] = xa[n, pz, py, px, c:c + k]
                 return t
-            for n in range(N):
-                for tz in range(gd // bd):
-                    for ty in range(gh // bh):
-                        for tx in range(gw // bw):
-                            for nt in range(cout // bn):
-                                acc = np.zeros((128, bn), np.float64)
-                                for kb in range(ntaps * cblocks):
-                                    tap, cb = kb // cblocks, kb % cblocks
-                                    a = tma5(cb * 32, tx * bw * stride + dx[tap], ty * bh * stride + dy[tap], tz * bd * stride + dz[tap], n)
-                                    big, small = unswz(w[nt, kb, 0], bn).astype(np.float64), unswz(w[nt, kb, 1], bn).astype(np.float64)
-                                    a_big = pr.trunc13(a)
-                                    a_small = pr.trunc13(a - a_big)
-                                    acc += a_small.astype(np.float64) @ big.T + a_big.astype(np.float64) @ small.T + a_big.astype(np.float64) @ big.T
-                                for r in range(128):
-                                    v = acc[r] + bz[nt * bn:(nt + 1) * bn]
-                                    ya[n, (tz * bd + r // (bw * bh)) * ostride + oz, (ty * bh + (r // bw) % bh) * ostride + oy,
-                                       (tx * bw + r % bw) * ostride + ox, nt * bn:(nt + 1) * bn] = np.where(v > 0, v, alpha * v).astype(np.float32)
+            n_items = N * (gd // bd) * (gh // bh) * (gw // bw) * nphase * n_nt
+            for item in range(n_items):                           # the kernel's item decomposition, verbatim
+                nt, ph, t = item % n_nt, (item // n_nt) % nphase, item // (n_nt * nphase)
+                tiles_x, tiles_y, tiles_z = gw // bw, gh // bh, gd // bd
+                n, tz, ty, tx = t // (tiles_x * tiles_y * tiles_z), (t // (tiles_x * tiles_y)) % tiles_z, (t // tiles_x) % tiles_y, t % tiles_x
+                num_kb = ntaps[ph] * cblocks
+                base = (tap0[ph] * cblocks * n_nt + nt * num_kb) * stage
+                acc = np.zeros((128, bn), np.float64)
+                for kb in range(num_kb):
+                    tap, cb = tap0[ph] + kb // cblocks, kb % cblocks
+                    a = tma5(cb * 32, tx * bw * stride + dx[tap], ty * bh * stride + dy[tap], tz * bd * stride + (dz[tap] if dz is not None else 0), n)
+                    st = w[base + kb * stage: base + (kb + 1) * stage]
+                    big, small = unswz(st[:bn * 32], bn).astype(np.float64), unswz(st[bn * 32:], bn).astype(np.float64)
+                    a_big = pr.trunc13(a)
+                    a_small = pr.trunc13(a - a_big)
+                    acc += a_small.astype(np.float64) @ big.T + a_big.astype(np.float64) @ small.T + a_big.astype(np.float64) @ big.T
+                o = [(v[ph] if v is not None else 0) for v in (oz, oy, ox)]
+                for r in range(128):
+                    v = acc[r] + bz[nt * bn:(nt + 1) * bn]
+                    ya[n, (tz * bd + r // (bw * bh)) * ostride + o[0], (ty * bh + (r // bw) % bh) * ostride + o[1],
+                       (tx * bw + r % bw) * ostride + o[2], nt * bn:(nt + 1) * bn] = np.where(v > 0, v, alpha * v).astype(np.float32)
             avg_us._obj.value = 1.0
             return 0
 
@@ -544,8 +550,9 @@ def test_probe_script_host_logic_against_emulated_kernels():
         def probe_conv_tma_fast(x, wp, bias, y, N, H, W, C, cout, stride, alpha, iters, avg_us):
             Ho, Wo = -(-H // stride), -(-W // stride)
             pad = max((Ho - 1) * stride + 3 - H, 0) // 2
-            return Fake.probe_conv_tma_taps(x, N, C, [1, H, W, 1, Ho, Wo, 1, Ho, Wo, 0, 0, 0], wp, bias, y, cout, stride, 9,
-                                            [t % 3 - pad for t in range(9)], [t // 3 - pad for t in range(9)], None, 1, alpha, iters, avg_us)
+            return Fake.probe_conv_tma_phases(x, N, C, [1, H, W, 1, Ho, Wo, 1, Ho, Wo], wp, bias, y, cout, stride, 1, [9],
+                                              [t % 3 - pad for t in range(9)], [t // 3 - pad for t in range(9)], None, None, None, None, 1,
+                                              alpha, iters, avg_us)
 
     lines = pr.main(lib=Fake, dev=torch.device("cpu"), quick=True)
     text = "\n".join(lines)
