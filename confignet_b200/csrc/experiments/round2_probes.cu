@@ -28,6 +28,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+// makes the initialised barriers visible to the async proxy (TMA completions, tcgen05.commit arrivals)
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(128) tf32_operand_kernel(const float* __restri
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int k = 0; k < 32; ++k) *reinterpret_cast<float*>(s->a + swz_off(tid, k)) = A[tid * 32 + k];
   if (tid < PN) for (int k = 0; k < 32; ++k) *reinterpret_cast<float*>(s->b + swz_off(tid, k)) = B[tid * 32 + k];
-  if (tid == 0) mbar_init(smem_u32(&s->bar_mma), 1);
+  if (tid == 0) { mbar_init(smem_u32(&s->bar_mma), 1); mbar_init_fence(); }
   fence_proxy_async();                                   // generic-proxy writes -> visible to the tensor core's async proxy
   const uint32_t tmem = tmem_alloc32(smem_u32(&s->tmem), &s->tmem, warp);
   if (tid == 0) {
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(128) tma_tile_kernel(const __grid_constant__ C
   ProbeSmem* s = reinterpret_cast<ProbeSmem*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x;
   for (int i = tid; i < A_BYTES / 4; i += 128) reinterpret_cast<float*>(s->a)[i] = -12345.0f;     // so untouched bytes show
-  if (tid == 0) mbar_init(smem_u32(&s->bar_full), 1);
+  if (tid == 0) { mbar_init(smem_u32(&s->bar_full), 1); mbar_init_fence(); }
   fence_proxy_async();
   __syncthreads();
   if (tid == 0) {
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(128) conv_tma_kernel(const __grid_constant__ C
   const int tiles_x = Wo / bw, tiles_y = Ho / bh;
   const int tile = blockIdx.x, n = tile / (tiles_x * tiles_y), ty = (tile / tiles_x) % tiles_y, tx = tile % tiles_x;
   const int x0 = tx * bw, y0 = ty * bh;
-  if (tid == 0) { mbar_init(smem_u32(&s->bar_full), 1); mbar_init(smem_u32(&s->bar_mma), 1); }
+  if (tid == 0) { mbar_init(smem_u32(&s->bar_full), 1); mbar_init(smem_u32(&s->bar_mma), 1); mbar_init_fence(); }
   fence_proxy_async();
   const uint32_t tmem = tmem_alloc32(smem_u32(&s->tmem), &s->tmem, warp);
   const int cblocks = (C + 31) / 32, num_kb = 9 * cblocks;   // a partial last block: the TMA zero-fills the missing channels
@@ -301,6 +303,7 @@ __global__ void __launch_bounds__(F_THREADS) conv_tma_fast_kernel(const __grid_c
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_small + 8 * s, 128); mbar_init(bar_empty + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_accfull + 8 * b, 1); mbar_init(bar_accempty + 8 * b, 128); }
+    mbar_init_fence();
   }
   fence_proxy_async();
   if (warp == 1) {
