@@ -58,6 +58,8 @@ SIGNATURES = {
     "cn_register_params": [_V, ctypes.c_size_t],
     "cn_unregister_params": [_V],
     "cn_weights_changed": [],
+    "cn_params_changed": [_V],
+    "cn_set_params_frozen": [_V, _I],
     "cn_graphs_captured": [],
     "cn_norm_coef": [_I, _V, _I, _V, _V, _I, _I, _I, _f, _V, _V, _V, _V, _V],
     "cn_lrelu_fwd": [_V, _f, _V, _L, _V],

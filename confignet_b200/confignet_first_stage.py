@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import netspec, networks, ops
-from .runtime import ParamGroup, Network, KerasAdam, GraphedFn, allreduce_grads, shard_rows, world
+from .runtime import ParamGroup, Network, KerasAdam, StepGraphs, shard_rows, world
 
 DEFAULT_CONFIG = {
     "model_type": None,
@@ -168,7 +168,7 @@ class GeneratorNet(Network):
         return super().__call__(None, inputs["rotation"], zs=zs)
 
 
-class ConfigNetFirstStage:
+class ConfigNetFirstStage(StepGraphs):
     def __init__(self, config, initialize=True, device=None, seed=1234):
         self.config = merge_configs(DEFAULT_CONFIG, config)
         self.config["model_type"] = "ConfigNetFirstStage"
@@ -245,8 +245,7 @@ class ConfigNetFirstStage:
         # seeded He-normal weights stand in; load real ones with perceptual_loss.set_weights().
         self.perceptual_loss = Network(self._make_group(netspec.vgg19_spec(), s + 7, vgg_like=True),
                                        networks.vgg19_activations)
-        for v in self.perceptual_loss.group.params.values():
-            v.requires_grad_(False)
+        self.perceptual_loss.group.set_frozen(self.drop_graphs)
 
     # ---------------------------------------------------------------- weights / io
     def get_weights(self, return_tensors=False):
@@ -446,33 +445,6 @@ class ConfigNetFirstStage:
         return facemodel_params, dataset.metadata_inputs["rotations"][idxs].astype(np.float32)
 
     # ---------------------------------------------------------------- training steps
-    def _apply(self, optimizer, loss, nets, device_lr=False):
-        """device_lr: the host half of the optimizer step (KerasAdam.begin_step) already ran; this is the device half."""
-        groups = [n.group for n in nets]
-        params = [p for g in groups for p in g.trainable_weights]
-        grads = torch.autograd.grad(loss, params, allow_unused=True)
-        keep, i = [], 0
-        for g in groups:
-            k = len(g.trainable_weights)
-            keep.append(g.pack_grads(grads[i:i + k]))
-            i += k
-        gscale = allreduce_grads(groups)
-        if device_lr:
-            optimizer.apply_flat_device_lr(groups, gscale)
-        else:
-            optimizer.apply_flat(groups, gscale)
-
-    def _graphed(self, name, optimizer, fn):
-        """One CUDA-graph wrapper per step, bound to the optimizer whose moment buffers the captured region holds."""
-        if not self.config.get("cuda_graphs", True):
-            return fn
-        entry = self._graphs.get(name)
-        if entry is None or entry[0] is not optimizer:
-            # a new optimizer object (a second train() call): its moment buffers and learning-rate scalar are not the
-            # ones the old graph captured - drop that graph (and its memory pool) and start over
-            entry = self._graphs[name] = (optimizer, GraphedFn(fn))
-        return entry[1]
-
     def _real_from_u8(self, imgs_u8, flips):
         """device half of _upload_images: optional per-image left-right flip, uint8 -> float32 [-1, 1]"""
         if flips is not None:
@@ -508,9 +480,10 @@ class ConfigNetFirstStage:
                 fake_imgs = self.generator((latent_d, rot_d))
             losses = networks.compute_discriminator_loss(self.discriminator.params, real_imgs, fake_imgs,
                                                          self.config["n_discr_layers"])
-            self._apply(optimizer, losses["loss_sum"], [self.discriminator], device_lr=True)
+            self._backward(losses["loss_sum"], [self.discriminator])
             return self._detached(losses)
-        return self._graphed("d", optimizer, device_half)(real_u8, flips_d, latent_d, rot_d)
+        fn = self._graphed("d", optimizer, device_half, [self.discriminator])
+        return self._global_losses(fn(real_u8, flips_d, latent_d, rot_d))
 
     def synth_discriminator_training_step(self, synth_training_set, optimizer):
         """confignet_first_stage.py:478-488 (batch assembly :452-464)."""
@@ -532,23 +505,31 @@ class ConfigNetFirstStage:
                 fake_imgs = self.generator((self.synthetic_encoder(list(fm_d)), rot_d))
             losses = networks.compute_discriminator_loss(self.synth_discriminator.params, real_imgs, fake_imgs,
                                                          self.config["n_discr_layers"])
-            self._apply(optimizer, losses["loss_sum"], [self.synth_discriminator], device_lr=True)
+            self._backward(losses["loss_sum"], [self.synth_discriminator])
             return self._detached(losses)
-        return self._graphed("synth_d", optimizer, device_half)(real_u8, flips_d, rot_d, *fm_d)
+        fn = self._graphed("synth_d", optimizer, device_half, [self.synth_discriminator])
+        return self._global_losses(fn(real_u8, flips_d, rot_d, *fm_d))
 
     def latent_discriminator_training_step(self, synth_training_set, optimizer):
+        """confignet_first_stage.py:490-504."""
         B = self.get_batch_size()
         real_latents = self.sample_latent_vector(B).astype(np.float32)
         facemodel_params, _ = self._sample_synth_metadata(synth_training_set, B)
         sliced = self._rank_rows(real_latents, *facemodel_params)
         real_latents, facemodel_params = sliced[0], sliced[1:]
-        with torch.no_grad():
-            fake_latents = self.synthetic_encoder([self._to_device(a, torch.float32) for a in facemodel_params])
-        losses = networks.compute_latent_discriminator_loss(
-            self.latent_discriminator.params, self._to_device(real_latents, torch.float32), fake_latents,
-            self.config["n_latent_discr_layers"])
-        self._apply(optimizer, losses["loss_sum"], [self.latent_discriminator])
-        return self._detached(losses)
+        real_d = self._to_device(real_latents, torch.float32)
+        fm_d = [self._to_device(a, torch.float32) for a in facemodel_params]
+        optimizer.begin_step(self.device)
+
+        def device_half(real_d, *fm_d):
+            with torch.no_grad():
+                fake_latents = self.synthetic_encoder(list(fm_d))
+            losses = networks.compute_latent_discriminator_loss(self.latent_discriminator.params, real_d, fake_latents,
+                                                                self.config["n_latent_discr_layers"])
+            self._backward(losses["loss_sum"], [self.latent_discriminator])
+            return self._detached(losses)
+        fn = self._graphed("latent_d", optimizer, device_half, [self.latent_discriminator])
+        return self._global_losses(fn(real_d, *fm_d))
 
     def generator_training_step(self, real_training_set, synth_training_set, optimizer):
         """confignet_first_stage.py:506-560."""
@@ -570,10 +551,11 @@ class ConfigNetFirstStage:
         real_rot_d = self._to_device(np.asarray(real_rot, np.float32), torch.float32)
         fm_d = [self._to_device(a, torch.float32) for a in facemodel_params]
         optimizer.begin_step(self.device)
-        fn = self._graphed("g", optimizer, lambda *t: self._generator_step_device(optimizer, *t))
-        return fn(gt_u8, masks_f, real_latents_d, synth_rot_d, real_rot_d, *fm_d)
+        fn = self._graphed("g", optimizer, self._generator_step_device,
+                           [self.generator, self.latent_regressor, self.synthetic_encoder])
+        return self._global_losses(fn(gt_u8, masks_f, real_latents_d, synth_rot_d, real_rot_d, *fm_d))
 
-    def _generator_step_device(self, optimizer, gt_u8, eye_masks, real_latents_d, synth_rot, real_rot, *fm_d):
+    def _generator_step_device(self, gt_u8, eye_masks, real_latents_d, synth_rot, real_rot, *fm_d):
         """device half of generator_training_step (confignet_first_stage.py:514-557)"""
         c = self.config
         gt_imgs = self._real_from_u8(gt_u8, None)
@@ -595,8 +577,7 @@ class ConfigNetFirstStage:
         losses["latent_regression_loss"] = c["latent_regression_weight"] * networks.latent_regression_loss(
             self.latent_regressor.params, stacked_imgs, labels, c["n_discr_layers"])
         losses["loss_sum"] = networks._sum(losses.values())
-        self._apply(optimizer, losses["loss_sum"], [self.generator, self.latent_regressor, self.synthetic_encoder],
-                    device_lr=True)
+        self._backward(losses["loss_sum"], [self.generator, self.latent_regressor, self.synthetic_encoder])
         return self._detached(losses)
 
     def setup_training(self, log_dir, synth_training_set, n_samples_for_metrics, real_training_set=None):

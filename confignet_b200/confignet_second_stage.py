@@ -71,8 +71,7 @@ class ConfigNet(ConfigNetFirstStage):
         # VGG16 with the VGGFace weights (perceptual_loss.py:26-41): not downloadable offline, seeded stand-in
         self.perceptual_loss_face_reco = Network(self._make_group(netspec.vgg16_spec(), s + 9, vgg_like=True),
                                                  networks.vggface_activations)
-        for v in self.perceptual_loss_face_reco.group.params.values():
-            v.requires_grad_(False)
+        self.perceptual_loss_face_reco.group.set_frozen(self.drop_graphs)
 
     def face_reco_loss(self, gt_imgs, gen_imgs):
         """confignet_second_stage.py:88-91: the VGGFace perceptual loss with (generated, ground truth) in the reference's
@@ -118,6 +117,33 @@ class ConfigNet(ConfigNetFirstStage):
         return real_imgs, fake_imgs
 
     # ---------------------------------------------------------------- training steps
+    # Same split as in stage 1: a host half (NumPy draws in the reference's order, pinned uploads, Keras-Adam's
+    # iteration count) and a device half on device tensors only, replayed as a CUDA graph after two eager calls.
+    def discriminator_training_step(self, training_set, optimizer):
+        """confignet_first_stage.py:466-476 over ConfigNet.get_discriminator_batch (confignet_second_stage.py:119-130):
+        the fakes are reconstructions generator(encoder(training images)) - not prior samples as in stage 1 - and the
+        NumPy stream sees (image rows, flips, input image rows)."""
+        B = self.get_batch_size()
+        idxs, flips = self._draw_image_rows(training_set, B)
+        input_img_idxs = np.random.randint(0, training_set.imgs.shape[0], B)
+        idxs, flips, input_img_idxs = self._rank_rows(idxs, flips, input_img_idxs)
+        real_u8 = self._to_device(self._take_rows(training_set.imgs, idxs), torch.uint8)
+        flips_d = self._to_device(np.asarray(flips).astype(np.bool_), torch.bool)
+        input_u8 = self._to_device(self._take_rows(training_set.imgs, input_img_idxs), torch.uint8)
+        optimizer.begin_step(self.device)
+
+        def device_half(real_u8, flips_d, input_u8):
+            real_imgs = self._real_from_u8(real_u8, flips_d)
+            with torch.no_grad():
+                latent_vector, rotation = self.encoder(self._real_from_u8(input_u8, None))
+                fake_imgs = self.generator((latent_vector, rotation))
+            losses = networks.compute_discriminator_loss(self.discriminator.params, real_imgs, fake_imgs,
+                                                         self.config["n_discr_layers"])
+            self._backward(losses["loss_sum"], [self.discriminator])
+            return self._detached(losses)
+        fn = self._graphed("d2", optimizer, device_half, [self.discriminator])
+        return self._global_losses(fn(real_u8, flips_d, input_u8))
+
     def latent_discriminator_training_step(self, real_training_set, synth_training_set, optimizer):
         """confignet_second_stage.py:132-147: real latents come from the encoder."""
         B = self.get_batch_size()
@@ -125,14 +151,21 @@ class ConfigNet(ConfigNetFirstStage):
         facemodel_params, _ = self._sample_synth_metadata(synth_training_set, B)
         sliced = self._rank_rows(idxs, flips, *facemodel_params)
         idxs, flips, facemodel_params = sliced[0], sliced[1], sliced[2:]
-        real_imgs = self._upload_images(self._take_rows(real_training_set.imgs, idxs), flips)
-        with torch.no_grad():
-            real_latents, _ = self.encoder(real_imgs)
-            fake_latents = self.synthetic_encoder([self._to_device(a, torch.float32) for a in facemodel_params])
-        losses = networks.compute_latent_discriminator_loss(self.latent_discriminator.params, real_latents, fake_latents,
-                                                            self.config["n_latent_discr_layers"])
-        self._apply(optimizer, losses["loss_sum"], [self.latent_discriminator])
-        return self._detached(losses)
+        real_u8 = self._to_device(self._take_rows(real_training_set.imgs, idxs), torch.uint8)
+        flips_d = self._to_device(np.asarray(flips).astype(np.bool_), torch.bool)
+        fm_d = [self._to_device(a, torch.float32) for a in facemodel_params]
+        optimizer.begin_step(self.device)
+
+        def device_half(real_u8, flips_d, *fm_d):
+            with torch.no_grad():
+                real_latents, _ = self.encoder(self._real_from_u8(real_u8, flips_d))
+                fake_latents = self.synthetic_encoder(list(fm_d))
+            losses = networks.compute_latent_discriminator_loss(self.latent_discriminator.params, real_latents, fake_latents,
+                                                                self.config["n_latent_discr_layers"])
+            self._backward(losses["loss_sum"], [self.latent_discriminator])
+            return self._detached(losses)
+        fn = self._graphed("latent_d2", optimizer, device_half, [self.latent_discriminator])
+        return self._global_losses(fn(real_u8, flips_d, *fm_d))
 
     def compute_normalized_latent_regression_loss(self, generator_outputs, labels):
         """confignet_second_stage.py:93-107.  The statistics are over the GLOBAL batch: with data parallelism the
@@ -153,12 +186,25 @@ class ConfigNet(ConfigNetFirstStage):
         sliced = self._rank_rows(idxs, synth_rot, *facemodel_params)
         idxs, synth_rot, facemodel_params = sliced[0], sliced[1], sliced[2:]
         ridxs, rflips = self._rank_rows(ridxs, rflips)
-        synth_imgs = self._upload_images(self._take_rows(synth_training_set.imgs, idxs))
-        eye_masks = self._to_device(self._take_rows(synth_training_set.eye_masks, idxs), torch.float32)
-        real_imgs = self._upload_images(self._take_rows(real_training_set.imgs, ridxs), rflips)
+        synth_u8 = self._to_device(self._take_rows(synth_training_set.imgs, idxs), torch.uint8)
+        masks_f = self._to_device(self._take_rows(synth_training_set.eye_masks, idxs), torch.float32)
+        real_u8 = self._to_device(self._take_rows(real_training_set.imgs, ridxs), torch.uint8)
+        rflips_d = self._to_device(np.asarray(rflips).astype(np.bool_), torch.bool)
+        synth_rot_d = self._to_device(np.asarray(synth_rot, np.float32), torch.float32)
+        fm_d = [self._to_device(a, torch.float32) for a in facemodel_params]
+        optimizer.begin_step(self.device)
+        # the batch-statistics loss all-gathers under data parallelism: a collective inside the step, so no capture there
+        fn = self._graphed("g2", optimizer, self._generator_step_device,
+                           [self.generator, self.latent_regressor, self.synthetic_encoder, self.encoder], dp_ok=False)
+        return self._global_losses(fn(synth_u8, masks_f, real_u8, rflips_d, synth_rot_d, *fm_d))
 
+    def _generator_step_device(self, synth_u8, eye_masks, real_u8, rflips_d, synth_rot, *fm_d):
+        """device half of the stage-2 generator_training_step (confignet_second_stage.py:166-216)"""
+        c = self.config
+        synth_imgs = self._real_from_u8(synth_u8, None)
+        real_imgs = self._real_from_u8(real_u8, rflips_d)
         losses = OrderedDict()
-        synth_latents = self.synthetic_encoder([self._to_device(a, torch.float32) for a in facemodel_params])
+        synth_latents = self.synthetic_encoder(list(fm_d))
         out_synth = self.generator((synth_latents, synth_rot))
         real_latents, real_rot = self.encoder(real_imgs)
         out_real = self.generator((real_latents, real_rot))
@@ -177,12 +223,11 @@ class ConfigNet(ConfigNetFirstStage):
         if c["latent_regression_weight"] > 0.0:
             stacked_latents = torch.cat((synth_latents, real_latents), dim=0)
             stacked_imgs = torch.cat((out_synth, out_real), dim=0)
-            stacked_rot = torch.cat((self._to_device(synth_rot, torch.float32), real_rot), dim=0)
+            stacked_rot = torch.cat((synth_rot, real_rot), dim=0)
             labels = torch.cat((stacked_latents, c["latent_regressor_rot_weight"] * stacked_rot), dim=-1)
             losses["latent_regression_loss"] = self.compute_normalized_latent_regression_loss(stacked_imgs, labels)
         losses["loss_sum"] = networks._sum(losses.values())
-        self._apply(optimizer, losses["loss_sum"],
-                    [self.generator, self.latent_regressor, self.synthetic_encoder, self.encoder])
+        self._backward(losses["loss_sum"], [self.generator, self.latent_regressor, self.synthetic_encoder, self.encoder])
         return self._detached(losses)
 
     def setup_training(self, log_dir, synth_training_set, n_samples_for_metrics, attribute_classifier=None,
@@ -295,14 +340,17 @@ class ConfigNet(ConfigNetFirstStage):
         if img_output_dir is not None and rank == 0:
             os.makedirs(img_output_dir, exist_ok=True)
         self.fine_tune_losses = []
-
+        # the tiled pre/post parts the reference returns are the ones built INSIDE the last tape, i.e. their values
+        # before the last optimizer update, next to the updated expression part (confignet_second_stage.py:361-364,402):
+        # found by executing the reference's fine_tune_on_img (tests/golden/reference_steps.npz) and kept
         pre_tiled, post_tiled = pre.detach().clone(), post.detach().clone()
-        for step_number in range(n_iters):
+        out_first = torch.empty((1,) + tuple(imgs.shape[1:]), device=self.device, dtype=torch.float32)
+
+        def iteration(imgs):
+            """one fine-tuning iteration on device tensors only (confignet_second_stage.py:359-392, without the update)"""
             losses = OrderedDict()
-            # the reference returns the tiled pre/post parts it built INSIDE the last tape, i.e. their values before the
-            # last optimizer update, next to the updated expression part (confignet_second_stage.py:361-364,402):
-            # found by executing the reference's fine_tune_on_img (tests/golden/reference_steps.npz) and kept
-            pre_tiled, post_tiled = pre.detach().clone(), post.detach().clone()
+            with torch.no_grad():
+                pre_tiled.copy_(pre); post_tiled.copy_(post)
             embeddings = torch.cat((pre.expand(n_imgs, -1), expr, post.expand(n_imgs, -1)), dim=1)
             out = gen((embeddings, rotations))
             losses["image_loss_real"] = 0.5 * c["image_loss_weight"] * networks.perceptual_loss(self.perceptual_loss.params, imgs, out)
@@ -314,20 +362,21 @@ class ConfigNet(ConfigNetFirstStage):
             labels = torch.cat((embeddings, c["latent_regressor_rot_weight"] * rotations), dim=-1)
             losses["latent_regression_loss"] = self.compute_normalized_latent_regression_loss(out, labels)
             losses["loss_sum"] = networks._sum(losses.values())
+            self._backward(losses["loss_sum"], [gen.group, shared, local])
+            with torch.no_grad():
+                out_first.copy_(out[:1])
+            return self._detached(losses)
 
-            groups = [gen.group, shared, local]
-            params = [p for g in groups for p in g.trainable_weights]
-            grads = torch.autograd.grad(losses["loss_sum"], params, allow_unused=True)
-            keep, i = [], 0
-            for g in groups:
-                k = len(g.trainable_weights)
-                keep.append(g.pack_grads(grads[i:i + k]))
-                i += k
-            gscale = allreduce_grads([gen.group, shared])
-            optimizer.apply_flat(groups, gscale)
-            self.fine_tune_losses.append(self._detached(losses))
+        # per call: new variables and a new optimizer, hence a new graph (captured at the third iteration)
+        self._graphs.pop("fine_tune", None)
+        step = self._graphed("fine_tune", optimizer, iteration, [gen.group, shared, local], dp_ok=False,
+                             reduce_groups=[gen.group, shared])
+        for step_number in range(n_iters):
+            optimizer.begin_step(self.device)
+            self.fine_tune_losses.append(step(imgs))
             if img_output_dir is not None and rank == 0:
-                np.save(os.path.join(img_output_dir, "output_%02d.npy" % step_number), ops.to_uint8(out.detach()[:1]).cpu().numpy()[0])
+                np.save(os.path.join(img_output_dir, "output_%02d.npy" % step_number), ops.to_uint8(out_first).cpu().numpy()[0])
+        self._graphs.pop("fine_tune", None)
 
         with torch.no_grad():
             embeddings = torch.cat((pre_tiled.expand(n_imgs, -1), expr, post_tiled.expand(n_imgs, -1)), dim=1)

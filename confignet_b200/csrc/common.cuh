@@ -7,7 +7,8 @@
 #include "../../include/confignet_b200.h"
 
 void cn_set_error(const char* fmt, ...);
-extern unsigned long long g_cn_weight_epoch;  // see error.cu
+extern unsigned long long g_cn_weight_epoch;  // see error.cu: global part of every parameter buffer's epoch (cn_weights_changed)
+void cn_mark_params_changed(const void* p);   // conv.cu: the registered buffer containing p was written
 extern unsigned long long g_cn_launches;     // kernels launched by this library (bench.py reports it)
 
 #define CN_CHECK_CUDA(expr)                                                            \
@@ -36,6 +37,12 @@ extern unsigned long long g_cn_launches;     // kernels launched by this library
       return (code);                                                                   \
     }                                                                                  \
   } while (0)
+
+// Internal helpers shared by the translation units (defined in conv.cu).
+//   cn_scratch      grow-only device scratch slot identified by `key` (any stable address); launches on one stream serialise
+//   cn_sum_slabs    out[i] = sum_b part[b][i] over `nslabs` slabs of n floats, in slab order (deterministic, no atomics)
+int cn_scratch(const void* key, size_t bytes, float** out);
+int cn_sum_slabs(const float* part, int nslabs, int n, float* out, cudaStream_t st);
 
 // Geometry of one implicit GEMM (see conv.cu).  Passed to kernels by value.
 struct GemmPlan {

@@ -493,7 +493,9 @@ template <int MODE, int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 igemm_ffma_kernel(GemmPlan p, const float* __restrict__ A, const float* __restrict__ B,
                   const float* __restrict__ bias, float* __restrict__ D, int act, float alpha,
-                  int kchunk, int use_atomic) {
+                  int kchunk, long long part_stride) {
+  // part_stride != 0: split-K - split blockIdx.z writes its raw partial sums into slab blockIdx.z of D (a workspace of
+  // gridDim.z slabs of part_stride floats); splitk_reduce_kernel adds the slabs in split order, then bias + activation.
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int BK = 16;
   static_assert(NT % BM == 0 || BM % NT == 0, "row mapping");
@@ -589,9 +591,8 @@ igemm_ffma_kernel(GemmPlan p, const float* __restrict__ A, const float* __restri
       int n = n0 + tx * TN + j;
       if (n >= Ng) continue;
       float v = acc[i][j];
-      if (use_atomic) {
-        if (bias != nullptr && blockIdx.z == 0) v += bias[n];
-        atomicAdd(D + rowoff + n, v);
+      if (part_stride) {
+        D[(size_t)blockIdx.z * (size_t)part_stride + rowoff + n] = v;
       } else {
         if (bias != nullptr) v += bias[n];
         D[rowoff + n] = cn_apply_act(v, act, alpha);
@@ -978,7 +979,7 @@ template <int B_MN, int WG, int PROF>
 __global__ void __launch_bounds__(TCP_THREADS)
 igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const float* __restrict__ Wp,
                       const float* __restrict__ bias, float* __restrict__ D, int act, float alpha,
-                      int bn, int bn_smem, int nb, int tmem_cols, int kb_per_split, int use_atomic,
+                      int bn, int bn_smem, int nb, int tmem_cols, int kb_per_split, long long part_stride,
                       int csize, int ny, int dbg, long long* prof) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1195,10 +1196,8 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
             float4 o;
             o.x = __uint_as_float(v[q]); o.y = __uint_as_float(v[q + 1]);
             o.z = __uint_as_float(v[q + 2]); o.w = __uint_as_float(v[q + 3]);
-            if (use_atomic) {
-              if (bias != nullptr && blockIdx.z == 0) { o.x += bias[n]; o.y += bias[n + 1]; o.z += bias[n + 2]; o.w += bias[n + 3]; }
-              atomicAdd(D + rowoff + n, o.x); atomicAdd(D + rowoff + n + 1, o.y);
-              atomicAdd(D + rowoff + n + 2, o.z); atomicAdd(D + rowoff + n + 3, o.w);
+            if (part_stride) {       // split-K: raw partial sums into this split's slab (splitk_reduce_kernel finishes)
+              *reinterpret_cast<float4*>(D + (size_t)blockIdx.z * (size_t)part_stride + rowoff + n) = o;
               continue;
             }
             if (bias != nullptr) { o.x += bias[n]; o.y += bias[n + 1]; o.z += bias[n + 2]; o.w += bias[n + 3]; }
@@ -1405,9 +1404,10 @@ wgrad_skinny_kernel(GemmPlan p, const float* __restrict__ A, const float* __rest
       acc[j] = a;
     }
   }
+  float* slab = D + (size_t)blockIdx.x * O;          // per-block partial; sum_slabs_kernel adds the blocks in order
 #pragma unroll
   for (int j = 0; j < SKW_MAXOUT; ++j)
-    if (ok[j] >= 0) atomicAdd(D + tid + 256 * j, acc[j]);
+    if (ok[j] >= 0) slab[tid + 256 * j] = acc[j];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1493,19 +1493,24 @@ skinny_cfew_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* _
       cursor_next(p, cur);
     }
   }
-  // block reduction over the 8 warps, then one atomic per output and block
+  // block reduction over the 8 warps in warp order (deterministic), then the block's partial goes to slab blockIdx.x
   __shared__ float red[16 * 32 * 4];
   for (int i = tid; i < 16 * 32 * 4; i += 256) red[i] = 0.f;
   __syncthreads();
+  for (int w = 0; w < 8; ++w) {
+    if ((tid >> 5) == w) {
 #pragma unroll
-  for (int t = 0; t < 16; ++t)
+      for (int t = 0; t < 16; ++t)
 #pragma unroll
-    for (int n = 0; n < 4; ++n)
-      if (t < p.ntaps && n < p.Cn) atomicAdd(&red[(t * 32 + lane) * 4 + n], acc[t][n]);
-  __syncthreads();
+        for (int n = 0; n < 4; ++n)
+          if (t < p.ntaps && n < p.Cn) red[(t * 32 + lane) * 4 + n] += acc[t][n];
+    }
+    __syncthreads();
+  }
+  float* slab = D + (size_t)blockIdx.x * ((size_t)p.Ktot * p.Cn);
   for (int i = tid; i < p.ntaps * 32 * 4; i += 256) {
     const int t = i >> 7, l = (i >> 2) & 31, n = i & 3, cc = blockIdx.y * 32 + l;
-    if (n < p.Cn && cc < p.Csrc) atomicAdd(D + ((size_t)t * p.Csrc + cc) * p.Cn + n, red[i]);
+    if (n < p.Cn && cc < p.Csrc) slab[((size_t)t * p.Csrc + cc) * p.Cn + n] = red[i];
   }
 }
 
@@ -1552,17 +1557,22 @@ skinny_kfew_wgrad_kernel(GemmPlan p, const float* __restrict__ A, const float* _
   __shared__ float red[32 * 64];
   for (int i = tid; i < 32 * 64; i += 256) red[i] = 0.f;
   __syncthreads();
+  for (int w = 0; w < 8; ++w) {                      // warp order: deterministic
+    if ((tid >> 5) == w) {
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    if (k < K) {
-      if (n0ok) atomicAdd(&red[k * 64 + lane], a0[k]);
-      if (n1ok) atomicAdd(&red[k * 64 + 32 + lane], a1[k]);
+      for (int k = 0; k < 32; ++k) {
+        if (k < K) {
+          if (n0ok) red[k * 64 + lane] += a0[k];
+          if (n1ok) red[k * 64 + 32 + lane] += a1[k];
+        }
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
+  float* slab = D + (size_t)blockIdx.x * ((size_t)K * p.Cn);
   for (int i = tid; i < K * 64; i += 256) {
     const int k = i >> 6, n = i & 63;
-    if (n < p.Cn) atomicAdd(D + (size_t)k * p.Cn + n, red[i]);
+    if (n < p.Cn) slab[(size_t)k * p.Cn + n] = red[i];
   }
 }
 
@@ -1585,20 +1595,21 @@ wgrad_flat_kernel(const float* __restrict__ X, const float* __restrict__ G, int 
 #pragma unroll
       for (int n = 0; n < 4; ++n) acc[c][n] = fmaf(x[c], g[n], acc[c][n]);
   }
-  __shared__ float red[16];
-  if (threadIdx.x < 16) red[threadIdx.x] = 0.f;
-  __syncthreads();
+  __shared__ float red[8][16];
 #pragma unroll
   for (int c = 0; c < 4; ++c)
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
       const float v = warp_sum(acc[c][n]);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&red[c * 4 + n], v);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][c * 4 + n] = v;
     }
   __syncthreads();
   if (threadIdx.x < 16) {
     const int c = threadIdx.x >> 2, n = threadIdx.x & 3;
-    if (c < cin && n < cout) atomicAdd(D + c * cout + n, red[threadIdx.x]);
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    if (c < cin && n < cout) D[(size_t)blockIdx.x * (cin * cout) + c * cout + n] = t;     // slab of this block
   }
 }
 
@@ -1610,7 +1621,7 @@ template <int MT>
 __global__ void __launch_bounds__(256)
 dense_small_kernel(const float* __restrict__ X, int M, int K, const float* __restrict__ W, int wsc, int wsn,
                    const float* __restrict__ bias, float* __restrict__ Y, int N, int act, float alpha,
-                   int kchunk, int use_atomic) {
+                   int kchunk, long long part_stride) {
   __shared__ __align__(16) float xs[MT][132];
   __shared__ float outs[MT][32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1654,9 +1665,8 @@ dense_small_kernel(const float* __restrict__ X, int M, int K, const float* __res
     const int m = i >> 5, nn = blockIdx.x * 32 + (i & 31);
     if (m >= M || nn >= N) continue;
     float v = outs[m][i & 31];
-    if (use_atomic) {
-      if (bias != nullptr && blockIdx.y == 0) v += bias[nn];
-      atomicAdd(Y + (size_t)m * N + nn, v);
+    if (part_stride) {             // split-K slab of this block row (splitk_reduce_kernel adds bias)
+      Y[(size_t)blockIdx.y * (size_t)part_stride + (size_t)m * N + nn] = v;
     } else {
       if (bias != nullptr) v += bias[nn];
       Y[(size_t)m * N + nn] = cn_apply_act(v, act, alpha);
@@ -1666,23 +1676,26 @@ dense_small_kernel(const float* __restrict__ X, int M, int K, const float* __res
 
 // column sums for narrow matrices (n < 32): flat coalesced walk, every thread stays on one column
 __global__ void __launch_bounds__(256)
-colsum_narrow_kernel(const float* __restrict__ g, size_t total, int n, int threads_used, float* __restrict__ out) {
-  __shared__ float s_acc[32];
-  if (threadIdx.x < 32) s_acc[threadIdx.x] = 0.f;
-  __syncthreads();
+colsum_narrow_kernel(const float* __restrict__ g, size_t total, int n, int threads_used, float* __restrict__ part) {
+  // part[blockIdx.x][n]: the block's column sums, its threads folded in thread order (deterministic)
+  __shared__ float s_acc[256];
   const int gt = blockIdx.x * 256 + threadIdx.x;
-  if (gt < threads_used) {
-    float acc = 0.f;
+  float acc = 0.f;
+  if (gt < threads_used)
     for (size_t i = gt; i < total; i += threads_used) acc += g[i];
-    atomicAdd(&s_acc[gt % n], acc);
-  }
+  s_acc[threadIdx.x] = acc;
   __syncthreads();
-  if (threadIdx.x < n) atomicAdd(out + threadIdx.x, s_acc[threadIdx.x]);
+  if (threadIdx.x < n) {
+    const int first = (int)(((unsigned)threadIdx.x + (unsigned)n - (unsigned)((blockIdx.x * 256) % n)) % (unsigned)n);   // first thread on this column
+    float t = 0.f;
+    for (int j = first; j < 256; j += n) t += s_acc[j];
+    part[(size_t)blockIdx.x * n + threadIdx.x] = t;
+  }
 }
 
 // column sums of a (rows, n) matrix: bias gradient
 __global__ void colsum_kernel(const float* __restrict__ g, int rows, int n, float* __restrict__ out) {
-  // grid.x covers columns in groups of 32, grid.y splits rows; blockDim = (32, 8)
+  // grid.x covers columns in groups of 32, grid.y splits rows; blockDim = (32, 8); out = [gridDim.y][n] partial sums
   __shared__ float sm[8][33];
   int col = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
@@ -1693,7 +1706,56 @@ __global__ void colsum_kernel(const float* __restrict__ g, int rows, int n, floa
   if (threadIdx.y == 0 && col < n) {
     float s = 0.f;
     for (int i = 0; i < 8; ++i) s += sm[i][threadIdx.x];
-    atomicAdd(out + col, s);
+    out[(size_t)blockIdx.y * n + col] = s;          // slab of this row split
+  }
+}
+
+// out[i] = act(bias[i % cn] + sum_z ws[z][i]) in split order: the deterministic second half of every split-K launch.
+// n4 = elements / 4 (the slabs are 16-byte aligned and cn % 4 == 0 on this path).
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int nsplit, size_t n4, int cn4, const float* __restrict__ bias,
+                     float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = reinterpret_cast<const float4*>(ws)[i];
+  for (int z = 1; z < nsplit; ++z) {
+    const float4 v = reinterpret_cast<const float4*>(ws)[(size_t)z * n4 + i];
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  if (bias != nullptr) {
+    const float4 b = reinterpret_cast<const float4*>(bias)[i % (size_t)cn4];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  reinterpret_cast<float4*>(out)[i] = a;
+}
+// scalar form for outputs whose size or channel count is not a multiple of 4
+__global__ void __launch_bounds__(256)
+splitk_reduce1_kernel(const float* __restrict__ ws, int nsplit, size_t n, int cn, const float* __restrict__ bias,
+                      float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float a = ws[i];
+  for (int z = 1; z < nsplit; ++z) a += ws[(size_t)z * n + i];
+  if (bias != nullptr) a += bias[i % (size_t)cn];
+  out[i] = a;
+}
+// out[i] = sum_b part[b][i] for MANY slabs of FEW outputs (per-block partials of the small weight / bias gradients):
+// block (32, 8) - thread (x, y) adds the slabs y, y+8, ... of output 32*blockIdx.x + x in order, then the 8 rows are
+// folded in order.  Deterministic; a single thread walking hundreds of slabs would be a chain of dependent L2 round trips.
+__global__ void __launch_bounds__(256)
+sum_slabs_kernel(const float* __restrict__ part, int nslabs, int n, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  float a = 0.f;
+  if (i < n)
+    for (int b = threadIdx.y; b < nslabs; b += 8) a += part[(size_t)b * n + i];
+  red[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    out[i] = t;
   }
 }
 
@@ -1765,11 +1827,19 @@ static float* g_gpack = nullptr;       // packed-gradient workspace of the wgrad
 static size_t g_gpack_bytes = 0;
 
 // Registered parameter buffers (ParamGroup flat buffers): their packed stage images are cached per (plan, weight
-// pointer) and reused until the parameter epoch changes - VGG19's frozen weights are packed once, a discriminator
-// kernel once per optimizer step instead of once per conv call.
-struct ParamRange { const char* lo; const char* hi; };
+// pointer) and reused until THAT buffer's epoch changes - VGG19's frozen weights are packed once per run, a
+// discriminator kernel once per optimizer step instead of once per conv call.
+//
+// CUDA graphs.  A capture records launches without running them, and a replay runs the optimizer kernels without the
+// host code that advances the epochs.  Two rules keep a captured step self-contained:
+//   * inside a capture an image counts as current only if it was packed INSIDE THIS capture (cudaStreamGetCaptureInfo's
+//     id), so every graph re-packs the trainable kernels it uses at their first use - except images of buffers the
+//     caller declared frozen (cn_set_params_frozen), which only change through cn_params_changed();
+//   * outside a capture an image recorded inside one is never trusted; the caller marks the buffers a replayed graph
+//     updated with cn_params_changed() after the replay (runtime.GraphedFn does).
+struct ParamRange { const char* lo; const char* hi; unsigned long long epoch; bool frozen; };
 static std::vector<ParamRange> g_param_ranges;
-struct PackedEntry { float* buf; size_t bytes; unsigned long long epoch; };
+struct PackedEntry { float* buf; size_t bytes; unsigned long long epoch; unsigned long long capture_id; };
 static std::map<std::pair<const void*, const void*>, PackedEntry> g_wcache;
 
 // Once a CUDA graph has been captured over these launches (cn_graphs_captured), buffers the graph may reference
@@ -1777,56 +1847,98 @@ static std::map<std::pair<const void*, const void*>, PackedEntry> g_wcache;
 static bool g_no_free = false;
 extern "C" int cn_graphs_captured(void) { g_no_free = true; return CN_OK; }
 static void cn_free(void* p) { if (!g_no_free && p) cudaFree(p); }
-static void drop_wcache_locked() {
-  if (g_wcache.empty()) return;
-  cudaDeviceSynchronize();
-  for (auto& kv : g_wcache) cn_free(kv.second.buf);
-  g_wcache.clear();
+static ParamRange* find_range_locked(const void* w) {
+  for (auto& r : g_param_ranges) if ((const char*)w >= r.lo && (const char*)w < r.hi) return &r;
+  return nullptr;
+}
+// drops the cached images of the kernels inside [lo, hi) only (the other networks keep theirs)
+static void drop_wcache_range_locked(const char* lo, const char* hi) {
+  bool synced = false;
+  for (auto it = g_wcache.begin(); it != g_wcache.end();) {
+    const char* w = (const char*)it->first.second;
+    if (w >= lo && w < hi) {
+      if (!g_no_free) { if (!synced) { cudaDeviceSynchronize(); synced = true; } cn_free(it->second.buf); }
+      it = g_wcache.erase(it);
+    } else ++it;
+  }
 }
 extern "C" int cn_register_params(const void* p, size_t bytes) {
   CN_REQUIRE(p != nullptr && bytes > 0, CN_ERR_BAD_SHAPE, "cn_register_params: bad range");
   std::lock_guard<std::mutex> lock(g_plan_mutex);
-  for (auto& r : g_param_ranges) if (r.lo == (const char*)p) { r.hi = r.lo + bytes; ++g_cn_weight_epoch; drop_wcache_locked(); return CN_OK; }
-  g_param_ranges.push_back({(const char*)p, (const char*)p + bytes});
-  ++g_cn_weight_epoch;           // a new buffer may reuse the address of a dead one
-  drop_wcache_locked();
+  drop_wcache_range_locked((const char*)p, (const char*)p + bytes);      // a new buffer may reuse the address of a dead one
+  for (auto& r : g_param_ranges) if (r.lo == (const char*)p) { r.hi = r.lo + bytes; ++r.epoch; r.frozen = false; return CN_OK; }
+  g_param_ranges.push_back({(const char*)p, (const char*)p + bytes, g_cn_weight_epoch, false});
   return CN_OK;
 }
 extern "C" int cn_unregister_params(const void* p) {
   std::lock_guard<std::mutex> lock(g_plan_mutex);
   for (size_t i = 0; i < g_param_ranges.size(); ++i)
-    if (g_param_ranges[i].lo == (const char*)p) { g_param_ranges.erase(g_param_ranges.begin() + i); break; }
-  ++g_cn_weight_epoch;
-  drop_wcache_locked();
+    if (g_param_ranges[i].lo == (const char*)p) {
+      drop_wcache_range_locked(g_param_ranges[i].lo, g_param_ranges[i].hi);
+      g_param_ranges.erase(g_param_ranges.begin() + i);
+      break;
+    }
+  return CN_OK;
+}
+// `p` = any address inside a registered buffer (the optimizer / EMA entry points pass the buffer they write)
+void cn_mark_params_changed(const void* p) {
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  ParamRange* r = find_range_locked(p);
+  if (r) ++r->epoch;
+}
+extern "C" int cn_params_changed(const void* p) { cn_mark_params_changed(p); return CN_OK; }
+extern "C" int cn_set_params_frozen(const void* p, int frozen) {
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  ParamRange* r = find_range_locked(p);
+  CN_REQUIRE(r != nullptr, CN_ERR_BAD_SHAPE, "cn_set_params_frozen: not a registered buffer");
+  r->frozen = frozen != 0;
   return CN_OK;
 }
 static bool is_registered_param(const void* w) {
-  for (auto& r : g_param_ranges) if ((const char*)w >= r.lo && (const char*)w < r.hi) return true;
-  return false;
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  return find_range_locked(w) != nullptr;
 }
 static bool g_wcache_on = true;
 extern "C" int cn_debug_set_wcache(int on) { g_wcache_on = on != 0; return CN_OK; }
+static unsigned long long capture_id_of(cudaStream_t st) {
+  cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+  unsigned long long id = 0;
+  if (cudaStreamGetCaptureInfo(st, &status, &id) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return status == cudaStreamCaptureStatusActive ? (id ? id : ~0ull) : 0;
+}
+// is the cached image `e` of a kernel in range `r` current for a launch on a stream whose capture id is `cap`?
+static bool entry_current(const PackedEntry& e, const ParamRange& r, unsigned long long cap) {
+  if (e.epoch != r.epoch + g_cn_weight_epoch) return false;
+  if (r.frozen) return true;
+  return e.capture_id == cap;       // eager: packed eagerly; capturing: packed inside this very capture
+}
 // -> *hit: the cached image is current (skip the pack).  Otherwise the caller packs into *out on the launch stream.
-static int cached_packed(const void* plan_key, const void* w, size_t bytes, float** out, bool* hit) {
+static int cached_packed(const void* plan_key, const void* w, size_t bytes, cudaStream_t st, float** out, bool* hit) {
+  const unsigned long long cap = capture_id_of(st);
   std::lock_guard<std::mutex> lock(g_plan_mutex);
+  ParamRange* r = find_range_locked(w);
+  CN_REQUIRE(r != nullptr, CN_ERR_BAD_SHAPE, "cached_packed: unregistered weight pointer");
   auto key = std::make_pair(plan_key, w);
   auto it = g_wcache.find(key);
   if (it == g_wcache.end() || it->second.bytes < bytes) {
-    if (it != g_wcache.end()) { CN_CHECK_CUDA(cudaDeviceSynchronize()); cn_free(it->second.buf); g_wcache.erase(it); }
-    PackedEntry e; e.bytes = bytes; e.epoch = 0; e.buf = nullptr;
+    if (it != g_wcache.end()) { if (!g_no_free) { CN_CHECK_CUDA(cudaDeviceSynchronize()); cn_free(it->second.buf); } g_wcache.erase(it); }
+    PackedEntry e; e.bytes = bytes; e.epoch = 0; e.capture_id = 0; e.buf = nullptr;
     CN_CHECK_CUDA(cudaMalloc(&e.buf, bytes));
     it = g_wcache.insert(std::make_pair(key, e)).first;
   }
-  *hit = it->second.epoch == g_cn_weight_epoch;
-  it->second.epoch = g_cn_weight_epoch;
+  *hit = entry_current(it->second, *r, cap);
+  if (!*hit) { it->second.epoch = r->epoch + g_cn_weight_epoch; it->second.capture_id = cap; }
   *out = it->second.buf;
   return CN_OK;
 }
-static bool packed_is_current(const void* plan_key, const void* w) {
-  if (!g_wcache_on || !is_registered_param(w)) return false;
+static bool packed_is_current(const void* plan_key, const void* w, cudaStream_t st) {
+  if (!g_wcache_on) return false;
+  const unsigned long long cap = capture_id_of(st);
   std::lock_guard<std::mutex> lock(g_plan_mutex);
+  ParamRange* r = find_range_locked(w);
+  if (r == nullptr) return false;
   auto it = g_wcache.find(std::make_pair(plan_key, w));
-  return it != g_wcache.end() && it->second.epoch == g_cn_weight_epoch;
+  return it != g_wcache.end() && entry_current(it->second, *r, cap);
 }
 
 static int packed_buffer(const void* key, size_t bytes, float** out) {
@@ -1850,6 +1962,31 @@ static int packed_buffer(const void* key, size_t bytes, float** out) {
   } else {
     *out = it->second.first;
   }
+  return CN_OK;
+}
+
+// Scratch slots of the deterministic reductions (grow-only like the pack buffers; launches on one stream serialise):
+// split-K slabs of the GEMM kernels, per-block partials of the small weight-gradient kernels, bias-gradient partials.
+static char k_ws_splitk, k_ws_small, k_ws_bias;
+
+int cn_scratch(const void* key, size_t bytes, float** out) {
+  CN_REQUIRE(key != nullptr, CN_ERR_BAD_SHAPE, "cn_scratch: null key");
+  return packed_buffer(key, bytes, out);
+}
+int cn_sum_slabs(const float* part, int nslabs, int n, float* out, cudaStream_t st) {
+  sum_slabs_kernel<<<(n + 31) / 32, dim3(32, 8), 0, st>>>(part, nslabs, n, out);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
+static int launch_splitk_reduce(const float* ws, int nsplit, size_t n, int cn, const float* bias, float* out, cudaStream_t st) {
+  if ((n & 3) == 0 && (cn & 3) == 0 && ((uintptr_t)out & 15) == 0 && (bias == nullptr || ((uintptr_t)bias & 15) == 0)) {
+    const size_t n4 = n >> 2;
+    splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(ws, nsplit, n4, cn >> 2, bias, out);
+  } else {
+    splitk_reduce1_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, nsplit, n, cn, bias, out);
+  }
+  CN_CHECK_LAUNCH();
   return CN_OK;
 }
 
@@ -1880,7 +2017,7 @@ static void tc_smem_config(int bn_smem, int* nb, int* smem) {
 
 template <int B_MN, int WG>
 static int launch_tc(const GemmPlan& g, const float* src, const float* packed, const float* bias, float* dst, int act,
-                     float alpha, int bn, int bn_smem, dim3 grid, int per, int split, cudaStream_t st) {
+                     float alpha, int bn, int bn_smem, dim3 grid, int per, int split, cudaStream_t st, size_t part_stride = 0) {
   int nb, smem;
   tc_smem_config(bn_smem, &nb, &smem);
   // thread-block cluster along M: the CTAs of a cluster share the B stream by multicast
@@ -1911,13 +2048,12 @@ static int launch_tc(const GemmPlan& g, const float* src, const float* packed, c
   auto kern = g_prof ? igemm_tc_pixel_kernel<B_MN, WG, 1> : igemm_tc_pixel_kernel<B_MN, WG, 0>;
   if (set_smem(kern, smem)) return CN_ERR_CUDA;
   CN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, g, src, packed, bias, dst, act, alpha, bn, bn_smem,
-                                   nb, 512, per, (int)(split > 1), csize, ny, (g_dbg & 0xff) | (g_chunk_kb << 8), g_prof));
+                                   nb, 512, per, (long long)(split > 1 ? part_stride : 0), csize, ny, (g_dbg & 0xff) | (g_chunk_kb << 8), g_prof));
   CN_CHECK_LAUNCH();
   return CN_OK;
 }
 
-// zero_mode: 0 = this launch covers all of dst and may zero it for a split-K run, 1 = dst was zeroed by the
-// caller (phased dgrad), 2 = no split-K allowed
+// zero_mode: 0 = this launch covers all of dst and may run split-K (slabs + ordered reduction), 2 = no split-K allowed
 static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const float* w, const float* bias,
                         float* dst, int act, float alpha, int impl, cudaStream_t st, int zero_mode = 0,
                         const float* w_ident = nullptr) {
@@ -1933,12 +2069,14 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
     dim3 grid((g.M + TC_BM - 1) / TC_BM, ((g.Cn + bn - 1) / bn) * nph, 1);
     const int total_kb = (g.Ktot + TC_BK - 1) / TC_BK;      // phased plans: Ktot is the longest phase (= kb_stride)
     int per = total_kb, split = 1;
-    if (nph == 1 && act == CN_ACT_NONE && zero_mode != 2 && (int)(grid.x * grid.y) < 4 * num_sms() && total_kb >= 32) {
-      split = pick_split((int)(grid.x * grid.y), total_kb, total_kb / 16);     // split 0 adds the bias
+    const size_t out_elems = (size_t)g.n_img * g.Q[0] * g.Q[1] * g.Q[2] * g.Cn;
+    float* ws = nullptr;
+    if (nph == 1 && act == CN_ACT_NONE && zero_mode == 0 && g.ostride == 1 && (int)(grid.x * grid.y) < 4 * num_sms() && total_kb >= 32) {
+      // split-K without atomics: every split writes its own slab, splitk_reduce_kernel adds them in order (+ bias)
+      split = pick_split((int)(grid.x * grid.y), total_kb, total_kb / 16);
       per = (total_kb + split - 1) / split;
       split = (total_kb + per - 1) / per;
-      if (split > 1 && zero_mode == 0)
-        CN_CHECK_CUDA(cudaMemsetAsync(dst, 0, (size_t)g.n_img * g.Q[0] * g.Q[1] * g.Q[2] * g.Cn * sizeof(float), st));
+      if (split > 1) { int rcw = packed_buffer(&k_ws_splitk, (size_t)split * out_elems * sizeof(float), &ws); if (rcw) return rcw; }
     }
     // pre-pack the weights into per-(n-tile, k-block) stage images (buffer cached per plan)
     float* wp = nullptr;
@@ -1946,7 +2084,7 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
     const size_t pbytes = (size_t)grid.y * total_kb * 2 * bn_smem * TC_BK * 4;
     const float* ident = w_ident ? w_ident : w;       // folded plans: identity = the original Keras kernel
     int rc;
-    if (g_wcache_on && is_registered_param(ident)) rc = cached_packed((const void*)g.taps, ident, pbytes, &wp, &hit);
+    if (g_wcache_on && is_registered_param(ident)) rc = cached_packed((const void*)g.taps, ident, pbytes, st, &wp, &hit);
     else rc = packed_buffer((const void*)g.taps, pbytes, &wp);
     if (rc) return rc;
     if (!hit) {
@@ -1955,8 +2093,12 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
       else pack_weights_kernel<0><<<pgrid, 256, 0, st>>>(g, w, wp, bn, bn_smem, total_kb);
       CN_CHECK_LAUNCH();
     }
-    if (b_mn) return launch_tc<1, 0>(g, src, wp, bias, dst, act, alpha, bn, bn_smem, grid, per, split, st);
-    return launch_tc<0, 0>(g, src, wp, bias, dst, act, alpha, bn, bn_smem, grid, per, split, st);
+    float* tdst = split > 1 ? ws : dst;
+    if (b_mn) rc = launch_tc<1, 0>(g, src, wp, bias, tdst, act, alpha, bn, bn_smem, grid, per, split, st, out_elems);
+    else rc = launch_tc<0, 0>(g, src, wp, bias, tdst, act, alpha, bn, bn_smem, grid, per, split, st, out_elems);
+    if (rc) return rc;
+    if (split > 1) return launch_splitk_reduce(ws, split, out_elems, g.Cn, bias, dst, st);
+    return CN_OK;
   }
   // CUDA-core path
   const bool flat = g.ntaps == 1 && g.E[0] * g.E[1] * g.E[2] == 1 && g.S[0] * g.S[1] * g.S[2] == 1 && g.Q[0] * g.Q[1] * g.Q[2] == 1;
@@ -1964,7 +2106,7 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
     // Dense layer on a few rows
     int nt = (g.Cn + 31) / 32;
     int split = 1;
-    if (act == CN_ACT_NONE && zero_mode != 2 && g.Ktot >= 1024) {
+    if (act == CN_ACT_NONE && zero_mode == 0 && g.Ktot >= 1024) {
       split = (num_sms() + nt - 1) / nt;
       int maxsplit = g.Ktot / 256;
       if (split > maxsplit) split = maxsplit;
@@ -1972,11 +2114,16 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
     }
     int kchunk = ((g.Ktot + split - 1) / split + 127) / 128 * 128;
     split = (g.Ktot + kchunk - 1) / kchunk;
-    if (split > 1 && zero_mode == 0) CN_CHECK_CUDA(cudaMemsetAsync(dst, 0, (size_t)g.M * g.Cn * sizeof(float), st));
+    const size_t out_elems = (size_t)g.M * g.Cn;
+    float* ws = nullptr;
+    if (split > 1) { int rcw = packed_buffer(&k_ws_splitk, (size_t)split * out_elems * sizeof(float), &ws); if (rcw) return rcw; }
+    float* tdst = split > 1 ? ws : dst;
+    const long long ps = split > 1 ? (long long)out_elems : 0;
     dim3 grid(nt, split);
-    if (g.M <= 16) dense_small_kernel<16><<<grid, 256, 0, st>>>(src, g.M, g.Ktot, w, g.wsc, g.wsn, bias, dst, g.Cn, act, alpha, kchunk, split > 1);
-    else if (g.M <= 32) dense_small_kernel<32><<<grid, 256, 0, st>>>(src, g.M, g.Ktot, w, g.wsc, g.wsn, bias, dst, g.Cn, act, alpha, kchunk, split > 1);
-    else dense_small_kernel<64><<<grid, 256, 0, st>>>(src, g.M, g.Ktot, w, g.wsc, g.wsn, bias, dst, g.Cn, act, alpha, kchunk, split > 1);
+    if (g.M <= 16) dense_small_kernel<16><<<grid, 256, 0, st>>>(src, g.M, g.Ktot, w, g.wsc, g.wsn, bias, tdst, g.Cn, act, alpha, kchunk, ps);
+    else if (g.M <= 32) dense_small_kernel<32><<<grid, 256, 0, st>>>(src, g.M, g.Ktot, w, g.wsc, g.wsn, bias, tdst, g.Cn, act, alpha, kchunk, ps);
+    else dense_small_kernel<64><<<grid, 256, 0, st>>>(src, g.M, g.Ktot, w, g.wsc, g.wsn, bias, tdst, g.Cn, act, alpha, kchunk, ps);
+    if (split > 1) { CN_CHECK_LAUNCH(); return launch_splitk_reduce(ws, split, out_elems, g.Cn, bias, dst, st); }
   } else if (g.Cn <= 4 && g.M >= 4096 && g.Ktot * 16 <= 96 * 1024) {
     dim3 grid((g.M + 255) / 256, 1, 1);
     int smem = g.Ktot * 16;
@@ -1984,20 +2131,24 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
     pixel_smalln_kernel<<<grid, 256, smem, st>>>(g, src, w, bias, dst, act, alpha);
   } else if (g.Cn <= 4 && g.M >= 4096) {
     dim3 grid((g.M + 255) / 256, 1, 1);
-    igemm_ffma_kernel<MODE_PIXEL, 256, 4, 1, 4><<<grid, 256, 0, st>>>(g, src, w, bias, dst, act, alpha, g.Ktot > 0 ? g.Ktot : 1, 0);
+    igemm_ffma_kernel<MODE_PIXEL, 256, 4, 1, 4><<<grid, 256, 0, st>>>(g, src, w, bias, dst, act, alpha, g.Ktot > 0 ? g.Ktot : 1, 0ll);
   } else {
     int mt = (g.M + 63) / 64, nt = (g.Cn + 63) / 64;
     int split = 1;
-    if (act == CN_ACT_NONE && zero_mode != 2 && mt * nt < num_sms() && g.Ktot >= 2048) {
+    if (act == CN_ACT_NONE && zero_mode == 0 && g.ostride == 1 && mt * nt < num_sms() && g.Ktot >= 2048) {
       split = (2 * num_sms() + mt * nt - 1) / (mt * nt);
       int maxsplit = g.Ktot / 256; if (maxsplit < 1) maxsplit = 1;
       if (split > maxsplit) split = maxsplit;
     }
     int kchunk = g.Ktot > 0 ? ((g.Ktot + split - 1) / split + 15) / 16 * 16 : 16;
     split = g.Ktot > 0 ? (g.Ktot + kchunk - 1) / kchunk : 1;
-    if (split > 1 && zero_mode == 0) CN_CHECK_CUDA(cudaMemsetAsync(dst, 0, (size_t)g.n_img * g.Q[0] * g.Q[1] * g.Q[2] * g.Cn * sizeof(float), st));
+    const size_t out_elems = (size_t)g.n_img * g.Q[0] * g.Q[1] * g.Q[2] * g.Cn;
+    float* ws = nullptr;
+    if (split > 1) { int rcw = packed_buffer(&k_ws_splitk, (size_t)split * out_elems * sizeof(float), &ws); if (rcw) return rcw; }
     dim3 grid(mt, nt, split);
-    igemm_ffma_kernel<MODE_PIXEL, 64, 64, 4, 4><<<grid, 256, 0, st>>>(g, src, w, bias, dst, act, alpha, kchunk, split > 1);
+    igemm_ffma_kernel<MODE_PIXEL, 64, 64, 4, 4><<<grid, 256, 0, st>>>(g, src, w, bias, split > 1 ? ws : dst, act, alpha, kchunk,
+                                                                      split > 1 ? (long long)out_elems : 0ll);
+    if (split > 1) { CN_CHECK_LAUNCH(); return launch_splitk_reduce(ws, split, out_elems, g.Cn, bias, dst, st); }
   }
   CN_CHECK_LAUNCH();
   return CN_OK;
@@ -2040,7 +2191,7 @@ extern "C" int cn_conv_fwd(const cn_conv_desc* d, const float* x, const float* w
       cudaStream_t st = (cudaStream_t)stream;
       float* wf = nullptr;
       const int cc = d->cin * d->cout;
-      if (!packed_is_current((const void*)g.taps, w)) {
+      if (!packed_is_current((const void*)g.taps, w, st)) {
         rc = packed_buffer((const char*)g.taps + 1, (size_t)fi->nfold * cc * sizeof(float), &wf); if (rc) return rc;
         fold_weights_kernel<<<dim3((cc / 4 + 255) / 256, fi->nfold), 256, 0, st>>>(w, fi->d_spec, d->ksize[1], d->ksize[2], cc / 4, wf);
         CN_CHECK_LAUNCH();
@@ -2068,7 +2219,7 @@ extern "C" int cn_conv_dgrad(const cn_conv_desc* d, const float* gy, const float
     if (rc == CN_OK && tc_pixel_eligible(g, false)) {
       float* wf = nullptr;
       const int cc = d->cin * d->cout;
-      if (!packed_is_current((const void*)g.taps, w)) {
+      if (!packed_is_current((const void*)g.taps, w, st)) {
         rc = packed_buffer((const char*)g.taps + 1, (size_t)fi->nfold * cc * sizeof(float), &wf); if (rc) return rc;
         fold_weights_kernel<<<dim3((cc / 4 + 255) / 256, fi->nfold), 256, 0, st>>>(w, fi->d_spec, d->ksize[1], d->ksize[2], cc / 4, wf);
         CN_CHECK_LAUNCH();
@@ -2084,13 +2235,7 @@ extern "C" int cn_conv_dgrad(const cn_conv_desc* d, const float* gy, const float
       return launch_pixel(g, false, gy, w, nullptr, gx, CN_ACT_NONE, 0.f, CN_IMPL_TC, st, 2);   // one launch, all parity phases
   }
   const int nphase = (d->stride == 2) ? (1 << d->nd) : 1;
-  int zero_mode = 0;
-  if (nphase > 1) {
-    // the phases write disjoint pixels of one tensor: zero it once so that each phase may use split-K
-    size_t n = (size_t)d->batch * d->in_dims[0] * d->in_dims[1] * d->in_dims[2] * d->cin;
-    if (n <= ((size_t)1 << 24)) { CN_CHECK_CUDA(cudaMemsetAsync(gx, 0, n * sizeof(float), st)); zero_mode = 1; }
-    else zero_mode = 2;
-  }
+  const int zero_mode = nphase > 1 ? 2 : 0;       // parity phases write disjoint pixels of one tensor: no split-K slabs for them
   for (int ph = 0; ph < nphase; ++ph) {
     GemmPlan g;
     rc = get_plan(d, KIND_DGRAD, ph, &g); if (rc) return rc;
@@ -2119,14 +2264,19 @@ static int launch_wgrad_tc(const GemmPlan& g, const float* src, const float* G, 
   int split = pick_split(mtc * nt, total_kb, maxsplit);
   int per = (total_kb + split - 1) / split;
   split = (total_kb + per - 1) / per;
-  if (split > 1) CN_CHECK_CUDA(cudaMemsetAsync(out, 0, wn * sizeof(float), st));
+  float* ws = nullptr;          // split-K slabs, summed in split order by splitk_reduce_kernel (no atomics)
+  int rc;
+  if (split > 1) { rc = packed_buffer(&k_ws_splitk, (size_t)split * wn * sizeof(float), &ws); if (rc) return rc; }
   // the gradient pre-split into per-(n-tile, k-block) stage images: every (tap,c)-tile CTA streams it
   float* gp = nullptr;
-  int rc = packed_buffer(nullptr, (size_t)nt * total_kb * 2 * bn_smem * TC_BK * 4, &gp);
+  rc = packed_buffer(nullptr, (size_t)nt * total_kb * 2 * bn_smem * TC_BK * 4, &gp);
   if (rc) return rc;
   pack_grad_kernel<<<dim3(total_kb, nt), 256, 0, st>>>(G, g.M, g.Cn, gp, bn, bn_smem, total_kb);
   CN_CHECK_LAUNCH();
-  return launch_tc<1, 1>(g, src, gp, nullptr, out, CN_ACT_NONE, 0.f, bn, bn_smem, dim3(mt, nt, 1), per, split, st);
+  rc = launch_tc<1, 1>(g, src, gp, nullptr, split > 1 ? ws : out, CN_ACT_NONE, 0.f, bn, bn_smem, dim3(mt, nt, 1), per, split, st, wn);
+  if (rc) return rc;
+  if (split > 1) return launch_splitk_reduce(ws, split, wn, g.Cn, nullptr, out, st);
+  return CN_OK;
 }
 
 extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float* gy, float* gw,
@@ -2172,22 +2322,33 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
     rc = launch_wgrad_tc(g, x, gy, gw, st);
     if (rc) return rc;
   } else if (g.ntaps == 1 && g.Csrc <= 4 && g.Cn <= 4 && g.mstride == 1 && g.ushift == 0 && g.M >= 4096) {   // 1x1, stride 1: source pixel = output pixel
-    CN_CHECK_CUDA(cudaMemsetAsync(gw, 0, wn * sizeof(float), st));
-    wgrad_flat_kernel<<<4 * num_sms(), 256, 0, st>>>(x, gy, g.M, g.Csrc, g.Cn, gw);
+    // the small weight-gradient kernels write per-block partials (slabs); sum_slabs_kernel adds them in block order
+    const int blocks = 4 * num_sms();
+    float* ws = nullptr;
+    rc = packed_buffer(&k_ws_small, (size_t)blocks * wn * sizeof(float), &ws); if (rc) return rc;
+    wgrad_flat_kernel<<<blocks, 256, 0, st>>>(x, gy, g.M, g.Csrc, g.Cn, ws);
+    CN_CHECK_LAUNCH();
+    sum_slabs_kernel<<<(unsigned)((wn + 31) / 32), dim3(32, 8), 0, st>>>(ws, blocks, (int)wn, gw);
     CN_CHECK_LAUNCH();
   } else if (g.Cn <= 4 && g.Csrc >= 8 && g.ntaps <= 16 && g.M >= 4096) {
     int warps = 16 * num_sms();
     int per = (g.M + warps - 1) / warps; if (per < 64) per = 64;
     int blocks = ((g.M + per - 1) / per + 7) / 8;
-    CN_CHECK_CUDA(cudaMemsetAsync(gw, 0, wn * sizeof(float), st));
-    skinny_cfew_wgrad_kernel<<<dim3(blocks, (g.Csrc + 31) / 32), 256, 0, st>>>(g, x, gy, gw, per);
+    float* ws = nullptr;
+    rc = packed_buffer(&k_ws_small, (size_t)blocks * wn * sizeof(float), &ws); if (rc) return rc;
+    skinny_cfew_wgrad_kernel<<<dim3(blocks, (g.Csrc + 31) / 32), 256, 0, st>>>(g, x, gy, ws, per);
+    CN_CHECK_LAUNCH();
+    sum_slabs_kernel<<<(unsigned)((wn + 31) / 32), dim3(32, 8), 0, st>>>(ws, blocks, (int)wn, gw);
     CN_CHECK_LAUNCH();
   } else if (g.Ktot <= 32 && g.Cn <= 64 && g.M >= 4096) {
     int warps = 16 * num_sms();
     int per = (g.M + warps - 1) / warps;
     int blocks = ((g.M + per - 1) / per + 7) / 8;
-    CN_CHECK_CUDA(cudaMemsetAsync(gw, 0, wn * sizeof(float), st));
-    skinny_kfew_wgrad_kernel<<<blocks, 256, 0, st>>>(g, x, gy, gw, per);
+    float* ws = nullptr;
+    rc = packed_buffer(&k_ws_small, (size_t)blocks * wn * sizeof(float), &ws); if (rc) return rc;
+    skinny_kfew_wgrad_kernel<<<blocks, 256, 0, st>>>(g, x, gy, ws, per);
+    CN_CHECK_LAUNCH();
+    sum_slabs_kernel<<<(unsigned)((wn + 31) / 32), dim3(32, 8), 0, st>>>(ws, blocks, (int)wn, gw);
     CN_CHECK_LAUNCH();
   } else if ((long long)g.Ktot * g.Cn <= 256 * SKW_MAXOUT && g.M >= 4096) {
     int P = 8192 / (g.Ktot + g.Cn); if (P > 64) P = 64; if (P < 4) P = 4;
@@ -2195,9 +2356,12 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
     int blocks = 4 * num_sms();
     int per = ((g.M + blocks - 1) / blocks + P - 1) / P * P;
     blocks = (g.M + per - 1) / per;
-    CN_CHECK_CUDA(cudaMemsetAsync(gw, 0, wn * sizeof(float), st));
+    float* ws = nullptr;
+    rc = packed_buffer(&k_ws_small, (size_t)blocks * wn * sizeof(float), &ws); if (rc) return rc;
     if (smem > 48 * 1024 && set_smem(wgrad_skinny_kernel, smem)) return CN_ERR_CUDA;
-    wgrad_skinny_kernel<<<blocks, 256, smem, st>>>(g, x, gy, gw, P, per);
+    wgrad_skinny_kernel<<<blocks, 256, smem, st>>>(g, x, gy, ws, P, per);
+    CN_CHECK_LAUNCH();
+    sum_slabs_kernel<<<(unsigned)((wn + 31) / 32), dim3(32, 8), 0, st>>>(ws, blocks, (int)wn, gw);
     CN_CHECK_LAUNCH();
   } else {
     int mt = (g.Ktot + 63) / 64, nt = (g.Cn + 63) / 64;
@@ -2206,23 +2370,34 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
     if (split > maxsplit) split = maxsplit;
     int kchunk = ((g.M + split - 1) / split + 15) / 16 * 16;
     split = (g.M + kchunk - 1) / kchunk;
-    if (split > 1) CN_CHECK_CUDA(cudaMemsetAsync(gw, 0, wn * sizeof(float), st));
+    float* ws = nullptr;
+    if (split > 1) { rc = packed_buffer(&k_ws_splitk, (size_t)split * wn * sizeof(float), &ws); if (rc) return rc; }
     dim3 grid(mt, nt, split);
-    igemm_ffma_kernel<MODE_WGRAD, 64, 64, 4, 4><<<grid, 256, 0, st>>>(g, x, gy, nullptr, gw, CN_ACT_NONE, 0.f, kchunk, split > 1);
+    igemm_ffma_kernel<MODE_WGRAD, 64, 64, 4, 4><<<grid, 256, 0, st>>>(g, x, gy, nullptr, split > 1 ? ws : gw, CN_ACT_NONE, 0.f, kchunk,
+                                                                      split > 1 ? (long long)wn : 0ll);
     CN_CHECK_LAUNCH();
+    if (split > 1) { rc = launch_splitk_reduce(ws, split, wn, g.Cn, nullptr, gw, st); if (rc) return rc; }
   }
   if (gbias != nullptr) {
-    CN_CHECK_CUDA(cudaMemsetAsync(gbias, 0, (size_t)g.Cn * sizeof(float), st));
+    // bias gradient = column sums of gy: per-block partial rows, then sum_slabs_kernel (fixed order, no atomics)
+    float* ws = nullptr;
+    int nslabs;
     if (g.Cn < 32) {
       size_t total = (size_t)g.M * g.Cn;
       int blocks = (int)((total / 16 + 255) / 256); if (blocks > 4 * num_sms()) blocks = 4 * num_sms(); if (blocks < 1) blocks = 1;
       int used = blocks * 256 / g.Cn * g.Cn;
-      colsum_narrow_kernel<<<blocks, 256, 0, st>>>(gy, total, g.Cn, used, gbias);
+      rc = packed_buffer(&k_ws_bias, (size_t)blocks * g.Cn * sizeof(float), &ws); if (rc) return rc;
+      colsum_narrow_kernel<<<blocks, 256, 0, st>>>(gy, total, g.Cn, used, ws);
+      nslabs = blocks;
     } else {
       int ysplit = (g.M + 511) / 512; if (ysplit > 8 * num_sms()) ysplit = 8 * num_sms(); if (ysplit < 1) ysplit = 1;
       dim3 grid((g.Cn + 31) / 32, ysplit), block(32, 8);
-      colsum_kernel<<<grid, block, 0, st>>>(gy, g.M, g.Cn, gbias);
+      rc = packed_buffer(&k_ws_bias, (size_t)ysplit * g.Cn * sizeof(float), &ws); if (rc) return rc;
+      colsum_kernel<<<grid, block, 0, st>>>(gy, g.M, g.Cn, ws);
+      nslabs = ysplit;
     }
+    CN_CHECK_LAUNCH();
+    sum_slabs_kernel<<<(g.Cn + 31) / 32, dim3(32, 8), 0, st>>>(ws, nslabs, g.Cn, gbias);
     CN_CHECK_LAUNCH();
   }
   (void)conv_numel_x;

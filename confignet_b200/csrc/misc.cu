@@ -144,15 +144,35 @@ __global__ void rotate3d_fwd_kernel(const float* __restrict__ grid, const float*
     o[ch] = c0 * (1.f - d2) + c1 * d2;
   }
 }
+// Gradient wrt the volume: a scatter (every output voxel adds into its 8 clamped corners; clamping piles whole rays onto
+// the faces, so there is no bounded gather form).  Floating-point atomics would make the result depend on the order
+// in which the warps arrive; the contributions are therefore accumulated as 64-bit FIXED-POINT integers (integer
+// addition is associative: bit-reproducible) with a scale taken from max|gout|: 2^46 steps below the largest
+// gradient, far finer than the fp32 rounding of the contributions themselves.
+__global__ void absmax_bits_kernel(const float* __restrict__ x, size_t n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));      // non-negative floats order like their bit patterns
+}
+__device__ __forceinline__ int fx_exponent(unsigned amax_bits) {       // e with max|g| < 2^e
+  int e = 0;
+  frexpf(__uint_as_float(amax_bits), &e);
+  return e;
+}
 __global__ void rotate3d_bwd_grid_kernel(const float* __restrict__ gout, const float* __restrict__ rot, int s, int c,
-                                         float* __restrict__ ggrid, int nvox_total) {
+                                         unsigned long long* __restrict__ acc, int nvox_total, const unsigned* __restrict__ amax_bits) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= nvox_total) return;
+  const unsigned ab = *amax_bits;
+  if (ab == 0u || ab >= 0x7f800000u) return;             // all-zero (or non-finite) gradient: the accumulator stays zero
+  const float scale = ldexpf(1.f, 46 - fx_exponent(ab));
   const int s3 = s * s * s;
   const int b = warp / s3, v = warp % s3;
   const int z = v % s, y = (v / s) % s, x = v / (s * s);
   RotCorner rc = rot_corners(rot + b * 9, s, x, y, z);
-  float* g = ggrid + (size_t)b * s3 * c;
+  unsigned long long* g = acc + (size_t)b * s3 * c;
   const float* go = gout + (size_t)warp * c;
   float wt[8];
 #pragma unroll
@@ -161,8 +181,18 @@ __global__ void rotate3d_bwd_grid_kernel(const float* __restrict__ gout, const f
   for (int ch = lane; ch < c; ch += 32) {
     float gv = go[ch];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(g + (size_t)rc.idx[k] * c + ch, gv * wt[k]);
+    for (int k = 0; k < 8; ++k) {
+      const long long q = __float2ll_rn(gv * wt[k] * scale);
+      if (q != 0) atomicAdd(g + (size_t)rc.idx[k] * c + ch, (unsigned long long)q);
+    }
   }
+}
+__global__ void fx_to_float_kernel(const long long* __restrict__ acc, size_t n, const unsigned* __restrict__ amax_bits, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned ab = *amax_bits;
+  if (ab == 0u || ab >= 0x7f800000u) { out[i] = 0.f; return; }
+  out[i] = (float)((double)acc[i] * ldexp(1.0, fx_exponent(ab) - 46));
 }
 extern "C" int cn_rotate3d_fwd(const float* grid, const float* rot, int b, int s, int c, float* out, void* stream) {
   int nv = b * s * s * s;
@@ -170,8 +200,22 @@ extern "C" int cn_rotate3d_fwd(const float* grid, const float* rot, int b, int s
   CN_CHECK_LAUNCH(); return CN_OK;
 }
 extern "C" int cn_rotate3d_bwd_grid(const float* gout, const float* rot, int b, int s, int c, float* ggrid, void* stream) {
-  int nv = b * s * s * s;
-  rotate3d_bwd_grid_kernel<<<(nv * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gout, rot, s, c, ggrid, nv);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nv = b * s * s * s;
+  const size_t n = (size_t)nv * c;
+  if (n == 0) return CN_OK;
+  static char key;
+  float* ws = nullptr;
+  int rc = cn_scratch(&key, n * 8 + 16, &ws); if (rc) return rc;        // [amax bits (16 B)] [int64 accumulators]
+  unsigned* amax = reinterpret_cast<unsigned*>(ws);
+  unsigned long long* acc = reinterpret_cast<unsigned long long*>(ws + 4);
+  CN_CHECK_CUDA(cudaMemsetAsync(ws, 0, n * 8 + 16, st));
+  int blocks = (int)((n + 255) / 256); if (blocks > 8 * 148) blocks = 8 * 148;
+  absmax_bits_kernel<<<blocks, 256, 0, st>>>(gout, n, amax);
+  CN_CHECK_LAUNCH();
+  rotate3d_bwd_grid_kernel<<<(nv * 32 + 255) / 256, 256, 0, st>>>(gout, rot, s, c, acc, nv, amax);
+  CN_CHECK_LAUNCH();
+  fx_to_float_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const long long*>(acc), n, amax, ggrid);
   CN_CHECK_LAUNCH(); return CN_OK;
 }
 
@@ -329,7 +373,7 @@ extern "C" int cn_adam_ema_step_dev(float* p, const float* g, float* m, float* v
                                     float b1, float b2, float eps, float ema_alpha, float gscale, void* stream) {
   if (n <= 0) return CN_OK;
   CN_REQUIRE(p && g && m && v && lr_t_dev, CN_ERR_BAD_SHAPE, "cn_adam_ema_step_dev: null pointer");
-  ++g_cn_weight_epoch;
+  cn_mark_params_changed(p); if (ema) cn_mark_params_changed(ema);
   adam_ema_dev_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, (size_t)n, lr_t_dev, b1, b2, eps, ema_alpha, gscale);
   CN_CHECK_LAUNCH(); return CN_OK;
 }
@@ -337,7 +381,7 @@ extern "C" int cn_adam_ema_step(float* p, const float* g, float* m, float* v, fl
                                 float b1, float b2, float eps, float ema_alpha, float gscale, void* stream) {
   if (n <= 0) return CN_OK;
   CN_REQUIRE(p && g && m && v, CN_ERR_BAD_SHAPE, "cn_adam_ema_step: null pointer");
-  ++g_cn_weight_epoch;
+  cn_mark_params_changed(p); if (ema) cn_mark_params_changed(ema);
   adam_ema_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, (size_t)n, lr_t, b1, b2, eps, ema_alpha, gscale);
   CN_CHECK_LAUNCH(); return CN_OK;
 }
@@ -347,7 +391,7 @@ __global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ p,
     ema[i] = alpha * ema[i] + (1.f - alpha) * p[i];
 }
 extern "C" int cn_ema(float* ema, const float* p, int64_t n, float alpha, void* stream) {
-  ++g_cn_weight_epoch;
+  cn_mark_params_changed(ema);
   if (n <= 0) return CN_OK;
   ema_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(ema, p, (size_t)n, alpha);
   CN_CHECK_LAUNCH(); return CN_OK;

@@ -79,19 +79,35 @@ __global__ void bn_act_bwd_kernel(const float* __restrict__ gout, const float* _
   if (threadIdx.y == 0 && ch < c) {
     float a = 0.f, b = 0.f;
     for (int i = 0; i < 8; ++i) { a += sg[i][threadIdx.x]; b += sb[i][threadIdx.x]; }
-    atomicAdd(dgamma + ch, a); atomicAdd(dbeta + ch, b);
+    // slab blockIdx.y of the partial buffer: [dgamma (c) | dbeta (c)]; cn_sum_slabs adds the slabs in order
+    dgamma[(size_t)blockIdx.y * 2 * c + ch] = a; dbeta[(size_t)blockIdx.y * 2 * c + ch] = b;
   }
+}
+// dgamma / dbeta <- the two halves of the summed slab
+__global__ void bn_split_sums_kernel(const float* __restrict__ sum2, int c, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c) { dgamma[i] = sum2[i]; dbeta[i] = sum2[c + i]; }
 }
 extern "C" int cn_bn_act_bwd(const float* gout, const float* out, const float* x, const float* scale, const float* mean,
                              const float* var, float eps, int relu, float* gx, float* gres, float* dgamma, float* dbeta,
                              int64_t npix, int c, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  CN_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)c * sizeof(float), st));
-  CN_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)c * sizeof(float), st));
-  if (npix == 0) return CN_OK;
+  if (npix == 0) {
+    CN_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)c * sizeof(float), st));
+    CN_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)c * sizeof(float), st));
+    return CN_OK;
+  }
   int ysplit = (int)((npix + 63) / 64); if (ysplit > 148 * 4) ysplit = 148 * 4; if (ysplit < 1) ysplit = 1;
   dim3 grid((c + 31) / 32, ysplit), block(32, 8);
-  bn_act_bwd_kernel<<<grid, block, 0, st>>>(gout, out, x, scale, mean, var, eps, relu, gx, gres, dgamma, dbeta, (int)npix, c);
+  // per-row-split partial sums (no atomics), then a fixed-order sum: the gamma / beta gradients are bit-reproducible
+  static char key;
+  float* ws = nullptr;
+  int rc = cn_scratch(&key, ((size_t)ysplit + 1) * 2 * c * sizeof(float), &ws); if (rc) return rc;
+  bn_act_bwd_kernel<<<grid, block, 0, st>>>(gout, out, x, scale, mean, var, eps, relu, gx, gres, ws, ws + c, (int)npix, c);
+  CN_CHECK_LAUNCH();
+  float* sum2 = ws + (size_t)ysplit * 2 * c;
+  rc = cn_sum_slabs(ws, ysplit, 2 * c, sum2, st); if (rc) return rc;
+  bn_split_sums_kernel<<<(c + 255) / 256, 256, 0, st>>>(sum2, c, dgamma, dbeta);
   CN_CHECK_LAUNCH(); return CN_OK;
 }
 
@@ -299,20 +315,46 @@ __global__ void rotate3d_bwd_rot_kernel(const float* __restrict__ grid, const fl
     for (int k = 0; k < 9; ++k) red[wl][k] = out9[k];
   }
   __syncthreads();
-  // the 8 voxels of a block belong to one sample (s^3 is a multiple of 8)
+  // the 8 voxels of a block belong to one sample (s^3 is a multiple of 8): one partial row per block
   if (threadIdx.x < 9 && blockIdx.x * 8 < nvox_total) {
     float v = 0.f;
     for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
-    atomicAdd(grot + (size_t)((blockIdx.x * 8) / s3) * 9 + threadIdx.x, v);
+    grot[(size_t)blockIdx.x * 9 + threadIdx.x] = v;
   }
+}
+// grot[b][k] = sum over the sample's `per` block partials, fixed order: thread t adds rows t, t+256, ..., then a fixed tree
+__global__ void __launch_bounds__(256)
+rot_partials_sum_kernel(const float* __restrict__ part, int per, float* __restrict__ grot) {
+  __shared__ float red[256][9];
+  const float* p = part + (size_t)blockIdx.x * per * 9;
+  float a[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) a[k] = 0.f;
+  for (int r = threadIdx.x; r < per; r += 256)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a[k] += p[(size_t)r * 9 + k];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) red[threadIdx.x][k] = a[k];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) red[threadIdx.x][k] += red[threadIdx.x + o][k];
+    __syncthreads();
+  }
+  if (threadIdx.x < 9) grot[(size_t)blockIdx.x * 9 + threadIdx.x] = red[0][threadIdx.x];
 }
 extern "C" int cn_rotate3d_bwd_rot(const float* grid, const float* gout, const float* rot, int b, int s, int c, float* grot, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   CN_REQUIRE((s * s * s) % 8 == 0, CN_ERR_UNSUPPORTED, "cn_rotate3d_bwd_rot: grid size^3 must be a multiple of 8");
-  CN_CHECK_CUDA(cudaMemsetAsync(grot, 0, (size_t)b * 9 * sizeof(float), st));
   int nv = b * s * s * s;
   if (nv == 0) return CN_OK;
-  rotate3d_bwd_rot_kernel<<<(nv + 7) / 8, 256, 0, st>>>(grid, gout, rot, s, c, grot, nv);
+  static char key;
+  float* ws = nullptr;
+  int rc = cn_scratch(&key, (size_t)(nv / 8) * 9 * sizeof(float), &ws); if (rc) return rc;
+  rotate3d_bwd_rot_kernel<<<nv / 8, 256, 0, st>>>(grid, gout, rot, s, c, ws, nv);
+  CN_CHECK_LAUNCH();
+  rot_partials_sum_kernel<<<b, 256, 0, st>>>(ws, s * s * s / 8, grot);
   CN_CHECK_LAUNCH(); return CN_OK;
 }
 

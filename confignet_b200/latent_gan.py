@@ -14,7 +14,7 @@ import torch
 
 from . import netspec, networks, ops
 from .confignet_first_stage import merge_configs
-from .runtime import ParamGroup, Network, KerasAdam, allreduce_grads, shard_rows, world
+from .runtime import ParamGroup, Network, KerasAdam, StepGraphs, shard_rows, world
 
 DEFAULT_CONFIG = {
     "latent_dim": None,
@@ -35,11 +35,12 @@ def _mlp_forward(p, x, num_layers, second_order=False):
     return f(x, p, "mlp", num_layers, 0.3)
 
 
-class LatentGAN:
+class LatentGAN(StepGraphs):
     def __init__(self, config, device=None, seed=4321):
         self.config = merge_configs(DEFAULT_CONFIG, config)
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self._seed = seed
+        self._graphs = {}                 # step name -> (optimizer, runtime.GraphedFn)
         self.generator = None
         self.generator_smoothed = None
         self.discriminator = None
@@ -98,13 +99,8 @@ class LatentGAN:
         lo, hi = shard_rows(arrays[0].shape[0]) if world()[1] > 1 else (0, arrays[0].shape[0])
         return [a[lo:hi] for a in arrays]
 
-    def _apply(self, optimizer, loss, net):
-        g = net.group
-        grads = torch.autograd.grad(loss, g.trainable_weights, allow_unused=True)
-        keep = g.pack_grads(grads)
-        optimizer.apply_flat([g], allreduce_grads([g]))
-        return keep
-
+    # these steps are launch-latency bound (three-layer MLPs on (B, latent) matrices, ~120 tiny
+    # launches each) - host half (NumPy draws, uploads, Adam's iteration count) + a CUDA-graph replay of the device half.
     def discriminator_training_step(self, gt_embeddings, optimizer):
         """latent_gan.py:117-149 (RNG draw order: input latents, then the real-embedding indices)."""
         B = self.config["batch_size"]
@@ -115,31 +111,44 @@ class LatentGAN:
             real = gt_embeddings[torch.as_tensor(real_idxs, device=gt_embeddings.device)].to(self.device, torch.float32)
         else:
             real = networks._as_dev(gt_embeddings[real_idxs], self.device)
-        fake = self.generator.predict(latent_vectors)
+        latent_d = networks._as_dev(latent_vectors, self.device)
+        optimizer.begin_step(self.device)
         nl = self.config["num_mlp_layers"]
-        real = real.detach().requires_grad_(True)
-        p_d = self.discriminator.params
-        o_real = _mlp_forward(p_d, real, nl, second_order=True)
-        o_fake = _mlp_forward(p_d, fake.detach(), nl, second_order=True)
-        losses = OrderedDict()
-        losses["GAN_loss_real"] = networks.gan_d_loss(1, o_real)
-        losses["GAN_loss_fake"] = networks.gan_d_loss(0, o_fake)
-        losses["gp_loss"] = networks.gradient_regularization(o_real, real)
-        losses["loss_sum"] = networks._sum(losses.values())
-        self._apply(optimizer, losses["loss_sum"], self.discriminator)
-        return OrderedDict((k, v.detach()) for k, v in losses.items())
+
+        def device_half(latent_d, real):
+            with torch.no_grad():
+                fake = self.generator(latent_d)
+            real = real.detach().requires_grad_(True)
+            p_d = self.discriminator.params
+            o_real = _mlp_forward(p_d, real, nl, second_order=True)
+            o_fake = _mlp_forward(p_d, fake.detach(), nl, second_order=True)
+            losses = OrderedDict()
+            losses["GAN_loss_real"] = networks.gan_d_loss(1, o_real)
+            losses["GAN_loss_fake"] = networks.gan_d_loss(0, o_fake)
+            losses["gp_loss"] = networks.gradient_regularization(o_real, real)
+            losses["loss_sum"] = networks._sum(losses.values())
+            self._backward(losses["loss_sum"], [self.discriminator])
+            return OrderedDict((k, v.detach()) for k, v in losses.items())
+        fn = self._graphed("d", optimizer, device_half, [self.discriminator])
+        return self._global_losses(fn(latent_d, real))
 
     def generator_training_step(self, optimizer):
         """latent_gan.py:151-165."""
         latents = self.sample_input_latent_vector(self.config["batch_size"]).astype(np.float32)
         latents, = self._rank_rows(latents)
+        latent_d = networks._as_dev(latents, self.device)
+        optimizer.begin_step(self.device)
         nl = self.config["num_mlp_layers"]
-        losses = OrderedDict()
-        generated = self.generator(latents)
-        losses["gan_loss"] = networks.gan_g_loss(_mlp_forward(self.discriminator.params, generated, nl))
-        losses["loss_sum"] = networks._sum(losses.values())
-        self._apply(optimizer, losses["loss_sum"], self.generator)
-        return OrderedDict((k, v.detach()) for k, v in losses.items())
+
+        def device_half(latent_d):
+            losses = OrderedDict()
+            generated = self.generator(latent_d)
+            losses["gan_loss"] = networks.gan_g_loss(_mlp_forward(self.discriminator.params, generated, nl))
+            losses["loss_sum"] = networks._sum(losses.values())
+            self._backward(losses["loss_sum"], [self.generator])
+            return OrderedDict((k, v.detach()) for k, v in losses.items())
+        fn = self._graphed("g", optimizer, device_half, [self.generator])
+        return self._global_losses(fn(latent_d))
 
     def update_smoothed_weights(self, smoother_alpha=0.999):
         """latent_gan.py:167-174, one kernel over the flat buffer."""

@@ -546,7 +546,7 @@ class Rotate3D(torch.autograd.Function):
         b, s, c = ctx.dims
         gg = grot = None
         if ctx.needs_input_grad[0]:
-            gg = torch.zeros_like(gout)
+            gg = torch.empty_like(gout)      # written whole (fixed-point scatter + conversion, csrc/misc.cu)
             L.call("cn_rotate3d_bwd_grid", _p(gout), _p(rot), b, s, c, _p(gg), _stream())
         if ctx.needs_input_grad[1]:
             grot = torch.empty((b, 9), device=gout.device, dtype=torch.float32)

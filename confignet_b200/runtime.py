@@ -12,6 +12,7 @@ buffers, and the data-parallel gradient exchange.
 import ctypes
 import math
 import os
+import weakref
 from collections import OrderedDict
 import numpy as np
 import torch
@@ -35,6 +36,7 @@ class ParamGroup:
             self.offsets.append(off)
             off += (n + 3) // 4 * 4
         self.total = off
+        self.frozen, self.on_frozen_change = False, None
         self.device = torch.device(device)
         self.flat = torch.zeros(self.total, device=self.device, dtype=torch.float32)
         self.grad = torch.zeros(self.total, device=self.device, dtype=torch.float32)
@@ -76,8 +78,21 @@ class ParamGroup:
         self._changed()
 
     def _changed(self):
+        """the flat buffer was written by something other than the library's optimizer / EMA entry points"""
         if self.flat.is_cuda:
-            L.call("cn_weights_changed")
+            L.call("cn_params_changed", ops._p(self.flat))
+            if self.frozen and self.on_frozen_change is not None:
+                self.on_frozen_change()
+
+    def set_frozen(self, on_change=None):
+        """Declares the buffer constant between set_weights() calls (VGG19 / VGGFace, perceptual_loss.py:19-41): captured
+        step graphs then keep using its packed kernels instead of re-packing them on every replay.  ``on_change`` is
+        called when set_weights() does change it (the owner drops its captured graphs)."""
+        self.frozen, self.on_frozen_change = True, on_change
+        for v in self.params.values():
+            v.requires_grad_(False)
+        if self.flat.is_cuda:
+            L.call("cn_set_params_frozen", ops._p(self.flat), 1)
 
     def __del__(self):
         try:
@@ -186,12 +201,8 @@ class KerasAdam:
     def begin_step(self, device):
         if getattr(self, "lr_dev", None) is None:
             self.lr_dev = torch.zeros(1, device=device, dtype=torch.float32)
-            self._lr_ring = torch.zeros(16, dtype=torch.float32)
-            if self.lr_dev.is_cuda:
-                self._lr_ring = self._lr_ring.pin_memory()
-        slot = self.iterations % 16
-        self._lr_ring[slot] = self._lr_t(self.iterations + 1)
-        self.lr_dev.copy_(self._lr_ring[slot:slot + 1], non_blocking=True)
+        # the value travels as a kernel argument (no staging buffer the host could overwrite while it runs ahead of the GPU)
+        self.lr_dev.fill_(self._lr_t(self.iterations + 1))
         self.iterations += 1
 
     def apply_flat_device_lr(self, groups, gscale=1.0):
@@ -201,60 +212,193 @@ class KerasAdam:
 
 
 class GraphedFn:
-    """Runs ``fn(*tensors) -> OrderedDict of scalar tensors`` (the device half of a training step: forward, losses,
-    backward, gradient packing, all-reduce, Adam) as a CUDA-graph replay.  The first ``warm`` calls run eagerly (they
-    are real steps and let the library create its plans and buffers), the next call is captured and replayed, later
-    calls copy their inputs into the captured input tensors and replay.  Any capture error switches the wrapper
-    back to eager execution for good.  Shapes must not change between calls (a new shape -> eager)."""
+    """Runs the device half of a training step as CUDA-graph replays.
+
+    ``fn(*tensors) -> OrderedDict of scalar tensors`` is everything up to and including the packing of the flat
+    gradient buffers of ``groups`` (forward, losses, backward incl. the R1 double backward); ``finish()`` is the
+    optimizer launch on those buffers.  On one GPU both are captured into ONE graph.  Under data parallelism the
+    gradient all-reduce sits between them and stays OUTSIDE the graphs: graph 1 (``fn``), NCCL all-reduce on the flat
+    buffers, graph 2 (``finish``).  No NCCL work is ever captured, so the process group can be torn down normally.
+
+    The first ``warm`` calls run eagerly (they are real steps and let the library create its plans and buffers), the
+    next call is captured and replayed, later calls copy their inputs into the captured input tensors and replay.  A
+    replay runs the optimizer kernels without the host code that tells the library its packed-weight cache is out of
+    date, so every replay marks the flat buffers of ``groups`` as changed (cn_params_changed).  Any capture error
+    switches the wrapper back to eager execution for good.  Shapes must not change between calls (new shape -> eager)."""
     ENABLED = os.environ.get("CN_GRAPHS", "1") != "0"
     REPLAYED_LAUNCHES = 0          # library kernels launched through graph replays (cn_launch_count only sees eager ones)
+    _live = weakref.WeakSet()      # every wrapper that holds a captured graph (release_graphs)
 
-    def __init__(self, fn, warm=2):
-        self.fn, self.warm = fn, warm
-        self.calls, self.graph, self.failed = 0, None, False
+    def __init__(self, fn, finish=None, groups=(), warm=2, reduce_groups=None):
+        self.fn, self.finish, self.groups, self.warm = fn, finish, list(groups), warm
+        self.rgroups = self.groups if reduce_groups is None else list(reduce_groups)     # gradients exchanged between ranks
+        self.calls, self.graph, self.graph2, self.failed = 0, None, None, False
         self.static_in, self.static_out, self.sig = None, None, None
+        self.launches = 0
 
     @staticmethod
     def _sig(tensors):
         return tuple((tuple(t.shape), t.dtype) for t in tensors)
 
+    def _eager(self, tensors):
+        out = self.fn(*tensors)
+        if self.finish is not None:
+            self.finish(allreduce_grads(self.rgroups))
+        return out
+
+    def release(self):
+        """drops the captured graphs (and their memory pool); the next call captures again"""
+        self.graph = self.graph2 = self.static_in = self.static_out = None
+        self.calls = min(self.calls, self.warm)
+
+    def _capture(self, tensors):
+        self.sig = self._sig(tensors)
+        self.static_in = [t.clone() for t in tensors]
+        torch.cuda.synchronize()
+        ws = world()[1]
+        lib = L.load()
+        n0 = int(lib.cn_launch_count(0))
+        g = torch.cuda.CUDAGraph()
+        g2 = None
+        with torch.cuda.graph(g):
+            out = self.fn(*self.static_in)
+            if self.finish is not None and ws == 1:
+                self.finish(1.0)
+        if self.finish is not None and ws > 1:
+            g.replay()                                 # the captured step's gradients are real before they are reduced
+            scale = allreduce_grads(self.rgroups)
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, pool=g.pool()):
+                self.finish(scale)
+            g2.replay()
+            first_done = True
+        else:
+            first_done = False
+        self.launches = int(lib.cn_launch_count(0)) - n0       # recorded, not executed
+        lib.cn_launch_count_add(-self.launches)
+        self.graph, self.graph2, self.static_out = g, g2, out
+        L.call("cn_graphs_captured")
+        GraphedFn._live.add(self)
+        return first_done
+
     def __call__(self, *tensors):
         if not GraphedFn.ENABLED or self.failed or ops.PROFILE[0] is not None or not tensors[0].is_cuda:
-            return self.fn(*tensors)
-        if world()[1] > 1 and os.environ.get("CN_GRAPHS_DP", "0") != "1":
-            # a captured NCCL all-reduce keeps the communicator busy at teardown (destroy_process_group hangs unless the
-            # graphs are dropped first): opt-in under data parallelism (bench.py does, and leaves without the teardown)
-            return self.fn(*tensors)
+            return self._eager(tensors)
         self.calls += 1
         if self.calls <= self.warm:
-            return self.fn(*tensors)
+            return self._eager(tensors)
+        done = False
         if self.graph is None:
             try:
-                self.sig = self._sig(tensors)
-                self.static_in = [t.clone() for t in tensors]
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                n0 = int(L.load().cn_launch_count(0))
-                with torch.cuda.graph(g):
-                    out = self.fn(*self.static_in)
-                self.launches = int(L.load().cn_launch_count(0)) - n0       # recorded, not executed
-                L.load().cn_launch_count_add(-self.launches)
-                self.graph, self.static_out = g, out
-                L.call("cn_graphs_captured")
+                done = self._capture(tensors)
             except Exception as e:                                   # pragma: no cover - depends on the driver
-                self.failed, self.graph = True, None
+                self.failed = True
+                self.release()
                 torch.cuda.synchronize()
                 import warnings
                 warnings.warn("CUDA-graph capture of a training step failed (%s); running eagerly" % (str(e)[:200],))
-                return self.fn(*tensors)
+                return self._eager(tensors)
         elif self._sig(tensors) != self.sig:
-            return self.fn(*tensors)
+            return self._eager(tensors)
         else:
             for s, t in zip(self.static_in, tensors):
                 s.copy_(t, non_blocking=True)
-        self.graph.replay()
+        if not done:
+            self.graph.replay()
+            if self.graph2 is not None:
+                allreduce_grads(self.rgroups)
+                self.graph2.replay()
+        for g in self.groups:                   # the replayed optimizer kernels changed these buffers
+            L.call("cn_params_changed", ops._p(g.flat))
         GraphedFn.REPLAYED_LAUNCHES += self.launches
         return OrderedDict((k, v.clone()) for k, v in self.static_out.items())
+
+
+def release_graphs():
+    """Drops every captured step graph of this process (their private memory pools go back to the allocator)."""
+    for g in list(GraphedFn._live):
+        g.release()
+    GraphedFn._live.clear()
+    import gc
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+
+
+class StepGraphs:
+    """What the model classes share around an optimizer step: tape.gradient + packing, the eager whole step, the
+    CUDA-graph wrapper per step, global loss values under data parallelism.  Expects ``self._graphs`` (dict),
+    ``self.config`` and ``self.device``."""
+
+    def _backward(self, loss, nets):
+        """tape.gradient(loss, trainable_weights) for the networks of one optimizer step, packed into their flat
+        gradient buffers -> the groups."""
+        groups = [n.group if hasattr(n, "group") else n for n in nets]
+        params = [p for g in groups for p in g.trainable_weights]
+        grads = torch.autograd.grad(loss, params, allow_unused=True)
+        i = 0
+        for g in groups:
+            k = len(g.trainable_weights)
+            g.pack_grads(grads[i:i + k])
+            i += k
+        return groups
+
+    def _apply(self, optimizer, loss, nets, device_lr=False):
+        """optimizer.apply_gradients(zip(tape.gradient(...), trainable_weights)): backward, gradient exchange, Adam.
+        device_lr: the host half of the optimizer step (KerasAdam.begin_step) already ran."""
+        groups = self._backward(loss, nets)
+        gscale = allreduce_grads(groups)
+        if device_lr:
+            optimizer.apply_flat_device_lr(groups, gscale)
+        else:
+            optimizer.apply_flat(groups, gscale)
+
+    def _graphed(self, name, optimizer, fn, nets, dp_ok=True, reduce_groups=None):
+        """One CUDA-graph wrapper per step, bound to the optimizer whose moment buffers the captured region holds.
+        ``fn`` ends with _backward(loss, nets); the wrapper adds the gradient exchange and the Adam launch.
+        dp_ok = False: ``fn`` itself contains a collective (the all-gathered batch-statistics loss of stage 2), which
+        must not be captured - such a step runs eagerly under data parallelism.  reduce_groups: the groups whose
+        gradients are exchanged when that is not all of them (fine-tuning keeps per-image variables rank-local)."""
+        groups = [n.group if hasattr(n, "group") else n for n in nets]
+        rgroups = groups if reduce_groups is None else list(reduce_groups)
+
+        def finish(gscale, o=optimizer, gr=groups):
+            o.apply_flat_device_lr(gr, gscale)
+        if not self.config.get("cuda_graphs", True) or (world()[1] > 1 and not dp_ok):
+            def eager(*tensors):
+                out = fn(*tensors)
+                finish(allreduce_grads(rgroups))
+                return out
+            return eager
+        entry = self._graphs.get(name)
+        if entry is None or entry[0] is not optimizer:
+            # a new optimizer object (a second train() call): its moment buffers and learning-rate scalar are not the
+            # ones the old graph captured - drop that graph (and its memory pool) and start over
+            entry = self._graphs[name] = (optimizer, GraphedFn(fn, finish, groups, reduce_groups=rgroups))
+        return entry[1]
+
+    def drop_graphs(self):
+        """forget the captured step graphs (the next step runs eagerly again and is re-captured)"""
+        for _, g in self._graphs.values():
+            g.release()
+        self._graphs.clear()
+
+    def close(self):
+        """release the captured step graphs and their memory pools (call before tearing the process group down)"""
+        self.drop_graphs()
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
+    def _global_losses(self, losses):
+        """Data parallelism: every loss term is a batch mean over this rank's equal shard; the value of the global batch
+        (what a single-GPU run reports and logs) is the mean over ranks - one small all-reduce per step."""
+        if world()[1] == 1:
+            return losses
+        keys = list(losses.keys())
+        t = torch.stack([losses[k].reshape(()) for k in keys])
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t = t / world()[1]
+        return OrderedDict((k, t[i]) for i, k in enumerate(keys))
 
 
 # ------------------------------------------------------------------------------------------------ data parallel

@@ -47,11 +47,16 @@ long long cn_launch_count_add(long long delta);
 
 /* Parameter buffers.  A caller that keeps its Keras kernels in long-lived device buffers (the ParamGroup flat
  * buffers behind model.get_weights()/set_weights(), confignet_first_stage.py:129-206) registers them once; the conv
- * entry points then keep the tensor-core stage images of those kernels until the buffer changes.  The optimizer and
- * EMA entry points below mark the change themselves; any OTHER writer (set_weights, a memcpy) must call
- * cn_weights_changed().  Unregistered weight pointers are re-packed on every call. */
+ * entry points then keep the tensor-core stage images of those kernels until THAT buffer changes.  The optimizer and
+ * EMA entry points below mark the buffers they write themselves; any OTHER writer (set_weights, a memcpy, a replayed
+ * CUDA graph that contains optimizer launches) must call cn_params_changed(base) - or cn_weights_changed() for all
+ * buffers.  cn_set_params_frozen(base, 1) declares a buffer that only changes through cn_params_changed (VGG19 /
+ * VGGFace, perceptual_loss.py:19-41): captured graphs then reuse its images instead of re-packing them per replay.
+ * Unregistered weight pointers are re-packed on every call. */
 int cn_register_params(const void* base, size_t bytes);
 int cn_unregister_params(const void* base);
+int cn_params_changed(const void* base);
+int cn_set_params_frozen(const void* base, int frozen);
 int cn_weights_changed(void);
 /* call once a CUDA graph has been captured over this library's launches: internal scratch / cache buffers are then
  * never freed (a graph may still reference them), growth abandons the old buffer instead */
@@ -137,7 +142,7 @@ int cn_maxpool2_bwd(const float* x, const float* y, const float* gy, int n, int 
 /* transform_3d_grid_tf (confignet_utils.py:63-120): trilinear resample of (B,S,S,S,C) under a
  * per-sample 3x3 matrix `rot` (B,9) about the volume centre, clamp-to-edge. */
 int cn_rotate3d_fwd(const float* grid, const float* rot, int b, int s, int c, float* out, void* stream);
-/* gradient wrt the grid (scatter-add; ggrid must be zero-filled by the caller) */
+/* gradient wrt the grid: a scatter accumulated in 64-bit fixed point (bit-reproducible), then written whole to ggrid */
 int cn_rotate3d_bwd_grid(const float* gout, const float* rot, int b, int s, int c, float* ggrid, void* stream);
 /* loss reductions (losses.py:7-18,75-82, perceptual_loss.py:76-80): deterministic two-stage sums.
  * kind 0: sum softplus(sign*x)   kind 1: sum (x-y)^2   kind 2: sum x^2   kind 3: sum x

@@ -829,12 +829,28 @@ def test_graph_wrappers_are_bound_to_their_optimizer_object():
                              "facemodel_inputs": netspec.default_facemodel_inputs()}, device="cpu")
     o1, o2 = KerasAdam(), KerasAdam()
     f = lambda *t: None
-    a = m._graphed("d", o1, f)
-    assert isinstance(a, GraphedFn) and m._graphed("d", o1, f) is a
-    c = m._graphed("d", o2, f)
-    assert c is not a and m._graphed("d", o2, f) is c and m._graphed("g", o2, f) is not c
+    nets = [m.discriminator]
+    a = m._graphed("d", o1, f, nets)
+    assert isinstance(a, GraphedFn) and m._graphed("d", o1, f, nets) is a
+    assert a.groups == [m.discriminator.group] and a.rgroups == a.groups
+    c = m._graphed("d", o2, f, nets)
+    assert c is not a and m._graphed("d", o2, f, nets) is c and m._graphed("g", o2, f, nets) is not c
+    m.drop_graphs()
+    assert not m._graphs and m._graphed("d", o2, f, nets) is not c
     m.config["cuda_graphs"] = False
-    assert m._graphed("d", o1, f) is f
+    assert not isinstance(m._graphed("d", o1, f, nets), GraphedFn)
+
+
+def test_step_wrapper_runs_fn_then_exchange_then_optimizer_on_cpu():
+    """The eager form of a wrapped step (CPU tensors never capture): fn, then the optimizer launch with the 1/world
+    scale, in that order and once per call; the iteration counter is advanced by begin_step only."""
+    from collections import OrderedDict
+    from confignet_b200.runtime import GraphedFn
+    order = []
+    g = GraphedFn(lambda x: (order.append("fn"), OrderedDict(s=x.sum()))[1], lambda scale: order.append(("finish", scale)))
+    for _ in range(3):
+        assert float(g(torch.ones(4))["s"]) == 4.0
+    assert order == ["fn", ("finish", 1.0)] * 3 and g.graph is None
 
 
 def test_oracle_matches_reference_float_code():
