@@ -1,19 +1,26 @@
-"""bench.py - G+D training-step throughput of the ConfigNet hot path on B200 (BASELINE.json configs[1]).
+"""bench.py - throughput of the ConfigNet hot path on B200 for the five BASELINE.json configurations.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference (oracle/)
+    python bench.py [--config C] --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py [--config C] --impl reference --steps K --warmup W    # CPU restatement of the reference (oracle/)
 
-A "step" = discriminator_training_step + generator_training_step (confignet_first_stage.py:466-476,
-506-560) on one synthetic 256x256 batch of 32 images per GPU.  Prints ONE JSON line (rank 0).
+--config (default 2, the configuration BASELINE.json's metric is quoted on), all through the class API
+(confignet_b200.ConfigNetFirstStage / ConfigNet / LatentGAN) on synthetic 256x256 data, sizes PER GPU (weak scaling):
+  1  generate_images, batch 1 (confignet_first_stage.py:633-639)                                   unit: images/s (and ms latency)
+  2  discriminator_training_step + generator_training_step + EMA, batch 32 (:466-476,506-560)      unit: images/s
+  3  full first-stage iteration: D, synth-D, latent-D, G steps + EMA, batch 64 (:604-626)          unit: images/s
+  4  full second-stage iteration (adds the ResNet50 encoder), batch 32 per GPU - 128 over 4 GPUs (confignet_second_stage.py:277-299)
+  5  LatentGAN D+G step at batch 256 global (latent_gan.py:234-247) + fine_tune_on_img on 32 images per GPU, n_iters = 10
+     (confignet_second_stage.py:321-403)                                                          unit: image-iterations/s
 
-  value     images/s with the image / mask stores already resident in HBM (CUDA events, max over ranks)
-  e2e       same metric through the public class API with HOST datasets: pinned-memory H2D of every batch
-            and a D2H read of all loss terms inside the timed region
-  roofline  the tcgen05 implicit-GEMM conv kernels: algorithmic FLOPs / CUDA-event time of their launches
-  cpu_baseline  the oracle (CPU restatement; TensorFlow 2.1 is not installable) on this box's host cores
+Prints ONE JSON line (rank 0):
+  value         units/s with the image / mask / embedding stores already resident in HBM (CUDA events, max over ranks)
+  e2e           the same metric through the public API with HOST (NumPy) inputs: pinned-memory H2D of every batch and a D2H
+                read of every result (all loss terms / the uint8 images / the fine-tuned embeddings) inside the timed region
+  roofline      the tcgen05 implicit-GEMM conv kernels: algorithmic FLOPs / CUDA-event time of their launches
+  cpu_baseline  the oracle (CPU restatement; TensorFlow 2.1 is not installable) on this box's host cores at the workload batch
 
-No work is skipped inside the timed region: both steps run forward, backward (incl. the R1 double
-backward), gradient packing, [all-reduce], and the Adam updates.
+No work is skipped inside the timed region: every step runs forward, backward (incl. the R1 double backward), gradient
+packing, [all-reduce], and the Adam updates.
 """
 import argparse
 import json
@@ -25,13 +32,30 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("CN_GRAPHS_DP", "1")      # CUDA-graph replay of the steps under data parallelism too (see finish())
 
 import numpy as np
 import torch
 
-PER_GPU_BATCH = 32
 RES = 256
+METRIC = "256x256 face images/sec (G+D step)"
+
+CONFIGS = {
+    1: dict(per_gpu=1, unit="images/s",
+            workload="single 256x256 generator forward on random latent, batch=1 (generate_images; BASELINE.json configs[0])"),
+    2: dict(per_gpu=32, unit="images/s",
+            workload="generator+discriminator train_step, synthetic 256x256 batch=32 per GPU (BASELINE.json configs[1])"),
+    3: dict(per_gpu=64, unit="images/s",
+            workload="full ConfigNet first-stage iteration (D + synth-D + latent-D + G steps, perceptual loss, EMA), batch=64 per GPU "
+                     "(BASELINE.json configs[2])"),
+    4: dict(per_gpu=32, unit="images/s",
+            workload="full ConfigNet second-stage iteration (real + synthetic encoders + generator), batch=32 per GPU = 128 over 4 GPUs, "
+                     "NCCL gradient all-reduce (BASELINE.json configs[3])"),
+    5: dict(per_gpu=32, unit="image-iterations/s",
+            workload="LatentGAN D+G step (batch 256 global) + one-shot fine_tune_on_img generator loop, 32 images per GPU x n_iters=10 "
+                     "(BASELINE.json configs[4])"),
+}
+FT_ITERS = 10
+LGAN_BATCH = 256
 
 
 def facemodel_cfg():
@@ -48,12 +72,14 @@ def measured_peaks():
     return 6650.0, 1590.0, "fallback"
 
 
-def bench_config(world):
-    return {"workload": "generator+discriminator train_step, synthetic 256x256 batch=32 per GPU (BASELINE.json configs[1])",
-            "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * world, "resolution": RES,
-            "parallelism": "dp%d" % world,
-            "l2": "inputs larger than L2: >1 GB of activations per step, no flush needed",
-            "resident": "image and mask stores in HBM; per-step RNG draws (<100 KB) made by the step",
+def bench_config(cfg_id, world):
+    c = CONFIGS[cfg_id]
+    return {"workload": c["workload"], "config_id": cfg_id, "per_gpu_batch": c["per_gpu"], "global_batch": c["per_gpu"] * world,
+            "resolution": RES, "parallelism": "dp%d" % world,
+            "l2": "inputs larger than L2: >1 GB of activations per step, no flush needed" if cfg_id != 1 else
+                  "batch-1 latency path: the generator's 32 MB of kernels and its activations stay in the 126 MB L2 by design (the "
+                  "demo loop's steady state); no flush",
+            "resident": "image / mask / embedding stores in HBM; per-step RNG draws (<100 KB) made by the step",
             "arithmetic": "fp32 in / fp32 out; tensor-core convs as 3xTF32 (tf32 big/small operand split, 3 MMAs per product, "
                           "fp32 accumulation with chunked promotion)"}
 
@@ -90,76 +116,227 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None, "reasons": reasons}
 
 
-# ------------------------------------------------------------------------------------------------ reference arm
-def oracle_step_inputs(rng, fm, b):
-    ns = b // 2
-    nr = b - ns
-    real_u8 = rng.randint(0, 256, (b, RES, RES, 3), dtype=np.uint8)
-    lat = rng.standard_normal((b, 145)).astype(np.float32)
-    rot = np.zeros((b, 3), np.float32)
-    rot[:, 0] = np.pi * rng.uniform(-30, 30, b) / 180
-    rot[:, 1] = np.pi * rng.uniform(-10, 10, b) / 180
-    fparams = [rng.uniform(0, 1, (ns, d[0])).astype(np.float32) for d in fm.values()]
-    gt_u8 = rng.randint(0, 256, (ns, RES, RES, 3), dtype=np.uint8)
-    masks = (rng.rand(ns, RES, RES) < 0.01).astype(np.uint8)
-    return dict(real_u8=real_u8, lat=lat, rot=rot, fparams=fparams, gt_u8=gt_u8, masks=masks,
-                real_lat=lat[:nr], real_rot=rot[:nr], synth_rot=rot[:ns])
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle/)
+class OracleWorkload:
+    """One step of configuration `cfg_id` on the CPU restatement of the reference (oracle/), at batch `b` - the same
+    step functions the parity tests check the CUDA path against.  -> seconds per step."""
+
+    def __init__(self, cfg_id, b):
+        from oracle import confignet_oracle as O
+        from oracle import confignet_oracle_stage2 as O2
+        from confignet_b200 import netspec
+        self.cfg_id, self.b = cfg_id, b
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.fm = netspec.default_facemodel_inputs()
+        self.rng = np.random.RandomState(0)
+        if cfg_id in (1, 2, 3):
+            self.tr = O.OracleFirstStage(self.fm, RES)
+        else:
+            self.tr = O2.OracleSecondStage(self.fm, RES)
+        if cfg_id == 5:
+            self.lgan = O2.OracleLatentGAN()
+            self.emb = self.rng.standard_normal((10000, 145)).astype(np.float32)
+
+    def _u8(self, n):
+        return self.rng.randint(0, 256, (n, RES, RES, 3), dtype=np.uint8)
+
+    def _rot(self, n):
+        r = np.zeros((n, 3), np.float32)
+        r[:, 0] = np.pi * self.rng.uniform(-30, 30, n) / 180
+        r[:, 1] = np.pi * self.rng.uniform(-10, 10, n) / 180
+        return r
+
+    def _fm(self, n):
+        return [self.rng.uniform(0, 1, (n, d[0])).astype(np.float32) for d in self.fm.values()]
+
+    def _lat(self, n):
+        return self.rng.standard_normal((n, 145)).astype(np.float32)
+
+    def step(self, ft_iters=FT_ITERS):
+        b, ns = self.b, self.b // 2
+        nr = b - ns
+        tr = self.tr
+        t0 = time.perf_counter()
+        if self.cfg_id == 1:
+            tr.generate_images(self._lat(b), self._rot(b))
+        elif self.cfg_id in (2, 3):
+            tr.discriminator_step(self._u8(b), self._lat(b), self._rot(b))
+            if self.cfg_id == 3:
+                tr.synth_discriminator_step(self._u8(b), self._fm(b), self._rot(b))
+                tr.latent_discriminator_step(self._lat(b), self._fm(b))
+            masks = (self.rng.rand(ns, RES, RES) < 0.01).astype(np.uint8)
+            tr.generator_step(self._fm(ns), self._rot(ns), self._u8(ns), masks, self._lat(nr), self._rot(nr))
+        elif self.cfg_id == 4:
+            tr.discriminator_step(self._u8(b), self._u8(b))
+            tr.synth_discriminator_step(self._u8(b), self._fm(b), self._rot(b))
+            tr.latent_discriminator_step(self._u8(b), self._fm(b))
+            masks = (self.rng.rand(ns, RES, RES) < 0.01).astype(np.uint8)
+            tr.generator_step(self._fm(ns), self._rot(ns), self._u8(ns), masks, self._u8(nr))
+        else:
+            idx = self.rng.randint(0, self.emb.shape[0], LGAN_BATCH)
+            self.lgan.step(self.emb[idx], self._lat(LGAN_BATCH), self._lat(LGAN_BATCH))
+            tr.fine_tune(self._u8(b), ft_iters)
+        return time.perf_counter() - t0
 
 
-def oracle_one_step(tr, inp):
-    d = tr.discriminator_step(inp["real_u8"], inp["lat"], inp["rot"])
-    g = tr.generator_step(inp["fparams"], inp["synth_rot"], inp["gt_u8"], inp["masks"], inp["real_lat"], inp["real_rot"])
-    return float(d["loss_sum"].detach()) + float(g["loss_sum"].detach())
+def units_per_step(cfg_id, batch, ft_iters=FT_ITERS):
+    return batch * ft_iters if cfg_id == 5 else batch
 
 
-def time_oracle(steps, warmup, sample_batch):
-    from oracle import confignet_oracle as O
-    from confignet_b200 import netspec
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    fm = netspec.default_facemodel_inputs()
-    tr = O.OracleFirstStage(fm, RES)
-    rng = np.random.RandomState(0)
-    for _ in range(warmup):
-        oracle_one_step(tr, oracle_step_inputs(rng, fm, sample_batch))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        oracle_one_step(tr, oracle_step_inputs(rng, fm, sample_batch))
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return sample_batch / dt, dt, cores
+def cpu_baseline_leg(cfg_id):
+    """bounded sample (10-30 s of CPU work) at the workload batch"""
+    b = CONFIGS[cfg_id]["per_gpu"]
+    w = OracleWorkload(cfg_id, b)
+    if cfg_id == 1:
+        w.step()
+        ts = sorted(w.step() for _ in range(5))
+        dt, sample = ts[2], "median of 5 generate_images calls at batch 1 after 1 warm-up"
+        units = 1
+    elif cfg_id == 5:
+        dt = w.step(ft_iters=2)
+        units = units_per_step(5, b, 2)
+        sample = "1 LatentGAN D+G step at batch %d + fine_tune on %d images for 2 of the %d iterations (no warm-up)" % (LGAN_BATCH, b, FT_ITERS)
+    else:
+        n = 2 if cfg_id == 2 else 1
+        w.step()
+        dt = sum(w.step() for _ in range(n)) / n
+        units = b
+        sample = "%d step(s) at the workload batch %d after 1 warm-up step, %.1f s per step" % (n, b, dt)
+    return {"value": units / dt, "unit": CONFIGS[cfg_id]["unit"], "cores": w.cores, "kind": "port",
+            "sample": sample + "; torch-CPU fp32 oracle (CPU restatement of the reference; TensorFlow 2.1 is not installable)"}
 
 
 def run_reference(args):
+    """The reference arm: the oracle port on all host cores, at the workload's per-GPU batch; W warm-up and K timed steps
+    as asked, shortened only if they would not end within ~4 minutes (the line then says how many ran)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    b = 4
-    val, dt, cores = time_oracle(args.steps, min(args.warmup, 1), b)
-    sample = "1 D step + 1 G step at batch %d per step (1/%d of the per-GPU batch), torch-CPU fp32 oracle" % (b, PER_GPU_BATCH // b)
-    line = {"impl": "reference", "metric": "256x256 face images/sec (G+D step)", "value": val, "unit": "images/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+    cfg_id = args.config
+    b = CONFIGS[cfg_id]["per_gpu"]
+    w = OracleWorkload(cfg_id, b)
+    ft = FT_ITERS if cfg_id != 5 else 2
+    budget = 240.0
+    t_start = time.perf_counter()
+    first = w.step(ft) if cfg_id == 5 else w.step()
+    warm_done = 1
+    while warm_done < args.warmup and (time.perf_counter() - t_start) + first * 2 < budget * 0.3:
+        w.step(ft) if cfg_id == 5 else w.step()
+        warm_done += 1
+    times = []
+    while len(times) < args.steps and (not times or (time.perf_counter() - t_start) + first < budget):
+        times.append(w.step(ft) if cfg_id == 5 else w.step())
+    dt = sum(times) / len(times)
+    units = units_per_step(cfg_id, b, ft)
+    val = units / dt
+    sample = "%d of %d requested steps (+%d warm-up) at the workload batch %d per step" % (len(times), args.steps, warm_done, b)
+    if cfg_id == 5:
+        sample += ", fine_tune for %d of the %d iterations per step" % (ft, FT_ITERS)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": CONFIGS[cfg_id]["unit"],
+            "n_gpus": args.gpus, "steps": len(times), "warmup": warm_done, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(bench_config(args.gpus), reference_sample_batch=b,
-                           note="CPU restatement of the reference (TensorFlow 2.1 not installable), bounded sample of the workload"),
-            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": dict(bench_config(cfg_id, 1), note="CPU restatement of the reference (TensorFlow 2.1 not installable) on the host "
+                           "cores, one process, at the per-GPU batch of the workload"),
+            "cpu_baseline": {"value": val, "unit": CONFIGS[cfg_id]["unit"], "cores": w.cores, "kind": "port",
+                             "sample": sample + "; torch-CPU fp32 oracle"},
+            "e2e": {"value": val, "unit": CONFIGS[cfg_id]["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def losses_to_host(*loss_dicts):
-    """One D2H read of every loss term (the reference does ~40 float() syncs per iteration)."""
-    vals = [v.detach().reshape(1) for d in loss_dicts for v in d.values()]
-    return torch.cat(vals).cpu().numpy()
+class Workload:
+    """Configuration `cfg_id` through the class API.  step(resident) runs one step on the device-resident (True) or the
+    host (False) stores and returns what the caller must read back (device tensors) or has already received (NumPy)."""
+
+    def __init__(self, cfg_id, dev, world, rank):
+        from confignet_b200.confignet_first_stage import ConfigNetFirstStage
+        from confignet_b200.confignet_second_stage import ConfigNet
+        from confignet_b200.latent_gan import LatentGAN
+        from confignet_b200.runtime import KerasAdam
+        from confignet_b200.synthetic_data import SyntheticDataset
+        self.cfg_id, self.dev, self.world = cfg_id, dev, world
+        b = CONFIGS[cfg_id]["per_gpu"]
+        self.b = b
+        cfg = {"output_shape": (RES, RES, 3), "batch_size": b * world, "facemodel_inputs": facemodel_cfg()}
+        if cfg_id in (4, 5):
+            cfg["image_loss_weight"] = 5e-4           # SURVEY.md section 8d, config 4
+        self.model = (ConfigNet if cfg_id in (4, 5) else ConfigNetFirstStage)(cfg, device=dev)
+        m = self.model
+        n_store = max(96, 3 * b)
+        if cfg_id in (2, 3, 4):
+            self.host = (SyntheticDataset(n_store, RES, seed=1), SyntheticDataset(n_store, RES, seed=2))
+            self.devs = (SyntheticDataset(n_store, RES, seed=1).to_device(dev), SyntheticDataset(n_store, RES, seed=2).to_device(dev))
+            self.d_opt, self.g_opt = KerasAdam(**m.config["optimizer"]), KerasAdam(**m.config["optimizer"])
+        rng = np.random.RandomState(3 + rank)
+        if cfg_id == 1:
+            self.lat = rng.standard_normal((b, m.config["latent_dim"])).astype(np.float32)
+            self.rot = np.zeros((b, 3), np.float32)
+            self.rot[:, 0] = np.pi * rng.uniform(-30, 30, b) / 180
+            self.rot[:, 1] = np.pi * rng.uniform(-10, 10, b) / 180
+            self.lat_d, self.rot_d = torch.from_numpy(self.lat).to(dev), torch.from_numpy(self.rot).to(dev)
+        if cfg_id == 5:
+            self.gan = LatentGAN({"latent_dim": m.config["latent_dim"], "batch_size": LGAN_BATCH}, device=dev)
+            self.gan_opt = KerasAdam(**self.gan.config["optimizer"])
+            self.emb = np.random.RandomState(5).standard_normal((10000, m.config["latent_dim"])).astype(np.float32)
+            self.emb_d = torch.from_numpy(self.emb).to(dev)
+            imgs = np.random.RandomState(7).randint(0, 256, (b * world, RES, RES, 3), dtype=np.uint8)      # the GLOBAL image set
+            self.imgs = imgs
+            self.imgs_d = torch.from_numpy(imgs).to(dev)
+        np.random.seed(0)
+
+    def step(self, resident):
+        m, c = self.model, self.cfg_id
+        if c == 1:
+            if resident:
+                return [m.generate_images_device(self.lat_d, self.rot_d)]
+            return [m.generate_images(self.lat, self.rot)]
+        if c == 5:
+            d = self.gan.discriminator_training_step(self.emb_d if resident else self.emb, self.gan_opt)
+            g = self.gan.generator_training_step(self.gan_opt)
+            self.gan.update_smoothed_weights()
+            emb, rot = m.fine_tune_on_img(self.imgs_d if resident else self.imgs, n_iters=FT_ITERS)
+            return [d, g, emb, rot]
+        real, synth = self.devs if resident else self.host
+        out = [m.discriminator_training_step(real, self.d_opt)]
+        if c in (3, 4):
+            out.append(m.synth_discriminator_training_step(synth, self.d_opt))
+            out.append(m.latent_discriminator_training_step(real, synth, self.d_opt) if c == 4 else
+                       m.latent_discriminator_training_step(synth, self.d_opt))
+        out.append(m.generator_training_step(real, synth, self.g_opt))
+        m.update_smoothed_weights()
+        return out
+
+    def units(self):
+        return units_per_step(self.cfg_id, self.b * self.world)
+
+    def close(self):
+        self.model.close()
+        if self.cfg_id == 5:
+            self.gan.close()
+
+
+def device_results(results):
+    """the device tensors among a step's results, flattened (loss scalars, uint8 images)"""
+    vals = []
+    for r in results:
+        if isinstance(r, dict):
+            vals += [v.detach().reshape(-1).float() for v in r.values()]
+        elif isinstance(r, torch.Tensor):
+            vals.append(r.detach().reshape(-1).float() if r.dtype != torch.uint8 else r.detach().reshape(-1))
+    return vals
+
+
+def host_bytes(results):
+    return sum(r.nbytes for r in results if isinstance(r, np.ndarray))
 
 
 def run_b200(args):
     import torch.distributed as dist
     from confignet_b200 import ops, _lib as L
-    from confignet_b200.confignet_first_stage import ConfigNetFirstStage
-    from confignet_b200.runtime import KerasAdam
-    from confignet_b200.synthetic_data import SyntheticDataset
+    from confignet_b200 import runtime
+    from confignet_b200.runtime import GraphedFn
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -182,21 +359,8 @@ def run_b200(args):
             os.dup2(saved, 1)
             os.close(saved)
     lib = L.load()
-
-    cfg = {"output_shape": (RES, RES, 3), "batch_size": PER_GPU_BATCH * world, "facemodel_inputs": facemodel_cfg()}
-    model = ConfigNetFirstStage(cfg, device=dev)
-    n_store = 96
-    host_real, host_synth = SyntheticDataset(n_store, RES, seed=1), SyntheticDataset(n_store, RES, seed=2)
-    dev_real = SyntheticDataset(n_store, RES, seed=1).to_device(dev)
-    dev_synth = SyntheticDataset(n_store, RES, seed=2).to_device(dev)
-    d_opt, g_opt = KerasAdam(**model.config["optimizer"]), KerasAdam(**model.config["optimizer"])
-    np.random.seed(0)
-
-    def step(real_set, synth_set):
-        d = model.discriminator_training_step(real_set, d_opt)
-        g = model.generator_training_step(real_set, synth_set, g_opt)
-        model.update_smoothed_weights()
-        return d, g
+    cfg_id = args.config
+    wl = Workload(cfg_id, dev, world, rank)
 
     def barrier():
         if world > 1:
@@ -211,44 +375,53 @@ def run_b200(args):
         return float(t.item())
 
     for _ in range(args.warmup):
-        step(dev_real, dev_synth)
+        wl.step(True)
     barrier()
 
     # ---- value: stores resident in HBM, CUDA events around the K steps
     sampler = ClockSampler(local)
     if rank == 0:                  # one nvidia-smi poller per job (8 of them would compete with the ranks' host halves)
         sampler.start()
-    # roofline: a CUDA-event pair around every conv-family launch INSIDE the timed region (default), or - with
-    # --roofline-pass separate - over extra steps right after it (to measure what the ~1200 event records cost)
+    # roofline: a CUDA-event pair around every conv-family launch over extra EAGER steps right after the timed region
+    # (default; a graph replay cannot carry them), or - with --roofline-pass inline - inside it (forces eager execution)
     inline = args.roofline_pass == "inline"
     prof = []
     if inline:
         ops.PROFILE[0] = prof
-    from confignet_b200.runtime import GraphedFn
     lib.cn_launch_count(1)
     replayed0 = GraphedFn.REPLAYED_LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        step(dev_real, dev_synth)
+        wl.step(True)
     e1.record()
     barrier()
     launches = int(lib.cn_launch_count(0)) + (GraphedFn.REPLAYED_LAUNCHES - replayed0)     # eager launches + launches replayed from CUDA graphs
     ops.PROFILE[0] = None
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     clocks = sampler.summary()
-    value = PER_GPU_BATCH * world / (ms * 1e-3)
+    value = wl.units() / (ms * 1e-3)
+    latency = None
+    if cfg_id == 1:                 # the latency of ONE call, each timed on its own (median of 5)
+        ts = []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record(); wl.step(True); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        latency = sorted(ts)[2]
     prof_steps = args.steps
     if not inline:
         ops.PROFILE[0] = prof
-        prof_steps = max(1, min(args.steps, 4))
+        prof_steps = max(1, min(args.steps, 4 if cfg_id != 5 else 1))
         for _ in range(prof_steps):
-            step(dev_real, dev_synth)
+            wl.step(True)
         barrier()
         ops.PROFILE[0] = None
 
-    # ---- roofline of the tcgen05 conv kernels (events recorded around each launch in the timed region)
+    # ---- roofline of the tcgen05 conv kernels (events recorded around each launch)
     tc_exec = sum(p[6] for p in prof if p[4] == 2)
     tc_flops = sum(p[1] for p in prof if p[4] == 2)
     tc_ms = sum(p[2].elapsed_time(p[3]) for p in prof if p[4] == 2)
@@ -257,28 +430,34 @@ def run_b200(args):
     hbm, tensor_peak, how = measured_peaks()
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "tc_dram_traffic.json")      # written by scripts/summarize_launches.py from ncu
-    if os.path.exists(tpath):
+    tpath = os.path.join(ROOT, "profiles", "tc_dram_traffic.json")      # written by scripts/summarize_launches.py from ncu (config 2)
+    if cfg_id == 2 and os.path.exists(tpath):
         with open(tpath) as fp:
             t = json.load(fp)
         traffic, traffic_src = t.get("dram_bytes_per_launch"), t.get("source")
     n_tc = sum(1 for p in prof if p[4] == 2)
+    tf32 = None
+    ppath = os.path.join(ROOT, "profiles", "tf32_mma_peak.json")        # measured by scripts/gpu_probe_round2.py (MMA-only loop)
+    if os.path.exists(ppath):
+        with open(ppath) as fp:
+            tf32 = json.load(fp)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": achieved / tensor_peak, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": how + " cuBLAS bf16 dense (sustained); kind::tf32 runs at half of it and every fp32 product "
+                "peak_source": how + " cuBLAS bf16 dense (sustained); kind::tf32 issues at half that rate and every fp32 product "
                                "takes 3 tf32 MMAs (3xTF32), so frac <= 1/6 on executed FLOPs",
+                "tf32_mma_peak": tf32,
                 "kernel": "igemm_tc_pixel_kernel<B_MN,WG> (tcgen05 kind::tf32 fwd/dgrad/wgrad, 3 MMAs per product)",
                 "algorithmic_gflop_per_launch": tc_flops / max(n_tc, 1) / 1e9,
                 "avg_launch_us": tc_ms * 1e3 / max(n_tc, 1),
                 "executed_tflops": tc_exec / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0,
                 "executed_note": "FLOPs executed after sub-pixel folding of UpSampling(2)+conv; achieved counts the "
                                  "reference formulation (convs on the upsampled grid)",
-                "launches": sum(1 for p in prof if p[4] == 2) // prof_steps,
+                "launches": n_tc // prof_steps,
                 "tc_ms_per_step": tc_ms / prof_steps, "cuda_core_conv_ms_per_step": cc_ms / prof_steps,
                 "algorithmic_conv_tflop_per_step": all_flops / prof_steps / 1e12,
                 "step_algorithmic_tflops": all_flops / prof_steps / 1e12 / (ms * 1e-3),
                 "measured": ("CUDA events around each conv launch inside the timed region" if inline else
-                             "CUDA events around each conv launch over %d extra steps right after the timed region" % prof_steps)}
+                             "CUDA events around each conv launch over %d extra eager step(s) right after the timed region" % prof_steps)}
 
     if args.breakdown and rank == 0:
         agg = {}
@@ -293,76 +472,83 @@ def run_b200(args):
             for (op, key, impl), (n, t, f) in rows:
                 fp.write("%-6s %-62s %4d %5d %9.3f %8.2f\n" % (op, str(key), impl, n // prof_steps, t / prof_steps,
                                                              f / (t * 1e-3) / 1e12 if t > 0 else 0))
+
     def finish():
+        # the captured step graphs hold no NCCL work (the all-reduce runs between two graphs): release them, then a
+        # normal teardown of the process group
+        wl.close()
         if world > 1:
-            # The captured step graphs hold NCCL work: tearing the communicator down under them hangs (measured: the
-            # 2-GPU run sat in destroy_process_group until its timeout).  Everything is measured and printed - drop
-            # the graphs, meet the other ranks once more and leave without the teardown.
-            sys.stdout.flush()
-            model._graphs.clear()
-            torch.cuda.synchronize()
             dist.barrier()
-            torch.cuda.synchronize()
-            sys.stdout.flush()
-            sys.stderr.flush()
-            os._exit(0)
+            dist.destroy_process_group()
 
     if args.no_e2e:
         if rank == 0:
             print(json.dumps({"value": value, "ms_per_step": ms, "note": "profiling run (no e2e leg)"}), flush=True)
         finish()
         return
-    # ---- e2e: public API, host datasets, H2D + D2H inside the timed region
+    # ---- e2e: public API, host (NumPy) inputs, H2D + D2H inside the timed region
     for _ in range(2):
-        d, g = step(host_real, host_synth)
-        losses_to_host(d, g)
+        r = wl.step(False)
+        [v.cpu() for v in device_results(r)]
     d2h = 0
-    # Every step's losses are read back inside the timed region, but without draining the GPU: the D2H copy into a
+    # Every step's results are read back inside the timed region, but without draining the GPU: the D2H copy into a
     # pinned buffer is enqueued right behind the step, and the host looks at step k-1's buffer while step k runs.
-    n_loss = sum(len(x) for x in step(host_real, host_synth))
-    pinned = [torch.zeros(n_loss, dtype=torch.float32).pin_memory() for _ in range(2)]
+    # (Results the API itself returns as NumPy - generate_images, fine_tune_on_img - have already crossed.)
+    probe = device_results(wl.step(False))
+    pinned = None
+    if probe:
+        n_res = sum(v.numel() for v in probe)
+        dt_ = probe[0].dtype if all(v.dtype == probe[0].dtype for v in probe) else torch.float32
+        pinned = [torch.zeros(n_res, dtype=dt_).pin_memory() for _ in range(2)]
 
-    def enqueue_readback(i, *loss_dicts):
-        vals = torch.cat([v.detach().reshape(1) for dct in loss_dicts for v in dct.values()])
-        pinned[i % 2].copy_(vals, non_blocking=True)
+    def enqueue_readback(i, results):
+        vals = device_results(results)
+        if not vals:
+            return None
+        flat = torch.cat([v.to(pinned[0].dtype) for v in vals])
+        pinned[i % 2].copy_(flat, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         return pinned[i % 2], ev
 
-    ConfigNetFirstStage.h2d_bytes = 0
+    runtime.H2D_BYTES[0] = 0
     barrier()
     t0 = time.perf_counter()
     pending = None
     for i in range(args.steps):
-        cur = step(host_real, host_synth)          # host halves (sampling, pinned uploads) + asynchronous device halves
-        rb = enqueue_readback(i, *cur)
+        cur = wl.step(False)              # host halves (sampling, pinned uploads) + asynchronous device halves
+        d2h += host_bytes(cur)
+        rb = enqueue_readback(i, cur)
         if pending is not None:
             pending[1].synchronize()
             d2h += pending[0].numpy().copy().nbytes
         pending = rb
-    pending[1].synchronize()
-    d2h += pending[0].numpy().copy().nbytes
+    if pending is not None:
+        pending[1].synchronize()
+        d2h += pending[0].numpy().copy().nbytes
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0) / args.steps
-    e2e = {"value": PER_GPU_BATCH * world / dt, "unit": "images/s",
-           "h2d_bytes_per_step": ConfigNetFirstStage.h2d_bytes // args.steps, "d2h_bytes_per_step": d2h // args.steps}
+    e2e = {"value": wl.units() / dt, "unit": CONFIGS[cfg_id]["unit"],
+           "h2d_bytes_per_step": runtime.H2D_BYTES[0] // args.steps, "d2h_bytes_per_step": d2h // args.steps}
+    if cfg_id == 1:
+        ts = []
+        for _ in range(5):
+            t1 = time.perf_counter(); wl.step(False); ts.append((time.perf_counter() - t1) * 1e3)
+        e2e["latency_ms_median_of_5"] = sorted(ts)[2]
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        b = 16
-        val, cdt, cores = time_oracle(3, 1, b)
-        cpu_baseline = {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
-                        "sample": "3 x (1 D step + 1 G step) at batch %d (1/%d of the workload batch) after 1 warm-up step, "
-                                  "torch-CPU fp32 oracle (CPU restatement of the reference; TensorFlow 2.1 is not "
-                                  "installable), %.1f s per step" % (b, PER_GPU_BATCH // b, cdt)}
+        cpu_baseline = cpu_baseline_leg(cfg_id)
     if rank == 0:
-        line = {"metric": "256x256 face images/sec (G+D step)", "value": value, "unit": "images/s", "n_gpus": world,
+        line = {"metric": METRIC, "value": value, "unit": CONFIGS[cfg_id]["unit"], "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": bench_config(world),
+                "config": bench_config(cfg_id, world),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": cpu_baseline}
+        if latency is not None:
+            line["latency_ms_median_of_5"] = latency
         print(json.dumps(line), flush=True)
     finish()
 
@@ -372,6 +558,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configuration (1-based), default 2")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")

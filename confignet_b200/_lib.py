@@ -93,7 +93,7 @@ SIGNATURES = {
     "cn_norm_latent_loss_bwd": [_V, _V, _I, _I, _I, _f, _V, _V, _V, _V],
 }
 NO_STATUS = {"cn_last_error": ctypes.c_char_p, "cn_version": ctypes.c_int, "cn_reduce_ws_floats": ctypes.c_int,
-             "cn_launch_count": ctypes.c_longlong, "cn_launch_count_add": ctypes.c_longlong, "cn_last_conv_impl": ctypes.c_int}
+             "cn_launch_count": ctypes.c_longlong, "cn_params_epoch": ctypes.c_longlong, "cn_launch_count_add": ctypes.c_longlong, "cn_last_conv_impl": ctypes.c_int}
 
 _lib = None
 
@@ -115,6 +115,7 @@ def load():
     if hasattr(lib, "cn_launch_count_add"):
         lib.cn_launch_count_add.argtypes = [ctypes.c_longlong]
     lib.cn_launch_count.argtypes = [ctypes.c_int]
+    lib.cn_params_epoch.argtypes = [ctypes.c_void_p]
     for name, restype in NO_STATUS.items():
         if not hasattr(lib, name) and os.environ.get("CN_ALLOW_PARTIAL") == "1":
             continue

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import netspec, networks, ops
-from .runtime import ParamGroup, Network, KerasAdam, StepGraphs, shard_rows, world
+from .runtime import ParamGroup, Network, KerasAdam, StepGraphs, InferenceGraphs, shard_rows, world
 
 DEFAULT_CONFIG = {
     "model_type": None,
@@ -176,6 +176,7 @@ class ConfigNetFirstStage(StepGraphs):
         self._seed = seed
 
         self._graphs = {}                 # step name -> (optimizer, runtime.GraphedFn)
+        self._infer = InferenceGraphs()   # captured generate_images per (network, batch)
         self.generator = None
         self.generator_smoothed = None
         self.discriminator = None
@@ -367,33 +368,12 @@ class ConfigNetFirstStage(StepGraphs):
         eye_masks = self._take_rows(dataset.eye_masks, idxs)
         return facemodel_params, render_rotations, gt_imgs, eye_masks
 
-    # ---------------------------------------------------------------- host -> device staging
-    h2d_bytes = 0       # bytes copied host->device by the staging helpers (bench.py reads and resets it)
-
+    # ---------------------------------------------------------------- host -> device staging (runtime.StepGraphs._to_device)
     def _take_rows(self, store, idxs):
         if isinstance(store, torch.Tensor):
-            return store[torch.as_tensor(idxs, device=store.device)]
+            # device-resident store: the row indices go up like every other input (pinned, side stream, no host sync)
+            return store.index_select(0, self._to_device(np.asarray(idxs, np.int64), torch.int64, count=False))
         return np.copy(store[idxs])
-
-    def _to_device(self, arr, dtype):
-        if isinstance(arr, torch.Tensor):
-            return arr.to(self.device, dtype)
-        arr = np.ascontiguousarray(arr)
-        if not arr.flags.writeable:            # a slice of the dataset's read-only np.memmap (neural_renderer_dataset.py:346)
-            arr = np.array(arr)
-        t = torch.from_numpy(arr)
-        ConfigNetFirstStage.h2d_bytes += t.numel() * t.element_size()
-        if self.device.type != "cuda":
-            return t.to(self.device).to(dtype)
-        # pinned staging + copy on a side stream: the next step's batch goes up while the current step computes
-        if getattr(self, "_upload_stream", None) is None:
-            self._upload_stream = torch.cuda.Stream(self.device)
-        cur = torch.cuda.current_stream(self.device)
-        with torch.cuda.stream(self._upload_stream):
-            d = t.pin_memory().to(self.device, non_blocking=True)
-        cur.wait_stream(self._upload_stream)
-        d.record_stream(cur)
-        return d.to(dtype)
 
     def _upload_images(self, imgs_u8, flip=None):
         """uint8 (B,H,W,3) batch -> float32 [-1,1] device tensor; optional per-image left-right flip."""
@@ -652,11 +632,27 @@ class ConfigNetFirstStage(StepGraphs):
             self.run_checkpoints(output_dir, self.last_iteration_time, aml_run=aml_run)
 
     # ---------------------------------------------------------------- evaluation
+    def _generate_u8(self, net, latent_vector, rotations):
+        """generator forward + clip + truncating uint8 cast on the device (confignet_first_stage.py:633-639).
+        latent_vector: (B, latent) or a list of 5 of them (hologan_generator.py:109-127); -> uint8 device tensor.
+        Batches up to 8 replay a captured graph (runtime.InferenceGraphs)."""
+        dev = self.device
+        if isinstance(latent_vector, (list, tuple)):
+            zs = [networks._as_dev(z, dev) for z in latent_vector]
+        else:
+            zs = [networks._as_dev(latent_vector, dev)] * 5
+        rot = networks._as_dev(rotations, dev).reshape(-1, 3)
+        if self.config.get("cuda_graphs", True):
+            return self._infer.run(net, zs, rot)
+        return InferenceGraphs._eager(net, zs, rot)
+
     def generate_images(self, latent_vector, rotations):
         """confignet_first_stage.py:633-639 -> uint8 (B,H,W,3)."""
-        d = self.generator.build_input_dict(latent_vector, rotations)
-        imgs = self.generator_smoothed.predict(d)
-        return ops.to_uint8(imgs).cpu().numpy()
+        return self._generate_u8(self.generator_smoothed, latent_vector, rotations).cpu().numpy()
+
+    def generate_images_device(self, latent_vector, rotations):
+        """generate_images with device tensors in and a uint8 device tensor out (no host round trip)"""
+        return self._generate_u8(self.generator_smoothed, latent_vector, rotations)
 
     def generate_images_from_facemodel(self, facemodel_params, rotations):
         with torch.no_grad():

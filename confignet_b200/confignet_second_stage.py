@@ -290,9 +290,11 @@ class ConfigNet(ConfigNetFirstStage):
 
     def generate_images(self, latent_vectors, rotations):
         """confignet_second_stage.py:310-319 -> uint8 (B,H,W,3)."""
-        d = self.generator.build_input_dict(latent_vectors, rotations)
+        return self.generate_images_device(latent_vectors, rotations).cpu().numpy()
+
+    def generate_images_device(self, latent_vectors, rotations):
         net = self.generator_fine_tuned if self.generator_fine_tuned is not None else self.generator_smoothed
-        return ops.to_uint8(net.predict(d)).cpu().numpy()
+        return self._generate_u8(net, latent_vectors, rotations)
 
     def fine_tune_on_img(self, input_images, n_iters=50, img_output_dir=None, force_neutral_expression=False):
         """confignet_second_stage.py:321-403.  One shared fine-tuned generator and shared pre/post-expression

@@ -1887,6 +1887,11 @@ void cn_mark_params_changed(const void* p) {
   if (r) ++r->epoch;
 }
 extern "C" int cn_params_changed(const void* p) { cn_mark_params_changed(p); return CN_OK; }
+extern "C" long long cn_params_epoch(const void* p) {
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  ParamRange* r = find_range_locked(p);
+  return r ? (long long)(r->epoch + g_cn_weight_epoch) : -1;
+}
 extern "C" int cn_set_params_frozen(const void* p, int frozen) {
   std::lock_guard<std::mutex> lock(g_plan_mutex);
   ParamRange* r = find_range_locked(p);

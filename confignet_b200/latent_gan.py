@@ -107,11 +107,12 @@ class LatentGAN(StepGraphs):
         latent_vectors = self.sample_input_latent_vector(B).astype(np.float32)
         real_idxs = np.random.randint(0, gt_embeddings.shape[0], B)
         latent_vectors, real_idxs = self._rank_rows(latent_vectors, real_idxs)
-        if isinstance(gt_embeddings, torch.Tensor):
-            real = gt_embeddings[torch.as_tensor(real_idxs, device=gt_embeddings.device)].to(self.device, torch.float32)
+        if isinstance(gt_embeddings, torch.Tensor):         # embedding store in HBM: only the row indices go up
+            idx_d = self._to_device(np.asarray(real_idxs, np.int64), torch.int64, count=False)
+            real = gt_embeddings.index_select(0, idx_d).to(self.device, torch.float32)
         else:
-            real = networks._as_dev(gt_embeddings[real_idxs], self.device)
-        latent_d = networks._as_dev(latent_vectors, self.device)
+            real = self._to_device(np.asarray(gt_embeddings[real_idxs], np.float32), torch.float32)
+        latent_d = self._to_device(latent_vectors, torch.float32)
         optimizer.begin_step(self.device)
         nl = self.config["num_mlp_layers"]
 
@@ -136,7 +137,7 @@ class LatentGAN(StepGraphs):
         """latent_gan.py:151-165."""
         latents = self.sample_input_latent_vector(self.config["batch_size"]).astype(np.float32)
         latents, = self._rank_rows(latents)
-        latent_d = networks._as_dev(latents, self.device)
+        latent_d = self._to_device(latents, torch.float32)
         optimizer.begin_step(self.device)
         nl = self.config["num_mlp_layers"]
 

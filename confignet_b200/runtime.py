@@ -314,6 +314,70 @@ class GraphedFn:
         return OrderedDict((k, v.clone()) for k, v in self.static_out.items())
 
 
+class InferenceGraphs:
+    """The small-batch evaluation path (generate_images at batch 1-6 in the demo loop,
+    evaluation/confignet_demo.py:154-160; the controllability sweep, metrics/metrics.py:98-102): one captured CUDA graph
+    per (generator network, batch size) - ~45 launches replayed as one - whose packed kernels are the ones of the eager
+    warm-up call (the buffer is declared frozen for the capture, so the graph holds no pack launches).  The graph is
+    re-captured when the network's change counter has moved (training, EMA, set_weights)."""
+    MAX_BATCH = 8
+
+    def __init__(self):
+        self.cache = {}
+
+    def clear(self):
+        self.cache.clear()
+
+    @staticmethod
+    def _eager(net, zs, rot):
+        keys = ("z_3d_0", "z_3d_1", "z_2d_0", "z_2d_1", "z_2d_2")
+        d = dict(zip(keys, zs))
+        d["rotation"] = rot
+        return ops.to_uint8(net.predict(d))
+
+    def run(self, net, zs, rot):
+        """zs: 5 device tensors (B, latent); rot: (B, 3) device tensor of Euler angles -> uint8 (B, H, W, 3) device tensor"""
+        B = zs[0].shape[0]
+        if not GraphedFn.ENABLED or B > self.MAX_BATCH or ops.PROFILE[0] is not None or not zs[0].is_cuda:
+            return self._eager(net, zs, rot)
+        flat = net.group.flat
+        epoch = int(L.load().cn_params_epoch(ops._p(flat)))
+        key = (id(net.group), B, zs[0].shape[1])
+        e = self.cache.get(key)
+        if e is None or e["epoch"] != epoch:
+            if e is not None and e.get("failed"):
+                return self._eager(net, zs, rot)
+            try:
+                s_zs = [z.clone() for z in zs]
+                s_rot = rot.clone()
+                self._eager(net, s_zs, s_rot)                      # plans, buffers and the packed kernels of the CURRENT weights
+                torch.cuda.synchronize()
+                frozen = net.group.frozen
+                L.call("cn_set_params_frozen", ops._p(flat), 1)
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        out = self._eager(net, s_zs, s_rot)
+                finally:
+                    L.call("cn_set_params_frozen", ops._p(flat), 1 if frozen else 0)
+                L.call("cn_graphs_captured")
+                e = self.cache[key] = dict(graph=g, zs=s_zs, rot=s_rot, out=out, epoch=epoch)
+            except Exception as ex:                                  # pragma: no cover - depends on the driver
+                torch.cuda.synchronize()
+                self.cache[key] = dict(failed=True, epoch=epoch)
+                import warnings
+                warnings.warn("CUDA-graph capture of generate_images failed (%s); running eagerly" % (str(ex)[:200],))
+                return self._eager(net, zs, rot)
+        if e.get("failed"):
+            return self._eager(net, zs, rot)
+        for s, z in zip(e["zs"], zs):
+            if s.data_ptr() != z.data_ptr():
+                s.copy_(z, non_blocking=True)
+        e["rot"].copy_(rot, non_blocking=True)
+        e["graph"].replay()
+        return e["out"].clone()
+
+
 def release_graphs():
     """Drops every captured step graph of this process (their private memory pools go back to the allocator)."""
     for g in list(GraphedFn._live):
@@ -325,10 +389,35 @@ def release_graphs():
         torch.cuda.synchronize()
 
 
+H2D_BYTES = [0]        # bytes staged host -> device by StepGraphs._to_device (bench.py reads and resets it)
+
+
 class StepGraphs:
     """What the model classes share around an optimizer step: tape.gradient + packing, the eager whole step, the
     CUDA-graph wrapper per step, global loss values under data parallelism.  Expects ``self._graphs`` (dict),
     ``self.config`` and ``self.device``."""
+
+    def _to_device(self, arr, dtype, count=True):
+        """host array -> device tensor of `dtype`: pinned staging + copy on a side stream, so the next step's batch goes
+        up while the current step computes and the host never blocks on a pageable copy."""
+        if isinstance(arr, torch.Tensor):
+            return arr.to(self.device, dtype)
+        arr = np.ascontiguousarray(arr)
+        if not arr.flags.writeable:            # a slice of the dataset's read-only np.memmap (neural_renderer_dataset.py:346)
+            arr = np.array(arr)
+        t = torch.from_numpy(arr)
+        if count:
+            H2D_BYTES[0] += t.numel() * t.element_size()
+        if self.device.type != "cuda":
+            return t.to(self.device).to(dtype)
+        if getattr(self, "_upload_stream", None) is None:
+            self._upload_stream = torch.cuda.Stream(self.device)
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._upload_stream):
+            d = t.pin_memory().to(self.device, non_blocking=True)
+        cur.wait_stream(self._upload_stream)
+        d.record_stream(cur)
+        return d.to(dtype)
 
     def _backward(self, loss, nets):
         """tape.gradient(loss, trainable_weights) for the networks of one optimizer step, packed into their flat
@@ -374,7 +463,8 @@ class StepGraphs:
         if entry is None or entry[0] is not optimizer:
             # a new optimizer object (a second train() call): its moment buffers and learning-rate scalar are not the
             # ones the old graph captured - drop that graph (and its memory pool) and start over
-            entry = self._graphs[name] = (optimizer, GraphedFn(fn, finish, groups, reduce_groups=rgroups))
+            entry = self._graphs[name] = (optimizer, GraphedFn(fn, finish, groups, warm=int(self.config.get("cuda_graph_warmup", 2)),
+                                                               reduce_groups=rgroups))
         return entry[1]
 
     def drop_graphs(self):
@@ -382,6 +472,8 @@ class StepGraphs:
         for _, g in self._graphs.values():
             g.release()
         self._graphs.clear()
+        if getattr(self, "_infer", None) is not None:
+            self._infer.clear()
 
     def close(self):
         """release the captured step graphs and their memory pools (call before tearing the process group down)"""

@@ -57,6 +57,8 @@ int cn_register_params(const void* base, size_t bytes);
 int cn_unregister_params(const void* base);
 int cn_params_changed(const void* base);
 int cn_set_params_frozen(const void* base, int frozen);
+/* the buffer's change counter (-1: not registered): a caller that captured a graph over frozen images re-captures when it moves */
+long long cn_params_epoch(const void* base);
 int cn_weights_changed(void);
 /* call once a CUDA graph has been captured over this library's launches: internal scratch / cache buffers are then
  * never freed (a graph may still reference them), growth abandons the old buffer instead */

@@ -518,6 +518,27 @@ class OracleFirstStage:
         self.d_opt.apply_gradients(zip(grads_of(losses["loss_sum"], self.p_d), self.p_d.values()))
         return losses
 
+    def synth_discriminator_step(self, real_u8, facemodel_params, rotations):
+        """synth_discriminator_training_step confignet_first_stage.py:452-464,478-488 (shared discriminator optimizer)"""
+        real = self._t(real_u8) / 127.5 - 1.0
+        losses = synth_discriminator_step_losses(self.p_sd, self.p_g, self.p_se, self.fm, real,
+                                                 [self._t(a) for a in facemodel_params], self._t(rotations), self.res)
+        self.d_opt.apply_gradients(zip(grads_of(losses["loss_sum"], self.p_sd), self.p_sd.values()))
+        return losses
+
+    def latent_discriminator_step(self, real_latents, facemodel_params):
+        """latent_discriminator_training_step confignet_first_stage.py:490-504 (shared discriminator optimizer)"""
+        losses = latent_discriminator_step_losses(self.p_ld, self.p_se, self.fm, self._t(real_latents),
+                                                  [self._t(a) for a in facemodel_params])
+        self.d_opt.apply_gradients(zip(grads_of(losses["loss_sum"], self.p_ld), self.p_ld.values()))
+        return losses
+
+    def generate_images(self, latents, rotations):
+        """generate_images confignet_first_stage.py:633-639: smoothed generator, clip, truncating uint8 cast"""
+        with torch.no_grad():
+            imgs = generator_forward(self.p_gs, self._t(latents), self._t(rotations), self.res)
+        return to_uint8_images(imgs.numpy())
+
     def generator_step(self, facemodel_params, synth_rot, gt_u8, eye_masks, real_latents, real_rot):
         batch = dict(facemodel_params=[self._t(a) for a in facemodel_params], synth_rotations=self._t(synth_rot),
                      gt_imgs=self._t(gt_u8) / 127.5 - 1.0, eye_masks=eye_masks, real_latents=self._t(real_latents),

@@ -6,6 +6,7 @@ torch-CPU restatement of the second-stage / fine-tuning / LatentGAN pieces of th
   vggface_*                                perceptual_loss.py:26-41,54-56 (VGG16 truncated at layer 12)
   normalized_latent_regression_loss        confignet_second_stage.py:93-107
   stage2_generator_step_losses             confignet_second_stage.py:149-218
+  stage2_discriminator_step_losses         confignet_first_stage.py:466-476 + confignet_second_stage.py:119-130
   stage2_latent_discriminator_step_losses  confignet_second_stage.py:132-147
   fine_tune_losses                         confignet_second_stage.py:360-390
   latent_gan_*                             latent_gan.py:117-165
@@ -132,6 +133,16 @@ def normalized_regression(out, labels, weight):
     return ((lab_n - out_n) ** 2).mean(dim=-1).mean() * weight
 
 
+def stage2_discriminator_step_losses(p_d, p_g, p_enc, real_imgs, input_imgs, output_res=256):
+    """discriminator_training_step of ConfigNet: confignet_first_stage.py:466-470 over the overridden
+    get_discriminator_batch (confignet_second_stage.py:119-130) - the fakes are reconstructions of encoded training
+    images, generator(encode_images(input_imgs)), built outside the tape."""
+    with torch.no_grad():
+        latent, rotation = real_encoder_forward(p_enc, input_imgs)
+        fake = O.generator_forward(p_g, latent, rotation, output_res)
+    return O.compute_discriminator_loss(p_d, real_imgs, fake)
+
+
 def stage2_latent_discriminator_step_losses(p_ld, p_enc, p_se, facemodel_inputs, real_imgs, facemodel_params):
     """latent_discriminator_training_step confignet_second_stage.py:132-147: real latents come from the encoder."""
     with torch.no_grad():
@@ -220,3 +231,87 @@ def latent_gan_generator_losses(p_d, p_g, input_latents, num_layers=3):
     losses["gan_loss"] = O.gan_g_loss(latent_gan_mlp(p_d, latent_gan_mlp(p_g, input_latents, num_layers), num_layers))
     losses["loss_sum"] = sum(losses.values())
     return losses
+
+
+# ----------------------------------------------------------------------------- whole iterations (CPU baselines of bench.py)
+class OracleSecondStage(O.OracleFirstStage):
+    """CPU restatement of the second-stage step loop (confignet_second_stage.py:119-218,268-299) on the first-stage
+    networks plus the RealEncoder; same step functions as the parity tests, torch-CPU fp32: the timed CPU baseline of
+    bench.py --config 4 and (fine_tune) --config 5."""
+
+    def __init__(self, facemodel_inputs, output_res=256, seed=1234, dtype=torch.float32, image_loss_weight=0.0005):
+        super().__init__(facemodel_inputs, output_res, seed, dtype)
+        from confignet_b200 import netspec          # parameter tables only (pure NumPy, no CUDA)
+        enc = netspec.init_real_encoder_params(145, seed + 8)
+        self.p_enc = OrderedDict((k, torch.tensor(v, dtype=dtype, requires_grad=netspec.is_trainable(k))) for k, v in enc.items())
+        self.p_vgg16 = O.to_torch(netspec.init_params(netspec.vgg16_spec(), seed + 9, vgg_like=True), dtype=dtype)
+        self.weights = dict(O.DEFAULT_LOSS_WEIGHTS); self.weights["image_loss_weight"] = image_loss_weight
+
+    def discriminator_step(self, real_u8, input_u8):
+        losses = stage2_discriminator_step_losses(self.p_d, self.p_g, self.p_enc, self._t(real_u8) / 127.5 - 1.0,
+                                                  self._t(input_u8) / 127.5 - 1.0, self.res)
+        self.d_opt.apply_gradients(zip(O.grads_of(losses["loss_sum"], self.p_d), self.p_d.values()))
+        return losses
+
+    def latent_discriminator_step(self, real_u8, facemodel_params):
+        losses = stage2_latent_discriminator_step_losses(self.p_ld, self.p_enc, self.p_se, self.fm, self._t(real_u8) / 127.5 - 1.0,
+                                                         [self._t(a) for a in facemodel_params])
+        self.d_opt.apply_gradients(zip(O.grads_of(losses["loss_sum"], self.p_ld), self.p_ld.values()))
+        return losses
+
+    def generator_step(self, facemodel_params, synth_rot, synth_u8, eye_masks, real_u8):
+        batch = dict(facemodel_params=[self._t(a) for a in facemodel_params], synth_rotations=self._t(synth_rot),
+                     synth_imgs=self._t(synth_u8) / 127.5 - 1.0, eye_masks=eye_masks, real_imgs=self._t(real_u8) / 127.5 - 1.0)
+        losses = stage2_generator_step_losses(self.p_g, self.p_lr, self.p_se, self.p_enc, self.p_d, self.p_sd, self.p_ld, self.p_vgg,
+                                              self.fm, batch, weights=self.weights, output_res=self.res)
+        allp = OrderedDict()
+        for pre, p in (("g/", self.p_g), ("lr/", self.p_lr), ("se/", self.p_se), ("enc/", self.p_enc)):
+            for k, v in p.items():
+                if v.requires_grad:
+                    allp[pre + k] = v
+        self.g_opt.apply_gradients(zip(O.grads_of(losses["loss_sum"], allp), allp.values()))
+        O.update_smoothed_weights(self.p_gs, self.p_g)
+        return losses
+
+    def fine_tune(self, imgs_u8, n_iters):
+        """fine_tune_on_img confignet_second_stage.py:321-403: encoder prediction, shared pre/post parts from the mean
+        embedding, per-image expression part and rotations, Adam(1e-4), n_iters iterations."""
+        imgs = self._t(imgs_u8) / 127.5 - 1.0
+        with torch.no_grad():
+            e0, r0 = real_encoder_forward(self.p_enc, imgs)
+        names = list(self.fm.keys())
+        lo = sum(self.fm[n][1] for n in names[:names.index("blendshape_values")])
+        hi = lo + self.fm["blendshape_values"][1]
+        mean_e = e0.mean(dim=0, keepdim=True)
+        pre, expr, post, rots = [t.clone().requires_grad_(True) for t in (mean_e[:, :lo], e0[:, lo:hi], mean_e[:, hi:], r0)]
+        opt = O.KerasAdam(lr=1e-4, beta_1=0.9, beta_2=0.999)
+        p_ft = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in self.p_gs.items())
+        for _ in range(n_iters):
+            l = fine_tune_losses(p_ft, self.p_lr, self.p_d, self.p_ld, self.p_vgg, self.p_vgg16, imgs, pre, expr, post, rots,
+                                 weights=self.weights, output_res=self.res)
+            tv = list(p_ft.values()) + [pre, post, rots, expr]
+            gs = torch.autograd.grad(l["loss_sum"], tv, allow_unused=True)
+            opt.apply_gradients(zip([torch.zeros_like(v) if q is None else q for q, v in zip(gs, tv)], tv))
+        return l
+
+
+class OracleLatentGAN:
+    """latent_gan.py:117-174,232-247 on CPU: one discriminator step, one generator step (one optimizer), EMA."""
+
+    def __init__(self, latent_dim=145, seed=4321, dtype=torch.float32):
+        from confignet_b200 import netspec
+        mk = lambda spec, s: O.to_torch(netspec.init_params(spec, s), dtype=dtype, requires_grad=True)
+        self.p_g = mk(netspec.latent_gan_mlp_spec(latent_dim), seed)
+        self.p_d = mk(netspec.latent_gan_mlp_spec(latent_dim, num_out=1), seed + 1)
+        self.p_gs = O.to_torch({k: v.detach().numpy() for k, v in self.p_g.items()}, dtype=dtype)
+        self.opt = O.KerasAdam(lr=5e-5)
+        self.dtype = dtype
+
+    def step(self, real_embeddings, z_d, z_g):
+        t = lambda a: torch.as_tensor(np.asarray(a)).to(self.dtype)
+        ld = latent_gan_discriminator_losses(self.p_d, self.p_g, t(real_embeddings), t(z_d))
+        self.opt.apply_gradients(zip(O.grads_of(ld["loss_sum"], self.p_d), self.p_d.values()))
+        lg = latent_gan_generator_losses(self.p_d, self.p_g, t(z_g))
+        self.opt.apply_gradients(zip(O.grads_of(lg["loss_sum"], self.p_g), self.p_g.values()))
+        O.update_smoothed_weights(self.p_gs, self.p_g)
+        return ld, lg

@@ -421,6 +421,21 @@ check("s2_g", l_ref, l_orc, [(ref_weight("g", "map_3d_1/conv/kernel"), P["g"]["m
                              (m2.encoder.A, p_enc["A"]), (m2.encoder.Br, p_enc["Br"])])
 assert g_opt_ref.iterations == g_opt_orc.iterations == 2 and d_opt_ref.iterations == d_opt_orc.iterations == 4
 
+# the image-discriminator step of stage 2: the base class' discriminator_training_step (confignet_first_stage.py:466-476)
+# calls get_discriminator_batch, which ConfigNet OVERRIDES (confignet_second_stage.py:119-130): fakes are
+# generator(encode_images(training images)); NumPy stream: image rows, flips, input image rows
+S.Model.predict = lambda self, x: tuple(v.detach().numpy() for v in self(x)) if isinstance(self(x), tuple) else self(x).detach().numpy()
+np.random.seed(49)
+l_ref = m2.discriminator_training_step(real_set, d_opt_ref)
+np.random.seed(49)
+rimgs = draw_random_batch(real_set, B)
+in_idx = np.random.randint(0, real_set.imgs.shape[0], B)
+in_imgs = real_set.imgs[in_idx].astype(np.float32) / 127.5 - 1.0
+l_orc = O2.stage2_discriminator_step_losses(P["d"], P["g"], p_enc, T64(rimgs), T64(in_imgs), output_res=RES)
+d_opt_orc.apply_gradients(zip(O.grads_of(l_orc["loss_sum"], P["d"]), P["d"].values()))
+check("s2_d", l_ref, l_orc, [(ref_weight("d", n), P["d"][n]) for n in ("block0/conv/kernel", "block3/in/gamma", "style2/kernel")])
+assert d_opt_ref.iterations == d_opt_orc.iterations == 5
+
 # ------------------------------------------------------------------------------------------------ fine_tune_on_img (confignet_second_stage.py:321-403)
 # Two iterations on two images: the embedding slicing (shared pre/post-expression parts from the MEAN embedding,
 # per-image expression part), the loss terms, the list of trained variables and Adam(lr=1e-4, Keras defaults).  The two

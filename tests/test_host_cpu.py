@@ -1168,6 +1168,16 @@ def test_oracle_steps_match_reference_steps():
             check("s2_g", l, [P["g"]["map_3d_1/conv/kernel"], P["g"]["map_final/kernel"], P["lr"]["latent_predictor/bias"],
                               P["se"]["mlp_blendshape_values/dense1/kernel"], p_enc["A"], p_enc["Br"]])
             assert g_opt.iterations == 2 and d_opt.iterations == 4
+            # ---- the stage-2 image-discriminator step: the base discriminator_training_step over ConfigNet's overridden
+            #      get_discriminator_batch (confignet_second_stage.py:119-130) - fakes = generator(encoder(training images))
+            np.random.seed(49)
+            rimgs = random_batch(real_set, B)
+            in_idx = np.random.randint(0, N, B)
+            in_imgs = real_set.imgs[in_idx].astype(np.float32) / 127.5 - 1.0
+            l = O2s.stage2_discriminator_step_losses(P["d"], P["g"], p_enc, T64(rimgs), T64(in_imgs), output_res=RES)
+            d_opt.apply_gradients(zip(O.grads_of(l["loss_sum"], P["d"]), P["d"].values()))
+            check("s2_d", l, [P["d"][n] for n in ("block0/conv/kernel", "block3/in/gamma", "style2/kernel")])
+            assert d_opt.iterations == 5
             # ---- ConfigNet.fine_tune_on_img (confignet_second_stage.py:321-403), 2 iterations on 2 images, asymmetric
             #      stand-ins for the two perceptual networks (see the generating script)
             saved_fr = O2s.face_reco_loss

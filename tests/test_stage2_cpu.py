@@ -152,3 +152,54 @@ def test_batch_statistics_loss_under_data_parallelism(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_stage2_step_host_halves_consume_the_reference_stream():
+    """Host halves of the stage-2 steps on a CPU model with the device halves recorded instead of run.  ConfigNet's
+    discriminator step must use ConfigNet's batch assembly (confignet_second_stage.py:119-130: image rows, flips, INPUT
+    image rows for the encoder -> generator reconstructions), not stage 1's prior samples (an inherited stage-1 step
+    would draw latents and rotations instead and leave the NumPy stream somewhere else)."""
+    from confignet_b200.confignet_second_stage import ConfigNet
+    from confignet_b200.confignet_first_stage import ConfigNetFirstStage
+    from confignet_b200.runtime import KerasAdam
+    from confignet_b200.synthetic_data import SyntheticDataset
+    assert ConfigNet.discriminator_training_step is not ConfigNetFirstStage.discriminator_training_step
+    B, res = 4, 16
+    m = ConfigNet({"output_shape": (res, res, 3), "batch_size": B, "facemodel_inputs": netspec.default_facemodel_inputs()},
+                  initialize=False, device="cpu")
+    rec = []
+    m._graphed = lambda name, opt, fn, nets, **kw: (lambda *t: (rec.append((name, [x.clone() for x in t], kw)), OrderedDict(loss_sum=torch.zeros(())))[1])
+    real, synth = SyntheticDataset(9, res, seed=1), SyntheticDataset(7, res, seed=2)
+    opt = KerasAdam()
+    m.discriminator = m.latent_discriminator = m.generator = m.latent_regressor = m.synthetic_encoder = m.encoder = None
+
+    np.random.seed(3)
+    m.discriminator_training_step(real, opt)
+    after = np.random.randint(0, 1 << 30)
+    np.random.seed(3)
+    idx = np.random.randint(0, 9, B); flips = np.random.randint(0, 2, size=B); in_idx = np.random.randint(0, 9, B)
+    assert np.random.randint(0, 1 << 30) == after                      # nothing else was drawn
+    name, t, kw = rec[-1]
+    assert name == "d2" and opt.iterations == 1
+    assert np.array_equal(t[0].numpy(), real.imgs[idx]) and np.array_equal(t[1].numpy(), flips.astype(bool))
+    assert np.array_equal(t[2].numpy(), real.imgs[in_idx])
+
+    np.random.seed(4)
+    m.latent_discriminator_training_step(real, synth, opt)
+    np.random.seed(4)
+    idx = np.random.randint(0, 9, B); flips = np.random.randint(0, 2, size=B); sidx = np.random.randint(0, 7, B)
+    name, t, kw = rec[-1]
+    assert name == "latent_d2" and opt.iterations == 2
+    assert np.array_equal(t[0].numpy(), real.imgs[idx]) and np.array_equal(t[1].numpy(), flips.astype(bool))
+    for x, n in zip(t[2:], netspec.default_facemodel_inputs().keys()):
+        assert np.array_equal(x.numpy(), synth.metadata_inputs[n][sidx])
+
+    np.random.seed(5)
+    m.generator_training_step(real, synth, opt)
+    np.random.seed(5)
+    sidx = np.random.randint(0, 7, B // 2); ridx = np.random.randint(0, 9, B - B // 2); rflips = np.random.randint(0, 2, size=B - B // 2)
+    name, t, kw = rec[-1]
+    assert name == "g2" and kw.get("dp_ok") is False                   # the all-gathered batch-statistics loss is not capturable under DP
+    assert np.array_equal(t[0].numpy(), synth.imgs[sidx]) and np.array_equal(t[1].numpy(), synth.eye_masks[sidx].astype(np.float32))
+    assert np.array_equal(t[2].numpy(), real.imgs[ridx]) and np.array_equal(t[3].numpy(), rflips.astype(bool))
+    assert np.array_equal(t[4].numpy(), synth.metadata_inputs["rotations"][sidx])

@@ -1,0 +1,502 @@
+"""-m gpu: the CLASS-SURFACE training steps - the very methods train() and bench.py call - against the CPU oracle.
+
+Each test builds the product model, gives every network perturbed seeded weights, and walks a few training iterations.
+Before every step the oracle (fp64) receives the model's CURRENT weights and the same NumPy draws (replayed here in the
+reference's draw order), so every step is compared from identical state ("teacher forcing" - B = 4 on untrained
+networks is chaotic after one Adam sign-step, a free-running comparison would only measure that):
+
+  * every loss term of the step                      <= 1e-3 relative (the north-star bar)
+  * the packed flat gradient the optimizer consumed  <= 3e-2 relative L2 per variable (see test_networks_gpu.py)
+  * the weights after the step == Keras-Adam [TF-2.1] applied in fp64 to (weights before, THAT gradient, moments before,
+    the optimizer's shared iteration count)          <= 2e-7 absolute: pack_grads offsets, the device learning rate, the
+                                                        1/world scale and the fused kernel are pinned exactly
+  * the EMA of the generator (confignet_first_stage.py:393-400) <= 1e-7
+
+The steps run with CUDA graphs on (eager call, captured call, replayed call = iterations 1, 2, 3) and a second model
+runs the same seeds without graphs: with the deterministic reductions of csrc/ both must agree BIT FOR BIT in every
+loss and every final weight."""
+from collections import OrderedDict
+import math
+import numpy as np
+import pytest
+import torch
+
+from confignet_b200 import netspec
+from oracle import confignet_oracle as O
+from oracle import confignet_oracle_stage2 as O2
+from parity_utils import l2err
+
+pytestmark = pytest.mark.gpu
+FM = netspec.default_facemodel_inputs()
+RES, B = 256, 4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def perturb(model, nets, seed):
+    """seeded noise on every trainable network (zero biases, unit gammas and the learned input get exercised)"""
+    for i, name in enumerate(nets):
+        net = getattr(model, name)
+        arrays = OrderedDict(zip(net.group.names, net.group.get_weights()))
+        keep = {k: v for k, v in arrays.items() if k.endswith("moving_variance") or k.endswith("moving_mean")}
+        arrays = netspec.perturb_params(arrays, seed + i, 0.05)
+        arrays.update(keep)
+        net.group.set_weights([arrays[k] for k in net.group.names])
+
+
+def oracle_params(group):
+    """fp64 leaf tensors holding the group's current weights (frozen variables do not require grad)"""
+    w = group.get_weights()
+    train = set() if group.frozen else set(group.names[i] for i in group._train_idx)
+    return OrderedDict((k, torch.tensor(a, dtype=torch.float64, requires_grad=(k in train))) for k, a in zip(group.names, w))
+
+
+def T(a):
+    return torch.as_tensor(np.asarray(a)).to(torch.float64)
+
+
+def ref_grads(loss, param_dicts):
+    """tape.gradient(loss, trainable weights of several networks): one backward pass -> one name->gradient dict per network"""
+    trainable = [OrderedDict((k, v) for k, v in p.items() if v.requires_grad) for p in param_dicts]
+    flat = [v for p in trainable for v in p.values()]
+    gs = torch.autograd.grad(loss, flat, allow_unused=True)
+    out, i = [], 0
+    for p in trainable:
+        d = OrderedDict()
+        for k, v in p.items():
+            d[k] = torch.zeros_like(v) if gs[i] is None else gs[i]
+            i += 1
+        out.append(d)
+    return out
+
+
+def rotations(n, ranges=((-30, 30), (-10, 10), (0, 0))):
+    """sample_rotations (confignet_first_stage.py:402-409): one uniform draw per axis"""
+    r = np.zeros((n, 3))
+    for ax in range(3):
+        r[:, ax] = np.pi * np.random.uniform(ranges[ax][0], ranges[ax][1], n) / 180
+    return r.astype(np.float32)
+
+
+def flipped_rows(ds, n):
+    """rows + flip_random_subset_of_images (confignet_first_stage.py:440-443, confignet_utils.py:198-204)"""
+    idx = np.random.randint(0, ds.imgs.shape[0], n)
+    flips = np.random.randint(0, 2, size=n)
+    imgs = ds.imgs[idx].astype(np.float64) / 127.5 - 1.0
+    for i in range(n):
+        if flips[i]:
+            imgs[i] = imgs[i][:, ::-1]
+    return imgs
+
+
+def synth_rows(ds, n):
+    """sample_synthetic_dataset (confignet_first_stage.py:425-435)"""
+    idx = np.random.randint(0, ds.imgs.shape[0], n)
+    return ([ds.metadata_inputs[k][idx] for k in FM.keys()], ds.metadata_inputs["rotations"][idx].astype(np.float32),
+            ds.imgs[idx].astype(np.float64) / 127.5 - 1.0, ds.eye_masks[idx])
+
+
+class StepCheck:
+    """snapshot before a step, comparison after it"""
+
+    def __init__(self, groups, opt):
+        self.groups, self.opt = groups, opt
+        self.t = opt.iterations + 1
+        self.w0 = [g.flat.detach().clone() for g in groups]
+        st = [opt.state.get(id(g)) for g in groups]
+        self.m0 = [None if s is None else s[0].clone() for s in st]
+        self.v0 = [None if s is None else s[1].clone() for s in st]
+
+    def check(self, losses, l_ref, g_ref_dicts, tag, loss_tol=1e-3, grad_tol=3e-2):
+        assert list(losses.keys()) == list(l_ref.keys()), (tag, list(losses.keys()), list(l_ref.keys()))
+        for k in l_ref:
+            a, b = float(losses[k]), float(l_ref[k])
+            assert abs(a - b) <= loss_tol * max(1.0, abs(b)), "%s %s: %.7g vs oracle %.7g" % (tag, k, a, b)
+        o = self.opt
+        assert o.iterations == self.t, (tag, o.iterations, self.t)
+        lr_t = np.float32(o.lr * math.sqrt(1 - o.b2 ** self.t) / (1 - o.b1 ** self.t))
+        worst = 0.0
+        for g, w0, m0, v0, g_ref in zip(self.groups, self.w0, self.m0, self.v0, g_ref_dicts):
+            grad = g.grad.detach().double().cpu().numpy()
+            # (1) the gradient the optimizer consumed, per variable, against the oracle's
+            top = max(float(v.double().norm()) for v in g_ref.values())
+            for i in g._train_idx:
+                name, off, n = g.names[i], g.offsets[i], g.sizes[i]
+                ref = g_ref[name].detach().numpy().reshape(-1)
+                if np.linalg.norm(ref) < 1e-3 * top:
+                    continue                      # cancellation noise (e.g. conv biases in front of an InstanceNorm), see parity_utils
+                e = np.linalg.norm(grad[off:off + n] - ref) / np.linalg.norm(ref)
+                worst = max(worst, e)
+                assert e <= grad_tol, "%s gradient of %s: relative L2 %.3e > %.1e" % (tag, name, e, grad_tol)
+            # (2) Keras Adam on exactly that gradient
+            w0 = w0.double().cpu().numpy()
+            m0 = np.zeros_like(w0) if m0 is None else m0.double().cpu().numpy()
+            v0 = np.zeros_like(w0) if v0 is None else v0.double().cpu().numpy()
+            m1 = o.b1 * m0 + (1 - o.b1) * grad
+            v1 = o.b2 * v0 + (1 - o.b2) * grad * grad
+            want = w0 - float(lr_t) * m1 / (np.sqrt(v1) + o.eps)
+            mask = np.zeros(w0.shape, bool)
+            for i in range(len(g.names)):
+                if i in g._train_idx:
+                    mask[g.offsets[i]:g.offsets[i] + g.sizes[i]] = True
+            want = np.where(mask, want, w0)       # non-trainable variables (BatchNorm moving statistics) and padding stay
+            got = g.flat.detach().double().cpu().numpy()
+            d = np.abs(got - want).max()
+            assert d <= 2e-7, "%s: weights after the step differ from Keras-Adam on the packed gradient by %.3e" % (tag, d)
+        return worst
+
+
+def cfg(graphs):
+    return {"output_shape": (RES, RES, 3), "batch_size": B, "facemodel_inputs": FM, "cuda_graphs": graphs,
+            "cuda_graph_warmup": 1}
+
+
+def flat_weights(model, nets):
+    return {n: getattr(model, n).group.flat.detach().cpu().numpy().copy() for n in nets}
+
+
+# ------------------------------------------------------------------------------------------------ stage 1
+STAGE1_NETS = ["synthetic_encoder", "discriminator", "synth_discriminator", "latent_discriminator", "latent_regressor", "generator"]
+
+
+def run_stage1(dev, graphs, with_oracle, n_iters=3):
+    from confignet_b200.confignet_first_stage import ConfigNetFirstStage
+    from confignet_b200.runtime import KerasAdam
+    from confignet_b200.synthetic_data import SyntheticDataset
+    model = ConfigNetFirstStage(cfg(graphs), device=dev)
+    perturb(model, STAGE1_NETS, 500)
+    model.generator_smoothed.group.copy_from(model.generator.group)
+    real, synth = SyntheticDataset(10, RES, seed=1), SyntheticDataset(10, RES, seed=2)
+    d_opt, g_opt = KerasAdam(**model.config["optimizer"]), KerasAdam(**model.config["optimizer"])
+    p_vgg = oracle_params(model.perceptual_loss.group) if with_oracle else None
+    hist, worst = [], {}
+    grp = lambda n: getattr(model, n).group
+
+    def P(*names):
+        return [oracle_params(grp(n)) for n in names]
+
+    for it in range(n_iters):
+        seed = 1000 + 10 * it
+        # ---- discriminator_training_step (confignet_first_stage.py:438-450,466-476)
+        chk = StepCheck([grp("discriminator")], d_opt)
+        if with_oracle:
+            p_d, p_g = P("discriminator", "generator")
+            np.random.seed(seed)
+            real_imgs = flipped_rows(real, B)
+            lat = np.random.normal(0, 1, (B, 145)).astype(np.float32)
+            rot = rotations(B)
+            l_ref = O.discriminator_step_losses(p_d, p_g, T(real_imgs), T(lat), T(rot), RES)
+            g_ref = ref_grads(l_ref["loss_sum"], [p_d])
+        np.random.seed(seed)
+        l = model.discriminator_training_step(real, d_opt)
+        hist.append([float(v) for v in l.values()])
+        if with_oracle:
+            worst["d%d" % it] = chk.check(l, l_ref, g_ref, "D step, iteration %d" % (it + 1))
+        # ---- synth_discriminator_training_step (:452-464,478-488)
+        chk = StepCheck([grp("synth_discriminator")], d_opt)
+        if with_oracle:
+            p_sd, p_g, p_se = P("synth_discriminator", "generator", "synthetic_encoder")
+            np.random.seed(seed + 1)
+            real_imgs = flipped_rows(synth, B)
+            fm_p, srot, _, _ = synth_rows(synth, B)
+            l_ref = O.synth_discriminator_step_losses(p_sd, p_g, p_se, FM, T(real_imgs), [T(a) for a in fm_p], T(srot), RES)
+            g_ref = ref_grads(l_ref["loss_sum"], [p_sd])
+        np.random.seed(seed + 1)
+        l = model.synth_discriminator_training_step(synth, d_opt)
+        hist.append([float(v) for v in l.values()])
+        if with_oracle:
+            worst["sd%d" % it] = chk.check(l, l_ref, g_ref, "synth-D step, iteration %d" % (it + 1))
+        # ---- latent_discriminator_training_step (:490-504): the SAME optimizer object (shared iteration count)
+        chk = StepCheck([grp("latent_discriminator")], d_opt)
+        if with_oracle:
+            p_ld, p_se = P("latent_discriminator", "synthetic_encoder")
+            np.random.seed(seed + 2)
+            real_lat = np.random.normal(0, 1, (B, 145)).astype(np.float32)
+            fm_p, _, _, _ = synth_rows(synth, B)
+            l_ref = O.latent_discriminator_step_losses(p_ld, p_se, FM, T(real_lat), [T(a) for a in fm_p])
+            g_ref = ref_grads(l_ref["loss_sum"], [p_ld])
+        np.random.seed(seed + 2)
+        l = model.latent_discriminator_training_step(synth, d_opt)
+        hist.append([float(v) for v in l.values()])
+        if with_oracle:
+            worst["ld%d" % it] = chk.check(l, l_ref, g_ref, "latent-D step, iteration %d" % (it + 1),
+                                           loss_tol=1e-4, grad_tol=1e-3)
+        assert d_opt.iterations == 3 * (it + 1)
+        # ---- generator_training_step (:506-560)
+        gnames = ["generator", "latent_regressor", "synthetic_encoder"]
+        chk = StepCheck([grp(n) for n in gnames], g_opt)
+        if with_oracle:
+            p_g, p_lr, p_se, p_d, p_sd, p_ld = P("generator", "latent_regressor", "synthetic_encoder", "discriminator",
+                                                  "synth_discriminator", "latent_discriminator")
+            np.random.seed(seed + 3)
+            fm_p, srot, gt, masks = synth_rows(synth, B // 2)
+            real_lat = np.random.normal(0, 1, (B - B // 2, 145)).astype(np.float32)
+            real_rot = rotations(B - B // 2)
+            batch = dict(facemodel_params=[T(a) for a in fm_p], synth_rotations=T(srot), gt_imgs=T(gt), eye_masks=masks,
+                         real_latents=T(real_lat), real_rotations=T(real_rot))
+            l_ref = O.generator_step_losses(p_g, p_lr, p_se, p_d, p_sd, p_ld, p_vgg, FM, batch, output_res=RES)
+            refs = ref_grads(l_ref["loss_sum"], [p_g, p_lr, p_se])
+        np.random.seed(seed + 3)
+        l = model.generator_training_step(real, synth, g_opt)
+        hist.append([float(v) for v in l.values()])
+        if with_oracle:
+            worst["g%d" % it] = chk.check(l, l_ref, refs, "G step, iteration %d" % (it + 1))
+        # ---- update_smoothed_weights (:393-400)
+        ema0 = model.generator_smoothed.group.flat.detach().double().cpu().numpy()
+        model.update_smoothed_weights()
+        want = 0.999 * ema0 + 0.001 * model.generator.group.flat.detach().double().cpu().numpy()
+        assert np.abs(model.generator_smoothed.group.flat.detach().double().cpu().numpy() - want).max() <= 1e-7
+    replayed = sorted(k for k, (_, v) in model._graphs.items() if v.graph is not None)
+    return hist, flat_weights(model, STAGE1_NETS + ["generator_smoothed"]), replayed, worst
+
+
+def test_first_stage_class_steps_match_oracle_and_replay_bit_exact(dev):
+    h_g, w_g, replayed, worst = run_stage1(dev, graphs=True, with_oracle=True)
+    print("worst relative-L2 gradient error per step:", {k: "%.2e" % v for k, v in worst.items()})
+    assert replayed == ["d", "g", "latent_d", "synth_d"]
+    h_e, w_e, none, _ = run_stage1(dev, graphs=False, with_oracle=False)
+    assert not none
+    for a, b in zip(h_g, h_e):
+        assert a == b, ("a replayed step reports different losses than the eager step", a, b)
+    for n in w_e:
+        assert np.array_equal(w_g[n], w_e[n]), "weights of %s differ between replayed and eager training" % n
+    # and a second eager run is bit-identical too (no atomics anywhere on the path)
+    h_e2, w_e2, _, _ = run_stage1(dev, graphs=False, with_oracle=False, n_iters=2)
+    assert h_e2 == h_e[:len(h_e2)]
+
+
+# ------------------------------------------------------------------------------------------------ stage 2
+STAGE2_NETS = STAGE1_NETS + ["encoder"]
+
+
+def run_stage2(dev, graphs, with_oracle, n_iters=3):
+    from confignet_b200.confignet_second_stage import ConfigNet
+    from confignet_b200.runtime import KerasAdam
+    from confignet_b200.synthetic_data import SyntheticDataset
+    model = ConfigNet(dict(cfg(graphs), image_loss_weight=5e-4), device=dev)
+    perturb(model, STAGE1_NETS, 700)
+    real, synth = SyntheticDataset(10, RES, seed=3), SyntheticDataset(10, RES, seed=4)
+    d_opt, g_opt = KerasAdam(**model.config["optimizer"]), KerasAdam(**model.config["optimizer"])
+    p_vgg = oracle_params(model.perceptual_loss.group) if with_oracle else None
+    W2 = dict(O.DEFAULT_LOSS_WEIGHTS); W2["image_loss_weight"] = 5e-4
+    hist, worst = [], {}
+    grp = lambda n: getattr(model, n).group
+
+    def P(*names):
+        return [oracle_params(grp(n)) for n in names]
+
+    for it in range(n_iters):
+        seed = 2000 + 10 * it
+        # ---- discriminator_training_step over ConfigNet.get_discriminator_batch (confignet_second_stage.py:119-130)
+        chk = StepCheck([grp("discriminator")], d_opt)
+        if with_oracle:
+            p_d, p_g, p_e = P("discriminator", "generator", "encoder")
+            np.random.seed(seed)
+            real_imgs = flipped_rows(real, B)
+            in_idx = np.random.randint(0, real.imgs.shape[0], B)
+            l_ref = O2.stage2_discriminator_step_losses(p_d, p_g, p_e, T(real_imgs), T(real.imgs[in_idx].astype(np.float64) / 127.5 - 1.0), RES)
+            g_ref = ref_grads(l_ref["loss_sum"], [p_d])
+        np.random.seed(seed)
+        l = model.discriminator_training_step(real, d_opt)
+        hist.append([float(v) for v in l.values()])
+        if with_oracle:
+            worst["d%d" % it] = chk.check(l, l_ref, g_ref, "stage-2 D step, iteration %d" % (it + 1))
+        # ---- latent_discriminator_training_step (confignet_second_stage.py:132-147)
+        chk = StepCheck([grp("latent_discriminator")], d_opt)
+        if with_oracle:
+            p_ld, p_e, p_se = P("latent_discriminator", "encoder", "synthetic_encoder")
+            np.random.seed(seed + 2)
+            real_imgs = flipped_rows(real, B)
+            fm_p, _, _, _ = synth_rows(synth, B)
+            l_ref = O2.stage2_latent_discriminator_step_losses(p_ld, p_e, p_se, FM, T(real_imgs), [T(a) for a in fm_p])
+            g_ref = ref_grads(l_ref["loss_sum"], [p_ld])
+        np.random.seed(seed + 2)
+        l = model.latent_discriminator_training_step(real, synth, d_opt)
+        hist.append([float(v) for v in l.values()])
+        if with_oracle:
+            worst["ld%d" % it] = chk.check(l, l_ref, g_ref, "stage-2 latent-D step, iteration %d" % (it + 1),
+                                           loss_tol=1e-3, grad_tol=2e-2)
+        # ---- generator_training_step (confignet_second_stage.py:149-218)
+        gnames = ["generator", "latent_regressor", "synthetic_encoder", "encoder"]
+        chk = StepCheck([grp(n) for n in gnames], g_opt)
+        if with_oracle:
+            p_g, p_lr, p_se, p_e, p_d, p_sd, p_ld = P("generator", "latent_regressor", "synthetic_encoder", "encoder", "discriminator",
+                                                       "synth_discriminator", "latent_discriminator")
+            np.random.seed(seed + 3)
+            fm_p, srot, simgs, masks = synth_rows(synth, B // 2)
+            rimgs = flipped_rows(real, B - B // 2)
+            batch = dict(facemodel_params=[T(a) for a in fm_p], synth_rotations=T(srot), synth_imgs=T(simgs), eye_masks=masks,
+                         real_imgs=T(rimgs))
+            l_ref = O2.stage2_generator_step_losses(p_g, p_lr, p_se, p_e, p_d, p_sd, p_ld, p_vgg, FM, batch, weights=W2, output_res=RES)
+            refs = ref_grads(l_ref["loss_sum"], [p_g, p_lr, p_se, p_e])
+        np.random.seed(seed + 3)
+        l = model.generator_training_step(real, synth, g_opt)
+        hist.append([float(v) for v in l.values()])
+        if with_oracle:
+            worst["g%d" % it] = chk.check(l, l_ref, refs, "stage-2 G step, iteration %d" % (it + 1))
+        model.update_smoothed_weights()
+    replayed = sorted(k for k, (_, v) in model._graphs.items() if v.graph is not None)
+    return hist, flat_weights(model, STAGE2_NETS + ["generator_smoothed"]), replayed, worst
+
+
+def test_second_stage_class_steps_match_oracle_and_replay_bit_exact(dev):
+    h_g, w_g, replayed, worst = run_stage2(dev, graphs=True, with_oracle=True)
+    print("worst relative-L2 gradient error per step:", {k: "%.2e" % v for k, v in worst.items()})
+    assert replayed == ["d2", "g2", "latent_d2"]
+    h_e, w_e, none, _ = run_stage2(dev, graphs=False, with_oracle=False)
+    assert not none
+    for a, b in zip(h_g, h_e):
+        assert a == b, ("a replayed step reports different losses than the eager step", a, b)
+    for n in w_e:
+        assert np.array_equal(w_g[n], w_e[n]), "weights of %s differ between replayed and eager training" % n
+
+
+# ------------------------------------------------------------------------------------------------ LatentGAN, fine-tuning
+def test_latent_gan_class_steps_match_oracle_and_replay_bit_exact(dev):
+    """LatentGAN.discriminator_training_step / generator_training_step (latent_gan.py:117-165), one optimizer for both
+    networks (latent_gan.py:236), replayed from the second iteration on."""
+    from confignet_b200.latent_gan import LatentGAN
+    from confignet_b200.runtime import KerasAdam
+    gt = np.random.RandomState(9).randn(64, 145).astype(np.float32)
+
+    def run(graphs, with_oracle):
+        gan = LatentGAN({"latent_dim": 145, "batch_size": 16, "cuda_graphs": graphs, "cuda_graph_warmup": 1}, device=dev)
+        perturb(gan, ["generator", "discriminator"], 900)
+        opt = KerasAdam(**gan.config["optimizer"])
+        hist = []
+        for it in range(4):
+            chk = StepCheck([gan.discriminator.group], opt)
+            if with_oracle:
+                p_d, p_g = oracle_params(gan.discriminator.group), oracle_params(gan.generator.group)
+                np.random.seed(300 + it)
+                zin = np.random.normal(0, 1, (16, 145)).astype(np.float32)
+                idx = np.random.randint(0, gt.shape[0], 16)
+                l_ref = O2.latent_gan_discriminator_losses(p_d, p_g, T(gt[idx]), T(zin))
+                g_ref = ref_grads(l_ref["loss_sum"], [p_d])
+            np.random.seed(300 + it)
+            l = gan.discriminator_training_step(gt, opt)
+            hist.append([float(v) for v in l.values()])
+            if with_oracle:
+                chk.check(l, l_ref, g_ref, "LatentGAN D step %d" % it, loss_tol=1e-4, grad_tol=1e-3)
+            chk = StepCheck([gan.generator.group], opt)
+            if with_oracle:
+                p_d, p_g = oracle_params(gan.discriminator.group), oracle_params(gan.generator.group)
+                np.random.seed(400 + it)
+                zin = np.random.normal(0, 1, (16, 145)).astype(np.float32)
+                l_ref = O2.latent_gan_generator_losses(p_d, p_g, T(zin))
+                g_ref = ref_grads(l_ref["loss_sum"], [p_g])
+            np.random.seed(400 + it)
+            l = gan.generator_training_step(opt)
+            hist.append([float(v) for v in l.values()])
+            if with_oracle:
+                chk.check(l, l_ref, g_ref, "LatentGAN G step %d" % it, loss_tol=1e-4, grad_tol=1e-3)
+            gan.update_smoothed_weights()
+        assert opt.iterations == 8
+        return hist, flat_weights(gan, ["generator", "discriminator", "generator_smoothed"]), sorted(
+            k for k, (_, v) in gan._graphs.items() if v.graph is not None)
+
+    h_g, w_g, replayed = run(True, True)
+    h_e, w_e, none = run(False, False)
+    assert replayed == ["d", "g"] and not none and h_g == h_e
+    for n in w_e:
+        assert np.array_equal(w_g[n], w_e[n]), n
+
+
+def test_fine_tune_replay_equals_eager(dev):
+    """fine_tune_on_img (confignet_second_stage.py:321-403): its iteration is captured at the second call and replayed;
+    embeddings, rotations, losses and the fine-tuned generator must equal the eager run bit for bit."""
+    from confignet_b200.confignet_second_stage import ConfigNet
+    imgs = np.random.RandomState(12).randint(0, 256, (2, RES, RES, 3)).astype(np.uint8)
+
+    def run(graphs):
+        model = ConfigNet(dict(cfg(graphs), image_loss_weight=5e-4), device=dev)
+        perturb(model, STAGE1_NETS, 800)
+        model.generator_smoothed.group.copy_from(model.generator.group)
+        emb, rot = model.fine_tune_on_img(imgs, n_iters=4)
+        losses = [[float(v) for v in d.values()] for d in model.fine_tune_losses]
+        return emb, rot, losses, model.generator_fine_tuned.group.flat.detach().cpu().numpy().copy()
+
+    e_g, r_g, l_g, w_g = run(True)
+    e_e, r_e, l_e, w_e = run(False)
+    assert np.isfinite(e_g).all() and l_g == l_e
+    assert np.array_equal(e_g, e_e) and np.array_equal(r_g, r_e) and np.array_equal(w_g, w_e)
+
+
+# ------------------------------------------------------------------------------------------------ cache hazards
+def test_eager_calls_between_replays_see_current_weights(dev):
+    """The packed-weight cache must not serve a stale image to an eager call that follows a replayed optimizer step
+    (the replay runs Adam without the host code that marks the buffer as changed), nor may an eager call right
+    before a capture leave the captured graph without its pack kernels.  An eager discriminator / generator call
+    is interleaved with every step; losses must equal those of a model that never uses graphs."""
+    from confignet_b200.confignet_first_stage import ConfigNetFirstStage
+    from confignet_b200.runtime import KerasAdam
+    from confignet_b200.synthetic_data import SyntheticDataset
+    probe = torch.tensor(np.random.RandomState(5).rand(2, RES, RES, 3).astype(np.float32) * 2 - 1, device=dev)
+    z = torch.tensor(np.random.RandomState(6).randn(2, 145).astype(np.float32), device=dev)
+    rot = np.array([[0.1, -0.05, 0.0], [-0.2, 0.1, 0.0]], np.float32)
+
+    def run(graphs):
+        model = ConfigNetFirstStage(dict(cfg(graphs), batch_size=2), device=dev)
+        perturb(model, STAGE1_NETS, 600)
+        real, synth = SyntheticDataset(6, RES, seed=1), SyntheticDataset(6, RES, seed=2)
+        d_opt, g_opt = KerasAdam(**model.config["optimizer"]), KerasAdam(**model.config["optimizer"])
+        np.random.seed(77)
+        seen = []
+        for it in range(4):
+            with torch.no_grad():
+                seen.append(float(model.discriminator(probe)["discr_final"].sum()))
+                seen.append(float(model.generator.predict([z, rot]).sum()))
+            d = model.discriminator_training_step(real, d_opt)
+            with torch.no_grad():
+                seen.append(float(model.discriminator(probe)["discr_final"].sum()))
+            g = model.generator_training_step(real, synth, g_opt)
+            with torch.no_grad():
+                seen.append(float(model.generator.predict([z, rot]).sum()))
+            seen += [float(d["loss_sum"]), float(g["loss_sum"])]
+        return seen
+
+    assert run(True) == run(False)
+
+
+def test_generate_images_graph_replay_matches_eager_and_follows_the_weights(dev):
+    """generate_images (confignet_first_stage.py:633-639) at the demo batch sizes 1 / 2 / 6 replays a captured graph
+    (runtime.InferenceGraphs): same uint8 bits as the eager path, within one grey level of the oracle, and - the graph
+    holds no pack kernels - it must be re-captured when the smoothed generator changes."""
+    from confignet_b200.confignet_first_stage import ConfigNetFirstStage
+    models = [ConfigNetFirstStage(cfg(g), device=dev) for g in (True, False)]
+    for m in models:
+        perturb(m, ["generator"], 321)
+        m.generator_smoothed.group.copy_from(m.generator.group)
+    rng = np.random.RandomState(8)
+    first = {}
+    for nb in (1, 2, 6):
+        lat = rng.randn(nb, 145).astype(np.float32)
+        rot = np.zeros((nb, 3), np.float32); rot[:, 0] = rng.uniform(-0.5, 0.5, nb); rot[:, 1] = rng.uniform(-0.17, 0.17, nb)
+        a1 = models[0].generate_images(lat, rot)          # warm-up + capture
+        a2 = models[0].generate_images(lat, rot)          # replay
+        b = models[1].generate_images(lat, rot)
+        assert a1.dtype == np.uint8 and a1.shape == (nb, RES, RES, 3)
+        assert np.array_equal(a1, b) and np.array_equal(a2, b)
+        first[nb] = (lat, rot, b)
+    assert len(models[0]._infer.cache) == 3 and all("graph" in e for e in models[0]._infer.cache.values())
+    lat, rot, b = first[1]
+    p = oracle_params(models[1].generator_smoothed.group)
+    with torch.no_grad():
+        ref = O.to_uint8_images(O.generator_forward(p, T(lat), T(rot), RES).numpy())
+    assert np.abs(ref.astype(np.int32) - b.astype(np.int32)).max() <= 1
+    # the list form (five per-block latents, hologan_generator.py:109-127) goes through the same graph
+    lat5 = [rng.randn(1, 145).astype(np.float32) for _ in range(5)]
+    assert np.array_equal(models[0].generate_images(lat5, rot), models[1].generate_images(lat5, rot))
+    # weights move (a training step's EMA): the captured graph must not keep serving the old packed kernels
+    for m in models:
+        perturb(m, ["generator"], 654)
+        m.update_smoothed_weights(0.5)
+    a = models[0].generate_images(lat, rot)
+    b2 = models[1].generate_images(lat, rot)
+    assert np.array_equal(a, b2) and not np.array_equal(a, b)
