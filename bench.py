@@ -85,35 +85,70 @@ def bench_config(cfg_id, world):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons DURING the timed region, read through NVML in this process (the library nvidia-smi is
+    a front end of): forking an nvidia-smi child out of a multi-GB Python process every 200 ms stalled the host half of
+    the first timed step by up to 30 ms (measured, profiles/r02_first_step_outlier.txt).  Falls back to nvidia-smi when
+    the NVML binding is missing.  The thread starts before the warm-up; only samples between begin() and summary() count."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.active = index, [], False, False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def run(self):
-        while not self.stop_flag:
-            try:
+    def sample(self):
+        try:
+            if self.nvml is not None:
+                n = self.nvml
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                bit = lambda name: "Active" if r & getattr(n, name, 0) else "Not Active"
+                f = [str(sm), str(mx), bit("nvmlClocksThrottleReasonHwSlowdown"), bit("nvmlClocksThrottleReasonHwThermalSlowdown"),
+                     bit("nvmlClocksThrottleReasonSwThermalSlowdown"), bit("nvmlClocksThrottleReasonSwPowerCap")]
+            else:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.2)
+            if len(f) >= 6 and self.active:
+                self.samples.append(f)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self.stop_flag:
+            self.sample()
+            time.sleep(0.05 if self.nvml is not None else 0.2)
+
+    def begin(self):
+        self.samples, self.active = [], True
 
     def summary(self):
-        self.stop_flag = True
+        if not self.samples:
+            self.sample()
+        self.stop_flag, self.active = True, False
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None, "reasons": reasons}
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None, "reasons": reasons,
+                "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle/)
@@ -374,14 +409,14 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local)
+    if rank == 0:                  # one poller per job
+        sampler.start()
     for _ in range(args.warmup):
         wl.step(True)
     barrier()
 
     # ---- value: stores resident in HBM, CUDA events around the K steps
-    sampler = ClockSampler(local)
-    if rank == 0:                  # one nvidia-smi poller per job (8 of them would compete with the ranks' host halves)
-        sampler.start()
     # roofline: a CUDA-event pair around every conv-family launch over extra EAGER steps right after the timed region
     # (default; a graph replay cannot carry them), or - with --roofline-pass inline - inside it (forces eager execution)
     inline = args.roofline_pass == "inline"
@@ -392,11 +427,23 @@ def run_b200(args):
     replayed0 = GraphedFn.REPLAYED_LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     e0.record()
+    marks, host_ms = [], []
     for _ in range(args.steps):
+        th = time.perf_counter()
         wl.step(True)
+        host_ms.append((time.perf_counter() - th) * 1e3)
+        if args.debug_steps:
+            ev = torch.cuda.Event(enable_timing=True); ev.record(); marks.append(ev)
     e1.record()
     barrier()
+    if args.debug_steps and rank == 0:
+        prev, per = e0, []
+        for ev in marks:
+            per.append(prev.elapsed_time(ev)); prev = ev
+        print("value loop: device ms per step %s | host ms per step %s" % (["%.1f" % x for x in per], ["%.1f" % x for x in host_ms]),
+              file=sys.stderr, flush=True)
     launches = int(lib.cn_launch_count(0)) + (GraphedFn.REPLAYED_LAUNCHES - replayed0)     # eager launches + launches replayed from CUDA graphs
     ops.PROFILE[0] = None
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
@@ -515,8 +562,14 @@ def run_b200(args):
     barrier()
     t0 = time.perf_counter()
     pending = None
+    ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
+    marks, host_ms = [], []
     for i in range(args.steps):
+        th = time.perf_counter()
         cur = wl.step(False)              # host halves (sampling, pinned uploads) + asynchronous device halves
+        host_ms.append((time.perf_counter() - th) * 1e3)
+        if args.debug_steps:
+            ev = torch.cuda.Event(enable_timing=True); ev.record(); marks.append(ev)
         d2h += host_bytes(cur)
         rb = enqueue_readback(i, cur)
         if pending is not None:
@@ -528,6 +581,12 @@ def run_b200(args):
         d2h += pending[0].numpy().copy().nbytes
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0) / args.steps
+    if args.debug_steps and rank == 0:
+        prev, per = ev0, []
+        for ev in marks:
+            per.append(prev.elapsed_time(ev)); prev = ev
+        print("e2e loop: device ms per step %s | host ms per step %s" % (["%.1f" % x for x in per], ["%.1f" % x for x in host_ms]),
+              file=sys.stderr, flush=True)
     e2e = {"value": wl.units() / dt, "unit": CONFIGS[cfg_id]["unit"],
            "h2d_bytes_per_step": runtime.H2D_BYTES[0] // args.steps, "d2h_bytes_per_step": d2h // args.steps}
     if cfg_id == 1:
@@ -567,6 +626,7 @@ def main():
                          "per-launch event pairs of the roofline run over extra eager steps right after it; inline: event "
                          "pairs inside the timed region (forces eager execution)")
     ap.add_argument("--breakdown", default=None, help="write a per-layer conv time table to this file")
+    ap.add_argument("--debug-steps", action="store_true", help="per-step device and host times of both timed loops on stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

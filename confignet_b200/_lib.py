@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libconfignet_b200.so")
+LIB_PATH = os.environ.get("CN_LIB") or os.path.join(_HERE, "lib", "libconfignet_b200.so")     # CN_LIB: an experimental build (A/B runs)
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 
@@ -129,6 +129,10 @@ def load():
         lib.cn_debug_set_persistent(int(os.environ["CN_PERSISTENT"]))
     if os.environ.get("CN_WCACHE"):
         lib.cn_debug_set_wcache(int(os.environ["CN_WCACHE"]))
+    if os.environ.get("CN_COAL"):              # measurement knob: channel-major epilogue pass 0 never / 1 rule / 2 always
+        lib.cn_debug_set_coal(int(os.environ["CN_COAL"]))
+    if os.environ.get("CN_DBG"):               # measurement knob: cn_debug_set bits (32 = thread-per-row epilogue stores)
+        lib.cn_debug_set(int(os.environ["CN_DBG"]))
     if os.environ.get("CN_CLUSTER"):
         lib.cn_debug_set_cluster(int(os.environ["CN_CLUSTER"]))
     _lib = lib

@@ -18,7 +18,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
-from . import netspec, networks, ops
+from . import netspec, networks, ops, pretrained
 from .runtime import ParamGroup, Network, KerasAdam, StepGraphs, InferenceGraphs, shard_rows, world
 
 DEFAULT_CONFIG = {
@@ -238,7 +238,7 @@ class ConfigNetFirstStage(StepGraphs):
             self._make_group(netspec.latent_regressor_spec(c["latent_dim"], **self._discr_args()), s + 5),
             networks.latent_regressor_forward, n_layers=nl)
         gspec = netspec.generator_spec(c["latent_dim"], res, c["n_adain_mlp_units"], c["n_adain_mlp_layers"])
-        gkw = dict(output_res=res, n_mlp_layers=c["n_adain_mlp_layers"])
+        gkw = dict(output_res=res, n_mlp_layers=c["n_adain_mlp_layers"], out_act=networks.output_activation(c["gen_output_activation"]))
         self.generator = GeneratorNet(self._make_group(gspec, s + 6), networks.generator_forward, **gkw)
         self.generator_smoothed = GeneratorNet(self._make_group(gspec, s + 6), networks.generator_forward, **gkw)
         self.generator_smoothed.group.copy_from(self.generator.group)
@@ -247,6 +247,17 @@ class ConfigNetFirstStage(StepGraphs):
         self.perceptual_loss = Network(self._make_group(netspec.vgg19_spec(), s + 7, vgg_like=True),
                                        networks.vgg19_activations)
         self.perceptual_loss.group.set_frozen(self.drop_graphs)
+        if type(self) is ConfigNetFirstStage:
+            pretrained.from_config_or_env(self)
+
+    PRETRAINED = (("perceptual_loss", "the VGG19 perceptual-loss network (perceptual_loss.py:19-24)"),)
+
+    def load_pretrained_weights(self, vgg19=None, **other):
+        """Loads the ImageNet VGG19 of the perceptual loss from an .npz export (confignet_b200/pretrained.py)."""
+        if other:
+            raise TypeError("unknown pretrained networks for the first stage: %s" % sorted(other))
+        if vgg19 is not None:
+            pretrained.load_vgg(self.perceptual_loss.group, vgg19, "VGG19")
 
     # ---------------------------------------------------------------- weights / io
     def get_weights(self, return_tensors=False):
@@ -400,7 +411,7 @@ class ConfigNetFirstStage(StepGraphs):
         rotation = self.sample_rotations(B)
         img_idxs, flips, latent, rotation = self._rank_rows(img_idxs, flips, latent, rotation)
         real_imgs = self._upload_images(self._take_rows(training_set.imgs, img_idxs), flips)
-        fake_imgs = self.generator.predict([self._to_device(latent, torch.float32), rotation])
+        fake_imgs = self.generator.predict_device([self._to_device(latent, torch.float32), rotation])
         return real_imgs, fake_imgs
 
     def get_synth_discriminator_batch(self, training_set):
@@ -513,6 +524,7 @@ class ConfigNetFirstStage(StepGraphs):
 
     def generator_training_step(self, real_training_set, synth_training_set, optimizer):
         """confignet_first_stage.py:506-560."""
+        pretrained.warn_if_standin(self, self.PRETRAINED[:1], "generator_training_step")
         c = self.config
         n_synth = self.get_batch_size() // 2
         n_real = self.get_batch_size() - n_synth

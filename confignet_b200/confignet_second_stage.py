@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import netspec, networks, ops
+from . import netspec, networks, ops, pretrained
 from .confignet_first_stage import (ConfigNetFirstStage, DEFAULT_CONFIG, merge_configs, update_loss_dict, GeneratorNet)
 from .runtime import ParamGroup, Network, KerasAdam, allreduce_grads, shard_rows, world, gather_rows
 
@@ -37,7 +37,12 @@ class RealEncoderNet(Network):
         return super().__call__(networks._as_dev(imgs, self.group.device))
 
     def predict(self, imgs):
-        """keras Model.predict: forward in batches of 32 without a tape -> (embeddings, rotations) device tensors."""
+        """keras Model.predict -> (embeddings, rotations) NumPy arrays"""
+        e, r = self.predict_device(imgs)
+        return e.cpu().numpy(), r.cpu().numpy()
+
+    def predict_device(self, imgs):
+        """keras Model.predict's batching: forward in batches of 32 without a tape -> (embeddings, rotations) device tensors."""
         embs, rots = [], []
         with torch.no_grad():
             for i in range(0, imgs.shape[0], PREDICT_BATCH):
@@ -72,6 +77,22 @@ class ConfigNet(ConfigNetFirstStage):
         self.perceptual_loss_face_reco = Network(self._make_group(netspec.vgg16_spec(), s + 9, vgg_like=True),
                                                  networks.vggface_activations)
         self.perceptual_loss_face_reco.group.set_frozen(self.drop_graphs)
+        pretrained.from_config_or_env(self)
+
+    PRETRAINED = (("perceptual_loss", "the VGG19 perceptual-loss network (perceptual_loss.py:19-24)"),
+                  ("encoder", "the ResNet50 trunk of the real encoder (real_encoder.py:13)"),
+                  ("perceptual_loss_face_reco", "the VGGFace VGG16 network (perceptual_loss.py:26-41)"))
+
+    def load_pretrained_weights(self, vgg19=None, vggface=None, resnet50=None):
+        """Loads the third-party networks from .npz exports (confignet_b200/pretrained.py): ImageNet VGG19 (perceptual
+        loss), VGGFace VGG16 (fine-tuning face-recognition loss), ImageNet ResNet50 (the encoder's trunk; a checkpoint
+        loaded with load() / set_weights() already carries a TRAINED encoder and marks it as such)."""
+        if vgg19 is not None:
+            pretrained.load_vgg(self.perceptual_loss.group, vgg19, "VGG19")
+        if vggface is not None:
+            pretrained.load_vgg(self.perceptual_loss_face_reco.group, vggface, "VGGFace VGG16")
+        if resnet50 is not None:
+            pretrained.load_resnet50(self.encoder.group, resnet50)
 
     def face_reco_loss(self, gt_imgs, gen_imgs):
         """confignet_second_stage.py:88-91: the VGGFace perceptual loss with (generated, ground truth) in the reference's
@@ -88,6 +109,7 @@ class ConfigNet(ConfigNetFirstStage):
     def set_weights(self, weights):
         super().set_weights(weights)
         self.encoder.set_weights(weights["real_encoder_weights"])
+        self.encoder.group.pretrained = True          # a checkpoint's encoder: trained, not the seeded stand-in
 
     # ---------------------------------------------------------------- batch assembly (reference RNG draw order)
     def _draw_image_rows(self, dataset, batch_size):
@@ -176,6 +198,7 @@ class ConfigNet(ConfigNetFirstStage):
 
     def generator_training_step(self, real_training_set, synth_training_set, optimizer):
         """confignet_second_stage.py:149-218."""
+        pretrained.warn_if_standin(self, self.PRETRAINED[:2], "generator_training_step")
         c = self.config
         n_synth = self.get_batch_size() // 2
         n_real = self.get_batch_size() - n_synth
@@ -282,7 +305,7 @@ class ConfigNet(ConfigNetFirstStage):
         """confignet_second_stage.py:301-308 -> (embeddings (B, latent) f32, rotations (B, 3) f32) NumPy."""
         embs, rots = [], []
         for i in range(0, input_images.shape[0], PREDICT_BATCH):
-            e, r = self.encoder.predict(self._images_to_device(input_images[i:i + PREDICT_BATCH]))
+            e, r = self.encoder.predict_device(self._images_to_device(input_images[i:i + PREDICT_BATCH]))
             embs.append(e); rots.append(r)
         if not embs:
             return np.zeros((0, self.config["latent_dim"]), np.float32), np.zeros((0, 3), np.float32)
@@ -301,6 +324,7 @@ class ConfigNet(ConfigNetFirstStage):
         embeddings, per-image expression embeddings and rotations; Keras Adam(lr=1e-4) defaults.  With data
         parallelism the images are sharded by rows: generator and pre/post gradients are all-reduced, the per-image
         variables stay rank-local."""
+        pretrained.warn_if_standin(self, self.PRETRAINED, "fine_tune_on_img")
         c = self.config
         if isinstance(input_images, np.ndarray) and input_images.ndim == 3:
             input_images = input_images[np.newaxis]
@@ -312,7 +336,6 @@ class ConfigNet(ConfigNetFirstStage):
         imgs = self._images_to_device(input_images)
         n_imgs = imgs.shape[0]
         pred_emb, pred_rot = self.encoder.predict(imgs)
-        pred_emb, pred_rot = pred_emb.cpu().numpy(), pred_rot.cpu().numpy()
         if force_neutral_expression:
             n_exp = c["facemodel_inputs"]["blendshape_values"][0]
             pred_emb = self.set_facemodel_param_in_latents(pred_emb, "blendshape_values", np.zeros((1, n_exp), np.float32))
@@ -320,7 +343,8 @@ class ConfigNet(ConfigNetFirstStage):
         if self.generator_fine_tuned is None:
             gspec = netspec.generator_spec(c["latent_dim"], c["output_shape"][0], c["n_adain_mlp_units"], c["n_adain_mlp_layers"])
             self.generator_fine_tuned = GeneratorNet(self._make_group(gspec, self._seed + 6), networks.generator_forward,
-                                                     output_res=c["output_shape"][0], n_mlp_layers=c["n_adain_mlp_layers"])
+                                                     output_res=c["output_shape"][0], n_mlp_layers=c["n_adain_mlp_layers"],
+                                                     out_act=networks.output_activation(c["gen_output_activation"]))
         self.generator_fine_tuned.group.copy_from(self.generator_smoothed.group)
 
         expr_idxs = self.get_facemodel_param_idxs_in_latent("blendshape_values")

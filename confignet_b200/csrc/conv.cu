@@ -730,6 +730,8 @@ __device__ __forceinline__ uint32_t mn_chunk_off(int r, int jn, uint32_t sbo) {
 constexpr int TC_BM = 128;        // GEMM rows per CTA (UMMA M)
 constexpr int TC_BK = 32;         // K elements per stage = one 128-byte swizzle row of tf32
 constexpr int TC_CHUNK_KB = 8;    // k-blocks (256 K elements) accumulated in the tensor core before promotion
+constexpr int TC_TOT_LD = 129;    // leading dimension of the running total [column][row] in shared memory: lane = row (promotion)
+                                  // and lane = column (the coalesced final pass) are both conflict-free
 
 // The tensor core adds into its fp32 accumulator with truncation: measured on B200 the result drifts by
 // ~1.1e-8 * K relative (1.2e-4 at K = 18432), a bias that plain fp32 FMAs do not have.  So the MMA warp
@@ -740,10 +742,11 @@ constexpr int TC_CHUNK_KB = 8;    // k-blocks (256 K elements) accumulated in th
 // accesses are conflict-free), which leaves the tensor memory to the two accumulators and the A stages.
 template <class StoreFn>
 __device__ __forceinline__ void tc_promote_smem_and_store(uint32_t tmem_base, float* tot, int pw, int bn, int bn_r, int c0, int nchunks,
-                                                          uint32_t bar_accfull, uint32_t bar_accempty, StoreFn store) {
+                                                          uint32_t bar_accfull, uint32_t bar_accempty, bool keep_last, StoreFn store) {
   // c0 = accumulation chunks this CTA has consumed before this item (persistent CTAs): the ping-pong accumulator
   // and the barrier phases follow the GLOBAL chunk index; every chunk, the last of an item included, releases its
   // accumulator so that a later item can reuse it.
+  // keep_last: the final sums stay in `tot` as well (the caller then writes them with lanes along the channels)
   const uint32_t lanebits = (uint32_t)(pw * 32) << 16;
   float* mine = tot + pw * 32 + (threadIdx.x & 31);
   for (int c = 0; c < nchunks; ++c) {
@@ -757,11 +760,11 @@ __device__ __forceinline__ void tc_promote_smem_and_store(uint32_t tmem_base, fl
       tc_ld32(tmem_base + lanebits + b * bn_r + cb, v);
       if (c > 0) {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + mine[(cb + q) * 128]);
+        for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + mine[(cb + q) * TC_TOT_LD]);
       }
-      if (!last) {
+      if (!last || keep_last) {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) mine[(cb + q) * 128] = __uint_as_float(v[q]);
+        for (int q = 0; q < 32; ++q) mine[(cb + q) * TC_TOT_LD] = __uint_as_float(v[q]);
       } else {
         store(cb, v);
       }
@@ -882,6 +885,19 @@ __device__ __forceinline__ void tc_st16_nowait(uint32_t taddr, const uint32_t* v
 }
 
 constexpr int TCP_MAX_A = 6;         // A stages in tensor memory (as many as fit beside the two accumulators)
+// Lanes per GEMM row in the pixel-mode gather (1, 2, 4 or 8).  LPR lanes read adjacent 16-byte chunks of one row, so a load
+// instruction touches 32 / LPR lines of 128 B instead of 32 (the L1 data pipe pays per line touched and was 90 % busy with
+// LPR = 1, profiles/r01_ncu_full_tc_final_summary.txt); an LPR x LPR register <-> lane transpose (log2 LPR butterfly stages
+// of shuffles) then gives every thread the eight chunks of ITS row.  More lanes per row = fewer L1 wavefronts but more
+// shuffle / select instructions in the gather warps; measured per value in profiles/r02_gather_lpr_ab.txt.
+#ifndef CN_LPR
+#define CN_LPR 2      // measured best on every fwd / dgrad layer of the bench step but two (1 / 2 / 4 / 8: 33.3 / 30.9 / 32.2 / 40.0 ms per step)
+#endif
+constexpr int TCP_LPR = CN_LPR;
+constexpr int TCP_RPI = 32 / TCP_LPR;            // rows per load instruction
+constexpr int TCP_HPR = 8 / TCP_LPR;             // load instructions per row group (chunk groups of LPR chunks)
+// GEMM row (inside its 32-row group) held by tensor-memory lane `lane`: lane = (r, c), row = c * TCP_RPI + r
+__device__ __forceinline__ int tcp_row_of_lane(int lane) { return (lane & (TCP_LPR - 1)) * TCP_RPI + (lane / TCP_LPR); }
 struct TcpLayout {
   // dynamic smem, 1024-byte aligned: nb B stages [B big][B small]; running total [bn_r][128] fp32; barriers, tmem ptr, taps
   uint32_t stage_bytes, b_bytes, tot_off, bar_off, tmem_off, taps_off, total;
@@ -891,7 +907,7 @@ __host__ __device__ inline TcpLayout tcp_layout(int nb, int bn_smem) {
   l.b_bytes = bn_smem * TC_BK * 4;
   l.stage_bytes = 2 * l.b_bytes;
   l.tot_off = nb * l.stage_bytes;
-  l.bar_off = l.tot_off + ((bn_smem + 31) / 32 * 32) * 128 * 4;
+  l.bar_off = (l.tot_off + ((bn_smem + 31) / 32 * 32) * TC_TOT_LD * 4 + 7) & ~7u;
   l.tmem_off = l.bar_off + (2 * nb + 2 * TCP_MAX_A + 4) * 8;      // full_b[], empty_b[], full_a[], empty_a[], acc_full[2], acc_empty[2]
   l.taps_off = (l.tmem_off + 4 + 7) & ~7u;
   l.total = l.taps_off + 256 * 8;
@@ -1056,8 +1072,11 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
     item(w, p, m0, n0, ysel, tap0, num_kb);
     const int kb_first = (par - gk_base) & 1;
     gk_base += num_kb;
-    // ---- pixel mode state
-    const RowInfo row = decode_row(p, WG ? p.M : m0 + q4 * 32 + lane);
+    // ---- pixel mode state.  Gather map (TCP_LPR lanes per row): load instruction i = g * TCP_HPR + h, lane (r, c) =
+    // (lane / LPR, lane % LPR) reads the 16-byte chunk h * LPR + c of row g * TCP_RPI + r of the warp's 32-row group.
+    // After the transpose (put_a) thread (r, c) holds the eight chunks of row c * TCP_RPI + r = tcp_row_of_lane(lane),
+    // splits them and writes them to ITS tensor-memory lane; the epilogue uses the same row <-> lane map.
+    const RowInfo row = decode_row(p, WG ? p.M : m0 + q4 * 32 + tcp_row_of_lane(lane));
     auto src_off = [&](int kt) -> uint32_t {
       if (kt >= p.ntaps) return 0xffffffffu;
       const uint32_t sp = src_pixel(p, row, s_taps[tap0 + kt].x);
@@ -1071,27 +1090,66 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
     int l_so_kt = -1;
     auto load_a = [&](float4* v) {
       const long long t0 = (PROF ? clock64() : 0ll);
-      if (l_kt != l_so_kt) { l_so = src_off(l_kt); l_so_kt = l_kt; }
+      const int c = lane & (TCP_LPR - 1), r = lane / TCP_LPR;
+      const bool skip = (dbg & 1) != 0;
       if (l_c + TC_BK <= p.Csrc) {
-        // common case: the 32 channels of this k-block lie inside one tap -> 8 loads off one base pointer
-        const float* src = A + (size_t)l_so + l_c;
-        const bool ok = l_so != 0xffffffffu && !(dbg & 1);
+        // common case: the 32 channels of this k-block lie inside one tap - the row owners keep their source offset
+        // for the tap, the loading lanes fetch it with one shuffle per row group (none with one lane per row)
+        if (l_kt != l_so_kt) { l_so = src_off(l_kt); l_so_kt = l_kt; }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = ok ? ldg128(src + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g = 0; g < TCP_LPR; ++g) {
+          const uint32_t so = TCP_LPR == 1 ? l_so : __shfl_sync(0xffffffffu, l_so, r * TCP_LPR + g);    // owner of row g * RPI + r
+#pragma unroll
+          for (int h = 0; h < TCP_HPR; ++h)
+            v[g * TCP_HPR + h] = (so != 0xffffffffu && !skip) ? ldg128(A + (size_t)so + l_c + 4 * (h * TCP_LPR + c))
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       } else {
-        // the k-block straddles a tap boundary (Csrc not a multiple of 32) or the end of K
-        int kt = l_kt, c = l_c;
-        uint32_t so = l_so;
+        // the k-block straddles taps (Csrc not a multiple of 32) or the end of K: every chunk finds its own (tap, channel)
+        // and the source pixel of its row from the owner's row decode
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          v[q] = (so != 0xffffffffu && !(dbg & 1)) ? ldg128(A + (size_t)so + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-          c += 4;
-          if (c >= p.Csrc) { c = 0; ++kt; so = src_off(kt); }
+        for (int g = 0; g < TCP_LPR; ++g) {
+          RowInfo ri = row;
+          if (TCP_LPR > 1) {
+            ri.base = __shfl_sync(0xffffffffu, row.base, r * TCP_LPR + g);
+            ri.pk = __shfl_sync(0xffffffffu, row.pk, r * TCP_LPR + g);
+          }
+          int kt = l_kt, cc = l_c + 4 * c;
+          while (cc >= p.Csrc) { cc -= p.Csrc; ++kt; }
+#pragma unroll
+          for (int h = 0; h < TCP_HPR; ++h) {
+            const uint32_t sp = kt < p.ntaps ? src_pixel(p, ri, s_taps[tap0 + kt].x) : 0xffffffffu;
+            v[g * TCP_HPR + h] = (sp != 0xffffffffu && !skip) ? ldg128(A + (size_t)sp * p.Csrc + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+            cc += 4 * TCP_LPR;
+            while (cc >= p.Csrc) { cc -= p.Csrc; ++kt; }
+          }
         }
       }
       l_c += 2 * TC_BK;
       while (l_c >= p.Csrc) { l_c -= p.Csrc; ++l_kt; }
       pt[2] += (PROF ? clock64() : 0ll) - t0;
+    };
+    // LPR x LPR transpose of the register index g against the lane's chunk slot c (per h): afterwards register
+    // g' * TCP_HPR + h of lane (r, c) holds chunk h * LPR + g' of row c * TCP_RPI + r
+    auto transpose_rows = [&](float4* v) {
+#pragma unroll
+      for (int m = 1; m < TCP_LPR; m <<= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int g = 0; g < TCP_LPR; ++g) {
+          if (g & m) continue;
+#pragma unroll
+          for (int h = 0; h < TCP_HPR; ++h) {
+            float4& lo = v[g * TCP_HPR + h];
+            float4& hi = v[(g | m) * TCP_HPR + h];
+            const float4 send = up ? lo : hi;
+            float4 recv;
+            recv.x = __shfl_xor_sync(0xffffffffu, send.x, m); recv.y = __shfl_xor_sync(0xffffffffu, send.y, m);
+            recv.z = __shfl_xor_sync(0xffffffffu, send.z, m); recv.w = __shfl_xor_sync(0xffffffffu, send.w, m);
+            if (up) lo = recv; else hi = recv;
+          }
+        }
+      }
     };
     // ---- wgrad mode state: this thread's (tap, channel) row and the warp-uniform pixel cursor (n, e0, e1, e2)
     const int wr = m0 + q4 * 32 + lane;
@@ -1135,16 +1193,21 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
       if (s_sa >= na) { s_sa -= na; ++s_u; }
       return (uint32_t)sa;
     };
-    auto put_a = [&](uint32_t sa, const float4* v) {
+    auto put_a = [&](uint32_t sa, float4* v) {
       const long long t0 = (PROF ? clock64() : 0ll);
       const uint32_t a_t = a_t0 + sa * TCP_A_COLS;
+      if (!WG && TCP_LPR > 1) transpose_rows(v);
       if (!(dbg & 8)) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t bg[16], sm[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float x[4] = {v[4 * h + q].x, v[4 * h + q].y, v[4 * h + q].z, v[4 * h + q].w};
+            // chunk k = 4h + q of this thread's row: register (k % LPR) * HPR + k / LPR in pixel mode, register k in wgrad mode
+            constexpr int dummy = 0; (void)dummy;
+            const int kch = 4 * h + q;
+            const float4 vv = WG ? v[kch] : v[(kch % TCP_LPR) * TCP_HPR + kch / TCP_LPR];
+            const float x[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               bg[4 * q + e] = __float_as_uint(x[e]) & 0xffffe000u;
@@ -1182,11 +1245,13 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
    for (int w = w_first; w < n_items; w += w_step) {
     GemmPlan p; int m0, n0, ysel, tap0, num_kb;
     item(w, p, m0, n0, ysel, tap0, num_kb);
-    const int m = m0 + pw * 32 + lane;
+    const int m = m0 + pw * 32 + (WG ? lane : tcp_row_of_lane(lane));     // pixel mode: the gather's row <-> lane map
     const bool mok = m < (WG ? p.Ktot : p.M);
     const size_t rowoff = mok ? (WG ? (size_t)m : (size_t)dest_pixel(p, m)) * p.Cn : 0;
     const int nchunks = (num_kb + chunk_kb - 1) / chunk_kb;
-    tc_promote_smem_and_store(tmem_base, reinterpret_cast<float*>(smem + L.tot_off), pw, bn, bn_r, c0, nchunks, bar_accfull, bar_accempty,
+    const bool coal = (dbg & 32) != 0;  // final pass with the lanes along the channels: every store instruction writes whole lines
+    float* tot = reinterpret_cast<float*>(smem + L.tot_off);
+    tc_promote_smem_and_store(tmem_base, tot, pw, bn, bn_r, c0, nchunks, bar_accfull, bar_accempty, coal,
                               [&](int cb, const uint32_t* v) {
       if (mok && !(dbg & 16)) {
 #pragma unroll
@@ -1208,6 +1273,38 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
         }
       }
     });
+    if (coal) {
+      // The thread-per-row stores above put 32 different lines under one instruction (measured: 22-33 % of the kernel,
+      // profiles/r01_role_prof_v8_persistent.txt).  Here a warp walks the 32 rows it promoted itself (no cross-warp
+      // dependency) with its lanes along the channels: one 128-byte line per instruction.
+      __syncwarp();
+      float* Dz = D + (part_stride ? (size_t)blockIdx.z * (size_t)part_stride : (size_t)0);
+      const bool raw = part_stride != 0;
+      float bz[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = lane + 32 * i, n = n0 + c;
+        bz[i] = (!raw && bias != nullptr && c < bn && n < p.Cn) ? bias[n] : 0.f;
+      }
+      const uint32_t myoff = mok ? (uint32_t)rowoff : 0xffffffffu;      // element offsets fit 32 bits (checked when the plan is built)
+      if (!(dbg & 16)) {
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const uint32_t ro = __shfl_sync(0xffffffffu, myoff, r);
+          if (ro == 0xffffffffu) continue;
+          const float* src = tot + pw * 32 + r;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = lane + 32 * i, n = n0 + c;
+            if (c < bn && n < p.Cn) {
+              const float v = src[c * TC_TOT_LD] + bz[i];
+              Dz[ro + n] = raw ? v : cn_apply_act(v, act, alpha);
+            }
+          }
+        }
+      }
+      __syncwarp();                       // the rows may be overwritten by the next item's first chunk
+    }
     c0 += nchunks;
    }
   } else if (warp == TCP_B_WARP) {
@@ -1769,6 +1866,8 @@ static long long* g_prof = nullptr;   // TEST HOOK: device buffer (16 x int64) r
 extern "C" int cn_debug_set_prof(void* p) { g_prof = (long long*)p; return CN_OK; }
 static int g_dbg = 0;   // TEST HOOK (cn_debug_set): bit 0/1 skip A/B global loads, bit 2 skip MMA issue, bit 3 skip STS
 extern "C" int cn_debug_set(int v) { g_dbg = v; return CN_OK; }
+static int g_coal = 1;         // channel-major final epilogue pass: 0 never, 1 by rule (launch_tc), 2 always (cn_debug_set_coal)
+extern "C" int cn_debug_set_coal(int v) { g_coal = v; return CN_OK; }
 static int g_persistent = 1;   // persistent CTAs in the tcgen05 pixel kernel (cn_debug_set_persistent)
 extern "C" int cn_debug_set_persistent(int v) { g_persistent = v; return CN_OK; }
 static int g_fold = 1;     // folded upsample+conv plans (cn_debug_set_fold)
@@ -2025,6 +2124,10 @@ static int launch_tc(const GemmPlan& g, const float* src, const float* packed, c
                      float alpha, int bn, int bn_smem, dim3 grid, int per, int split, cudaStream_t st, size_t part_stride = 0) {
   int nb, smem;
   tc_smem_config(bn_smem, &nb, &smem);
+  // Final pass of the epilogue with the lanes along the channels (whole 128-byte lines per store instruction) where it
+  // was measured to pay: forward launches with full 128-column tiles (profiles/r02_epilogue_ab.txt: +6..17 % there, a loss
+  // on narrow tiles and strided outputs, where one row is only 1-3 store instructions).  g_coal: 0 never, 1 rule, 2 always.
+  const bool coal = g_coal == 2 || (g_coal == 1 && B_MN && !WG && bn == 128 && g.nphase <= 1);
   // thread-block cluster along M: the CTAs of a cluster share the B stream by multicast
   int csize = g_cluster;
   while (csize > 1 && (int)grid.x < csize) csize >>= 1;
@@ -2053,7 +2156,8 @@ static int launch_tc(const GemmPlan& g, const float* src, const float* packed, c
   auto kern = g_prof ? igemm_tc_pixel_kernel<B_MN, WG, 1> : igemm_tc_pixel_kernel<B_MN, WG, 0>;
   if (set_smem(kern, smem)) return CN_ERR_CUDA;
   CN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, g, src, packed, bias, dst, act, alpha, bn, bn_smem,
-                                   nb, 512, per, (long long)(split > 1 ? part_stride : 0), csize, ny, (g_dbg & 0xff) | (g_chunk_kb << 8), g_prof));
+                                   nb, 512, per, (long long)(split > 1 ? part_stride : 0), csize, ny,
+                                   ((g_dbg & 0xdf) | (coal ? 32 : 0)) | (g_chunk_kb << 8), g_prof));
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

@@ -612,3 +612,96 @@ extern "C" int probe_conv_tma(const float* x, const float* wp, float* y, int N, 
   conv_tma_kernel<<<N * (Ho / bh) * (Wo / bw), 128, sizeof(ProbeSmem) + 1024>>>(map, wp, y, Ho, Wo, C, stride, pad, bw, bh);
   return finish();
 }
+
+// ---- 5. kind::tf32 MMA peak: an MMA-only loop (no loads) on every SM.  One thread per CTA issues `iters` k-blocks of
+//         4 k-steps x `per_step` MMAs (M = 128, N = n, K = 8 each) into one accumulator; operands are pseudo-random
+//         fp32 bit patterns already in shared / tensor memory.  mode 0: A from tensor memory (TS form, production's a_small
+//         product), mode 1: A from shared memory (SS form), mode 2: the production mix (1 TS + 2 TS = all TS), mode 3: the
+//         candidate mix (1 TS + 2 SS).  -> per-CTA clocks; the host times the launch with CUDA events.
+namespace {
+__global__ void __launch_bounds__(128) mma_peak_kernel(int n, int iters, int mode, long long* __restrict__ clk) {
+  extern __shared__ unsigned char raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  // [A tile 16 KB][B big n*128][B small n*128][barrier][tmem ptr]
+  const uint32_t sbase = smem_u32(sm);
+  const uint32_t a_off = 0, b_off = 16384, b2_off = b_off + n * 128, bar_off = b2_off + n * 128, tm_off = bar_off + 8;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint32_t x = 0x9e3779b9u * (blockIdx.x * 128 + tid + 1);
+  for (int i = tid; i < (int)(bar_off / 4); i += 128) {
+    x = x * 1664525u + 1013904223u;
+    reinterpret_cast<uint32_t*>(sm)[i] = 0x3f000000u | (x >> 9);            // floats in [0.5, 1)
+  }
+  if (tid == 0) { mbar_init(sbase + bar_off, 1); mbar_init_fence(); }
+  fence_proxy_async();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + tm_off), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + tm_off);
+  {   // A operand in tensor memory: 32 columns of pseudo-random floats per lane (columns 256..287)
+    uint32_t v[32];
+    for (int j = 0; j < 32; ++j) { x = x * 1664525u + 1013904223u; v[j] = 0x3f000000u | (x >> 9); }
+    tc_st32(tmem + ((uint32_t)(warp * 32) << 16) + 256, v);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  long long t0 = 0;
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_tf32(n);
+    const uint64_t ad = umma_desc_k128(sbase + a_off), bb = umma_desc_k128(sbase + b_off), bs = umma_desc_k128(sbase + b2_off);
+    const uint32_t a_t = tmem + 256;
+    t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint32_t acc = (it | kk) != 0;
+        if (mode == 0) {
+          tc_mma_tf32_ts(tmem, a_t + kk * 8, bb + kk * 2, idesc, acc);
+        } else if (mode == 1) {
+          tc_mma_tf32_ss(tmem, ad + kk * 2, bb + kk * 2, idesc, acc);
+        } else if (mode == 2) {
+          tc_mma_tf32_ts(tmem, a_t + kk * 8, bb + kk * 2, idesc, acc);
+          tc_mma_tf32_ts(tmem, a_t + kk * 8, bs + kk * 2, idesc, 1);
+          tc_mma_tf32_ts(tmem, a_t + kk * 8, bb + kk * 2, idesc, 1);
+        } else {
+          tc_mma_tf32_ts(tmem, a_t + kk * 8, bb + kk * 2, idesc, acc);
+          tc_mma_tf32_ss(tmem, ad + kk * 2, bs + kk * 2, idesc, 1);
+          tc_mma_tf32_ss(tmem, ad + kk * 2, bb + kk * 2, idesc, 1);
+        }
+      }
+    }
+    tc_commit(sbase + bar_off);
+  }
+  mbar_wait(sbase + bar_off, 0);
+  tc_fence_after();
+  if (tid == 0 && clk) clk[blockIdx.x] = clock64() - t0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+}  // namespace
+
+// n: MMA N (16..256, multiple of 16); iters k-blocks per CTA; grid CTAs (one per SM); -> *ms = launch time (CUDA events, after one
+// warm-up launch), clk (device, grid entries or null) = per-CTA clocks of the issue loop incl. completion
+extern "C" int probe_mma_peak(int n, int iters, int mode, int grid, float* ms, long long* clk) {
+  if (n < 16 || n > 256 || n % 16) return -2;
+  const int smem = 16384 + 2 * n * 128 + 64 + 1024;
+  if (cudaFuncSetAttribute(mma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -2;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  mma_peak_kernel<<<grid, 128, 200 * 1024>>>(n, iters, mode, clk);     // 200 KB: one CTA per SM (each allocates all 512 TMEM columns)
+  cudaEventRecord(e0);
+  mma_peak_kernel<<<grid, 128, 200 * 1024>>>(n, iters, mode, clk);
+  cudaEventRecord(e1);
+  const int f = finish();
+  float t = 0.f;
+  cudaEventElapsedTime(&t, e0, e1);
+  if (ms) *ms = t;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  (void)smem;
+  return f;
+}

@@ -206,4 +206,4 @@ class LatentGAN(StepGraphs):
     def generate_latents(self, n_samples, truncation=1.0):
         """latent_gan.py:249-253 -> (n, latent_dim) float32 NumPy."""
         input_latents = (self.sample_input_latent_vector(n_samples) * truncation).astype(np.float32)
-        return self.generator_smoothed.predict(input_latents).cpu().numpy()
+        return self.generator_smoothed.predict(input_latents)

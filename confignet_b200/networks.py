@@ -67,7 +67,18 @@ def conv_adain(x, z, p, prefix, upsample, n_mlp_layers=2):
     return ops.adain(a, sb, mask_alpha=0.3)
 
 
-def generator_forward(p, z, rotation, output_res=256, zs=None, n_mlp_layers=2):
+OUTPUT_ACTIVATIONS = {"tanh": L.ACT_TANH, None: L.ACT_NONE, "linear": L.ACT_NONE, "relu": L.ACT_RELU}
+
+
+def output_activation(name):
+    """gen_output_activation (confignet_first_stage.py:44,246; passed by the reference to keras Conv2D(activation=...)) ->
+    the epilogue activation of map_final; anything the kernels do not implement fails loudly instead of silently being tanh."""
+    if name not in OUTPUT_ACTIVATIONS:
+        raise ValueError("gen_output_activation %r is not supported (supported: %s)" % (name, sorted(map(str, OUTPUT_ACTIVATIONS))))
+    return OUTPUT_ACTIVATIONS[name]
+
+
+def generator_forward(p, z, rotation, output_res=256, zs=None, n_mlp_layers=2, out_act=L.ACT_TANH):
     """HologanGenerator.call.  z: (B, latent) device tensor (or ``zs`` = the 5 per-block latents);
     rotation: (B,3) host array / tensor of Euler angles in radians."""
     if zs is None:
@@ -96,7 +107,7 @@ def generator_forward(p, z, rotation, output_res=256, zs=None, n_mlp_layers=2):
         x = conv_adain(x, zs[4], p, "map_2d_2b", 2, n_mlp_layers)
     if output_res > 256:
         x = conv_adain(x, zs[4], p, "map_2d_2c", 2, n_mlp_layers)
-    return ops.conv_act(x, p["map_final/kernel"], p["map_final/bias"], upsample=2, act=L.ACT_TANH)
+    return ops.conv_act(x, p["map_final/kernel"], p["map_final/bias"], upsample=2, act=out_act)
 
 
 # ------------------------------------------------------------------------------------------------ discriminators

@@ -116,6 +116,16 @@ class ParamGroup:
         return keep       # keeps the sources alive until the copy is enqueued
 
 
+def _to_numpy(out):
+    if isinstance(out, torch.Tensor):
+        return out.detach().cpu().numpy()
+    if isinstance(out, dict):
+        return type(out)((k, _to_numpy(v)) for k, v in out.items())
+    if isinstance(out, (tuple, list)):
+        return type(out)(_to_numpy(v) for v in out)
+    return out
+
+
 class Network:
     """Keras-Model-like shim around (ParamGroup, forward function)."""
 
@@ -139,10 +149,15 @@ class Network:
         k = dict(self._kw); k.update(kw)
         return self._forward(self.group.params, *inputs, **k)
 
-    def predict(self, *inputs, **kw):
+    def predict_device(self, *inputs, **kw):
+        """forward without a tape -> device tensors (what the step functions use internally)"""
         with torch.no_grad():
-            out = self(*inputs, **kw)
-        return out
+            return self(*inputs, **kw)
+
+    def predict(self, *inputs, **kw):
+        """keras Model.predict: forward without a tape -> NumPy arrays (tuples / dicts of them for multi-output models),
+        as the reference's callers expect (metrics/metrics.py:54-61, latent_gan.py:249-253)."""
+        return _to_numpy(self.predict_device(*inputs, **kw))
 
     def build(self, input_shape=None):
         return None
@@ -333,7 +348,7 @@ class InferenceGraphs:
         keys = ("z_3d_0", "z_3d_1", "z_2d_0", "z_2d_1", "z_2d_2")
         d = dict(zip(keys, zs))
         d["rotation"] = rot
-        return ops.to_uint8(net.predict(d))
+        return ops.to_uint8(net.predict_device(d))
 
     def run(self, net, zs, rot):
         """zs: 5 device tensors (B, latent); rot: (B, 3) device tensor of Euler angles -> uint8 (B, H, W, 3) device tensor"""
@@ -354,14 +369,18 @@ class InferenceGraphs:
                 torch.cuda.synchronize()
                 frozen = net.group.frozen
                 L.call("cn_set_params_frozen", ops._p(flat), 1)
+                lib = L.load()
+                n0 = int(lib.cn_launch_count(0))
                 try:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         out = self._eager(net, s_zs, s_rot)
                 finally:
                     L.call("cn_set_params_frozen", ops._p(flat), 1 if frozen else 0)
+                launches = int(lib.cn_launch_count(0)) - n0              # recorded, not executed
+                lib.cn_launch_count_add(-launches)
                 L.call("cn_graphs_captured")
-                e = self.cache[key] = dict(graph=g, zs=s_zs, rot=s_rot, out=out, epoch=epoch)
+                e = self.cache[key] = dict(graph=g, zs=s_zs, rot=s_rot, out=out, epoch=epoch, launches=launches)
             except Exception as ex:                                  # pragma: no cover - depends on the driver
                 torch.cuda.synchronize()
                 self.cache[key] = dict(failed=True, epoch=epoch)
@@ -375,6 +394,7 @@ class InferenceGraphs:
                 s.copy_(z, non_blocking=True)
         e["rot"].copy_(rot, non_blocking=True)
         e["graph"].replay()
+        GraphedFn.REPLAYED_LAUNCHES += e["launches"]
         return e["out"].clone()
 
 

@@ -203,3 +203,52 @@ def test_stage2_step_host_halves_consume_the_reference_stream():
     assert np.array_equal(t[0].numpy(), synth.imgs[sidx]) and np.array_equal(t[1].numpy(), synth.eye_masks[sidx].astype(np.float32))
     assert np.array_equal(t[2].numpy(), real.imgs[ridx]) and np.array_equal(t[3].numpy(), rflips.astype(bool))
     assert np.array_equal(t[4].numpy(), synth.metadata_inputs["rotations"][sidx])
+
+
+def test_pretrained_standins_warn_and_npz_exports_load():
+    """The VGG19 / VGGFace / ResNet50 weights the reference downloads (perceptual_loss.py:19-41, real_encoder.py:13) are
+    seeded stand-ins here: the first training / fine-tuning call says so once, and an .npz export in Keras'
+    get_weights() order (or keyed by variable name) replaces them - truncated-away trailing layers ignored, shapes checked."""
+    import warnings
+    import tempfile
+    from confignet_b200 import pretrained
+    from confignet_b200.runtime import ParamGroup, Network
+
+    class M:
+        PRETRAINED = (("perceptual_loss", "VGG19"), ("encoder", "ResNet50"))
+        config = {}
+    m = M()
+    m.perceptual_loss = Network(ParamGroup(netspec.init_params(netspec.vgg19_spec(), 1, vgg_like=True), "cpu"), lambda *a: None)
+    m.encoder = Network(ParamGroup(netspec.init_real_encoder_params(145, 2), "cpu", trainable=netspec.is_trainable), lambda *a: None)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        pretrained.warn_if_standin(m, M.PRETRAINED, "generator_training_step")
+        pretrained.warn_if_standin(m, M.PRETRAINED, "generator_training_step")
+    assert len(w) == 2 and "stand-in" in str(w[0].message)
+    rng = np.random.RandomState(0)
+    g = m.perceptual_loss.group
+    want = [rng.randn(*s).astype(np.float32) for s in g.shapes]
+    extra = [rng.randn(3, 3, 512, 512).astype(np.float32), rng.randn(512).astype(np.float32)]      # block4_conv3...: not in the spec
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "vgg19.npz")
+        np.savez(path, *(want + extra))
+        pretrained.load_vgg(g, path, "VGG19")
+        for a, b in zip(g.get_weights(), want):
+            assert np.array_equal(a, b)
+        assert g.pretrained
+        bad = list(want); bad[0] = bad[0][:2]
+        np.savez(path, *bad)
+        with pytest.raises(ValueError):
+            pretrained.load_vgg(g, path, "VGG19")
+    e = m.encoder.group
+    res = {n[len("resnet/"):]: rng.randn(*s).astype(np.float32) for n, s in zip(e.names, e.shapes) if n.startswith("resnet/")}
+    heads = {n: a for n, a in zip(e.names, e.get_weights()) if not n.startswith("resnet/")}
+    pretrained.load_resnet50(e, res)
+    got = dict(zip(e.names, e.get_weights()))
+    assert all(np.array_equal(got["resnet/" + k], v) for k, v in res.items())
+    assert all(np.array_equal(got[k], v) for k, v in heads.items())
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m2 = M(); m2.perceptual_loss, m2.encoder = m.perceptual_loss, m.encoder
+        pretrained.warn_if_standin(m2, M.PRETRAINED, "fine_tune_on_img")
+    assert not w
