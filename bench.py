@@ -132,7 +132,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         while not self.stop_flag:
             self.sample()
-            time.sleep(0.05 if self.nvml is not None else 0.2)
+            time.sleep(0.25)
 
     def begin(self):
         self.samples, self.active = [], True

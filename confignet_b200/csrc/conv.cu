@@ -622,6 +622,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   } while (!done);
 }
+// waits for two barriers at once: both polls are in flight together (one round trip instead of two when both are complete)
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
+  uint32_t da, db;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "selp.u32 %1, 1, 0, q;\n\t}"
+        : "=r"(da), "=r"(db) : "r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b) : "memory");
+  } while (!(da & db));
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -916,8 +929,11 @@ __host__ __device__ inline TcpLayout tcp_layout(int nb, int bn_smem) {
 
 // Gradient pre-pack for the wgrad GEMM: the B operand tile of (n-tile, k-block) is 32 consecutive output pixels
 // x bn_smem channels of G, MN-major (channels contiguous, as in HBM).  Same stage image format as above.
+// colpart != nullptr: the block also writes the column sums of its 32 x bn piece of G to colpart[kb][n] - the bias
+// gradient's partial sums come out of the pass that reads G anyway (sum_slabs_kernel adds the k-blocks in order).
 __global__ void __launch_bounds__(256)
-pack_grad_kernel(const float* __restrict__ G, int M, int Cn, float* __restrict__ out, int bn, int bn_smem, int total_kb) {
+pack_grad_kernel(const float* __restrict__ G, int M, int Cn, float* __restrict__ out, int bn, int bn_smem, int total_kb,
+                 float* __restrict__ colpart) {
   const int kb = blockIdx.x, nt = blockIdx.y;
   const uint32_t b_bytes = (uint32_t)bn_smem * TC_BK * 4;
   uint8_t* tile = reinterpret_cast<uint8_t*>(out) + ((size_t)nt * total_kb + kb) * 2 * b_bytes;
@@ -941,6 +957,16 @@ pack_grad_kernel(const float* __restrict__ G, int M, int Cn, float* __restrict__
     }
     *reinterpret_cast<uint4*>(tile + off) = bg;
     *reinterpret_cast<uint4*>(tile + b_bytes + off) = sm;
+  }
+  if (colpart != nullptr) {
+    // the 32 rows were just read (they sit in L1 / L2): thread t < bn adds column n0 + t over them in row order
+    const int t = threadIdx.x, n = n0 + t;
+    if (t < bn && n < Cn) {
+      float a = 0.f;
+      const int rows = min(TC_BK, M - m0);
+      for (int r = 0; r < rows; ++r) a += __ldg(G + (size_t)(m0 + r) * Cn + n);
+      colpart[(size_t)kb * Cn + n] = a;
+    }
   }
 }
 
@@ -1204,14 +1230,17 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             // chunk k = 4h + q of this thread's row: register (k % LPR) * HPR + k / LPR in pixel mode, register k in wgrad mode
-            constexpr int dummy = 0; (void)dummy;
             const int kch = 4 * h + q;
             const float4 vv = WG ? v[kch] : v[(kch % TCP_LPR) * TCP_HPR + kch / TCP_LPR];
             const float x[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              bg[4 * q + e] = __float_as_uint(x[e]) & 0xffffe000u;
-              sm[4 * q + e] = __float_as_uint(x[e] - __uint_as_float(bg[4 * q + e])) & 0xffffe000u;
+              // kind::tf32 reads the upper 19 bits of an operand word and ignores the 13 low mantissa bits (measured:
+              // profiles/r02_probes_first_run.txt, probe 1 - truncation, exact to 1.6e-7): the big half is the RAW value,
+              // the small half the exact residual x - trunc(x), itself truncated by the tensor core.  2 ALU ops per
+              // element instead of 3, bit-identical products.
+              bg[4 * q + e] = __float_as_uint(x[e]);
+              sm[4 * q + e] = __float_as_uint(x[e] - __uint_as_float(__float_as_uint(x[e]) & 0xffffe000u));
             }
           }
           tc_st16_nowait(a_t + 16 * h, bg);
@@ -1343,40 +1372,41 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
     int sa = 0, pa = 0, sb = 0, pb = 0, b = 0, inchunk = 0, c = 0;
     const int chunk_kb = (dbg >> 8) ? (dbg >> 8) : TC_CHUNK_KB;
     uint32_t b16 = sbase >> 4;
-    int last_num_kb = 0;
+    int last_num_kb = 0;          // role timers: k-blocks of ALL items of this CTA (the per-k-block averages divide by it)
+    // ONE elected thread runs the whole role (waits, MMAs, commits): no election / reconvergence per k-block, and the
+    // two operand barriers are polled together.  Role timers (r02_role_prof_lpr2.txt) had this warp busy all the time:
+    // ~890 clk per k-block inside the issue section (the tensor pipe's back-pressure) plus ~450 clk of waits, election
+    // and bookkeeping during which the pipe ran dry.
+   if (elect_one()) {
    for (int w = w_first; w < n_items; w += w_step) {
     GemmPlan p; int m0, n0, ysel, tap0, num_kb;
     item(w, p, m0, n0, ysel, tap0, num_kb);
-    last_num_kb = num_kb;
+    last_num_kb += num_kb;
     for (int kb = 0; kb < num_kb; ++kb) {
       const bool chunk_first = inchunk == 0;
       const bool chunk_last = inchunk == chunk_kb - 1 || kb == num_kb - 1;
       long long t0 = (PROF ? clock64() : 0ll);
       if (chunk_first && c >= 2) { mbar_wait(bar_accempty + 8 * b, ((c >> 1) - 1) & 1); }
       long long t1 = (PROF ? clock64() : 0ll); pt[0] += t1 - t0;
-      mbar_wait(bar_fulla + 8 * sa, pa);
+      mbar_wait2(bar_fulla + 8 * sa, pa, bar_fullb + 8 * sb, pb);
       t0 = (PROF ? clock64() : 0ll); pt[1] += t0 - t1;
-      mbar_wait(bar_fullb + 8 * sb, pb);
-      t1 = (PROF ? clock64() : 0ll); pt[2] += t1 - t0;
+      t1 = t0;
       tc_fence_after();
-      if (elect_one()) {
-        if (!(dbg & 4)) {
-          const uint32_t d_t = tmem_base + b * bn_r;
-          const uint32_t a_big = tmem_base + a_col0 + sa * TCP_A_COLS, a_small = a_big + 32;
+      if (!(dbg & 4)) {
+        const uint32_t d_t = tmem_base + b * bn_r;
+        const uint32_t a_big = tmem_base + a_col0 + sa * TCP_A_COLS, a_small = a_big + 32;
 #pragma unroll
-          for (int kk = 0; kk < TC_BK / 8; ++kk) {
-            const uint32_t lo_big = desc_lo0 | ((b16 + kk * kk16) & 0x3fffu), lo_small = desc_lo0 | ((b16 + plane16 + kk * kk16) & 0x3fffu);
-            const uint64_t bb = ((uint64_t)desc_hi << 32) | lo_big, bs = ((uint64_t)desc_hi << 32) | lo_small;
-            tc_mma_tf32_ts(d_t, a_small + kk * 8, bb, idesc, !(chunk_first && kk == 0));
-            tc_mma_tf32_ts(d_t, a_big + kk * 8, bs, idesc, 1);
-            tc_mma_tf32_ts(d_t, a_big + kk * 8, bb, idesc, 1);
-          }
+        for (int kk = 0; kk < TC_BK / 8; ++kk) {
+          const uint32_t lo_big = desc_lo0 | ((b16 + kk * kk16) & 0x3fffu), lo_small = desc_lo0 | ((b16 + plane16 + kk * kk16) & 0x3fffu);
+          const uint64_t bb = ((uint64_t)desc_hi << 32) | lo_big, bs = ((uint64_t)desc_hi << 32) | lo_small;
+          tc_mma_tf32_ts(d_t, a_small + kk * 8, bb, idesc, !(chunk_first && kk == 0));
+          tc_mma_tf32_ts(d_t, a_big + kk * 8, bs, idesc, 1);
+          tc_mma_tf32_ts(d_t, a_big + kk * 8, bb, idesc, 1);
         }
-        tc_commit(bar_emptya + 8 * sa);
-        if (csize > 1) tc_commit_mc(bar_emptyb + 8 * sb, cmask); else tc_commit(bar_emptyb + 8 * sb);
-        if (chunk_last) tc_commit(bar_accfull + 8 * b);
       }
-      __syncwarp();
+      tc_commit(bar_emptya + 8 * sa);
+      if (csize > 1) tc_commit_mc(bar_emptyb + 8 * sb, cmask); else tc_commit(bar_emptyb + 8 * sb);
+      if (chunk_last) tc_commit(bar_accfull + 8 * b);
       if (++sa == na) { sa = 0; pa ^= 1; }
       b16 += stage16;
       if (++sb == nb) { sb = 0; pb ^= 1; b16 = sbase >> 4; }
@@ -1385,7 +1415,9 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
     }
     if (inchunk != 0) { inchunk = 0; ++c; b ^= 1; }      // the item's last chunk was committed short: the next item starts a new one
    }
-    if (do_prof && lane == 0) { prof[4] = pt[0]; prof[5] = pt[1]; prof[6] = pt[2]; prof[7] = pt[3]; prof[8] = (PROF ? clock64() : 0ll) - t_begin; prof[9] = last_num_kb; }
+    if (do_prof) { prof[4] = pt[0]; prof[5] = pt[1]; prof[6] = 0; prof[7] = pt[3]; prof[8] = (PROF ? clock64() : 0ll) - t_begin; prof[9] = last_num_kb; }
+   }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -2268,7 +2300,7 @@ int cn_skinny_fwd(const cn_conv_desc* d, const float* x, const float* w, const f
                   float* y, cudaStream_t st);
 int cn_skinny_dgrad(const cn_conv_desc* d, const float* gy, const float* w, float* gx, cudaStream_t st);
 size_t cn_skinny_wgrad_scratch(const cn_conv_desc* d);
-int cn_skinny_wgrad(const cn_conv_desc* d, const float* x, const float* gy, float* gw, float* scratch, cudaStream_t st);
+int cn_skinny_wgrad(const cn_conv_desc* d, const float* x, const float* gy, float* gw, float* gbias, float* scratch, cudaStream_t st);
 
 static size_t conv_numel_x(const cn_conv_desc* d) {
   return (size_t)d->batch * d->in_dims[0] * d->in_dims[1] * d->in_dims[2] * d->cin;
@@ -2362,7 +2394,8 @@ static bool wgrad_tc_eligible(const GemmPlan& g) {
 }
 
 // Weight-gradient GEMM on the tensor cores: out[(tap,c)][n] = sum_m src[pix(m,tap)][c] * G[m][n]
-static int launch_wgrad_tc(const GemmPlan& g, const float* src, const float* G, float* out, cudaStream_t st) {
+// gbias != nullptr (and G is the layer's output gradient): the bias gradient = column sums of G comes out of the pack pass
+static int launch_wgrad_tc(const GemmPlan& g, const float* src, const float* G, float* out, cudaStream_t st, float* gbias = nullptr) {
   const size_t wn = (size_t)g.Ktot * g.Cn;
   int bn, bn_smem; pick_bn_mn(g.Cn, &bn, &bn_smem);
   int mt = (g.Ktot + TC_BM - 1) / TC_BM, nt = (g.Cn + bn - 1) / bn;
@@ -2380,8 +2413,14 @@ static int launch_wgrad_tc(const GemmPlan& g, const float* src, const float* G, 
   float* gp = nullptr;
   rc = packed_buffer(nullptr, (size_t)nt * total_kb * 2 * bn_smem * TC_BK * 4, &gp);
   if (rc) return rc;
-  pack_grad_kernel<<<dim3(total_kb, nt), 256, 0, st>>>(G, g.M, g.Cn, gp, bn, bn_smem, total_kb);
+  float* colpart = nullptr;
+  if (gbias != nullptr) { rc = packed_buffer(&k_ws_bias, (size_t)total_kb * g.Cn * sizeof(float), &colpart); if (rc) return rc; }
+  pack_grad_kernel<<<dim3(total_kb, nt), 256, 0, st>>>(G, g.M, g.Cn, gp, bn, bn_smem, total_kb, colpart);
   CN_CHECK_LAUNCH();
+  if (gbias != nullptr) {
+    sum_slabs_kernel<<<(g.Cn + 31) / 32, dim3(32, 8), 0, st>>>(colpart, total_kb, g.Cn, gbias);
+    CN_CHECK_LAUNCH();
+  }
   rc = launch_tc<1, 1>(g, src, gp, nullptr, split > 1 ? ws : out, CN_ACT_NONE, 0.f, bn, bn_smem, dim3(mt, nt, 1), per, split, st, wn);
   if (rc) return rc;
   if (split > 1) return launch_splitk_reduce(ws, split, wn, g.Cn, nullptr, out, st);
@@ -2404,8 +2443,9 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
   if (skinny_ws > 0) {
     float* ws = nullptr;
     rc = packed_buffer(nullptr, skinny_ws, &ws); if (rc) return rc;
-    rc = cn_skinny_wgrad(d, x, gy, gw, ws, st);
+    rc = cn_skinny_wgrad(d, x, gy, gw, gbias, ws, st);
     if (rc < 0) return rc;
+    if (rc == 2) return CN_OK;           // weight and bias gradient both done (1x1, 3 -> 3)
   }
   bool folded = false;
   if (skinny_ws == 0 && impl != CN_IMPL_FFMA && g_fold && fold_ok(d)) {
@@ -2428,8 +2468,9 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
   } else if (skinny_ws > 0 && rc == 1) {
     // launched by skinny.cu
   } else if (tc) {
-    rc = launch_wgrad_tc(g, x, gy, gw, st);
+    rc = launch_wgrad_tc(g, x, gy, gw, st, gbias);
     if (rc) return rc;
+    if (gbias != nullptr) return CN_OK;      // the bias gradient came out of the gradient pack pass
   } else if (g.ntaps == 1 && g.Csrc <= 4 && g.Cn <= 4 && g.mstride == 1 && g.ushift == 0 && g.M >= 4096) {   // 1x1, stride 1: source pixel = output pixel
     // the small weight-gradient kernels write per-block partials (slabs); sum_slabs_kernel adds them in block order
     const int blocks = 4 * num_sms();

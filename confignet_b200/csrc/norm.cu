@@ -11,7 +11,9 @@
 // HBM-bound: one read of each operand per pass, float4 along the channel axis, warp-shuffle-free
 // column reductions (threads own channels, so no cross-lane traffic until the 8-row smem fold).
 #include "common.cuh"
+#include <stdlib.h>
 
+#define CN_SUMS_LD 8        // floats per (slice, sample, channel) record of the statistics buffer: 7 sums + 1 pad
 #define CN_FLAG_LRELU_A 1   // a := lrelu(a, alpha) before use
 #define CN_FLAG_MASK_OUT 2  // affine result *= lrelu'(a_raw)
 #define CN_FLAG_MASK_C 4    // c := c * lrelu'(a_raw)
@@ -51,7 +53,7 @@ __global__ void chan_sums_kernel(const float* __restrict__ a, const float* __res
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += sm[j][i][threadIdx.x];
-    sums[(((size_t)blockIdx.z * gridDim.y + n) * ch + col) * 7 + j] = t;
+    sums[(((size_t)blockIdx.z * gridDim.y + n) * ch + col) * CN_SUMS_LD + j] = t;
   }
 }
 
@@ -105,7 +107,7 @@ chan_sums4_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
     const int cc = o / 7, j = o - cc * 7, qq = cc >> 2, e = cc & 3;
     float t = 0.f;
     for (int k = 0; k < R; ++k) t += red[((size_t)(k * chq + qq) * 7 + j) * 4 + e];
-    sums[(((size_t)blockIdx.y * gridDim.x + n) * ch + cc) * 7 + j] = t;
+    sums[(((size_t)blockIdx.y * gridDim.x + n) * ch + cc) * CN_SUMS_LD + j] = t;
   }
 }
 
@@ -113,7 +115,11 @@ extern "C" int cn_chan_sums_splits(int n, int p, int ch) {
   if (n <= 0 || p <= 0 || ch <= 0) return 1;
   int cb = (ch + 31) / 32;
   if (ch % 4 == 0 && ch <= 1024) cb = 1;           // float4 kernel: one block per (sample, slice), ~2 blocks per SM
-  int psplit = ((ch % 4 == 0 && ch <= 1024 ? 2 : 4) * 148 + cb * n - 1) / (cb * n);
+  // ~4 blocks of 256 threads per SM: a one-operand pass needs that many 16-byte loads in flight to approach the HBM rate
+  // (measured with 2 per SM: 2.1 TB/s on one operand, 4.9 TB/s on two - profiles/r02_launches_v11_summary.txt)
+  static int per_sm = 0;
+  if (per_sm == 0) { const char* e = getenv("CN_SUMS_BLOCKS_PER_SM"); per_sm = e ? atoi(e) : 4; if (per_sm < 1) per_sm = 4; }
+  int psplit = (per_sm * 148 + cb * n - 1) / (cb * n);
   int maxsplit = (p + 63) / 64;
   if (psplit > maxsplit) psplit = maxsplit;
   if (psplit < 1) psplit = 1;
@@ -199,7 +205,8 @@ extern "C" int cn_chan_affine(const float* a, const float* b, const float* c, co
 
 // ------------------------------------------------------------------------------------------------
 // Coefficient kernels: one thread per channel, loop over samples (so per-channel parameter
-// gradients need no second reduction).  S(n,c,j) = sums[(n*ch+c)*7+j], N = pixels per sample.
+// gradients need no second reduction).  S(n,c,j) = sums[(n*ch+c)*8+j] (7 sums, padded to 32 bytes so that a slice is two
+// 16-byte loads), N = pixels per sample.
 // ------------------------------------------------------------------------------------------------
 enum {
   CN_COEF_IN_FWD = 0,       // p0=gamma p1=beta            -> coef0
@@ -231,9 +238,9 @@ norm_coef_kernel(int kind, const float* __restrict__ sums, int nsplit, const flo
     for (int j = 0; j < 7; ++j) S[j] = 0.f;
 #pragma unroll 4
     for (int z = 0; z < nsplit; ++z) {          // independent loads: let several slices be in flight
-      const float* Sz = sums + (((size_t)z * n + i) * ch + c) * 7;
-#pragma unroll
-      for (int j = 0; j < 7; ++j) S[j] += Sz[j];
+      const float4* Sz = reinterpret_cast<const float4*>(sums + (((size_t)z * n + i) * ch + c) * CN_SUMS_LD);
+      const float4 lo = Sz[0], hi = Sz[1];
+      S[0] += lo.x; S[1] += lo.y; S[2] += lo.z; S[3] += lo.w; S[4] += hi.x; S[5] += hi.y; S[6] += hi.z;
     }
     const size_t nc = (size_t)i * ch + c;
     const float mu = S[0] * invN;

@@ -503,6 +503,110 @@ int sm_count() {
   return g_sms;
 }
 
+// ------------------------------------------------------------------------------------------------
+// p3: Conv2D(3 -> 3, 1x1, stride 1) - the discriminators' / latent regressor's fromRGB layer
+// (hologan_discriminator.py:20-26,75-81, initial_1x1_conv).  A pixel is 12 bytes in and 12 bytes out: the tensor is walked
+// as a flat stream, 4 pixels = 3 float4 per thread per step, so every load / store is a full-width coalesced access and
+// the kernel runs at the copy rate (the generic thread-per-pixel kernel spent its time in row decodes and 4-byte accesses:
+// 40 us per launch for 50 MB, profiles/r01_conv_breakdown_final.txt).
+//   forward : y[p][n] = b[n] + sum_c x[p][c] W[c][n]        (T = 0)
+//   dgrad   : gx[p][c] = sum_n gy[p][n] W[c][n]             (T = 1: the same kernel with W transposed)
+//   wgrad   : gW[c][n] = sum_p x[p][c] gy[p][n], gb[n] = sum_p gy[p][n]: per-block partials + ordered sum
+// ------------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(256)
+p3_map_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
+              size_t ngroups, size_t npix, int act, float alpha) {
+  float W[3][3], B[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int n = 0; n < 3; ++n) W[c][n] = T ? __ldg(w + n * 3 + c) : __ldg(w + c * 3 + n);
+#pragma unroll
+  for (int n = 0; n < 3; ++n) B[n] = bias != nullptr ? __ldg(bias + n) : 0.f;
+  for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ngroups; g += (size_t)gridDim.x * 256) {
+    float v[12], o[12];
+    if (4 * g + 4 <= npix) {
+      const float4 a = ldg4(x + 12 * g), b = ldg4(x + 12 * g + 4), c = ldg4(x + 12 * g + 8);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) v[i] = (12 * g + i < 3 * npix) ? __ldg(x + 12 * g + i) : 0.f;
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        float r = B[n];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) r = fmaf(v[3 * p + c], W[c][n], r);
+        o[3 * p + n] = cn_apply_act(r, act, alpha);
+      }
+    if (4 * g + 4 <= npix) {
+      float4* dst = reinterpret_cast<float4*>(y + 12 * g);
+      dst[0] = make_float4(o[0], o[1], o[2], o[3]); dst[1] = make_float4(o[4], o[5], o[6], o[7]); dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) if (12 * g + i < 3 * npix) y[12 * g + i] = o[i];
+    }
+  }
+}
+
+// part[block][12]: 9 weight-gradient sums then 3 bias-gradient sums of the block's pixels (fixed order inside the block)
+__global__ void __launch_bounds__(256)
+p3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ part, size_t ngroups, size_t npix) {
+  float acc[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+  for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ngroups; g += (size_t)gridDim.x * 256) {
+    float v[12], u[12];
+    if (4 * g + 4 <= npix) {
+      const float4 a = ldg4(x + 12 * g), b = ldg4(x + 12 * g + 4), c = ldg4(x + 12 * g + 8);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+      const float4 d = ldg4(gy + 12 * g), e = ldg4(gy + 12 * g + 4), f = ldg4(gy + 12 * g + 8);
+      u[0] = d.x; u[1] = d.y; u[2] = d.z; u[3] = d.w; u[4] = e.x; u[5] = e.y; u[6] = e.z; u[7] = e.w;
+      u[8] = f.x; u[9] = f.y; u[10] = f.z; u[11] = f.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const bool ok = 12 * g + i < 3 * npix;
+        v[i] = ok ? __ldg(x + 12 * g + i) : 0.f; u[i] = ok ? __ldg(gy + 12 * g + i) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int n = 0; n < 3; ++n) acc[c * 3 + n] = fmaf(v[3 * p + c], u[3 * p + n], acc[c * 3 + n]);
+#pragma unroll
+      for (int n = 0; n < 3; ++n) acc[9 + n] += u[3 * p + n];
+    }
+  }
+  __shared__ float red[8][12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    float t = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    float t = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) t += red[wq][threadIdx.x];
+    part[(size_t)blockIdx.x * 12 + threadIdx.x] = t;
+  }
+}
+
+bool is_p3(const cn_conv_desc* d) {
+  return d->nd == 2 && d->cin == 3 && d->cout == 3 && d->ksize[0] == 1 && d->ksize[1] == 1 && d->stride == 1 && d->upsample == 1 &&
+         d->pad <= 0;
+}
+
 void same_pad(int in, int k, int s, int* out, int* pb) {
   *out = (in + s - 1) / s;
   int tot = (*out - 1) * s + k - in;
@@ -536,6 +640,13 @@ int opt_in_smem(K kernel, int bytes) {
 int cn_skinny_fwd(const cn_conv_desc* d, const float* x, const float* w, const float* bias, int act, float alpha,
                   float* y, cudaStream_t st) {
   const int H = d->in_dims[0], W = d->in_dims[1];
+  if (is_p3(d)) {
+    const size_t npix = (size_t)d->batch * H * W, ng = (npix + 3) / 4;
+    int blocks = (int)((ng + 255) / 256); if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+    p3_map_kernel<0><<<blocks, 256, 0, st>>>(x, w, bias, y, ng, npix, act, alpha);
+    CN_CHECK_LAUNCH();
+    return 1;
+  }
   if (is_c3(d)) {
     int OH, OW, pby, pbx;
     same_pad(H, 3, d->stride, &OH, &pby); same_pad(W, 3, d->stride, &OW, &pbx);
@@ -560,6 +671,13 @@ int cn_skinny_fwd(const cn_conv_desc* d, const float* x, const float* w, const f
 
 int cn_skinny_dgrad(const cn_conv_desc* d, const float* gy, const float* w, float* gx, cudaStream_t st) {
   const int H = d->in_dims[0], W = d->in_dims[1];
+  if (is_p3(d)) {
+    const size_t npix = (size_t)d->batch * H * W, ng = (npix + 3) / 4;
+    int blocks = (int)((ng + 255) / 256); if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+    p3_map_kernel<1><<<blocks, 256, 0, st>>>(gy, w, nullptr, gx, ng, npix, CN_ACT_NONE, 0.f);
+    CN_CHECK_LAUNCH();
+    return 1;
+  }
   if (is_c3(d)) {
     int OH, OW, pby, pbx;
     same_pad(H, 3, d->stride, &OH, &pby); same_pad(W, 3, d->stride, &OW, &pbx);
@@ -594,13 +712,32 @@ int cn_skinny_dgrad(const cn_conv_desc* d, const float* gy, const float* w, floa
 }
 
 size_t cn_skinny_wgrad_scratch(const cn_conv_desc* d) {
+  if (is_p3(d)) return (size_t)(4 * sm_count() + 1) * 12 * sizeof(float);
   if (is_c3(d)) return (size_t)2 * sm_count() * 27 * d->cout * sizeof(float);
   if (is_up4c3(d)) return (size_t)2 * sm_count() * 25 * 32 * 3 * sizeof(float);
   return 0;
 }
 
-int cn_skinny_wgrad(const cn_conv_desc* d, const float* x, const float* gy, float* gw, float* scratch, cudaStream_t st) {
+// p3 (1x1, 3 -> 3) also produces the bias gradient when gbias != nullptr and then returns 2
+__global__ void p3_finish_kernel(const float* __restrict__ sum12, float* __restrict__ gw, float* __restrict__ gbias) {
+  const int i = threadIdx.x;
+  if (i < 9) gw[i] = sum12[i];
+  else if (i < 12 && gbias != nullptr) gbias[i - 9] = sum12[i];
+}
+int cn_skinny_wgrad(const cn_conv_desc* d, const float* x, const float* gy, float* gw, float* gbias, float* scratch, cudaStream_t st) {
   const int H = d->in_dims[0], W = d->in_dims[1];
+  if (is_p3(d)) {
+    const size_t npix = (size_t)d->batch * H * W, ng = (npix + 3) / 4;
+    int blocks = (int)((ng + 255) / 256); if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+    p3_wgrad_kernel<<<blocks, 256, 0, st>>>(x, gy, scratch, ng, npix);
+    CN_CHECK_LAUNCH();
+    float* sum12 = scratch + (size_t)4 * sm_count() * 12;
+    sum_partials_kernel<<<1, dim3(32, 8), 0, st>>>(scratch, blocks, 12, sum12);
+    CN_CHECK_LAUNCH();
+    p3_finish_kernel<<<1, 32, 0, st>>>(sum12, gw, gbias);
+    CN_CHECK_LAUNCH();
+    return gbias != nullptr ? 2 : 1;
+  }
   if (is_c3(d) && d->cout == 48) {
     int OH, OW, pby, pbx;
     same_pad(H, 3, d->stride, &OH, &pby); same_pad(W, 3, d->stride, &OW, &pbx);

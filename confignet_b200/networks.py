@@ -262,10 +262,10 @@ def latent_regression_loss(p_lr, imgs, labels, n_layers=5):
 
 
 def _sum(vals):
-    total = None
-    for v in vals:
-        total = v if total is None else total + v
-    return total
+    """tf.reduce_sum(list(losses.values())) (confignet_first_stage.py:553, losses.py:44): one stack + one sum instead of a
+    chain of ~20 scalar additions (each a launch of its own on the device)."""
+    vals = [v.reshape(()) for v in vals]
+    return vals[0] if len(vals) == 1 else torch.stack(vals).sum()
 
 
 # ------------------------------------------------------------------------------------------------ second stage

@@ -268,7 +268,7 @@ def _sums(a, b=None, c=None, flags=0, alpha=0.0):
     ns = _SPLITS.get((n, p, ch))
     if ns is None:
         ns = _SPLITS[(n, p, ch)] = int(L.load().cn_chan_sums_splits(n, p, ch))
-    s = torch.empty((ns, n, ch, 7), device=a.device, dtype=torch.float32)
+    s = torch.empty((ns, n, ch, 8), device=a.device, dtype=torch.float32)       # 7 sums + 1 pad per record (csrc/norm.cu)
     L.call("cn_chan_sums", _p(a), _p(b), _p(c), n, p, ch, flags, alpha, _p(s), _stream())
     return s
 

@@ -105,8 +105,8 @@ int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float* gy, float*
 #define CN_FLAG_LRELU_A 1   /* a := lrelu(a, alpha) before use                    */
 #define CN_FLAG_MASK_OUT 2  /* affine result *= lrelu'(a_raw)                     */
 #define CN_FLAG_MASK_C 4    /* c := c * lrelu'(a_raw)                             */
-/* sums[((z*n + i)*C + ch)*7 + j]: partial sums of pixel slice z (0 <= z < cn_chan_sums_splits(n, p, ch)) of
- * sample i; the caller provides splits*n*C*7 floats, no zero-fill needed; cn_norm_coef adds the slices in a
+/* sums[((z*n + i)*C + ch)*8 + j], j < 7: partial sums of pixel slice z (0 <= z < cn_chan_sums_splits(n, p, ch)) of
+ * sample i; the caller provides splits*n*C*8 floats (16-byte aligned), no zero-fill needed; cn_norm_coef adds the slices in a
  * fixed order (bit-reproducible statistics).
  *   j: 0 sum a, 1 sum b, 2 sum c, 3 sum a*a, 4 sum a*b, 5 sum a*c, 6 sum b*c  (b, c may be NULL) */
 int cn_chan_sums_splits(int n, int p, int ch);

@@ -10,10 +10,11 @@ st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
 lib.cn_debug_set_prof.argtypes = [ctypes.c_void_p]
 buf = torch.zeros(16, dtype=torch.int64, device=dev)
-SHAPES = [(2, 32, (128, 128), 48, 96, 3, 2, 1, "fwd"), (2, 32, (128, 128), 48, 96, 3, 2, 1, "dgrad"),
-          (2, 32, (128, 128), 48, 96, 3, 2, 1, "wgrad"), (2, 16, (256, 256), 64, 64, 3, 1, 1, "fwd"),
-          (2, 16, (64, 64), 256, 256, 3, 1, 1, "fwd"), (2, 16, (64, 64), 32, 32, 4, 1, 2, "fwd"),
-          (3, 16, (16, 16, 16), 64, 64, 3, 1, 1, "fwd"), (2, 32, (32, 32), 192, 384, 3, 2, 1, "fwd")]
+SHAPES = [(2, 16, (64, 64), 256, 256, 3, 1, 1, "fwd"), (2, 16, (64, 64), 256, 256, 3, 1, 1, "dgrad"),
+          (2, 16, (256, 256), 64, 64, 3, 1, 1, "fwd"), (2, 32, (128, 128), 48, 96, 3, 2, 1, "dgrad"),
+          (2, 32, (128, 128), 48, 96, 3, 2, 1, "wgrad"), (2, 16, (128, 128), 128, 128, 3, 1, 1, "fwd")]
+if len(sys.argv) > 1:
+    SHAPES = SHAPES[:int(sys.argv[1])]
 for (nd, B, dims, cin, cout, k, s, up, op) in SHAPES:
     d = L.make_conv_desc(nd, B, dims, cin, cout, [k] * nd, s, up)
     od = (ctypes.c_int * 3)(); L.call("cn_conv_out_dims", ctypes.byref(d), od)
@@ -29,7 +30,7 @@ for (nd, B, dims, cin, cout, k, s, up, op) in SHAPES:
             L.call("cn_conv_dgrad", ctypes.byref(d), P(gy), P(w), P(gx), 0, st())
         else:
             L.call("cn_conv_wgrad", ctypes.byref(d), P(x), P(gy), P(gw), None, 0, st())
-    for cl, dbgmask in ((1, 0), (1, 16), (1, 4), (1, 20)):
+    for cl, dbgmask in ((1, 0), (1, 16), (1, 4), (1, 1)):
         lib.cn_debug_set_cluster(cl)
         lib.cn_debug_set(dbgmask)
         for _ in range(2):
@@ -43,7 +44,7 @@ for (nd, B, dims, cin, cout, k, s, up, op) in SHAPES:
         torch.cuda.synchronize()
         lib.cn_debug_set_prof(None)
         v = buf.cpu().numpy().astype(float); nkb = max(v[9], 1)
-        print("%s %s cluster=%d dbg=%d (16 = no epilogue stores, 4 = no MMA issue): %.1f us/call, CTA0: %d k-blocks, total %.0f clk (%.0f clk per k-block)" %
+        print("%s %s cluster=%d dbg=%d (16 = no epilogue stores, 4 = no MMA issue, 1 = no A loads): %.1f us/call, CTA0: %d k-blocks, total %.0f clk (%.0f clk per k-block)" %
               (op, (nd, B, dims, cin, cout, k, s, up), cl, dbgmask, us, nkb, v[12], v[12] / nkb))
         print("   gather warp0 per own k-block: wait_free_stage %.0f  split+st(+load wait) %.0f  issue_loads %.0f | role total %.0f" %
               (tuple(2 * v[i] / nkb for i in (0, 1, 2)) + (v[3],)))

@@ -54,7 +54,9 @@ SMALL = [(2, 2, (8, 8), 3, 5, 4, 1, 1), (2, 2, (8, 8), 3, 5, 3, 2, 1), (2, 1, (7
          # skinny.cu: odd sizes, rows longer than one 128-pixel segment, partial segments
          (2, 1, (9, 11), 3, 48, 3, 2, 1), (2, 1, (6, 300), 3, 48, 3, 2, 1), (2, 1, (4, 300), 3, 64, 3, 1, 1),
          (2, 3, (5, 7), 3, 48, 3, 1, 1), (2, 1, (6, 130), 32, 3, 4, 1, 2), (2, 2, (3, 5), 32, 3, 4, 1, 2),
-         (2, 1, (258, 256), 3, 48, 3, 2, 1)]
+         (2, 1, (258, 256), 3, 48, 3, 2, 1),
+         # fromRGB 1x1 3 -> 3 as a flat stream (skinny.cu p3_*): pixel counts that are / are not multiples of 4
+         (2, 1, (5, 7), 3, 3, 1, 1, 1), (2, 3, (64, 64), 3, 3, 1, 1, 1), (2, 1, (1, 1), 3, 3, 1, 1, 1)]
 TCS = [(2, 2, (16, 16), 64, 64, 3, 1, 1), (2, 2, (16, 16), 32, 32, 4, 1, 1), (2, 4, (16, 16), 48, 96, 3, 2, 1),
        (2, 2, (8, 8), 64, 32, 4, 1, 2), (3, 2, (4, 4, 4), 64, 32, 3, 1, 2), (3, 1, (8, 8, 8), 32, 64, 3, 1, 1),
        (2, 1, (16, 16), 128, 256, 1, 1, 1), (2, 2, (32, 32), 96, 192, 3, 2, 1), (2, 4, (15, 17), 64, 48, 3, 2, 1),
