@@ -131,6 +131,8 @@ def load():
         lib.cn_debug_set_wcache(int(os.environ["CN_WCACHE"]))
     if os.environ.get("CN_COAL"):              # measurement knob: channel-major epilogue pass 0 never / 1 rule / 2 always
         lib.cn_debug_set_coal(int(os.environ["CN_COAL"]))
+    if os.environ.get("CN_C3K"):               # measurement knob: 0 = first-generation c3 kernels (weights in shared memory)
+        lib.cn_debug_set_c3k(int(os.environ["CN_C3K"]))
     if os.environ.get("CN_DBG"):               # measurement knob: cn_debug_set bits (32 = thread-per-row epilogue stores)
         lib.cn_debug_set(int(os.environ["CN_DBG"]))
     if os.environ.get("CN_CLUSTER"):

@@ -24,6 +24,7 @@
 //
 // Reference call sites: keras Conv2D/Conv3D/Dense in confignet/dnn_models/*.py (see include/confignet_b200.h).
 #include "common.cuh"
+#include <cuda.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -743,8 +744,15 @@ __device__ __forceinline__ uint32_t mn_chunk_off(int r, int jn, uint32_t sbo) {
 constexpr int TC_BM = 128;        // GEMM rows per CTA (UMMA M)
 constexpr int TC_BK = 32;         // K elements per stage = one 128-byte swizzle row of tf32
 constexpr int TC_CHUNK_KB = 8;    // k-blocks (256 K elements) accumulated in the tensor core before promotion
-constexpr int TC_TOT_LD = 129;    // leading dimension of the running total [column][row] in shared memory: lane = row (promotion)
-                                  // and lane = column (the coalesced final pass) are both conflict-free
+// The running total of the chunked promotion lives in shared memory as ceil(bn / 32) chunks of [128 rows][32 columns]
+// fp32 with the 16-byte units of a row XOR-ed with (row & 7): exactly the SWIZZLE_128B box layout of a TMA tensor store
+// (the final tile leaves through cp.async.bulk.tensor straight from here), conflict-free for the promotion's per-row
+// 16-byte accesses (a quarter warp = 8 consecutive rows = 8 different units) and for the channel-major pass (one row =
+// one 128-byte line).
+constexpr int TC_TOT_CHUNK = 128 * 128;   // bytes per 32-column chunk
+__device__ __forceinline__ uint32_t tot_unit_off(int row, int unit) {      // byte offset of 16-byte unit `unit` (0..7) of `row` inside a chunk
+  return (uint32_t)row * 128u + ((uint32_t)(unit ^ (row & 7)) << 4);
+}
 
 // The tensor core adds into its fp32 accumulator with truncation: measured on B200 the result drifts by
 // ~1.1e-8 * K relative (1.2e-4 at K = 18432), a bias that plain fp32 FMAs do not have.  So the MMA warp
@@ -753,15 +761,16 @@ constexpr int TC_TOT_LD = 129;    // leading dimension of the running total [col
 // tensor core works on the next chunk.  store(cb, v) receives the final 32-column groups of this thread's
 // accumulator row.  The running total lives in shared memory ([column][128 rows] fp32: lane = row, so the
 // accesses are conflict-free), which leaves the tensor memory to the two accumulators and the A stages.
-template <class StoreFn>
-__device__ __forceinline__ void tc_promote_smem_and_store(uint32_t tmem_base, float* tot, int pw, int bn, int bn_r, int c0, int nchunks,
-                                                          uint32_t bar_accfull, uint32_t bar_accempty, bool keep_last, StoreFn store) {
+template <class StoreFn, class KeepFn>
+__device__ __forceinline__ void tc_promote_smem_and_store(uint32_t tmem_base, uint8_t* tot, int pw, int bn, int bn_r, int c0, int nchunks,
+                                                          uint32_t bar_accfull, uint32_t bar_accempty, bool keep_last, StoreFn store, KeepFn keep) {
   // c0 = accumulation chunks this CTA has consumed before this item (persistent CTAs): the ping-pong accumulator
   // and the barrier phases follow the GLOBAL chunk index; every chunk, the last of an item included, releases its
   // accumulator so that a later item can reuse it.
-  // keep_last: the final sums stay in `tot` as well (the caller then writes them with lanes along the channels)
+  // keep_last: the final sums go back to `tot` after keep(cb, v) has finished them (bias, activation) - the caller then
+  // writes the tile from shared memory (TMA tensor store, or lanes along the channels); else store(cb, v) writes them.
   const uint32_t lanebits = (uint32_t)(pw * 32) << 16;
-  float* mine = tot + pw * 32 + (threadIdx.x & 31);
+  const int row = pw * 32 + (threadIdx.x & 31);
   for (int c = 0; c < nchunks; ++c) {
     const int gc = c0 + c;
     const int b = gc & 1;
@@ -771,20 +780,36 @@ __device__ __forceinline__ void tc_promote_smem_and_store(uint32_t tmem_base, fl
     for (int cb = 0; cb < bn; cb += 32) {
       uint32_t v[32];
       tc_ld32(tmem_base + lanebits + b * bn_r + cb, v);
+      uint8_t* chunk = tot + (cb >> 5) * TC_TOT_CHUNK;
       if (c > 0) {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + mine[(cb + q) * TC_TOT_LD]);
+        for (int u = 0; u < 8; ++u) {
+          const float4 t = *reinterpret_cast<const float4*>(chunk + tot_unit_off(row, u));
+          v[4 * u] = __float_as_uint(__uint_as_float(v[4 * u]) + t.x); v[4 * u + 1] = __float_as_uint(__uint_as_float(v[4 * u + 1]) + t.y);
+          v[4 * u + 2] = __float_as_uint(__uint_as_float(v[4 * u + 2]) + t.z); v[4 * u + 3] = __float_as_uint(__uint_as_float(v[4 * u + 3]) + t.w);
+        }
       }
-      if (!last || keep_last) {
+      if (last && !keep_last) { store(cb, v); continue; }
+      if (last) keep(cb, v);
 #pragma unroll
-        for (int q = 0; q < 32; ++q) mine[(cb + q) * TC_TOT_LD] = __uint_as_float(v[q]);
-      } else {
-        store(cb, v);
-      }
+      for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<float4*>(chunk + tot_unit_off(row, u)) =
+            make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3]));
     }
     tc_fence_before(); __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(bar_accempty + 8 * b);
   }
 }
+
+// TMA tensor store of one 32-column chunk of the finished tile: box {32 channels, 128 rows} at (column c0, row r0) of the
+// layer's output seen as a (rows, channels) matrix; rows / columns beyond the tensor are clipped by the unit.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int r0) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(r0), "r"(smem_src) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }     // the 4 promotion / epilogue warps
 
 // Weight pre-pack: writes, for every (n-tile, k-block), the exact shared-memory image of the B stage
 // (big tile then small tile, swizzled) so that the conv kernel fetches a whole B stage with ONE bulk copy
@@ -907,10 +932,7 @@ constexpr int TCP_MAX_A = 6;         // A stages in tensor memory (as many as fi
 #define CN_LPR 2      // measured best on every fwd / dgrad layer of the bench step but two (1 / 2 / 4 / 8: 33.3 / 30.9 / 32.2 / 40.0 ms per step)
 #endif
 constexpr int TCP_LPR = CN_LPR;
-constexpr int TCP_RPI = 32 / TCP_LPR;            // rows per load instruction
 constexpr int TCP_HPR = 8 / TCP_LPR;             // load instructions per row group (chunk groups of LPR chunks)
-// GEMM row (inside its 32-row group) held by tensor-memory lane `lane`: lane = (r, c), row = c * TCP_RPI + r
-__device__ __forceinline__ int tcp_row_of_lane(int lane) { return (lane & (TCP_LPR - 1)) * TCP_RPI + (lane / TCP_LPR); }
 struct TcpLayout {
   // dynamic smem, 1024-byte aligned: nb B stages [B big][B small]; running total [bn_r][128] fp32; barriers, tmem ptr, taps
   uint32_t stage_bytes, b_bytes, tot_off, bar_off, tmem_off, taps_off, total;
@@ -920,7 +942,7 @@ __host__ __device__ inline TcpLayout tcp_layout(int nb, int bn_smem) {
   l.b_bytes = bn_smem * TC_BK * 4;
   l.stage_bytes = 2 * l.b_bytes;
   l.tot_off = nb * l.stage_bytes;
-  l.bar_off = (l.tot_off + ((bn_smem + 31) / 32 * 32) * TC_TOT_LD * 4 + 7) & ~7u;
+  l.bar_off = l.tot_off + ((bn_smem + 31) / 32) * TC_TOT_CHUNK;
   l.tmem_off = l.bar_off + (2 * nb + 2 * TCP_MAX_A + 4) * 8;      // full_b[], empty_b[], full_a[], empty_a[], acc_full[2], acc_empty[2]
   l.taps_off = (l.tmem_off + 4 + 7) & ~7u;
   l.total = l.taps_off + 256 * 8;
@@ -1022,7 +1044,7 @@ __global__ void __launch_bounds__(TCP_THREADS)
 igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const float* __restrict__ Wp,
                       const float* __restrict__ bias, float* __restrict__ D, int act, float alpha,
                       int bn, int bn_smem, int nb, int tmem_cols, int kb_per_split, long long part_stride,
-                      int csize, int ny, int dbg, long long* prof) {
+                      int csize, int ny, int dbg, long long* prof, const __grid_constant__ CUtensorMap omap) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // Work items.  ny == 0 (wgrad, clusters): one item per CTA, (blockIdx.x, blockIdx.y) = (M tile, n-tile/phase).
@@ -1099,10 +1121,10 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
     const int kb_first = (par - gk_base) & 1;
     gk_base += num_kb;
     // ---- pixel mode state.  Gather map (TCP_LPR lanes per row): load instruction i = g * TCP_HPR + h, lane (r, c) =
-    // (lane / LPR, lane % LPR) reads the 16-byte chunk h * LPR + c of row g * TCP_RPI + r of the warp's 32-row group.
-    // After the transpose (put_a) thread (r, c) holds the eight chunks of row c * TCP_RPI + r = tcp_row_of_lane(lane),
-    // splits them and writes them to ITS tensor-memory lane; the epilogue uses the same row <-> lane map.
-    const RowInfo row = decode_row(p, WG ? p.M : m0 + q4 * 32 + tcp_row_of_lane(lane));
+    // (lane / LPR, lane % LPR) reads the 16-byte chunk h * LPR + c of row r * LPR + g of the warp's 32-row group - the
+    // LPR lanes of a group read adjacent chunks of one row.  After the transpose (put_a) thread (r, c) holds the eight
+    // chunks of row r * LPR + c = ITS OWN lane index, splits them and writes them to its tensor-memory lane.
+    const RowInfo row = decode_row(p, WG ? p.M : m0 + q4 * 32 + lane);
     auto src_off = [&](int kt) -> uint32_t {
       if (kt >= p.ntaps) return 0xffffffffu;
       const uint32_t sp = src_pixel(p, row, s_taps[tap0 + kt].x);
@@ -1124,7 +1146,7 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
         if (l_kt != l_so_kt) { l_so = src_off(l_kt); l_so_kt = l_kt; }
 #pragma unroll
         for (int g = 0; g < TCP_LPR; ++g) {
-          const uint32_t so = TCP_LPR == 1 ? l_so : __shfl_sync(0xffffffffu, l_so, r * TCP_LPR + g);    // owner of row g * RPI + r
+          const uint32_t so = TCP_LPR == 1 ? l_so : __shfl_sync(0xffffffffu, l_so, r * TCP_LPR + g);    // owner of row r * LPR + g
 #pragma unroll
           for (int h = 0; h < TCP_HPR; ++h)
             v[g * TCP_HPR + h] = (so != 0xffffffffu && !skip) ? ldg128(A + (size_t)so + l_c + 4 * (h * TCP_LPR + c))
@@ -1156,7 +1178,7 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
       pt[2] += (PROF ? clock64() : 0ll) - t0;
     };
     // LPR x LPR transpose of the register index g against the lane's chunk slot c (per h): afterwards register
-    // g' * TCP_HPR + h of lane (r, c) holds chunk h * LPR + g' of row c * TCP_RPI + r
+    // g' * TCP_HPR + h of lane (r, c) holds chunk h * LPR + g' of row r * LPR + c (= lane)
     auto transpose_rows = [&](float4* v) {
 #pragma unroll
       for (int m = 1; m < TCP_LPR; m <<= 1) {
@@ -1271,16 +1293,24 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
     const int pw = warp - 8;
     const int chunk_kb = (dbg >> 8) ? (dbg >> 8) : TC_CHUNK_KB;
     int c0 = 0;                              // accumulation chunks of this CTA's earlier items
+    bool tma_pending = false;                // a TMA tensor store of this CTA may still be reading the running-total buffer
    for (int w = w_first; w < n_items; w += w_step) {
     GemmPlan p; int m0, n0, ysel, tap0, num_kb;
     item(w, p, m0, n0, ysel, tap0, num_kb);
-    const int m = m0 + pw * 32 + (WG ? lane : tcp_row_of_lane(lane));     // pixel mode: the gather's row <-> lane map
+    const int m = m0 + pw * 32 + lane;
     const bool mok = m < (WG ? p.Ktot : p.M);
     const size_t rowoff = mok ? (WG ? (size_t)m : (size_t)dest_pixel(p, m)) * p.Cn : 0;
     const int nchunks = (num_kb + chunk_kb - 1) / chunk_kb;
-    const bool coal = (dbg & 32) != 0;  // final pass with the lanes along the channels: every store instruction writes whole lines
-    float* tot = reinterpret_cast<float*>(smem + L.tot_off);
-    tc_promote_smem_and_store(tmem_base, tot, pw, bn, bn_r, c0, nchunks, bar_accfull, bar_accempty, coal,
+    // how the finished tile leaves: dbg bit 6 = TMA tensor store from the running-total buffer, bit 5 = a pass with the
+    // lanes along the channels, else every thread stores its own row
+    const bool tma_out = (dbg & 64) != 0, coal = (dbg & 32) != 0;
+    uint8_t* tot = smem + L.tot_off;
+    if (tma_out && tma_pending) {          // the previous item's stores must have read the buffer before it is written again
+      if (pw == 0 && lane == 0) tma_store_wait_read();
+      epi_bar_sync();
+      tma_pending = false;
+    }
+    tc_promote_smem_and_store(tmem_base, tot, pw, bn, bn_r, c0, nchunks, bar_accfull, bar_accempty, coal || tma_out,
                               [&](int cb, const uint32_t* v) {
       if (mok && !(dbg & 16)) {
 #pragma unroll
@@ -1301,34 +1331,45 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
           }
         }
       }
+    },
+                              [&](int cb, uint32_t* v) {
+      // finish the sums in registers (bias, activation) before they go back to the buffer
+      if (part_stride) return;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int n = n0 + cb + q;
+        float o = __uint_as_float(v[q]);
+        if (bias != nullptr && cb + q < bn && n < p.Cn) o += bias[n];
+        v[q] = __float_as_uint(cn_apply_act(o, act, alpha));
+      }
     });
-    if (coal) {
-      // The thread-per-row stores above put 32 different lines under one instruction (measured: 22-33 % of the kernel,
-      // profiles/r01_role_prof_v8_persistent.txt).  Here a warp walks the 32 rows it promoted itself (no cross-warp
-      // dependency) with its lanes along the channels: one 128-byte line per instruction.
+    if (tma_out) {
+      // generic-proxy writes -> visible to the TMA unit, all four warps done, then ONE thread stores the chunks: no
+      // store instruction of this warp touches global memory, partial tiles are clipped by the tensor map
+      fence_proxy_async();
+      epi_bar_sync();
+      if (pw == 0 && lane == 0 && !(dbg & 16)) {
+        for (int cb = 0; cb < bn; cb += 32) tma_store_2d(&omap, smem_u32(tot + (cb >> 5) * TC_TOT_CHUNK), n0 + cb, m0);
+        tma_store_commit();
+      }
+      tma_pending = true;
+    } else if (coal) {
+      // The thread-per-row stores put 32 different lines under one instruction.  Here a warp walks the 32 rows it
+      // promoted itself (no cross-warp dependency) with its lanes along the channels: one 128-byte line per instruction.
       __syncwarp();
       float* Dz = D + (part_stride ? (size_t)blockIdx.z * (size_t)part_stride : (size_t)0);
-      const bool raw = part_stride != 0;
-      float bz[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = lane + 32 * i, n = n0 + c;
-        bz[i] = (!raw && bias != nullptr && c < bn && n < p.Cn) ? bias[n] : 0.f;
-      }
       const uint32_t myoff = mok ? (uint32_t)rowoff : 0xffffffffu;      // element offsets fit 32 bits (checked when the plan is built)
       if (!(dbg & 16)) {
 #pragma unroll 4
         for (int r = 0; r < 32; ++r) {
           const uint32_t ro = __shfl_sync(0xffffffffu, myoff, r);
           if (ro == 0xffffffffu) continue;
-          const float* src = tot + pw * 32 + r;
+          const int rr = pw * 32 + r;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int c = lane + 32 * i, n = n0 + c;
-            if (c < bn && n < p.Cn) {
-              const float v = src[c * TC_TOT_LD] + bz[i];
-              Dz[ro + n] = raw ? v : cn_apply_act(v, act, alpha);
-            }
+            if (c < bn && n < p.Cn)
+              Dz[ro + n] = *reinterpret_cast<const float*>(tot + i * TC_TOT_CHUNK + tot_unit_off(rr, lane >> 2) + (lane & 3) * 4);
           }
         }
       }
@@ -1336,6 +1377,7 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
     }
     c0 += nchunks;
    }
+    if (tma_pending && pw == 0 && lane == 0) tma_store_wait_all();      // the last tile's stores complete before the CTA leaves
   } else if (warp == TCP_B_WARP) {
     // ===== B stage fetch: the pre-packed smem image of (n-tile, k-block) is one contiguous block; this CTA
     //       fetches slice `rank` of it and multicasts it to the same offset in all CTAs of the cluster =====
@@ -1898,8 +1940,41 @@ static long long* g_prof = nullptr;   // TEST HOOK: device buffer (16 x int64) r
 extern "C" int cn_debug_set_prof(void* p) { g_prof = (long long*)p; return CN_OK; }
 static int g_dbg = 0;   // TEST HOOK (cn_debug_set): bit 0/1 skip A/B global loads, bit 2 skip MMA issue, bit 3 skip STS
 extern "C" int cn_debug_set(int v) { g_dbg = v; return CN_OK; }
-static int g_coal = 1;         // channel-major final epilogue pass: 0 never, 1 by rule (launch_tc), 2 always (cn_debug_set_coal)
+// how a finished tile leaves the tcgen05 kernel (cn_debug_set_coal): 0 = every thread stores its row, 1 = channel-major
+// pass by rule (launch_tc), 2 = channel-major pass always, 3 (default) = TMA tensor store from shared memory wherever the
+// output rows are consecutive and the launch does not split K, else as 1
+static int g_coal = 3;
 extern "C" int cn_debug_set_coal(int v) { g_coal = v; return CN_OK; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tma_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+// the layer output as a (rows, cn) fp32 matrix, box = 32 columns x 128 rows, 128-byte swizzle (the running-total layout)
+static bool make_out_map(CUtensorMap* map, float* dst, long long rows, int cn) {
+  EncodeTiledFn enc = tma_encode_fn();
+  if (enc == nullptr || ((uintptr_t)dst & 15) != 0 || (cn & 3) != 0 || rows <= 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cn, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cn * 4};
+  const cuuint32_t box[2] = {32, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dst, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 static int g_persistent = 1;   // persistent CTAs in the tcgen05 pixel kernel (cn_debug_set_persistent)
 extern "C" int cn_debug_set_persistent(int v) { g_persistent = v; return CN_OK; }
 static int g_fold = 1;     // folded upsample+conv plans (cn_debug_set_fold)
@@ -2159,7 +2234,19 @@ static int launch_tc(const GemmPlan& g, const float* src, const float* packed, c
   // Final pass of the epilogue with the lanes along the channels (whole 128-byte lines per store instruction) where it
   // was measured to pay: forward launches with full 128-column tiles (profiles/r02_epilogue_ab.txt: +6..17 % there, a loss
   // on narrow tiles and strided outputs, where one row is only 1-3 store instructions).  g_coal: 0 never, 1 rule, 2 always.
-  const bool coal = g_coal == 2 || (g_coal == 1 && B_MN && !WG && bn == 128 && g.nphase <= 1);
+  const bool coal = g_coal == 2 || ((g_coal == 1 || g_coal == 3) && B_MN && !WG && bn == 128 && g.nphase <= 1);
+  // TMA tensor store of the finished tile: the GEMM rows must be consecutive rows of the output matrix (wgrad: always;
+  // pixel mode: plain plans, i.e. no phases / strided output) and the launch must write final values (no split-K slabs)
+  CUtensorMap omap;
+  memset(&omap, 0, sizeof(omap));
+  bool tma_out = false;
+  if (g_coal == 3 && split == 1) {
+    const bool rows_consecutive = WG || (g.nphase <= 1 && g.ostride == 1 && g.ooff[0] == 0 && g.ooff[1] == 0 && g.ooff[2] == 0 &&
+                                         g.Q[0] == g.E[0] && g.Q[1] == g.E[1] && g.Q[2] == g.E[2]);
+    // a 32-column store box must stay inside this tile's columns (or fall off the tensor, where the unit clips it)
+    const bool boxes_ok = (bn % 32 == 0) || bn >= g.Cn;
+    if (rows_consecutive && boxes_ok) tma_out = make_out_map(&omap, dst, WG ? (long long)g.Ktot : (long long)g.M, g.Cn);
+  }
   // thread-block cluster along M: the CTAs of a cluster share the B stream by multicast
   int csize = g_cluster;
   while (csize > 1 && (int)grid.x < csize) csize >>= 1;
@@ -2189,7 +2276,7 @@ static int launch_tc(const GemmPlan& g, const float* src, const float* packed, c
   if (set_smem(kern, smem)) return CN_ERR_CUDA;
   CN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, g, src, packed, bias, dst, act, alpha, bn, bn_smem,
                                    nb, 512, per, (long long)(split > 1 ? part_stride : 0), csize, ny,
-                                   ((g_dbg & 0xdf) | (coal ? 32 : 0)) | (g_chunk_kb << 8), g_prof));
+                                   ((g_dbg & 0x9f) | (tma_out ? 64 : (coal ? 32 : 0))) | (g_chunk_kb << 8), g_prof, omap));
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

@@ -504,6 +504,129 @@ int sm_count() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// c3k: the c3 forward and stride-2 input gradient with the KERNEL IN THE CONSTANT BANK.  Per output pixel these layers
+// do 27 x COUT FMAs on 27 input values: the layer is FFMA-bound (0.68 GFMA for D.block0 at batch 32 = 19 us at the FP32
+// peak, the same 19 us its 125 MB take at the HBM rate) if - and only if - the inner loop is nothing but FFMAs.  The
+// first-generation kernels above read the weights from shared memory (3 - 4 LDS.128 per 12 - 24 FFMAs: shared-memory
+// bound, 72 / 109 us measured).  Here a thread owns ALL output channels of its pixel(s) and every FFMA takes its weight
+// as a constant-bank operand c[bank][imm] (the 27 x COUT kernel is copied into c_c3w, stream-ordered, before the launch):
+// no weight loads at all, 27 (forward) or 48 (gradient) shared-memory reads per 1296 FFMAs.
+//   forward : thread = one output pixel x COUT channels; the tile leaves through shared memory as whole lines
+//   dgrad s2: thread = one 2x2 cell of gx; walks its 4 neighbouring gy pixels (48 channels in registers each)
+// ------------------------------------------------------------------------------------------------
+__constant__ float c_c3w[27 * 64];
+
+template <int S, int COUT>
+__global__ void __launch_bounds__(128)
+c3k_fwd_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y,
+               int H, int W, int OH, int OW, int pby, int pbx, int act, float alpha) {
+  constexpr int C4 = COUT / 4, PSO = COUT + 4;          // padded pixel stride of the output tile: conflict-free float4 rows
+  constexpr int NCOL = 127 * S + 3, RS = NCOL * 3;
+  extern __shared__ __align__(16) float sm[];
+  float* s_x = sm;                                       // [3][RS]
+  float* s_o = sm + ((3 * RS + 3) & ~3);                 // [128][PSO]
+  const int tid = threadIdx.x, n = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * 128;
+  const int ix0 = ox0 * S - pbx;
+  for (int i = tid; i < 3 * RS; i += 128) {
+    const int r = i / RS, j = i - r * RS, col = j / 3;
+    const int iy = oy * S + r - pby, ix = ix0 + col;
+    float v = 0.f;
+    if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) v = __ldg(x + ((long long)(n * H + iy) * W + ix0) * 3 + j);
+    s_x[i] = v;
+  }
+  __syncthreads();
+  float xv[27];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int e = 0; e < 9; ++e) xv[ky * 9 + e] = s_x[ky * RS + tid * S * 3 + e];
+  float acc[COUT];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) acc[co] = bias != nullptr ? __ldg(bias + co) : 0.f;
+#pragma unroll
+  for (int k = 0; k < 27; ++k)
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv[k], c_c3w[k * COUT + co], acc[co]);
+#pragma unroll
+  for (int f = 0; f < C4; ++f)
+    *reinterpret_cast<float4*>(s_o + tid * PSO + 4 * f) =
+        make_float4(cn_apply_act(acc[4 * f], act, alpha), cn_apply_act(acc[4 * f + 1], act, alpha),
+                    cn_apply_act(acc[4 * f + 2], act, alpha), cn_apply_act(acc[4 * f + 3], act, alpha));
+  __syncthreads();
+  float* out = y + ((size_t)(n * OH + oy) * OW + ox0) * COUT;       // the 128 pixels of this block are contiguous in y
+  const int npx = min(128, OW - ox0);
+  for (int i = tid; i < npx * C4; i += 128) {
+    const int px = i / C4, f = i - px * C4;
+    *reinterpret_cast<float4*>(out + 4 * (size_t)i) = *reinterpret_cast<const float4*>(s_o + px * PSO + 4 * f);
+  }
+}
+
+// stride 2, even H and W, TF-SAME (pad 0 in front): gx[2a+dy][2b+dx][ci] = sum over ky = dy (mod 2), kx = dx (mod 2) of
+// gy[a + (dy-ky)/2][b + (dx-kx)/2][:] . w[ky][kx][ci][:]
+template <int COUT>
+__global__ void __launch_bounds__(128)
+c3k_dgrad_s2_kernel(const float* __restrict__ gy, float* __restrict__ gx, int H, int W, int OH, int OW) {
+  constexpr int C4 = COUT / 4, PS = COUT + 4, GYW = 129;
+  extern __shared__ __align__(16) float sm[];            // [2][GYW][PS]: gy rows a-1, a; columns b0-1 .. b0+127
+  const int tid = threadIdx.x, n = blockIdx.z, a = blockIdx.y, b0 = blockIdx.x * 128;
+  for (int i = tid; i < 2 * GYW * C4; i += 128) {
+    const int f = i % C4, pc = i / C4, col = pc % GYW, row = pc / GYW;
+    const int gr = a - 1 + row, gc = b0 - 1 + col;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((unsigned)gr < (unsigned)OH && (unsigned)gc < (unsigned)OW) v = ldg4(gy + ((size_t)(n * OH + gr) * OW + gc) * COUT + 4 * f);
+    *reinterpret_cast<float4*>(sm + (row * GYW + col) * PS + 4 * f) = v;
+  }
+  __syncthreads();
+  float acc[2][2][3];
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) acc[dy][dx][ci] = 0.f;
+#pragma unroll
+  for (int lrow = 0; lrow < 2; ++lrow) {
+#pragma unroll
+    for (int lc = 0; lc < 2; ++lc) {
+      float g[COUT];
+      const float* src = sm + (lrow * GYW + tid + lc) * PS;
+#pragma unroll
+      for (int f = 0; f < C4; ++f) {
+        const float4 t = *reinterpret_cast<const float4*>(src + 4 * f);
+        g[4 * f] = t.x; g[4 * f + 1] = t.y; g[4 * f + 2] = t.z; g[4 * f + 3] = t.w;
+      }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int dy = ky & 1;                            // parity of the input row this tap reaches
+        if ((dy - ky) / 2 + 1 != lrow) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int dx = kx & 1;
+          if ((dx - kx) / 2 + 1 != lc) continue;
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci) {
+            float t = acc[dy][dx][ci];
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) t = fmaf(g[co], c_c3w[((ky * 3 + kx) * 3 + ci) * COUT + co], t);
+            acc[dy][dx][ci] = t;
+          }
+        }
+      }
+    }
+  }
+  const int b = b0 + tid;
+  if (2 * b < W) {
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      float* out = gx + ((size_t)(n * H + 2 * a + dy) * W + 2 * b) * 3;     // 6 contiguous floats: pixels (2b, 2b+1)
+      *reinterpret_cast<float2*>(out) = make_float2(acc[dy][0][0], acc[dy][0][1]);
+      *reinterpret_cast<float2*>(out + 2) = make_float2(acc[dy][0][2], acc[dy][1][0]);
+      *reinterpret_cast<float2*>(out + 4) = make_float2(acc[dy][1][1], acc[dy][1][2]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // p3: Conv2D(3 -> 3, 1x1, stride 1) - the discriminators' / latent regressor's fromRGB layer
 // (hologan_discriminator.py:20-26,75-81, initial_1x1_conv).  A pixel is 12 bytes in and 12 bytes out: the tensor is walked
 // as a flat stream, 4 pixels = 3 float4 per thread per step, so every load / store is a full-width coalesced access and
@@ -602,6 +725,12 @@ p3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float
   }
 }
 
+// second-generation c3 kernels (cn_debug_set_c3k), bit 0 = forward, bit 1 = stride-2 input gradient.  Measured on B200
+// (profiles/r02_skinny_c3k.txt, D.block0 at batch 32): dgrad 119.8 -> 89.1 us; forward 85.0 -> 85.0 us (both generations sit
+// on the FP32 pipe: ptxas keeps the kernel out of the FFMA operand slot and loads it with LDC.128, and three-register
+// FFMAs issue at half rate) - so only the gradient kernel is on by default.
+int g_c3k = 2;
+
 bool is_p3(const cn_conv_desc* d) {
   return d->nd == 2 && d->cin == 3 && d->cout == 3 && d->ksize[0] == 1 && d->ksize[1] == 1 && d->stride == 1 && d->upsample == 1 &&
          d->pad <= 0;
@@ -647,6 +776,20 @@ int cn_skinny_fwd(const cn_conv_desc* d, const float* x, const float* w, const f
     CN_CHECK_LAUNCH();
     return 1;
   }
+  if (is_c3(d) && (g_c3k & 1)) {
+    int OH, OW, pby, pbx;
+    same_pad(H, 3, d->stride, &OH, &pby); same_pad(W, 3, d->stride, &OW, &pbx);
+    CN_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_c3w, w, (size_t)27 * d->cout * sizeof(float), 0, cudaMemcpyDeviceToDevice, st));
+    dim3 grid((OW + 127) / 128, OH, d->batch);
+    const int ncol = 127 * d->stride + 3;
+    const int smem = (((3 * ncol * 3 + 3) & ~3) + 128 * (d->cout + 4)) * (int)sizeof(float);
+    if (d->stride == 2 && d->cout == 48) c3k_fwd_kernel<2, 48><<<grid, 128, smem, st>>>(x, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+    else if (d->stride == 2) c3k_fwd_kernel<2, 64><<<grid, 128, smem, st>>>(x, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+    else if (d->cout == 48) c3k_fwd_kernel<1, 48><<<grid, 128, smem, st>>>(x, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+    else c3k_fwd_kernel<1, 64><<<grid, 128, smem, st>>>(x, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+    CN_CHECK_LAUNCH();
+    return 1;
+  }
   if (is_c3(d)) {
     int OH, OW, pby, pbx;
     same_pad(H, 3, d->stride, &OH, &pby); same_pad(W, 3, d->stride, &OW, &pbx);
@@ -681,6 +824,15 @@ int cn_skinny_dgrad(const cn_conv_desc* d, const float* gy, const float* w, floa
   if (is_c3(d)) {
     int OH, OW, pby, pbx;
     same_pad(H, 3, d->stride, &OH, &pby); same_pad(W, 3, d->stride, &OW, &pbx);
+    if ((g_c3k & 2) && d->stride == 2 && d->cout == 48 && H % 2 == 0 && W % 2 == 0) {
+      const int smem = 2 * 129 * (48 + 4) * (int)sizeof(float);
+      int rc = opt_in_smem(c3k_dgrad_s2_kernel<48>, smem); if (rc) return rc;
+      CN_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_c3w, w, (size_t)27 * 48 * sizeof(float), 0, cudaMemcpyDeviceToDevice, st));
+      dim3 grid((W / 2 + 127) / 128, H / 2, d->batch);
+      c3k_dgrad_s2_kernel<48><<<grid, 128, smem, st>>>(gy, gx, H, W, OH, OW);
+      CN_CHECK_LAUNCH();
+      return 1;
+    }
     if (d->stride == 2 && d->cout == 48 && H % 2 == 0 && W % 2 == 0) {
       constexpr int PS = 48;
       const int smem = (27 * 48 + 2 * 65 * PS) * 4;
@@ -761,3 +913,5 @@ int cn_skinny_wgrad(const cn_conv_desc* d, const float* x, const float* gy, floa
   }
   return 0;
 }
+
+extern "C" int cn_debug_set_c3k(int v) { g_c3k = v; return CN_OK; }
