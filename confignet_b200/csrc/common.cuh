@@ -90,6 +90,19 @@ __device__ __forceinline__ int cn_select_phase(GemmPlan& p, int by, int grid_y) 
   return by - ph * ntn;
 }
 
+// Read-only loads as volatile asm statements.  The compiler keeps volatile asm in program order, so a batch of these is
+// issued back to back; plain C++ loads of a streaming loop get sunk next to their first use - ONE load in flight per thread,
+// 0.3-0.5 of the HBM rate (SASS of the round-1 statistics / column-sum kernels, profiles/r02_hbm_kernels_batched_loads.txt).
+__device__ __forceinline__ float4 cn_ldg4_ordered(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float cn_ldg1_ordered(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ float cn_apply_act(float v, int act, float alpha) {
   if (act == CN_ACT_LRELU) return v >= 0.f ? v : v * alpha;
   if (act == CN_ACT_RELU) return v > 0.f ? v : 0.f;

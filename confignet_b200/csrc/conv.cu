@@ -31,6 +31,7 @@
 #include <mutex>
 #include <algorithm>
 #include <string.h>
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------
 // Plans (host)
@@ -806,6 +807,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sm
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(r0), "r"(smem_src) : "memory");
 }
+// The same chunk of a stride-2 PHASE tile (parity phases of the stride-2 input gradient, sub-pixel phases of the folded 2-D
+// upsample + conv): the output seen as (channels, x parity, x / 2, y parity, sample * H / 2 + y / 2); the 128 GEMM rows are
+// box {32, 1, bw, 1, 128 / bw} of it, in exactly the row order of the running-total buffer.
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t smem_src, int c0, int px, int x0, int py, int r0) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(px), "r"(x0), "r"(py), "r"(r0), "r"(smem_src) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -1349,7 +1357,13 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
       fence_proxy_async();
       epi_bar_sync();
       if (pw == 0 && lane == 0 && !(dbg & 16)) {
-        for (int cb = 0; cb < bn; cb += 32) tma_store_2d(&omap, smem_u32(tot + (cb >> 5) * TC_TOT_CHUNK), n0 + cb, m0);
+        if (!WG && p.nphase > 1) {
+          const int x0 = m0 % p.E[1], r0 = m0 / p.E[1];
+          for (int cb = 0; cb < bn; cb += 32)
+            tma_store_5d(&omap, smem_u32(tot + (cb >> 5) * TC_TOT_CHUNK), n0 + cb, p.ooff[1], x0, p.ooff[0], r0);
+        } else {
+          for (int cb = 0; cb < bn; cb += 32) tma_store_2d(&omap, smem_u32(tot + (cb >> 5) * TC_TOT_CHUNK), n0 + cb, m0);
+        }
         tma_store_commit();
       }
       tma_pending = true;
@@ -1881,6 +1895,42 @@ __global__ void colsum_kernel(const float* __restrict__ g, int rows, int n, floa
   }
 }
 
+// 16-byte form (n % 4 == 0, n <= 1024): a block owns a run of rows, thread (q, rr) owns column quad q and walks the rows
+// rr, rr + R, ... with eight loads in flight (the kernel above keeps ONE 4-byte load in flight per thread and took 34 us
+// whatever the matrix, profiles/r02_launches_s2a_summary.txt); the R row groups are folded in order.  out = [gridDim.x][n].
+__global__ void __launch_bounds__(256)
+colsum4_kernel(const float* __restrict__ g, int rows, int n, int per, float* __restrict__ out) {
+  __shared__ __align__(16) float red[1024];
+  const int nq = n >> 2, R = 256 / nq;
+  const int tid = threadIdx.x, q = tid % nq, rr = tid / nq;
+  const int rbeg = blockIdx.x * per, rend = min(rows, rbeg + per);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rr < R) {
+    int r = rbeg + rr;
+    for (; r + 7 * R < rend; r += 8 * R) {                // eight rows loaded before the first is added
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = cn_ldg4_ordered(g + (size_t)(r + u * R) * n + 4 * q);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    for (; r < rend; r += R) {
+      const float4 v = cn_ldg4_ordered(g + (size_t)r * n + 4 * q);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(red + (rr * nq + q) * 4) = acc;
+  }
+  __syncthreads();
+  if (tid < nq) {
+    float4 t = *reinterpret_cast<const float4*>(red + tid * 4);
+    for (int k = 1; k < R; ++k) {
+      const float4 v = *reinterpret_cast<const float4*>(red + (k * nq + tid) * 4);
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + (size_t)blockIdx.x * n + 4 * tid) = t;
+  }
+}
+
 // out[i] = act(bias[i % cn] + sum_z ws[z][i]) in split order: the deterministic second half of every split-K launch.
 // n4 = elements / 4 (the slabs are 16-byte aligned and cn % 4 == 0 on this path).
 __global__ void __launch_bounds__(256)
@@ -1913,21 +1963,34 @@ splitk_reduce1_kernel(const float* __restrict__ ws, int nsplit, size_t n, int cn
 // out[i] = sum_b part[b][i] for MANY slabs of FEW outputs (per-block partials of the small weight / bias gradients):
 // block (32, 8) - thread (x, y) adds the slabs y, y+8, ... of output 32*blockIdx.x + x in order, then the 8 rows are
 // folded in order.  Deterministic; a single thread walking hundreds of slabs would be a chain of dependent L2 round trips.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 sum_slabs_kernel(const float* __restrict__ part, int nslabs, int n, float* __restrict__ out) {
-  __shared__ float red[8][33];
-  const int i = blockIdx.x * 32 + threadIdx.x;
+  // block (32, Y), Y = 8 or 32 rows (sum_slabs picks 32 above 256 slabs: the 4096 per-k-block slabs of a bias gradient
+  // took 48 us with 8 rows and one load in flight); eight slabs are loaded before the first is added
+  __shared__ float red[32][33];
+  const int i = blockIdx.x * 32 + threadIdx.x, Y = blockDim.y;
   float a = 0.f;
-  if (i < n)
-    for (int b = threadIdx.y; b < nslabs; b += 8) a += part[(size_t)b * n + i];
+  if (i < n) {
+    int b = threadIdx.y;
+    for (; b + 7 * Y < nslabs; b += 8 * Y) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = cn_ldg1_ordered(part + (size_t)(b + u * Y) * n + i);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a += v[u];
+    }
+    for (; b < nslabs; b += Y) a += cn_ldg1_ordered(part + (size_t)b * n + i);
+  }
   red[threadIdx.y][threadIdx.x] = a;
   __syncthreads();
   if (threadIdx.y == 0 && i < n) {
     float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    for (int k = 0; k < Y; ++k) t += red[k][threadIdx.x];
     out[i] = t;
   }
+}
+static inline void sum_slabs(const float* part, int nslabs, int n, float* out, cudaStream_t st) {
+  sum_slabs_kernel<<<(unsigned)((n + 31) / 32), dim3(32, nslabs > 256 ? 32 : 8), 0, st>>>(part, nslabs, n, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1975,6 +2038,25 @@ static bool make_out_map(CUtensorMap* map, float* dst, long long rows, int cn) {
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dst, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// the output of a 2-D stride-2 phase plan (q = 2 e + parity): (channels, x parity, x / 2, y parity, sample * H / 2 + y / 2),
+// box {32, 1, bw, 1, 128 / bw}: one M tile of one phase
+static bool make_out_map_phased(CUtensorMap* map, float* dst, const GemmPlan& g) {
+  EncodeTiledFn enc = tma_encode_fn();
+  if (enc == nullptr || ((uintptr_t)dst & 15) != 0 || (g.Cn & 3) != 0) return false;
+  if (g.ostride != 2 || g.E[2] != 1 || g.Q[2] != 1 || g.Q[0] != 2 * g.E[0] || g.Q[1] != 2 * g.E[1]) return false;
+  for (int ph = 0; ph < g.nphase; ++ph) if (g.ph_ooff[ph] & 4) return false;
+  const int bw = g.E[1] < 128 ? g.E[1] : 128;
+  if ((g.E[1] >= 128 && g.E[1] % 128 != 0) || (g.E[1] < 128 && 128 % g.E[1] != 0)) return false;
+  const cuuint64_t C4 = (cuuint64_t)g.Cn * 4, W = (cuuint64_t)g.Q[1];
+  const cuuint64_t dims[5] = {(cuuint64_t)g.Cn, 2, (cuuint64_t)g.E[1], 2, (cuuint64_t)g.n_img * g.E[0]};
+  const cuuint64_t strides[4] = {C4, 2 * C4, W * C4, 2 * W * C4};
+  const cuuint32_t box[5] = {32, 1, (cuuint32_t)bw, 1, (cuuint32_t)(128 / bw)};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, dst, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// TMA tensor stores for 2-D stride-2 phase plans too (environment CN_TMA_PHASED=0 switches them off for A/B runs)
+static int g_tma_phased = [] { const char* e = getenv("CN_TMA_PHASED"); return e ? atoi(e) : 1; }();
 static int g_persistent = 1;   // persistent CTAs in the tcgen05 pixel kernel (cn_debug_set_persistent)
 extern "C" int cn_debug_set_persistent(int v) { g_persistent = v; return CN_OK; }
 static int g_fold = 1;     // folded upsample+conv plans (cn_debug_set_fold)
@@ -2185,7 +2267,7 @@ int cn_scratch(const void* key, size_t bytes, float** out) {
   return packed_buffer(key, bytes, out);
 }
 int cn_sum_slabs(const float* part, int nslabs, int n, float* out, cudaStream_t st) {
-  sum_slabs_kernel<<<(n + 31) / 32, dim3(32, 8), 0, st>>>(part, nslabs, n, out);
+  sum_slabs(part, nslabs, n, out, st);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }
@@ -2246,6 +2328,7 @@ static int launch_tc(const GemmPlan& g, const float* src, const float* packed, c
     // a 32-column store box must stay inside this tile's columns (or fall off the tensor, where the unit clips it)
     const bool boxes_ok = (bn % 32 == 0) || bn >= g.Cn;
     if (rows_consecutive && boxes_ok) tma_out = make_out_map(&omap, dst, WG ? (long long)g.Ktot : (long long)g.M, g.Cn);
+    else if (!WG && g.nphase > 1 && boxes_ok && g_tma_phased) tma_out = make_out_map_phased(&omap, dst, g);
   }
   // thread-block cluster along M: the CTAs of a cluster share the B stream by multicast
   int csize = g_cluster;
@@ -2505,7 +2588,7 @@ static int launch_wgrad_tc(const GemmPlan& g, const float* src, const float* G, 
   pack_grad_kernel<<<dim3(total_kb, nt), 256, 0, st>>>(G, g.M, g.Cn, gp, bn, bn_smem, total_kb, colpart);
   CN_CHECK_LAUNCH();
   if (gbias != nullptr) {
-    sum_slabs_kernel<<<(g.Cn + 31) / 32, dim3(32, 8), 0, st>>>(colpart, total_kb, g.Cn, gbias);
+    sum_slabs(colpart, total_kb, g.Cn, gbias, st);
     CN_CHECK_LAUNCH();
   }
   rc = launch_tc<1, 1>(g, src, gp, nullptr, split > 1 ? ws : out, CN_ACT_NONE, 0.f, bn, bn_smem, dim3(mt, nt, 1), per, split, st, wn);
@@ -2565,7 +2648,7 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
     rc = packed_buffer(&k_ws_small, (size_t)blocks * wn * sizeof(float), &ws); if (rc) return rc;
     wgrad_flat_kernel<<<blocks, 256, 0, st>>>(x, gy, g.M, g.Csrc, g.Cn, ws);
     CN_CHECK_LAUNCH();
-    sum_slabs_kernel<<<(unsigned)((wn + 31) / 32), dim3(32, 8), 0, st>>>(ws, blocks, (int)wn, gw);
+    sum_slabs(ws, blocks, (int)wn, gw, st);
     CN_CHECK_LAUNCH();
   } else if (g.Cn <= 4 && g.Csrc >= 8 && g.ntaps <= 16 && g.M >= 4096) {
     int warps = 16 * num_sms();
@@ -2575,7 +2658,7 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
     rc = packed_buffer(&k_ws_small, (size_t)blocks * wn * sizeof(float), &ws); if (rc) return rc;
     skinny_cfew_wgrad_kernel<<<dim3(blocks, (g.Csrc + 31) / 32), 256, 0, st>>>(g, x, gy, ws, per);
     CN_CHECK_LAUNCH();
-    sum_slabs_kernel<<<(unsigned)((wn + 31) / 32), dim3(32, 8), 0, st>>>(ws, blocks, (int)wn, gw);
+    sum_slabs(ws, blocks, (int)wn, gw, st);
     CN_CHECK_LAUNCH();
   } else if (g.Ktot <= 32 && g.Cn <= 64 && g.M >= 4096) {
     int warps = 16 * num_sms();
@@ -2585,7 +2668,7 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
     rc = packed_buffer(&k_ws_small, (size_t)blocks * wn * sizeof(float), &ws); if (rc) return rc;
     skinny_kfew_wgrad_kernel<<<blocks, 256, 0, st>>>(g, x, gy, ws, per);
     CN_CHECK_LAUNCH();
-    sum_slabs_kernel<<<(unsigned)((wn + 31) / 32), dim3(32, 8), 0, st>>>(ws, blocks, (int)wn, gw);
+    sum_slabs(ws, blocks, (int)wn, gw, st);
     CN_CHECK_LAUNCH();
   } else if ((long long)g.Ktot * g.Cn <= 256 * SKW_MAXOUT && g.M >= 4096) {
     int P = 8192 / (g.Ktot + g.Cn); if (P > 64) P = 64; if (P < 4) P = 4;
@@ -2598,7 +2681,7 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
     if (smem > 48 * 1024 && set_smem(wgrad_skinny_kernel, smem)) return CN_ERR_CUDA;
     wgrad_skinny_kernel<<<blocks, 256, smem, st>>>(g, x, gy, ws, P, per);
     CN_CHECK_LAUNCH();
-    sum_slabs_kernel<<<(unsigned)((wn + 31) / 32), dim3(32, 8), 0, st>>>(ws, blocks, (int)wn, gw);
+    sum_slabs(ws, blocks, (int)wn, gw, st);
     CN_CHECK_LAUNCH();
   } else {
     int mt = (g.Ktot + 63) / 64, nt = (g.Cn + 63) / 64;
@@ -2616,26 +2699,37 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
     if (split > 1) { rc = launch_splitk_reduce(ws, split, wn, g.Cn, nullptr, gw, st); if (rc) return rc; }
   }
   if (gbias != nullptr) {
-    // bias gradient = column sums of gy: per-block partial rows, then sum_slabs_kernel (fixed order, no atomics)
+    // bias gradient = column sums of gy: per-block partial rows, then sum_slabs_kernel (fixed order, no atomics); a
+    // matrix that one block row covers (Dense layers: 16-32 rows) is summed straight into gbias by ONE launch
     float* ws = nullptr;
     int nslabs;
     if (g.Cn < 32) {
       size_t total = (size_t)g.M * g.Cn;
       int blocks = (int)((total / 16 + 255) / 256); if (blocks > 4 * num_sms()) blocks = 4 * num_sms(); if (blocks < 1) blocks = 1;
       int used = blocks * 256 / g.Cn * g.Cn;
+      if (blocks > 1) { rc = packed_buffer(&k_ws_bias, (size_t)blocks * g.Cn * sizeof(float), &ws); if (rc) return rc; }
+      colsum_narrow_kernel<<<blocks, 256, 0, st>>>(gy, total, g.Cn, used, blocks > 1 ? ws : gbias);
+      nslabs = blocks;
+    } else if (g.M > 512 && g.Cn % 4 == 0 && g.Cn <= 1024 && ((uintptr_t)gy & 15) == 0) {
+      const int R = 256 / (g.Cn / 4);
+      int blocks = 8 * num_sms();
+      int per = (g.M + blocks - 1) / blocks; if (per < 4 * R) per = 4 * R;
+      blocks = (g.M + per - 1) / per;
       rc = packed_buffer(&k_ws_bias, (size_t)blocks * g.Cn * sizeof(float), &ws); if (rc) return rc;
-      colsum_narrow_kernel<<<blocks, 256, 0, st>>>(gy, total, g.Cn, used, ws);
+      colsum4_kernel<<<blocks, 256, 0, st>>>(gy, g.M, g.Cn, per, ws);
       nslabs = blocks;
     } else {
       int ysplit = (g.M + 511) / 512; if (ysplit > 8 * num_sms()) ysplit = 8 * num_sms(); if (ysplit < 1) ysplit = 1;
       dim3 grid((g.Cn + 31) / 32, ysplit), block(32, 8);
-      rc = packed_buffer(&k_ws_bias, (size_t)ysplit * g.Cn * sizeof(float), &ws); if (rc) return rc;
-      colsum_kernel<<<grid, block, 0, st>>>(gy, g.M, g.Cn, ws);
+      if (ysplit > 1) { rc = packed_buffer(&k_ws_bias, (size_t)ysplit * g.Cn * sizeof(float), &ws); if (rc) return rc; }
+      colsum_kernel<<<grid, block, 0, st>>>(gy, g.M, g.Cn, ysplit > 1 ? ws : gbias);
       nslabs = ysplit;
     }
     CN_CHECK_LAUNCH();
-    sum_slabs_kernel<<<(g.Cn + 31) / 32, dim3(32, 8), 0, st>>>(ws, nslabs, g.Cn, gbias);
-    CN_CHECK_LAUNCH();
+    if (nslabs > 1) {
+      sum_slabs(ws, nslabs, g.Cn, gbias, st);
+      CN_CHECK_LAUNCH();
+    }
   }
   (void)conv_numel_x;
   return CN_OK;

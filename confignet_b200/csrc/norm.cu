@@ -78,14 +78,8 @@ chan_sums4_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
     for (int e = 0; e < 4; ++e) s[j][e] = 0.f;
   if (rr < R) {
     const size_t base = (size_t)n * p * ch + 4 * q;
-#pragma unroll 4
-    for (int r = pbeg + rr; r < pend; r += R) {
-      const size_t i = base + (size_t)r * ch;
-      const float4 a4 = *reinterpret_cast<const float4*>(a + i);
-      const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
-      float bv[4] = {0.f, 0.f, 0.f, 0.f}, cv[4] = {0.f, 0.f, 0.f, 0.f};
-      if (NT >= 2) { const float4 t = *reinterpret_cast<const float4*>(b + i); bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w; }
-      if (NT >= 3) { const float4 t = *reinterpret_cast<const float4*>(c + i); cv[0] = t.x; cv[1] = t.y; cv[2] = t.z; cv[3] = t.w; }
+    auto add = [&](const float4& a4, const float4& b4, const float4& c4) {
+      const float ar[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float av = (flags & CN_FLAG_LRELU_A) ? lrelu_f(ar[e], alpha) : ar[e];
@@ -97,6 +91,27 @@ chan_sums4_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
           s[2][e] += cc; s[5][e] += av * cc; s[6][e] += bv[e] * cc;
         }
       }
+    };
+    // U pixels of every operand are loaded before the first is used: written as "#pragma unroll" of a load-use loop the
+    // compiler keeps ONE load in flight per thread (each use waits for its load) and the pass runs at 0.3-0.5 of the HBM rate
+    constexpr int U = (NT == 1) ? 8 : 4;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int r = pbeg + rr;
+    for (; r + (U - 1) * R < pend; r += U * R) {          // full batches: unconditional loads, all issued before the first use
+      float4 A[U], B[U], C[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t i = base + (size_t)(r + u * R) * ch;
+        A[u] = cn_ldg4_ordered(a + i);
+        B[u] = (NT >= 2) ? cn_ldg4_ordered(b + i) : z4;
+        C[u] = (NT >= 3) ? cn_ldg4_ordered(c + i) : z4;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) add(A[u], B[u], C[u]);
+    }
+    for (; r < pend; r += R) {
+      const size_t i = base + (size_t)r * ch;
+      add(cn_ldg4_ordered(a + i), (NT >= 2) ? cn_ldg4_ordered(b + i) : z4, (NT >= 3) ? cn_ldg4_ordered(c + i) : z4);
     }
 #pragma unroll
     for (int j = 0; j < 7; ++j)
@@ -120,7 +135,11 @@ extern "C" int cn_chan_sums_splits(int n, int p, int ch) {
   static int per_sm = 0;
   if (per_sm == 0) { const char* e = getenv("CN_SUMS_BLOCKS_PER_SM"); per_sm = e ? atoi(e) : 4; if (per_sm < 1) per_sm = 4; }
   int psplit = (per_sm * 148 + cb * n - 1) / (cb * n);
-  int maxsplit = (p + 63) / 64;
+  // at least 8 pixels (float4 kernel: 4 per row group) per block: a thread that walks 64 pixels alone is 16 dependent
+  // DRAM round trips - 20 us on the 4 MB tensors of the last discriminator blocks, whatever the grid
+  int minpix = 64;
+  if (ch % 4 == 0 && ch <= 1024) { minpix = 4 * (256 / (ch / 4)); if (minpix < 8) minpix = 8; if (minpix > 64) minpix = 64; }
+  int maxsplit = (p + minpix - 1) / minpix;
   if (psplit > maxsplit) psplit = maxsplit;
   if (psplit < 1) psplit = 1;
   return psplit;
@@ -186,11 +205,82 @@ __global__ void chan_affine_kernel(const float* __restrict__ a, const float* __r
   }
 }
 
+// Row-walking form (ch % 4 == 0, ch <= 1024): block = one (sample, pixel slice), thread (q, rr) owns channel quad q and
+// walks the pixels rr, rr + R, ... of the slice.  Its four coefficient records are loaded ONCE into registers (the
+// grid-stride kernel above re-reads 64 bytes of coefficients and does two 64-bit divisions per 16 bytes of data: it ran at
+// 0.2-0.45 of the HBM rate, profiles/r02_launches_v11_summary.txt), a warp instruction is one contiguous 512-byte run,
+// four pixels are in flight per thread.  grid (n, psplit), 256 threads.
+template <bool HB, bool HC>
+__global__ void __launch_bounds__(256)
+chan_affine_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                        const float4* __restrict__ coef, int p, int ch, int flags, float alpha, float* __restrict__ out) {
+  const int chq = ch >> 2, R = 256 / chq;
+  const int tid = threadIdx.x, q = tid % chq, rr = tid / chq;
+  if (rr >= R) return;
+  const int n = blockIdx.x;
+  const int per = (p + gridDim.y - 1) / gridDim.y;
+  const int pbeg = blockIdx.y * per, pend = min(p, pbeg + per);
+  float4 k[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) k[e] = coef[(size_t)n * ch + 4 * q + e];
+  const size_t base = (size_t)n * p * ch + 4 * q;
+  constexpr int U = 4;                                   // four pixels of every operand in flight per thread
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto one = [&](const float4& A, const float4& B, const float4& C, float* o4) {
+    const float ar[4] = {A.x, A.y, A.z, A.w}, br[4] = {B.x, B.y, B.z, B.w}, cr[4] = {C.x, C.y, C.z, C.w};
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float araw = ar[e];
+      const float aa = (flags & CN_FLAG_LRELU_A) ? lrelu_f(araw, alpha) : araw;
+      float v = fmaf(k[e].x, aa, k[e].w);
+      if (HB) v = fmaf(k[e].y, br[e], v);
+      if (HC) { float cc = cr[e]; if (flags & CN_FLAG_MASK_C) cc *= lrelu_d(araw, alpha); v = fmaf(k[e].z, cc, v); }
+      if (flags & CN_FLAG_MASK_OUT) v *= lrelu_d(araw, alpha);
+      o[e] = v;
+    }
+    *reinterpret_cast<float4*>(o4) = make_float4(o[0], o[1], o[2], o[3]);
+  };
+  int r = pbeg + rr;
+  for (; r + (U - 1) * R < pend; r += U * R) {           // full batches, no branch between the loads and the stores
+    float4 A[U], B[U], C[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = base + (size_t)(r + u * R) * ch;
+      A[u] = cn_ldg4_ordered(a + i);
+      B[u] = HB ? cn_ldg4_ordered(b + i) : z4;
+      C[u] = HC ? cn_ldg4_ordered(c + i) : z4;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) one(A[u], B[u], C[u], out + base + (size_t)(r + u * R) * ch);
+  }
+  for (; r < pend; r += R) {
+    const size_t i = base + (size_t)r * ch;
+    one(cn_ldg4_ordered(a + i), HB ? cn_ldg4_ordered(b + i) : z4, HC ? cn_ldg4_ordered(c + i) : z4, out + i);
+  }
+}
+
 extern "C" int cn_chan_affine(const float* a, const float* b, const float* c, const float* coef,
                               int n, int p, int ch, int flags, float alpha, float* out, void* stream) {
   CN_REQUIRE(a && coef && out && n > 0 && p > 0 && ch > 0, CN_ERR_BAD_SHAPE, "cn_chan_affine: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)n * p * ch;
+  static int rows_form = -1;
+  if (rows_form < 0) { const char* e = getenv("CN_AFFINE_ROWS"); rows_form = e ? atoi(e) : 1; }
+  if (rows_form && ch % 4 == 0 && ch <= 1024 && n <= 65535) {
+    const int R = 256 / (ch / 4);
+    int psplit = (8 * 148 + n - 1) / n;                    // ~8 blocks of 256 threads per SM
+    int maxsplit = p / (2 * R); if (maxsplit < 1) maxsplit = 1;
+    if (psplit > maxsplit) psplit = maxsplit;
+    dim3 grid(n, psplit);
+    const float4* k4 = (const float4*)coef;
+    if (b && c) chan_affine_rows_kernel<true, true><<<grid, 256, 0, st>>>(a, b, c, k4, p, ch, flags, alpha, out);
+    else if (b) chan_affine_rows_kernel<true, false><<<grid, 256, 0, st>>>(a, b, c, k4, p, ch, flags, alpha, out);
+    else if (c) chan_affine_rows_kernel<false, true><<<grid, 256, 0, st>>>(a, b, c, k4, p, ch, flags, alpha, out);
+    else chan_affine_rows_kernel<false, false><<<grid, 256, 0, st>>>(a, b, c, k4, p, ch, flags, alpha, out);
+    CN_CHECK_LAUNCH();
+    return CN_OK;
+  }
   if (ch % 4 == 0) {
     size_t tv = total / 4;
     int blocks = (int)((tv + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
@@ -223,25 +313,58 @@ __global__ void __launch_bounds__(1024)
 norm_coef_kernel(int kind, const float* __restrict__ sums, int nsplit, const float* __restrict__ p0,
                                  const float* __restrict__ p1, int n, int ch, float N, float eps,
                                  float4* __restrict__ coef0, float4* __restrict__ coef1,
-                                 float* __restrict__ out0, float* __restrict__ out1) {
-  // block (32, R): lane = channel, the R = 8 | 32 rows take every R-th sample (R = 32: one sample per thread at the
-  // batch sizes of the training step - the kernel is a chain of dependent L2 round trips, not bandwidth)
-  __shared__ float red[2][32][33];
-  const int R = blockDim.y;
-  const int c = blockIdx.x * 32 + threadIdx.x;
+                                 float* __restrict__ out0, float* __restrict__ out1, int spb) {
+  // block (8, 128): x = channel (8 records = one 256-byte run), the 128 rows are spb samples x G = 128 / spb slice groups
+  // (spb = 32, 16, 8 or 4, the largest that the batch fills).  The kernel is a chain of dependent L2 round trips, not
+  // bandwidth: a row adds the slices g, g + G, ... of its sample, the G partial records are folded in group order through
+  // shared memory, then the row of group 0 evaluates the closed form (fixed order everywhere: bit-reproducible).
+  // grid = ch / 8 blocks (6 .. 96 on the step's layers; 32-channel blocks left the GPU to 2 .. 24 blocks of serial walks).
+  __shared__ float red[2][32][9];
+  __shared__ float fold[7][128][9];
+  const int G = 128 / spb;
+  const int si = threadIdx.y % spb, gz = threadIdx.y / spb;
+  const int c = blockIdx.x * 8 + threadIdx.x;
   const bool cok = c < ch;
   const float invN = 1.f / N;
   float acc0 = 0.f, acc1 = 0.f;
-  for (int i = threadIdx.y; cok && i < n; i += R) {
+  for (int i0 = 0; i0 < n; i0 += spb) {
+    const int i = i0 + si;
+    const bool ok = cok && i < n;
     float S[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) S[j] = 0.f;
-#pragma unroll 4
-    for (int z = 0; z < nsplit; ++z) {          // independent loads: let several slices be in flight
-      const float4* Sz = reinterpret_cast<const float4*>(sums + (((size_t)z * n + i) * ch + c) * CN_SUMS_LD);
-      const float4 lo = Sz[0], hi = Sz[1];
-      S[0] += lo.x; S[1] += lo.y; S[2] += lo.z; S[3] += lo.w; S[4] += hi.x; S[5] += hi.y; S[6] += hi.z;
+    if (ok) {
+      int z = gz;
+      for (; z + 3 * G < nsplit; z += 4 * G) {    // four slices (eight 16-byte loads) in flight
+        float4 lo[4], hi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float* Sz = sums + (((size_t)(z + u * G) * n + i) * ch + c) * CN_SUMS_LD;
+          lo[u] = cn_ldg4_ordered(Sz); hi[u] = cn_ldg4_ordered(Sz + 4);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          S[0] += lo[u].x; S[1] += lo[u].y; S[2] += lo[u].z; S[3] += lo[u].w; S[4] += hi[u].x; S[5] += hi[u].y; S[6] += hi[u].z;
+        }
+      }
+      for (; z < nsplit; z += G) {
+        const float* Sz = sums + (((size_t)z * n + i) * ch + c) * CN_SUMS_LD;
+        const float4 lo = cn_ldg4_ordered(Sz), hi = cn_ldg4_ordered(Sz + 4);
+        S[0] += lo.x; S[1] += lo.y; S[2] += lo.z; S[3] += lo.w; S[4] += hi.x; S[5] += hi.y; S[6] += hi.z;
+      }
     }
+    if (G > 1) {
+      if (i0 > 0) __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 7; ++j) fold[j][threadIdx.y][threadIdx.x] = S[j];
+      __syncthreads();
+      if (gz == 0) {
+        for (int g = 1; g < G; ++g)
+#pragma unroll
+          for (int j = 0; j < 7; ++j) S[j] += fold[j][g * spb + si][threadIdx.x];
+      }
+    }
+    if (!ok || gz != 0) continue;
     const size_t nc = (size_t)i * ch + c;
     const float mu = S[0] * invN;
     float var = S[3] * invN - mu * mu;
@@ -314,12 +437,14 @@ norm_coef_kernel(int kind, const float* __restrict__ sums, int nsplit, const flo
     }
   }
   if (kind == CN_COEF_IN_BWD || kind == CN_COEF_IN_BWDBWD) {     // per-channel parameter gradients: fold the 8 rows in order
-    red[0][threadIdx.y][threadIdx.x] = acc0;
-    red[1][threadIdx.y][threadIdx.x] = acc1;
+    if (threadIdx.y < 32) {                                      // rows of group 0 (spb <= 32 of them hold a sample)
+      red[0][threadIdx.y][threadIdx.x] = threadIdx.y < spb ? acc0 : 0.f;
+      red[1][threadIdx.y][threadIdx.x] = threadIdx.y < spb ? acc1 : 0.f;
+    }
     __syncthreads();
     if (threadIdx.y == 0 && cok) {
       float t0 = 0.f, t1 = 0.f;
-      for (int i = 0; i < R; ++i) { t0 += red[0][i][threadIdx.x]; t1 += red[1][i][threadIdx.x]; }
+      for (int i = 0; i < 32; ++i) { t0 += red[0][i][threadIdx.x]; t1 += red[1][i][threadIdx.x]; }
       out0[c] = t0;
       if (kind == CN_COEF_IN_BWD) out1[c] = t1;
     }
@@ -330,8 +455,9 @@ extern "C" int cn_norm_coef(int kind, const float* sums, int nsplit, const float
                             int npix, float eps, float* coef0, float* coef1, float* out0, float* out1,
                             void* stream) {
   CN_REQUIRE(kind >= 0 && kind <= 7 && sums && nsplit >= 1 && n > 0 && ch > 0 && npix > 0, CN_ERR_BAD_SHAPE, "cn_norm_coef: bad arguments");
-  norm_coef_kernel<<<(ch + 31) / 32, dim3(32, n >= 16 ? 32 : 8), 0, (cudaStream_t)stream>>>(kind, sums, nsplit, p0, p1, n, ch, (float)npix, eps,
-                                                                              (float4*)coef0, (float4*)coef1, out0, out1);
+  const int spb = n >= 32 ? 32 : n >= 16 ? 16 : n >= 8 ? 8 : 4;
+  norm_coef_kernel<<<(ch + 7) / 8, dim3(8, 128), 0, (cudaStream_t)stream>>>(kind, sums, nsplit, p0, p1, n, ch, (float)npix, eps,
+                                                                              (float4*)coef0, (float4*)coef1, out0, out1, spb);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

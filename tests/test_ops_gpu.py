@@ -98,7 +98,10 @@ def test_conv_double_backward(dev):
     assert nerr(got[0], ref[0]) <= TOL_FP32 and nerr(got[1], ref[1]) <= TOL_FP32
 
 
-@pytest.mark.parametrize("shape", [(3, 5, 4, 6), (2, 16, 16, 48), (2, 8, 8, 7)])
+@pytest.mark.parametrize("shape", [(3, 5, 4, 6), (2, 16, 16, 48), (2, 8, 8, 7),
+                                   # sample groups x slice groups of the coefficient kernel (batch 16 / 33 / 9), one row group
+                                   # per block in the float4 kernels (192 channels), > 1024 channels (grid-stride fallback)
+                                   (16, 8, 8, 192), (33, 6, 6, 96), (9, 40, 40, 24), (2, 3, 3, 1028)])
 def test_instance_norm_all_orders(dev, shape):
     from confignet_b200 import ops
     torch.manual_seed(2)
@@ -121,7 +124,7 @@ def test_instance_norm_all_orders(dev, shape):
         assert nerr(a, b) <= 5 * TOL_FP32
 
 
-@pytest.mark.parametrize("shape", [(3, 5, 4, 6), (2, 16, 16, 48)])
+@pytest.mark.parametrize("shape", [(3, 5, 4, 6), (2, 16, 16, 48), (16, 8, 8, 192), (33, 6, 6, 96)])
 def test_layer_style_all_orders(dev, shape):
     from confignet_b200 import ops
     torch.manual_seed(3)
@@ -141,11 +144,11 @@ def test_layer_style_all_orders(dev, shape):
     assert nerr(q2[0], g2[0]) <= 5 * TOL_FP32 and nerr(q2[1], g2[1]) <= 5 * TOL_FP32
 
 
-def test_adain(dev):
+@pytest.mark.parametrize("n,ch,side", [(3, 8, 4), (16, 128, 6), (5, 512, 3)])
+def test_adain(dev, n, ch, side):
     from confignet_b200 import ops
     torch.manual_seed(4)
-    n, ch = 3, 8
-    a0 = torch.randn(n, 4, 4, 4, ch); sb = torch.randn(n, 2 * ch)
+    a0 = torch.randn(n, side, side, side, ch); sb = torch.randn(n, 2 * ch)
     pre = a0.double().requires_grad_(True); sbr = sb.double().requires_grad_(True)
     a = O.lrelu(pre, 0.3)
     mean = a.mean((1, 2, 3), keepdim=True); var = ((a - mean) ** 2).mean((1, 2, 3), keepdim=True)
@@ -180,15 +183,20 @@ def test_rotate3d(dev):
 def test_maxpool_vggpre_reduce_uint8(dev):
     from confignet_b200 import ops
     torch.manual_seed(6)
-    x = torch.randn(2, 8, 6, 5)
-    xr = x.double().requires_grad_(True)
-    yr = torch.nn.functional.max_pool2d(xr.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
-    gy = torch.randn(*yr.shape)
-    gxr, = torch.autograd.grad(yr, xr, gy.double())
-    xg = x.to(dev).requires_grad_(True)
-    y = ops.maxpool2(xg)
-    gx, = torch.autograd.grad(y, xg, gy.to(dev))
-    assert torch.equal(y.cpu().double(), yr.detach()) and nerr(gx, gxr) == 0.0
+    # scalar kernels (5 channels) and the 16-byte kernels (8 / 64 channels); ReLU outputs tie at 0 inside a window: the
+    # gradient goes to the first maximum in (dy, dx) order, as in the oracle
+    for shape, relu in [((2, 8, 6, 5), False), ((3, 6, 10, 8), True), ((2, 16, 12, 64), True)]:
+        x = torch.randn(*shape)
+        if relu:
+            x = torch.relu(x)
+        xr = x.double().requires_grad_(True)
+        yr = torch.nn.functional.max_pool2d(xr.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+        gy = torch.randn(*yr.shape)
+        gxr, = torch.autograd.grad(yr, xr, gy.double())
+        xg = x.to(dev).requires_grad_(True)
+        y = ops.maxpool2(xg)
+        gx, = torch.autograd.grad(y, xg, gy.to(dev))
+        assert torch.equal(y.cpu().double(), yr.detach()) and nerr(gx, gxr) == 0.0
     img = torch.rand(2, 4, 4, 3) * 2 - 1
     ir = img.double().requires_grad_(True)
     pr = O.vgg19_preprocess(ir)
