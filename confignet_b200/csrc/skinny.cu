@@ -626,6 +626,83 @@ c3k_dgrad_s2_kernel(const float* __restrict__ gy, float* __restrict__ gx, int H,
   }
 }
 
+// stride 1, TF-SAME (pad 1): gx[y][x][ci] = sum_{ky,kx,co} gy[y+1-ky][x+1-kx][co] . w[ky][kx][ci][co]  (VGG block1_conv1's
+// input gradient, 64 -> 3 at 256x256: the one perceptual-loss layer whose gradient reaches the image).
+// block = 128 pixels of one row, 128 threads: thread (t, half) owns the pixel PAIR (2t, 2t+1) and one half of the output
+// channels; a gy pixel is read once (8 LDS.128) and feeds both pixels of the pair: 96 LDS.128 per 1728 FFMAs, every FFMA with
+// its weight as a constant-bank immediate (the first-generation kernel: 4 LDS.128 per 12 FFMAs, 490 us at batch 16).
+// The staged gy columns are split by parity (even | odd) so that the lanes of a warp - which walk columns 2t + j - read
+// consecutive records: pixel stride 68 floats = 4 banks, conflict-free 16-byte reads.  The two channel halves are added
+// through shared memory in a fixed order.
+template <int COUT, int HALF>
+__device__ __forceinline__ void c3k_dgrad_s1_body(const float* __restrict__ s, int t, float (&acc)[2][3]) {
+  constexpr int PS = COUT + 4, HC = COUT / 2, KS = 65;
+#pragma unroll
+  for (int lrow = 0; lrow < 3; ++lrow) {
+    const int ky = 2 - lrow;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* src = s + ((size_t)((lrow * 2 + (j & 1)) * KS + t + (j >> 1))) * PS + HALF * HC;
+      float g[HC];
+#pragma unroll
+      for (int f = 0; f < HC / 4; ++f) {
+        const float4 v = *reinterpret_cast<const float4*>(src + 4 * f);
+        g[4 * f] = v.x; g[4 * f + 1] = v.y; g[4 * f + 2] = v.z; g[4 * f + 3] = v.w;
+      }
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const int kx = d + 2 - j;
+        if (kx < 0 || kx > 2) continue;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          float a = acc[d][ci];
+#pragma unroll
+          for (int co = 0; co < HC; ++co) a = fmaf(g[co], c_c3w[((ky * 3 + kx) * 3 + ci) * COUT + HALF * HC + co], a);
+          acc[d][ci] = a;
+        }
+      }
+    }
+  }
+}
+template <int COUT>
+__global__ void __launch_bounds__(128)
+c3k_dgrad_s1_kernel(const float* __restrict__ gy, float* __restrict__ gx, int H, int W) {
+  constexpr int C4 = COUT / 4, PS = COUT + 4, KS = 65, NCOL = 130;
+  extern __shared__ __align__(16) float sm[];            // [3 rows y-1..y+1][parity][KS][PS]; columns x0-1 .. x0+128
+  const int tid = threadIdx.x, n = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 128;
+  for (int i = tid; i < 3 * NCOL * C4; i += 128) {
+    const int f = i % C4, pc = i / C4, col = pc % NCOL, row = pc / NCOL;
+    const int gr = y - 1 + row, gc = x0 - 1 + col;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((unsigned)gr < (unsigned)H && (unsigned)gc < (unsigned)W) v = ldg4(gy + ((size_t)(n * H + gr) * W + gc) * COUT + 4 * f);
+    *reinterpret_cast<float4*>(sm + ((size_t)((row * 2 + (col & 1)) * KS + (col >> 1))) * PS + 4 * f) = v;
+  }
+  __syncthreads();
+  const int t = tid & 63, half = tid >> 6;               // warps 0-1: channels 0..COUT/2-1, warps 2-3: the rest
+  float acc[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  if (half == 0) c3k_dgrad_s1_body<COUT, 0>(sm, t, acc);
+  else c3k_dgrad_s1_body<COUT, 1>(sm, t, acc);
+  __syncthreads();                                        // the staged rows are dead: their space carries the second half's sums
+  if (half == 1) {
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) sm[t * 6 + d * 3 + ci] = acc[d][ci];
+  }
+  __syncthreads();
+  const int px = x0 + 2 * t;
+  if (half == 0 && px < W) {
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) acc[d][ci] += sm[t * 6 + d * 3 + ci];
+    float* out = gx + ((size_t)(n * H + y) * W + px) * 3;                  // 6 contiguous floats: pixels (px, px + 1)
+    *reinterpret_cast<float2*>(out) = make_float2(acc[0][0], acc[0][1]);
+    *reinterpret_cast<float2*>(out + 2) = make_float2(acc[0][2], acc[1][0]);
+    *reinterpret_cast<float2*>(out + 4) = make_float2(acc[1][1], acc[1][2]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // p3: Conv2D(3 -> 3, 1x1, stride 1) - the discriminators' / latent regressor's fromRGB layer
 // (hologan_discriminator.py:20-26,75-81, initial_1x1_conv).  A pixel is 12 bytes in and 12 bytes out: the tensor is walked
@@ -729,7 +806,7 @@ p3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float
 // (profiles/r02_skinny_c3k.txt, D.block0 at batch 32): dgrad 119.8 -> 89.1 us; forward 85.0 -> 85.0 us (both generations sit
 // on the FP32 pipe: ptxas keeps the kernel out of the FFMA operand slot and loads it with LDC.128, and three-register
 // FFMAs issue at half rate) - so only the gradient kernel is on by default.
-int g_c3k = 2;
+int g_c3k = 6;
 
 bool is_p3(const cn_conv_desc* d) {
   return d->nd == 2 && d->cin == 3 && d->cout == 3 && d->ksize[0] == 1 && d->ksize[1] == 1 && d->stride == 1 && d->upsample == 1 &&
@@ -839,6 +916,15 @@ int cn_skinny_dgrad(const cn_conv_desc* d, const float* gy, const float* w, floa
       int rc = opt_in_smem(c3_dgrad_kernel<2, 48, PS>, smem); if (rc) return rc;
       dim3 grid((W + 127) / 128, H / 2, d->batch);
       c3_dgrad_kernel<2, 48, PS><<<grid, 256, smem, st>>>(gy, w, gx, H, W, OH, OW);
+      CN_CHECK_LAUNCH();
+      return 1;
+    }
+    if ((g_c3k & 4) && d->stride == 1 && d->cout == 64 && W % 2 == 0) {
+      const int smem = 3 * 2 * 65 * (64 + 4) * (int)sizeof(float);
+      int rc = opt_in_smem(c3k_dgrad_s1_kernel<64>, smem); if (rc) return rc;
+      CN_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_c3w, w, (size_t)27 * 64 * sizeof(float), 0, cudaMemcpyDeviceToDevice, st));
+      dim3 grid((W + 127) / 128, H, d->batch);
+      c3k_dgrad_s1_kernel<64><<<grid, 128, smem, st>>>(gy, gx, H, W);
       CN_CHECK_LAUNCH();
       return 1;
     }

@@ -510,3 +510,32 @@ def test_generate_images_graph_replay_matches_eager_and_follows_the_weights(dev)
     a = models[0].generate_images(lat, rot)
     b2 = models[1].generate_images(lat, rot)
     assert np.array_equal(a, b2) and not np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ input pipeline (f2)
+def test_device_image_path_matches_reference_batch_assembly(dev):
+    """get_discriminator_batch's image half (confignet_first_stage.py:440-443, confignet_utils.py:198-204): rows of the
+    uint8 store -> float32 / 127.5 - 1 -> np.fliplr on the drawn subset.  The product uploads uint8 rows (or gathers them
+    from the HBM-resident store), flips and converts on the device: same draws, bit-identical float32 batch."""
+    from confignet_b200.confignet_first_stage import ConfigNetFirstStage
+    from confignet_b200.synthetic_data import SyntheticDataset
+    model = ConfigNetFirstStage({"output_shape": (128, 128, 3), "batch_size": 6, "facemodel_inputs": FM, "cuda_graphs": False},
+                                device=dev)
+    ds = SyntheticDataset(24, 128, seed=3)
+    for seed in (5, 6):
+        np.random.seed(seed)
+        idx = np.random.randint(0, ds.imgs.shape[0], 6)
+        want = np.copy(ds.imgs[idx]).astype(np.float32) / 127.5 - 1.0
+        flip_or_not = np.random.randint(0, 2, size=6)
+        for i, flip in enumerate(flip_or_not):
+            if flip == 1:
+                want[i] = np.fliplr(want[i])
+        # host store: pinned upload of the uint8 rows, flip + conversion on the device
+        got = model._upload_images(model._take_rows(ds.imgs, idx), flip_or_not)
+        assert np.array_equal(got.cpu().numpy(), want)
+        # device-resident store: index_select + flip + conversion, all on the device (the captured steps' path)
+        store = torch.as_tensor(ds.imgs).to(dev)
+        rows = model._take_rows(store, idx)
+        got2 = model._real_from_u8(rows, torch.as_tensor(flip_or_not.astype(np.bool_)).to(dev))
+        assert np.array_equal(got2.cpu().numpy(), want)
+        assert flip_or_not.any() and not flip_or_not.all()      # both branches exercised
