@@ -187,14 +187,24 @@ c3_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ w, float
 // Persistent blocks walk output rows; thread = (pixel group g, kernel row ky, 8 output channels) holds a
 // 9 x 8 register tile; the 14 pixel groups of a block are folded in a fixed order at the end.
 // ------------------------------------------------------------------------------------------------
+// The rows are staged with cp.async into TWO buffers: row i + 1 is in flight while row i is multiplied (one buffer and plain
+// loads left every row iteration waiting on ~9 dependent scalar loads per thread: 93-113 us per launch for a layer whose
+// FFMAs take ~40 us, profiles/r02_launches_s2c_summary.txt).
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(float* dst, const float* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
 template <int S, int COUT>
 __global__ void __launch_bounds__(256, 2)
 c3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ part,
                 int B, int H, int W, int OH, int OW, int pby, int pbx) {
   constexpr int NC8 = COUT / 8, ITEMS = 3 * NC8, GROUPS = 256 / ITEMS, C4 = COUT / 4;
-  constexpr int NCOL = 127 * S + 3, RS = NCOL * 3;
-  __shared__ __align__(16) float s_gy[128 * COUT];
-  __shared__ float s_x[3 * RS + 8];
+  constexpr int NCOL = 127 * S + 3, RS = NCOL * 3, XBUF = (3 * RS + 8 + 3) & ~3;
+  extern __shared__ __align__(16) float sm_w[];          // [2][128 * COUT] gy rows, then [2][XBUF] input rows
+  float* s_gy = sm_w;
+  float* s_xb = sm_w + 2 * 128 * COUT;
   const int tid = threadIdx.x;
   const int g = tid / ITEMS, item = tid - g * ITEMS, ky = item / NC8, c8 = item - ky * NC8;
   const bool active = g < GROUPS;
@@ -205,27 +215,43 @@ c3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float
     for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
   const int nseg = (OW + 127) / 128;
   const int nrows = B * OH * nseg;
-  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+  auto stage = [&](int row, int buf) {
     const int seg = row % nseg, r2 = row / nseg, oy = r2 % OH, n = r2 / OH;
     const int ox0 = seg * 128, npx = min(128, OW - ox0);
-    __syncthreads();
     const float* grow = gy + ((size_t)(n * OH + oy) * OW + ox0) * COUT;
-    for (int i = tid; i < npx * C4; i += 256) reinterpret_cast<float4*>(s_gy)[i] = ldg4(grow + 4 * i);
+    float* dg = s_gy + buf * 128 * COUT;
+    for (int i = tid; i < npx * C4; i += 256) cp_async16(dg + 4 * i, grow + 4 * i);
     const int ix0 = ox0 * S - pbx;
+    float* dx = s_xb + buf * XBUF;
     for (int i = tid; i < 3 * RS; i += 256) {
       const int r = i / RS, j = i - r * RS, col = j / 3;
       const int iy = oy * S + r - pby, ix = ix0 + col;
-      float v = 0.f;
-      if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) v = __ldg(x + ((long long)(n * H + iy) * W + ix0) * 3 + j);
-      s_x[i] = v;
+      const bool in = (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+      cp_async4_zfill(dx + i, in ? x + ((long long)(n * H + iy) * W + ix0) * 3 + j : x, in);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  if ((int)blockIdx.x < nrows) stage(blockIdx.x, 0);
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x, buf ^= 1) {
+    const int seg = row % nseg;
+    const int npx = min(128, OW - seg * 128);
+    const int next = row + gridDim.x;
+    if (next < nrows) {
+      stage(next, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");   // this row has landed, the next one stays in flight
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     if (active) {
+      const float* bg = s_gy + buf * 128 * COUT;
+      const float* bx = s_xb + buf * XBUF;
       for (int p = g; p < npx; p += GROUPS) {
-        const float4 ga = reinterpret_cast<const float4*>(s_gy)[p * C4 + 2 * c8];
-        const float4 gb = reinterpret_cast<const float4*>(s_gy)[p * C4 + 2 * c8 + 1];
+        const float4 ga = reinterpret_cast<const float4*>(bg)[p * C4 + 2 * c8];
+        const float4 gb = reinterpret_cast<const float4*>(bg)[p * C4 + 2 * c8 + 1];
         const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-        const float* xr = s_x + ky * RS + p * S * 3;
+        const float* xr = bx + ky * RS + p * S * 3;
 #pragma unroll
         for (int a = 0; a < 9; ++a) {
           const float xv = xr[a];
@@ -234,6 +260,7 @@ c3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float
         }
       }
     }
+    __syncthreads();                                       // this buffer is refilled by the next iteration's stage()
   }
   // fixed-order fold of the pixel groups, then one partial per block
   __syncthreads();
@@ -628,21 +655,22 @@ c3k_dgrad_s2_kernel(const float* __restrict__ gy, float* __restrict__ gx, int H,
 
 // stride 1, TF-SAME (pad 1): gx[y][x][ci] = sum_{ky,kx,co} gy[y+1-ky][x+1-kx][co] . w[ky][kx][ci][co]  (VGG block1_conv1's
 // input gradient, 64 -> 3 at 256x256: the one perceptual-loss layer whose gradient reaches the image).
-// block = 128 pixels of one row, 128 threads: thread (t, half) owns the pixel PAIR (2t, 2t+1) and one half of the output
-// channels; a gy pixel is read once (8 LDS.128) and feeds both pixels of the pair: 96 LDS.128 per 1728 FFMAs, every FFMA with
-// its weight as a constant-bank immediate (the first-generation kernel: 4 LDS.128 per 12 FFMAs, 490 us at batch 16).
-// The staged gy columns are split by parity (even | odd) so that the lanes of a warp - which walk columns 2t + j - read
-// consecutive records: pixel stride 68 floats = 4 banks, conflict-free 16-byte reads.  The two channel halves are added
-// through shared memory in a fixed order.
+// block = 128 pixels x R = 4 rows, 64 R threads: thread (t, r) owns the pixel PAIR (2t, 2t+1) of row r.  The output channels
+// of gy go through shared memory in two halves (R + 2 rows x 130 columns x 32 channels, fetched with cp.async: every 16-byte
+// piece of a half is in flight at once, rows are read 1.5 times from L2 instead of 3); a gy pixel is read once (8 LDS.128)
+// and feeds both pixels of the pair: 96 LDS.128 per 3456 FFMAs, every FFMA with its weight as a constant-bank operand (the
+// first-generation kernel: 4 LDS.128 per 12 FFMAs, 490 us at batch 16).  The staged columns are split by parity
+// (even | odd) so that the lanes of a warp - which walk columns 2t + j - read consecutive records: pixel stride 36 floats =
+// 4 banks, conflict-free 16-byte reads.
 template <int COUT, int HALF>
 __device__ __forceinline__ void c3k_dgrad_s1_body(const float* __restrict__ s, int t, float (&acc)[2][3]) {
-  constexpr int PS = COUT + 4, HC = COUT / 2, KS = 65;
+  constexpr int HC = COUT / 2, PS = HC + 4, KS = 65;
 #pragma unroll
   for (int lrow = 0; lrow < 3; ++lrow) {
     const int ky = 2 - lrow;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float* src = s + ((size_t)((lrow * 2 + (j & 1)) * KS + t + (j >> 1))) * PS + HALF * HC;
+      const float* src = s + ((size_t)((lrow * 2 + (j & 1)) * KS + t + (j >> 1))) * PS;
       float g[HC];
 #pragma unroll
       for (int f = 0; f < HC / 4; ++f) {
@@ -664,38 +692,34 @@ __device__ __forceinline__ void c3k_dgrad_s1_body(const float* __restrict__ s, i
     }
   }
 }
-template <int COUT>
-__global__ void __launch_bounds__(128)
+template <int COUT, int R>
+__global__ void __launch_bounds__(64 * R)
 c3k_dgrad_s1_kernel(const float* __restrict__ gy, float* __restrict__ gx, int H, int W) {
-  constexpr int C4 = COUT / 4, PS = COUT + 4, KS = 65, NCOL = 130;
-  extern __shared__ __align__(16) float sm[];            // [3 rows y-1..y+1][parity][KS][PS]; columns x0-1 .. x0+128
-  const int tid = threadIdx.x, n = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 128;
-  for (int i = tid; i < 3 * NCOL * C4; i += 128) {
-    const int f = i % C4, pc = i / C4, col = pc % NCOL, row = pc / NCOL;
-    const int gr = y - 1 + row, gc = x0 - 1 + col;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((unsigned)gr < (unsigned)H && (unsigned)gc < (unsigned)W) v = ldg4(gy + ((size_t)(n * H + gr) * W + gc) * COUT + 4 * f);
-    *reinterpret_cast<float4*>(sm + ((size_t)((row * 2 + (col & 1)) * KS + (col >> 1))) * PS + 4 * f) = v;
-  }
-  __syncthreads();
-  const int t = tid & 63, half = tid >> 6;               // warps 0-1: channels 0..COUT/2-1, warps 2-3: the rest
+  constexpr int HC = COUT / 2, H4 = HC / 4, PS = HC + 4, KS = 65, NCOL = 130, NT = 64 * R;
+  extern __shared__ __align__(16) float sm[];            // [R + 2 rows y0-1 ..][parity][KS][PS]; columns x0-1 .. x0+128
+  const int tid = threadIdx.x, n = blockIdx.z, y0 = blockIdx.y * R, x0 = blockIdx.x * 128;
+  const int t = tid & 63, r = tid >> 6;
   float acc[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-  if (half == 0) c3k_dgrad_s1_body<COUT, 0>(sm, t, acc);
-  else c3k_dgrad_s1_body<COUT, 1>(sm, t, acc);
-  __syncthreads();                                        // the staged rows are dead: their space carries the second half's sums
-  if (half == 1) {
 #pragma unroll
-    for (int d = 0; d < 2; ++d)
-#pragma unroll
-      for (int ci = 0; ci < 3; ++ci) sm[t * 6 + d * 3 + ci] = acc[d][ci];
+  for (int half = 0; half < 2; ++half) {
+    if (half) __syncthreads();                            // every thread is done with the first half's rows
+    for (int i = tid; i < (R + 2) * NCOL * H4; i += NT) {
+      const int f = i % H4, pc = i / H4, col = pc % NCOL, row = pc / NCOL;
+      const int gr = y0 - 1 + row, gc = x0 - 1 + col;
+      const bool in = (unsigned)gr < (unsigned)H && (unsigned)gc < (unsigned)W;
+      const float* src = in ? gy + ((size_t)(n * H + gr) * W + gc) * COUT + half * HC + 4 * f : gy;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sm + ((size_t)((row * 2 + (col & 1)) * KS + (col >> 1))) * PS + 4 * f);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(in ? 16 : 0) : "memory");   // outside: zeros
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const float* rows = sm + (size_t)r * 2 * KS * PS;     // this thread's output row y0 + r reads staged rows r .. r + 2
+    if (half == 0) c3k_dgrad_s1_body<COUT, 0>(rows, t, acc);
+    else c3k_dgrad_s1_body<COUT, 1>(rows, t, acc);
   }
-  __syncthreads();
-  const int px = x0 + 2 * t;
-  if (half == 0 && px < W) {
-#pragma unroll
-    for (int d = 0; d < 2; ++d)
-#pragma unroll
-      for (int ci = 0; ci < 3; ++ci) acc[d][ci] += sm[t * 6 + d * 3 + ci];
+  const int px = x0 + 2 * t, y = y0 + r;
+  if (px < W && y < H) {
     float* out = gx + ((size_t)(n * H + y) * W + px) * 3;                  // 6 contiguous floats: pixels (px, px + 1)
     *reinterpret_cast<float2*>(out) = make_float2(acc[0][0], acc[0][1]);
     *reinterpret_cast<float2*>(out + 2) = make_float2(acc[0][2], acc[1][0]);
@@ -920,11 +944,12 @@ int cn_skinny_dgrad(const cn_conv_desc* d, const float* gy, const float* w, floa
       return 1;
     }
     if ((g_c3k & 4) && d->stride == 1 && d->cout == 64 && W % 2 == 0) {
-      const int smem = 3 * 2 * 65 * (64 + 4) * (int)sizeof(float);
-      int rc = opt_in_smem(c3k_dgrad_s1_kernel<64>, smem); if (rc) return rc;
+      constexpr int R = 4;
+      const int smem = (R + 2) * 2 * 65 * (32 + 4) * (int)sizeof(float);
+      int rc = opt_in_smem(c3k_dgrad_s1_kernel<64, R>, smem); if (rc) return rc;
       CN_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_c3w, w, (size_t)27 * 64 * sizeof(float), 0, cudaMemcpyDeviceToDevice, st));
-      dim3 grid((W + 127) / 128, H, d->batch);
-      c3k_dgrad_s1_kernel<64><<<grid, 128, smem, st>>>(gy, gx, H, W);
+      dim3 grid((W + 127) / 128, (H + R - 1) / R, d->batch);
+      c3k_dgrad_s1_kernel<64, R><<<grid, 64 * R, smem, st>>>(gy, gx, H, W);
       CN_CHECK_LAUNCH();
       return 1;
     }
@@ -981,8 +1006,15 @@ int cn_skinny_wgrad(const cn_conv_desc* d, const float* x, const float* gy, floa
     same_pad(H, 3, d->stride, &OH, &pby); same_pad(W, 3, d->stride, &OW, &pbx);
     int rows = d->batch * OH * ((OW + 127) / 128);
     int blocks = 2 * sm_count(); if (blocks > rows) blocks = rows;
-    if (d->stride == 2) c3_wgrad_kernel<2, 48><<<blocks, 256, 0, st>>>(x, gy, scratch, d->batch, H, W, OH, OW, pby, pbx);
-    else c3_wgrad_kernel<1, 48><<<blocks, 256, 0, st>>>(x, gy, scratch, d->batch, H, W, OH, OW, pby, pbx);
+    if (d->stride == 2) {
+      const int smem = (2 * 128 * 48 + 2 * ((3 * (127 * 2 + 3) * 3 + 8 + 3) & ~3)) * (int)sizeof(float);
+      int rc = opt_in_smem(c3_wgrad_kernel<2, 48>, smem); if (rc) return rc;
+      c3_wgrad_kernel<2, 48><<<blocks, 256, smem, st>>>(x, gy, scratch, d->batch, H, W, OH, OW, pby, pbx);
+    } else {
+      const int smem = (2 * 128 * 48 + 2 * ((3 * (127 * 1 + 3) * 3 + 8 + 3) & ~3)) * (int)sizeof(float);
+      int rc = opt_in_smem(c3_wgrad_kernel<1, 48>, smem); if (rc) return rc;
+      c3_wgrad_kernel<1, 48><<<blocks, 256, smem, st>>>(x, gy, scratch, d->batch, H, W, OH, OW, pby, pbx);
+    }
     CN_CHECK_LAUNCH();
     sum_partials_kernel<<<(27 * 48 + 31) / 32, dim3(32, 8), 0, st>>>(scratch, blocks, 27 * 48, gw);
     CN_CHECK_LAUNCH();
