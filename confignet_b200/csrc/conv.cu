@@ -1818,23 +1818,33 @@ dense_small_kernel(const float* __restrict__ X, int M, int K, const float* __res
 #pragma unroll
   for (int m = 0; m < MT; ++m) acc[m] = 0.f;
   for (int k0 = kbeg; k0 < kend; k0 += 128) {
+    // this thread's 16 weights of the chunk first (ordered loads: all in flight), then the x tile through cp.async:
+    // ONE memory round trip per chunk (the loop used to wait for x, then for the weights group by group - these layers
+    // are nothing but latency, ~150 launches per step)
+    float wv[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int k = k0 + warp * 16 + e;
+      wv[e] = (nok && k < kend) ? cn_ldg1_ordered(W + (size_t)k * wsc + (size_t)n * wsn) : 0.f;
+    }
     __syncthreads();
     for (int i = tid; i < MT * 128; i += 256) {
       const int m = i >> 7, kk = i & 127;
-      xs[m][kk] = (m < M && k0 + kk < kend) ? __ldg(X + (size_t)m * K + k0 + kk) : 0.f;
+      const bool in = m < M && k0 + kk < kend;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(&xs[m][kk])), "l"(in ? X + (size_t)m * K + k0 + kk : X),
+                   "r"(in ? 4 : 0) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < 16; q += 4) {
-      const int kk = warp * 16 + q, k = k0 + kk;
-      float wv[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) wv[e] = (nok && k + e < kend) ? __ldg(W + (size_t)(k + e) * wsc + (size_t)n * wsn) : 0.f;
+      const int kk = warp * 16 + q;
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         const float4 xv = *reinterpret_cast<const float4*>(&xs[m][kk]);
-        acc[m] = fmaf(xv.x, wv[0], acc[m]); acc[m] = fmaf(xv.y, wv[1], acc[m]);
-        acc[m] = fmaf(xv.z, wv[2], acc[m]); acc[m] = fmaf(xv.w, wv[3], acc[m]);
+        acc[m] = fmaf(xv.x, wv[q], acc[m]); acc[m] = fmaf(xv.y, wv[q + 1], acc[m]);
+        acc[m] = fmaf(xv.z, wv[q + 2], acc[m]); acc[m] = fmaf(xv.w, wv[q + 3], acc[m]);
       }
     }
   }
@@ -1938,9 +1948,17 @@ splitk_reduce_kernel(const float* __restrict__ ws, int nsplit, size_t n4, int cn
                      float* __restrict__ out) {
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n4) return;
-  float4 a = reinterpret_cast<const float4*>(ws)[i];
-  for (int z = 1; z < nsplit; ++z) {
-    const float4 v = reinterpret_cast<const float4*>(ws)[(size_t)z * n4 + i];
+  float4 a = cn_ldg4_ordered(ws + 4 * i);
+  int z = 1;
+  for (; z + 3 < nsplit; z += 4) {                    // four slabs in flight, added in split order
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = cn_ldg4_ordered(ws + 4 * ((size_t)(z + u) * n4 + i));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+  }
+  for (; z < nsplit; ++z) {
+    const float4 v = cn_ldg4_ordered(ws + 4 * ((size_t)z * n4 + i));
     a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
   }
   if (bias != nullptr) {

@@ -16,6 +16,8 @@
 //             (R+sy, C+sx), sy,sx in {-1,0,1}, and the taps that land on the same source pixel are pre-summed
 //             (sub-pixel folding, SURVEY.md section 7 hard part 5): 25 folded taps per 2x2 output cell instead of 64.
 #include "common.cuh"
+#include <stdlib.h>
+#include <map>
 
 namespace {
 
@@ -26,6 +28,23 @@ __device__ __forceinline__ void fma4(float4& a, float x, const float4& w) {
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
   acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
   return acc;
+}
+
+// cp.async staging (global -> shared without a register round trip): every piece a thread issues is in flight at once.  The
+// plain "load, store to shared" loops below it replaced kept ONE load in flight per thread (the compiler places each store
+// right behind its load), i.e. a chain of ~10 dependent HBM / L2 round trips per block before the first FFMA.
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(float* dst, const float* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -42,15 +61,15 @@ c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
   __shared__ __align__(16) float s_w[27 * COUT];
   __shared__ float s_x[3 * RS];
   const int tid = threadIdx.x, n = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * 128;
-  for (int i = tid; i < 27 * C4; i += 256) reinterpret_cast<float4*>(s_w)[i] = ldg4(w + 4 * i);
+  for (int i = tid; i < 27 * C4; i += 256) cp_async16(s_w + 4 * i, w + 4 * i);
   const int ix0 = ox0 * S - pbx;
   for (int i = tid; i < 3 * RS; i += 256) {
     const int r = i / RS, j = i - r * RS, col = j / 3;
     const int iy = oy * S + r - pby, ix = ix0 + col;
-    float v = 0.f;
-    if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) v = __ldg(x + ((long long)(n * H + iy) * W + ix0) * 3 + j);
-    s_x[i] = v;
+    const bool in = (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+    cp_async4_zfill(s_x + i, in ? x + ((long long)(n * H + iy) * W + ix0) * 3 + j : x, in);
   }
+  cp_async_wait_all();
   __syncthreads();
   const int q = tid & 3, pp = tid >> 2, la = 2 * pp * S;
   float4 acc[2][CPT];
@@ -190,12 +209,6 @@ c3_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ w, float
 // The rows are staged with cp.async into TWO buffers: row i + 1 is in flight while row i is multiplied (one buffer and plain
 // loads left every row iteration waiting on ~9 dependent scalar loads per thread: 93-113 us per launch for a layer whose
 // FFMAs take ~40 us, profiles/r02_launches_s2c_summary.txt).
-__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4_zfill(float* dst, const float* src, bool valid) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(valid ? 4 : 0) : "memory");
-}
 template <int S, int COUT>
 __global__ void __launch_bounds__(256, 2)
 c3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ part,
@@ -336,14 +349,14 @@ up4c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const
   float4* s_wd = reinterpret_cast<float4*>(sm);               // [25][CIN]
   float4* s_x = s_wd + 25 * CIN;                              // [3][XW][PS4]
   const int tid = threadIdx.x, n = blockIdx.z, R = blockIdx.y, c0 = blockIdx.x * 128;
-  build_folded<CIN>(w, s_wd, tid, 256);
   for (int i = tid; i < 3 * XW * CI4; i += 256) {
     const int f = i % CI4, pc = i / CI4, col = pc % XW, row = pc / XW;
     const int r = R - 1 + row, c = c0 - 1 + col;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((unsigned)r < (unsigned)H && (unsigned)c < (unsigned)W) v = ldg4(x + ((size_t)(n * H + r) * W + c) * CIN + 4 * f);
-    s_x[(row * XW + col) * PS4 + f] = v;
+    const bool in = (unsigned)r < (unsigned)H && (unsigned)c < (unsigned)W;
+    cp_async16_zfill(reinterpret_cast<float*>(s_x + (row * XW + col) * PS4 + f), in ? x + ((size_t)(n * H + r) * W + c) * CIN + 4 * f : x, in);
   }
+  build_folded<CIN>(w, s_wd, tid, 256);                       // overlaps the copies in flight
+  cp_async_wait_all();
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
   const int dy = warp & 1, cell = (warp >> 1) * 32 + lane;
@@ -397,6 +410,15 @@ up4c3_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ w, fl
   float* s_wt = sm;                         // [25][3][CIN]  (transposed: source channels contiguous)
   float* s_gy = sm + 25 * 3 * CIN;          // [5][GW][3]
   const int tid = threadIdx.x, n = blockIdx.z, r = blockIdx.y, c0 = blockIdx.x * PXB;
+  {
+    const int OHh = 2 * H, OWw = 2 * W;
+    for (int i = tid; i < 5 * GW * 3; i += 256) {           // cp.async: all pieces in flight while the kernel is folded below
+      const int row = i / (GW * 3), j = i - row * GW * 3, col = j / 3;
+      const int oy = 2 * r - 2 + row, ox = 2 * c0 - 2 + col;
+      const bool in = (unsigned)oy < (unsigned)OHh && (unsigned)ox < (unsigned)OWw;
+      cp_async4_zfill(s_gy + i, in ? gy + ((long long)(n * OHh + oy) * OWw + (2 * c0 - 2)) * 3 + j : gy, in);
+    }
+  }
   for (int i = tid; i < 25 * CIN; i += 256) {
     const int ci = i % CIN, l = i / CIN, lr = l / 5, lc = l - lr * 5;
     int y0, y1, x0, x1;
@@ -407,14 +429,7 @@ up4c3_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ w, fl
         for (int co = 0; co < 3; ++co) a[co] += __ldg(w + ((size_t)(ty * 4 + tx) * CIN + ci) * 3 + co);
     for (int co = 0; co < 3; ++co) s_wt[(l * 3 + co) * CIN + ci] = a[co];
   }
-  const int OHh = 2 * H, OWw = 2 * W;
-  for (int i = tid; i < 5 * GW * 3; i += 256) {
-    const int row = i / (GW * 3), j = i - row * GW * 3, col = j / 3;
-    const int oy = 2 * r - 2 + row, ox = 2 * c0 - 2 + col;
-    float v = 0.f;
-    if ((unsigned)oy < (unsigned)OHh && (unsigned)ox < (unsigned)OWw) v = __ldg(gy + ((long long)(n * OHh + oy) * OWw + (2 * c0 - 2)) * 3 + j);
-    s_gy[i] = v;
-  }
+  cp_async_wait_all();
   __syncthreads();
   const int grp = tid % NG, px = tid / NG;
   float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
@@ -557,10 +572,10 @@ c3k_fwd_kernel(const float* __restrict__ x, const float* __restrict__ bias, floa
   for (int i = tid; i < 3 * RS; i += 128) {
     const int r = i / RS, j = i - r * RS, col = j / 3;
     const int iy = oy * S + r - pby, ix = ix0 + col;
-    float v = 0.f;
-    if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) v = __ldg(x + ((long long)(n * H + iy) * W + ix0) * 3 + j);
-    s_x[i] = v;
+    const bool in = (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+    cp_async4_zfill(s_x + i, in ? x + ((long long)(n * H + iy) * W + ix0) * 3 + j : x, in);
   }
+  cp_async_wait_all();
   __syncthreads();
   float xv[27];
 #pragma unroll
@@ -599,10 +614,10 @@ c3k_dgrad_s2_kernel(const float* __restrict__ gy, float* __restrict__ gx, int H,
   for (int i = tid; i < 2 * GYW * C4; i += 128) {
     const int f = i % C4, pc = i / C4, col = pc % GYW, row = pc / GYW;
     const int gr = a - 1 + row, gc = b0 - 1 + col;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((unsigned)gr < (unsigned)OH && (unsigned)gc < (unsigned)OW) v = ldg4(gy + ((size_t)(n * OH + gr) * OW + gc) * COUT + 4 * f);
-    *reinterpret_cast<float4*>(sm + (row * GYW + col) * PS + 4 * f) = v;
+    const bool in = (unsigned)gr < (unsigned)OH && (unsigned)gc < (unsigned)OW;
+    cp_async16_zfill(sm + (row * GYW + col) * PS + 4 * f, in ? gy + ((size_t)(n * OH + gr) * OW + gc) * COUT + 4 * f : gy, in);
   }
+  cp_async_wait_all();
   __syncthreads();
   float acc[2][2][3];
 #pragma unroll
@@ -830,7 +845,7 @@ p3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float
 // (profiles/r02_skinny_c3k.txt, D.block0 at batch 32): dgrad 119.8 -> 89.1 us; forward 85.0 -> 85.0 us (both generations sit
 // on the FP32 pipe: ptxas keeps the kernel out of the FFMA operand slot and loads it with LDC.128, and three-register
 // FFMAs issue at half rate) - so only the gradient kernel is on by default.
-int g_c3k = 6;
+int g_c3k = [] { const char* e = getenv("CN_C3K"); return e ? atoi(e) : 6; }();   // environment CN_C3K overrides for A/B runs
 
 bool is_p3(const cn_conv_desc* d) {
   return d->nd == 2 && d->cin == 3 && d->cout == 3 && d->ksize[0] == 1 && d->ksize[1] == 1 && d->stride == 1 && d->upsample == 1 &&
@@ -855,10 +870,13 @@ bool is_up4c3(const cn_conv_desc* d) {
 
 template <typename K>
 int opt_in_smem(K kernel, int bytes) {
-  static int have = 0;            // per instantiation: keeps the attribute call out of captured CUDA graphs
-  if (bytes > 48 * 1024 && have < bytes) {
+  // once per (kernel, size): keeps the attribute call out of captured CUDA graphs.  Keyed by the kernel's ADDRESS: two
+  // instantiations with the same signature (c3_wgrad_kernel<2, 48> / <1, 48>) share this function template's statics.
+  static std::map<const void*, int> have;
+  int& h = have[reinterpret_cast<const void*>(kernel)];
+  if (bytes > 48 * 1024 && h < bytes) {
     CN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    have = bytes;
+    h = bytes;
   }
   return CN_OK;
 }
