@@ -213,7 +213,8 @@ __global__ void chan_affine_kernel(const float* __restrict__ a, const float* __r
 template <bool HB, bool HC>
 __global__ void __launch_bounds__(256)
 chan_affine_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
-                        const float4* __restrict__ coef, int p, int ch, int flags, float alpha, float* __restrict__ out) {
+                        const float4* __restrict__ coef, const float4* __restrict__ coef2, int p, int ch, int flags, float alpha,
+                        float* __restrict__ out) {
   const int chq = ch >> 2, R = 256 / chq;
   const int tid = threadIdx.x, q = tid % chq, rr = tid / chq;
   if (rr >= R) return;
@@ -223,6 +224,14 @@ chan_affine_rows_kernel(const float* __restrict__ a, const float* __restrict__ b
   float4 k[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) k[e] = coef[(size_t)n * ch + 4 * q + e];
+  // second coefficient set (cn_chan_affine2): + k2.x * a_raw + k2.w after the mask - the layer-style gradient riding on
+  // the InstanceNorm gradient's pass over the same tensor
+  float k2x[4] = {0.f, 0.f, 0.f, 0.f}, k2w[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool two = coef2 != nullptr;
+  if (two) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float4 t = coef2[(size_t)n * ch + 4 * q + e]; k2x[e] = t.x; k2w[e] = t.w; }
+  }
   const size_t base = (size_t)n * p * ch + 4 * q;
   constexpr int U = 4;                                   // four pixels of every operand in flight per thread
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -237,6 +246,7 @@ chan_affine_rows_kernel(const float* __restrict__ a, const float* __restrict__ b
       if (HB) v = fmaf(k[e].y, br[e], v);
       if (HC) { float cc = cr[e]; if (flags & CN_FLAG_MASK_C) cc *= lrelu_d(araw, alpha); v = fmaf(k[e].z, cc, v); }
       if (flags & CN_FLAG_MASK_OUT) v *= lrelu_d(araw, alpha);
+      if (two) v += fmaf(k2x[e], araw, k2w[e]);
       o[e] = v;
     }
     *reinterpret_cast<float4*>(o4) = make_float4(o[0], o[1], o[2], o[3]);
@@ -260,24 +270,32 @@ chan_affine_rows_kernel(const float* __restrict__ a, const float* __restrict__ b
   }
 }
 
+static bool affine_rows_ok(int n, int ch) {
+  static int rows_form = -1;
+  if (rows_form < 0) { const char* e = getenv("CN_AFFINE_ROWS"); rows_form = e ? atoi(e) : 1; }
+  return rows_form && ch % 4 == 0 && ch <= 1024 && n <= 65535;
+}
+static void launch_affine_rows(const float* a, const float* b, const float* c, const float* coef, const float* coef2,
+                               int n, int p, int ch, int flags, float alpha, float* out, cudaStream_t st) {
+  const int R = 256 / (ch / 4);
+  int psplit = (8 * 148 + n - 1) / n;                    // ~8 blocks of 256 threads per SM
+  int maxsplit = p / (2 * R); if (maxsplit < 1) maxsplit = 1;
+  if (psplit > maxsplit) psplit = maxsplit;
+  dim3 grid(n, psplit);
+  const float4 *k4 = (const float4*)coef, *k2 = (const float4*)coef2;
+  if (b && c) chan_affine_rows_kernel<true, true><<<grid, 256, 0, st>>>(a, b, c, k4, k2, p, ch, flags, alpha, out);
+  else if (b) chan_affine_rows_kernel<true, false><<<grid, 256, 0, st>>>(a, b, c, k4, k2, p, ch, flags, alpha, out);
+  else if (c) chan_affine_rows_kernel<false, true><<<grid, 256, 0, st>>>(a, b, c, k4, k2, p, ch, flags, alpha, out);
+  else chan_affine_rows_kernel<false, false><<<grid, 256, 0, st>>>(a, b, c, k4, k2, p, ch, flags, alpha, out);
+}
+
 extern "C" int cn_chan_affine(const float* a, const float* b, const float* c, const float* coef,
                               int n, int p, int ch, int flags, float alpha, float* out, void* stream) {
   CN_REQUIRE(a && coef && out && n > 0 && p > 0 && ch > 0, CN_ERR_BAD_SHAPE, "cn_chan_affine: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)n * p * ch;
-  static int rows_form = -1;
-  if (rows_form < 0) { const char* e = getenv("CN_AFFINE_ROWS"); rows_form = e ? atoi(e) : 1; }
-  if (rows_form && ch % 4 == 0 && ch <= 1024 && n <= 65535) {
-    const int R = 256 / (ch / 4);
-    int psplit = (8 * 148 + n - 1) / n;                    // ~8 blocks of 256 threads per SM
-    int maxsplit = p / (2 * R); if (maxsplit < 1) maxsplit = 1;
-    if (psplit > maxsplit) psplit = maxsplit;
-    dim3 grid(n, psplit);
-    const float4* k4 = (const float4*)coef;
-    if (b && c) chan_affine_rows_kernel<true, true><<<grid, 256, 0, st>>>(a, b, c, k4, p, ch, flags, alpha, out);
-    else if (b) chan_affine_rows_kernel<true, false><<<grid, 256, 0, st>>>(a, b, c, k4, p, ch, flags, alpha, out);
-    else if (c) chan_affine_rows_kernel<false, true><<<grid, 256, 0, st>>>(a, b, c, k4, p, ch, flags, alpha, out);
-    else chan_affine_rows_kernel<false, false><<<grid, 256, 0, st>>>(a, b, c, k4, p, ch, flags, alpha, out);
+  if (affine_rows_ok(n, ch)) {
+    launch_affine_rows(a, b, c, coef, nullptr, n, p, ch, flags, alpha, out, st);
     CN_CHECK_LAUNCH();
     return CN_OK;
   }
@@ -289,6 +307,19 @@ extern "C" int cn_chan_affine(const float* a, const float* b, const float* c, co
     int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
     chan_affine_kernel<1><<<blocks, 256, 0, st>>>(a, b, c, (const float4*)coef, p, ch, flags, alpha, out, total);
   }
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
+// out = [cn_chan_affine(a, b, c, coef, flags)] + coef2.x * a_raw + coef2.w: two broadcast-affine results over the same
+// tensor in ONE pass (the InstanceNorm and layer-style gradients of a DiscrBlock's conv output, building_blocks.py:100-106).
+// Channel counts the row-walking kernel does not take (ch % 4 != 0 or ch > 1024) return CN_ERR_UNSUPPORTED: the caller
+// then issues the two passes and adds them.
+extern "C" int cn_chan_affine2(const float* a, const float* b, const float* c, const float* coef, const float* coef2,
+                               int n, int p, int ch, int flags, float alpha, float* out, void* stream) {
+  CN_REQUIRE(a && coef && coef2 && out && n > 0 && p > 0 && ch > 0, CN_ERR_BAD_SHAPE, "cn_chan_affine2: bad arguments");
+  CN_REQUIRE(affine_rows_ok(n, ch), CN_ERR_UNSUPPORTED, "cn_chan_affine2: channel count needs the two-pass form");
+  launch_affine_rows(a, b, c, coef, coef2, n, p, ch, flags, alpha, out, (cudaStream_t)stream);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

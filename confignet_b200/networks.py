@@ -114,9 +114,9 @@ def generator_forward(p, z, rotation, output_res=256, zs=None, n_mlp_layers=2, o
 def discr_block(x, p, prefix, return_styles):
     """DiscrBlock.call (building_blocks.py:97-111)."""
     c = ops.conv(x, p[prefix + "/conv/kernel"], p[prefix + "/conv/bias"], stride=2)
-    style = ops.layer_style(c) if return_styles else None
-    y = ops.lrelu_instance_norm(c, p[prefix + "/in/gamma"], p[prefix + "/in/beta"], 0.3)
-    return y, style
+    if return_styles:          # both consumers of c as one autograd node: their input gradients leave in one pass
+        return ops.discr_norm(c, p[prefix + "/in/gamma"], p[prefix + "/in/beta"], 0.3)
+    return ops.lrelu_instance_norm(c, p[prefix + "/in/gamma"], p[prefix + "/in/beta"], 0.3), None
 
 
 def discriminator_forward(p, img, n_layers=5):

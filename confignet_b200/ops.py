@@ -295,6 +295,44 @@ STYLE_EPS = 1e-6    # confignet_utils.py:154
 ADAIN_EPS = 1e-3    # keras LayerNormalization default epsilon [TF-2.1]
 
 
+def _in_bwd_bwd(c, gamma, gy, h, alpha, need_c, need_gy):
+    """Second-order terms of InstanceNorm(LeakyReLU(c)): given the cotangent h of the input gradient, the gradients wrt c,
+    gamma and gy (shared by LReluInstanceNormBwd and the fused DiscrNormBwd)."""
+    h = _chk(h)
+    n, p, ch = _npc(c)
+    fl = FLAG_LRELU_A | FLAG_MASK_C
+    s = _sums(c, gy, h, flags=fl, alpha=alpha)
+    (coef_a, coef_g), dgamma, _ = _coef(COEF_IN_BWDBWD, s, gamma, None, n, ch, p, IN_EPS, 2, (ch,))
+    d_c = _affine(c, gy, h, coef_a, fl | FLAG_MASK_OUT, alpha) if need_c else None
+    d_gy = _affine(c, None, h, coef_g, fl, alpha) if need_gy else None
+    return d_c, (dgamma if _want_param_grads() else None), d_gy
+
+
+def _style_bwd_bwd(c, gstyle, h, need_c):
+    """Second-order terms of get_layer_style: gradients wrt c and gstyle given the cotangent h of the input gradient."""
+    h = _chk(h)
+    n, p, ch = _npc(c)
+    s = _sums(c, h)
+    (coef,), d_gstyle, _ = _coef(COEF_STYLE_BWDBWD, s, gstyle, None, n, ch, p, STYLE_EPS, 1, (n, 2 * ch))
+    d_c = _affine(c, h, None, coef) if need_c else None
+    return d_c, d_gstyle
+
+
+def _affine2(a, b, coef, coef2, flags=0, alpha=0.0):
+    """[affine(a, b, coef, flags)] + coef2.x * a + coef2.w in one pass (cn_chan_affine2); channel counts the one-pass
+    kernel does not take fall back to two passes and an add (same values, same rounding)."""
+    n, p, ch = _npc(a)
+    if ch % 4 == 0 and ch <= 1024 and n <= 65535:
+        out = torch.empty_like(a)
+        try:
+            L.call("cn_chan_affine2", _p(a), _p(b), None, _p(coef), _p(coef2), n, p, ch, flags, alpha, _p(out), _stream())
+            return out
+        except L.CnError as e:                     # CN_AFFINE_ROWS=0 (A/B runs): the row-walking kernel is switched off
+            if "two-pass" not in str(e):
+                raise
+    return _affine(a, b, None, coef, flags, alpha) + _affine(a, None, None, coef2)
+
+
 class LReluInstanceNorm(torch.autograd.Function):
     """y = InstanceNormalization(LeakyReLU(alpha)(c)) (building_blocks.py:104-106,
     instance_normalization.py:108-131); any-order differentiable."""
@@ -338,14 +376,8 @@ class LReluInstanceNormBwd(torch.autograd.Function):
         c, gamma, gy = ctx.saved_tensors
         if h is None:
             return None, None, None, None
-        h = _chk(h)
-        n, p, ch = _npc(c)
-        fl = FLAG_LRELU_A | FLAG_MASK_C
-        s = _sums(c, gy, h, flags=fl, alpha=ctx.alpha)
-        (coef_a, coef_g), dgamma, _ = _coef(COEF_IN_BWDBWD, s, gamma, None, n, ch, p, IN_EPS, 2, (ch,))
-        d_c = _affine(c, gy, h, coef_a, fl | FLAG_MASK_OUT, ctx.alpha) if ctx.needs_input_grad[0] else None
-        d_gy = _affine(c, None, h, coef_g, fl, ctx.alpha) if ctx.needs_input_grad[2] else None
-        return d_c, (dgamma if _want_param_grads() else None), d_gy, None
+        d_c, dgamma, d_gy = _in_bwd_bwd(c, gamma, gy, h, ctx.alpha, ctx.needs_input_grad[0], ctx.needs_input_grad[2])
+        return d_c, dgamma, d_gy, None
 
 
 def lrelu_instance_norm(c, gamma, beta, alpha=0.3):
@@ -384,16 +416,79 @@ class LayerStyleBwd(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, h):
         c, gstyle = ctx.saved_tensors
-        h = _chk(h)
-        n, p, ch = _npc(c)
-        s = _sums(c, h)
-        (coef,), d_gstyle, _ = _coef(COEF_STYLE_BWDBWD, s, gstyle, None, n, ch, p, STYLE_EPS, 1, (n, 2 * ch))
-        d_c = _affine(c, h, None, coef) if ctx.needs_input_grad[0] else None
-        return d_c, d_gstyle
+        return _style_bwd_bwd(c, gstyle, h, ctx.needs_input_grad[0])
 
 
 def layer_style(c):
     return LayerStyle.apply(c)
+
+
+class DiscrNorm(torch.autograd.Function):
+    """The two consumers of a DiscrBlock's conv output c (building_blocks.py:100-106): style = get_layer_style(c) and
+    y = InstanceNormalization(LeakyReLU(c)), as ONE autograd node.  Values are those of layer_style(c) and
+    lrelu_instance_norm(c, ...); the point is the backward: when both outputs carry a gradient the two input gradients
+    leave in one pass (DiscrNormBwd) instead of statistics + affine per consumer and an add by the autograd engine
+    (11 -> 5 tensor passes), and the raw statistics of the forward pass are reused.  Any-order differentiable."""
+
+    @staticmethod
+    def forward(ctx, c, gamma, beta, alpha):
+        c, gamma, beta = _chk(c), _chk(gamma), _chk(beta)
+        n, p, ch = _npc(c)
+        s_raw = _sums(c)
+        _, style, _ = _coef(COEF_STYLE_FWD, s_raw, None, None, n, ch, p, STYLE_EPS, 0, (n, 2 * ch))
+        s = _sums(c, flags=FLAG_LRELU_A, alpha=alpha)
+        (coef,), _, _ = _coef(COEF_IN_FWD, s, gamma, beta, n, ch, p, IN_EPS)
+        ctx.alpha = alpha
+        ctx.save_for_backward(c, gamma, s_raw)
+        ctx.set_materialize_grads(False)
+        return _affine(c, None, None, coef, FLAG_LRELU_A, alpha), style
+
+    @staticmethod
+    def backward(ctx, gy, gstyle):
+        c, gamma, s_raw = ctx.saved_tensors
+        gc = dgamma = dbeta = None
+        if gy is not None and gstyle is not None:
+            gc, dgamma, dbeta = DiscrNormBwd.apply(c, gamma, gy, gstyle, s_raw, ctx.alpha)
+        elif gy is not None:                               # R1 passes of a later head: only the trunk carries a gradient
+            gc, dgamma, dbeta = LReluInstanceNormBwd.apply(c, gamma, gy, ctx.alpha)
+        elif gstyle is not None:                           # R1 pass of this block's own style head
+            gc = LayerStyleBwd.apply(c, gstyle)
+        if not _want_param_grads():
+            dgamma = dbeta = None
+        return gc, dgamma, dbeta, None
+
+
+class DiscrNormBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, c, gamma, gy, gstyle, s_raw, alpha):
+        c, gamma, gy, gstyle = _chk(c), _chk(gamma), _chk(gy), _chk(gstyle)
+        n, p, ch = _npc(c)
+        s = _sums(c, gy, flags=FLAG_LRELU_A, alpha=alpha)
+        (coef_in,), dgamma, dbeta = _coef(COEF_IN_BWD, s, gamma, None, n, ch, p, IN_EPS, 1, (ch,), (ch,))
+        (coef_st,), _, _ = _coef(COEF_STYLE_BWD, s_raw, gstyle, None, n, ch, p, STYLE_EPS)
+        ctx.alpha = alpha
+        ctx.save_for_backward(c, gamma, gy, gstyle)
+        ctx.set_materialize_grads(False)
+        return _affine2(c, gy, coef_in, coef_st, FLAG_LRELU_A | FLAG_MASK_OUT, alpha), dgamma, dbeta
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, h, h_dgamma, h_dbeta):
+        if h_dgamma is not None or h_dbeta is not None:
+            raise NotImplementedError("second-order terms through d(gamma)/d(beta) are not on ConfigNet's path")
+        c, gamma, gy, gstyle = ctx.saved_tensors
+        if h is None:
+            return None, None, None, None, None, None
+        need_c = ctx.needs_input_grad[0]
+        d_c1, dgamma, d_gy = _in_bwd_bwd(c, gamma, gy, h, ctx.alpha, need_c, ctx.needs_input_grad[2])
+        d_c2, d_gstyle = _style_bwd_bwd(c, gstyle, h, need_c)
+        d_c = (d_c1 + d_c2) if need_c else None
+        return d_c, dgamma, d_gy, (d_gstyle if ctx.needs_input_grad[3] else None), None, None
+
+
+def discr_norm(c, gamma, beta, alpha=0.3):
+    """(InstanceNormalization(LeakyReLU(alpha)(c)), get_layer_style(c)) - see DiscrNorm."""
+    return DiscrNorm.apply(c, gamma, beta, alpha)
 
 
 class AdaIN(torch.autograd.Function):

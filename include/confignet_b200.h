@@ -115,6 +115,11 @@ int cn_chan_sums(const float* a, const float* b, const float* c, int n, int p, i
 /* out = ka[n,ch]*a + kb[n,ch]*b + kc[n,ch]*c + k0[n,ch]; coef is (n, ch, 4) = (ka,kb,kc,k0). */
 int cn_chan_affine(const float* a, const float* b, const float* c, const float* coef,
                    int n, int p, int ch, int flags, float alpha, float* out, void* stream);
+/* out = [cn_chan_affine(a, b, c, coef, flags)] + coef2.x[n,ch]*a_raw + coef2.w[n,ch]: the InstanceNorm and layer-style
+ * gradients of one DiscrBlock conv output (building_blocks.py:100-106: both consume `c`) in one pass instead of two
+ * passes and an add.  CN_ERR_UNSUPPORTED when ch % 4 != 0 or ch > 1024 (use two cn_chan_affine calls). */
+int cn_chan_affine2(const float* a, const float* b, const float* c, const float* coef, const float* coef2,
+                    int n, int p, int ch, int flags, float alpha, float* out, void* stream);
 /* closed-form coefficients from the 7 sums.  kind:
  *  0 IN fwd      p0=gamma p1=beta          -> coef0
  *  1 IN bwd      sums(a,gy) p0=gamma       -> coef0 (input grad), out0=dgamma[ch], out1=dbeta[ch]

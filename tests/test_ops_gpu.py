@@ -144,6 +144,45 @@ def test_layer_style_all_orders(dev, shape):
     assert nerr(q2[0], g2[0]) <= 5 * TOL_FP32 and nerr(q2[1], g2[1]) <= 5 * TOL_FP32
 
 
+@pytest.mark.parametrize("shape", [(3, 5, 4, 6), (2, 16, 16, 48), (16, 8, 8, 192), (9, 12, 12, 24)])
+def test_discr_norm_fused_node_all_orders(dev, shape):
+    """ops.discr_norm = (InstanceNorm(LeakyReLU(c)), layer_style(c)) as one node (DiscrBlock, building_blocks.py:100-106):
+    outputs, the one-pass input gradient when both outputs carry a cotangent (cn_chan_affine2), the single-consumer
+    branches, and the second-order terms through the fused backward - against the fp64 oracle; the fused input gradient
+    must also equal the sum of the two unfused nodes' gradients bit for bit."""
+    from confignet_b200 import ops
+    torch.manual_seed(11)
+    c = torch.randn(*shape); gam = torch.randn(shape[-1]); bet = torch.randn(shape[-1])
+    cr, gr, br = [t.double().requires_grad_(True) for t in (c, gam, bet)]
+    yr = O.instance_norm_std(O.lrelu(cr, 0.3), gr, br)
+    sr = O.layer_style(cr)
+    gy = torch.randn(*shape); gs = torch.randn(*sr.shape); h = torch.randn(*shape)
+    gyr, gsr = gy.double().requires_grad_(True), gs.double().requires_grad_(True)
+    g1 = torch.autograd.grad((yr, sr), (cr, gr, br), (gyr, gsr), create_graph=True)
+    g2 = torch.autograd.grad(g1[0], (cr, gr, gyr, gsr), h.double())
+    cg, gg, bg = [t.to(dev).requires_grad_(True) for t in (c, gam, bet)]
+    y, st = ops.discr_norm(cg, gg, bg, 0.3)
+    gyg, gsg = gy.to(dev).requires_grad_(True), gs.to(dev).requires_grad_(True)
+    q1 = torch.autograd.grad((y, st), (cg, gg, bg), (gyg, gsg), create_graph=True)
+    q2 = torch.autograd.grad(q1[0], (cg, gg, gyg, gsg), h.to(dev))
+    assert nerr(y, yr) <= TOL_FP32 and nerr(st, sr) <= TOL_FP32
+    for a, b in zip(q1, g1):
+        assert nerr(a, b) <= TOL_FP32
+    for a, b in zip(q2, g2):
+        assert nerr(a, b) <= 5 * TOL_FP32
+    # the unfused nodes on the same inputs: same outputs, and gc(fused) == gc(InstanceNorm) + gc(style) exactly
+    c2, g2_, b2 = [t.to(dev).requires_grad_(True) for t in (c, gam, bet)]
+    y2 = ops.lrelu_instance_norm(c2, g2_, b2, 0.3); st2 = ops.layer_style(c2)
+    assert torch.equal(y, y2) and torch.equal(st, st2)
+    ga, = torch.autograd.grad(y2, c2, gy.to(dev), retain_graph=True)
+    gb, = torch.autograd.grad(st2, c2, gs.to(dev))
+    assert torch.equal(q1[0].detach(), ga + gb)
+    # single-consumer branches of the fused node (the R1 passes): only y, only the style
+    only_y, = torch.autograd.grad(y, cg, gy.to(dev), retain_graph=True)
+    only_s, = torch.autograd.grad(st, cg, gs.to(dev), retain_graph=True)
+    assert torch.equal(only_y, ga) and torch.equal(only_s, gb)
+
+
 @pytest.mark.parametrize("n,ch,side", [(3, 8, 4), (16, 128, 6), (5, 512, 3)])
 def test_adain(dev, n, ch, side):
     from confignet_b200 import ops
