@@ -483,6 +483,19 @@ def run_b200(args):
             t = json.load(fp)
         traffic, traffic_src = t.get("dram_bytes_per_launch"), t.get("source")
     n_tc = sum(1 for p in prof if p[4] == 2)
+
+    def conv_bytes(key):
+        """algorithmic bytes of one conv launch: input + output + kernel, each moved once (fp32)"""
+        nd, batch, in_dims, cin, cout, ksize, stride, up = key[:8]      # a ninth entry = explicit padding (ResNet stem)
+        n_in = n_out = batch
+        for d_ in in_dims:
+            n_in *= d_
+            n_out *= -(-(d_ * up) // stride)
+        kvol = 1
+        for k_ in ksize:
+            kvol *= k_
+        return 4.0 * (n_in * cin + n_out * cout + kvol * cin * cout)
+    tc_bytes = sum(conv_bytes(p[5]) for p in prof if p[4] == 2)
     tf32 = None
     ppath = os.path.join(ROOT, "profiles", "tf32_mma_peak.json")        # measured by scripts/gpu_probe_round2.py (MMA-only loop)
     if os.path.exists(ppath):
@@ -490,8 +503,13 @@ def run_b200(args):
             tf32 = json.load(fp)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": achieved / tensor_peak, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": how + " cuBLAS bf16 dense (sustained); kind::tf32 issues at half that rate and every fp32 product "
-                               "takes 3 tf32 MMAs (3xTF32), so frac <= 1/6 on executed FLOPs",
+                "traffic_algorithmic": tc_bytes / max(n_tc, 1),
+                "traffic_note": "algorithmic bytes per launch = fp32 input + output + kernel of the layer, each once; the ncu "
+                                "figure is below it because the tail of every output is still in the 126 MB L2 when its kernel ends",
+                "peak_source": how + " cuBLAS bf16 dense (sustained) - the contract's denominator.  The measured kind::tf32 "
+                               "issue peak is in tf32_mma_peak: 1116 TFLOP/s with 256-column tiles, 934 with the 128-column tiles "
+                               "of this kernel (75 clk per MMA for any N <= 128); every fp32 product takes 3 tf32 MMAs (3xTF32), "
+                               "so the ceiling on executed FLOPs is 311 TFLOP/s = 0.23 of this peak",
                 "tf32_mma_peak": tf32,
                 "kernel": "igemm_tc_pixel_kernel<B_MN,WG> (tcgen05 kind::tf32 fwd/dgrad/wgrad, 3 MMAs per product)",
                 "algorithmic_gflop_per_launch": tc_flops / max(n_tc, 1) / 1e9,
