@@ -8,7 +8,11 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("CN_LIB") or os.path.join(_HERE, "lib", "libconfignet_b200.so")     # CN_LIB: an experimental build (A/B runs)
+# The product library carries no test hooks.  CN_TEST_HOOKS=1 loads the hooks build of the same sources (cn_debug_* entry
+# points, in-kernel role timers) for the measurement scripts; CN_LIB names an experimental build (A/B runs).
+HOOKS_LIB_PATH = os.path.join(_HERE, "lib", "libconfignet_b200_hooks.so")
+LIB_PATH = os.environ.get("CN_LIB") or (HOOKS_LIB_PATH if os.environ.get("CN_TEST_HOOKS") == "1" else
+                                        os.path.join(_HERE, "lib", "libconfignet_b200.so"))
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 
@@ -121,24 +125,30 @@ def load():
         if not hasattr(lib, name) and os.environ.get("CN_ALLOW_PARTIAL") == "1":
             continue
         getattr(lib, name).restype = restype
-    if os.environ.get("CN_CHUNK_KB"):          # measurement knob: k-blocks per tensor-core accumulation chunk
-        lib.cn_debug_set_chunk(int(os.environ["CN_CHUNK_KB"]))
+    # measurement knobs of the hooks build (ignored - loudly - by the product library, which has no cn_debug_* symbols)
+    knobs = [("CN_CHUNK_KB", "cn_debug_set_chunk"), ("CN_PERSISTENT", "cn_debug_set_persistent"), ("CN_WCACHE", "cn_debug_set_wcache"),
+             ("CN_COAL", "cn_debug_set_coal"), ("CN_DBG", "cn_debug_set"), ("CN_CLUSTER", "cn_debug_set_cluster")]
+    for env, sym in knobs:
+        if os.environ.get(env):
+            if not hasattr(lib, sym):
+                raise CnError("%s needs the hooks build: set CN_TEST_HOOKS=1 (%s is not in the product library)" % (env, sym))
+            getattr(lib, sym)(int(os.environ[env]))
     if os.environ.get("CN_FOLD"):               # "fold,s2all" e.g. "0,1": folded upsample+conv plans / merged stride-2 dgrad phases
+        if not hasattr(lib, "cn_debug_set_fold"):
+            raise CnError("CN_FOLD needs the hooks build: set CN_TEST_HOOKS=1")
         a, b = (os.environ["CN_FOLD"].split(",") + ["1"])[:2]
         lib.cn_debug_set_fold(int(a), int(b))
-    if os.environ.get("CN_PERSISTENT"):
-        lib.cn_debug_set_persistent(int(os.environ["CN_PERSISTENT"]))
-    if os.environ.get("CN_WCACHE"):
-        lib.cn_debug_set_wcache(int(os.environ["CN_WCACHE"]))
-    if os.environ.get("CN_COAL"):              # measurement knob: channel-major epilogue pass 0 never / 1 rule / 2 always
-        lib.cn_debug_set_coal(int(os.environ["CN_COAL"]))
-    if os.environ.get("CN_C3K"):               # measurement knob: 0 = first-generation c3 kernels (weights in shared memory)
-        lib.cn_debug_set_c3k(int(os.environ["CN_C3K"]))
-    if os.environ.get("CN_DBG"):               # measurement knob: cn_debug_set bits (32 = thread-per-row epilogue stores)
-        lib.cn_debug_set(int(os.environ["CN_DBG"]))
-    if os.environ.get("CN_CLUSTER"):
-        lib.cn_debug_set_cluster(int(os.environ["CN_CLUSTER"]))
     _lib = lib
+    return lib
+
+
+def load_hooks():
+    """The hooks build of the library as a SEPARATE handle (tests of the host-evaluated plan geometry, cn_debug_conv_host):
+    it shares no state with the product library the ops go through."""
+    if not os.path.exists(HOOKS_LIB_PATH):
+        raise CnError("libconfignet_b200_hooks.so not built (%s); run __graft_entry__.build()" % HOOKS_LIB_PATH)
+    lib = ctypes.CDLL(HOOKS_LIB_PATH)
+    lib.cn_debug_conv_host.restype = ctypes.c_int
     return lib
 
 

@@ -2016,16 +2016,24 @@ static inline void sum_slabs(const float* part, int nslabs, int n, float* out, c
 // ------------------------------------------------------------------------------------------------
 static int g_cluster = 1;   // CTAs per cluster in the tcgen05 pixel kernel (cn_debug_set_cluster: 1, 2 or 4); measured per layer in
                             // profiles/r01_cluster_ab_v5.txt: sharing the weight stream by multicast no longer pays (c2/c1 = 1.00..1.06)
+#ifdef CN_TEST_HOOKS
 extern "C" int cn_debug_set_cluster(int v) { g_cluster = (v == 4 || v == 2) ? v : 1; return CN_OK; }
+#endif
 static long long* g_prof = nullptr;   // TEST HOOK: device buffer (16 x int64) receiving CTA 0's role timings
+#ifdef CN_TEST_HOOKS
 extern "C" int cn_debug_set_prof(void* p) { g_prof = (long long*)p; return CN_OK; }
+#endif
 static int g_dbg = 0;   // TEST HOOK (cn_debug_set): bit 0/1 skip A/B global loads, bit 2 skip MMA issue, bit 3 skip STS
+#ifdef CN_TEST_HOOKS
 extern "C" int cn_debug_set(int v) { g_dbg = v; return CN_OK; }
+#endif
 // how a finished tile leaves the tcgen05 kernel (cn_debug_set_coal): 0 = every thread stores its row, 1 = channel-major
 // pass by rule (launch_tc), 2 = channel-major pass always, 3 (default) = TMA tensor store from shared memory wherever the
 // output rows are consecutive and the launch does not split K, else as 1
 static int g_coal = 3;
+#ifdef CN_TEST_HOOKS
 extern "C" int cn_debug_set_coal(int v) { g_coal = v; return CN_OK; }
+#endif
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -2076,12 +2084,18 @@ static bool make_out_map_phased(CUtensorMap* map, float* dst, const GemmPlan& g)
 // TMA tensor stores for 2-D stride-2 phase plans too (environment CN_TMA_PHASED=0 switches them off for A/B runs)
 static int g_tma_phased = [] { const char* e = getenv("CN_TMA_PHASED"); return e ? atoi(e) : 1; }();
 static int g_persistent = 1;   // persistent CTAs in the tcgen05 pixel kernel (cn_debug_set_persistent)
+#ifdef CN_TEST_HOOKS
 extern "C" int cn_debug_set_persistent(int v) { g_persistent = v; return CN_OK; }
+#endif
 static int g_fold = 1;     // folded upsample+conv plans (cn_debug_set_fold)
 static int g_s2all = 1;    // all parity phases of a stride-2 dgrad in one launch
+#ifdef CN_TEST_HOOKS
 extern "C" int cn_debug_set_fold(int fold, int s2all) { g_fold = fold; g_s2all = s2all; return CN_OK; }
+#endif
 static int g_chunk_kb = 0;   // k-blocks per tensor-core accumulation chunk (0 = TC_CHUNK_KB); cn_debug_set_chunk
+#ifdef CN_TEST_HOOKS
 extern "C" int cn_debug_set_chunk(int v) { g_chunk_kb = (v >= 1 && v <= 64) ? v : 0; return CN_OK; }
+#endif
 static thread_local int g_last_impl = 0;     // 1 = CUDA-core, 2 = tcgen05: what the last conv call on this thread ran
 extern "C" int cn_last_conv_impl(void) { return g_last_impl; }
 static int g_num_sms = 0;
@@ -2210,7 +2224,9 @@ static bool is_registered_param(const void* w) {
   return find_range_locked(w) != nullptr;
 }
 static bool g_wcache_on = true;
+#ifdef CN_TEST_HOOKS
 extern "C" int cn_debug_set_wcache(int on) { g_wcache_on = on != 0; return CN_OK; }
+#endif
 static unsigned long long capture_id_of(cudaStream_t st) {
   cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
   unsigned long long id = 0;
@@ -2373,7 +2389,11 @@ static int launch_tc(const GemmPlan& g, const float* src, const float* packed, c
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  auto kern = g_prof ? igemm_tc_pixel_kernel<B_MN, WG, 1> : igemm_tc_pixel_kernel<B_MN, WG, 0>;
+#ifdef CN_TEST_HOOKS
+  auto kern = g_prof ? igemm_tc_pixel_kernel<B_MN, WG, 1> : igemm_tc_pixel_kernel<B_MN, WG, 0>;   // role timers: hooks build only
+#else
+  auto kern = igemm_tc_pixel_kernel<B_MN, WG, 0>;
+#endif
   if (set_smem(kern, smem)) return CN_ERR_CUDA;
   CN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, g, src, packed, bias, dst, act, alpha, bn, bn_smem,
                                    nb, 512, per, (long long)(split > 1 ? part_stride : 0), csize, ny,
@@ -2753,6 +2773,7 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
   return CN_OK;
 }
 
+#ifdef CN_TEST_HOOKS
 // ------------------------------------------------------------------------------------------------
 // Host evaluation of a plan with scalar loops.  TEST HOOK ONLY (tests/test_plan_host.py): lets the
 // CPU-only test suite check the integer geometry (SAME padding, phases, fused upsample, tap tables)
@@ -2870,3 +2891,4 @@ extern "C" int cn_debug_conv_host(const cn_conv_desc* d, int kind, const float* 
   }
   return CN_OK;
 }
+#endif  // CN_TEST_HOOKS

@@ -1050,4 +1050,6 @@ int cn_skinny_wgrad(const cn_conv_desc* d, const float* x, const float* gy, floa
   return 0;
 }
 
+#ifdef CN_TEST_HOOKS
 extern "C" int cn_debug_set_c3k(int v) { g_c3k = v; return CN_OK; }
+#endif

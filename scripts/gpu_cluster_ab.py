@@ -3,6 +3,8 @@ tcgen05 (op, layer) of the bench step (keys read from a bench.py --breakdown tab
 import sys, os, re, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
+import os
+os.environ.setdefault("CN_TEST_HOOKS", "1")      # the cn_debug_* hooks live in libconfignet_b200_hooks.so only
 from confignet_b200 import _lib as L
 lib = L.load(); dev = torch.device("cuda:0")
 st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -4,6 +4,8 @@ Not a bench number: used to find which part of a kernel (gather / STS / MMA) bou
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
+import os
+os.environ.setdefault("CN_TEST_HOOKS", "1")      # the cn_debug_* hooks live in libconfignet_b200_hooks.so only
 from confignet_b200 import _lib as L
 
 lib = L.load()

@@ -33,8 +33,14 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), "symbol %s declared in the header but not exported" % name
     bound = set(L.SIGNATURES) | set(L.NO_STATUS)
-    assert declared <= bound | {"cn_debug_conv_host"}, declared - bound
+    assert declared <= bound, declared - bound
     assert lib.cn_version() >= 1
+    # the product library ships no test hook; the hooks build of the same sources carries them
+    assert not any(n.startswith("cn_debug") for n in declared)
+    import subprocess
+    exported = subprocess.run(["nm", "-D", "--defined-only", L.LIB_PATH], capture_output=True, text=True).stdout
+    assert "cn_debug" not in exported
+    assert hasattr(L.load_hooks(), "cn_debug_conv_host")
 
 
 def test_missing_cuda_fails_loudly():
@@ -56,8 +62,7 @@ def test_plan_geometry_matches_oracle(cfg):
     """TF SAME padding, stride-2 dgrad phases, fused upsample, tap tables: the host evaluation of the very
     plans the kernels consume must equal the oracle's conv / its autograd gradients."""
     from confignet_b200 import _lib as L
-    lib = L.load()
-    lib.cn_debug_conv_host.restype = ctypes.c_int
+    lib = L.load_hooks()          # cn_debug_conv_host lives in the hooks build only
     nd, B, dims, cin, cout, k, s, up = cfg
     rng = np.random.RandomState(0)
     d = L.make_conv_desc(nd, B, dims, cin, cout, [k] * nd, s, up)
@@ -91,8 +96,7 @@ def test_folded_upsample_conv_plans_match_oracle(cfg):
     folded input-gradient plan and the folded weight gradient (+ unfold lists), evaluated on the host exactly as the
     kernels consume them, equal the oracle's upsample -> conv_same and its autograd gradients."""
     from confignet_b200 import _lib as L
-    lib = L.load()
-    lib.cn_debug_conv_host.restype = ctypes.c_int
+    lib = L.load_hooks()          # cn_debug_conv_host lives in the hooks build only
     nd, B, dims, cin, cout, k, s, up = cfg
     rng = np.random.RandomState(1)
     d = L.make_conv_desc(nd, B, dims, cin, cout, [k] * nd, s, up)
@@ -119,8 +123,7 @@ def test_folded_upsample_conv_plans_match_oracle(cfg):
 def test_stride2_dgrad_single_phased_plan(cfg):
     """All parity phases of the stride-2 input gradient as ONE phased plan (the discriminator blocks' dgrad)."""
     from confignet_b200 import _lib as L
-    lib = L.load()
-    lib.cn_debug_conv_host.restype = ctypes.c_int
+    lib = L.load_hooks()          # cn_debug_conv_host lives in the hooks build only
     nd, B, dims, cin, cout, k, s, up = cfg
     rng = np.random.RandomState(2)
     d = L.make_conv_desc(nd, B, dims, cin, cout, [k] * nd, s, up)

@@ -23,8 +23,7 @@ def test_plan_geometry_explicit_padding(cfg):
     """ZeroPadding2D(p) + VALID conv (keras-applications ResNet50 stem): forward, dgrad and wgrad plans evaluated on
     the host equal the oracle's conv / its autograd gradients."""
     from confignet_b200 import _lib as L
-    lib = L.load()
-    lib.cn_debug_conv_host.restype = ctypes.c_int
+    lib = L.load_hooks()          # cn_debug_conv_host lives in the hooks build only
     B, dims, cin, cout, k, s, pad = cfg
     rng = np.random.RandomState(1)
     d = L.make_conv_desc(2, B, dims, cin, cout, [k, k], s, 1, pad)
