@@ -69,6 +69,7 @@ SIGNATURES = {
     "cn_norm_coef": [_I, _V, _I, _V, _V, _I, _I, _I, _f, _V, _V, _V, _V, _V],
     "cn_lrelu_fwd": [_V, _f, _V, _L, _V],
     "cn_act_bwd": [_V, _V, _I, _f, _V, _L, _V],
+    "cn_act_bwd_sqdiff": [_V, _V, _V, _V, _f, _I, _f, _V, _L, _V],
     "cn_axpby": [_V, _V, _f, _f, _V, _L, _V],
     "cn_maxpool2_fwd": [_V, _I, _I, _I, _I, _V, _V],
     "cn_maxpool2_bwd": [_V, _V, _V, _I, _I, _I, _I, _V, _V],

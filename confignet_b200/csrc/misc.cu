@@ -66,6 +66,54 @@ act_bwd_vec_kernel(const float4* __restrict__ gy, const float4* __restrict__ ref
     gx[i] = make_float4(one(r.x, g.x), one(r.y, g.y), one(r.z, g.z), one(r.w, g.w));
   }
 }
+// Activation backward with a squared-difference loss tapped on the activation (perceptual loss, perceptual_loss.py:61-82:
+// loss_l = mean((y - t)^2) on a VGG activation y that also feeds the next layer):
+//   gx = (gy + (2 (y - t)) * (gloss[0] * k)) * act'(y)        gy may be NULL (the deepest tapped layer)
+// - the loss gradient, its accumulation onto the gradient from the next layer and the activation derivative in ONE pass
+// (3 reads + 1 write) instead of reduce_bwd + an add by the autograd engine + act_bwd (9 tensor passes), same arithmetic.
+__global__ void __launch_bounds__(256)
+act_bwd_sqdiff_kernel(const float4* __restrict__ gy, const float4* __restrict__ y, const float4* __restrict__ t,
+                      const float* __restrict__ gloss, float k, int act, float alpha, float4* __restrict__ gx, size_t n4) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const float gs = gloss[0] * k;
+  auto one = [&](float g, float r, float tv) {
+    g += (2.f * (r - tv)) * gs;
+    if (act == CN_ACT_LRELU) g *= (r > 0.f ? 1.f : alpha);
+    else if (act == CN_ACT_RELU) g = r > 0.f ? g : 0.f;
+    else if (act == CN_ACT_TANH) g *= (1.f - r * r);
+    return g;
+  };
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 r[4], tv[4], g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      r[u] = cn_ldg4_ordered(reinterpret_cast<const float*>(y + i + u * stride));
+      tv[u] = cn_ldg4_ordered(reinterpret_cast<const float*>(t + i + u * stride));
+      g[u] = gy ? cn_ldg4_ordered(reinterpret_cast<const float*>(gy + i + u * stride)) : z4;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      gx[i + u * stride] = make_float4(one(g[u].x, r[u].x, tv[u].x), one(g[u].y, r[u].y, tv[u].y), one(g[u].z, r[u].z, tv[u].z),
+                                       one(g[u].w, r[u].w, tv[u].w));
+  }
+  for (; i < n4; i += stride) {
+    const float4 r = y[i], tv = t[i], g = gy ? gy[i] : z4;
+    gx[i] = make_float4(one(g.x, r.x, tv.x), one(g.y, r.y, tv.y), one(g.z, r.z, tv.z), one(g.w, r.w, tv.w));
+  }
+}
+extern "C" int cn_act_bwd_sqdiff(const float* gy, const float* y, const float* t, const float* gloss, float k, int act,
+                                 float alpha, float* gx, int64_t n, void* stream) {
+  CN_REQUIRE(y && t && gloss && gx && n > 0, CN_ERR_BAD_SHAPE, "cn_act_bwd_sqdiff: bad arguments");
+  CN_REQUIRE((n & 3) == 0 && (((uintptr_t)gy | (uintptr_t)y | (uintptr_t)t | (uintptr_t)gx) & 15) == 0, CN_ERR_BAD_ALIGN,
+             "cn_act_bwd_sqdiff: tensors must be 16-byte aligned with a multiple of 4 elements");
+  const size_t n4 = (size_t)n / 4;
+  size_t blocks = (n4 + 1023) / 1024; if (blocks > 8 * 148) blocks = 8 * 148; if (blocks < 1) blocks = 1;
+  act_bwd_sqdiff_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)gy, (const float4*)y, (const float4*)t, gloss, k,
+                                                                           act, alpha, (float4*)gx, n4);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
 extern "C" int cn_act_bwd(const float* gy, const float* y, int act, float alpha, float* gx, int64_t n, void* stream) {
   if (n <= 0) return CN_OK;
   if ((n & 3) == 0 && n >= 4096 && (((uintptr_t)gy | (uintptr_t)y | (uintptr_t)gx) & 15) == 0) {

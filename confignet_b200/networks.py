@@ -182,10 +182,38 @@ def vggface_activations(p, img):
     return _vgg_activations(p, img, VGG16_LAYERS, VGG16_USED_LAYER_IDXS, True)
 
 
+def _vgg_tapped_loss(p, img, targets, layers, used, face):
+    """The VGG pass of the side that carries the gradient, every used layer tapped by its squared-difference term against
+    the other side's activation (ops.conv_act_sqdiff: loss gradient + accumulation + ReLU derivative in one pass)."""
+    x = ops.vgg_preprocess(img, face=face)
+    total, j = None, 0
+    for idx, layer in enumerate(layers, start=1):
+        if layer[0] == "conv":
+            w, b = p[layer[1] + "/kernel"], p[layer[1] + "/bias"]
+            if idx in used:
+                t = targets[j]; j += 1
+                x, term = ops.conv_act_sqdiff(x, w, b, t, 1.0 / t.numel())
+                total = term if total is None else total + term
+            else:
+                x = ops.conv_act(x, w, b, act=L.ACT_RELU)
+        else:
+            x = ops.maxpool2(x)
+    return total
+
+
 def perceptual_loss(p_vgg, predicted, data, model_type="imagenet"):
     """PerceptualLoss.loss: sum over the 4 layers of the batch-wide MSE.  Gradient flows to both arguments
     that require it (in ConfigNet only one of them does).  model_type "imagenet" = VGG19, "VGGFace" = VGG16."""
     fwd = vgg19_activations if model_type == "imagenet" else vggface_activations
+    layers, used, face = ((VGG19_LAYERS, VGG19_USED_LAYER_IDXS, False) if model_type == "imagenet"
+                          else (VGG16_LAYERS, VGG16_USED_LAYER_IDXS, True))
+    if predicted.requires_grad != data.requires_grad and torch.is_grad_enabled():
+        # ConfigNet's case: one side is a constant.  Its activations first, then the other side with tapped layers.
+        live, const = (predicted, data) if predicted.requires_grad else (data, predicted)
+        with torch.no_grad():
+            targets = fwd(p_vgg, const)
+        if all(layers[i - 1][0] == "conv" for i in used) and all(t.numel() % 4 == 0 for t in targets):
+            return _vgg_tapped_loss(p_vgg, live, targets, layers, used, face)
 
     def acts(t):
         if t.requires_grad:

@@ -241,6 +241,52 @@ class ConvActFwd(torch.autograd.Function):
         return gx, gw, gb, None, None, None, None
 
 
+class ConvActSqdiff(torch.autograd.Function):
+    """y = act(conv_same(x, w) + bias) AND loss = scale * sum((y - target)^2) as one node (a tapped VGG layer of the
+    perceptual loss, perceptual_loss.py:61-82).  The backward folds the loss gradient, its accumulation onto the gradient
+    coming from the next layer and the activation derivative into ONE pass (cn_act_bwd_sqdiff) - separately they are
+    reduce_bwd + an add by the autograd engine + act_bwd, 9 tensor passes instead of 4 - with the same arithmetic, so the
+    gradients are bit-identical to the unfused graph.  First order only (the VGG path is never differentiated twice)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, g, act, alpha, target, scale):
+        x, w, bias, target = _chk(x), _chk(w), _chk(bias), _chk(target)
+        y = _conv_fwd_raw(g, x, w, bias, act, alpha)
+        res = torch.empty(1, device=x.device, dtype=torch.float32)
+        L.call("cn_reduce", _p(y), _p(target), None, 1, y.numel(), RED_SQDIFF, 1.0, scale, _p(_ws(x.device)), _p(res), _stream())
+        ctx.g, ctx.act, ctx.alpha, ctx.scale = g, act, alpha, scale
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, w, y, target)
+        ctx.set_materialize_grads(False)
+        return y, res
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy, gres):
+        x, w, y, target = ctx.saved_tensors
+        g = ctx.g
+        if gy is None and gres is None:
+            return (None,) * 8
+        gpre = torch.empty_like(y)
+        if gres is None:
+            L.call("cn_act_bwd", _p(_chk(gy)), _p(y), ctx.act, ctx.alpha, _p(gpre), y.numel(), _stream())
+        else:
+            L.call("cn_act_bwd_sqdiff", _p(_chk(gy)), _p(y), _p(target), _p(_chk(gres)), ctx.scale, ctx.act, ctx.alpha, _p(gpre),
+                   y.numel(), _stream())
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = _conv_dgrad_raw(g, gpre, w)
+        if _want_param_grads() and (ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])):
+            gw, gb = _conv_wgrad_raw(g, x, gpre, ctx.has_bias)
+        return gx, gw, gb, None, None, None, None, None
+
+
+def conv_act_sqdiff(x, w, bias, target, scale, act=L.ACT_RELU, alpha=0.0):
+    """(activation, scale * sum((activation - target)^2)); needs numel % 4 == 0 (every VGG activation)."""
+    g = ConvGeom.get(x.shape, w.shape, 1, 1, -1)
+    return ConvActSqdiff.apply(x, w, bias, g, act, alpha, target, scale)
+
+
 def conv_act(x, w, bias=None, stride=1, upsample=1, act=L.ACT_NONE, alpha=0.0, grad_is_preact=False, pad=-1):
     """pad = -1: TF "SAME"; pad >= 0: ZeroPadding(pad) + "VALID" (ResNet50 stem)."""
     g = ConvGeom.get(x.shape, w.shape, stride, upsample, pad)

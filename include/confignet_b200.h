@@ -137,6 +137,12 @@ int cn_norm_coef(int kind, const float* sums, int nsplit, const float* p0, const
 int cn_lrelu_fwd(const float* x, float alpha, float* y, int64_t n, void* stream);
 /* gx = gy * act'(ref): lrelu (ref = pre- or post-activation), relu (ref = y), tanh (ref = y: 1-y^2) */
 int cn_act_bwd(const float* gy, const float* ref, int act, float alpha, float* gx, int64_t n, void* stream);
+/* gx = (gy + 2 (y - t) * gloss[0] * k) * act'(y): the activation backward of a layer whose output y is also tapped by a
+ * squared-difference loss against t (PerceptualLoss._loss_terms, perceptual_loss.py:61-82); gloss = device scalar (the loss
+ * cotangent), gy = gradient from the next layer or NULL.  Replaces SquaredDifference/Mean gradients + AddN + ReluGrad.
+ * n % 4 == 0, 16-byte aligned tensors. */
+int cn_act_bwd_sqdiff(const float* gy, const float* y, const float* t, const float* gloss, float k, int act,
+                      float alpha, float* gx, int64_t n, void* stream);
 /* out = a*x + b*y (y may be NULL) */
 int cn_axpby(const float* x, const float* y, float a, float b, float* out, int64_t n, void* stream);
 

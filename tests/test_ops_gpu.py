@@ -183,6 +183,34 @@ def test_discr_norm_fused_node_all_orders(dev, shape):
     assert torch.equal(only_y, ga) and torch.equal(only_s, gb)
 
 
+def test_conv_act_sqdiff_tapped_layer_equals_unfused_graph(dev):
+    """ops.conv_act_sqdiff (a tapped VGG layer of the perceptual loss, perceptual_loss.py:61-82): activation, loss term and
+    the input gradient - with and without a gradient arriving from the next layer - equal the unfused graph
+    (conv_act -> reduce_sum + next layer) bit for bit, and the oracle within the operator tolerance."""
+    from confignet_b200 import ops, _lib as L
+    torch.manual_seed(21)
+    x = torch.randn(2, 12, 10, 8); w = torch.randn(3, 3, 8, 16) * 0.2; b = torch.randn(16) * 0.1
+    t = torch.randn(2, 12, 10, 16).abs(); gnext = torch.randn(2, 12, 10, 16); gl = torch.tensor([0.7])
+    scale = 1.0 / t.numel()
+    xr = x.double().requires_grad_(True)
+    yr = torch.relu(O.conv_same(xr, w.double(), b.double(), 1))
+    lr = ((yr - t.double()) ** 2).sum() * scale
+    for with_next in (True, False):
+        ref, = torch.autograd.grad((yr, lr) if with_next else (lr,), xr,
+                                   (gnext.double(), gl.double()[0]) if with_next else (gl.double()[0],), retain_graph=True)
+        xa = x.to(dev).requires_grad_(True)
+        ya, la = ops.conv_act_sqdiff(xa, w.to(dev), b.to(dev), t.to(dev), scale)
+        outs, cot = ((ya, la), (gnext.to(dev), gl.to(dev))) if with_next else ((la,), (gl.to(dev),))
+        ga, = torch.autograd.grad(outs, xa, cot)
+        xb = x.to(dev).requires_grad_(True)
+        yb = ops.conv_act(xb, w.to(dev), b.to(dev), act=L.ACT_RELU)
+        lb = ops.reduce_sum(yb, ops.RED_SQDIFF, y=t.to(dev), scale=scale)
+        outs, cot = ((yb, lb), (gnext.to(dev), gl.to(dev))) if with_next else ((lb,), (gl.to(dev),))
+        gb, = torch.autograd.grad(outs, xb, cot)
+        assert torch.equal(ya, yb) and torch.equal(la, lb) and torch.equal(ga, gb)
+        assert nerr(ya, yr) <= TOL_TC and nerr(la, lr) <= TOL_TC and nerr(ga, ref) <= TOL_TC
+
+
 @pytest.mark.parametrize("n,ch,side", [(3, 8, 4), (16, 128, 6), (5, 512, 3)])
 def test_adain(dev, n, ch, side):
     from confignet_b200 import ops
