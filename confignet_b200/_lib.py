@@ -57,6 +57,7 @@ SIGNATURES = {
     "cn_conv_dgrad": [_D, _V, _V, _V, _I, _V],
     "cn_conv_wgrad": [_D, _V, _V, _V, _V, _I, _V],
     "cn_chan_sums": [_V, _V, _V, _I, _I, _I, _I, _f, _V, _V],
+    "cn_chan_sums_dual": [_V, _I, _I, _I, _f, _V, _V, _V],
     "cn_chan_affine": [_V, _V, _V, _V, _I, _I, _I, _I, _f, _V, _V],
     "cn_chan_affine2": [_V, _V, _V, _V, _V, _I, _I, _I, _I, _f, _V, _V],
     "cn_chan_sums_splits": [_I, _I, _I],

@@ -77,7 +77,7 @@ act_bwd_sqdiff_kernel(const float4* __restrict__ gy, const float4* __restrict__ 
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const float gs = gloss[0] * k;
   auto one = [&](float g, float r, float tv) {
-    g += (2.f * (r - tv)) * gs;
+    g = __fadd_rn(g, __fmul_rn(2.f * (r - tv), gs));      // two roundings, as the separate kernels + add do (no FMA contraction)
     if (act == CN_ACT_LRELU) g *= (r > 0.f ? 1.f : alpha);
     else if (act == CN_ACT_RELU) g = r > 0.f ? g : 0.f;
     else if (act == CN_ACT_TANH) g *= (1.f - r * r);

@@ -126,6 +126,58 @@ chan_sums4_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
   }
 }
 
+// One pass over a for BOTH statistics a DiscrBlock needs of its conv output (building_blocks.py:100-106): the raw sums
+// (get_layer_style) into sums_raw and the sums of lrelu(a) (InstanceNormalization after LeakyReLU) into sums_act, records
+// laid out as by chan_sums4_kernel<1> (j = 0: sum, j = 3: sum of squares).  Same thread mapping, eight pixels in flight.
+__global__ void __launch_bounds__(256)
+chan_sums4_dual_kernel(const float* __restrict__ a, int p, int ch, float alpha, float* __restrict__ sums_act,
+                       float* __restrict__ sums_raw) {
+  extern __shared__ __align__(16) float red[];   // [R][chq][4][4]: act sum, act squares, raw sum, raw squares
+  const int chq = ch >> 2, R = 256 / chq;
+  const int tid = threadIdx.x, q = tid % chq, rr = tid / chq;
+  const int n = blockIdx.x;
+  const int per = (p + gridDim.y - 1) / gridDim.y;
+  const int pbeg = blockIdx.y * per, pend = min(p, pbeg + per);
+  float s[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s[j][e] = 0.f;
+  if (rr < R) {
+    const size_t base = (size_t)n * p * ch + 4 * q;
+    auto add = [&](const float4& a4) {
+      const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float av = lrelu_f(ar[e], alpha);
+        s[0][e] += av; s[1][e] += av * av;
+        s[2][e] += ar[e]; s[3][e] += ar[e] * ar[e];
+      }
+    };
+    constexpr int U = 8;
+    int r = pbeg + rr;
+    for (; r + (U - 1) * R < pend; r += U * R) {
+      float4 A[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) A[u] = cn_ldg4_ordered(a + base + (size_t)(r + u * R) * ch);
+#pragma unroll
+      for (int u = 0; u < U; ++u) add(A[u]);
+    }
+    for (; r < pend; r += R) add(cn_ldg4_ordered(a + base + (size_t)r * ch));
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(red + ((size_t)(rr * chq + q) * 4 + j) * 4) = make_float4(s[j][0], s[j][1], s[j][2], s[j][3]);
+  }
+  __syncthreads();
+  for (int o = tid; o < ch * 4; o += 256) {
+    const int cc = o >> 2, j = o & 3, qq = cc >> 2, e = cc & 3;
+    float t = 0.f;
+    for (int k = 0; k < R; ++k) t += red[((size_t)(k * chq + qq) * 4 + j) * 4 + e];
+    float* dst = (j < 2 ? sums_act : sums_raw) + (((size_t)blockIdx.y * gridDim.x + n) * ch + cc) * CN_SUMS_LD;
+    dst[(j & 1) ? 3 : 0] = t;
+  }
+}
+
 extern "C" int cn_chan_sums_splits(int n, int p, int ch) {
   if (n <= 0 || p <= 0 || ch <= 0) return 1;
   int cb = (ch + 31) / 32;
@@ -166,6 +218,20 @@ extern "C" int cn_chan_sums(const float* a, const float* b, const float* c, int 
   if (c) chan_sums_kernel<3><<<grid, block, 0, st>>>(a, b, c, p, ch, flags, alpha, sums);
   else if (b) chan_sums_kernel<2><<<grid, block, 0, st>>>(a, b, c, p, ch, flags, alpha, sums);
   else chan_sums_kernel<1><<<grid, block, 0, st>>>(a, b, c, p, ch, flags, alpha, sums);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
+// sums of lrelu(a, alpha) into sums_act and of a itself into sums_raw in one pass (records as cn_chan_sums writes them for
+// one operand; the j = 1, 2, 4, 5, 6 entries are left untouched - the one-operand closed forms do not read them).
+// CN_ERR_UNSUPPORTED when ch % 4 != 0 or ch > 1024: the caller then runs two cn_chan_sums passes.
+extern "C" int cn_chan_sums_dual(const float* a, int n, int p, int ch, float alpha, float* sums_act, float* sums_raw, void* stream) {
+  CN_REQUIRE(a && sums_act && sums_raw && n > 0 && p > 0 && ch > 0, CN_ERR_BAD_SHAPE, "cn_chan_sums_dual: bad arguments");
+  CN_REQUIRE(ch % 4 == 0 && ch <= 1024, CN_ERR_UNSUPPORTED, "cn_chan_sums_dual: channel count needs the two-pass form");
+  const int psplit = cn_chan_sums_splits(n, p, ch);
+  const int chq = ch / 4, R = 256 / chq;
+  const int smem = R * ch * 4 * (int)sizeof(float);
+  chan_sums4_dual_kernel<<<dim3(n, psplit), 256, smem, (cudaStream_t)stream>>>(a, p, ch, alpha, sums_act, sums_raw);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

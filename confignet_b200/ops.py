@@ -319,6 +319,21 @@ def _sums(a, b=None, c=None, flags=0, alpha=0.0):
     return s
 
 
+def _sums_dual(a, alpha):
+    """(sums of lrelu(a), sums of a) in one pass over a (cn_chan_sums_dual); two passes where the one-pass kernel does not
+    take the channel count.  Same records, bit for bit, as _sums(a, flags=FLAG_LRELU_A) and _sums(a)."""
+    n, p, ch = _npc(a)
+    if ch % 4 != 0 or ch > 1024:
+        return _sums(a, flags=FLAG_LRELU_A, alpha=alpha), _sums(a)
+    ns = _SPLITS.get((n, p, ch))
+    if ns is None:
+        ns = _SPLITS[(n, p, ch)] = int(L.load().cn_chan_sums_splits(n, p, ch))
+    s_act = torch.empty((ns, n, ch, 8), device=a.device, dtype=torch.float32)
+    s_raw = torch.empty((ns, n, ch, 8), device=a.device, dtype=torch.float32)
+    L.call("cn_chan_sums_dual", _p(a), n, p, ch, alpha, _p(s_act), _p(s_raw), _stream())
+    return s_act, s_raw
+
+
 def _affine(a, b, c, coef, flags=0, alpha=0.0):
     n, p, ch = _npc(a)
     out = torch.empty_like(a)
@@ -480,9 +495,8 @@ class DiscrNorm(torch.autograd.Function):
     def forward(ctx, c, gamma, beta, alpha):
         c, gamma, beta = _chk(c), _chk(gamma), _chk(beta)
         n, p, ch = _npc(c)
-        s_raw = _sums(c)
+        s, s_raw = _sums_dual(c, alpha)
         _, style, _ = _coef(COEF_STYLE_FWD, s_raw, None, None, n, ch, p, STYLE_EPS, 0, (n, 2 * ch))
-        s = _sums(c, flags=FLAG_LRELU_A, alpha=alpha)
         (coef,), _, _ = _coef(COEF_IN_FWD, s, gamma, beta, n, ch, p, IN_EPS)
         ctx.alpha = alpha
         ctx.save_for_backward(c, gamma, s_raw)

@@ -112,6 +112,10 @@ int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float* gy, float*
 int cn_chan_sums_splits(int n, int p, int ch);
 int cn_chan_sums(const float* a, const float* b, const float* c, int n, int p, int ch,
                  int flags, float alpha, float* sums, void* stream);
+/* one pass for the two one-operand statistics of a DiscrBlock's conv output (building_blocks.py:100-106): sums of
+ * lrelu(a, alpha) -> sums_act (InstanceNormalization after LeakyReLU), sums of a -> sums_raw (get_layer_style); both buffers
+ * as for cn_chan_sums, only j = 0 and j = 3 are written.  CN_ERR_UNSUPPORTED when ch % 4 != 0 or ch > 1024. */
+int cn_chan_sums_dual(const float* a, int n, int p, int ch, float alpha, float* sums_act, float* sums_raw, void* stream);
 /* out = ka[n,ch]*a + kb[n,ch]*b + kc[n,ch]*c + k0[n,ch]; coef is (n, ch, 4) = (ka,kb,kc,k0). */
 int cn_chan_affine(const float* a, const float* b, const float* c, const float* coef,
                    int n, int p, int ch, int flags, float alpha, float* out, void* stream);
