@@ -60,6 +60,7 @@ SIGNATURES = {
     "cn_chan_sums_dual": [_V, _I, _I, _I, _f, _V, _V, _V],
     "cn_chan_affine": [_V, _V, _V, _V, _I, _I, _I, _I, _f, _V, _V],
     "cn_chan_affine2": [_V, _V, _V, _V, _V, _I, _I, _I, _I, _f, _V, _V],
+    "cn_chan_affine_pair": [_V, _V, _V, _V, _V, _I, _I, _I, _f, _V, _V, _V],
     "cn_chan_sums_splits": [_I, _I, _I],
     "cn_register_params": [_V, ctypes.c_size_t],
     "cn_unregister_params": [_V],

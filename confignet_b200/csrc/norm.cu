@@ -83,12 +83,12 @@ chan_sums4_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float av = (flags & CN_FLAG_LRELU_A) ? lrelu_f(ar[e], alpha) : ar[e];
-        s[0][e] += av; s[3][e] += av * av;
-        if (NT >= 2) { s[1][e] += bv[e]; s[4][e] += av * bv[e]; }
+        s[0][e] += av; s[3][e] = fmaf(av, av, s[3][e]);       // explicit FMAs: the dual kernel below must round identically
+        if (NT >= 2) { s[1][e] += bv[e]; s[4][e] = fmaf(av, bv[e], s[4][e]); }
         if (NT >= 3) {
           float cc = cv[e];
           if (flags & CN_FLAG_MASK_C) cc *= lrelu_d(ar[e], alpha);
-          s[2][e] += cc; s[5][e] += av * cc; s[6][e] += bv[e] * cc;
+          s[2][e] += cc; s[5][e] = fmaf(av, cc, s[5][e]); s[6][e] = fmaf(bv[e], cc, s[6][e]);
         }
       }
     };
@@ -150,8 +150,8 @@ chan_sums4_dual_kernel(const float* __restrict__ a, int p, int ch, float alpha, 
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float av = lrelu_f(ar[e], alpha);
-        s[0][e] += av; s[1][e] += av * av;
-        s[2][e] += ar[e]; s[3][e] += ar[e] * ar[e];
+        s[0][e] += av; s[1][e] = fmaf(av, av, s[1][e]);
+        s[2][e] += ar[e]; s[3][e] = fmaf(ar[e], ar[e], s[3][e]);
       }
     };
     constexpr int U = 8;
@@ -386,6 +386,75 @@ extern "C" int cn_chan_affine2(const float* a, const float* b, const float* c, c
   CN_REQUIRE(a && coef && coef2 && out && n > 0 && p > 0 && ch > 0, CN_ERR_BAD_SHAPE, "cn_chan_affine2: bad arguments");
   CN_REQUIRE(affine_rows_ok(n, ch), CN_ERR_UNSUPPORTED, "cn_chan_affine2: channel count needs the two-pass form");
   launch_affine_rows(a, b, c, coef, coef2, n, p, ch, flags, alpha, out, (cudaStream_t)stream);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
+// Two broadcast-affine results of the SAME three operands in one pass: the second-order terms of InstanceNorm(LeakyReLU(a))
+// (R1 penalty, losses.py:75-82) need, from (a, gy, h),
+//   out_a = (ka.x lrelu(a) + ka.y gy + ka.z h' + ka.w) * lrelu'(a)      (gradient wrt the conv output)
+//   out_g =  kg.x lrelu(a)            + kg.z h' + kg.w                   (gradient wrt the incoming gradient)
+// with h' = h * lrelu'(a): 3 reads + 2 writes instead of two passes (4 + 3 tensor moves).  Same arithmetic as two
+// cn_chan_affine calls with flags LRELU_A | MASK_C (| MASK_OUT for out_a).
+__global__ void __launch_bounds__(256)
+chan_affine_pair_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                        const float4* __restrict__ coef_a, const float4* __restrict__ coef_g, int p, int ch, float alpha,
+                        float* __restrict__ out_a, float* __restrict__ out_g) {
+  const int chq = ch >> 2, R = 256 / chq;
+  const int tid = threadIdx.x, q = tid % chq, rr = tid / chq;
+  if (rr >= R) return;
+  const int n = blockIdx.x;
+  const int per = (p + gridDim.y - 1) / gridDim.y;
+  const int pbeg = blockIdx.y * per, pend = min(p, pbeg + per);
+  float4 ka[4], kg[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { ka[e] = coef_a[(size_t)n * ch + 4 * q + e]; kg[e] = coef_g[(size_t)n * ch + 4 * q + e]; }
+  const size_t base = (size_t)n * p * ch + 4 * q;
+  auto one = [&](const float4& A, const float4& B, const float4& C, size_t i) {
+    const float ar[4] = {A.x, A.y, A.z, A.w}, br[4] = {B.x, B.y, B.z, B.w}, cr[4] = {C.x, C.y, C.z, C.w};
+    float oa[4], og[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float araw = ar[e], aa = lrelu_f(araw, alpha), d = lrelu_d(araw, alpha);
+      const float cc = cr[e] * d;
+      float v = fmaf(ka[e].x, aa, ka[e].w);
+      v = fmaf(ka[e].y, br[e], v);
+      v = fmaf(ka[e].z, cc, v);
+      oa[e] = v * d;
+      float g = fmaf(kg[e].x, aa, kg[e].w);
+      og[e] = fmaf(kg[e].z, cc, g);
+    }
+    *reinterpret_cast<float4*>(out_a + i) = make_float4(oa[0], oa[1], oa[2], oa[3]);
+    *reinterpret_cast<float4*>(out_g + i) = make_float4(og[0], og[1], og[2], og[3]);
+  };
+  constexpr int U = 4;
+  int r = pbeg + rr;
+  for (; r + (U - 1) * R < pend; r += U * R) {
+    float4 A[U], B[U], C[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = base + (size_t)(r + u * R) * ch;
+      A[u] = cn_ldg4_ordered(a + i); B[u] = cn_ldg4_ordered(b + i); C[u] = cn_ldg4_ordered(c + i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) one(A[u], B[u], C[u], base + (size_t)(r + u * R) * ch);
+  }
+  for (; r < pend; r += R) {
+    const size_t i = base + (size_t)r * ch;
+    one(cn_ldg4_ordered(a + i), cn_ldg4_ordered(b + i), cn_ldg4_ordered(c + i), i);
+  }
+}
+extern "C" int cn_chan_affine_pair(const float* a, const float* b, const float* c, const float* coef_a, const float* coef_g,
+                                   int n, int p, int ch, float alpha, float* out_a, float* out_g, void* stream) {
+  CN_REQUIRE(a && b && c && coef_a && coef_g && out_a && out_g && n > 0 && p > 0 && ch > 0, CN_ERR_BAD_SHAPE,
+             "cn_chan_affine_pair: bad arguments");
+  CN_REQUIRE(affine_rows_ok(n, ch), CN_ERR_UNSUPPORTED, "cn_chan_affine_pair: channel count needs the two-pass form");
+  const int R = 256 / (ch / 4);
+  int psplit = (8 * 148 + n - 1) / n;
+  int maxsplit = p / (2 * R); if (maxsplit < 1) maxsplit = 1;
+  if (psplit > maxsplit) psplit = maxsplit;
+  chan_affine_pair_kernel<<<dim3(n, psplit), 256, 0, (cudaStream_t)stream>>>(a, b, c, (const float4*)coef_a, (const float4*)coef_g, p, ch,
+                                                                             alpha, out_a, out_g);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

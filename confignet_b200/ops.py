@@ -10,6 +10,7 @@ There is no CPU implementation: tensors must live on a CUDA device.
 """
 import ctypes
 import contextlib
+import os
 import torch
 from . import _lib as L
 
@@ -364,8 +365,16 @@ def _in_bwd_bwd(c, gamma, gy, h, alpha, need_c, need_gy):
     fl = FLAG_LRELU_A | FLAG_MASK_C
     s = _sums(c, gy, h, flags=fl, alpha=alpha)
     (coef_a, coef_g), dgamma, _ = _coef(COEF_IN_BWDBWD, s, gamma, None, n, ch, p, IN_EPS, 2, (ch,))
-    d_c = _affine(c, gy, h, coef_a, fl | FLAG_MASK_OUT, alpha) if need_c else None
-    d_gy = _affine(c, None, h, coef_g, fl, alpha) if need_gy else None
+    d_c = d_gy = None
+    if need_c and need_gy and ch % 4 == 0 and ch <= 1024 and n <= 65535 and os.environ.get("CN_AFFINE_ROWS", "1") != "0":
+        # both results share (c, gy, h): one pass, 3 reads + 2 writes (same arithmetic as the two calls below)
+        d_c, d_gy = torch.empty_like(c), torch.empty_like(c)
+        L.call("cn_chan_affine_pair", _p(c), _p(gy), _p(h), _p(coef_a), _p(coef_g), n, p, ch, alpha, _p(d_c), _p(d_gy), _stream())
+    else:
+        if need_c:
+            d_c = _affine(c, gy, h, coef_a, fl | FLAG_MASK_OUT, alpha)
+        if need_gy:
+            d_gy = _affine(c, None, h, coef_g, fl, alpha)
     return d_c, (dgamma if _want_param_grads() else None), d_gy
 
 

@@ -124,6 +124,12 @@ int cn_chan_affine(const float* a, const float* b, const float* c, const float* 
  * passes and an add.  CN_ERR_UNSUPPORTED when ch % 4 != 0 or ch > 1024 (use two cn_chan_affine calls). */
 int cn_chan_affine2(const float* a, const float* b, const float* c, const float* coef, const float* coef2,
                     int n, int p, int ch, int flags, float alpha, float* out, void* stream);
+/* the two second-order results of InstanceNormalization(LeakyReLU(a)) that share the operands (a, gy = b, h = c) in one
+ * pass: out_a = cn_chan_affine(a, b, c, coef_a, LRELU_A | MASK_C | MASK_OUT), out_g = cn_chan_affine(a, NULL, c, coef_g,
+ * LRELU_A | MASK_C) (R1 penalty: the gradients wrt the conv output and wrt the incoming gradient, losses.py:75-82).
+ * CN_ERR_UNSUPPORTED when ch % 4 != 0 or ch > 1024. */
+int cn_chan_affine_pair(const float* a, const float* b, const float* c, const float* coef_a, const float* coef_g,
+                        int n, int p, int ch, float alpha, float* out_a, float* out_g, void* stream);
 /* closed-form coefficients from the 7 sums.  kind:
  *  0 IN fwd      p0=gamma p1=beta          -> coef0
  *  1 IN bwd      sums(a,gy) p0=gamma       -> coef0 (input grad), out0=dgamma[ch], out1=dbeta[ch]

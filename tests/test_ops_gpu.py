@@ -170,6 +170,11 @@ def test_discr_norm_fused_node_all_orders(dev, shape):
         assert nerr(a, b) <= TOL_FP32
     for a, b in zip(q2, g2):
         assert nerr(a, b) <= 5 * TOL_FP32
+    # the one-pass dual statistics write the same records as the two one-operand passes
+    s_act, s_raw = ops._sums_dual(cg.detach(), 0.3)
+    ref_act, ref_raw = ops._sums(cg.detach(), flags=ops.FLAG_LRELU_A, alpha=0.3), ops._sums(cg.detach())
+    for got, want, what in ((s_act, ref_act, "lrelu sums"), (s_raw, ref_raw, "raw sums")):
+        assert torch.equal(got[..., 0], want[..., 0]) and torch.equal(got[..., 3], want[..., 3]), what
     # the unfused nodes on the same inputs: same outputs, and gc(fused) == gc(InstanceNorm) + gc(style) exactly
     c2, g2_, b2 = [t.to(dev).requires_grad_(True) for t in (c, gam, bet)]
     y2 = ops.lrelu_instance_norm(c2, g2_, b2, 0.3); st2 = ops.layer_style(c2)
