@@ -50,10 +50,14 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // ------------------------------------------------------------------------------------------------
 // c3 forward: block = (128 output pixels of one output row); thread = (pixel pair, channel quarter)
 // ------------------------------------------------------------------------------------------------
-template <int S, int COUT>
-__global__ void __launch_bounds__(256)
+template <int S, int COUT, int PXT>
+__global__ void __launch_bounds__(512 / PXT)
 c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
               float* __restrict__ y, int H, int W, int OH, int OW, int pby, int pbx, int act, float alpha) {
+  // thread = (PXT consecutive pixels, channel quarter).  The kernel is bound by shared-memory wavefronts, not FFMAs (ncu:
+  // L1 data pipe 87 % busy, FMA pipe 40 % with two pixels per thread - a weight float4 costs four wavefronts and fed only
+  // 8 FFMAs): PXT = 4 pixels per thread halve the weight reads per FFMA.
+  constexpr int NT = 512 / PXT;           // threads per block: (128 / PXT pixel groups) x 4 channel quarters
   constexpr int CPT = COUT / 16;          // float4 channel groups per thread
   constexpr int C4 = COUT / 4;
   constexpr int NCOL = 127 * S + 3;       // input columns under 128 output pixels
@@ -61,9 +65,9 @@ c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
   __shared__ __align__(16) float s_w[27 * COUT];
   __shared__ float s_x[3 * RS];
   const int tid = threadIdx.x, n = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * 128;
-  for (int i = tid; i < 27 * C4; i += 256) cp_async16(s_w + 4 * i, w + 4 * i);
+  for (int i = tid; i < 27 * C4; i += NT) cp_async16(s_w + 4 * i, w + 4 * i);
   const int ix0 = ox0 * S - pbx;
-  for (int i = tid; i < 3 * RS; i += 256) {
+  for (int i = tid; i < 3 * RS; i += NT) {
     const int r = i / RS, j = i - r * RS, col = j / 3;
     const int iy = oy * S + r - pby, ix = ix0 + col;
     const bool in = (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
@@ -71,10 +75,10 @@ c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
   }
   cp_async_wait_all();
   __syncthreads();
-  const int q = tid & 3, pp = tid >> 2, la = 2 * pp * S;
-  float4 acc[2][CPT];
+  const int q = tid & 3, pp = tid >> 2, la = PXT * pp * S;
+  float4 acc[PXT][CPT];
 #pragma unroll
-  for (int p = 0; p < 2; ++p)
+  for (int p = 0; p < PXT; ++p)
 #pragma unroll
     for (int j = 0; j < CPT; ++j) acc[p][j] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4* w4 = reinterpret_cast<const float4*>(s_w);
@@ -82,18 +86,20 @@ c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
   for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
     for (int e = 0; e < 9; ++e) {           // e = kx*3 + ci: 9 contiguous floats of the input row
-      const float xa = s_x[ky * RS + la * 3 + e], xb = s_x[ky * RS + (la + S) * 3 + e];
+      float xs[PXT];
+#pragma unroll
+      for (int p = 0; p < PXT; ++p) xs[p] = s_x[ky * RS + (la + p * S) * 3 + e];
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
         const float4 wv = w4[(ky * 9 + e) * C4 + q + 4 * j];
-        fma4(acc[0][j], xa, wv);
-        fma4(acc[1][j], xb, wv);
+#pragma unroll
+        for (int p = 0; p < PXT; ++p) fma4(acc[p][j], xs[p], wv);
       }
     }
   }
 #pragma unroll
-  for (int p = 0; p < 2; ++p) {
-    const int ox = ox0 + 2 * pp + p;
+  for (int p = 0; p < PXT; ++p) {
+    const int ox = ox0 + PXT * pp + p;
     if (ox >= OW) continue;
     float* out = y + ((size_t)(n * OH + oy) * OW + ox) * COUT;
 #pragma unroll
@@ -913,10 +919,18 @@ int cn_skinny_fwd(const cn_conv_desc* d, const float* x, const float* w, const f
     int OH, OW, pby, pbx;
     same_pad(H, 3, d->stride, &OH, &pby); same_pad(W, 3, d->stride, &OW, &pbx);
     dim3 grid((OW + 127) / 128, OH, d->batch);
-    if (d->stride == 2 && d->cout == 48) c3_fwd_kernel<2, 48><<<grid, 256, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
-    else if (d->stride == 2) c3_fwd_kernel<2, 64><<<grid, 256, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
-    else if (d->cout == 48) c3_fwd_kernel<1, 48><<<grid, 256, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
-    else c3_fwd_kernel<1, 64><<<grid, 256, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+    static const int pxt = [] { const char* e = getenv("CN_C3_PXT"); return e ? atoi(e) : 4; }();     // pixels per thread (A/B: 2)
+    if (pxt == 2) {
+      if (d->stride == 2 && d->cout == 48) c3_fwd_kernel<2, 48, 2><<<grid, 256, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+      else if (d->stride == 2) c3_fwd_kernel<2, 64, 2><<<grid, 256, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+      else if (d->cout == 48) c3_fwd_kernel<1, 48, 2><<<grid, 256, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+      else c3_fwd_kernel<1, 64, 2><<<grid, 256, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+    } else {
+      if (d->stride == 2 && d->cout == 48) c3_fwd_kernel<2, 48, 4><<<grid, 128, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+      else if (d->stride == 2) c3_fwd_kernel<2, 64, 4><<<grid, 128, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+      else if (d->cout == 48) c3_fwd_kernel<1, 48, 4><<<grid, 128, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+      else c3_fwd_kernel<1, 64, 4><<<grid, 128, 0, st>>>(x, w, bias, y, H, W, OH, OW, pby, pbx, act, alpha);
+    }
     CN_CHECK_LAUNCH();
     return 1;
   }
