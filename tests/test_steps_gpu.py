@@ -6,7 +6,11 @@ reference's draw order), so every step is compared from identical state ("teache
 networks is chaotic after one Adam sign-step, a free-running comparison would only measure that):
 
   * every loss term of the step                      <= 1e-3 relative (the north-star bar)
-  * the packed flat gradient the optimizer consumed  <= 3e-2 relative L2 per variable (see test_networks_gpu.py)
+  * the packed flat gradient the optimizer consumed, relative L2 per variable: discriminator steps <= 1e-2 (measured
+    5e-5 .. 4e-3), latent-discriminator steps <= 1e-4 .. 1e-3 (measured 2e-7 .. 5e-6), generator steps <= 3e-2 (stage 1:
+    measured 7e-3 .. 9e-3; stage 2: 5e-2, see there) - the generator gradient runs through ~25 LeakyReLU / normalisation
+    stages on untrained B = 4 networks, where the fp32 CPU oracle itself is 5e-3 .. 2e-2 from the fp64 oracle
+    (profiles/r01_precision_study.md)
   * the weights after the step == Keras-Adam [TF-2.1] applied in fp64 to (weights before, THAT gradient, moments before,
     the optimizer's shared iteration count)          <= 2e-7 absolute: pack_grads offsets, the device learning rate, the
                                                         1/world scale and the fused kernel are pinned exactly
@@ -201,7 +205,7 @@ def run_stage1(dev, graphs, with_oracle, n_iters=3):
         l = model.discriminator_training_step(real, d_opt)
         hist.append([float(v) for v in l.values()])
         if with_oracle:
-            worst["d%d" % it] = chk.check(l, l_ref, g_ref, "D step, iteration %d" % (it + 1))
+            worst["d%d" % it] = chk.check(l, l_ref, g_ref, "D step, iteration %d" % (it + 1), grad_tol=1e-2)
         # ---- synth_discriminator_training_step (:452-464,478-488)
         chk = StepCheck([grp("synth_discriminator")], d_opt)
         if with_oracle:
@@ -215,7 +219,7 @@ def run_stage1(dev, graphs, with_oracle, n_iters=3):
         l = model.synth_discriminator_training_step(synth, d_opt)
         hist.append([float(v) for v in l.values()])
         if with_oracle:
-            worst["sd%d" % it] = chk.check(l, l_ref, g_ref, "synth-D step, iteration %d" % (it + 1))
+            worst["sd%d" % it] = chk.check(l, l_ref, g_ref, "synth-D step, iteration %d" % (it + 1), grad_tol=1e-2)
         # ---- latent_discriminator_training_step (:490-504): the SAME optimizer object (shared iteration count)
         chk = StepCheck([grp("latent_discriminator")], d_opt)
         if with_oracle:
@@ -310,7 +314,7 @@ def run_stage2(dev, graphs, with_oracle, n_iters=3):
         l = model.discriminator_training_step(real, d_opt)
         hist.append([float(v) for v in l.values()])
         if with_oracle:
-            worst["d%d" % it] = chk.check(l, l_ref, g_ref, "stage-2 D step, iteration %d" % (it + 1))
+            worst["d%d" % it] = chk.check(l, l_ref, g_ref, "stage-2 D step, iteration %d" % (it + 1), grad_tol=1e-2)
         # ---- latent_discriminator_training_step (confignet_second_stage.py:132-147)
         chk = StepCheck([grp("latent_discriminator")], d_opt)
         if with_oracle:
