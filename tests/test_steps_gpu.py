@@ -7,7 +7,7 @@ networks is chaotic after one Adam sign-step, a free-running comparison would on
 
   * every loss term of the step                      <= 1e-3 relative (the north-star bar)
   * the packed flat gradient the optimizer consumed, relative L2 per variable: discriminator steps <= 1e-2 (measured
-    5e-5 .. 4e-3), latent-discriminator steps <= 1e-4 .. 1e-3 (measured 2e-7 .. 5e-6), generator steps <= 3e-2 (stage 1:
+    5e-5 .. 4e-3), latent-discriminator steps <= 1e-3 (measured 2e-7 .. 5e-6), generator steps <= 3e-2 (stage 1:
     measured 7e-3 .. 9e-3; stage 2: 5e-2, see there) - the generator gradient runs through ~25 LeakyReLU / normalisation
     stages on untrained B = 4 networks, where the fp32 CPU oracle itself is 5e-3 .. 2e-2 from the fp64 oracle
     (profiles/r01_precision_study.md)
@@ -329,7 +329,7 @@ def run_stage2(dev, graphs, with_oracle, n_iters=3):
         hist.append([float(v) for v in l.values()])
         if with_oracle:
             worst["ld%d" % it] = chk.check(l, l_ref, g_ref, "stage-2 latent-D step, iteration %d" % (it + 1),
-                                           loss_tol=1e-3, grad_tol=2e-2)
+                                           loss_tol=1e-3, grad_tol=1e-3)        # measured 2e-7 .. 5e-6
         # ---- generator_training_step (confignet_second_stage.py:149-218)
         gnames = ["generator", "latent_regressor", "synthetic_encoder", "encoder"]
         chk = StepCheck([grp(n) for n in gnames], g_opt)
