@@ -1905,6 +1905,40 @@ __global__ void colsum_kernel(const float* __restrict__ g, int rows, int n, floa
   }
 }
 
+// Dense-layer weight gradient with a handful of rows (the AdaIN / latent MLPs, style heads: M = batch <= 64):
+// gW[k][n] = sum_m x[m][k] * gy[m][n].  Thread = (k, column quad); its M row pairs are independent loads, eight in flight;
+// the sum runs over m in order (deterministic).  The generic 64x64-tile kernel spent ~9 us per launch on these
+// (~80 launches per step: staging, split-K slabs and a reduce for a few kFLOP).
+__global__ void __launch_bounds__(256)
+dense_wgrad_small_kernel(const float* __restrict__ X, const float* __restrict__ G, float* __restrict__ gW,
+                         float* __restrict__ gbias, int M, int K, int N) {
+  const int nq = N >> 2;
+  const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (size_t)K * nq) return;
+  const int k = (int)(t / nq), j = (int)(t - (size_t)k * nq);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), bs = acc;     // bs: the bias gradient (column sums of gy), kept by the k = 0 threads
+  int m = 0;
+  for (; m + 7 < M; m += 8) {
+    float xv[8]; float4 g[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { xv[u] = cn_ldg1_ordered(X + (size_t)(m + u) * K + k); g[u] = cn_ldg4_ordered(G + (size_t)(m + u) * N + 4 * j); }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc.x = fmaf(xv[u], g[u].x, acc.x); acc.y = fmaf(xv[u], g[u].y, acc.y);
+      acc.z = fmaf(xv[u], g[u].z, acc.z); acc.w = fmaf(xv[u], g[u].w, acc.w);
+      bs.x += g[u].x; bs.y += g[u].y; bs.z += g[u].z; bs.w += g[u].w;
+    }
+  }
+  for (; m < M; ++m) {
+    const float xv = cn_ldg1_ordered(X + (size_t)m * K + k);
+    const float4 g = cn_ldg4_ordered(G + (size_t)m * N + 4 * j);
+    acc.x = fmaf(xv, g.x, acc.x); acc.y = fmaf(xv, g.y, acc.y); acc.z = fmaf(xv, g.z, acc.z); acc.w = fmaf(xv, g.w, acc.w);
+    bs.x += g.x; bs.y += g.y; bs.z += g.z; bs.w += g.w;
+  }
+  *reinterpret_cast<float4*>(gW + (size_t)k * N + 4 * j) = acc;
+  if (k == 0 && gbias != nullptr) *reinterpret_cast<float4*>(gbias + 4 * j) = bs;
+}
+
 // 16-byte form (n % 4 == 0, n <= 1024): a block owns a run of rows, thread (q, rr) owns column quad q and walks the rows
 // rr, rr + R, ... with eight loads in flight (the kernel above keeps ONE 4-byte load in flight per thread and took 34 us
 // whatever the matrix, profiles/r02_launches_s2a_summary.txt); the R row groups are folded in order.  out = [gridDim.x][n].
@@ -2679,6 +2713,13 @@ extern "C" int cn_conv_wgrad(const cn_conv_desc* d, const float* x, const float*
     rc = launch_wgrad_tc(g, x, gy, gw, st, gbias);
     if (rc) return rc;
     if (gbias != nullptr) return CN_OK;      // the bias gradient came out of the gradient pack pass
+  } else if (d->nd == 0 && g.ntaps == 1 && g.M <= 64 && g.Cn % 4 == 0 && (((uintptr_t)gy | (uintptr_t)gw) & 15) == 0) {
+    // Dense layer, a handful of rows: one thread per (input, output quad), no slabs
+    const size_t threads = (size_t)g.Ktot * (g.Cn / 4);
+    const bool bias_here = gbias != nullptr && ((uintptr_t)gbias & 15) == 0;
+    dense_wgrad_small_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, gy, gw, bias_here ? gbias : nullptr, g.M, g.Ktot, g.Cn);
+    CN_CHECK_LAUNCH();
+    if (bias_here) return CN_OK;           // the bias gradient came out of the same launch
   } else if (g.ntaps == 1 && g.Csrc <= 4 && g.Cn <= 4 && g.mstride == 1 && g.ushift == 0 && g.M >= 4096) {   // 1x1, stride 1: source pixel = output pixel
     // the small weight-gradient kernels write per-block partials (slabs); sum_slabs_kernel adds them in block order
     const int blocks = 4 * num_sms();
