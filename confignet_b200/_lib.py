@@ -40,7 +40,8 @@ def make_conv_desc(nd, batch, in_dims, cin, cout, ksize, stride=1, upsample=1, p
                     stride, upsample, pad)
 
 
-ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_RELU6, ACT_SIGMOID = 0, 1, 2, 3, 4, 5
+POOL_MAX, POOL_AVG_VALID = 0, 1
 IMPL_AUTO, IMPL_FFMA, IMPL_TC = 0, 1, 2
 
 _F = ctypes.POINTER(ctypes.c_float)
@@ -99,6 +100,11 @@ SIGNATURES = {
     "cn_rotate3d_bwd_rot": [_V, _V, _V, _I, _I, _I, _V, _V],
     "cn_norm_latent_loss_fwd": [_V, _V, _I, _I, _I, _f, _V, _V],
     "cn_norm_latent_loss_bwd": [_V, _V, _I, _I, _I, _f, _V, _V, _V, _V],
+    "cn_pool2d_fwd": [_V, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _V, _I, _V],
+    "cn_dwconv3x3_fwd": [_V, _V, _V, _I, _I, _I, _I, _I, _I, _f, _V, _V],
+    "cn_resize_bilinear": [_V, _I, _I, _I, _I, _I, _I, _I, _V, _V],
+    "cn_u8_to_f32": [_V, _V, _L, _V],
+    "cn_pixel_map": [_V, _V, _L, _I, _V],
 }
 NO_STATUS = {"cn_last_error": ctypes.c_char_p, "cn_version": ctypes.c_int, "cn_reduce_ws_floats": ctypes.c_int,
              "cn_launch_count": ctypes.c_longlong, "cn_params_epoch": ctypes.c_longlong, "cn_launch_count_add": ctypes.c_longlong, "cn_last_conv_impl": ctypes.c_int}

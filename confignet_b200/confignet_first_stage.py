@@ -576,13 +576,21 @@ class ConfigNetFirstStage(StepGraphs):
         """confignet_first_stage.py:562-595.  Draws from NumPy's global stream what the reference's set-up draws, in its
         order - the InceptionMetrics sample rows (metrics/metrics.py:206; always 1000), the metric latents / rotations,
         the checkpoint latents and the checkpoint rows of the synthetic set - so a seeded run enters its first training
-        step at the reference's stream position, and keeps the same checkpoint / metric inputs.  KID / FID themselves
-        (InceptionV3 with ImageNet weights) and TensorBoard are out of scope."""
+        step at the reference's stream position, and keeps the same checkpoint / metric inputs.  A real training set that
+        carries precomputed ``inception_features`` (NeuralRendererDataset does) gets the reference's InceptionMetrics object
+        (KID / FID on the B200 InceptionV3, confignet_b200/metrics); one without them only consumes the same draw.
+        TensorBoard is out of scope."""
         if real_training_set is None:
             real_training_set = synth_training_set
         if log_dir:
             os.makedirs(log_dir, exist_ok=True)
-        self._metric_sample_idxs = np.random.randint(0, real_training_set.imgs.shape[0], 1000)
+        if getattr(real_training_set, "inception_features", None) is not None:
+            from .metrics.metrics import InceptionMetrics
+            self._inception_metric_object = InceptionMetrics(self.config, real_training_set, weights=self.config.get("inception_weights"),
+                                                             device=self.device)
+        else:
+            self._inception_metric_object = None
+            self._metric_sample_idxs = np.random.randint(0, real_training_set.imgs.shape[0], 1000)
         self._generator_input_for_metrics = {"latent": self.sample_latent_vector(n_samples_for_metrics),
                                              "rotation": self.sample_rotations(n_samples_for_metrics)}
         n_rot, n_smp = self.n_checkpoint_rotations, self.n_checkpoint_samples
@@ -600,8 +608,9 @@ class ConfigNetFirstStage(StepGraphs):
     def run_checkpoints(self, output_dir, iteration_time, aml_run=None, checkpoint_start=None):
         """confignet_first_stage.py:332-375: the cadence and the files a resumed run needs - the loss histories as
         <prefix>losses.txt (confignet_utils.py:239-241) every image_checkpoint_period steps, a checkpoint under
-        <output_dir>/checkpoints/<step, 6 digits> every metrics_checkpoint_period steps (step 0 included).  Image grids
-        (OpenCV), loss plots (matplotlib), TensorBoard / AzureML scalars and KID / FID are out of scope."""
+        <output_dir>/checkpoints/<step, 6 digits> every metrics_checkpoint_period steps (step 0 included), preceded by
+        calculate_metrics() when setup_training() built the metric objects.  Image grids (OpenCV), loss plots (matplotlib)
+        and TensorBoard / AzureML scalars are out of scope."""
         if not output_dir or world()[0] != 0:
             return
         step_number = self.get_training_step_number()
@@ -610,6 +619,9 @@ class ConfigNetFirstStage(StepGraphs):
             _log_loss_vals(self.synth_d_losses, output_dir, "synth_discriminator_")
             _log_loss_vals(self.latent_d_losses, output_dir, "latent_discriminator_")
         if step_number % self.config["metrics_checkpoint_period"] == 0:
+            if getattr(self, "_inception_metric_object", None) is not None:
+                print("Running metrics")
+                self.calculate_metrics(output_dir, aml_run=aml_run)
             checkpoint_output_dir = os.path.join(output_dir, "checkpoints")
             os.makedirs(checkpoint_output_dir, exist_ok=True)
             self.save(checkpoint_output_dir, str(step_number).zfill(6))
@@ -617,6 +629,17 @@ class ConfigNetFirstStage(StepGraphs):
             _log_loss_vals(self.g_losses, output_dir, "generator_")
             _log_loss_vals(self.d_losses, output_dir, "discriminator_")
             print("Training iteration time: %f" % iteration_time)
+
+    def generate_output_for_metrics(self):
+        """confignet_first_stage.py:331-332"""
+        return self.generate_images(self._generator_input_for_metrics["latent"], self._generator_input_for_metrics["rotation"])
+
+    def calculate_metrics(self, output_dir, aml_run=None):
+        """confignet_first_stage.py:378-385: KID / FID of the smoothed generator's images against the real set's features,
+        appended to self.metrics (saved with the checkpoint) and written to <output_dir>/inception_metrics.txt"""
+        generated_images = self.generate_output_for_metrics()
+        self.metrics.setdefault("training_step_number", []).append(self.get_training_step_number())
+        self._inception_metric_object.update_and_log_metrics(generated_images, self.metrics, output_dir, aml_run, None)
 
     def train(self, real_training_set, synth_training_set, output_dir, log_dir, n_steps=100000,
               n_samples_for_metrics=1000, aml_run=None):

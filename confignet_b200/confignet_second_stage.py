@@ -6,7 +6,7 @@ dnn_models/real_encoder.py:9-34), the second-stage latent-discriminator / genera
 batch-normalised latent regression loss (:93-107), ``encode_images`` (:301-308), ``generate_images`` with the
 fine-tuned generator (:310-319) and ``fine_tune_on_img`` (:321-403) with its VGGFace (VGG16) perceptual term.
 
-Out of scope: image / metric checkpoints, ControllabilityMetrics, TensorBoard.
+Out of scope: image checkpoints (OpenCV grids), TensorBoard.
 """
 import os
 import time
@@ -256,14 +256,51 @@ class ConfigNet(ConfigNetFirstStage):
     def setup_training(self, log_dir, synth_training_set, n_samples_for_metrics, attribute_classifier=None,
                        real_training_set=None, validation_set=None):
         """confignet_second_stage.py:255-266: + the checkpoint / metric rows of the validation set (two more draws from
-        the NumPy stream; skipped, like the reference would fail, when there is no validation set).  The controllability
-        metrics (CelebA attribute classifier) are out of scope."""
+        the NumPy stream; skipped, like the reference would fail, when there is no validation set) and the
+        ControllabilityMetrics object around ``attribute_classifier`` (a CelebaAttributeClassifier or the path of its
+        .json; None: no controllability metrics)."""
         super().setup_training(log_dir, synth_training_set, n_samples_for_metrics, real_training_set)
         if validation_set is not None:
             idxs = np.random.randint(0, validation_set.imgs.shape[0], self.n_checkpoint_samples)
             self._checkpoint_visualization_input["input_images"] = self._take_rows(validation_set.imgs, idxs)
             idxs = np.random.randint(0, validation_set.imgs.shape[0], n_samples_for_metrics)
             self._generator_input_for_metrics["input_images"] = self._take_rows(validation_set.imgs, idxs)
+        if attribute_classifier is not None:
+            from .metrics.metrics import ControllabilityMetrics
+            self.controllability_metrics = ControllabilityMetrics(self, attribute_classifier)
+
+    def generate_output_for_metrics(self):
+        """confignet_second_stage.py:81-83: reconstructions of the validation rows"""
+        latent, rotation = self.encode_images(self._generator_input_for_metrics["input_images"])
+        return self.generate_images(latent, rotation)
+
+    def calculate_metrics(self, output_dir, aml_run=None):
+        """confignet_second_stage.py:220-253: KID / FID of the reconstructions, the controllability metrics, and the mean
+        perceptual (VGG19) loss between the validation images and their reconstructions in batches of 16 -> self.metrics,
+        controllability_metrics.json, image_metrics.txt"""
+        super().calculate_metrics(output_dir, aml_run)
+        input_images = self._generator_input_for_metrics["input_images"]
+        if self.controllability_metrics is not None:
+            self.controllability_metrics.update_and_log_metrics(input_images, self.metrics, output_dir, aml_run, None)
+        latents, rotations = self.encode_images(input_images)
+        metric_batch_size = 16
+        n_valid_samples = len(input_images)
+        perceptual_loss = []
+        with torch.no_grad():
+            for i in range(1 + n_valid_samples // metric_batch_size):
+                start_idx, end_idx = i * metric_batch_size, min(n_valid_samples, (i + 1) * metric_batch_size)
+                if end_idx <= start_idx:
+                    break           # (the reference evaluates an empty trailing batch - NaN - when n is a multiple of 16)
+                gt_imgs = self._images_to_device(input_images[start_idx:end_idx])
+                gen_imgs = self.generator_smoothed.predict_device(
+                    self.generator_smoothed.build_input_dict(self._to_device(latents[start_idx:end_idx], torch.float32),
+                                                             self._to_device(rotations[start_idx:end_idx], torch.float32)))
+                perceptual_loss.append(float(networks.perceptual_loss(self.perceptual_loss.params, gt_imgs, gen_imgs)))
+        perceptual_loss = float(np.mean(perceptual_loss))
+        self.metrics.setdefault("perceptual_loss", []).append(perceptual_loss)
+        if aml_run is not None:
+            aml_run.log("perceptual_loss", perceptual_loss)
+        np.savetxt(os.path.join(output_dir, "image_metrics.txt"), self.metrics["perceptual_loss"])
 
     def train(self, real_training_set, synth_training_set, validation_set=None, attribute_classifier=None,
               output_dir=None, log_dir=None, n_steps=100000, n_samples_for_metrics=1000, aml_run=None):

@@ -107,5 +107,7 @@ __device__ __forceinline__ float cn_apply_act(float v, int act, float alpha) {
   if (act == CN_ACT_LRELU) return v >= 0.f ? v : v * alpha;
   if (act == CN_ACT_RELU) return v > 0.f ? v : 0.f;
   if (act == CN_ACT_TANH) return tanhf(v);
+  if (act == CN_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
+  if (act == CN_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
   return v;
 }

@@ -32,6 +32,8 @@ extern "C" {
 #define CN_ACT_LRELU 1
 #define CN_ACT_RELU 2
 #define CN_ACT_TANH 3
+#define CN_ACT_RELU6 4    /* keras ReLU(6.) of MobileNetV2 (metric networks, forward only) */
+#define CN_ACT_SIGMOID 5  /* attribute-classifier head (metrics/celeba_attribute_prediction.py:62), forward only */
 
 /* kernel selection for the conv / dense family */
 #define CN_IMPL_AUTO 0   /* tcgen05 tensor-core kernel where the shape allows, else CUDA-core */
@@ -238,6 +240,31 @@ int cn_rotate3d_bwd_rot(const float* grid, const float* gout, const float* rot, 
 int cn_norm_latent_loss_fwd(const float* out, const float* labels, int b, int j, int nrot, float weight, float* loss, void* stream);
 int cn_norm_latent_loss_bwd(const float* out, const float* labels, int b, int j, int nrot, float weight, const float* gscale,
                             float* g_out, float* g_labels, void* stream);
+
+/* ---- training-time metric networks (metrics/inception_distance.py, metrics/celeba_attribute_prediction.py) --------
+ * Forward only.  The convolutions of InceptionV3 / MobileNetV2 go through cn_conv_fwd with their inference BatchNorm folded
+ * into kernel and bias by the host (netspec.fold_batchnorm); these are the remaining layers. */
+#define CN_POOL_MAX 0        /* MaxPooling2D: maximum over the in-bounds part of the window                       */
+#define CN_POOL_AVG_VALID 1  /* AveragePooling2D(padding="same"): mean over the in-bounds elements (TF leaves the
+                                padding out of the count)                                                          */
+/* y[n,oy,ox,0:c] = pool over the kh x kw window whose corner is (oy*stride - pad_t, ox*stride - pad_l); output pixel
+ * records are ldy >= c floats apart, so a branch of an Inception block can write its slice of the concatenated tensor.
+ * replaces MaxPooling2D / AveragePooling2D inside keras.applications.InceptionV3 (inception_distance.py:11). */
+int cn_pool2d_fwd(const float* x, int n, int h, int w, int c, int kh, int kw, int stride, int pad_t, int pad_l,
+                  int oh, int ow, int mode, float* y, int ldy, void* stream);
+/* y = act(depthwise_conv3x3_same(x, wk) + bias): wk (3,3,c) = the Keras DepthwiseConv2D kernel (3,3,c,1), stride 1 or 2,
+ * TF SAME geometry.  replaces DepthwiseConv2D + BatchNormalization + ReLU(6.) inside keras.applications.MobileNetV2
+ * (celeba_attribute_prediction.py:55). */
+int cn_dwconv3x3_fwd(const float* x, const float* wk, const float* bias, int n, int h, int w, int c, int stride,
+                     int act, float alpha, float* y, void* stream);
+/* cv2.resize(img, (ow, oh)) with the default INTER_LINEAR on channels-last images: uint8 (is_u8 = 1, OpenCV's fixed-point
+ * form, bit-exact) or float32.  replaces celeba_attribute_prediction.py:131-136. */
+int cn_resize_bilinear(const void* x, int n, int h, int w, int c, int oh, int ow, int is_u8, void* y, void* stream);
+/* y = (float)x for uint8 x (keras-applications preprocess_input's astype, celeba_attribute_prediction.py:138) */
+int cn_u8_to_f32(const void* x, float* y, int64_t n, void* stream);
+/* mode 0: y = (x + 1) * 127.5 (celeba_attribute_prediction.py:129-130); mode 1: y = x / 127.5 - 1 (preprocess_input
+ * mode "tf": inception_distance.py:24, celeba_attribute_prediction.py:138); one rounding per NumPy operation */
+int cn_pixel_map(const float* x, float* y, int64_t n, int mode, void* stream);
 
 #ifdef __cplusplus
 }

@@ -137,11 +137,26 @@ def main():
                      "generator_training_step"):
             setattr(cls, name, recorder(name))
         cls.update_smoothed_weights = lambda self, smoother_alpha=0.999: calls.append([type(self).__name__, "update_smoothed_weights"])
+    # calculate_metrics (KID / FID, controllability, perceptual loss) needs the GPU networks: recorded here, executed by
+    # tests/test_metrics_gpu.py.  setup_training builds the metric objects for real (host half only).
+    metric_calls = []
+    for cls in (confignet_b200.ConfigNetFirstStage, confignet_b200.ConfigNet):
+        cls.calculate_metrics = (lambda cls: lambda self, output_dir, aml_run=None: metric_calls.append(
+            [cls.__name__, self.get_training_step_number(), type(self._inception_metric_object).__name__,
+             type(getattr(self, "controllability_metrics", None)).__name__]))(cls)
     seen_cfg = []
     orig_train2 = confignet_b200.ConfigNet.train
     confignet_b200.ConfigNet.train = lambda self, *a, **k: (seen_cfg.append(dict(self.config)), orig_train2(self, *a, **k))[1]
     out2 = tempfile.mkdtemp(prefix="cn_train2_")
-    train_confignet.parse_args(script_args(out2))
+    # the attribute classifier the script hands to stage 2 (--attribute_classifier_path): a file pair in the reference's format
+    from confignet_b200.metrics import CelebaAttributeClassifier
+    CelebaAttributeClassifier({"input_shape": [128, 128, 3], "predicted_attributes": ["Smiling", "Young"]}, device="cpu").save(out2, "no_classifier")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")             # stand-in InceptionV3 weights (no download offline)
+        train_confignet.parse_args(script_args(out2))
+    assert metric_calls == [["ConfigNetFirstStage", 0, "InceptionMetrics", "NoneType"],
+                            ["ConfigNet", 0, "InceptionMetrics", "ControllabilityMetrics"]], metric_calls
     names = [c[:2] for c in calls]
     assert names == [["ConfigNetFirstStage", "discriminator_training_step"], ["ConfigNetFirstStage", "synth_discriminator_training_step"],
                      ["ConfigNetFirstStage", "latent_discriminator_training_step"], ["ConfigNetFirstStage", "generator_training_step"],
