@@ -235,7 +235,7 @@ def dwconv3x3(x, wk, bias, stride, act):
     return y
 
 
-def add(a, b):
+def residual_add(a, b):
     """keras.layers.Add of a MobileNetV2 block"""
     out = torch.empty_like(a)
     L.call("cn_axpby", ops._p(ops._chk(a)), ops._p(ops._chk(b)), 1.0, 1.0, ops._p(out), a.numel(), ops._stream())
@@ -255,7 +255,7 @@ def attribute_classifier_forward(p, x):
             else:
                 x = ops.conv_act(x, p[cname + "/kernel"], p[cname + "/bias"], stride=stride, act=acts[act])
                 if add:
-                    x = add(x, block_in)
+                    x = residual_add(x, block_in)
         feat = ops.global_avg_pool(x)
         return ops.conv_act(feat, p["dense/kernel"], p["dense/bias"], act=L.ACT_SIGMOID)
 
