@@ -52,6 +52,18 @@ t = timed(lambda: ex.features_device(imgs))
 impl, ms, fl = breakdown(lambda: ex.features_device(imgs))
 print("InceptionV3 features: batch %d, %.2f ms, %.0f images/s, %.1f GFLOP/image, %.1f TFLOP/s; conv launches by family (2 = tcgen05, 1 = CUDA-core) %s, conv ms by family %s"
       % (B, t, B / t * 1e3, fl / B / 1e9, fl / t / 1e9, impl, ms))
+# the CPU restatement beside it (oracle, fp32, all host cores, a bounded sample of the same workload)
+import time                                                                    # noqa: E402
+from oracle import metrics_oracle as MO, confignet_oracle as O                  # noqa: E402
+ncpu = 8
+xc = torch.tensor(imgs[:ncpu].cpu().numpy().astype(np.float32) / np.float32(127.5) - np.float32(1))
+pc = O.to_torch(ex.raw_weights, dtype=torch.float32)
+with torch.no_grad():
+    MO.inception_v3_features(pc, xc[:2])
+    t0 = time.perf_counter()
+    MO.inception_v3_features(pc, xc)
+    tc = time.perf_counter() - t0
+print("InceptionV3 features, CPU oracle (torch fp32, %d threads): %d images in %.2f s = %.1f images/s" % (torch.get_num_threads(), ncpu, tc, ncpu / tc))
 clf = CelebaAttributeClassifier({"input_shape": [128, 128, 3], "predicted_attributes": ["a%d" % i for i in range(40)]}, device=dev)
 t = timed(lambda: clf.predict_attributes(imgs))
 x = ops.from_uint8(nets.resize_images(imgs, 128, 128))
