@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import netspec, networks, ops, pretrained
-from .runtime import ParamGroup, Network, KerasAdam, StepGraphs, InferenceGraphs, shard_rows, world
+from .runtime import ParamGroup, Network, KerasAdam, StepGraphs, InferenceGraphs, shard_rows, world, coalesce_grads
 
 DEFAULT_CONFIG = {
     "model_type": None,
@@ -248,6 +248,8 @@ class ConfigNetFirstStage(StepGraphs):
                                        networks.vgg19_activations)
         self.perceptual_loss.group.set_frozen(self.drop_graphs)
         if type(self) is ConfigNetFirstStage:
+            # the three networks of the generator step share one gradient allocation: one all-reduce per step (runtime.coalesce_grads)
+            coalesce_grads([self.generator.group, self.latent_regressor.group, self.synthetic_encoder.group])
             pretrained.from_config_or_env(self)
 
     PRETRAINED = (("perceptual_loss", "the VGG19 perceptual-loss network (perceptual_loss.py:19-24)"),)

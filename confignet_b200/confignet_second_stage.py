@@ -17,7 +17,7 @@ import torch.distributed as dist
 
 from . import netspec, networks, ops, pretrained
 from .confignet_first_stage import (ConfigNetFirstStage, DEFAULT_CONFIG, merge_configs, update_loss_dict, GeneratorNet)
-from .runtime import ParamGroup, Network, KerasAdam, allreduce_grads, shard_rows, world, gather_rows
+from .runtime import ParamGroup, Network, KerasAdam, allreduce_grads, shard_rows, world, gather_rows, coalesce_grads
 
 PREDICT_BATCH = 32       # keras Model.predict default batch size [TF-2.1]
 
@@ -77,6 +77,8 @@ class ConfigNet(ConfigNetFirstStage):
         self.perceptual_loss_face_reco = Network(self._make_group(netspec.vgg16_spec(), s + 9, vgg_like=True),
                                                  networks.vggface_activations)
         self.perceptual_loss_face_reco.group.set_frozen(self.drop_graphs)
+        # the four networks of the stage-2 generator step, in _backward's order: one all-reduce per step
+        coalesce_grads([self.generator.group, self.latent_regressor.group, self.synthetic_encoder.group, self.encoder.group])
         pretrained.from_config_or_env(self)
 
     PRETRAINED = (("perceptual_loss", "the VGG19 perceptual-loss network (perceptual_loss.py:19-24)"),

@@ -520,15 +520,53 @@ def world():
     return 0, 1
 
 
+def coalesce_grads(groups):
+    """One allocation behind the flat gradient buffers of the networks ONE optimizer step updates (generator + latent
+    regressor + synthetic encoder (+ real encoder)): their gradient exchange is then a single all-reduce over the span
+    instead of one call per network - the exchange sits between two graph replays, so every call is exposed latency
+    ('one flat gradient buffer per optimizer step').  Must run before any graph is captured over
+    the groups (the buffers' addresses are baked into captured launches)."""
+    groups = [g for g in groups if g is not None]
+    if len(groups) < 2:
+        return
+    arena = torch.zeros(sum(g.total for g in groups), device=groups[0].device, dtype=torch.float32)
+    off = 0
+    for g in groups:
+        g.grad = arena[off:off + g.total]            # totals are multiples of 4 floats: every slot stays 16-byte aligned
+        g._grad_arena = (arena, off)
+        off += g.total
+
+
+def _grad_spans(groups):
+    """-> tensors to all-reduce: maximal runs of groups whose buffers are adjacent in one arena collapse into one span"""
+    spans, i = [], 0
+    while i < len(groups):
+        arena_off = getattr(groups[i], "_grad_arena", None)
+        j = i
+        if arena_off is not None:
+            arena, end = arena_off[0], arena_off[1] + groups[i].grad.numel()
+            while j + 1 < len(groups):
+                nxt = getattr(groups[j + 1], "_grad_arena", None)
+                if nxt is None or nxt[0] is not arena or nxt[1] != end:
+                    break
+                end += groups[j + 1].grad.numel()
+                j += 1
+            spans.append(arena[arena_off[1]:end] if j > i else groups[i].grad)
+        else:
+            spans.append(groups[i].grad)
+        i = j + 1
+    return spans
+
+
 def allreduce_grads(groups):
-    """Sum the flat gradient buffers over ranks (one NCCL all-reduce per network, fp32) and return the
-    1/world scale to fold into the optimizer kernel.  Losses are batch means over equal shards, so the
-    averaged gradient equals the single-process gradient of the global batch."""
+    """Sum the flat gradient buffers over ranks (fp32 NCCL all-reduce: one call per run of coalesced buffers, else one
+    per network) and return the 1/world scale to fold into the optimizer kernel.  Losses are batch means over equal
+    shards, so the averaged gradient equals the single-process gradient of the global batch."""
     rank, ws = world()
     if ws == 1:
         return 1.0
-    for g in groups:
-        dist.all_reduce(g.grad, op=dist.ReduceOp.SUM)
+    for span in _grad_spans(list(groups)):
+        dist.all_reduce(span, op=dist.ReduceOp.SUM)
     return 1.0 / ws
 
 

@@ -722,6 +722,23 @@ full = O.compute_latent_discriminator_loss(p, torch.tensor(real), torch.tensor(f
 want = torch.cat([x.reshape(-1) for x in O.grads_of(full, p)])
 err = float((g.grad * scale - want).abs().max() / want.abs().max())
 assert scale == 0.5 and err < 1e-12, err
+# coalesced gradient buffers (runtime.coalesce_grads): the networks of one optimizer step are exchanged in ONE call
+from confignet_b200.runtime import ParamGroup, coalesce_grads, _grad_spans
+gs = [ParamGroup(OrderedDict(w=np.full((n,), 1.0, np.float32)), "cpu") for n in (5, 8, 3, 6)]
+coalesce_grads(gs[:3])
+assert [sp.numel() for sp in _grad_spans(gs)] == [8 + 8 + 4, 8]                 # slots padded to 4 floats; the 4th group stays alone
+assert [sp.numel() for sp in _grad_spans([gs[0], gs[2], gs[3]])] == [8, 4, 8]   # not adjacent: no span across the gap
+assert [sp.numel() for sp in _grad_spans(gs[1:3])] == [12]
+calls = []
+real_all_reduce = dist.all_reduce
+dist.all_reduce = lambda t, op=None: (calls.append(t.numel()), real_all_reduce(t, op=op))[1]
+for i, g_ in enumerate(gs):
+    g_.grad[:g_.sizes[0]] = float(rank + 1) * (i + 1)
+assert allreduce_grads(gs) == 0.5 and calls == [20, 8]
+dist.all_reduce = real_all_reduce
+for i, g_ in enumerate(gs):
+    assert torch.equal(g_.grad[:g_.sizes[0]], torch.full((g_.sizes[0],), 3.0 * (i + 1))), (i, g_.grad)
+    assert float(g_.grad[g_.sizes[0]:].abs().sum()) == 0.0                       # padding stays zero
 dist.destroy_process_group()
 print("rank", rank, "ok", err)
 '''
