@@ -105,6 +105,7 @@ SIGNATURES = {
     "cn_resize_bilinear": [_V, _I, _I, _I, _I, _I, _I, _I, _V, _V],
     "cn_u8_to_f32": [_V, _V, _L, _V],
     "cn_pixel_map": [_V, _V, _L, _I, _V],
+    "cn_act_ext": [_V, _V, _L, _I, _V],
 }
 NO_STATUS = {"cn_last_error": ctypes.c_char_p, "cn_version": ctypes.c_int, "cn_reduce_ws_floats": ctypes.c_int,
              "cn_launch_count": ctypes.c_longlong, "cn_params_epoch": ctypes.c_longlong, "cn_launch_count_add": ctypes.c_longlong, "cn_last_conv_impl": ctypes.c_int}

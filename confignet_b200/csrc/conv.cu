@@ -762,6 +762,16 @@ __device__ __forceinline__ uint32_t tot_unit_off(int row, int unit) {      // by
 // tensor core works on the next chunk.  store(cb, v) receives the final 32-column groups of this thread's
 // accumulator row.  The running total lives in shared memory ([column][128 rows] fp32: lane = row, so the
 // accesses are conflict-free), which leaves the tensor memory to the two accumulators and the A stages.
+#ifdef CN_TC_COMPACT_ACT
+// Activation of the tcgen05 epilogue in three instructions per element: none / LeakyReLU / ReLU are one select on a
+// per-launch negative-side slope (1, alpha, 0; the fused add of +0 turns ReLU's -0 into +0, as v > 0 ? v : 0 gives);
+// tanh (no tensor-core layer of the training step uses it) stays out of line.  The epilogue unrolls this 64 times.
+__device__ __noinline__ float tc_tanh_out_of_line(float v) { return tanhf(v); }
+__device__ __forceinline__ float tc_act(float v, float slope, bool is_tanh) {
+  if (is_tanh) return tc_tanh_out_of_line(v);
+  return v >= 0.f ? v : fmaf(v, slope, 0.f);
+}
+#endif
 template <class StoreFn, class KeepFn>
 __device__ __forceinline__ void tc_promote_smem_and_store(uint32_t tmem_base, uint8_t* tot, int pw, int bn, int bn_r, int c0, int nchunks,
                                                           uint32_t bar_accfull, uint32_t bar_accempty, bool keep_last, StoreFn store, KeepFn keep) {
@@ -1299,6 +1309,10 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
   } else if (warp < 12) {
     // ===== promotion + epilogue: TMEM -> registers -> global (warp pw owns TMEM lanes 32pw..32pw+31) =====
     const int pw = warp - 8;
+#ifdef CN_TC_COMPACT_ACT
+    const float act_slope = act == CN_ACT_LRELU ? alpha : (act == CN_ACT_RELU ? 0.f : 1.f);
+    const bool act_tanh = act == CN_ACT_TANH;
+#endif
     const int chunk_kb = (dbg >> 8) ? (dbg >> 8) : TC_CHUNK_KB;
     int c0 = 0;                              // accumulation chunks of this CTA's earlier items
     bool tma_pending = false;                // a TMA tensor store of this CTA may still be reading the running-total buffer
@@ -1333,8 +1347,13 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
               continue;
             }
             if (bias != nullptr) { o.x += bias[n]; o.y += bias[n + 1]; o.z += bias[n + 2]; o.w += bias[n + 3]; }
+#ifdef CN_TC_COMPACT_ACT
+            o.x = tc_act(o.x, act_slope, act_tanh); o.y = tc_act(o.y, act_slope, act_tanh);
+            o.z = tc_act(o.z, act_slope, act_tanh); o.w = tc_act(o.w, act_slope, act_tanh);
+#else
             o.x = cn_apply_act(o.x, act, alpha); o.y = cn_apply_act(o.y, act, alpha);
             o.z = cn_apply_act(o.z, act, alpha); o.w = cn_apply_act(o.w, act, alpha);
+#endif
             *reinterpret_cast<float4*>(D + rowoff + n) = o;
           }
         }
@@ -1348,7 +1367,11 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
         const int n = n0 + cb + q;
         float o = __uint_as_float(v[q]);
         if (bias != nullptr && cb + q < bn && n < p.Cn) o += bias[n];
+#ifdef CN_TC_COMPACT_ACT
+        v[q] = __float_as_uint(tc_act(o, act_slope, act_tanh));
+#else
         v[q] = __float_as_uint(cn_apply_act(o, act, alpha));
+#endif
       }
     });
     if (tma_out) {
@@ -2560,6 +2583,8 @@ extern "C" int cn_conv_fwd(const cn_conv_desc* d, const float* x, const float* w
                            int act, float alpha, float* y, int impl, void* stream) {
   int rc = validate_desc(d); if (rc) return rc;
   CN_REQUIRE(x && w && y, CN_ERR_BAD_SHAPE, "null tensor pointer");
+  CN_REQUIRE(act >= CN_ACT_NONE && act <= CN_ACT_TANH, CN_ERR_UNSUPPORTED,
+             "activation code %d is not one of the conv epilogue's four (none, lrelu, relu, tanh); see cn_act_ext", act);
   if (impl != CN_IMPL_TC) {
     rc = cn_skinny_fwd(d, x, w, bias, act, alpha, y, (cudaStream_t)stream);
     if (rc < 0) return rc;

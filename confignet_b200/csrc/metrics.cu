@@ -113,7 +113,7 @@ __global__ void dwconv3x3_fwd_kernel(const float* __restrict__ x, const float* _
       }
     }
 #pragma unroll
-    for (int q = 0; q < VEC; ++q) acc[q] = cn_apply_act(acc[q] + (bias ? bias[ch + q] : 0.f), act, alpha);
+    for (int q = 0; q < VEC; ++q) acc[q] = cn_apply_act_ext(acc[q] + (bias ? bias[ch + q] : 0.f), act, alpha);
     float* dst = y + ((n * oh + oy) * ow + ox) * (size_t)c + ch;
     if (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
     else dst[0] = acc[0];
@@ -226,5 +226,29 @@ extern "C" int cn_pixel_map(const float* x, float* y, int64_t n, int mode, void*
   CN_REQUIRE(mode == 0 || mode == 1, CN_ERR_UNSUPPORTED, "cn_pixel_map: mode %d", mode);
   if (n <= 0) return CN_OK;
   pixel_map_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(x, y, (size_t)n, mode);
+  CN_CHECK_LAUNCH(); return CN_OK;
+}
+
+// y = act(x) for the two activation codes the conv epilogues do not carry (CN_ACT_RELU6 after a conv that ran with
+// CN_ACT_RELU is the clamp at 6; CN_ACT_SIGMOID on the attribute head's logits), in place or out of place.
+__global__ void act_ext_kernel(const float* __restrict__ x, float* __restrict__ y, size_t total, int act) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = cn_apply_act_ext(x[i], act, 0.f);
+}
+__global__ void act_ext4_kernel(const float4* __restrict__ x, float4* __restrict__ y, size_t total4, int act) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = x[i];
+    v.x = cn_apply_act_ext(v.x, act, 0.f); v.y = cn_apply_act_ext(v.y, act, 0.f);
+    v.z = cn_apply_act_ext(v.z, act, 0.f); v.w = cn_apply_act_ext(v.w, act, 0.f);
+    y[i] = v;
+  }
+}
+extern "C" int cn_act_ext(const float* x, float* y, int64_t n, int act, void* stream) {
+  CN_REQUIRE(act == CN_ACT_RELU6 || act == CN_ACT_SIGMOID, CN_ERR_UNSUPPORTED, "cn_act_ext: activation code %d", act);
+  if (n <= 0) return CN_OK;
+  if (n % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0)
+    act_ext4_kernel<<<grid_for((size_t)n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, (size_t)n / 4, act);
+  else
+    act_ext_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(x, y, (size_t)n, act);
   CN_CHECK_LAUNCH(); return CN_OK;
 }

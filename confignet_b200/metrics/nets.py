@@ -242,22 +242,32 @@ def residual_add(a, b):
     return out
 
 
+def act_ext_(x, act):
+    """in place: ReLU6's clamp behind a conv that ran with ReLU in its epilogue / the sigmoid of the head.  The conv
+    epilogues carry four activation codes only (csrc/common.cuh: a fifth one in the tcgen05 kernel's unrolled epilogue
+    costs the training step 13 %)."""
+    L.call("cn_act_ext", ops._p(x), ops._p(x), x.numel(), act, ops._stream())
+    return x
+
+
 def attribute_classifier_forward(p, x):
     """x: (B,H,W,3) float32 in [-1,1] -> (B, n_attributes) sigmoid probabilities (Dropout is the identity at inference)"""
-    acts = {"relu6": L.ACT_RELU6, None: L.ACT_NONE}
+    acts = {"relu6": L.ACT_RELU, None: L.ACT_NONE}
     with torch.no_grad():
         block_in = x
         for kind, cname, bname, cin, cout, stride, act, add in mobilenet_v2_layers():
             if cname.endswith("_expand") or cname == "expanded_conv_depthwise":
                 block_in = x                                   # first layer of an inverted residual block
             if kind == "dw":
-                x = dwconv3x3(x, p[cname + "/kernel"], p[cname + "/bias"], stride, acts[act])
+                x = dwconv3x3(x, p[cname + "/kernel"], p[cname + "/bias"], stride, L.ACT_RELU6)
             else:
                 x = ops.conv_act(x, p[cname + "/kernel"], p[cname + "/bias"], stride=stride, act=acts[act])
+                if act == "relu6":
+                    x = act_ext_(x, L.ACT_RELU6)
                 if add:
                     x = residual_add(x, block_in)
         feat = ops.global_avg_pool(x)
-        return ops.conv_act(feat, p["dense/kernel"], p["dense/bias"], act=L.ACT_SIGMOID)
+        return act_ext_(ops.conv_act(feat, p["dense/kernel"], p["dense/bias"]), L.ACT_SIGMOID)
 
 
 # ------------------------------------------------------------------------------------------------ image plumbing

@@ -32,8 +32,10 @@ extern "C" {
 #define CN_ACT_LRELU 1
 #define CN_ACT_RELU 2
 #define CN_ACT_TANH 3
-#define CN_ACT_RELU6 4    /* keras ReLU(6.) of MobileNetV2 (metric networks, forward only) */
-#define CN_ACT_SIGMOID 5  /* attribute-classifier head (metrics/celeba_attribute_prediction.py:62), forward only */
+/* two more codes for the metric networks, accepted by cn_dwconv3x3_fwd and cn_act_ext ONLY (the conv / dense entry points
+ * reject them: their epilogues carry the four codes above) */
+#define CN_ACT_RELU6 4    /* keras ReLU(6.) of MobileNetV2 */
+#define CN_ACT_SIGMOID 5  /* attribute-classifier head (metrics/celeba_attribute_prediction.py:62) */
 
 /* kernel selection for the conv / dense family */
 #define CN_IMPL_AUTO 0   /* tcgen05 tensor-core kernel where the shape allows, else CUDA-core */
@@ -257,6 +259,9 @@ int cn_pool2d_fwd(const float* x, int n, int h, int w, int c, int kh, int kw, in
  * (celeba_attribute_prediction.py:55). */
 int cn_dwconv3x3_fwd(const float* x, const float* wk, const float* bias, int n, int h, int w, int c, int stride,
                      int act, float alpha, float* y, void* stream);
+/* y = act(x), act in {CN_ACT_RELU6, CN_ACT_SIGMOID}; x == y allowed.  ReLU(6.) behind a 1x1 conv of MobileNetV2 = the conv
+ * with CN_ACT_RELU in its epilogue, then this clamp. */
+int cn_act_ext(const float* x, float* y, int64_t n, int act, void* stream);
 /* cv2.resize(img, (ow, oh)) with the default INTER_LINEAR on channels-last images: uint8 (is_u8 = 1, OpenCV's fixed-point
  * form, bit-exact) or float32.  replaces celeba_attribute_prediction.py:131-136. */
 int cn_resize_bilinear(const void* x, int n, int h, int w, int c, int oh, int ow, int is_u8, void* y, void* stream);
