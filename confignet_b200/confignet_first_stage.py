@@ -168,6 +168,9 @@ class GeneratorNet(Network):
         return super().__call__(None, inputs["rotation"], zs=zs)
 
 
+GENERATE_CHUNK = 64     # images per generator pass of a large generate_images call (per-sample network: chunking changes no value)
+
+
 class ConfigNetFirstStage(StepGraphs):
     def __init__(self, config, initialize=True, device=None, seed=1234):
         self.config = merge_configs(DEFAULT_CONFIG, config)
@@ -679,6 +682,11 @@ class ConfigNetFirstStage(StepGraphs):
         else:
             zs = [networks._as_dev(latent_vector, dev)] * 5
         rot = networks._as_dev(rotations, dev).reshape(-1, 3)
+        n = rot.shape[0]
+        if n > GENERATE_CHUNK:          # the metric passes generate 1000 images per call (keras predict walks them in batches too)
+            parts = [InferenceGraphs._eager(net, [z[i:i + GENERATE_CHUNK] for z in zs], rot[i:i + GENERATE_CHUNK])
+                     for i in range(0, n, GENERATE_CHUNK)]
+            return torch.cat(parts, dim=0)
         if self.config.get("cuda_graphs", True):
             return self._infer.run(net, zs, rot)
         return InferenceGraphs._eager(net, zs, rot)
