@@ -168,7 +168,7 @@ class GeneratorNet(Network):
         return super().__call__(None, inputs["rotation"], zs=zs)
 
 
-GENERATE_CHUNK = 64     # images per generator pass of a large generate_images call (per-sample network: chunking changes no value)
+GENERATE_CHUNK = 64     # images per generator pass of a large generate_images call (a per-sample network: the batch size only moves last bits)
 
 
 class ConfigNetFirstStage(StepGraphs):

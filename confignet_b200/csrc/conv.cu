@@ -1240,9 +1240,11 @@ igemm_tc_pixel_kernel(const GemmPlan pin, const float* __restrict__ A, const flo
       const bool ok = wrok && Ac_ld != nullptr;
       const int seg = wg.E[2];
       if (seg % TC_BK == 0) wg_load<32>(wg, Ac, ok, woff0, woff1, woff2, en, e0, e1, e2, v);
+#ifndef CN_WG_SEG32_ONLY      // code-size experiment (profiles/r02_m4_wgrad_code_size_ab.txt): only the 32-pixel and the general variant
       else if (seg == 16) wg_load<16>(wg, Ac, ok, woff0, woff1, woff2, en, e0, e1, e2, v);
       else if (seg == 8) wg_load<8>(wg, Ac, ok, woff0, woff1, woff2, en, e0, e1, e2, v);
       else if (seg == 4) wg_load<4>(wg, Ac, ok, woff0, woff1, woff2, en, e0, e1, e2, v);
+#endif
       else wg_load<1>(wg, Ac, ok, woff0, woff1, woff2, en, e0, e1, e2, v);
       e2 += 2 * TC_BK;                                           // the sibling warp takes the next k-block
       while (e2 >= wg.E[2]) {

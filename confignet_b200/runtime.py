@@ -196,6 +196,12 @@ class KerasAdam:
     def _lr_t(self, t):
         return self.lr * math.sqrt(1 - self.b2 ** t) / (1 - self.b1 ** t)
 
+    def reset(self):
+        """back to a freshly constructed optimizer, keeping the moment buffers' addresses (captured graphs hold them)"""
+        self.iterations = 0
+        for m, v in self.state.values():
+            m.zero_(); v.zero_()
+
     def _state(self, g):
         st = self.state.get(id(g))
         if st is None:

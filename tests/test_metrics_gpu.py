@@ -151,11 +151,14 @@ def test_metric_classes_end_to_end(tmp_path):
     assert abs(m.metrics["kid"][0] - kid) <= 5e-3 * abs(kid) and abs(m.metrics["fid"][0] - fid) <= 5e-3 * abs(fid)
     rows = np.loadtxt(tmp_path / "inception_metrics.txt", ndmin=2)
     assert rows.shape == (1, 3) and rows[0, 0] == 0
-    # a metric-sized generate_images call walks the generator in chunks: same bits as small calls (per-sample network)
+    # a metric-sized generate_images call walks the generator in chunks of 64: a chunk equals a call of its own size bit
+    # for bit; against a call of another batch size (other reduction splits) the truncating uint8 cast may move a grey level
     lat, rot = m.sample_latent_vector(66), m.sample_rotations(66)
     big = m.generate_images(lat, rot)
     assert big.shape == (66, 256, 256, 3) and big.dtype == np.uint8
-    assert np.array_equal(big[64:], m.generate_images(lat[64:], rot[64:])) and np.array_equal(big[:3], m.generate_images(lat[:3], rot[:3]))
+    assert np.array_equal(big[64:], m.generate_images(lat[64:], rot[64:]))
+    d = np.abs(big[:3].astype(int) - m.generate_images(lat[:3], rot[:3]).astype(int))
+    assert d.max() <= 1 and (d != 0).mean() < 1e-2
 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")

@@ -442,6 +442,42 @@ def test_fine_tune_replay_equals_eager(dev):
     assert np.array_equal(e_g, e_e) and np.array_equal(r_g, r_e) and np.array_equal(w_g, w_e)
 
 
+def test_fine_tune_state_reused_across_calls_equals_fresh_variables(dev):
+    """The reference builds new variables and a new Adam per fine_tune_on_img call (confignet_second_stage.py:341-358);
+    the product re-initialises the buffers of an earlier call in place and replays the graph that call captured.  A
+    second call on OTHER images (every iteration a replay) must equal, bit for bit, the first call of a fresh model on
+    those images - and an interleaved call with another image count gets its own state."""
+    from confignet_b200.confignet_second_stage import ConfigNet
+    rs = np.random.RandomState(13)
+    imgs_a, imgs_b = (rs.randint(0, 256, (2, RES, RES, 3)).astype(np.uint8) for _ in range(2))
+    imgs_c = rs.randint(0, 256, (1, RES, RES, 3)).astype(np.uint8)
+
+    def fresh(graphs):
+        model = ConfigNet(dict(cfg(graphs), image_loss_weight=5e-4), device=dev)
+        perturb(model, STAGE1_NETS, 801)
+        model.generator_smoothed.group.copy_from(model.generator.group)
+        return model
+
+    def result(model, imgs, **kw):
+        emb, rot = model.fine_tune_on_img(imgs, n_iters=4, **kw)
+        return (emb, rot, [[float(v) for v in d.values()] for d in model.fine_tune_losses],
+                model.generator_fine_tuned.group.flat.detach().cpu().numpy().copy())
+
+    m = fresh(True)
+    result(m, imgs_a)                                    # captures at its third iteration
+    one = result(m, imgs_c)                              # another image count in between: its own variables and graph
+    again = result(m, imgs_b)                            # state of the first call, re-initialised: four replays
+    assert len(m._fine_tune_state) == 2
+    ref_b, ref_c = result(fresh(False), imgs_b), result(fresh(False), imgs_c)
+    for got, want in ((again, ref_b), (one, ref_c)):
+        assert got[2] == want[2]
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[3], want[3])
+    neutral = result(m, imgs_b, force_neutral_expression=True)       # third case: the oldest one is evicted
+    assert len(m._fine_tune_state) == 2 and np.isfinite(neutral[0]).all()
+    want = result(fresh(False), imgs_b, force_neutral_expression=True)
+    assert neutral[2] == want[2] and np.array_equal(neutral[0], want[0])
+
+
 # ------------------------------------------------------------------------------------------------ cache hazards
 def test_eager_calls_between_replays_see_current_weights(dev):
     """The packed-weight cache must not serve a stale image to an eager call that follows a replayed optimizer step
