@@ -14,7 +14,8 @@ torch-CPU restatement of the second-stage / fine-tuning / LatentGAN pieces of th
 PINNING (see oracle/confignet_oracle.py): unpinned against TensorFlow itself; normalized_regression, the stage-2
 latent-discriminator / generator steps (with a stand-in encoder) and the latent_gan_* steps are pinned to the reference's own code executed on TensorFlow stand-ins (tests/golden/reference_float_logic.npz,
 reference_steps.npz); the ResNet50 / VGG16 pieces (keras-applications, not reference code) restate SURVEY.md section 8c
-items 9-11.  Allowed importers: tests/, __graft_entry__.smoke(), bench.py.
+items 9-11 and are pinned (<= 1e-9, fp64) to torchvision's ResNet50 (strides moved to the v1 position) and VGG16 run here
+on the same weights (tests/test_third_party_pins_cpu.py).  Allowed importers: tests/, __graft_entry__.smoke(), bench.py.
 """
 from collections import OrderedDict
 import numpy as np

@@ -193,3 +193,87 @@ def test_attribute_classifier_files_round_trip_without_a_gpu(tmp_path):
     from confignet_b200._lib import CnError
     with pytest.raises((CnError, RuntimeError, AssertionError)):       # no CPU fallback: predicting without CUDA fails loudly
         c2.predict_attributes(np.zeros((1, 128, 128, 3), np.uint8))
+
+
+# ------------------------------------------------------------------------------------------------ third-party cross-check
+def _kernel_to_torch(k):
+    return torch.tensor(np.transpose(k, (3, 2, 0, 1)).copy())
+
+
+def test_oracle_inception_v3_equals_torchvision_with_tf_average_pooling():
+    """keras-applications cannot be executed here, torchvision can: its Inception3 is the same published architecture
+    (Szegedy et al. 2015: stem, 3 x InceptionA, InceptionB, 4 x InceptionC, InceptionD, 2 x InceptionE; BatchNorm eps 1e-3)
+    and differs from the Keras model in ONE layer semantic - its 3x3 average pools count the zero padding, TensorFlow's
+    SAME pooling does not.  With that one function patched and the same weights (BasicConv2d modules in registration order
+    = Keras creation order; BatchNorm weight 1 = scale=False), the oracle's restatement must reproduce torchvision's
+    network: an independent pin of the wiring (branch order, kernel shapes, strides, paddings, concatenation order)."""
+    tv = pytest.importorskip("torchvision")
+    from torchvision.models import inception as tvi
+    raw = nets.init_stand_in(nets.inception_v3_spec(), 11)
+    model = tvi.Inception3(num_classes=3, aux_logits=False, transform_input=False, init_weights=False).double().eval()
+    blocks = [m for m in model.modules() if isinstance(m, tvi.BasicConv2d)]
+    assert len(blocks) == 94
+    with torch.no_grad():
+        for i, b in enumerate(blocks, start=1):
+            k = raw["conv2d_%d/kernel" % i]
+            assert tuple(b.conv.weight.shape) == (k.shape[3], k.shape[2], k.shape[0], k.shape[1]), (i, b.conv.weight.shape, k.shape)
+            b.conv.weight.copy_(_kernel_to_torch(k))
+            q = "batch_normalization_%d" % i
+            assert b.bn.eps == 1e-3
+            b.bn.weight.fill_(1.0)
+            b.bn.bias.copy_(torch.tensor(raw[q + "/beta"]))
+            b.bn.running_mean.copy_(torch.tensor(raw[q + "/moving_mean"]))
+            b.bn.running_var.copy_(torch.tensor(raw[q + "/moving_variance"]))
+    x = torch.tensor(np.random.RandomState(1).uniform(-1, 1, (1, 151, 139, 3)))
+    keep = tvi.F.avg_pool2d
+    tvi.F.avg_pool2d = lambda t, kernel_size, stride=None, padding=0: keep(t, kernel_size, stride, padding, count_include_pad=False)
+    try:
+        with torch.no_grad():
+            t = x.permute(0, 3, 1, 2)
+            for name, layer in model.named_children():          # Inception3._forward without dropout / fc
+                if name in ("AuxLogits", "dropout", "fc"):
+                    continue
+                t = layer(t)
+            want = torch.flatten(t, 1)
+    finally:
+        tvi.F.avg_pool2d = keep
+    got = MO.inception_v3_features(O.to_torch(raw, dtype=torch.float64), x)
+    assert want.shape == got.shape == (1, 2048) and float(want.std()) > 1e-3
+    assert float((want - got).abs().max() / want.abs().max()) < 1e-9
+
+
+def test_oracle_mobilenet_v2_equals_torchvision_on_odd_sizes():
+    """torchvision's MobileNetV2 is the architecture of the paper's table 2, as keras-applications' is; the two differ in
+    the padding of the stride-2 layers (torch pads 1 on both sides, Keras pads by correct_pad() = TF SAME) and in the
+    BatchNorm epsilon.  On an input whose size stays odd down the network (97 -> 49 -> 25 -> 13 -> 7) correct_pad() is (1, 1)
+    too, so with eps set to 1e-3 and the same weights the oracle's restatement must reproduce torchvision's features:
+    an independent pin of the block table, the expansion / depthwise / projection order and the residual rule."""
+    pytest.importorskip("torchvision")
+    from torchvision.models import mobilenetv2 as tvm
+    n_attr = 5
+    raw = nets.init_stand_in(nets.attribute_classifier_spec(n_attr), 12)
+    model = tvm.MobileNetV2(num_classes=3).double().eval()
+    convs = [m for m in model.features.modules() if isinstance(m, torch.nn.Conv2d)]
+    bns = [m for m in model.features.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    layers = nets.mobilenet_v2_layers()
+    assert len(convs) == len(bns) == len(layers) == 52
+    with torch.no_grad():
+        for (kind, cname, bname, cin, cout, stride, act, add), conv, bn in zip(layers, convs, bns):
+            if kind == "dw":
+                k = raw[cname + "/depthwise_kernel"]                      # (3,3,C,1) -> (C,1,3,3)
+                w = torch.tensor(np.transpose(k, (2, 3, 0, 1)).copy())
+                assert conv.groups == cin and conv.stride == (stride, stride)
+            else:
+                w = _kernel_to_torch(raw[cname + "/kernel"])
+                assert conv.groups == 1 and conv.stride == (stride, stride)
+            assert tuple(conv.weight.shape) == tuple(w.shape), (cname, conv.weight.shape, w.shape)
+            conv.weight.copy_(w)
+            bn.eps = 1e-3
+            bn.weight.copy_(torch.tensor(raw[bname + "/gamma"])); bn.bias.copy_(torch.tensor(raw[bname + "/beta"]))
+            bn.running_mean.copy_(torch.tensor(raw[bname + "/moving_mean"])); bn.running_var.copy_(torch.tensor(raw[bname + "/moving_variance"]))
+    x = torch.tensor(np.random.RandomState(2).uniform(-1, 1, (2, 97, 97, 3)))
+    with torch.no_grad():
+        want = model.features(x.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    got = MO.mobilenet_v2_features(O.to_torch(raw, dtype=torch.float64), x)
+    assert tuple(got.shape) == tuple(want.shape) == (2, 4, 4, 1280) and float(want.std()) > 1e-3
+    assert float((want - got).abs().max() / want.abs().max()) < 1e-9
