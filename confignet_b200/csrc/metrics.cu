@@ -56,6 +56,65 @@ __global__ void pool2d_fwd_kernel(const float* __restrict__ x, int h, int w, int
   }
 }
 
+// 3x3 windows, four channels x a strip of TX output pixels per thread: a stride-1 strip of 4 reads 6 columns per row
+// instead of 12 (4.5 loads per output instead of 9), every row's loads are issued together.  The one-pixel-per-thread form
+// above ran the stride-1 average pool of InceptionV3 at 0.24 of the HBM rate (profiles/r02_m6_metric_kernels_hbm.txt).
+template <int STRIDE, int MODE, int TX>
+__global__ void __launch_bounds__(256)
+pool3x3_strip_kernel(const float* __restrict__ x, int h, int w, int c, int pad_t, int pad_l, int oh, int ow,
+                     float* __restrict__ y, int ldy, size_t total) {
+  constexpr int NC = (TX - 1) * STRIDE + 3;
+  const int c4 = c >> 2, nxs = (ow + TX - 1) / TX;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c4) * 4; size_t t = i / c4;
+    const int ox0 = (int)(t % nxs) * TX; t /= nxs;
+    const int oy = (int)(t % oh); const size_t n = t / oh;
+    const int y0 = oy * STRIDE - pad_t, x0 = ox0 * STRIDE - pad_l;
+    float4 acc[TX];
+#pragma unroll
+    for (int j = 0; j < TX; ++j) acc[j] = MODE == CN_POOL_MAX ? make_float4(-3.402823466e38f, -3.402823466e38f, -3.402823466e38f, -3.402823466e38f)
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    int rows = 0;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = y0 + ky;
+      if ((unsigned)iy >= (unsigned)h) continue;
+      ++rows;
+      const float* row = x + ((n * h + iy) * w) * (size_t)c + ch;
+      float4 v[NC];
+#pragma unroll
+      for (int q = 0; q < NC; ++q) {
+        const int ix = x0 + q;
+        v[q] = (unsigned)ix < (unsigned)w ? cn_ldg4_ordered(row + (size_t)ix * c)
+                                          : (MODE == CN_POOL_MAX ? make_float4(-3.402823466e38f, -3.402823466e38f, -3.402823466e38f, -3.402823466e38f)
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+#pragma unroll
+      for (int j = 0; j < TX; ++j)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4 f = v[j * STRIDE + kx];
+          if (MODE == CN_POOL_MAX) { acc[j].x = fmaxf(acc[j].x, f.x); acc[j].y = fmaxf(acc[j].y, f.y); acc[j].z = fmaxf(acc[j].z, f.z); acc[j].w = fmaxf(acc[j].w, f.w); }
+          else { acc[j].x += f.x; acc[j].y += f.y; acc[j].z += f.z; acc[j].w += f.w; }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < TX; ++j) {
+      const int ox = ox0 + j;
+      if (ox >= ow) break;
+      float4 o = acc[j];
+      if (MODE != CN_POOL_MAX) {
+        int cols = 0;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) cols += (unsigned)(ox * STRIDE - pad_l + kx) < (unsigned)w ? 1 : 0;
+        const float d = (float)(rows * cols > 0 ? rows * cols : 1);
+        o.x = o.x / d; o.y = o.y / d; o.z = o.z / d; o.w = o.w / d;
+      }
+      *reinterpret_cast<float4*>(y + ((n * oh + oy) * ow + ox) * (size_t)ldy + ch) = o;
+    }
+  }
+}
+
 extern "C" int cn_pool2d_fwd(const float* x, int n, int h, int w, int c, int kh, int kw, int stride, int pad_t, int pad_l,
                              int oh, int ow, int mode, float* y, int ldy, void* stream) {
   CN_REQUIRE(n >= 0 && h > 0 && w > 0 && c > 0 && kh > 0 && kw > 0 && stride > 0 && oh > 0 && ow > 0 && ldy >= c,
@@ -67,6 +126,16 @@ extern "C" int cn_pool2d_fwd(const float* x, int n, int h, int w, int c, int kh,
              "cn_pool2d_fwd: a window of the %dx%d output lies outside the %dx%d input", oh, ow, h, w);
   if (n == 0) return CN_OK;
   const bool vec = c % 4 == 0 && ldy % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0;
+  if (vec && kh == 3 && kw == 3 && (stride == 1 || stride == 2)) {
+    constexpr int TX = 4;
+    const size_t items = (size_t)n * oh * ((ow + TX - 1) / TX) * (c / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stride == 1 && mode == CN_POOL_MAX) pool3x3_strip_kernel<1, CN_POOL_MAX, TX><<<grid_for(items), 256, 0, st>>>(x, h, w, c, pad_t, pad_l, oh, ow, y, ldy, items);
+    else if (stride == 1) pool3x3_strip_kernel<1, CN_POOL_AVG_VALID, TX><<<grid_for(items), 256, 0, st>>>(x, h, w, c, pad_t, pad_l, oh, ow, y, ldy, items);
+    else if (mode == CN_POOL_MAX) pool3x3_strip_kernel<2, CN_POOL_MAX, TX><<<grid_for(items), 256, 0, st>>>(x, h, w, c, pad_t, pad_l, oh, ow, y, ldy, items);
+    else pool3x3_strip_kernel<2, CN_POOL_AVG_VALID, TX><<<grid_for(items), 256, 0, st>>>(x, h, w, c, pad_t, pad_l, oh, ow, y, ldy, items);
+    CN_CHECK_LAUNCH(); return CN_OK;
+  }
   const size_t total = (size_t)n * oh * ow * (vec ? c / 4 : c);
   if (vec)
     pool2d_fwd_kernel<4><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, h, w, c, kh, kw, stride, pad_t, pad_l, oh, ow, mode, y, ldy, total);
@@ -120,6 +189,58 @@ __global__ void dwconv3x3_fwd_kernel(const float* __restrict__ x, const float* _
   }
 }
 
+// the same strip form for the depthwise convolution: four channels x TX output pixels per thread, the nine kernel quads
+// in registers, one row of (TX - 1) * STRIDE + 3 input quads in flight at a time
+template <int STRIDE, int TX>
+__global__ void __launch_bounds__(256)
+dwconv3x3_strip_kernel(const float* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ bias, int h, int w, int c,
+                       int pad_t, int pad_l, int oh, int ow, int act, float alpha, float* __restrict__ y, size_t total) {
+  constexpr int NC = (TX - 1) * STRIDE + 3;
+  const int c4 = c >> 2, nxs = (ow + TX - 1) / TX;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c4) * 4; size_t t = i / c4;
+    const int ox0 = (int)(t % nxs) * TX; t /= nxs;
+    const int oy = (int)(t % oh); const size_t n = t / oh;
+    const int y0 = oy * STRIDE - pad_t, x0 = ox0 * STRIDE - pad_l;
+    float4 acc[TX];
+#pragma unroll
+    for (int j = 0; j < TX; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = y0 + ky;
+      if ((unsigned)iy >= (unsigned)h) continue;
+      const float* row = x + ((n * h + iy) * w) * (size_t)c + ch;
+      float4 v[NC];
+#pragma unroll
+      for (int q = 0; q < NC; ++q) {
+        const int ix = x0 + q;
+        v[q] = (unsigned)ix < (unsigned)w ? cn_ldg4_ordered(row + (size_t)ix * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4 g = *reinterpret_cast<const float4*>(wk + (ky * 3 + kx) * c + ch);
+#pragma unroll
+        for (int j = 0; j < TX; ++j) {
+          const float4 f = v[j * STRIDE + kx];
+          acc[j].x = fmaf(f.x, g.x, acc[j].x); acc[j].y = fmaf(f.y, g.y, acc[j].y);
+          acc[j].z = fmaf(f.z, g.z, acc[j].z); acc[j].w = fmaf(f.w, g.w, acc[j].w);
+        }
+      }
+    }
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) b = *reinterpret_cast<const float4*>(bias + ch);
+#pragma unroll
+    for (int j = 0; j < TX; ++j) {
+      const int ox = ox0 + j;
+      if (ox >= ow) break;
+      float4 o;
+      o.x = cn_apply_act_ext(acc[j].x + b.x, act, alpha); o.y = cn_apply_act_ext(acc[j].y + b.y, act, alpha);
+      o.z = cn_apply_act_ext(acc[j].z + b.z, act, alpha); o.w = cn_apply_act_ext(acc[j].w + b.w, act, alpha);
+      *reinterpret_cast<float4*>(y + ((n * oh + oy) * ow + ox) * (size_t)c + ch) = o;
+    }
+  }
+}
+
 extern "C" int cn_dwconv3x3_fwd(const float* x, const float* wk, const float* bias, int n, int h, int w, int c, int stride,
                                 int act, float alpha, float* y, void* stream) {
   CN_REQUIRE(n >= 0 && h > 0 && w > 0 && c > 0 && (stride == 1 || stride == 2), CN_ERR_BAD_SHAPE,
@@ -129,6 +250,13 @@ extern "C" int cn_dwconv3x3_fwd(const float* x, const float* wk, const float* bi
   const int tot_h = (oh - 1) * stride + 3 - h, tot_w = (ow - 1) * stride + 3 - w;       // TF SAME: the smaller half in front
   const int pad_t = (tot_h > 0 ? tot_h : 0) / 2, pad_l = (tot_w > 0 ? tot_w : 0) / 2;
   const bool vec = c % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)wk % 16) == 0;
+  if (vec && (bias == nullptr || ((uintptr_t)bias % 16) == 0)) {
+    constexpr int TX = 4;
+    const size_t items = (size_t)n * oh * ((ow + TX - 1) / TX) * (c / 4);
+    if (stride == 1) dwconv3x3_strip_kernel<1, TX><<<grid_for(items), 256, 0, (cudaStream_t)stream>>>(x, wk, bias, h, w, c, pad_t, pad_l, oh, ow, act, alpha, y, items);
+    else dwconv3x3_strip_kernel<2, TX><<<grid_for(items), 256, 0, (cudaStream_t)stream>>>(x, wk, bias, h, w, c, pad_t, pad_l, oh, ow, act, alpha, y, items);
+    CN_CHECK_LAUNCH(); return CN_OK;
+  }
   const size_t total = (size_t)n * oh * ow * (vec ? c / 4 : c);
   if (vec)
     dwconv3x3_fwd_kernel<4><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, wk, bias, h, w, c, stride, pad_t, pad_l, oh, ow, act, alpha, y, total);
