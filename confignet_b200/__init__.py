@@ -7,6 +7,9 @@ import sys
 from .confignet_first_stage import ConfigNetFirstStage, DEFAULT_CONFIG, merge_configs  # noqa: F401
 from .confignet_second_stage import ConfigNet  # noqa: F401
 from .latent_gan import LatentGAN  # noqa: F401
+from .metrics.inception_distance import InceptionFeatureExtractor, compute_FID, compute_KID  # noqa: F401
+from .metrics.metrics import InceptionMetrics, ControllabilityMetrics  # noqa: F401
+from .metrics.celeba_attribute_prediction import CelebaAttributeClassifier  # noqa: F401
 
 
 def load_confignet(model_path, **kw):

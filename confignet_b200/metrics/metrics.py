@@ -1,8 +1,8 @@
 """ControllabilityMetrics and InceptionMetrics (reference metrics/metrics.py): the host logic of the reference - which face
 model parameter is overwritten in which latent slice, which attribute columns are compared, how the scores are combined and
 which files are written - around the B200 networks (generator, encoders, InceptionV3, MobileNetV2).  TensorBoard / AzureML
-logging, the matplotlib plot and the per-image OpenCV dumps are out of scope; the JSON /
-text files a resumed run or a plotting script reads are written as the reference writes them."""
+logging and the matplotlib plot are out of scope; the JSON / text files a resumed run or a
+plotting script reads and the per-image PNG dumps of get_metrics are written as the reference writes them."""
 import json
 import os
 import numpy as np
@@ -102,8 +102,19 @@ class ControllabilityMetrics:
         return self.get_metrics_for_attribute_pairs(set_attributes, not_set_attributes, attribute_config)
 
     def get_metrics(self, input_images, img_output_dir=None):
-        """metrics.py:139-156 (the per-image PNG dumps of img_output_dir are out of scope)"""
-        _, images_with_attributes, images_without_attributes = self.generate_images_for_metric(input_images)
+        """metrics.py:139-156; with ``img_output_dir`` every input, its reconstruction and the two images of every attribute
+        configuration are written as PNG files under the reference's names (OpenCV, imported on demand)"""
+        raw_decoded_images, images_with_attributes, images_without_attributes = self.generate_images_for_metric(input_images)
+        if img_output_dir is not None:
+            import cv2
+            os.makedirs(img_output_dir, exist_ok=True)
+            for i in range(len(input_images)):
+                cv2.imwrite(os.path.join(img_output_dir, "gt_img_%04d.png" % i), np.asarray(input_images[i]))
+                cv2.imwrite(os.path.join(img_output_dir, "raw_img_%04d.png" % i), raw_decoded_images[i])
+                for config_name, _ in ControllabilityMetricConfigs.all_configs():
+                    cv2.imwrite(os.path.join(img_output_dir, "%s_img_%04d.png" % (config_name, i)), images_with_attributes[config_name][i])
+                    cv2.imwrite(os.path.join(img_output_dir, "%s_img_not_set_%04d.png" % (config_name, i)),
+                                images_without_attributes[config_name][i])
         return self.get_metrics_from_attribute_images(images_with_attributes, images_without_attributes)
 
     def get_metrics_from_attribute_images(self, images_with_attributes, images_without_attributes):

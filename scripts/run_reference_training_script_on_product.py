@@ -16,6 +16,7 @@ This container has no GPU and the product has no CPU fallback, so the run is don
 Build container only (/root/reference is read at run time):  python scripts/run_reference_training_script_on_product.py
 """
 import importlib
+import json
 import os
 import pickle
 import sys
@@ -201,6 +202,7 @@ def main():
         print("3. train_latent_gan.py loaded the product checkpoint through the reference's load_confignet and reached the "
               "first kernel of encode_images: %s" % str(e).splitlines()[0][:80])
     gcalls = []
+    real_encode_images = confignet_b200.ConfigNet.encode_images
     confignet_b200.ConfigNet.encode_images = lambda self, imgs: (np.zeros((imgs.shape[0], 145), np.float32), np.zeros((imgs.shape[0], 3), np.float32))
     confignet_b200.LatentGAN.discriminator_training_step = lambda self, emb, opt: gcalls.append(["d", tuple(emb.shape)]) or {"loss_sum": 1.0}
     confignet_b200.LatentGAN.generator_training_step = lambda self, opt: gcalls.append(["g"]) or {"loss_sum": 2.0}
@@ -209,7 +211,63 @@ def main():
     assert gcalls == [["d", (2, 145)], ["g"], ["ema"]], gcalls                  # the test dataset holds two images
     assert sorted(os.listdir(os.path.join(out3, "checkpoints"))) == ["000000.json", "000000.npz"]
     print("   ... and, with the steps recorded, ran its loop and left checkpoints/000000.{json,npz}")
+    # ---- 4. evaluation/evaluate_confignet_controllability.py (the body of tests/evaluation_test.py::test_confignet_evaluation)
+    #         on the stage-2 checkpoint of phase 2 and the classifier file pair: confignet.ControllabilityMetrics is the
+    #         product's class.  Unmodified it must fail loudly at the first kernel; with the four device entry points it calls
+    #         replaced by deterministic stand-ins its host logic runs through and leaves the reference's output files.
+    pkg.ControllabilityMetrics = confignet_b200.ControllabilityMetrics
+    sys.path.insert(0, os.path.join(REF, "evaluation"))
+    evaluate = importlib.import_module("evaluate_confignet_controllability")
+    out4 = tempfile.mkdtemp(prefix="cn_eval4_")
+    confignet_b200.ConfigNet.encode_images = real_encode_images                  # phase 3's stand-in: back to the real method
+    for n_iters in (0, 1):
+        eval_args = ("--model_path %s --test_set_path %s --output_dir %s --attribute_classifier_path %s --n_samples 2 "
+                     "--n_fine_tuning_iters %d --write_images"
+                     % (os.path.join(out2, "checkpoints", "000000.json"), os.path.join(ASSETS, "test_dataset_res_256.pck"), out4,
+                        os.path.join(out2, "no_classifier.json"), n_iters)).split(" ")
+        if n_iters == 0:
+            try:
+                evaluate.parse_args(eval_args)
+                raise SystemExit("the product computed metrics without CUDA - there must be no CPU fallback")
+            except L.CnError as e:
+                import traceback
+                frames = [f.name for f in traceback.extract_tb(e.__traceback__)]
+                assert "get_metrics" in frames and "generate_images_for_metric" in frames and "encode_images" in frames, frames
+                print("4. evaluate_confignet_controllability.py built the product's ControllabilityMetrics and reached the first "
+                      "kernel of encode_images: %s" % str(e).splitlines()[0][:70])
+            ecalls = []
+            rs = np.random.RandomState(0)
+            confignet_b200.ConfigNet.encode_images = lambda self, imgs: (ecalls.append(["encode", len(imgs)]), (rs.randn(len(imgs), 145).astype(np.float32), np.zeros((len(imgs), 3), np.float32)))[1]
+            confignet_b200.ConfigNet.fine_tune_on_img = lambda self, imgs, n_iters=50, **kw: (ecalls.append(["fine_tune", len(imgs), n_iters]), (rs.randn(len(imgs), 145).astype(np.float32), np.zeros((len(imgs), 3), np.float32)))[1]
+            confignet_b200.ConfigNet.generate_images = lambda self, lat, rot: (ecalls.append(["generate", len(lat)]), rs.randint(0, 256, (len(lat), 256, 256, 3)).astype(np.uint8))[1]
+            from confignet_b200.confignet_first_stage import SyntheticEncoderNet
+            SyntheticEncoderNet.predict = lambda self, params: (ecalls.append(["synthetic_encoder", len(params)]), rs.randn(1, 145).astype(np.float32))[1]
+            from confignet_b200.metrics import CelebaAttributeClassifier as Clf
+            Clf.predict_attributes = lambda self, imgs: (ecalls.append(["predict_attributes", len(imgs)]), rs.rand(len(imgs), len(self.config["predicted_attributes"])).astype(np.float32))[1]
+            # the stand-in classifier of phase 2 predicts two attributes; the metric configurations name CelebA's
+            with open(os.path.join(out2, "no_classifier.json")) as fp:
+                meta = json.load(fp)
+            meta["config"]["predicted_attributes"] = ["Black_Hair", "Blond_Hair", "Brown_Hair", "Gray_Hair", "Mouth_Slightly_Open", "Smiling",
+                                                      "Narrow_Eyes", "Mustache", "No_Beard", "Goatee", "Sideburns", "Young"]
+            Clf({"input_shape": [128, 128, 3], "predicted_attributes": meta["config"]["predicted_attributes"]}, device="cpu").save(out2, "no_classifier")
+        ecalls.clear()
+        evaluate.parse_args(eval_args)
+        name = "contr_metrics_tuning_iters_%d_000000" % n_iters
+        produced = sorted(os.listdir(out4))
+        assert name + ".json" in produced and name + ".csv" in produced and name in produced, produced
+        with open(os.path.join(out4, name + ".json")) as fp:
+            m = json.load(fp)
+        assert len(m) == 10 and "controllability" in m and len(m["smile_config"]) == 4, sorted(m)
+        assert np.loadtxt(os.path.join(out4, name + ".csv"), delimiter=",").shape == (4, 9)          # 8 configurations + their mean
+        assert os.path.isdir(os.path.join(out4, name))        # --write_images (cv2 is a stub in this harness; the PNG dump itself: tests/test_metrics_cpu.py)
+        kinds = [c[0] for c in ecalls]
+        if n_iters == 0:
+            assert kinds.count("encode") == 1 and kinds.count("generate") == 1 + 16 and kinds.count("predict_attributes") == 16, kinds
+        else:
+            assert kinds.count("fine_tune") == 2 and kinds.count("generate") == 2 * (1 + 16) and ["fine_tune", 1, 1] in ecalls, kinds
+    print("   ... and, with the device entry points replaced, wrote contr_metrics_tuning_iters_{0,1}_000000.{json,csv}")
     import shutil
+    shutil.rmtree(out4, ignore_errors=True)
     shutil.rmtree(out3, ignore_errors=True)
     shutil.rmtree(out1, ignore_errors=True)
     shutil.rmtree(out2, ignore_errors=True)

@@ -61,6 +61,12 @@ def test_controllability_metrics_host_logic_matches_the_executed_reference(tmp_p
     assert list(got.keys()) == list(want.keys())
     for k in want:
         assert np.allclose(np.asarray(got[k], np.float64), np.asarray(want[k], np.float64), rtol=1e-12, atol=1e-15), k
+    if iters == 0:        # get_metrics(img_output_dir=...): the reference's per-image PNG dumps (metrics.py:141-154)
+        cv2 = pytest.importorskip("cv2")
+        cm.get_metrics(GOLD["contr_input_images"], img_output_dir=str(tmp_path / "imgs"))
+        files = sorted(os.listdir(tmp_path / "imgs"))
+        assert len(files) == 5 * (2 + 2 * 8) and "gt_img_0000.png" in files and "smile_config_img_not_set_0004.png" in files
+        assert np.array_equal(cv2.imread(str(tmp_path / "imgs" / "gt_img_0003.png")), GOLD["contr_input_images"][3])
     pair = cm.get_metrics_for_attribute_pairs(FK.fake_predict_attributes(GOLD["contr_input_images"]),
                                               FK.fake_predict_attributes(GOLD["contr_input_images"][::-1]),
                                               ControllabilityMetricConfigs.smile_config)
