@@ -352,7 +352,8 @@ class ConfigNet(ConfigNetFirstStage):
 
     def generate_images(self, latent_vectors, rotations):
         """confignet_second_stage.py:310-319 -> uint8 (B,H,W,3)."""
-        return self.generate_images_device(latent_vectors, rotations).cpu().numpy()
+        net = self.generator_fine_tuned if self.generator_fine_tuned is not None else self.generator_smoothed
+        return self._to_host(self._generate_u8(net, latent_vectors, rotations, borrow=True))
 
     def generate_images_device(self, latent_vectors, rotations):
         net = self.generator_fine_tuned if self.generator_fine_tuned is not None else self.generator_smoothed

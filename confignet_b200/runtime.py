@@ -356,8 +356,10 @@ class InferenceGraphs:
         d["rotation"] = rot
         return ops.to_uint8(net.predict_device(d))
 
-    def run(self, net, zs, rot):
-        """zs: 5 device tensors (B, latent); rot: (B, 3) device tensor of Euler angles -> uint8 (B, H, W, 3) device tensor"""
+    def run(self, net, zs, rot, borrow=False):
+        """zs: 5 device tensors (B, latent); rot: (B, 3) device tensor of Euler angles -> uint8 (B, H, W, 3) device tensor.
+        ``borrow``: return the graph's own output buffer (valid until the next replay) instead of a copy - for a caller that
+        moves it to the host right away."""
         B = zs[0].shape[0]
         if not GraphedFn.ENABLED or B > self.MAX_BATCH or ops.PROFILE[0] is not None or not zs[0].is_cuda:
             return self._eager(net, zs, rot)
@@ -401,7 +403,7 @@ class InferenceGraphs:
         e["rot"].copy_(rot, non_blocking=True)
         e["graph"].replay()
         GraphedFn.REPLAYED_LAUNCHES += e["launches"]
-        return e["out"].clone()
+        return e["out"] if borrow else e["out"].clone()
 
 
 def release_graphs():
