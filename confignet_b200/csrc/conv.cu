@@ -2004,7 +2004,7 @@ colsum4_kernel(const float* __restrict__ g, int rows, int n, int per, float* __r
 // n4 = elements / 4 (the slabs are 16-byte aligned and cn % 4 == 0 on this path).
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ ws, int nsplit, size_t n4, int cn4, const float* __restrict__ bias,
-                     float* __restrict__ out) {
+                     float* __restrict__ out, int act, float alpha) {
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n4) return;
   float4 a = cn_ldg4_ordered(ws + 4 * i);
@@ -2024,18 +2024,22 @@ splitk_reduce_kernel(const float* __restrict__ ws, int nsplit, size_t n4, int cn
     const float4 b = reinterpret_cast<const float4*>(bias)[i % (size_t)cn4];
     a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
   }
+  if (act != CN_ACT_NONE) {
+    a.x = cn_apply_act(a.x, act, alpha); a.y = cn_apply_act(a.y, act, alpha);
+    a.z = cn_apply_act(a.z, act, alpha); a.w = cn_apply_act(a.w, act, alpha);
+  }
   reinterpret_cast<float4*>(out)[i] = a;
 }
 // scalar form for outputs whose size or channel count is not a multiple of 4
 __global__ void __launch_bounds__(256)
 splitk_reduce1_kernel(const float* __restrict__ ws, int nsplit, size_t n, int cn, const float* __restrict__ bias,
-                      float* __restrict__ out) {
+                      float* __restrict__ out, int act, float alpha) {
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   float a = ws[i];
   for (int z = 1; z < nsplit; ++z) a += ws[(size_t)z * n + i];
   if (bias != nullptr) a += bias[i % (size_t)cn];
-  out[i] = a;
+  out[i] = cn_apply_act(a, act, alpha);
 }
 // out[i] = sum_b part[b][i] for MANY slabs of FEW outputs (per-block partials of the small weight / bias gradients):
 // block (32, 8) - thread (x, y) adds the slabs y, y+8, ... of output 32*blockIdx.x + x in order, then the 8 rows are
@@ -2147,6 +2151,8 @@ static int g_persistent = 1;   // persistent CTAs in the tcgen05 pixel kernel (c
 extern "C" int cn_debug_set_persistent(int v) { g_persistent = v; return CN_OK; }
 #endif
 static int g_fold = 1;     // folded upsample+conv plans (cn_debug_set_fold)
+static int g_act_split = [] { const char* e = getenv("CN_ACT_SPLIT"); return e ? atoi(e) : 1; }();     // split-K of launches with a fused activation (A/B knob)
+static int g_fold_split = [] { const char* e = getenv("CN_FOLD_SPLIT"); return e ? atoi(e) : 1; }();   // split-K of the folded forward at small batch (A/B knob)
 static int g_s2all = 1;    // all parity phases of a stride-2 dgrad in one launch
 #ifdef CN_TEST_HOOKS
 extern "C" int cn_debug_set_fold(int fold, int s2all) { g_fold = fold; g_s2all = s2all; return CN_OK; }
@@ -2365,12 +2371,13 @@ int cn_sum_slabs(const float* part, int nslabs, int n, float* out, cudaStream_t 
   return CN_OK;
 }
 
-static int launch_splitk_reduce(const float* ws, int nsplit, size_t n, int cn, const float* bias, float* out, cudaStream_t st) {
+static int launch_splitk_reduce(const float* ws, int nsplit, size_t n, int cn, const float* bias, float* out, cudaStream_t st,
+                                int act = CN_ACT_NONE, float alpha = 0.f) {
   if ((n & 3) == 0 && (cn & 3) == 0 && ((uintptr_t)out & 15) == 0 && (bias == nullptr || ((uintptr_t)bias & 15) == 0)) {
     const size_t n4 = n >> 2;
-    splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(ws, nsplit, n4, cn >> 2, bias, out);
+    splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(ws, nsplit, n4, cn >> 2, bias, out, act, alpha);
   } else {
-    splitk_reduce1_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, nsplit, n, cn, bias, out);
+    splitk_reduce1_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, nsplit, n, cn, bias, out, act, alpha);
   }
   CN_CHECK_LAUNCH();
   return CN_OK;
@@ -2461,7 +2468,8 @@ static int launch_tc(const GemmPlan& g, const float* src, const float* packed, c
   return CN_OK;
 }
 
-// zero_mode: 0 = this launch covers all of dst and may run split-K (slabs + ordered reduction), 2 = no split-K allowed
+// zero_mode: 0 = this launch covers all of dst and may run split-K (slabs + ordered reduction), 2 = no split-K allowed,
+// 3 = phased plan covering all of dst in this one launch: split-K allowed when its phases have equal tap counts
 static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const float* w, const float* bias,
                         float* dst, int act, float alpha, int impl, cudaStream_t st, int zero_mode = 0,
                         const float* w_ident = nullptr) {
@@ -2479,7 +2487,21 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
     int per = total_kb, split = 1;
     const size_t out_elems = (size_t)g.n_img * g.Q[0] * g.Q[1] * g.Q[2] * g.Cn;
     float* ws = nullptr;
-    if (nph == 1 && act == CN_ACT_NONE && zero_mode == 0 && g.ostride == 1 && (int)(grid.x * grid.y) < 4 * num_sms() && total_kb >= 32) {
+    // zero_mode 3: a phased plan whose ONE launch writes every pixel of dst (the sub-pixel phases of a folded upsample + conv)
+    // and whose phases all have the same number of taps - every split of every phase then has k-blocks to work on and every
+    // slab is written completely.  At batch 1 (generate_images, the demo loop) the folded 3-D convs of the generator are
+    // 16 / 32 tiles of 128 / 64 k-blocks on 148 SMs: 265 + 164 us of a 0.83 ms call (profiles/r02_m7_generate_timeline_b1.txt).
+    bool phased_split = false;
+    if (zero_mode == 3 && nph > 1) {
+      phased_split = true;
+      for (int ph = 1; ph < nph; ++ph) phased_split = phased_split && g.ph_ntaps[ph] == g.ph_ntaps[0];
+    }
+    // A fused activation does not rule split-K out: the slabs hold raw sums and splitk_reduce_kernel finishes them (bias,
+    // activation).  g_act_split: 0 = only activation-free launches split (rounds 1-2), 1 = launches with an activation too
+    // when their tiles do not fill one wave of SMs (the small-batch path), 2 = under the same rule as activation-free ones.
+    const int tiles = (int)(grid.x * grid.y);
+    const bool act_ok = act == CN_ACT_NONE || g_act_split == 2 || (g_act_split == 1 && tiles < num_sms());
+    if (((nph == 1 && zero_mode == 0 && g.ostride == 1) || phased_split) && act_ok && tiles < 4 * num_sms() && total_kb >= 32) {
       // split-K without atomics: every split writes its own slab, splitk_reduce_kernel adds them in order (+ bias)
       split = pick_split((int)(grid.x * grid.y), total_kb, total_kb / 16);
       per = (total_kb + split - 1) / split;
@@ -2505,7 +2527,7 @@ static int launch_pixel(const GemmPlan& g, bool b_mn, const float* src, const fl
     if (b_mn) rc = launch_tc<1, 0>(g, src, wp, bias, tdst, act, alpha, bn, bn_smem, grid, per, split, st, out_elems);
     else rc = launch_tc<0, 0>(g, src, wp, bias, tdst, act, alpha, bn, bn_smem, grid, per, split, st, out_elems);
     if (rc) return rc;
-    if (split > 1) return launch_splitk_reduce(ws, split, out_elems, g.Cn, bias, dst, st);
+    if (split > 1) return launch_splitk_reduce(ws, split, out_elems, g.Cn, bias, dst, st, act, alpha);
     return CN_OK;
   }
   // CUDA-core path
@@ -2606,7 +2628,7 @@ extern "C" int cn_conv_fwd(const cn_conv_desc* d, const float* x, const float* w
         fold_weights_kernel<<<dim3((cc / 4 + 255) / 256, fi->nfold), 256, 0, st>>>(w, fi->d_spec, d->ksize[1], d->ksize[2], cc / 4, wf);
         CN_CHECK_LAUNCH();
       }
-      return launch_pixel(g, true, x, wf, bias, y, act, alpha, CN_IMPL_TC, st, 2, w);
+      return launch_pixel(g, true, x, wf, bias, y, act, alpha, CN_IMPL_TC, st, g_fold_split ? 3 : 2, w);
     }
   }
   rc = get_plan(d, KIND_FWD, 0, &g); if (rc) return rc;

@@ -63,7 +63,9 @@ TCS = [(2, 2, (16, 16), 64, 64, 3, 1, 1), (2, 2, (16, 16), 32, 32, 4, 1, 1), (2,
        (2, 4, (16, 16), 512, 256, 4, 1, 1), (0, 256, (), 256, 512, 1, 1, 1),
        # folded upsample+conv (phased forward, folded dgrad, folded wgrad + unfold) at sizes the tensor-core path takes
        (2, 4, (16, 16), 64, 32, 4, 1, 2), (3, 4, (4, 4, 4), 64, 32, 3, 1, 2), (3, 2, (8, 8, 8), 32, 64, 3, 1, 2),
-       (2, 3, (16, 32), 32, 32, 4, 1, 2), (2, 2, (32, 32), 192, 384, 3, 2, 1)]
+       (2, 3, (16, 32), 32, 32, 4, 1, 2), (2, 2, (32, 32), 192, 384, 3, 2, 1),
+       # the generator's folded 3-D convs at generate_images batch sizes: split-K over the equal-length sub-pixel phases
+       (3, 2, (8, 8, 8), 256, 128, 3, 1, 2)]
 
 
 @pytest.mark.parametrize("cfg", SMALL)
@@ -76,6 +78,29 @@ def test_conv_cuda_core(dev, cfg):
 def test_conv_tcgen05(dev, cfg):
     from confignet_b200 import _lib as L
     _conv_case(dev, L.IMPL_TC, TOL_TC, *cfg)
+
+
+@pytest.mark.parametrize("cfg", [(3, 1, (4, 4, 4), 512, 256, 3, 1, 2), (3, 1, (8, 8, 8), 256, 128, 3, 1, 2), (3, 1, (16, 16, 16), 128, 64, 3, 1, 1),
+                                 (2, 1, (16, 16), 1024, 512, 1, 1, 1), (2, 1, (16, 16), 512, 256, 4, 1, 1), (2, 2, (16, 16), 256, 64, 4, 1, 2)])
+@pytest.mark.parametrize("act", ["lrelu", "none"])
+def test_conv_small_batch_split_k_with_activation(dev, cfg, act):
+    """generate_images at batch 1-2: a handful of tiles with hundreds of k-blocks each.  These launches split K across the SMs
+    (slabs + ordered reduction) also when the layer carries a fused LeakyReLU - the reduction kernel applies bias and
+    activation - and, for the folded upsample + conv, over the equal-length sub-pixel phases of the one phased launch."""
+    from confignet_b200 import ops, _lib as L
+    nd, B, dims, cin, cout, k, s, up = cfg
+    torch.manual_seed(3)
+    x = torch.randn(B, *dims, cin)
+    w = torch.randn(*([k] * nd), cin, cout) / np.sqrt(cin * k ** nd)
+    b = torch.randn(cout)
+    xu = O.upsample_nearest2(x.double()) if up == 2 else x.double()
+    yr = O.conv_same(xu, w.double(), b.double(), s)
+    if act == "lrelu":
+        yr = O.lrelu(yr, 0.3)
+    with torch.no_grad():
+        y = ops.conv_act(x.to(dev), w.to(dev), b.to(dev), stride=s, upsample=up, act=L.ACT_LRELU if act == "lrelu" else L.ACT_NONE, alpha=0.3)
+    assert L.load().cn_last_conv_impl() == 2
+    assert nerr(y, yr) <= TOL_TC, nerr(y, yr)
 
 
 def test_conv_double_backward(dev):
