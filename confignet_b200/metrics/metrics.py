@@ -14,130 +14,134 @@ from .blendshape_names import blendshape_names
 
 
 class ControllabilityMetrics:
+    """Does setting a face-model parameter move the CelebA attribute it should, and nothing else?  For every attribute
+    configuration two image sets are rendered from the same latents - the driven parameter's latent slice replaced by the
+    synthetic encoder's embedding of the "set" value and of the "other" value - and the attribute classifier scores both."""
+
     def __init__(self, confinet_model, attribute_classifier, per_image_tuning_iters=0):
         self.confinet_model = confinet_model
-        if isinstance(attribute_classifier, CelebaAttributeClassifier) or hasattr(attribute_classifier, "predict_attributes"):
-            self.attribute_classifier = attribute_classifier
-        else:       # a path: metrics.py:22-24
-            self.attribute_classifier = CelebaAttributeClassifier.load(attribute_classifier)
+        is_classifier = isinstance(attribute_classifier, CelebaAttributeClassifier) or hasattr(attribute_classifier, "predict_attributes")
+        # anything else is the path of a saved classifier (metrics.py:22-24)
+        self.attribute_classifier = attribute_classifier if is_classifier else CelebaAttributeClassifier.load(attribute_classifier)
         self.per_image_tuning_iters = per_image_tuning_iters
         if confinet_model is not None:
-            self.facemodel_param_names = list(self.confinet_model.config["facemodel_inputs"].keys())
+            self.facemodel_param_names = list(confinet_model.config["facemodel_inputs"].keys())
+
+    # ---- face-model side
+    def _latent_slice(self, param_name):
+        """columns of the latent vector that belong to one face-model input (the inputs are laid out in config order)"""
+        dims = [v[1] for v in self.confinet_model.config["facemodel_inputs"].values()]
+        at = self.facemodel_param_names.index(param_name)
+        start = int(np.sum(dims[:at]))
+        return start, start + dims[at]
 
     def get_facemodel_params_for_config(self, attribute_config, other_param):
-        """metrics.py:30-50: one sampled face-model parameter set with the configured parameter overwritten"""
-        facemodel_params = self.confinet_model.sample_facemodel_params(1)
-        param_value = attribute_config.facemodel_param_value_other if other_param else attribute_config.facemodel_param_value
-        param_idx = self.facemodel_param_names.index(attribute_config.facemodel_param_name)
-        if isinstance(param_value, dict):
-            if attribute_config.facemodel_param_name != "blendshape_values":
-                raise NotImplementedError
-            facemodel_params[param_idx][:] = 0
-            for key, value in param_value.items():
-                facemodel_params[param_idx][:, blendshape_names.index(key)] = value
-        else:
-            facemodel_params[param_idx][:] = param_value
-        return facemodel_params
+        """metrics.py:30-50: ONE sampled parameter set (a draw from the fitted distributions) whose driven input is
+        overwritten - a vector as it is, a {blendshape name: value} dict on an otherwise zero blendshape vector"""
+        params = self.confinet_model.sample_facemodel_params(1)
+        value = attribute_config.facemodel_param_value_other if other_param else attribute_config.facemodel_param_value
+        target = params[self.facemodel_param_names.index(attribute_config.facemodel_param_name)]
+        if not isinstance(value, dict):
+            target[:] = value
+            return params
+        if attribute_config.facemodel_param_name != "blendshape_values":
+            raise NotImplementedError
+        target[:] = 0
+        for shape_name, amount in value.items():
+            target[:, blendshape_names.index(shape_name)] = amount
+        return params
 
     def get_images_for_controllable_attribute(self, attribute_config, latent_vectors, rotations, other_param=False):
-        """metrics.py:52-67: the latent slice of the driven parameter is replaced in every latent vector"""
-        facemodel_params = self.get_facemodel_params_for_config(attribute_config, other_param)
-        latent_vector_with_attribute_set = np.asarray(self.confinet_model.synthetic_encoder.predict(facemodel_params))
-        modified_param_idx = self.facemodel_param_names.index(attribute_config.facemodel_param_name)
-        facemodel_param_dims = list(self.confinet_model.config["facemodel_inputs"].values())
-        start_idx = int(np.sum([x[1] for x in facemodel_param_dims[:modified_param_idx]]))
-        end_idx = start_idx + facemodel_param_dims[modified_param_idx][1]
-        modified_latent_vectors = np.copy(latent_vectors)
-        modified_latent_vectors[:, start_idx:end_idx] = latent_vector_with_attribute_set[0, start_idx:end_idx]
-        return self.confinet_model.generate_images(modified_latent_vectors, rotations)
+        """metrics.py:52-67: every latent vector gets the driven input's slice of the encoded parameter set"""
+        encoded = np.asarray(self.confinet_model.synthetic_encoder.predict(
+            self.get_facemodel_params_for_config(attribute_config, other_param)))
+        lo, hi = self._latent_slice(attribute_config.facemodel_param_name)
+        edited = np.copy(latent_vectors)
+        edited[:, lo:hi] = encoded[0, lo:hi]
+        return self.confinet_model.generate_images(edited, rotations)
+
+    def _render_all(self, latent_vectors, rotations):
+        """-> (reconstruction, {config: images with the attribute}, {config: images with the other value}); the call order
+        (reconstruction, then per configuration set / other) is the reference's - the face-model draws follow it"""
+        model = self.confinet_model
+        decoded = model.generate_images(latent_vectors, rotations)
+        with_attr, without_attr = {}, {}
+        for name, cfg in ControllabilityMetricConfigs.all_configs():
+            with_attr[name] = self.get_images_for_controllable_attribute(cfg, latent_vectors, rotations)
+            without_attr[name] = self.get_images_for_controllable_attribute(cfg, latent_vectors, rotations, other_param=True)
+        return decoded, with_attr, without_attr
 
     def generate_images_for_metric(self, input_images):
-        """metrics.py:69-102"""
-        configs = ControllabilityMetricConfigs.all_configs()
-        if self.per_image_tuning_iters > 0:
-            raw_decoded_images = []
-            images_with_attributes = {name: [] for name, _ in configs}
-            images_without_attributes = {name: [] for name, _ in configs}
-            for img in input_images:
-                img = img[np.newaxis]
-                latent_vectors, rotations = self.confinet_model.fine_tune_on_img(img, n_iters=self.per_image_tuning_iters)
-                raw_decoded_images.append(self.confinet_model.generate_images(latent_vectors, rotations)[0])
-                for name, cfg in configs:
-                    images_with_attributes[name].append(self.get_images_for_controllable_attribute(cfg, latent_vectors, rotations)[0])
-                    images_without_attributes[name].append(
-                        self.get_images_for_controllable_attribute(cfg, latent_vectors, rotations, other_param=True)[0])
-            raw_decoded_images = np.array(raw_decoded_images)
-            images_with_attributes = {k: np.array(v) for k, v in images_with_attributes.items()}
-            images_without_attributes = {k: np.array(v) for k, v in images_without_attributes.items()}
-        else:
+        """metrics.py:69-102: latents from the encoder for the whole set at once, or (per_image_tuning_iters > 0) from
+        fine_tune_on_img image by image, each image rendered with the generator fine-tuned on it"""
+        if self.per_image_tuning_iters <= 0:
             latent_vectors, rotations = self.confinet_model.encode_images(input_images)
-            raw_decoded_images = self.confinet_model.generate_images(latent_vectors, rotations)
-            images_with_attributes, images_without_attributes = {}, {}
-            for name, cfg in configs:
-                images_with_attributes[name] = self.get_images_for_controllable_attribute(cfg, latent_vectors, rotations)
-                images_without_attributes[name] = self.get_images_for_controllable_attribute(cfg, latent_vectors, rotations,
-                                                                                             other_param=True)
-        return raw_decoded_images, images_with_attributes, images_without_attributes
+            return self._render_all(latent_vectors, rotations)
+        names = [name for name, _ in ControllabilityMetricConfigs.all_configs()]
+        decoded, with_attr, without_attr = [], {n: [] for n in names}, {n: [] for n in names}
+        for img in input_images:
+            latent_vectors, rotations = self.confinet_model.fine_tune_on_img(img[np.newaxis], n_iters=self.per_image_tuning_iters)
+            one, one_with, one_without = self._render_all(latent_vectors, rotations)
+            decoded.append(one[0])
+            for n in names:
+                with_attr[n].append(one_with[n][0])
+                without_attr[n].append(one_without[n][0])
+        return (np.array(decoded), {n: np.array(v) for n, v in with_attr.items()}, {n: np.array(v) for n, v in without_attr.items()})
 
+    # ---- classifier side
     def get_metrics_for_attribute_pairs(self, set_attributes, not_set_attributes, attribute_config):
         """metrics.py:104-130 -> (mean of the driven attribute when set, when set to the other value, mean absolute
         difference of the attributes that should stay constant, correlation of the driven attribute with the setting)"""
-        attribute_names = self.attribute_classifier.config["predicted_attributes"]
-        driven = attribute_names.index(attribute_config.driven_attribute)
-        changing = list(attribute_config.ignored_attributes) + [attribute_config.driven_attribute]
-        constant = [i for i, name in enumerate(attribute_names) if name not in changing]
-        mean_set = np.mean(set_attributes[:, driven])
-        mean_other = np.mean(not_set_attributes[:, driven])
-        n_samples = len(set_attributes)
-        assert n_samples == len(not_set_attributes)
-        setting = np.hstack((np.ones(n_samples), np.zeros(n_samples)))
-        predicted = np.hstack((set_attributes[:, driven], not_set_attributes[:, driven]))
-        corr_coef = np.corrcoef(np.vstack((setting, predicted)))
-        mad = np.mean(np.mean(np.abs(set_attributes[:, constant] - not_set_attributes[:, constant]), axis=0))
-        return float(mean_set), float(mean_other), float(mad), float(corr_coef[0, 1])
+        names = self.attribute_classifier.config["predicted_attributes"]
+        driven = names.index(attribute_config.driven_attribute)
+        may_move = set(attribute_config.ignored_attributes) | {attribute_config.driven_attribute}
+        fixed = [i for i, n in enumerate(names) if n not in may_move]
+        count = len(set_attributes)
+        assert count == len(not_set_attributes)
+        on, off = set_attributes[:, driven], not_set_attributes[:, driven]
+        correlation = np.corrcoef(np.vstack((np.hstack((np.ones(count), np.zeros(count))), np.hstack((on, off)))))[0, 1]
+        drift = np.mean(np.mean(np.abs(set_attributes[:, fixed] - not_set_attributes[:, fixed]), axis=0))
+        return float(np.mean(on)), float(np.mean(off)), float(drift), float(correlation)
 
     def get_metrics_for_attribute_config(self, attribute_config, images_with_attribute, images_without_attribute):
-        set_attributes = self.attribute_classifier.predict_attributes(images_with_attribute)
-        not_set_attributes = self.attribute_classifier.predict_attributes(images_without_attribute)
-        return self.get_metrics_for_attribute_pairs(set_attributes, not_set_attributes, attribute_config)
+        predict = self.attribute_classifier.predict_attributes
+        return self.get_metrics_for_attribute_pairs(predict(images_with_attribute), predict(images_without_attribute), attribute_config)
+
+    def get_metrics_from_attribute_images(self, images_with_attributes, images_without_attributes):
+        """metrics.py:158-169: the four numbers per configuration, their means, and the scalar the training logs plot"""
+        metrics = {name: self.get_metrics_for_attribute_config(cfg, images_with_attributes[name], images_without_attributes[name])
+                   for name, cfg in ControllabilityMetricConfigs.all_configs()}
+        means = tuple(np.mean(list(metrics.values()), axis=0))
+        metrics["contr_attribute_means"] = means
+        metrics["controllability"] = 10 * means[2] + (1 - means[0])          # weights "based on perceived importance"
+        return metrics
 
     def get_metrics(self, input_images, img_output_dir=None):
         """metrics.py:139-156; with ``img_output_dir`` every input, its reconstruction and the two images of every attribute
         configuration are written as PNG files under the reference's names (OpenCV, imported on demand)"""
-        raw_decoded_images, images_with_attributes, images_without_attributes = self.generate_images_for_metric(input_images)
+        decoded, with_attr, without_attr = self.generate_images_for_metric(input_images)
         if img_output_dir is not None:
             import cv2
             os.makedirs(img_output_dir, exist_ok=True)
+            put = lambda stem, i, img: cv2.imwrite(os.path.join(img_output_dir, "%s_%04d.png" % (stem, i)), np.asarray(img))
             for i in range(len(input_images)):
-                cv2.imwrite(os.path.join(img_output_dir, "gt_img_%04d.png" % i), np.asarray(input_images[i]))
-                cv2.imwrite(os.path.join(img_output_dir, "raw_img_%04d.png" % i), raw_decoded_images[i])
-                for config_name, _ in ControllabilityMetricConfigs.all_configs():
-                    cv2.imwrite(os.path.join(img_output_dir, "%s_img_%04d.png" % (config_name, i)), images_with_attributes[config_name][i])
-                    cv2.imwrite(os.path.join(img_output_dir, "%s_img_not_set_%04d.png" % (config_name, i)),
-                                images_without_attributes[config_name][i])
-        return self.get_metrics_from_attribute_images(images_with_attributes, images_without_attributes)
-
-    def get_metrics_from_attribute_images(self, images_with_attributes, images_without_attributes):
-        """metrics.py:158-169"""
-        metrics = {}
-        for name, cfg in ControllabilityMetricConfigs.all_configs():
-            metrics[name] = self.get_metrics_for_attribute_config(cfg, images_with_attributes[name], images_without_attributes[name])
-        metrics["contr_attribute_means"] = tuple(np.mean(list(metrics.values()), axis=0))
-        metrics["controllability"] = 10 * metrics["contr_attribute_means"][2] + (1 - metrics["contr_attribute_means"][0])
-        return metrics
+                put("gt_img", i, input_images[i])
+                put("raw_img", i, decoded[i])
+                for name in with_attr:
+                    put(name + "_img", i, with_attr[name][i])
+                    put(name + "_img_not_set", i, without_attr[name][i])
+        return self.get_metrics_from_attribute_images(with_attr, without_attr)
 
     def update_and_log_metrics(self, images, metrics_dict, output_dir, aml_run=None, tb_log_writer=None):
         """metrics.py:171-199: appends to metrics_dict and rewrites controllability_metrics.json"""
         os.makedirs(output_dir, exist_ok=True)
-        new_metrics = self.get_metrics(images)
-        for key, value in new_metrics.items():
+        fresh = self.get_metrics(images)
+        for key, value in fresh.items():
             metrics_dict.setdefault(key, []).append(value)
-        if aml_run is not None:
-            for key, value in new_metrics.items():
+            if aml_run is not None:
                 aml_run.log(key, value)
-        contr_only = dict((key, metrics_dict[key]) for key in new_metrics.keys())
         with open(os.path.join(output_dir, "controllability_metrics.json"), "w") as fp:
-            json.dump(contr_only, fp, indent=4)
+            json.dump({key: metrics_dict[key] for key in fresh}, fp, indent=4)
 
 
 class InceptionMetrics:
