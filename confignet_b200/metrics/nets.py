@@ -250,24 +250,47 @@ def act_ext_(x, act):
     return x
 
 
+def attribute_classifier_graph(r, p, x):
+    """MobileNetV2 + head written against a small layer interface (conv / dwconv / add / gap / dense_sigmoid), so that the
+    device forward and a torch-CPU check of the wiring + folding (tests/test_metrics_cpu.py) walk the same code"""
+    block_in = x
+    for kind, cname, bname, cin, cout, stride, act, add in mobilenet_v2_layers():
+        if cname.endswith("_expand") or cname == "expanded_conv_depthwise":
+            block_in = x                                       # first layer of an inverted residual block
+        if kind == "dw":
+            x = r.dwconv(x, p[cname + "/kernel"], p[cname + "/bias"], stride)            # + ReLU6
+        else:
+            x = r.conv(x, p[cname + "/kernel"], p[cname + "/bias"], stride, relu6=act == "relu6")
+            if add:
+                x = r.add(x, block_in)
+    return r.dense_sigmoid(r.gap(x), p["dense/kernel"], p["dense/bias"])
+
+
+class _ClassifierDeviceLayers:
+    """the B200 kernels behind attribute_classifier_graph"""
+
+    @staticmethod
+    def conv(x, k, b, stride, relu6):
+        # ReLU6 = the conv's fused ReLU + an in-place clamp: the conv epilogues carry four activation codes only
+        y = ops.conv_act(x, k, b, stride=stride, act=L.ACT_RELU if relu6 else L.ACT_NONE)
+        return act_ext_(y, L.ACT_RELU6) if relu6 else y
+
+    @staticmethod
+    def dwconv(x, k, b, stride):
+        return dwconv3x3(x, k, b, stride, L.ACT_RELU6)
+
+    add = staticmethod(residual_add)
+    gap = staticmethod(ops.global_avg_pool)
+
+    @staticmethod
+    def dense_sigmoid(feat, k, b):
+        return act_ext_(ops.conv_act(feat, k, b), L.ACT_SIGMOID)
+
+
 def attribute_classifier_forward(p, x):
     """x: (B,H,W,3) float32 in [-1,1] -> (B, n_attributes) sigmoid probabilities (Dropout is the identity at inference)"""
-    acts = {"relu6": L.ACT_RELU, None: L.ACT_NONE}
     with torch.no_grad():
-        block_in = x
-        for kind, cname, bname, cin, cout, stride, act, add in mobilenet_v2_layers():
-            if cname.endswith("_expand") or cname == "expanded_conv_depthwise":
-                block_in = x                                   # first layer of an inverted residual block
-            if kind == "dw":
-                x = dwconv3x3(x, p[cname + "/kernel"], p[cname + "/bias"], stride, L.ACT_RELU6)
-            else:
-                x = ops.conv_act(x, p[cname + "/kernel"], p[cname + "/bias"], stride=stride, act=acts[act])
-                if act == "relu6":
-                    x = act_ext_(x, L.ACT_RELU6)
-                if add:
-                    x = residual_add(x, block_in)
-        feat = ops.global_avg_pool(x)
-        return act_ext_(ops.conv_act(feat, p["dense/kernel"], p["dense/bias"]), L.ACT_SIGMOID)
+        return attribute_classifier_graph(_ClassifierDeviceLayers, p, x)
 
 
 # ------------------------------------------------------------------------------------------------ image plumbing

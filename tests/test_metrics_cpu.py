@@ -283,3 +283,36 @@ def test_oracle_mobilenet_v2_equals_torchvision_on_odd_sizes():
     got = MO.mobilenet_v2_features(O.to_torch(raw, dtype=torch.float64), x)
     assert tuple(got.shape) == tuple(want.shape) == (2, 4, 4, 1280) and float(want.std()) > 1e-3
     assert float((want - got).abs().max() / want.abs().max()) < 1e-9
+
+
+class _ClassifierCpuLayers:
+    """torch-CPU layers behind the product's attribute_classifier_graph, on the FOLDED parameters"""
+
+    @staticmethod
+    def conv(x, k, b, stride, relu6):
+        y = O.conv_same(x, k, b, stride)
+        return MO.relu6(y) if relu6 else y
+
+    @staticmethod
+    def dwconv(x, k, b, stride):
+        xt = x
+        if stride == 2:
+            xt = MO._pad_hw(x, MO._correct_pad(x.shape[1]), MO._correct_pad(x.shape[2]))
+        return MO.relu6(MO.depthwise3x3(xt, k.unsqueeze(-1), stride) + b)
+
+    add = staticmethod(lambda a, b: a + b)
+    gap = staticmethod(lambda x: x.mean(dim=(1, 2)))
+    dense_sigmoid = staticmethod(lambda f, k, b: torch.sigmoid(f @ k + b))
+
+
+@pytest.mark.parametrize("size", [96, 97])
+def test_classifier_graph_and_folding_equal_the_oracle_restatement(size):
+    """the product's MobileNetV2 + head wiring with BatchNorm folded into kernels / biases / the Dense layer, against the
+    oracle's unfolded restatement (even size: TF-SAME (0,1) padding of the stride-2 layers; odd size: (1,1))"""
+    raw = nets.init_stand_in(nets.attribute_classifier_spec(7), 21)
+    x = torch.tensor(np.random.RandomState(3).uniform(-1, 1, (2, size, size, 3)))
+    want = MO.attribute_classifier_forward(O.to_torch(raw, dtype=torch.float64), x)
+    folded = O.to_torch(nets.fold_attribute_classifier_params(raw, 7), dtype=torch.float64)
+    got = nets.attribute_classifier_graph(_ClassifierCpuLayers, folded, x)
+    assert tuple(got.shape) == (2, 7) and float(want.std()) > 1e-4
+    assert float((want - got).abs().max()) < 1e-6
