@@ -110,8 +110,8 @@ __device__ __forceinline__ float cn_apply_act(float v, int act, float alpha) {
   return v;
 }
 // The hot kernels take the four codes above only: the tcgen05 conv kernel is ~119 KB of SASS and its epilogue unrolls the
-// activation 64 times - one more inlined branch there (ReLU6) cost 5 ms of the 39 ms training step on B200 (instruction
-// cache; profiles/r02_m3_activation_code_size_ab.txt).  The metric networks' extra codes exist in the cold kernels only.
+// activation 64 times - one more inlined branch there (ReLU6) cost 5 ms of the 39 ms training step on B200 (measured
+// A/B, profiles/r02_m3_activation_code_size_ab.txt).  The metric networks' extra codes exist in the cold kernels only.
 __device__ __forceinline__ float cn_apply_act_ext(float v, int act, float alpha) {
   if (act == CN_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
   if (act == CN_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
